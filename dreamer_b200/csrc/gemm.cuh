@@ -1,0 +1,185 @@
+// The fused GEMM main loop shared by every tensor-core stage of the RSSM path.
+//
+//   out_tile[128 x N] = A[128 x K] (bf16, K-major, TMA-staged) * B[N x K]^T (bf16, K-major, TMA-staged)
+//
+// accumulated in TMEM by tcgen05.mma (one elected thread), then handed to a per-stage epilogue
+// functor that reads the accumulator with tcgen05.ld -- one thread per output row, so row-wise
+// reductions (LayerNorm, softmax, the 32-class CDF) need no shuffles.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// Pipeline: STAGES-deep smem ring (full/empty mbarriers), one tmem_full barrier.
+#pragma once
+
+#include "common.cuh"
+
+namespace drm {
+
+constexpr int BM = 128;           // rows per CTA tile == UMMA M == TMEM lanes
+constexpr int BK = 64;            // bf16 per k-block == one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmCommon {
+  CUtensorMap tmA;   // activations, box {64, 128}
+  CUtensorMap tmB;   // packed weights, box {64, bn}
+  int M;             // valid rows (epilogues guard their global stores with m < M)
+  int bn;            // B rows per tile == UMMA N of the (first) accumulator group
+  int a_row0;        // A row of tile (x = 0, slot = 0)
+  int a_y_stride;    // extra A rows per slot
+  int ka0, nka0;     // A k-block ranges [ka0, ka0 + nka0) then [ka1, ka1 + nka1); B k-blocks are
+  int ka1, nka1;     //   consumed sequentially from 0
+  int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
+  int y_slot[8];
+};
+
+template <int B_ROWS_MAX, int STAGES>
+struct GemmSmem {
+  static constexpr int B_STAGE_BYTES = B_ROWS_MAX * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+};
+
+// Epi must provide:
+//   static constexpr int B_ROWS_MAX, STAGES, TMEM_COLS;  static constexpr int GRU_U (0 = plain)
+//   struct Params;
+//   static __device__ void run(const Params&, const GemmCommon&, uint32_t taddr, int m, int slot);
+template <class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename Epi::Params ep) {
+  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
+  constexpr int STAGES = Epi::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nk = g.nka0 + g.nka1;
+  const int slot = g.n_slots > 0 ? g.y_slot[blockIdx.y] : (int)blockIdx.y;
+  const int a_row = g.a_row0 + slot * g.a_y_stride + (int)blockIdx.x * BM;
+  const int b_row = slot * g.bn;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.tmA);
+    tma_prefetch_desc(&g.tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Epi::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = A_STAGE_BYTES + (uint32_t)g.bn * BK * 2;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* sa = smem + s * SL::STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
+        mbar_expect_tx(&full[s], tx);
+        tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
+        tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+        if constexpr (Epi::GRU_U == 0) {
+          const uint32_t idesc = umma_idesc_bf16(g.bn);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        } else {
+          // GRU tile: B rows = [r(U) | z(U) | n(U)], TMEM cols = [r | z | n_x | n_h].
+          // x-part k-blocks feed r, z, n_x in one N = 3U MMA; h-part k-blocks feed r, z (N = 2U)
+          // and n_h (N = U, B rows 2U.., TMEM cols 3U..) because r multiplies only W_hn h.
+          constexpr int U = Epi::GRU_U;
+          if (kb < g.nka0) {
+            const uint32_t idesc = umma_idesc_bf16(3 * U);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          } else {
+            const uint32_t idesc_rz = umma_idesc_bf16(2 * U);
+            const uint32_t idesc_n = umma_idesc_bf16(U);
+            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
+              umma_bf16(tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > g.nka0 || k > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int m = (int)blockIdx.x * BM + row;
+    Epi::run(ep, g, tmem + ((uint32_t)(q * 32) << 16), m, slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Epi::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// row-store helpers: each epilogue thread owns one output row
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void store_f32_row(float* dst, const float (&v)[N], int nvalid) {
+  if (nvalid >= N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+    for (int j = 0; j < N; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < nvalid) dst[j] = v[j];
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float (&v)[N], int nvalid) {
+  if (nvalid >= N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+    for (int j = 0; j < N; j += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(v[j], v[j + 1]);
+      u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+      u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+      u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+      *reinterpret_cast<uint4*>(dst + j) = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+}  // namespace drm

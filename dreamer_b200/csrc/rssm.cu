@@ -1,0 +1,619 @@
+// RSSM on tcgen05: packed bf16 weights, the per-stage fused GEMM launches and the imagination
+// rollout driver (Dreamer.dream_episodes, Dreamer.py:143-175).
+//
+// HBM layout
+//   state buffer S[2]  bf16 [Mp, KS]  columns  [ z : R*C | a : 64 (A used) | h : DP ]   (Mp = B up to 128)
+//       -> one TMA descriptor serves every stage: the GRU reads k-blocks z|a (x part) then h,
+//          the prior reads h, the [h, z] heads read z then h.  Ping-pong between steps.
+//   Y1, Y2             bf16 [6 * Mp, 256]    hidden activations; slot 0 = prior, 1.. = heads
+//   packed weights     bf16, K-major, columns permuted to the state layout, rows grouped per tile
+//       Wgru [tiles * 3U, 1088 + DP]  rows of tile j = [r | z | n] of hidden units j*U .. j*U+U-1
+//       Wp1 [bn, DP]  Wp2 [bn, 256]  Wp3 [R*C, 256]
+//       Wh1 [5 * bn, R*C + DP]  Wh2 [5 * bn, 256]  Wh3 [5 * 256, 256]
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "epilogues.cuh"
+#include "internal.h"
+
+namespace drm {
+
+// ------------------------------------------------------------------------------------------
+// small support kernels
+// ------------------------------------------------------------------------------------------
+__global__ void pack_matrix_kernel(__nv_bfloat16* __restrict__ dst, int ld_dst, int dst_row0, int nrows, int dst_col0,
+                                   int ncols, const float* __restrict__ src, int ld_src, const int* __restrict__ row_map,
+                                   const int* __restrict__ col_map) {
+  const long total = (long)nrows * ncols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ncols), c = (int)(i % ncols);
+    const int sr = row_map[r], sc = col_map[c];
+    const float v = (sr >= 0 && sc >= 0) ? src[(long)sr * ld_src + sc] : 0.f;
+    dst[(long)(dst_row0 + r) * ld_dst + dst_col0 + c] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void pack_vector_kernel(float* __restrict__ dst, int n, const float* __restrict__ src, const int* __restrict__ map,
+                                   float fill) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = map[i] >= 0 ? src[map[i]] : fill;
+}
+
+// fp32 rows -> bf16 columns of a state buffer (and optional fp32 copies into strided outputs).
+__global__ void pack_state_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int col0, const float* __restrict__ src,
+                                  long ld_src, int ncols, int N, float* __restrict__ copy, long ld_copy) {
+  const long total = (long)N * ncols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ncols), c = (int)(i % ncols);
+    const float v = src[(long)r * ld_src + c];
+    S[(long)r * ld_s + col0 + c] = __float2bfloat16_rn(v);
+    if (copy) copy[(long)r * ld_copy + c] = v;
+  }
+}
+__global__ void zero_cols_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int col0, int ncols, int N) {
+  const long total = (long)N * ncols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+    S[(long)(i / ncols) * ld_s + col0 + (int)(i % ncols)] = __float2bfloat16_rn(0.f);
+}
+__global__ void f32_to_bf16_pad_kernel(__nv_bfloat16* __restrict__ dst, int ld_dst, const float* __restrict__ src, int rows,
+                                       int cols) {
+  const long total = (long)rows * ld_dst;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+    dst[i] = __float2bfloat16_rn(c < cols ? src[(long)r * cols + c] : 0.f);
+  }
+}
+
+static int grid_for(long total, int threads = 256) {
+  long b = (total + threads - 1) / threads;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b < 1 ? 1 : b);
+}
+
+template <class Epi>
+static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3 grid, cudaStream_t st) {
+  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(fused_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
+    attr_set = true;
+  }
+  fused_gemm_kernel<Epi><<<grid, GEMM_THREADS, SL::TOTAL, st>>>(g, ep);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// packed model
+// ------------------------------------------------------------------------------------------
+enum Src {
+  S_GRU_WIH, S_GRU_WHH, S_GRU_BIH, S_GRU_BHH,
+  S_MLP0,  // + 10 * mlp + {w0,b0,g0,be0,w1,b1,g1,be1,w2,b2};  mlp: 0 prior 1 reward 2 cont 3 actor 4 critic 5 target
+  S_MU_W = S_MLP0 + 60, S_MU_B, S_LS_W, S_LS_B, S_BK_REW, S_BK_CRIT, S_COUNT
+};
+enum { HS_REWARD = 0, HS_CONT = 1, HS_ACTOR = 2, HS_CRITIC = 3, HS_TARGET = 4 };
+
+struct MatOp { __nv_bfloat16* dst; int ld_dst, row0, nrows, col0, ncols, src, ld_src; int *row_map, *col_map; };
+struct VecOp { float* dst; int n, src; int* map; float fill; };
+
+}  // namespace drm
+
+using namespace drm;
+
+struct drm_rssm {
+  drm_dims d;
+  int ZP, DP, KS, KG, KH;        // state layout: z cols, padded h cols, state pitch, GRU K, head-L1 K
+  int U, gru_tiles;              // GRU units per tile
+  int bnp1, bnp2, bnh1, bnh2;    // padded hidden widths (multiples of 16)
+  __nv_bfloat16 *Wgru, *Wp1, *Wp2, *Wp3, *Wh1, *Wh2, *Wh3;
+  float *b_ih, *b_hh;            // [3D]
+  float *p1_b, *p1_g, *p1_be, *p2_b, *p2_g, *p2_be, *p3_b;
+  float *h1_b, *h1_g, *h1_be, *h2_b, *h2_g, *h2_be, *h3_b;  // [5 * bn]
+  float *bk_rew, *bk_crit;       // [NB]
+  CUtensorMap tmWgru, tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
+  std::vector<MatOp> mat_ops;
+  std::vector<VecOp> vec_ops;
+  std::vector<void*> allocs;
+  bool packed, has_critic;
+};
+
+struct drm_rollout {
+  drm_rssm* m;
+  int B, H, Mp;
+  __nv_bfloat16* S[2];
+  __nv_bfloat16 *Y1, *Y2;
+  CUtensorMap tmS[2], tmY1, tmY2;
+  std::vector<void*> allocs;
+};
+
+namespace drm {
+
+template <class T>
+static int dev_alloc(std::vector<void*>& bag, T** out, size_t count) {
+  void* p = nullptr;
+  DRM_CUDA(cudaMalloc(&p, count * sizeof(T) + 16));
+  DRM_CUDA(cudaMemset(p, 0, count * sizeof(T) + 16));
+  bag.push_back(p);
+  *out = static_cast<T*>(p);
+  return DRM_OK;
+}
+static int upload_map(std::vector<void*>& bag, const std::vector<int>& h, int** out) {
+  int* d = nullptr;
+  if (int rc = dev_alloc(bag, &d, h.size() ? h.size() : 1)) return rc;
+  if (!h.empty()) DRM_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+  *out = d;
+  return DRM_OK;
+}
+static std::vector<int> iota_lim(int n, int limit, int offset = 0) {  // i -> offset + i if i < limit else -1
+  std::vector<int> v(n);
+  for (int i = 0; i < n; ++i) v[i] = i < limit ? offset + i : -1;
+  return v;
+}
+
+static int add_mat(drm_rssm* m, __nv_bfloat16* dst, int ld_dst, int row0, int col0, int src, int ld_src,
+                   const std::vector<int>& rows, const std::vector<int>& cols) {
+  MatOp op{dst, ld_dst, row0, (int)rows.size(), col0, (int)cols.size(), src, ld_src, nullptr, nullptr};
+  if (int rc = upload_map(m->allocs, rows, &op.row_map)) return rc;
+  if (int rc = upload_map(m->allocs, cols, &op.col_map)) return rc;
+  m->mat_ops.push_back(op);
+  return DRM_OK;
+}
+static int add_vec(drm_rssm* m, float* dst, int src, const std::vector<int>& map, float fill = 0.f) {
+  VecOp op{dst, (int)map.size(), src, nullptr, fill};
+  if (int rc = upload_map(m->allocs, map, &op.map)) return rc;
+  m->vec_ops.push_back(op);
+  return DRM_OK;
+}
+
+static int pick_gru_u(int D) {
+  if (const char* e = getenv("DRM_GRU_U")) {
+    const int u = atoi(e);
+    if (u == 32 || u == 64) return u;
+  }
+  return D >= 1536 ? 64 : 32;
+}
+
+}  // namespace drm
+
+#define RC(x)            \
+  do {                   \
+    if (int rc__ = (x)) return rc__; \
+  } while (0)
+
+extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
+  RC(check_arch());
+  DRM_REQUIRE(dims && out, DRM_ERR_ARG, "drm_rssm_create: NULL argument");
+  const drm_dims d = *dims;
+  DRM_REQUIRE(d.C == 32, DRM_ERR_SHAPE, "drm_rssm_create: latent classes C must be 32");
+  DRM_REQUIRE(d.R > 0 && (d.R * d.C) % 256 == 0, DRM_ERR_SHAPE, "drm_rssm_create: R * C must be a multiple of 256");
+  DRM_REQUIRE(d.D >= 16 && d.D <= 16384, DRM_ERR_SHAPE, "drm_rssm_create: D out of range");
+  DRM_REQUIRE(d.A >= 1 && d.A <= 16, DRM_ERR_SHAPE, "drm_rssm_create: A must be in [1, 16]");
+  DRM_REQUIRE(d.NB >= 2 && d.NB <= 256, DRM_ERR_SHAPE, "drm_rssm_create: NB must be in [2, 256]");
+  for (int i = 0; i < 2; ++i)
+    DRM_REQUIRE(d.h_prior[i] >= 1 && d.h_prior[i] <= 256 && d.h_head[i] >= 1 && d.h_head[i] <= 256, DRM_ERR_SHAPE,
+                "drm_rssm_create: MLP hidden sizes must be in [1, 256]");
+  drm_rssm* m = new drm_rssm();
+  m->d = d;
+  m->packed = false;
+  m->has_critic = false;
+  m->ZP = d.R * d.C;
+  m->DP = round_up(d.D, 64);
+  m->KS = m->ZP + 64 + m->DP;
+  m->KG = m->KS;              // GRU consumes [z | a | h]
+  m->KH = m->ZP + m->DP;      // head layer 1 consumes [z | h]
+  m->U = pick_gru_u(d.D);
+  m->gru_tiles = ceil_div(d.D, m->U);
+  m->bnp1 = round_up(d.h_prior[0], 16);
+  m->bnp2 = round_up(d.h_prior[1], 16);
+  m->bnh1 = round_up(d.h_head[0], 16);
+  m->bnh2 = round_up(d.h_head[1], 16);
+  const int U = m->U, D = d.D, ZP = m->ZP, DP = m->DP, A = d.A, NB = d.NB;
+  auto& bag = m->allocs;
+  int rc = DRM_OK;
+#define TRY(x) if (rc == DRM_OK) rc = (x)
+  TRY(dev_alloc(bag, &m->Wgru, (size_t)m->gru_tiles * 3 * U * m->KG));
+  TRY(dev_alloc(bag, &m->Wp1, (size_t)m->bnp1 * DP));
+  TRY(dev_alloc(bag, &m->Wp2, (size_t)m->bnp2 * 256));
+  TRY(dev_alloc(bag, &m->Wp3, (size_t)ZP * 256));
+  TRY(dev_alloc(bag, &m->Wh1, (size_t)MAX_HEADS * m->bnh1 * m->KH));
+  TRY(dev_alloc(bag, &m->Wh2, (size_t)MAX_HEADS * m->bnh2 * 256));
+  TRY(dev_alloc(bag, &m->Wh3, (size_t)MAX_HEADS * 256 * 256));
+  TRY(dev_alloc(bag, &m->b_ih, (size_t)3 * D));
+  TRY(dev_alloc(bag, &m->b_hh, (size_t)3 * D));
+  TRY(dev_alloc(bag, &m->p1_b, (size_t)m->bnp1)); TRY(dev_alloc(bag, &m->p1_g, (size_t)m->bnp1)); TRY(dev_alloc(bag, &m->p1_be, (size_t)m->bnp1));
+  TRY(dev_alloc(bag, &m->p2_b, (size_t)m->bnp2)); TRY(dev_alloc(bag, &m->p2_g, (size_t)m->bnp2)); TRY(dev_alloc(bag, &m->p2_be, (size_t)m->bnp2));
+  TRY(dev_alloc(bag, &m->p3_b, (size_t)ZP));
+  TRY(dev_alloc(bag, &m->h1_b, (size_t)MAX_HEADS * m->bnh1)); TRY(dev_alloc(bag, &m->h1_g, (size_t)MAX_HEADS * m->bnh1)); TRY(dev_alloc(bag, &m->h1_be, (size_t)MAX_HEADS * m->bnh1));
+  TRY(dev_alloc(bag, &m->h2_b, (size_t)MAX_HEADS * m->bnh2)); TRY(dev_alloc(bag, &m->h2_g, (size_t)MAX_HEADS * m->bnh2)); TRY(dev_alloc(bag, &m->h2_be, (size_t)MAX_HEADS * m->bnh2));
+  TRY(dev_alloc(bag, &m->h3_b, (size_t)MAX_HEADS * 256));
+  TRY(dev_alloc(bag, &m->bk_rew, (size_t)NB));
+  TRY(dev_alloc(bag, &m->bk_crit, (size_t)NB));
+
+  // ---- GRU: rows grouped per tile [r | z | n], columns [z | a(pad 64) | h(pad DP)]
+  {
+    std::vector<int> rows((size_t)m->gru_tiles * 3 * U);
+    for (int j = 0; j < m->gru_tiles; ++j)
+      for (int gte = 0; gte < 3; ++gte)
+        for (int u = 0; u < U; ++u) {
+          const int unit = j * U + u;
+          rows[(size_t)j * 3 * U + gte * U + u] = unit < D ? gte * D + unit : -1;
+        }
+    std::vector<int> xcols(ZP + 64);
+    for (int c = 0; c < ZP + 64; ++c) xcols[c] = c < ZP + A ? c : -1;   // reference x = [z, a]  (SequenceModel.py:21)
+    TRY(add_mat(m, m->Wgru, m->KG, 0, 0, S_GRU_WIH, ZP + A, rows, xcols));
+    TRY(add_mat(m, m->Wgru, m->KG, 0, ZP + 64, S_GRU_WHH, D, rows, iota_lim(DP, D)));
+    TRY(add_vec(m, m->b_ih, S_GRU_BIH, iota_lim(3 * D, 3 * D)));
+    TRY(add_vec(m, m->b_hh, S_GRU_BHH, iota_lim(3 * D, 3 * D)));
+  }
+  // ---- prior MLP (input h)
+  {
+    const int h1 = d.h_prior[0], h2 = d.h_prior[1], s = S_MLP0 + 0;
+    TRY(add_mat(m, m->Wp1, DP, 0, 0, s + 0, D, iota_lim(m->bnp1, h1), iota_lim(DP, D)));
+    TRY(add_vec(m, m->p1_b, s + 1, iota_lim(m->bnp1, h1)));
+    TRY(add_vec(m, m->p1_g, s + 2, iota_lim(m->bnp1, h1)));
+    TRY(add_vec(m, m->p1_be, s + 3, iota_lim(m->bnp1, h1)));
+    TRY(add_mat(m, m->Wp2, 256, 0, 0, s + 4, h1, iota_lim(m->bnp2, h2), iota_lim(256, h1)));
+    TRY(add_vec(m, m->p2_b, s + 5, iota_lim(m->bnp2, h2)));
+    TRY(add_vec(m, m->p2_g, s + 6, iota_lim(m->bnp2, h2)));
+    TRY(add_vec(m, m->p2_be, s + 7, iota_lim(m->bnp2, h2)));
+    TRY(add_mat(m, m->Wp3, 256, 0, 0, s + 8, h2, iota_lim(ZP, ZP), iota_lim(256, h2)));
+    TRY(add_vec(m, m->p3_b, s + 9, iota_lim(ZP, ZP)));
+  }
+  // ---- [h, z] heads: slots reward, cont, actor, critic, target critic
+  {
+    const int h1 = d.h_head[0], h2 = d.h_head[1];
+    std::vector<int> l1cols(m->KH);   // packed columns [z | h]; reference input is [h, z] (DynamicsPredictors.py:65-66)
+    for (int c = 0; c < m->KH; ++c) l1cols[c] = c < ZP ? D + c : (c - ZP < D ? c - ZP : -1);
+    for (int hs = 0; hs < MAX_HEADS; ++hs) {
+      const int mlp = hs + 1, s = S_MLP0 + 10 * mlp;
+      TRY(add_mat(m, m->Wh1, m->KH, hs * m->bnh1, 0, s + 0, D + ZP, iota_lim(m->bnh1, h1), l1cols));
+      TRY(add_vec(m, m->h1_b + hs * m->bnh1, s + 1, iota_lim(m->bnh1, h1)));
+      TRY(add_vec(m, m->h1_g + hs * m->bnh1, s + 2, iota_lim(m->bnh1, h1)));
+      TRY(add_vec(m, m->h1_be + hs * m->bnh1, s + 3, iota_lim(m->bnh1, h1)));
+      TRY(add_mat(m, m->Wh2, 256, hs * m->bnh2, 0, s + 4, h1, iota_lim(m->bnh2, h2), iota_lim(256, h1)));
+      TRY(add_vec(m, m->h2_b + hs * m->bnh2, s + 5, iota_lim(m->bnh2, h2)));
+      TRY(add_vec(m, m->h2_g + hs * m->bnh2, s + 6, iota_lim(m->bnh2, h2)));
+      TRY(add_vec(m, m->h2_be + hs * m->bnh2, s + 7, iota_lim(m->bnh2, h2)));
+      if (hs == HS_ACTOR) {  // mu rows at 0.., log-sigma rows at 16..  (Agent.py:186-187)
+        std::vector<int> r_mu(256, -1), r_ls(256, -1);
+        for (int a = 0; a < A; ++a) { r_mu[a] = a; r_ls[16 + a] = a; }
+        // two ops writing disjoint rows of the same 256-row block: pack mu rows [0,16) and ls rows [16,32) separately
+        TRY(add_mat(m, m->Wh3, 256, hs * 256, 0, S_MU_W, h2, std::vector<int>(r_mu.begin(), r_mu.begin() + 16), iota_lim(256, h2)));
+        TRY(add_mat(m, m->Wh3, 256, hs * 256 + 16, 0, S_LS_W, h2, std::vector<int>(r_ls.begin() + 16, r_ls.begin() + 32), iota_lim(256, h2)));
+        TRY(add_vec(m, m->h3_b + hs * 256, S_MU_B, std::vector<int>(r_mu.begin(), r_mu.begin() + 16)));
+        TRY(add_vec(m, m->h3_b + hs * 256 + 16, S_LS_B, std::vector<int>(r_ls.begin() + 16, r_ls.begin() + 32)));
+      } else {
+        const int nout = hs == HS_CONT ? 1 : NB;
+        TRY(add_mat(m, m->Wh3, 256, hs * 256, 0, s + 8, h2, iota_lim(256, nout), iota_lim(256, h2)));
+        TRY(add_vec(m, m->h3_b + hs * 256, s + 9, iota_lim(256, nout)));
+      }
+    }
+    TRY(add_vec(m, m->bk_rew, S_BK_REW, iota_lim(NB, NB)));
+    TRY(add_vec(m, m->bk_crit, S_BK_CRIT, iota_lim(NB, NB)));
+  }
+  // ---- TMA descriptors of the packed weights (box = {64, rows per tile})
+  TRY(make_tmap_bf16_2d(&m->tmWgru, m->Wgru, (uint64_t)m->gru_tiles * 3 * U, m->KG, m->KG, 3 * U));
+  TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, m->bnp1, DP, DP, m->bnp1));
+  TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, m->bnp2, 256, 256, m->bnp2));
+  TRY(make_tmap_bf16_2d(&m->tmWp3, m->Wp3, ZP, 256, 256, 256));
+  TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * m->bnh1, m->KH, m->KH, m->bnh1));
+  TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * m->bnh2, 256, 256, m->bnh2));
+  TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
+#undef TRY
+  if (rc != DRM_OK) {
+    drm_rssm_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return DRM_OK;
+}
+
+extern "C" int drm_rssm_destroy(drm_rssm* m) {
+  if (!m) return DRM_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return DRM_OK;
+}
+
+extern "C" int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(m && w, DRM_ERR_ARG, "drm_rssm_pack: NULL argument");
+  const float* src[S_COUNT] = {};
+  src[S_GRU_WIH] = w->gru_w_ih; src[S_GRU_WHH] = w->gru_w_hh; src[S_GRU_BIH] = w->gru_b_ih; src[S_GRU_BHH] = w->gru_b_hh;
+  const drm_mlp_w* mlps[6] = {&w->prior, &w->reward, &w->cont, &w->actor, &w->critic, &w->target_critic};
+  for (int i = 0; i < 6; ++i) {
+    const float* f[10] = {mlps[i]->w0, mlps[i]->b0, mlps[i]->g0, mlps[i]->be0, mlps[i]->w1,
+                          mlps[i]->b1, mlps[i]->g1, mlps[i]->be1, mlps[i]->w2, mlps[i]->b2};
+    for (int k = 0; k < 10; ++k) src[S_MLP0 + 10 * i + k] = f[k];
+  }
+  src[S_MU_W] = w->actor_mu_w; src[S_MU_B] = w->actor_mu_b; src[S_LS_W] = w->actor_ls_w; src[S_LS_B] = w->actor_ls_b;
+  src[S_BK_REW] = w->buckets_rew; src[S_BK_CRIT] = w->buckets_crit;
+  DRM_REQUIRE(w->gru_w_ih && w->gru_w_hh && w->gru_b_ih && w->gru_b_hh, DRM_ERR_ARG, "drm_rssm_pack: GRU weights are NULL");
+  DRM_REQUIRE(w->prior.w0 && w->prior.w2 && w->reward.w0 && w->reward.w2 && w->cont.w0 && w->cont.w2 && w->actor.w0 &&
+                  w->actor_mu_w && w->actor_ls_w && w->buckets_rew,
+              DRM_ERR_ARG, "drm_rssm_pack: prior / reward / continue / actor weights are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (const MatOp& op : m->mat_ops) {
+    if (!src[op.src]) continue;  // optional head (critic) absent
+    pack_matrix_kernel<<<grid_for((long)op.nrows * op.ncols), 256, 0, st>>>(op.dst, op.ld_dst, op.row0, op.nrows, op.col0, op.ncols,
+                                                                         src[op.src], op.ld_src, op.row_map, op.col_map);
+    DRM_LAUNCH_CHECK();
+  }
+  for (const VecOp& op : m->vec_ops) {
+    if (!src[op.src]) continue;
+    pack_vector_kernel<<<ceil_div(op.n, 256), 256, 0, st>>>(op.dst, op.n, src[op.src], op.map, op.fill);
+    DRM_LAUNCH_CHECK();
+  }
+  m->packed = true;
+  m->has_critic = w->critic.w0 != nullptr;
+  return DRM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout** out) {
+  RC(check_arch());
+  DRM_REQUIRE(m && out, DRM_ERR_ARG, "drm_rollout_create: NULL argument");
+  DRM_REQUIRE(B >= 1 && H >= 1, DRM_ERR_SHAPE, "drm_rollout_create: B and H must be >= 1");
+  drm_rollout* r = new drm_rollout();
+  r->m = m; r->B = B; r->H = H; r->Mp = round_up(B, BM);
+  int rc = DRM_OK;
+#define TRY(x) if (rc == DRM_OK) rc = (x)
+  for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->S[i], (size_t)r->Mp * m->KS));
+  TRY(dev_alloc(r->allocs, &r->Y1, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
+  TRY(dev_alloc(r->allocs, &r->Y2, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
+  for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM));
+  TRY(make_tmap_bf16_2d(&r->tmY1, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
+  TRY(make_tmap_bf16_2d(&r->tmY2, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
+#undef TRY
+  if (rc != DRM_OK) {
+    drm_rollout_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return DRM_OK;
+}
+
+extern "C" int drm_rollout_destroy(drm_rollout* r) {
+  if (!r) return DRM_OK;
+  for (void* p : r->allocs) cudaFree(p);
+  delete r;
+  return DRM_OK;
+}
+
+namespace drm {
+
+static GemmCommon common(const CUtensorMap& A, const CUtensorMap& B, int M, int bn) {
+  GemmCommon g;
+  memset(&g, 0, sizeof(g));
+  g.tmA = A; g.tmB = B; g.M = M; g.bn = bn;
+  return g;
+}
+
+// GRU: S[cur] = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into S[nxt].h)
+static int stage_gru(drm_rollout* r, int cur, int nxt, const float* h_prev, long ld_hprev, float* h_out, long ld_hout, int M,
+                     cudaStream_t st) {
+  drm_rssm* m = r->m;
+  GemmCommon g = common(r->tmS[cur], m->tmWgru, M, 3 * m->U);
+  g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
+  g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
+  const dim3 grid(ceil_div(M, BM), m->gru_tiles);
+  if (m->U == 32) {
+    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
+    return launch_gemm<EpiGru<32>>(g, p, grid, st);
+  }
+  EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
+  return launch_gemm<EpiGru<64>>(g, p, grid, st);
+}
+
+// prior MLP on S[sb].h -> logits -> (optional) categorical sample
+static int stage_prior(drm_rollout* r, int sb, const float* uniforms, float* latent, long ld_latent, float* logits,
+                       long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, int M, cudaStream_t st) {
+  drm_rssm* m = r->m;
+  const int mt = ceil_div(M, BM);
+  {
+    GemmCommon g = common(r->tmS[sb], m->tmWp1, M, m->bnp1);
+    g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
+    g.n_slots = 1; g.y_slot[0] = 0;
+    EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, r->Y1, 256, 0, r->Mp, m->d.h_prior[0], 1e-5f};
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st));
+  }
+  {
+    GemmCommon g = common(r->tmY1, m->tmWp2, M, m->bnp2);
+    g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
+    g.n_slots = 1; g.y_slot[0] = 0;
+    EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, r->Y2, 256, 0, r->Mp, m->d.h_prior[1], 1e-5f};
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st));
+  }
+  {
+    GemmCommon g = common(r->tmY2, m->tmWp3, M, 256);
+    g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
+    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? r->S[sb] : nullptr, ld_latent, ld_logits, ld_idx, m->KS, m->d.R};
+    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st));
+  }
+  return DRM_OK;
+}
+
+// [h, z] heads on S[sb]: slots listed in `slots` (HS_*)
+static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st) {
+  drm_rssm* m = r->m;
+  const int mt = ceil_div(M, BM);
+  if (n_slots <= 0) return DRM_OK;
+  {
+    GemmCommon g = common(r->tmS[sb], m->tmWh1, M, m->bnh1);
+    g.ka0 = 0; g.nka0 = m->ZP / 64;                   // z blocks
+    g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;      // h blocks (the action block is skipped)
+    g.n_slots = n_slots;
+    for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, r->Y1, 256, r->Mp, r->Mp, m->d.h_head[0], 1e-5f};
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st));
+  }
+  {
+    GemmCommon g = common(r->tmY1, m->tmWh2, M, m->bnh2);
+    g.a_row0 = r->Mp; g.a_y_stride = r->Mp;
+    g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[0], 64);
+    g.n_slots = n_slots;
+    for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, r->Y2, 256, r->Mp, r->Mp, m->d.h_head[1], 1e-5f};
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st));
+  }
+  {
+    GemmCommon g = common(r->tmY2, m->tmWh3, M, 256);
+    g.a_row0 = r->Mp; g.a_y_stride = r->Mp;
+    g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[1], 64);
+    g.n_slots = n_slots;
+    for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    hp.bias = m->h3_b;
+    hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
+    hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
+    hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
+    hp.NB = m->d.NB; hp.A = m->d.A;
+    RC(launch_gemm<EpiHeads>(g, hp, dim3(mt, n_slots), st));
+  }
+  return DRM_OK;
+}
+
+static int pack_state(drm_rollout* r, int sb, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
+                      long ld_copy, cudaStream_t st) {
+  pack_state_kernel<<<grid_for((long)N * ncols), 256, 0, st>>>(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+}  // namespace drm
+
+extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const float* uniforms, const float* normals,
+                               float* latent, float* hidden, float* actions, float* rewards, float* continues, float* mu,
+                               float* sigma, uint8_t* idx, void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(r && z0 && h0 && uniforms && normals && latent && hidden && actions && rewards && continues && mu && sigma,
+              DRM_ERR_ARG, "drm_rollout_run: NULL argument");
+  drm_rssm* m = r->m;
+  DRM_REQUIRE(m->packed, DRM_ERR_ARG, "drm_rollout_run: weights were never packed (call drm_rssm_pack)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP, A = m->d.A, R = m->d.R;
+  const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D, ldA = (long)H * A;
+  // t = 0 state into S[0]; latent[:, 0] = z0, hidden[:, 0] = h0
+  RC(pack_state(r, 0, 0, z0, ZP, ZP, B, latent, ldL, st));
+  RC(pack_state(r, 0, ZP + 64, h0, D, D, B, hidden, ldH, st));
+  const int actor_only[1] = {HS_ACTOR};
+  const int all3[3] = {HS_REWARD, HS_CONT, HS_ACTOR};
+  {
+    EpiHeads::Params hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.normals = normals; hp.ld_normals = A; hp.mu = mu; hp.sigma = sigma; hp.action = actions; hp.ld_act = ldA;
+    hp.s_a = r->S[0] + ZP; hp.ld_s = m->KS;
+    RC(stage_heads(r, 0, actor_only, 1, hp, B, st));
+  }
+  for (int t = 0; t < H; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    RC(stage_gru(r, cur, nxt, hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st));
+    RC(stage_prior(r, nxt, uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
+                   idx ? idx + (long)t * R : nullptr, (long)H * R, true, B, st));
+    EpiHeads::Params hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.value[HS_REWARD] = rewards + t; hp.ld_value[HS_REWARD] = H;
+    hp.value[HS_CONT] = continues + t; hp.ld_value[HS_CONT] = H;
+    const bool more = t + 1 < H;
+    if (more) {
+      hp.normals = normals + (long)(t + 1) * B * A;  // [B, A] slab of step t + 1
+      hp.ld_normals = A;
+      hp.mu = mu + (long)(t + 1) * A; hp.sigma = sigma + (long)(t + 1) * A; hp.action = actions + (long)(t + 1) * A;
+      hp.ld_act = ldA;
+      hp.s_a = r->S[nxt] + ZP; hp.ld_s = m->KS;
+    }
+    RC(stage_heads(r, nxt, all3, more ? 3 : 2, hp, B, st));
+  }
+  return DRM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// step-level entry points (the drop-in classes' per-call path)
+// ------------------------------------------------------------------------------------------
+extern "C" int drm_gru_step(drm_rollout* r, const float* z, const float* h, const float* a, float* h_out, int32_t N,
+                            void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(r && z && h && a && h_out, DRM_ERR_ARG, "drm_gru_step: NULL argument");
+  DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_gru_step: N exceeds the workspace rows");
+  DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_gru_step: weights were never packed");
+  if (N == 0) return DRM_OK;
+  drm_rssm* m = r->m;
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
+  RC(pack_state(r, 0, m->ZP, a, m->d.A, m->d.A, N, nullptr, 0, st));
+  RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
+  return stage_gru(r, 0, 1, h, m->d.D, h_out, m->d.D, N, st);
+}
+
+extern "C" int drm_prior(drm_rollout* r, const float* h, const float* uniforms, float* logits, float* z_st, uint8_t* idx,
+                         int32_t N, void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(r && h, DRM_ERR_ARG, "drm_prior: NULL argument");
+  DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_prior: N exceeds the workspace rows");
+  DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_prior: weights were never packed");
+  if (N == 0) return DRM_OK;
+  drm_rssm* m = r->m;
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
+  return stage_prior(r, 0, uniforms, z_st, m->ZP, logits, m->ZP, idx, m->d.R, false, N, st);
+}
+
+extern "C" int drm_heads(drm_rollout* r, const float* h, const float* z, const float* normals, int32_t heads,
+                         const drm_heads_out* out, int32_t N, void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(r && h && z && out, DRM_ERR_ARG, "drm_heads: NULL argument");
+  DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_heads: N exceeds the workspace rows");
+  DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_heads: weights were never packed");
+  drm_rssm* m = r->m;
+  DRM_REQUIRE(!(heads & (DRM_HEAD_CRITIC | DRM_HEAD_TARGET_CRITIC)) || m->has_critic, DRM_ERR_ARG,
+              "drm_heads: critic requested but no critic weights were packed");
+  if (N == 0) return DRM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
+  RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
+  int slots[MAX_HEADS], n = 0;
+  EpiHeads::Params hp;
+  memset(&hp, 0, sizeof(hp));
+  const int NB = m->d.NB;
+  if (heads & DRM_HEAD_REWARD) { slots[n++] = HS_REWARD; hp.value[HS_REWARD] = out->reward; hp.ld_value[HS_REWARD] = 1; hp.logits[HS_REWARD] = out->reward_logits; hp.ld_logits[HS_REWARD] = NB; }
+  if (heads & DRM_HEAD_CONT) { slots[n++] = HS_CONT; hp.value[HS_CONT] = out->cont_prob; hp.logits[HS_CONT] = out->cont_logit; hp.ld_value[HS_CONT] = 1; }
+  if (heads & DRM_HEAD_ACTOR) { slots[n++] = HS_ACTOR; hp.normals = normals; hp.ld_normals = m->d.A; hp.mu = out->mu; hp.sigma = out->sigma; hp.action = out->action; hp.ld_act = m->d.A; }
+  if (heads & DRM_HEAD_CRITIC) { slots[n++] = HS_CRITIC; hp.value[HS_CRITIC] = out->value; hp.ld_value[HS_CRITIC] = 1; hp.logits[HS_CRITIC] = out->value_logits; hp.ld_logits[HS_CRITIC] = NB; }
+  if (heads & DRM_HEAD_TARGET_CRITIC) { slots[n++] = HS_TARGET; hp.value[HS_TARGET] = out->target_value; hp.ld_value[HS_TARGET] = 1; }
+  return stage_heads(r, 0, slots, n, hp, N, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// test hook: plain GEMM through the same TMA / tcgen05 main loop
+// ------------------------------------------------------------------------------------------
+extern "C" int drm_test_gemm(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                             void* stream) {
+  RC(check_arch());
+  DRM_REQUIRE(A && W && out, DRM_ERR_ARG, "drm_test_gemm: NULL argument");
+  DRM_REQUIRE(M >= 1 && N >= 1 && K >= 1, DRM_ERR_SHAPE, "drm_test_gemm: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = round_up(K, 64), Mp = round_up(M, BM), Np = round_up(N, 256);
+  std::vector<void*> bag;
+  __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
+  int rc = dev_alloc(bag, &a16, (size_t)Mp * Kp);
+  if (rc == DRM_OK) rc = dev_alloc(bag, &w16, (size_t)Np * Kp);
+  CUtensorMap tA, tW;
+  if (rc == DRM_OK) {
+    f32_to_bf16_pad_kernel<<<grid_for((long)M * Kp), 256, 0, st>>>(a16, Kp, A, M, K);
+    f32_to_bf16_pad_kernel<<<grid_for((long)N * Kp), 256, 0, st>>>(w16, Kp, W, N, K);
+    g_launches.fetch_add(2);
+    rc = make_tmap_bf16_2d(&tA, a16, Mp, Kp, Kp, BM);
+  }
+  if (rc == DRM_OK) rc = make_tmap_bf16_2d(&tW, w16, Np, Kp, Kp, 256);
+  if (rc == DRM_OK) {
+    GemmCommon g = common(tA, tW, M, 256);
+    g.ka0 = 0; g.nka0 = Kp / 64;
+    EpiPlain::Params p{bias, out, nullptr, (long)N, 0, N, 0};
+    rc = launch_gemm<EpiPlain>(g, p, dim3(Mp / BM, Np / 256), st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (void* q : bag) cudaFree(q);
+  if (rc == DRM_OK && e != cudaSuccess) return fail(DRM_ERR_CUDA, std::string("drm_test_gemm: ") + cudaGetErrorString(e));
+  return rc;
+}

@@ -1,0 +1,363 @@
+// HBM-bound fp32/u8 kernels of the hot path: the fused 32-class categorical head, the KL-balance
+// terms, the replay-ring gather/insert, the lambda-return scan, two-hot cross-entropy and the
+// bucket-value readout.  One warp per row everywhere (lane = class / bucket stripe), 16-byte
+// vector accesses where the layout allows, grids sized in multiples of the SM count.
+#include <string>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace drm {
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// categorical32: softmax -> unimix -> inverse-CDF sample -> one-hot -> straight-through.
+// DynamicsPredictors.py:33-39 / VariationalAutoEncoder.py:88-98.  Lane = class.
+// Algorithmic bytes per row: 128 B logits + 4 B uniform read; 128 B z_st (+ 1 B idx, + optional
+// 128 B probs, 64 B bf16 one-hot) written.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) categorical32_kernel(const float* __restrict__ logits,
+                                                            const float* __restrict__ uniforms,
+                                                            uint8_t* __restrict__ idx_out, float* __restrict__ z_st,
+                                                            float* __restrict__ probs, uint16_t* __restrict__ z_bf16,
+                                                            int64_t n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = warp; row < n_rows; row += nwarps) {
+    const float x = __ldg(logits + row * 32 + lane);
+    const float u = __ldg(uniforms + row);
+    const float m = warp_max(x);
+    const float e = expf(x - m);
+    const float s = warp_sum(e);
+    const float p = 0.99f * (e / s) + 0.01f * (1.0f / 32.0f);
+    // left-to-right fp32 prefix sum (the contract's order): lane k accumulates p_0 .. p_k
+    float cdf = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      if (j <= lane) cdf += pj;
+    }
+    const unsigned le = __ballot_sync(0xffffffffu, cdf <= u);
+    int idx = __popc(le);
+    idx = idx > 31 ? 31 : idx;
+    const float oh = (lane == idx) ? 1.0f : 0.0f;
+    if (z_st) z_st[row * 32 + lane] = (oh + p) - p;
+    if (probs) probs[row * 32 + lane] = p;
+    if (z_bf16) z_bf16[row * 32 + lane] = (lane == idx) ? (uint16_t)0x3F80 : (uint16_t)0;
+    if (idx_out && lane == 0) idx_out[row] = (uint8_t)idx;
+  }
+}
+
+// KL(Cat(post) || Cat(prior)) summed over the rows of a group (one warp per group).
+// WorldModel.py:175-181.
+__global__ void __launch_bounds__(256) categorical32_kl_kernel(const float* __restrict__ post,
+                                                               const float* __restrict__ prior,
+                                                               float* __restrict__ kl, int64_t n_groups,
+                                                               int rows_per_group) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = warp; g < n_groups; g += nwarps) {
+    float acc = 0.f;
+    for (int r = 0; r < rows_per_group; ++r) {
+      const int64_t off = (g * rows_per_group + r) * 32 + lane;
+      const float a = __ldg(post + off), b = __ldg(prior + off);
+      const float ma = warp_max(a), mb = warp_max(b);
+      const float lsa = logf(warp_sum(expf(a - ma))), lsb = logf(warp_sum(expf(b - mb)));
+      const float lp = a - ma - lsa, lq = b - mb - lsb;
+      acc += expf(lp) * (lp - lq);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) kl[g] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// replay ring: gather of B windows of L consecutive transitions (modulo capacity).
+// Buffer.py:49-61.  One block per (b, t) frame: 4-byte pixel loads (a warp reads 128 contiguous
+// bytes), 16-byte float4 stores (a warp writes 512 contiguous bytes).
+// Algorithmic bytes per (b, t): frame_bytes + 4 (A + 2) read, 4 * that written (61 480 B at 64x64x3).
+// ------------------------------------------------------------------------------------------
+template <bool NORM>
+__global__ void __launch_bounds__(256) replay_gather_kernel(const uint8_t* __restrict__ ring_obs,
+                                                            const float* __restrict__ ring_act,
+                                                            const float* __restrict__ ring_rew,
+                                                            const float* __restrict__ ring_con,
+                                                            const int64_t* __restrict__ starts,
+                                                            float* __restrict__ obs_out, float* __restrict__ act_out,
+                                                            float* __restrict__ rew_out, float* __restrict__ con_out,
+                                                            int L, int64_t cap, int frame_bytes, int A) {
+  const int64_t bt = blockIdx.x;
+  const int b = (int)(bt / L), t = (int)(bt % L);
+  const int64_t src = (__ldg(starts + b) + t) % cap;
+  const uchar4* __restrict__ in = reinterpret_cast<const uchar4*>(ring_obs + src * (int64_t)frame_bytes);
+  float4* __restrict__ out = reinterpret_cast<float4*>(obs_out + bt * (int64_t)frame_bytes);
+  const int nvec = frame_bytes >> 2;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * 256) {
+    uchar4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * 256;
+      if (i < nvec) v[j] = __ldg(in + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * 256;
+      if (i < nvec) {
+        float4 f = make_float4((float)v[j].x, (float)v[j].y, (float)v[j].z, (float)v[j].w);
+        if (NORM) {
+          f.x = f.x / 255.0f - 0.5f; f.y = f.y / 255.0f - 0.5f; f.z = f.z / 255.0f - 0.5f; f.w = f.w / 255.0f - 0.5f;
+        }
+        __stcs(out + i, f);
+      }
+    }
+  }
+  if (threadIdx.x < A) act_out[bt * A + threadIdx.x] = __ldg(ring_act + src * A + threadIdx.x);
+  if (threadIdx.x == 32) rew_out[bt] = __ldg(ring_rew + src);
+  if (threadIdx.x == 33) con_out[bt] = __ldg(ring_con + src);
+}
+
+// Buffer.add_to_buffer (Buffer.py:19-30) for n transitions: one block per transition.
+__global__ void __launch_bounds__(256) replay_insert_kernel(uint8_t* __restrict__ ring_obs, float* __restrict__ ring_act,
+                                                            float* __restrict__ ring_rew, float* __restrict__ ring_con,
+                                                            const uint8_t* __restrict__ obs, const float* __restrict__ act,
+                                                            const float* __restrict__ rew, const float* __restrict__ con,
+                                                            int64_t next_idx, int64_t cap, int frame_bytes, int A) {
+  const int i = blockIdx.x;
+  const int64_t dst = (next_idx + i) % cap;
+  const uint4* __restrict__ in = reinterpret_cast<const uint4*>(obs + (int64_t)i * frame_bytes);
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(ring_obs + dst * (int64_t)frame_bytes);
+  for (int k = threadIdx.x; k < (frame_bytes >> 4); k += blockDim.x) out[k] = __ldg(in + k);
+  if (threadIdx.x < A) ring_act[dst * A + threadIdx.x] = act[(int64_t)i * A + threadIdx.x];
+  if (threadIdx.x == 32) ring_rew[dst] = symlogf_(rew[i]);
+  if (threadIdx.x == 33) ring_con[dst] = con[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// lambda-return reverse scan, one thread per start state, registers only.  Agent.py:158-171.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) lambda_return_kernel(const float* __restrict__ rew, const float* __restrict__ cont,
+                                                            const float* __restrict__ value, float* __restrict__ out, int B,
+                                                            int H, float gamma, float lam) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* r = rew + (int64_t)b * H;
+  const float* c = cont + (int64_t)b * H;
+  const float* v = value + (int64_t)b * (H + 1);
+  float* o = out + (int64_t)b * H;
+  float nxt = r[H - 1] + gamma * c[H - 1] * v[H];
+  o[H - 1] = nxt;
+  for (int t = H - 2; t >= 0; --t) {
+    nxt = r[t] + gamma * c[t] * ((1.0f - lam) * v[t + 1] + lam * nxt);
+    o[t] = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// two-hot cross-entropy without materialising the two-hot (one warp per row).
+// DreamerUtils.py:39-50 + WorldModel.py:137-138 / Agent.py:129-134.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void twohot_index_weight(const float* __restrict__ buckets, int NB, float v, int& idx, float& w) {
+  const float lo0 = buckets[0], hi0 = buckets[NB - 1];
+  v = fminf(fmaxf(v, lo0), hi0);
+  // searchsorted(right=True) - 1 == (#buckets <= v) - 1
+  int lo = 0, hi = NB;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (buckets[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  idx = lo - 1;
+  idx = idx > NB - 2 ? NB - 2 : idx;
+  idx = idx < 0 ? 0 : idx;
+  const float bl = buckets[idx], bh = buckets[idx + 1];
+  w = (v - bl) / (bh - bl + 1e-8f);
+}
+
+__global__ void __launch_bounds__(256) twohot_ce_kernel(const float* __restrict__ logits, const float* __restrict__ value,
+                                                        const float* __restrict__ buckets, float* __restrict__ ll, int64_t N,
+                                                        int NB, int apply_symlog) {
+  __shared__ float sb[256];
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) sb[i] = buckets[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = warp; row < N; row += nwarps) {
+    const float* x = logits + row * NB;
+    float xv[8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      xv[j] = c < NB ? __ldg(x + c) : -INFINITY;
+      m = fmaxf(m, xv[j]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += (lane + 32 * j < NB) ? expf(xv[j] - m) : 0.f;
+    const float lse = m + logf(warp_sum(s));
+    if (lane == 0) {
+      float v = __ldg(value + row);
+      if (apply_symlog) v = symlogf_(v);
+      int idx; float w;
+      twohot_index_weight(sb, NB, v, idx, w);
+      ll[row] = (1.0f - w) * (__ldg(x + idx) - lse) + w * (__ldg(x + idx + 1) - lse);
+    }
+  }
+}
+
+// symexp(sum(softmax(logits) * buckets)), one warp per row.  DynamicsPredictors.py:70-74.
+__global__ void __launch_bounds__(256) bucket_value_kernel(const float* __restrict__ logits, const float* __restrict__ buckets,
+                                                           float* __restrict__ value, int64_t N, int NB) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = warp; row < N; row += nwarps) {
+    const float* x = logits + row * NB;
+    float xv[8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      xv[j] = c < NB ? __ldg(x + c) : -INFINITY;
+      m = fmaxf(m, xv[j]);
+    }
+    m = warp_max(m);
+    float s = 0.f, ws = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      if (c < NB) {
+        const float e = expf(xv[j] - m);
+        s += e;
+        ws += e * __ldg(buckets + c);
+      }
+    }
+    s = warp_sum(s);
+    ws = warp_sum(ws);
+    if (lane == 0) value[row] = symexpf_(ws / s);
+  }
+}
+
+static int rows_grid(int64_t rows, int warps_per_block) {
+  int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace drm
+
+using namespace drm;
+
+extern "C" int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* idx, float* z_st, float* probs,
+                                     uint16_t* z_bf16, int64_t n_rows, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(logits && uniforms, DRM_ERR_ARG, "drm_categorical32_fwd: logits/uniforms are NULL");
+  DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_fwd: n_rows < 0");
+  if (n_rows == 0) return DRM_OK;
+  categorical32_kernel<<<rows_grid(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_categorical32_kl(const float* post_logits, const float* prior_logits, float* kl, int64_t n_groups,
+                                    int rows_per_group, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(post_logits && prior_logits && kl, DRM_ERR_ARG, "drm_categorical32_kl: NULL pointer");
+  DRM_REQUIRE(n_groups >= 0 && rows_per_group > 0, DRM_ERR_SHAPE, "drm_categorical32_kl: bad shape");
+  if (n_groups == 0) return DRM_OK;
+  categorical32_kl_kernel<<<rows_grid(n_groups, 8), 256, 0, (cudaStream_t)stream>>>(post_logits, prior_logits, kl, n_groups, rows_per_group);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_replay_gather(const uint8_t* ring_obs, const float* ring_act, const float* ring_rew, const float* ring_con,
+                                 const int64_t* starts, float* obs_out, float* act_out, float* rew_out, float* con_out,
+                                 int32_t B, int32_t L, int64_t cap, int32_t frame_bytes, int32_t A, int32_t normalise,
+                                 void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(ring_obs && ring_act && ring_rew && ring_con && starts && obs_out && act_out && rew_out && con_out, DRM_ERR_ARG,
+              "drm_replay_gather: NULL pointer");
+  DRM_REQUIRE(B >= 0 && L > 0 && cap > 0 && A > 0 && A <= 32, DRM_ERR_SHAPE, "drm_replay_gather: bad shape");
+  DRM_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0, DRM_ERR_ALIGN, "drm_replay_gather: frame_bytes must be a multiple of 16");
+  DRM_REQUIRE(((uintptr_t)ring_obs % 16 == 0) && ((uintptr_t)obs_out % 16 == 0), DRM_ERR_ALIGN, "drm_replay_gather: 16-byte alignment required");
+  if (B == 0) return DRM_OK;
+  const int64_t frames = (int64_t)B * L;
+  DRM_REQUIRE(frames < (1ll << 31), DRM_ERR_SHAPE, "drm_replay_gather: B * L too large");
+  if (normalise)
+    replay_gather_kernel<true><<<(unsigned)frames, 256, 0, (cudaStream_t)stream>>>(ring_obs, ring_act, ring_rew, ring_con, starts, obs_out, act_out, rew_out, con_out, L, cap, frame_bytes, A);
+  else
+    replay_gather_kernel<false><<<(unsigned)frames, 256, 0, (cudaStream_t)stream>>>(ring_obs, ring_act, ring_rew, ring_con, starts, obs_out, act_out, rew_out, con_out, L, cap, frame_bytes, A);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_replay_insert(uint8_t* ring_obs, float* ring_act, float* ring_rew, float* ring_con, const uint8_t* obs,
+                                 const float* act, const float* rew, const float* con, int64_t next_idx, int32_t n, int64_t cap,
+                                 int32_t frame_bytes, int32_t A, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(ring_obs && ring_act && ring_rew && ring_con && obs && act && rew && con, DRM_ERR_ARG, "drm_replay_insert: NULL pointer");
+  DRM_REQUIRE(n >= 0 && n <= cap && cap > 0 && A > 0 && A <= 32 && next_idx >= 0 && next_idx < cap, DRM_ERR_SHAPE, "drm_replay_insert: bad shape");
+  DRM_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0, DRM_ERR_ALIGN, "drm_replay_insert: frame_bytes must be a multiple of 16");
+  DRM_REQUIRE(((uintptr_t)ring_obs % 16 == 0) && ((uintptr_t)obs % 16 == 0), DRM_ERR_ALIGN, "drm_replay_insert: 16-byte alignment required");
+  if (n == 0) return DRM_OK;
+  replay_insert_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(ring_obs, ring_act, ring_rew, ring_con, obs, act, rew, con, next_idx, cap, frame_bytes, A);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_lambda_return(const float* rew, const float* cont, const float* value, float* out, int32_t B, int32_t H,
+                                 float gamma, float lambda_, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rew && cont && value && out, DRM_ERR_ARG, "drm_lambda_return: NULL pointer");
+  DRM_REQUIRE(B >= 0 && H >= 1, DRM_ERR_SHAPE, "drm_lambda_return: bad shape");
+  if (B == 0) return DRM_OK;
+  lambda_return_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(rew, cont, value, out, B, H, gamma, lambda_);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_twohot_ce(const float* logits, const float* value, const float* buckets, float* ll, int64_t N, int32_t NB,
+                             int32_t apply_symlog, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(logits && value && buckets && ll, DRM_ERR_ARG, "drm_twohot_ce: NULL pointer");
+  DRM_REQUIRE(N >= 0 && NB >= 2 && NB <= 256, DRM_ERR_SHAPE, "drm_twohot_ce: NB must be in [2, 256]");
+  if (N == 0) return DRM_OK;
+  twohot_ce_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, value, buckets, ll, N, NB, apply_symlog);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_bucket_value(const float* logits, const float* buckets, float* value, int64_t N, int32_t NB, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(logits && buckets && value, DRM_ERR_ARG, "drm_bucket_value: NULL pointer");
+  DRM_REQUIRE(N >= 0 && NB >= 1 && NB <= 256, DRM_ERR_SHAPE, "drm_bucket_value: NB must be in [1, 256]");
+  if (N == 0) return DRM_OK;
+  bucket_value_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, buckets, value, N, NB);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}

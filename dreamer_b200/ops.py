@@ -1,0 +1,318 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point of include/dreamer_b200.h).
+
+All tensors must live on the CUDA device; outputs are allocated with torch (device memory
+plumbing only) and filled by the library on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------------------------
+# (2) categorical head
+# --------------------------------------------------------------------------------------------
+def categorical32(logits: torch.Tensor, uniforms: torch.Tensor, want_probs: bool = False, want_bf16: bool = False):
+    """logits (..., 32) fp32, uniforms (...) -> dict(z=(...,32) straight-through, idx=(...) uint8[, probs, z_bf16]).
+
+    Replaces DynamicsPredictors.py:33-39 / VariationalAutoEncoder.py:88-98.
+    """
+    L.require_cuda(logits, "logits")
+    if logits.shape[-1] != 32:
+        raise RuntimeError("dreamer_b200.categorical32: the class dimension must be 32")
+    lg = L.f32c(logits)
+    u = L.f32c(uniforms)
+    n = lg.numel() // 32
+    if u.numel() != n:
+        raise RuntimeError("dreamer_b200.categorical32: one uniform per categorical row is required")
+    z = torch.empty_like(lg)
+    idx = torch.empty(lg.shape[:-1], dtype=torch.uint8, device=lg.device)
+    probs = torch.empty_like(lg) if want_probs else None
+    zb = torch.empty(lg.shape, dtype=torch.bfloat16, device=lg.device) if want_bf16 else None
+    L.check(L.load().drm_categorical32_fwd(L.ptr(lg), L.ptr(u), L.ptr(idx), L.ptr(z), L.ptr(probs), L.ptr(zb), n, L.stream()),
+            "categorical32_fwd")
+    out = dict(z=z, idx=idx)
+    if want_probs:
+        out["probs"] = probs
+    if want_bf16:
+        out["z_bf16"] = zb
+    return out
+
+
+def categorical32_kl(post_logits: torch.Tensor, prior_logits: torch.Tensor) -> torch.Tensor:
+    """(..., R, 32) x2 -> (...) sum over R of KL(Cat(post)||Cat(prior)).  WorldModel.py:175-181."""
+    L.require_cuda(post_logits, "post_logits")
+    a, b = L.f32c(post_logits), L.f32c(prior_logits)
+    if a.shape != b.shape or a.shape[-1] != 32:
+        raise RuntimeError("dreamer_b200.categorical32_kl: shapes must match and end in 32")
+    R = a.shape[-2]
+    out = torch.empty(a.shape[:-2], dtype=torch.float32, device=a.device)
+    L.check(L.load().drm_categorical32_kl(L.ptr(a), L.ptr(b), L.ptr(out), out.numel(), R, L.stream()), "categorical32_kl")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# (4) replay ring
+# --------------------------------------------------------------------------------------------
+def replay_gather(ring_obs, ring_act, ring_rew, ring_con, starts, L_seq: int, normalise: bool = False):
+    """Buffer.py:49-61.  ring_obs (cap, 3, H, W) uint8 on device; starts (B,) int64 -> obs (B, L, 3, H, W) fp32, ..."""
+    L.require_cuda(ring_obs, "ring_obs")
+    cap = ring_obs.shape[0]
+    frame = ring_obs[0].numel()
+    A = ring_act.shape[1]
+    B = starts.numel()
+    starts = starts.to(device=ring_obs.device, dtype=torch.int64).contiguous()
+    obs = torch.empty((B, L_seq) + tuple(ring_obs.shape[1:]), dtype=torch.float32, device=ring_obs.device)
+    act = torch.empty((B, L_seq, A), dtype=torch.float32, device=ring_obs.device)
+    rew = torch.empty((B, L_seq, 1), dtype=torch.float32, device=ring_obs.device)
+    con = torch.empty((B, L_seq, 1), dtype=torch.float32, device=ring_obs.device)
+    L.check(L.load().drm_replay_gather(L.ptr(ring_obs), L.ptr(ring_act), L.ptr(ring_rew), L.ptr(ring_con), L.ptr(starts),
+                                       L.ptr(obs), L.ptr(act), L.ptr(rew), L.ptr(con), B, L_seq, cap, frame, A,
+                                       1 if normalise else 0, L.stream()), "replay_gather")
+    return obs, act, rew, con
+
+
+def replay_insert(ring_obs, ring_act, ring_rew, ring_con, obs_u8, act, rew, con, next_idx: int):
+    """Buffer.py:19-30 for n transitions already on the device."""
+    L.require_cuda(ring_obs, "ring_obs")
+    n = obs_u8.shape[0]
+    L.check(L.load().drm_replay_insert(L.ptr(ring_obs), L.ptr(ring_act), L.ptr(ring_rew), L.ptr(ring_con),
+                                       L.ptr(obs_u8.contiguous()), L.ptr(L.f32c(act)), L.ptr(L.f32c(rew)), L.ptr(L.f32c(con)),
+                                       next_idx, n, ring_obs.shape[0], ring_obs[0].numel(), ring_act.shape[1], L.stream()),
+            "replay_insert")
+
+
+# --------------------------------------------------------------------------------------------
+# returns / losses
+# --------------------------------------------------------------------------------------------
+def lambda_return(rew, cont, value, gamma: float, lam: float):
+    """Agent.py:158-171.  rew, cont (B,H,1) or (B,H); value (B,H+1,1) or (B,H+1) -> same rank as rew."""
+    L.require_cuda(rew, "rew")
+    r, c, v = L.f32c(rew), L.f32c(cont), L.f32c(value)
+    B, H = r.shape[0], r.shape[1]
+    if v.shape[1] != H + 1:
+        raise RuntimeError("dreamer_b200.lambda_return: value must have H + 1 steps")
+    out = torch.empty_like(r)
+    L.check(L.load().drm_lambda_return(L.ptr(r), L.ptr(c), L.ptr(v), L.ptr(out), B, H, gamma, lam, L.stream()), "lambda_return")
+    return out
+
+
+def twohot_ce(logits, value, buckets, apply_symlog: bool = False):
+    """sum(twohot(value) * log_softmax(logits)): logits (..., NB), value (..., 1) -> (..., 1)."""
+    L.require_cuda(logits, "logits")
+    lg, v, b = L.f32c(logits), L.f32c(value), L.f32c(buckets)
+    NB = lg.shape[-1]
+    N = lg.numel() // NB
+    out = torch.empty(lg.shape[:-1] + (1,), dtype=torch.float32, device=lg.device)
+    L.check(L.load().drm_twohot_ce(L.ptr(lg), L.ptr(v), L.ptr(b), L.ptr(out), N, NB, 1 if apply_symlog else 0, L.stream()), "twohot_ce")
+    return out
+
+
+def bucket_value(logits, buckets):
+    """symexp(sum(softmax(logits) * buckets)): (..., NB) -> (..., 1)."""
+    L.require_cuda(logits, "logits")
+    lg, b = L.f32c(logits), L.f32c(buckets)
+    NB = lg.shape[-1]
+    out = torch.empty(lg.shape[:-1] + (1,), dtype=torch.float32, device=lg.device)
+    L.check(L.load().drm_bucket_value(L.ptr(lg), L.ptr(b), L.ptr(out), lg.numel() // NB, NB, L.stream()), "bucket_value")
+    return out
+
+
+def test_gemm(A, W, bias=None):
+    """out = bf16(A) @ bf16(W)^T + bias through the TMA/tcgen05 main loop (test hook)."""
+    L.require_cuda(A, "A")
+    a, w = L.f32c(A), L.f32c(W)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    b = L.f32c(bias) if bias is not None else None
+    L.check(L.load().drm_test_gemm(L.ptr(a), L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, L.stream()), "test_gemm")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# packed RSSM + rollout workspace
+# --------------------------------------------------------------------------------------------
+def _mlp_struct(sd: Dict[str, torch.Tensor], prefix: Optional[str], keep: list, final: bool = True) -> L.DrmMlpW:
+    s = L.DrmMlpW()
+    if prefix is None:
+        return s
+    names = [("w0", "0.weight"), ("b0", "0.bias"), ("g0", "1.weight"), ("be0", "1.bias"),
+             ("w1", "3.weight"), ("b1", "3.bias"), ("g1", "4.weight"), ("be1", "4.bias")]
+    if final:
+        names += [("w2", "6.weight"), ("b2", "6.bias")]
+    for field, key in names:
+        t = L.f32c(sd[f"{prefix}.{key}"])
+        L.require_cuda(t, f"{prefix}.{key}")
+        keep.append(t)
+        setattr(s, field, t.data_ptr())
+    return s
+
+
+class PackedRssm:
+    """drm_rssm handle: bf16 tile-packed copies of the RSSM / head weights.
+
+    ``state_dict`` uses the reference's key names (``world_model.*`` / ``agent.*``).
+    Call :meth:`pack` again after every optimiser step -- the packed weights are a cache.
+    """
+
+    def __init__(self, D: int, R: int, C_: int, A: int, NB: int, h_prior, h_head):
+        self.dims = L.DrmDims(D, R, C_, A, NB, (C.c_int32 * 2)(*h_prior), (C.c_int32 * 2)(*h_head))
+        self.D, self.R, self.C, self.A, self.NB = D, R, C_, A, NB
+        self.handle = C.c_void_p()
+        L.check(L.load().drm_rssm_create(C.byref(self.dims), C.byref(self.handle)), "rssm_create")
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], R: int = 32, C_: int = 32):
+        D = sd["world_model.sequence_model.GRU.weight_hh"].shape[1]
+        A = sd["world_model.sequence_model.GRU.weight_ih"].shape[1] - R * C_
+        NB = sd["world_model.reward_predictor.buckets_rew"].shape[0]
+        hp = (sd["world_model.dynamics_predictor.logit_net.0.weight"].shape[0],
+              sd["world_model.dynamics_predictor.logit_net.3.weight"].shape[0])
+        heads = ["world_model.reward_predictor.logit_net", "world_model.continue_predictor.logit_generator",
+                 "agent.actor.base_net"] + (["agent.critic.value_net"] if "agent.critic.value_net.0.weight" in sd else [])
+        sizes = {(sd[f"{p}.0.weight"].shape[0], sd[f"{p}.3.weight"].shape[0]) for p in heads}
+        if len(sizes) != 1:
+            raise RuntimeError("dreamer_b200: reward / continue / actor / critic MLPs must share hidden sizes "
+                               f"(got {sorted(sizes)}); the fused head stage batches them in one launch")
+        obj = cls(D, R, C_, A, NB, hp, sizes.pop())
+        obj.pack(sd)
+        return obj
+
+    def pack(self, sd: Dict[str, torch.Tensor]):
+        keep = []
+        w = L.DrmRssmWeights()
+        g = "world_model.sequence_model.GRU."
+        for field, key in (("gru_w_ih", "weight_ih"), ("gru_w_hh", "weight_hh"), ("gru_b_ih", "bias_ih"), ("gru_b_hh", "bias_hh")):
+            t = L.f32c(sd[g + key]); L.require_cuda(t, g + key); keep.append(t); setattr(w, field, t.data_ptr())
+        w.prior = _mlp_struct(sd, "world_model.dynamics_predictor.logit_net", keep)
+        w.reward = _mlp_struct(sd, "world_model.reward_predictor.logit_net", keep)
+        w.cont = _mlp_struct(sd, "world_model.continue_predictor.logit_generator", keep)
+        w.actor = _mlp_struct(sd, "agent.actor.base_net", keep, final=False)
+        for field, key in (("actor_mu_w", "mu_head.weight"), ("actor_mu_b", "mu_head.bias"),
+                           ("actor_ls_w", "log_sig_head.weight"), ("actor_ls_b", "log_sig_head.bias")):
+            t = L.f32c(sd["agent.actor." + key]); keep.append(t); setattr(w, field, t.data_ptr())
+        has_c = "agent.critic.value_net.0.weight" in sd
+        w.critic = _mlp_struct(sd, "agent.critic.value_net" if has_c else None, keep)
+        w.target_critic = _mlp_struct(sd, "agent.target_critic.value_net" if "agent.target_critic.value_net.0.weight" in sd else None, keep)
+        t = L.f32c(sd["world_model.reward_predictor.buckets_rew"]); keep.append(t); w.buckets_rew = t.data_ptr()
+        if has_c:
+            t = L.f32c(sd["agent.critic.buckets_crit"]); keep.append(t); w.buckets_crit = t.data_ptr()
+        L.check(L.load().drm_rssm_pack(self.handle, C.byref(w), L.stream()), "rssm_pack")
+        self._keep = keep  # sources must stay alive until the pack kernels have run
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().drm_rssm_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+class Rollout:
+    """drm_rollout handle: state buffers + TMA descriptors for up to B rows and horizon H."""
+
+    def __init__(self, model: PackedRssm, B: int, H: int):
+        self.model, self.B, self.H = model, B, H
+        self.handle = C.c_void_p()
+        L.check(L.load().drm_rollout_create(model.handle, B, H, C.byref(self.handle)), "rollout_create")
+
+    def run(self, z0, h0, uniforms, normals, want_idx: bool = True):
+        """Dreamer.dream_episodes (Dreamer.py:143-175).
+
+        z0 (B,1,R,C) or (B,R*C); h0 (B,1,D) or (B,D); uniforms (H,B,R); normals (H,B,A).
+        Returns the reference 7-tuple (+ idx (B,H,R) uint8 when want_idx).
+        """
+        m, B, H = self.model, self.B, self.H
+        L.require_cuda(z0, "z0")
+        dev = z0.device
+        z0f = L.f32c(z0).reshape(B, m.R * m.C)
+        h0f = L.f32c(h0).reshape(B, m.D)
+        u = L.f32c(uniforms)
+        n = L.f32c(normals)
+        if tuple(u.shape) != (H, B, m.R) or tuple(n.shape) != (H, B, m.A):
+            raise RuntimeError(f"dreamer_b200.Rollout.run: uniforms must be {(H, B, m.R)} and normals {(H, B, m.A)}")
+        f = dict(dtype=torch.float32, device=dev)
+        latent = torch.empty((B, H + 1, m.R, m.C), **f)
+        hidden = torch.empty((B, H + 1, m.D), **f)
+        actions = torch.empty((B, H, m.A), **f)
+        mu = torch.empty((B, H, m.A), **f)
+        sigma = torch.empty((B, H, m.A), **f)
+        rewards = torch.empty((B, H, 1), **f)
+        conts = torch.empty((B, H, 1), **f)
+        idx = torch.empty((B, H, m.R), dtype=torch.uint8, device=dev) if want_idx else None
+        L.check(L.load().drm_rollout_run(self.handle, L.ptr(z0f), L.ptr(h0f), L.ptr(u), L.ptr(n), L.ptr(latent), L.ptr(hidden),
+                                         L.ptr(actions), L.ptr(rewards), L.ptr(conts), L.ptr(mu), L.ptr(sigma), L.ptr(idx),
+                                         L.stream()), "rollout_run")
+        out = (latent, hidden, actions, rewards, conts, mu, sigma)
+        return out + (idx,) if want_idx else out
+
+    # ---- step-level calls -------------------------------------------------------------------
+    def gru_step(self, z, h, a):
+        m = self.model
+        N = h.shape[0]
+        zf, hf, af = L.f32c(z).reshape(N, -1), L.f32c(h), L.f32c(a)
+        out = torch.empty_like(hf)
+        L.check(L.load().drm_gru_step(self.handle, L.ptr(zf), L.ptr(hf), L.ptr(af), L.ptr(out), N, L.stream()), "gru_step")
+        return out
+
+    def prior(self, h, uniforms=None, want_logits: bool = True):
+        m = self.model
+        N = h.shape[0]
+        hf = L.f32c(h)
+        logits = torch.empty((N, m.R, m.C), dtype=torch.float32, device=hf.device) if want_logits else None
+        z = idx = None
+        u = None
+        if uniforms is not None:
+            u = L.f32c(uniforms)
+            z = torch.empty((N, m.R, m.C), dtype=torch.float32, device=hf.device)
+            idx = torch.empty((N, m.R), dtype=torch.uint8, device=hf.device)
+        L.check(L.load().drm_prior(self.handle, L.ptr(hf), L.ptr(u), L.ptr(logits), L.ptr(z), L.ptr(idx), N, L.stream()), "prior")
+        return dict(logits=logits, z=z, idx=idx)
+
+    def heads(self, h, z, heads: int, normals=None, want_logits: bool = False):
+        m = self.model
+        N = h.shape[0]
+        hf, zf = L.f32c(h), L.f32c(z).reshape(N, -1)
+        f = dict(dtype=torch.float32, device=hf.device)
+        o = L.DrmHeadsOut()
+        res = {}
+
+        def alloc(name, shape):
+            t = torch.empty(shape, **f)
+            res[name] = t
+            setattr(o, name, t.data_ptr())
+
+        if heads & L.HEAD_REWARD:
+            alloc("reward", (N, 1))
+            if want_logits:
+                alloc("reward_logits", (N, m.NB))
+        if heads & L.HEAD_CONT:
+            alloc("cont_prob", (N, 1)); alloc("cont_logit", (N, 1))
+        nf = None
+        if heads & L.HEAD_ACTOR:
+            alloc("mu", (N, m.A)); alloc("sigma", (N, m.A))
+            if normals is not None:
+                nf = L.f32c(normals)
+                alloc("action", (N, m.A))
+        if heads & L.HEAD_CRITIC:
+            alloc("value", (N, 1))
+            if want_logits:
+                alloc("value_logits", (N, m.NB))
+        if heads & L.HEAD_TARGET_CRITIC:
+            alloc("target_value", (N, 1))
+        L.check(L.load().drm_heads(self.handle, L.ptr(hf), L.ptr(zf), L.ptr(nf), heads, C.byref(o), N, L.stream()), "heads")
+        return res
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().drm_rollout_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,186 @@
+/*
+ * dreamer_b200.h -- C-ABI of libdreamer_b200.so (sm_100a only).
+ *
+ * The reference (youngers2006/Dreamer) is pure PyTorch and has no FFI / plugin layer: its
+ * "ABI" is the Python class surface.  This header is therefore the boundary a
+ * maintainer binds to when swapping the hot path: every entry point names the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces.  The Python mirror
+ * of the reference classes (dreamer_b200/*.py) is a thin ctypes layer over exactly these calls.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller, row-major contiguous unless a
+ *     leading dimension is given; the library never frees or retains caller memory beyond the
+ *     call, except inside explicit handles (drm_rssm, drm_rollout, ...) the caller destroys;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued there, no host sync;
+ *   - return value: 0 = DRM_OK, negative = error; drm_last_error() gives a thread-local message;
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x every entry
+ *     point returns DRM_ERR_ARCH.
+ *
+ * Sampling contract (bit-exact indices given the same fp32 logits and uniforms):
+ *     p   = 0.99 * softmax(logits) + 0.01 / C
+ *     cdf = inclusive left-to-right fp32 prefix sum of p
+ *     idx = min(C - 1, #{k : cdf[k] <= u})
+ *     z   = (onehot(idx) + p) - p              (DynamicsPredictors.py:38-39)
+ */
+#ifndef DREAMER_B200_H_
+#define DREAMER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRM_OK 0
+#define DRM_ERR_SHAPE (-1)
+#define DRM_ERR_ALIGN (-2)
+#define DRM_ERR_ARCH (-3)
+#define DRM_ERR_CUDA (-4)
+#define DRM_ERR_ARG (-5)
+
+#define DRM_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+int drm_abi_version(void);
+const char* drm_last_error(void);
+/* 0 if the current device is sm_100-class, else DRM_ERR_ARCH. */
+int drm_device_check(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t drm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (2) fused 32-class categorical head                                                          */
+/*   replaces DynamicsPredictor.predict  DynamicsPredictors.py:33-39                            */
+/*            Encoder.encode            VariationalAutoEncoder.py:88-98                         */
+/* ------------------------------------------------------------------------------------------ */
+/* logits [n_rows, 32] fp32, uniforms [n_rows] fp32.  Outputs (each may be NULL):               */
+/*   idx [n_rows] u8, z_st [n_rows, 32] fp32, probs [n_rows, 32] fp32 (unimixed),               */
+/*   z_bf16 [n_rows, 32] bf16 one-hot (raw uint16 storage).                                     */
+int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* idx, float* z_st, float* probs,
+                          uint16_t* z_bf16, int64_t n_rows, void* stream);
+/* KL balance terms of WorldModel.training_step  WorldModel.py:175-181:                         */
+/*   kl[g] = sum over the `rows_per_group` categorical rows of group g of KL(Cat(post)||Cat(prior)) */
+/* post/prior logits [n_groups * rows_per_group, 32] fp32 -> kl [n_groups] fp32.                 */
+int drm_categorical32_kl(const float* post_logits, const float* prior_logits, float* kl, int64_t n_groups,
+                         int rows_per_group, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (4) replay ring gather -- replaces Buffer.sample_sequences' gather  Buffer.py:49-61           */
+/* ------------------------------------------------------------------------------------------ */
+/* ring_obs [cap, frame_bytes] u8 (frame_bytes % 16 == 0), ring_act [cap, A], ring_rew/ring_con  */
+/* [cap, 1] fp32, starts [B] int64 (window = (start + t) % cap).  Outputs: obs_out [B, L,        */
+/* frame_bytes] fp32 holding 0..255 (normalise = 0, as the reference returns) or x/255 - 0.5     */
+/* (normalise = 1, WorldModel.py:156 fused), act_out [B, L, A], rew_out/con_out [B, L, 1].       */
+int drm_replay_gather(const uint8_t* ring_obs, const float* ring_act, const float* ring_rew, const float* ring_con,
+                      const int64_t* starts, float* obs_out, float* act_out, float* rew_out, float* con_out,
+                      int32_t B, int32_t L, int64_t cap, int32_t frame_bytes, int32_t A, int32_t normalise,
+                      void* stream);
+/* Buffer.add_to_buffer  Buffer.py:19-30 for `n` consecutive transitions already on the device   */
+/* (obs u8 [n, frame_bytes], act [n, A], rew raw [n], con [n]); rewards are stored symlog'd.     */
+int drm_replay_insert(uint8_t* ring_obs, float* ring_act, float* ring_rew, float* ring_con, const uint8_t* obs,
+                      const float* act, const float* rew, const float* con, int64_t next_idx, int32_t n,
+                      int64_t cap, int32_t frame_bytes, int32_t A, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* returns / losses (fp32, HBM-bound)                                                            */
+/* ------------------------------------------------------------------------------------------ */
+/* Agent.compute_batched_R_lambda_returns' reverse scan  Agent.py:158-171.                       */
+/* rew, cont [B, H]; value [B, H + 1] -> out [B, H].                                             */
+int drm_lambda_return(const float* rew, const float* cont, const float* value, float* out, int32_t B, int32_t H,
+                      float gamma, float lambda_, void* stream);
+/* sum(twohot(v) * log_softmax(logits))  DreamerUtils.py:39-50 + WorldModel.py:137-138 /         */
+/* Agent.py:129-134, without materialising the two-hot.  logits [N, NB], value [N] (symlog is    */
+/* applied first when apply_symlog != 0), buckets [NB] -> ll [N] (log-likelihood, not negated).  */
+int drm_twohot_ce(const float* logits, const float* value, const float* buckets, float* ll, int64_t N, int32_t NB,
+                  int32_t apply_symlog, void* stream);
+/* symexp(sum(softmax(logits) * buckets))  DynamicsPredictors.py:70-74, Agent.py:237-241.        */
+int drm_bucket_value(const float* logits, const float* buckets, float* value, int64_t N, int32_t NB, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (1)(2)(5) RSSM: packed weights + fused tcgen05 stages                                         */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct drm_dims {
+  int32_t D;          /* hidden_state_dims (GRU width)                                          */
+  int32_t R, C;       /* latent rows x classes; C must be 32, R * C a multiple of 256            */
+  int32_t A;          /* action_dims (<= 16)                                                    */
+  int32_t NB;         /* reward / critic buckets (<= 256)                                       */
+  int32_t h_prior[2]; /* dyn_pred_hidden_num_nodes_{1,2} (<= 256)                               */
+  int32_t h_head[2];  /* hidden sizes shared by reward / continue / actor / critic MLPs (<= 256) */
+} drm_dims;
+
+/* One Linear-LN-SiLU-Linear-LN-SiLU(-Linear) head in reference state_dict layout, fp32:         */
+/* w0 [h1, in], b0, g0, be0 [h1]; w1 [h2, h1], b1, g1, be1 [h2]; w2 [out, h2], b2 [out] or NULL. */
+typedef struct drm_mlp_w {
+  const float *w0, *b0, *g0, *be0, *w1, *b1, *g1, *be1, *w2, *b2;
+} drm_mlp_w;
+
+typedef struct drm_rssm_weights {
+  /* SequenceModel.GRU (nn.GRUCell)  SequenceModel.py:13-17; gate order [r; z; n]              */
+  const float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh; /* [3D, R*C + A], [3D, D], [3D], [3D] */
+  drm_mlp_w prior;   /* DynamicsPredictor.logit_net        DynamicsPredictors.py:15-23  in = D  */
+  drm_mlp_w reward;  /* RewardPredictor.logit_net          DynamicsPredictors.py:52-60  in=[h,z] */
+  drm_mlp_w cont;    /* ContinuePredictor.logit_generator  DynamicsPredictors.py:85-93  in=[h,z] */
+  drm_mlp_w actor;   /* Actor.base_net (w2 = b2 = NULL)    Agent.py:178-185             in=[h,z] */
+  const float *actor_mu_w, *actor_mu_b, *actor_ls_w, *actor_ls_b; /* Agent.py:186-187  [A, h2]  */
+  drm_mlp_w critic;        /* Critic.value_net        Agent.py:219-227 (may be all NULL)        */
+  drm_mlp_w target_critic; /* Agent.target_critic     Agent.py:50      (may be all NULL)        */
+  const float* buckets_rew;  /* [NB]  DynamicsPredictors.py:61-62                               */
+  const float* buckets_crit; /* [NB]  Agent.py:228-229 (NULL if no critic)                      */
+} drm_rssm_weights;
+
+typedef struct drm_rssm drm_rssm;       /* packed bf16 weights (a cache: re-pack after every optimiser step) */
+typedef struct drm_rollout drm_rollout; /* workspace + TMA descriptors for a fixed (B, H) */
+
+int drm_rssm_create(const drm_dims* dims, drm_rssm** out);
+int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* stream);
+int drm_rssm_destroy(drm_rssm* m);
+
+int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout** out);
+int drm_rollout_destroy(drm_rollout* r);
+
+/* Dreamer.dream_episodes  Dreamer.py:143-175  (Actor.act Agent.py:202-210 ->                    */
+/* WorldModel.imagine_step WorldModel.py:72-77, H times), with host-supplied randomness.        */
+/*   z0 [B, R*C] fp32 (a one-hot / straight-through latent), h0 [B, D] fp32,                     */
+/*   uniforms [H, B, R], normals [H, B, A]                                                       */
+/*   -> latent [B, H+1, R*C], hidden [B, H+1, D], actions/mu/sigma [B, H, A],                    */
+/*      rewards/continues [B, H] (all fp32), idx [B, H, R] u8 (may be NULL).                     */
+int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const float* uniforms, const float* normals,
+                    float* latent, float* hidden, float* actions, float* rewards, float* continues, float* mu,
+                    float* sigma, uint8_t* idx, void* stream);
+
+/* Step-level entry points behind the drop-in classes.  They run on the rollout workspace (any   */
+/* N <= B of drm_rollout_create).                                                                */
+/* SequenceModel.forward  SequenceModel.py:19-24:  z [N, R*C], h [N, D], a [N, A] -> h_out [N, D] */
+int drm_gru_step(drm_rollout* r, const float* z, const float* h, const float* a, float* h_out, int32_t N,
+                 void* stream);
+/* DynamicsPredictor.forward / .predict  DynamicsPredictors.py:25-40: h [N, D] -> logits         */
+/* [N, R*C]; when uniforms [N, R] != NULL also z_st [N, R*C] and idx [N, R] (each may be NULL).  */
+int drm_prior(drm_rollout* r, const float* h, const float* uniforms, float* logits, float* z_st, uint8_t* idx,
+              int32_t N, void* stream);
+/* Reward / Continue / Actor / Critic heads on [h, z]  DynamicsPredictors.py:64-74, 95-105;      */
+/* Agent.py:191-210, 231-241.  `heads` is a bit mask of DRM_HEAD_*; outputs of unselected heads   */
+/* and any NULL output are skipped.  reward/value [N] (symexp'd), *_logits [N, NB], cont_prob /   */
+/* cont_logit [N], mu/sigma/action [N, A] (action = tanh(mu + sigma * normals), normals [N, A]).  */
+#define DRM_HEAD_REWARD 1
+#define DRM_HEAD_CONT 2
+#define DRM_HEAD_ACTOR 4
+#define DRM_HEAD_CRITIC 8
+#define DRM_HEAD_TARGET_CRITIC 16
+typedef struct drm_heads_out {
+  float *reward, *reward_logits, *cont_prob, *cont_logit, *mu, *sigma, *action;
+  float *value, *value_logits, *target_value;
+} drm_heads_out;
+int drm_heads(drm_rollout* r, const float* h, const float* z, const float* normals, int32_t heads,
+              const drm_heads_out* out, int32_t N, void* stream);
+
+/* Test hook: plain bf16 GEMM  out[M, N] = A[M, K] * W[N, K]^T + bias  through the same TMA /      */
+/* tcgen05 main loop the fused stages use (fp32 inputs are rounded to bf16 on the device).        */
+int drm_test_gemm(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DREAMER_B200_H_ */

@@ -82,13 +82,24 @@ def unimix_probs(logits: torch.Tensor) -> torch.Tensor:
     return 0.99 * torch.softmax(logits.float(), dim=-1) + 0.01 * (1.0 / C)
 
 
+def cumsum_f32(p: torch.Tensor) -> torch.Tensor:
+    """Inclusive left-to-right prefix sum with every partial sum rounded to fp32 (the contract's
+    cdf; torch.cumsum on CPU may accumulate in a wider type)."""
+    out = torch.empty_like(p)
+    acc = torch.zeros_like(p[..., 0])
+    for k in range(p.shape[-1]):
+        acc = acc + p[..., k]
+        out[..., k] = acc
+    return out
+
+
 def interior_uniforms(p: torch.Tensor, u: torch.Tensor, margin_frac: float = 0.0, delta: float = 1e-5) -> torch.Tensor:
     """Move each uniform into the interior of the bin the contract selects for it.
 
     The selected index is unchanged; the draw merely becomes insensitive to ULP-level (delta) or
     bf16-level (margin_frac of the bin width) perturbations of the CDF (SURVEY.md section 7 hard part b).
     """
-    cdf = torch.cumsum(p, dim=-1)
+    cdf = cumsum_f32(p)
     C = p.shape[-1]
     idx = (cdf <= u.unsqueeze(-1)).sum(-1).clamp(max=C - 1)
     hi = cdf.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
@@ -107,7 +118,7 @@ def categorical_st(logits: torch.Tensor, u: torch.Tensor):
     (DynamicsPredictors.py:33-39; VariationalAutoEncoder.py:88-98) with the inverse-CDF rule.
     """
     p = unimix_probs(logits)
-    cdf = torch.cumsum(p, dim=-1)
+    cdf = cumsum_f32(p)
     C = p.shape[-1]
     idx = (cdf <= u.unsqueeze(-1)).sum(-1).clamp(max=C - 1)
     oh = F.one_hot(idx, C).float()
