@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- imagined latent states/s of the RSSM imagination rollout (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2x16|c4] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: Dreamer.dream_episodes (Dreamer.py:143-175) for
+B start states x H imagined steps with random-init weights of the reference architecture and
+synthetic inputs.  Default workload = BASELINE.json configs[1]: 1024 start states
+x horizon 15 at car_racer_config.yaml sizes, per GPU (weak scaling: every rank owns its own 1024
+start states; the rollout needs no collective).
+
+One JSON line is printed by rank 0.  `value` = device-timed whole-job states/s with inputs resident
+in HBM; `e2e` = the same through the public host-buffer API (pinned-host inputs copied H2D and the
+rewards/continues read back D2H inside the timed region); `roofline` = the dominant kernel (the fused
+tcgen05 GRU stage) against the measured bf16 peak; `cpu_baseline` = the CPU port of the reference
+(oracle/, stock sampler) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (B per GPU, H, config overrides, description)
+    "c2": (1024, 15, {}, "imagination rollout 1024 start states x horizon 15, car_racer_config sizes (BASELINE configs[1])"),
+    "c2x16": (16384, 15, {}, "imagination rollout 16384 start states x horizon 15, car_racer_config sizes"),
+    "c4": (16384, 15, {"hidden_state_dims": 4096}, "imagination rollout 16384 start states x horizon 15, GRU deter 4096 (BASELINE configs[3])"),
+}
+
+
+def flops_per_state(cfg):
+    """Dense forward FLOPs per imagined state as the reference computes them."""
+    D = cfg["hidden_state_dims"]; Z = cfg["latent_state_dims"][0] * cfg["latent_state_dims"][1]; A = cfg["action_dims"]
+    NB = cfg["critic_reward_buckets"]
+    hp1, hp2 = cfg["dyn_pred_hidden_num_nodes_1"], cfg["dyn_pred_hidden_num_nodes_2"]
+    gru = 2 * (3 * D * (Z + A + D))
+    actor = 2 * ((D + Z) * cfg["hidden_layer_actor_1_size"] + cfg["hidden_layer_actor_1_size"] * cfg["hidden_layer_actor_2_size"] + cfg["hidden_layer_actor_2_size"] * 2 * A)
+    prior = 2 * (D * hp1 + hp1 * hp2 + hp2 * Z)
+    rew = 2 * ((D + Z) * cfg["rew_pred_hidden_num_nodes_1"] + cfg["rew_pred_hidden_num_nodes_1"] * cfg["rew_pred_hidden_num_nodes_2"] + cfg["rew_pred_hidden_num_nodes_2"] * NB)
+    con = 2 * ((D + Z) * cfg["cont_pred_hidden_num_nodes_1"] + cfg["cont_pred_hidden_num_nodes_1"] * cfg["cont_pred_hidden_num_nodes_2"] + cfg["cont_pred_hidden_num_nodes_2"] * 1)
+    return dict(gru=gru, total=gru + actor + prior + rew + con)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="MEASURED_PEAKS.json")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
+
+
+def make_problem(workload):
+    from oracle import weights as W   # synthetic weights/inputs only (deterministic numpy streams)
+    B, H, over, desc = WORKLOADS[workload]
+    cfg = dict(W.REF_CONFIG, horizon=H, **over)
+    sd = W.make_state_dict(cfg, seed=0, actor_mu_zero=True)
+    return cfg, sd, B, H, desc
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port with the stock sampler),
+    all host threads, on a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import rssm as O
+    from oracle import weights as W
+    cfg, sd, B, H, desc = make_problem(args.workload)
+    Bs = min(B, args.cpu_rows)
+    torch.set_num_threads(os.cpu_count() or 1)
+    z0, h0, _, n = W.rollout_inputs(cfg, Bs, H, seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.dream_episodes(sd, z0, h0, None, n)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    val = Bs * H * len(times) / total
+    sample = f"{Bs} of {B} start states x horizon {H}, {len(times)} timed rollouts, stock torch sampler, fp32, no_grad"
+    line = dict(impl="reference", metric="imagined latent states/sec", value=val, unit="states/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=dict(workload=desc, l2="n/a (CPU)"),
+                cpu_baseline=dict(value=val, unit="states/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+                e2e=dict(value=val, unit="states/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, cfg, sd, B, H):
+    from oracle import rssm as O
+    from oracle import weights as W
+    Bs = min(B, args.cpu_rows)
+    torch.set_num_threads(os.cpu_count() or 1)
+    z0, h0, _, n = W.rollout_inputs(cfg, Bs, H, seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(1 + args.cpu_reps):
+            t0 = time.perf_counter()
+            O.dream_episodes(sd, z0, h0, None, n)
+            if i:
+                times.append(time.perf_counter() - t0)
+    val = Bs * H / statistics.median(times)
+    return dict(value=val, unit="states/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{Bs} of {B} start states x horizon {H}, median of {len(times)} rollouts after 1 warm-up, stock torch sampler, fp32, no_grad")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=1024, help="start states in the CPU sample")
+    ap.add_argument("--cpu-reps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from dreamer_b200 import _lib as L
+    from dreamer_b200 import ops
+    from dreamer_b200.rollout import dream_episodes_host
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.load().drm_device_check(), "device_check")
+
+    cfg, sd, B, H, desc = make_problem(args.workload)
+    from oracle import weights as W
+    z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=1234 + rank)      # every rank owns different start states
+    model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in sd.items()})
+    ro = ops.Rollout(model, B, H)
+    z0d, h0d, ud, nd = (t.to(dev) for t in (z0, h0, u, n))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.zero_(); fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                              # L2 flush between timed iterations (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
+        return float(t.item())
+
+    lib = L.load()
+    # ---- device-resident throughput ------------------------------------------------------------
+    step = lambda: ro.run(z0d, h0d, ud, nd, want_idx=False)
+    sampler = ClockSampler(local)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = lib.drm_launch_count()
+    total_ms = timed(step, args.steps, args.warmup)
+    launches = lib.drm_launch_count() - launches0
+    clocks = sampler.stop()
+    states = B * H * world
+    value = states * args.steps / (total_ms * 1e-3)
+    gpu_launches = launches * args.steps // (args.steps + args.warmup)
+
+    # ---- end to end through the public host-buffer API -------------------------------------------
+    pin = [t.contiguous().pin_memory() for t in (z0, h0, u, n)]
+    h2d = sum(t.numel() * t.element_size() for t in pin)
+    res = {}
+
+    def e2e_step():
+        out = dream_episodes_host(ro, *pin)
+        res["d2h"] = sum(t.numel() * t.element_size() for t in out["host"])
+    e2e_ms = timed(e2e_step, args.steps, args.warmup)
+    e2e_val = states * args.steps / (e2e_ms * 1e-3)
+
+    # ---- per-stage device times (separate profiled pass over the same workload) -----------------
+    import ctypes as C
+    lib.drm_profile_enable(1)
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        flush.zero_(); step()
+    torch.cuda.synchronize()
+    lib.drm_profile_enable(0)
+    names = ["gru", "prior_l1", "prior_l2", "prior_cat", "heads_l1", "heads_l2", "heads_out", "other"]
+    stages = {}
+    for i, nm in enumerate(names):
+        ms, cnt = C.c_double(), C.c_int64()
+        lib.drm_profile_read(i, C.byref(ms), C.byref(cnt))
+        if cnt.value:
+            stages[nm] = dict(ms_per_step=ms.value / prof_steps, launches_per_step=cnt.value / prof_steps, us_per_launch=1e3 * ms.value / cnt.value)
+    fl = flops_per_state(cfg)
+    peaks = measured_peaks()
+    gru_us = stages["gru"]["us_per_launch"]
+    gru_tf = fl["gru"] * B / (gru_us * 1e-6) / 1e12
+    whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12 / world
+    roofline = dict(bound="tensor", kernel="fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)", achieved=gru_tf, peak=peaks["bf16_burst"],
+                    unit="TFLOP/s", frac=gru_tf / peaks["bf16_burst"], traffic=None, peak_source=peaks["source"] + " bf16 burst",
+                    flops_per_launch=fl["gru"] * B, us_per_launch=gru_us,
+                    whole_rollout=dict(achieved=whole_tf, peak=peaks["bf16_sustained"], frac=whole_tf / peaks["bf16_sustained"],
+                                       flops_per_state=fl["total"]),
+                    stages=stages)
+
+    line = dict(metric="imagined latent states/sec", value=value, unit="states/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic", config=dict(workload=desc, start_states_per_gpu=B, horizon=H, l2="flushed (256 MiB write) between timed iterations",
+                                              parallelism=f"start states sharded over {world} rank(s), no data-path collective"),
+                e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
+                gpu_launches=int(gpu_launches), clocks=clocks, roofline=roofline)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, cfg, sd, B, H)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

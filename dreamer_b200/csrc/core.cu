@@ -4,6 +4,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "internal.h"
 
@@ -71,7 +72,54 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return DRM_OK;
 }
 
+// ---- per-stage event timing ---------------------------------------------------------------
+static bool g_profile = false;
+static std::mutex g_prof_mu;
+struct EvPair { cudaEvent_t a, b; };
+static std::vector<EvPair> g_events[DRM_STAGE_COUNT];
+static cudaEvent_t g_open[DRM_STAGE_COUNT];
+
+bool profile_on() { return g_profile; }
+void profile_begin(int stage, cudaStream_t st) {
+  if (!g_profile) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_open[stage] = e;
+}
+void profile_end(int stage, cudaStream_t st) {
+  if (!g_profile) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_events[stage].push_back({g_open[stage], e});
+}
+
 }  // namespace drm
+
+extern "C" int drm_profile_enable(int32_t on) {
+  drm::g_profile = on != 0;
+  return DRM_OK;
+}
+extern "C" int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches) {
+  using namespace drm;
+  if (stage < 0 || stage >= DRM_STAGE_COUNT || !total_ms || !launches) return fail(DRM_ERR_ARG, "drm_profile_read: bad argument");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0;
+  for (auto& p : g_events[stage]) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    tot += ms;
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  *total_ms = tot;
+  *launches = (int64_t)g_events[stage].size();
+  g_events[stage].clear();
+  return DRM_OK;
+}
 
 extern "C" int drm_abi_version(void) { return DRM_ABI_VERSION; }
 extern "C" const char* drm_last_error(void) { return drm::t_err.c_str(); }

@@ -16,6 +16,11 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 extern std::atomic<int64_t> g_launches;
 
+// per-stage event timing (drm_profile_enable / drm_profile_read)
+bool profile_on();
+void profile_begin(int stage, cudaStream_t st);
+void profile_end(int stage, cudaStream_t st);
+
 // 0 when the current device is sm_100-class; caches the answer per device.
 int check_arch();
 

@@ -71,14 +71,16 @@ static int grid_for(long total, int threads = 256) {
 }
 
 template <class Epi>
-static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3 grid, cudaStream_t st) {
+static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3 grid, cudaStream_t st, int stage = DRM_STAGE_OTHER) {
   using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     DRM_CUDA(cudaFuncSetAttribute(fused_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
     attr_set = true;
   }
+  profile_begin(stage, st);
   fused_gemm_kernel<Epi><<<grid, GEMM_THREADS, SL::TOTAL, st>>>(g, ep);
+  profile_end(stage, st);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -401,10 +403,10 @@ static int stage_gru(drm_rollout* r, int cur, int nxt, const float* h_prev, long
   const dim3 grid(ceil_div(M, BM), m->gru_tiles);
   if (m->U == 32) {
     EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
-    return launch_gemm<EpiGru<32>>(g, p, grid, st);
+    return launch_gemm<EpiGru<32>>(g, p, grid, st, DRM_STAGE_GRU);
   }
   EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
-  return launch_gemm<EpiGru<64>>(g, p, grid, st);
+  return launch_gemm<EpiGru<64>>(g, p, grid, st, DRM_STAGE_GRU);
 }
 
 // prior MLP on S[sb].h -> logits -> (optional) categorical sample
@@ -417,20 +419,20 @@ static int stage_prior(drm_rollout* r, int sb, const float* uniforms, float* lat
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
     EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, r->Y1, 256, 0, r->Mp, m->d.h_prior[0], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st));
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L1));
   }
   {
     GemmCommon g = common(r->tmY1, m->tmWp2, M, m->bnp2);
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
     g.n_slots = 1; g.y_slot[0] = 0;
     EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, r->Y2, 256, 0, r->Mp, m->d.h_prior[1], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st));
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L2));
   }
   {
     GemmCommon g = common(r->tmY2, m->tmWp3, M, 256);
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
     EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? r->S[sb] : nullptr, ld_latent, ld_logits, ld_idx, m->KS, m->d.R};
-    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st));
+    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
 }
@@ -447,7 +449,7 @@ static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, Ep
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, r->Y1, 256, r->Mp, r->Mp, m->d.h_head[0], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st));
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L1));
   }
   {
     GemmCommon g = common(r->tmY1, m->tmWh2, M, m->bnh2);
@@ -456,7 +458,7 @@ static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, Ep
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
     EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, r->Y2, 256, r->Mp, r->Mp, m->d.h_head[1], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st));
+    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L2));
   }
   {
     GemmCommon g = common(r->tmY2, m->tmWh3, M, 256);
@@ -469,7 +471,7 @@ static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, Ep
     hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
     hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
     hp.NB = m->d.NB; hp.A = m->d.A;
-    RC(launch_gemm<EpiHeads>(g, hp, dim3(mt, n_slots), st));
+    RC(launch_gemm<EpiHeads>(g, hp, dim3(mt, n_slots), st, DRM_STAGE_HEADS_OUT));
   }
   return DRM_OK;
 }

@@ -276,9 +276,9 @@ using namespace drm;
 extern "C" int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* idx, float* z_st, float* probs,
                                      uint16_t* z_bf16, int64_t n_rows, void* stream) {
   if (int rc = check_arch()) return rc;
-  DRM_REQUIRE(logits && uniforms, DRM_ERR_ARG, "drm_categorical32_fwd: logits/uniforms are NULL");
   DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_fwd: n_rows < 0");
-  if (n_rows == 0) return DRM_OK;
+  if (n_rows == 0) return DRM_OK;  // empty input: nothing to do (pointers may be NULL)
+  DRM_REQUIRE(logits && uniforms, DRM_ERR_ARG, "drm_categorical32_fwd: logits/uniforms are NULL");
   categorical32_kernel<<<rows_grid(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -287,9 +287,9 @@ extern "C" int drm_categorical32_fwd(const float* logits, const float* uniforms,
 extern "C" int drm_categorical32_kl(const float* post_logits, const float* prior_logits, float* kl, int64_t n_groups,
                                     int rows_per_group, void* stream) {
   if (int rc = check_arch()) return rc;
-  DRM_REQUIRE(post_logits && prior_logits && kl, DRM_ERR_ARG, "drm_categorical32_kl: NULL pointer");
   DRM_REQUIRE(n_groups >= 0 && rows_per_group > 0, DRM_ERR_SHAPE, "drm_categorical32_kl: bad shape");
   if (n_groups == 0) return DRM_OK;
+  DRM_REQUIRE(post_logits && prior_logits && kl, DRM_ERR_ARG, "drm_categorical32_kl: NULL pointer");
   categorical32_kl_kernel<<<rows_grid(n_groups, 8), 256, 0, (cudaStream_t)stream>>>(post_logits, prior_logits, kl, n_groups, rows_per_group);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -300,9 +300,10 @@ extern "C" int drm_replay_gather(const uint8_t* ring_obs, const float* ring_act,
                                  int32_t B, int32_t L, int64_t cap, int32_t frame_bytes, int32_t A, int32_t normalise,
                                  void* stream) {
   if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(B >= 0 && L > 0 && cap > 0 && A > 0 && A <= 32, DRM_ERR_SHAPE, "drm_replay_gather: bad shape");
+  if (B == 0) return DRM_OK;
   DRM_REQUIRE(ring_obs && ring_act && ring_rew && ring_con && starts && obs_out && act_out && rew_out && con_out, DRM_ERR_ARG,
               "drm_replay_gather: NULL pointer");
-  DRM_REQUIRE(B >= 0 && L > 0 && cap > 0 && A > 0 && A <= 32, DRM_ERR_SHAPE, "drm_replay_gather: bad shape");
   DRM_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0, DRM_ERR_ALIGN, "drm_replay_gather: frame_bytes must be a multiple of 16");
   DRM_REQUIRE(((uintptr_t)ring_obs % 16 == 0) && ((uintptr_t)obs_out % 16 == 0), DRM_ERR_ALIGN, "drm_replay_gather: 16-byte alignment required");
   if (B == 0) return DRM_OK;
@@ -333,9 +334,9 @@ extern "C" int drm_replay_insert(uint8_t* ring_obs, float* ring_act, float* ring
 extern "C" int drm_lambda_return(const float* rew, const float* cont, const float* value, float* out, int32_t B, int32_t H,
                                  float gamma, float lambda_, void* stream) {
   if (int rc = check_arch()) return rc;
-  DRM_REQUIRE(rew && cont && value && out, DRM_ERR_ARG, "drm_lambda_return: NULL pointer");
   DRM_REQUIRE(B >= 0 && H >= 1, DRM_ERR_SHAPE, "drm_lambda_return: bad shape");
   if (B == 0) return DRM_OK;
+  DRM_REQUIRE(rew && cont && value && out, DRM_ERR_ARG, "drm_lambda_return: NULL pointer");
   lambda_return_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(rew, cont, value, out, B, H, gamma, lambda_);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -344,9 +345,9 @@ extern "C" int drm_lambda_return(const float* rew, const float* cont, const floa
 extern "C" int drm_twohot_ce(const float* logits, const float* value, const float* buckets, float* ll, int64_t N, int32_t NB,
                              int32_t apply_symlog, void* stream) {
   if (int rc = check_arch()) return rc;
-  DRM_REQUIRE(logits && value && buckets && ll, DRM_ERR_ARG, "drm_twohot_ce: NULL pointer");
   DRM_REQUIRE(N >= 0 && NB >= 2 && NB <= 256, DRM_ERR_SHAPE, "drm_twohot_ce: NB must be in [2, 256]");
   if (N == 0) return DRM_OK;
+  DRM_REQUIRE(logits && value && buckets && ll, DRM_ERR_ARG, "drm_twohot_ce: NULL pointer");
   twohot_ce_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, value, buckets, ll, N, NB, apply_symlog);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -354,9 +355,9 @@ extern "C" int drm_twohot_ce(const float* logits, const float* value, const floa
 
 extern "C" int drm_bucket_value(const float* logits, const float* buckets, float* value, int64_t N, int32_t NB, void* stream) {
   if (int rc = check_arch()) return rc;
-  DRM_REQUIRE(logits && buckets && value, DRM_ERR_ARG, "drm_bucket_value: NULL pointer");
   DRM_REQUIRE(N >= 0 && NB >= 1 && NB <= 256, DRM_ERR_SHAPE, "drm_bucket_value: NB must be in [1, 256]");
   if (N == 0) return DRM_OK;
+  DRM_REQUIRE(logits && buckets && value, DRM_ERR_ARG, "drm_bucket_value: NULL pointer");
   bucket_value_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, buckets, value, N, NB);
   DRM_LAUNCH_CHECK();
   return DRM_OK;

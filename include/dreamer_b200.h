@@ -5,7 +5,7 @@
  * "ABI" is the Python class surface.  This header is therefore the boundary a
  * maintainer binds to when swapping the hot path: every entry point names the reference
  * function (file:line under /root/reference) whose arithmetic it replaces.  The Python mirror
- * of the reference classes (dreamer_b200/*.py) is a thin ctypes layer over exactly these calls.
+ * of the reference classes (the modules under dreamer_b200/) is a thin ctypes layer over exactly these calls.
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller, row-major contiguous unless a
@@ -49,6 +49,20 @@ const char* drm_last_error(void);
 int drm_device_check(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t drm_launch_count(void);
+/* Per-stage device timing for bench.py's roofline line: while enabled, every fused tcgen05 stage  */
+/* launch is bracketed by CUDA events on its stream.  drm_profile_read synchronises those events    */
+/* and returns the summed milliseconds and launch count of `stage` (DRM_STAGE_*), then clears it.   */
+#define DRM_STAGE_GRU 0
+#define DRM_STAGE_PRIOR_L1 1
+#define DRM_STAGE_PRIOR_L2 2
+#define DRM_STAGE_PRIOR_CAT 3
+#define DRM_STAGE_HEADS_L1 4
+#define DRM_STAGE_HEADS_L2 5
+#define DRM_STAGE_HEADS_OUT 6
+#define DRM_STAGE_OTHER 7
+#define DRM_STAGE_COUNT 8
+int drm_profile_enable(int32_t on);
+int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (2) fused 32-class categorical head                                                          */

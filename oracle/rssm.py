@@ -111,13 +111,20 @@ def interior_uniforms(p: torch.Tensor, u: torch.Tensor, margin_frac: float = 0.0
     return out.clamp(0.0, 1.0 - 1e-7)
 
 
-def categorical_st(logits: torch.Tensor, u: torch.Tensor):
+def categorical_st(logits: torch.Tensor, u: Optional[torch.Tensor]):
     """logits (..., R, C), u (..., R) in [0,1) -> (z_st, idx, p).
 
     Restates softmax -> unimix -> sample -> one_hot -> straight-through
     (DynamicsPredictors.py:33-39; VariationalAutoEncoder.py:88-98) with the inverse-CDF rule.
+    ``u=None`` draws with the stock sampler exactly as the reference does
+    (``Categorical(probs=p).sample()``); only bench.py's CPU-baseline timing uses that mode, so the
+    timed CPU work has the reference's cost structure (the sampler dominates it).
     """
     p = unimix_probs(logits)
+    if u is None:
+        idx = torch.distributions.Categorical(probs=p).sample()
+        oh = F.one_hot(idx, p.shape[-1]).float()
+        return (oh + p) - p, idx, p
     cdf = cumsum_f32(p)
     C = p.shape[-1]
     idx = (cdf <= u.unsqueeze(-1)).sum(-1).clamp(max=C - 1)
@@ -231,7 +238,7 @@ def imagine_step(sd: SD, h: torch.Tensor, z: torch.Tensor, a: torch.Tensor, u: t
     """
     h2 = gru_step(sd, z, h, a)
     logits = prior_logits(sd, h2, z.shape[-2], z.shape[-1])
-    if margin_frac > 0.0 or delta > 0.0:
+    if u is not None and (margin_frac > 0.0 or delta > 0.0):
         u = interior_uniforms(unimix_probs(logits), u, margin_frac, delta)
     z2, idx, _ = categorical_st(logits, u)
     r = reward_predict(sd, h2, z2)
@@ -243,22 +250,23 @@ def dream_episodes(sd: SD, z0: torch.Tensor, h0: torch.Tensor, uniforms: torch.T
                    margin_frac: float = 0.0, delta: float = 0.0):
     """Dreamer.dream_episodes (Dreamer.py:143-175) with host-supplied randomness.
 
-    z0 (B,1,R,C), h0 (B,1,D), uniforms (H,B,R), normals (H,B,A).
+    z0 (B,1,R,C), h0 (B,1,D), uniforms (H,B,R) or None (stock sampler, timing only), normals (H,B,A).
     Returns the reference 7-tuple (latent (B,H+1,R,C), hidden (B,H+1,D), actions, rewards,
     continues, mu, sigma) followed by extras: idx (B,H,R) int64, prior logits (B,H,R,C), and the
     uniforms actually consumed (H,B,R).
     """
-    H = uniforms.shape[0]
+    H = normals.shape[0]
     h = h0[:, 0]
     z = z0[:, 0]
     Z, Hs, A, Rw, Cn, MU, SG, IDX, LG, U = [z], [h], [], [], [], [], [], [], [], []
     for t in range(H):
         a, mu, sg = actor_act(sd, h, z, normals[t])
-        h, z, r, c, lg, idx, u = imagine_step(sd, h, z, a, uniforms[t], margin_frac, delta)
+        h, z, r, c, lg, idx, u = imagine_step(sd, h, z, a, None if uniforms is None else uniforms[t], margin_frac, delta)
         Z.append(z); Hs.append(h); A.append(a); Rw.append(r); Cn.append(c); MU.append(mu); SG.append(sg)
         IDX.append(idx); LG.append(lg); U.append(u)
     st = lambda xs: torch.stack(xs, dim=1)
-    return (st(Z), st(Hs), st(A), st(Rw), st(Cn), st(MU), st(SG), st(IDX), st(LG), torch.stack(U, 0))
+    used = None if uniforms is None else torch.stack(U, 0)
+    return (st(Z), st(Hs), st(A), st(Rw), st(Cn), st(MU), st(SG), st(IDX), st(LG), used)
 
 
 # --------------------------------------------------------------------------------------
