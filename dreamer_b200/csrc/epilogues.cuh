@@ -1,16 +1,43 @@
-// Epilogue functors for fused_gemm_kernel.  Each thread owns one accumulator row (one start
-// state / one frame), so every row-wise operation below is register-only.
+// Epilogue functors for fused_gemm_kernel.
+//
+// Thread mapping: EPI_PARTS (= 4) threads share one accumulator row (one start state / frame);
+// thread `part` owns columns [64 * part, 64 * part + 64) of the tile.  Row-wise reductions
+// (LayerNorm statistics, the bucket softmax) are done per part and combined through a small smem
+// exchange (Chan's parallel variance / log-sum-exp merge).  Per-tile constants (biases, LN affine,
+// buckets) are staged in shared memory by `stage` while the main loop runs and read back as
+// warp-wide 16-byte broadcasts.  Outputs go through a shared-memory tile (gemm.cuh: tile_put /
+// tile_copy_out) so that global stores are coalesced.
 #pragma once
 
 #include "gemm.cuh"
 
 namespace drm {
 
+constexpr int XCHG = 1024;  // float offset of the exchange scratch inside the epilogue smem
+
+// v[j] += c[j] for 32 consecutive constants (16-byte aligned) read as float4 broadcasts
+__device__ __forceinline__ void add_const32(float (&v)[32], const float* c) {
+  const float4* c4 = reinterpret_cast<const float4*>(c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = c4[j];
+    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+  }
+}
+__device__ __forceinline__ void load_const32(float (&v)[32], const float* c) {
+  const float4* c4 = reinterpret_cast<const float4*>(c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = c4[j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
-// plain: out = act(acc + bias); used by the test hook, the decoder/encoder dense layers
+// plain: out = act(acc + bias); used by the test hook and the dense encoder / decoder layers
 // ------------------------------------------------------------------------------------------
 struct EpiPlain {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
   struct Params {
     const float* bias;       // [N] or NULL
     float* out_f32;          // [M, ld_f32] or NULL
@@ -19,23 +46,31 @@ struct EpiPlain {
     int N;                   // valid output columns
     int act;                 // 0 none, 1 SiLU
   };
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, uint32_t taddr, int m, int slot) {
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
     const int n0 = slot * g.bn;
-    for (int c = 0; c < g.bn; c += 32) {
-      if (n0 + c >= p.N) break;
+    for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (p.bias && i < g.bn && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int n0 = slot * g.bn;
+    const int ncols = (g.bn + 31) & ~31;   // whole 32-column chunks are staged
+    const int pitch = ncols + 4;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int c = part * 64 + 32 * h;
+      if (c >= g.bn) break;
       float v[32];
       tmem_ld32(taddr + c, v);
-      const int nvalid = min(32, p.N - (n0 + c));
+      add_const32(v, sm + c);
+      if (p.act == 1) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = v[j] + ((p.bias && j < nvalid) ? __ldg(p.bias + n0 + c + j) : 0.f);
-        v[j] = p.act == 1 ? siluf_(x) : x;
+        for (int j = 0; j < 32; ++j) v[j] = siluf_(v[j]);
       }
-      if (m < g.M) {
-        if (p.out_f32) store_f32_row<32>(p.out_f32 + (long)m * p.ld_f32 + n0 + c, v, nvalid);
-        if (p.out_bf16) store_bf16_row<32>(p.out_bf16 + (long)m * p.ld_bf16 + n0 + c, v, nvalid);
-      }
+      tile_put<32>(tile, pitch, row, c, v);
     }
+    epi_bar_sync();
+    tile_copy_out(tile, pitch, ncols, min(g.bn, p.N - n0), (int)blockIdx.x * BM, g.M, p.out_f32 ? p.out_f32 + n0 : nullptr, p.ld_f32,
+                  p.out_bf16 ? p.out_bf16 + n0 : nullptr, p.ld_bf16, tid);
   }
 };
 
@@ -43,77 +78,129 @@ struct EpiPlain {
 // Linear + LayerNorm(eps) + SiLU -> bf16 (the hidden layers of every MLP head:
 // DynamicsPredictors.py:15-23, 52-60, 85-93; Agent.py:178-185, 219-227;
 // VariationalAutoEncoder.py:50-53, 119-122).  One tile holds the whole feature row (<= 256).
+//
+// bn (the MMA N) is the feature count rounded up to 32 with zero weight rows, and bias / gamma /
+// beta are staged as zeros beyond n_valid, so pad columns are exact zeros end to end and the inner
+// loops carry no masks: the statistics pass corrects for the pads analytically, and the
+// normalise pass yields silu(0 * t + 0) = 0 there.
 // ------------------------------------------------------------------------------------------
-struct EpiLnSilu {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0;
+template <bool HAS_ADD>
+struct EpiLnSiluT {
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
   struct Params {
     const float* bias;   // [slots * bn]
     const float* gamma;  // [slots * bn]
     const float* beta;   // [slots * bn]
-    const float* addend; // optional fp32 [M, ld_addend] added before LN (pre-computed partial product)
+    const float* addend; // HAS_ADD: fp32 [M, ld_addend] added before LN (pre-computed partial product)
     long ld_addend;
     __nv_bfloat16* out;  // rows (out_row0 + slot * out_y_stride + m), ld_out columns
     int ld_out, out_row0, out_y_stride;
     int n_valid;         // features (<= bn)
     float eps;
   };
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, uint32_t taddr, int m, int slot) {
-    const float* bias = p.bias + slot * g.bn;
-    const float* gamma = p.gamma + slot * g.bn;
-    const float* beta = p.beta + slot * g.bn;
-    const float* add = (p.addend && m < g.M) ? p.addend + (long)m * p.ld_addend : nullptr;
-    const int nch = (p.n_valid + 15) >> 4;
-    float sum = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      float v[16];
-      tmem_ld16(taddr + c * 16, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = c * 16 + j;
-        if (n < p.n_valid) sum += v[j] + __ldg(bias + n) + (add ? __ldg(add + n) : 0.f);
-      }
-    }
-    const float mean = sum / (float)p.n_valid;
-    float ss = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      float v[16];
-      tmem_ld16(taddr + c * 16, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = c * 16 + j;
-        if (n < p.n_valid) {
-          const float d = v[j] + __ldg(bias + n) + (add ? __ldg(add + n) : 0.f) - mean;
-          ss += d * d;
-        }
-      }
-    }
-    const float rstd = rsqrtf(ss / (float)p.n_valid + p.eps);
-    __nv_bfloat16* out = p.out + (long)(p.out_row0 + slot * p.out_y_stride + m) * p.ld_out;
-    for (int c = 0; c < nch; ++c) {
-      float v[16];
-      tmem_ld16(taddr + c * 16, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = c * 16 + j;
-        float y = 0.f;
-        if (n < p.n_valid) {
-          const float x = v[j] + __ldg(bias + n) + (add ? __ldg(add + n) : 0.f);
-          y = siluf_((x - mean) * rstd * __ldg(gamma + n) + __ldg(beta + n));
-        }
-        v[j] = y;
-      }
-      if (m < g.M) store_bf16_row<16>(out + c * 16, v, 16);  // pad columns inside the chunk are written as 0
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+    for (int i = tid; i < 256; i += EPI_THREADS) {
+      const bool ok = i < p.n_valid;
+      sm[i] = ok ? __ldg(p.bias + slot * g.bn + i) : 0.f;
+      sm[256 + i] = ok ? __ldg(p.gamma + slot * g.bn + i) : 0.f;
+      sm[512 + i] = ok ? __ldg(p.beta + slot * g.bn + i) : 0.f;
     }
   }
+  // x = acc + bias (+ addend) for the 32 columns starting at tile column c (pads are exact zeros)
+  static __device__ __forceinline__ void load_x32(const float* sm, uint32_t taddr, const float* add, int c, int nv, float (&v)[32]) {
+    tmem_ld32(taddr + c, v);
+    add_const32(v, sm + c);
+    if constexpr (HAS_ADD) {
+      if (add) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < nv) v[j] += __ldg(add + c + j);
+      }
+    }
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int nv = p.n_valid;
+    const int c0 = part * 64;
+    const int cnt = max(0, min(64, nv - c0));          // this part's valid columns
+    const int nld = min(64, max(0, g.bn - c0));        // columns this part loads (multiple of 32)
+    const float* add = (HAS_ADD && p.addend && m < g.M) ? p.addend + (long)m * p.ld_addend : nullptr;
+    // single statistics pass: sums of (x - shift), (x - shift)^2 with shift = the part's first column
+    float s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      if (32 * h >= nld) break;
+      float v[32];
+      load_x32(sm, taddr, add, c0 + 32 * h, nv, v);
+      if (h == 0) shift = v[0];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+    }
+    const float npad = (float)(nld - cnt);             // loaded pad columns contributed (0 - shift)
+    s1 = fmaf(npad, shift, s1);
+    s2 = fmaf(-npad * shift, shift, s2);
+    const float inv_cnt = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+    float* xs = sm + XCHG;
+    xs[part * 128 + row] = shift + s1 * inv_cnt;                       // local mean
+    xs[512 + part * 128 + row] = fmaxf(s2 - s1 * s1 * inv_cnt, 0.f);   // local M2
+    epi_bar_sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPI_PARTS; ++q) tot += xs[q * 128 + row] * (float)max(0, min(64, nv - q * 64));
+    const float mean = tot / (float)nv;
+    float M2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPI_PARTS; ++q) {
+      const float d = xs[q * 128 + row] - mean;
+      M2 += xs[512 + q * 128 + row] + d * d * (float)max(0, min(64, nv - q * 64));
+    }
+    const float rstd = rsqrtf(M2 / (float)nv + p.eps);
+    const float nmr = -mean * rstd;
+    const int ncols = min(p.ld_out, (nv + 63) & ~63);  // the consumer reads ceil64(n_valid) columns: pad with zeros
+    const int pitch = ncols + 4;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 32 * h;
+      if (c >= ncols) break;
+      float v[32];
+      if (c < g.bn) load_x32(sm, taddr, add, c, nv, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const float4* ga = reinterpret_cast<const float4*>(sm + 256 + c);
+      const float4* be = reinterpret_cast<const float4*>(sm + 512 + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 G = ga[j], Bt = be[j];
+        v[4 * j] = siluf_(fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x));
+        v[4 * j + 1] = siluf_(fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y));
+        v[4 * j + 2] = siluf_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
+        v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
+      }
+      tile_put<32>(tile, pitch, row, c, v);
+    }
+    epi_bar_sync();
+    tile_copy_out(tile, pitch, ncols, ncols, (int)blockIdx.x * BM, g.M, nullptr, 0,
+                  p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out, p.ld_out, tid);
+  }
 };
+using EpiLnSilu = EpiLnSiluT<false>;
+using EpiLnSiluAdd = EpiLnSiluT<true>;
 
 // ------------------------------------------------------------------------------------------
-// GRU gates + state update (nn.GRUCell, SequenceModel.py:13-24), U hidden units per tile.
-// TMEM columns: [r | z | n_x | n_h], each U wide.
+// GRU gates + state update (nn.GRUCell, SequenceModel.py:13-24), U hidden units per tile,
+// U / 4 units per thread.  TMEM columns: [r | z | n_x | n_h], each U wide.
 // ------------------------------------------------------------------------------------------
 template <int U>
 struct EpiGru {
-  static constexpr int B_ROWS_MAX = 3 * U, STAGES = (U == 32 ? 6 : 4), TMEM_COLS = 4 * U, GRU_U = U;
+  static constexpr int B_ROWS_MAX = 3 * U, STAGES = (U == 32 ? 3 : 4), TMEM_COLS = 4 * U, GRU_U = U;
+  static constexpr int MIN_CTAS = (U == 32 ? 2 : 1);  // U = 32: two co-resident CTAs per SM (99 KB smem, 128 TMEM columns each)
+  static constexpr int UP = U / EPI_PARTS;            // units per thread: 8 or 16
   struct Params {
     const float* b_ih;   // [3D] reference layout [r; z; n]
     const float* b_hh;   // [3D]
@@ -123,45 +210,71 @@ struct EpiGru {
     long ld_hprev, ld_hout;
     int ld_s, D;
   };
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, uint32_t taddr, int m, int slot) {
+  // sm: [b_r (U) | b_z (U) | b_in (U) | b_hn (U)] with b_r = b_ir + b_hr, b_z = b_iz + b_hz
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+    const int D = p.D;
+    for (int i = tid; i < U; i += EPI_THREADS) {
+      const int u = slot * U + i;
+      const bool ok = u < D;
+      sm[i] = ok ? __ldg(p.b_ih + u) + __ldg(p.b_hh + u) : 0.f;
+      sm[U + i] = ok ? __ldg(p.b_ih + D + u) + __ldg(p.b_hh + D + u) : 0.f;
+      sm[2 * U + i] = ok ? __ldg(p.b_ih + 2 * D + u) : 0.f;
+      sm[3 * U + i] = ok ? __ldg(p.b_hh + 2 * D + u) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+    if constexpr (UP == 8) tmem_ld8_nowait(taddr, v);
+    else tmem_ld16_nowait(taddr, *reinterpret_cast<float(*)[16]>(v));
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int c = part * UP;
     const int u0 = slot * U;
     const int D = p.D;
-    for (int c = 0; c < U; c += 16) {
-      if (u0 + c >= D) break;
-      float r[16], z[16], nx[16], nh[16];
-      tmem_ld16(taddr + c, r);
-      tmem_ld16(taddr + U + c, z);
-      tmem_ld16(taddr + 2 * U + c, nx);
-      tmem_ld16(taddr + 3 * U + c, nh);
-      const int nvalid = min(16, D - (u0 + c));
-      if (m < g.M) {
-        const float* hp = p.h_prev + (long)m * p.ld_hprev + u0 + c;
-        float hn[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          hn[j] = 0.f;
-          if (j < nvalid) {
-            const int u = u0 + c + j;
-            const float rr = sigmoidf_(r[j] + __ldg(p.b_ih + u) + __ldg(p.b_hh + u));
-            const float zz = sigmoidf_(z[j] + __ldg(p.b_ih + D + u) + __ldg(p.b_hh + D + u));
-            const float nn = tanhf(nx[j] + __ldg(p.b_ih + 2 * D + u) + rr * (nh[j] + __ldg(p.b_hh + 2 * D + u)));
-            hn[j] = (1.0f - zz) * nn + zz * __ldg(hp + j);
-          }
-        }
-        store_f32_row<16>(p.h_out + (long)m * p.ld_hout + u0 + c, hn, nvalid);
-        store_bf16_row<16>(p.s_h + (long)m * p.ld_s + u0 + c, hn, nvalid);
+    const int m0 = (int)blockIdx.x * BM;
+    constexpr int pitch = U + 4;
+    // h_prev tile [128 x U] -> smem, coalesced (consecutive threads on consecutive 16 bytes of a row)
+    float* hp_tile = tile + BM * pitch;
+    const int nvalid = min(U, D - u0);
+    for (int i = tid; i < BM * (U / 4); i += EPI_THREADS) {
+      const int r = i / (U / 4), cc = (i % (U / 4)) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < g.M && cc < nvalid) {
+        const float* src = p.h_prev + (long)(m0 + r) * p.ld_hprev + u0 + cc;
+        if (cc + 4 <= nvalid && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) x = __ldg(reinterpret_cast<const float4*>(src));
+        else { x.x = __ldg(src); if (cc + 1 < nvalid) x.y = __ldg(src + 1); if (cc + 2 < nvalid) x.z = __ldg(src + 2); if (cc + 3 < nvalid) x.w = __ldg(src + 3); }
       }
+      *reinterpret_cast<float4*>(hp_tile + r * pitch + cc) = x;
     }
+    float r_[UP], z_[UP], nx[UP], nh[UP];
+    ld(taddr + c, r_);
+    ld(taddr + U + c, z_);
+    ld(taddr + 2 * U + c, nx);
+    ld(taddr + 3 * U + c, nh);
+    epi_bar_sync();           // h_prev tile visible
+    tmem_ld_wait();
+    float hn[UP];
+#pragma unroll
+    for (int j = 0; j < UP; ++j) {
+      const float rr = sigmoidf_(r_[j] + sm[c + j]);
+      const float zz = sigmoidf_(z_[j] + sm[U + c + j]);
+      const float nn = tanhf_(nx[j] + sm[2 * U + c + j] + rr * (nh[j] + sm[3 * U + c + j]));
+      hn[j] = (1.0f - zz) * nn + zz * hp_tile[row * pitch + c + j];
+    }
+    tile_put<UP>(tile, pitch, row, c, hn);
+    epi_bar_sync();
+    tile_copy_out(tile, pitch, U, nvalid, m0, g.M, p.h_out + u0, p.ld_hout, p.s_h + u0, p.ld_s, tid);
   }
 };
 
 // ------------------------------------------------------------------------------------------
 // prior / posterior logits -> 32-class categorical (softmax, 1% unimix, inverse-CDF sample from a
 // host-supplied uniform, one-hot, straight-through).  DynamicsPredictors.py:31-40;
-// VariationalAutoEncoder.py:85-99.  A 256-column tile = 8 latent rows x 32 classes.
+// VariationalAutoEncoder.py:85-99.  A 256-column tile = 8 latent rows x 32 classes; each thread
+// owns 2 of them.
 // ------------------------------------------------------------------------------------------
 struct EpiCat {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
   struct Params {
     const float* bias;     // [R * 32]
     const float* uniforms; // [M, R] for this step, or NULL (logits only)
@@ -169,61 +282,90 @@ struct EpiCat {
     float* logits;         // fp32 [M, ld_logits] or NULL
     uint8_t* idx;          // [M, ld_idx] or NULL
     __nv_bfloat16* s_z;    // bf16 one-hot into the z columns of a state buffer [M, ld_s] or NULL
-    long ld_latent, ld_logits, ld_idx;
+    const float* addend;   // optional fp32 [M, ld_addend] added to the logits (unused by the prior)
+    long ld_latent, ld_logits, ld_idx, ld_addend;
     int ld_s, R;
   };
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, uint32_t taddr, int m, int slot) {
-    const bool live = m < g.M;
-    for (int gi = 0; gi < 8; ++gi) {
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+    for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (slot * 256 + i < p.R * 32) ? __ldg(p.bias + slot * 256 + i) : 0.f;
+    // this tile's uniforms [128 rows x 8 latent rows] -> sm[256 ..), coalesced 32-byte row segments
+    const int m0 = (int)blockIdx.x * BM;
+    for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+      const int r = i >> 3, gi = i & 7;
       const int lrow = slot * 8 + gi;
-      if (lrow >= p.R) break;
+      sm[256 + i] = (p.uniforms && m0 + r < g.M && lrow < p.R) ? __ldg(p.uniforms + (long)(m0 + r) * p.R + lrow) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int m0 = (int)blockIdx.x * BM;
+    const int ncols = min(256, p.R * 32 - slot * 256);
+    constexpr int pitch = 256 + 4;
+    uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);   // [128 rows][8] (sm[256, 1280) holds the uniforms)
+    if (p.logits) {   // pass A: logits tile out (training paths only)
+#pragma unroll 1
+      for (int gg = 0; gg < 2; ++gg) {
+        const int gi = part * 2 + gg;
+        float v[32];
+        tmem_ld32(taddr + gi * 32, v);
+        add_const32(v, sm + gi * 32);
+        tile_put<32>(tile, pitch, row, gi * 32, v);
+      }
+      epi_bar_sync();
+      tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.logits + slot * 256, p.ld_logits, nullptr, 0, tid);
+      epi_bar_sync();
+    }
+    if (p.uniforms == nullptr) return;
+#pragma unroll 1
+    for (int gg = 0; gg < 2; ++gg) {
+      const int gi = part * 2 + gg;
       float v[32];
       tmem_ld32(taddr + gi * 32, v);
-      const float* b = p.bias + lrow * 32;
+      add_const32(v, sm + gi * 32);
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] += __ldg(b + j);
-        mx = fmaxf(mx, v[j]);
-      }
-      if (live && p.logits) store_f32_row<32>(p.logits + (long)m * p.ld_logits + lrow * 32, v, 32);
-      if (p.uniforms == nullptr) continue;
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = expf(v[j] - mx);
+        v[j] = fexpf_(v[j] - mx);
         s += v[j];
       }
-      const float u = live ? __ldg(p.uniforms + (long)m * p.R + lrow) : 0.f;
+      const float u = sm[256 + row * 8 + gi];
+      const float k = 0.99f / s;
       float cdf = 0.f;
       int idx = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = 0.99f * (v[j] / s) + 0.01f * (1.0f / 32.0f);
+        v[j] = fmaf(v[j], k, 0.01f * (1.0f / 32.0f));
         cdf += v[j];
         idx += (cdf <= u) ? 1 : 0;
       }
       idx = idx > 31 ? 31 : idx;
-      if (live) {
-        if (p.idx) p.idx[(long)m * p.ld_idx + lrow] = (uint8_t)idx;
-        if (p.s_z) {
-          uint4* dst = reinterpret_cast<uint4*>(p.s_z + (long)m * p.ld_s + lrow * 32);
+      idx_sm[row * 8 + gi] = (uint8_t)idx;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            uint32_t q[4];
+      for (int j = 0; j < 32; ++j) v[j] = ((j == idx ? 1.0f : 0.0f) + v[j]) - v[j];   // (onehot + p) - p
+      tile_put<32>(tile, pitch, row, gi * 32, v);
+    }
+    epi_bar_sync();
+    if (p.latent) tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.latent + slot * 256, p.ld_latent, nullptr, 0, tid);
+    // idx [128 x 8] bytes and the bf16 one-hot [128 x 256] straight from the staged indices
+    const int ngrp = ncols >> 5;
+    if (p.idx) {
+      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+        const int r = i >> 3, gi = i & 7;
+        if (m0 + r < g.M && gi < ngrp) p.idx[(long)(m0 + r) * p.ld_idx + slot * 8 + gi] = idx_sm[i];
+      }
+    }
+    if (p.s_z) {
+      for (int i = tid; i < BM * 32; i += EPI_THREADS) {    // one uint4 (8 bf16) per item
+        const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
+        if (m0 + r >= g.M || gi >= ngrp) continue;
+        const int idx = idx_sm[r * 8 + gi];
+        uint32_t q[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = w * 8 + e * 2;
-              q[e] = (idx == j ? 0x3F80u : 0u) | (idx == j + 1 ? 0x3F800000u : 0u);
-            }
-            dst[w] = make_uint4(q[0], q[1], q[2], q[3]);
-          }
-        }
-        if (p.latent) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((j == idx ? 1.0f : 0.0f) + v[j]) - v[j];
-          store_f32_row<32>(p.latent + (long)m * p.ld_latent + lrow * 32, v, 32);
-        }
+        for (int e = 0; e < 4; ++e) q[e] = (idx == j0 + 2 * e ? 0x3F80u : 0u) | (idx == j0 + 2 * e + 1 ? 0x3F800000u : 0u);
+        *reinterpret_cast<uint4*>(p.s_z + (long)(m0 + r) * p.ld_s + slot * 256 + w * 8) = make_uint4(q[0], q[1], q[2], q[3]);
       }
     }
   }
@@ -238,7 +380,7 @@ enum HeadKind { HEAD_BUCKET = 0, HEAD_SIGMOID = 1, HEAD_ACTOR = 2 };
 constexpr int MAX_HEADS = 5;
 
 struct EpiHeads {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
   struct Params {
     const float* bias;  // [MAX_HEADS * 256]
     int kind[MAX_HEADS];
@@ -254,52 +396,80 @@ struct EpiHeads {
     __nv_bfloat16* s_a;    // bf16 action into the a columns of a state buffer [M, ld_s] or NULL
     int ld_s;
   };
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, uint32_t taddr, int m, int slot) {
-    const float* bias = p.bias + slot * 256;
+  // sm: [bias (256) | buckets (256)]
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+    const bool bucket = p.kind[slot] == HEAD_BUCKET;
+    for (int i = tid; i < 256; i += EPI_THREADS) {
+      sm[i] = __ldg(p.bias + slot * 256 + i);
+      sm[256 + i] = (bucket && i < p.NB) ? __ldg(p.buckets[slot] + i) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
     const bool live = m < g.M;
     const int kind = p.kind[slot];
+    const int m0 = (int)blockIdx.x * BM;
     if (kind == HEAD_BUCKET) {
       const int NB = p.NB;
-      const int nch = (NB + 31) >> 5;
-      float mx = -INFINITY;
-      for (int c = 0; c < nch; ++c) {
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        const int nvalid = min(32, NB - c * 32);
+      const int c0 = part * 64;
+      const int cnt = max(0, min(64, NB - c0));
+      constexpr int pitch = 256 + 4;
+      const bool want_logits = p.logits[slot] != nullptr;
+      float mx = -INFINITY, s = 0.f, ws = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {          // online (max, sum, weighted sum) over two 32-column halves
+        const int c = c0 + 32 * h;
+        const int n = cnt - 32 * h;
+        if (n <= 0) break;
+        float v[32], bk[32];
+        tmem_ld32(taddr + c, v);
+        add_const32(v, sm + c);
+        load_const32(bk, sm + 256 + c);
+        if (want_logits) tile_put<32>(tile, pitch, row, c, v);
+        float hm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hm = fmaxf(hm, j < n ? v[j] : -INFINITY);
+        const float nm = fmaxf(mx, hm);
+        const float f = mx == -INFINITY ? 0.f : fexpf_(mx - nm);
+        s *= f; ws *= f; mx = nm;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (j < nvalid) {
-            v[j] += __ldg(bias + c * 32 + j);
-            mx = fmaxf(mx, v[j]);
-          }
+          const float e = j < n ? fexpf_(v[j] - mx) : 0.f;
+          s += e;
+          ws = fmaf(e, bk[j], ws);
         }
-        if (live && p.logits[slot]) store_f32_row<32>(p.logits[slot] + (long)m * p.ld_logits[slot] + c * 32, v, nvalid);
       }
-      float s = 0.f, ws = 0.f;
-      const float* bk = p.buckets[slot];
-      for (int c = 0; c < nch; ++c) {
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        const int nvalid = min(32, NB - c * 32);
+      float* xs = sm + XCHG;
+      xs[part * 128 + row] = mx;
+      xs[512 + part * 128 + row] = s;
+      xs[1024 + part * 128 + row] = ws;
+      epi_bar_sync();
+      if (want_logits) tile_copy_out(tile, pitch, 256, NB, m0, g.M, p.logits[slot], p.ld_logits[slot], nullptr, 0, tid);
+      if (part == 0 && live && p.value[slot]) {
+        float M = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nvalid) {
-            const float e = expf(v[j] + __ldg(bias + c * 32 + j) - mx);
-            s += e;
-            ws += e * __ldg(bk + c * 32 + j);
-          }
+        for (int q = 0; q < EPI_PARTS; ++q) M = fmaxf(M, xs[q * 128 + row]);
+        float S = 0.f, WS = 0.f;
+#pragma unroll
+        for (int q = 0; q < EPI_PARTS; ++q) {
+          const float mq = xs[q * 128 + row];
+          const float f = mq == -INFINITY ? 0.f : fexpf_(mq - M);
+          S = fmaf(xs[512 + q * 128 + row], f, S);
+          WS = fmaf(xs[1024 + q * 128 + row], f, WS);
         }
+        p.value[slot][(long)m * p.ld_value[slot]] = symexpf_(WS / S);
       }
-      if (live && p.value[slot]) p.value[slot][(long)m * p.ld_value[slot]] = symexpf_(ws / s);
     } else if (kind == HEAD_SIGMOID) {
+      if (part != 0) return;
       float v[16];
       tmem_ld16(taddr, v);
-      const float x = v[0] + __ldg(bias);
+      const float x = v[0] + sm[0];
       if (live) {
-        if (p.value[slot]) p.value[slot][(long)m * p.ld_value[slot]] = sigmoidf_(x);
+        if (p.value[slot]) p.value[slot][(long)m * p.ld_value[slot]] = 1.0f / (1.0f + expf(-x));
         if (p.logits[slot]) p.logits[slot][(long)m * p.ld_value[slot]] = x;
       }
     } else {
+      if (part != 0) return;
       float v[32];
       tmem_ld32(taddr, v);
       if (live) {
@@ -309,8 +479,8 @@ struct EpiHeads {
         for (int j = 0; j < 16; ++j) {
           act[j] = 0.f;
           if (j < A) {
-            const float mu = v[j] + __ldg(bias + j);
-            float ls = v[16 + j] + __ldg(bias + 16 + j);  // log-sigma rows are packed at 16..16+A
+            const float mu = v[j] + sm[j];
+            float ls = v[16 + j] + sm[16 + j];  // log-sigma rows are packed at 16..16+A
             ls = fminf(fmaxf(ls, -5.0f), 2.0f);
             const float sg = softplusf_(ls) + 1e-3f;
             if (p.mu) p.mu[(long)m * p.ld_act + j] = mu;

@@ -6,8 +6,9 @@
 // functor that reads the accumulator with tcgen05.ld -- one thread per output row, so row-wise
 // reductions (LayerNorm, softmax, the 32-class CDF) need no shuffles.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..17 = epilogue: TMEM lane quadrant = warp_id % 4, and the four warps sharing a quadrant
+// split the tile's columns four ways (`part`), exchanging partial row statistics through smem.
 // Pipeline: STAGES-deep smem ring (full/empty mbarriers), one tmem_full barrier.
 #pragma once
 
@@ -17,7 +18,9 @@ namespace drm {
 
 constexpr int BM = 128;           // rows per CTA tile == UMMA M == TMEM lanes
 constexpr int BK = 64;            // bf16 per k-block == one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_PARTS = 4;        // epilogue threads per accumulator row
+constexpr int EPI_THREADS = 128 * EPI_PARTS;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 struct GemmCommon {
@@ -31,23 +34,42 @@ struct GemmCommon {
   int ka1, nka1;     //   consumed sequentially from 0
   int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
   int y_slot[8];
+  unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL
 };
+
+__device__ __forceinline__ void probe(const GemmCommon& g, int i) {
+  if (g.timeline && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.timeline[2 * i] = t;
+    g.timeline[2 * i + 1] = (unsigned long long)clock64();
+  }
+}
 
 template <int B_ROWS_MAX, int STAGES>
 struct GemmSmem {
   static constexpr int B_STAGE_BYTES = B_ROWS_MAX * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + 256;        // 1024 floats of per-tile constants + 2048 of row-stat exchange
+  static constexpr int TOTAL = EPI_OFF + 12288 + 1024; // barriers + epilogue scratch + alignment slack
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
 // Epi must provide:
 //   static constexpr int B_ROWS_MAX, STAGES, TMEM_COLS;  static constexpr int GRU_U (0 = plain)
 //   struct Params;
-//   static __device__ void run(const Params&, const GemmCommon&, uint32_t taddr, int m, int slot);
+//   static __device__ void stage(const Params&, const GemmCommon&, int slot, float* sm, int tid);
+//       -- the EPI_THREADS epilogue threads copy the tile's constants (biases, LN affine, buckets)
+//          into shared memory while the main loop runs
+//   static __device__ void run(const Params&, const GemmCommon&, float* sm, float* tile, uint32_t taddr, int m,
+//                              int row, int part, int slot, int tid);
+//       -- sm + 1024 = exchange scratch [.][128 rows]; `tile` = the pipeline stages' shared memory, free once the
+//          accumulator is complete, used to transpose the output tile so that global stores are fully coalesced
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_THREADS) : "memory"); }
+
 template <class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, Epi::MIN_CTAS)
 fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename Epi::Params ep) {
   using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
   constexpr int STAGES = Epi::STAGES;
@@ -65,7 +87,11 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int a_row = g.a_row0 + slot * g.a_y_stride + (int)blockIdx.x * BM;
   const int b_row = slot * g.bn;
 
+  // Programmatic dependent launch: let the next stage's CTAs start their prologue now; everything this CTA
+  // reads that an earlier stage produced (activations via TMA, h_prev) is touched only after griddep_wait().
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
+    probe(g, 0);
     tma_prefetch_desc(&g.tmA);
     tma_prefetch_desc(&g.tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -80,9 +106,11 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");  // producer / MMA warps; epilogue warps wait after staging
 
   if (warp == 0) {
     if (lane == 0) {
+      probe(g, 1);
       const uint32_t tx = A_STAGE_BYTES + (uint32_t)g.bn * BK * 2;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
@@ -94,6 +122,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         mbar_expect_tx(&full[s], tx);
         tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
         tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
+        if (kb == 0) probe(g, 2);
       }
     }
   } else if (warp == 1) {
@@ -103,6 +132,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (kb == 0) probe(g, 3);
         const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
         const uint64_t adesc = umma_desc_sw128(a_addr);
         const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
@@ -135,18 +165,74 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
       }
       umma_commit(tmem_full);    // accumulator complete
+      probe(g, 4);
     }
   } else {
+    float* epi_sm = reinterpret_cast<float*>(smem + SL::EPI_OFF);
+    Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64);   // weights-derived constants + host inputs only
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    epi_bar_sync();                                     // epilogue warps only
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    if (threadIdx.x == 64) probe(g, 5);
+    const int q = warp & 3;                             // TMEM lane quadrant this warp may access
+    const int part = (warp - 2) >> 2;                   // which quarter of the columns
     const int row = q * 32 + lane;
     const int m = (int)blockIdx.x * BM + row;
-    Epi::run(ep, g, tmem + ((uint32_t)(q * 32) << 16), m, slot);
+    Epi::run(ep, g, epi_sm, reinterpret_cast<float*>(smem), tmem + ((uint32_t)(q * 32) << 16), m, row, part, slot,
+             (int)threadIdx.x - 64);
+    if (threadIdx.x == 64) probe(g, 6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, Epi::TMEM_COLS);
+  if (threadIdx.x == 32) probe(g, 7);
+}
+
+// ------------------------------------------------------------------------------------------
+// output-tile transposition.  An epilogue thread owns (part of) one ROW of the tile; writing rows
+// straight to global memory makes every warp-level store touch 32 different lines.  Instead each
+// thread drops its values into a padded fp32 shared-memory tile (pitch = ncols + 4 floats: the 8
+// threads of a store phase hit 8 distinct 16-byte bank groups), and after a barrier all
+// EPI_THREADS threads stream the tile out with consecutive threads on consecutive 16 bytes.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tile_put(float* tile, int pitch, int row, int col, const float (&v)[N]) {
+  float4* dst = reinterpret_cast<float4*>(tile + row * pitch + col);
+#pragma unroll
+  for (int j = 0; j < N; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+// rows [0, 128) x cols [0, ncols) of `tile` -> out_f32[(m0 + r) * ld_f + c] and / or out_bf[(m0 + r) * ld_b + c]
+// for m0 + r < M and c < nvalid (ncols % 4 == 0; full float4 groups take the vector path).
+// Warp w streams rows w, w + 16, ...; its lanes walk the row 16 bytes apiece (no integer division).
+__device__ __forceinline__ void tile_copy_out(const float* tile, int pitch, int ncols, int nvalid, int m0, int M, float* out_f32,
+                                              long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid) {
+  const bool al_f = out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0) && ((ld_f & 3) == 0);
+  const bool al_b = out_bf && ((reinterpret_cast<uintptr_t>(out_bf) & 7u) == 0) && ((ld_b & 3) == 0);
+  const int lane4 = (tid & 31) << 2;
+  const int rows = min(BM, M - m0);
+  for (int r = tid >> 5; r < rows; r += EPI_THREADS / 32) {
+    const float* trow = tile + r * pitch;
+    for (int c = lane4; c < nvalid; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(trow + c);
+      const bool full = c + 4 <= nvalid;
+      if (out_f32) {
+        float* o = out_f32 + (long)(m0 + r) * ld_f + c;
+        if (full && al_f) *reinterpret_cast<float4*>(o) = x;
+        else { o[0] = x.x; if (c + 1 < nvalid) o[1] = x.y; if (c + 2 < nvalid) o[2] = x.z; if (c + 3 < nvalid) o[3] = x.w; }
+      }
+      if (out_bf) {
+        __nv_bfloat16* o = out_bf + (long)(m0 + r) * ld_b + c;
+        if (full && al_b) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+        else {
+          o[0] = __float2bfloat16_rn(x.x);
+          if (c + 1 < nvalid) o[1] = __float2bfloat16_rn(x.y);
+          if (c + 2 < nvalid) o[2] = __float2bfloat16_rn(x.z);
+          if (c + 3 < nvalid) o[3] = __float2bfloat16_rn(x.w);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -64,6 +64,9 @@ __global__ void f32_to_bf16_pad_kernel(__nv_bfloat16* __restrict__ dst, int ld_d
   }
 }
 
+// debug probe buffer: [DRM_STAGE_COUNT][16] u64 (drm_debug_timeline)
+static unsigned long long* g_timeline = nullptr;
+
 static int grid_for(long total, int threads = 256) {
   long b = (total + threads - 1) / threads;
   if (b > 148 * 16) b = 148 * 16;
@@ -79,7 +82,20 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
     attr_set = true;
   }
   profile_begin(stage, st);
-  fused_gemm_kernel<Epi><<<grid, GEMM_THREADS, SL::TOTAL, st>>>(g, ep);
+  if (g_timeline) const_cast<GemmCommon&>(g).timeline = g_timeline + 16 * stage;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = SL::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this prologue with the previous stage's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = profile_on() ? 0 : 1;
+    DRM_CUDA(cudaLaunchKernelEx(&cfg, fused_gemm_kernel<Epi>, g, ep));
+  }
   profile_end(stage, st);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -205,10 +221,10 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   m->KH = m->ZP + m->DP;      // head layer 1 consumes [z | h]
   m->U = pick_gru_u(d.D);
   m->gru_tiles = ceil_div(d.D, m->U);
-  m->bnp1 = round_up(d.h_prior[0], 16);
-  m->bnp2 = round_up(d.h_prior[1], 16);
-  m->bnh1 = round_up(d.h_head[0], 16);
-  m->bnh2 = round_up(d.h_head[1], 16);
+  m->bnp1 = round_up(d.h_prior[0], 32);   // LN tiles: MMA N rounded to 32 so pad columns are exact zeros
+  m->bnp2 = round_up(d.h_prior[1], 32);
+  m->bnh1 = round_up(d.h_head[0], 32);
+  m->bnh2 = round_up(d.h_head[1], 32);
   const int U = m->U, D = d.D, ZP = m->ZP, DP = m->DP, A = d.A, NB = d.NB;
   auto& bag = m->allocs;
   int rc = DRM_OK;
@@ -431,7 +447,7 @@ static int stage_prior(drm_rollout* r, int sb, const float* uniforms, float* lat
   {
     GemmCommon g = common(r->tmY2, m->tmWp3, M, 256);
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
-    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? r->S[sb] : nullptr, ld_latent, ld_logits, ld_idx, m->KS, m->d.R};
+    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? r->S[sb] : nullptr, nullptr, ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
@@ -618,4 +634,22 @@ extern "C" int drm_test_gemm(const float* A, const float* W, const float* bias, 
   for (void* q : bag) cudaFree(q);
   if (rc == DRM_OK && e != cudaSuccess) return fail(DRM_ERR_CUDA, std::string("drm_test_gemm: ") + cudaGetErrorString(e));
   return rc;
+}
+
+// Debug: enable (on = 1) the in-kernel probe of CTA (0,0) of every fused stage, or read the last probes back
+// (on = 0 with out != NULL: copies DRM_STAGE_COUNT * 16 u64 = {globaltimer ns, clock64} x 8 points per stage).
+extern "C" int drm_debug_timeline(int32_t on, unsigned long long* out_host) {
+  if (on) {
+    if (!g_timeline) {
+      DRM_CUDA(cudaMalloc(&g_timeline, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long)));
+      DRM_CUDA(cudaMemset(g_timeline, 0, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long)));
+    }
+    return DRM_OK;
+  }
+  if (g_timeline && out_host) {
+    DRM_CUDA(cudaDeviceSynchronize());
+    DRM_CUDA(cudaMemcpy(out_host, g_timeline, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  if (g_timeline) { cudaFree(g_timeline); g_timeline = nullptr; }
+  return DRM_OK;
 }

@@ -61,6 +61,10 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_HEADS_OUT 6
 #define DRM_STAGE_OTHER 7
 #define DRM_STAGE_COUNT 8
+/* Debug probe: with on = 1 CTA (0,0) of every fused stage records {globaltimer ns, clock64} at 8 points */
+/* (entry, setup done, first TMA issued, first operands landed, last MMA issued, accumulator ready,     */
+/* epilogue done, TMEM freed); on = 0 copies DRM_STAGE_COUNT * 16 u64 to out_host and disables it.       */
+int drm_debug_timeline(int32_t on, unsigned long long* out_host);
 int drm_profile_enable(int32_t on);
 int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches);
 
