@@ -39,6 +39,17 @@ class DrmHeadsOut(C.Structure):
                                           "value", "value_logits", "target_value")]
 
 
+class DrmVaeDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("H", "W", "e1", "e2", "d1", "d2", "h_enc", "h_dec")]
+
+
+class DrmVaeWeights(C.Structure):
+    _fields_ = ([("enc_conv_w", C.c_void_p * 4), ("enc_conv_b", C.c_void_p * 4)] +
+                [(n, C.c_void_p) for n in ("enc_l1_w", "enc_l1_b", "enc_ln_g", "enc_ln_b", "enc_l2_w", "enc_l2_b",
+                                           "dec_l1_w", "dec_l1_b", "dec_ln_g", "dec_ln_b", "dec_l2_w", "dec_l2_b")] +
+                [("dec_conv_w", C.c_void_p * 4), ("dec_conv_b", C.c_void_p * 4)])
+
+
 HEAD_REWARD, HEAD_CONT, HEAD_ACTOR, HEAD_CRITIC, HEAD_TARGET_CRITIC = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); kept in sync with include/dreamer_b200.h (tests/test_cabi.py checks
@@ -67,6 +78,16 @@ SIGNATURES = {
     "drm_gru_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, c_stream]),
     "drm_prior": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, c_stream]),
     "drm_heads": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.POINTER(DrmHeadsOut), C.c_int32, c_stream]),
+    "drm_vae_create": (C.c_int, [C.c_void_p, C.POINTER(DrmVaeDims), C.POINTER(C.c_void_p)]),
+    "drm_vae_pack": (C.c_int, [C.c_void_p, C.POINTER(DrmVaeWeights), c_stream]),
+    "drm_vae_destroy": (C.c_int, [C.c_void_p]),
+    "drm_observe_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "drm_observe_destroy": (C.c_int, [C.c_void_p]),
+    "drm_observe_scan": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 4 + [c_stream]),
+    "drm_observe_heads": (C.c_int, [C.c_void_p] * 5 + [c_stream]),
+    "drm_encoder_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, c_stream]),
+    "drm_decoder_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, c_stream]),
+    "drm_neg_sse_rows": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, c_stream]),
     "drm_test_gemm": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32, c_stream]),
 }
 

@@ -34,25 +34,29 @@ __device__ __forceinline__ void load_const32(float (&v)[32], const float* c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// plain: out = act(acc + bias); used by the test hook and the dense encoder / decoder layers
+// plain: out = act(acc + bias) with an optional output-row remap; used by the test hook, the dense
+// encoder / decoder layers and the (transposed) convolutions (VariationalAutoEncoder.py:33-42,
+// 119-137), whose GEMM rows are pixels.
 // ------------------------------------------------------------------------------------------
 struct EpiPlain {
   static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
   struct Params {
-    const float* bias;       // [N] or NULL
-    float* out_f32;          // [M, ld_f32] or NULL
-    __nv_bfloat16* out_bf16; // [M, ld_bf16] or NULL
+    const float* bias;       // [slots_or_tiles * bn] when bias_per_slot, else [N]; or NULL
+    float* out_f32;          // [rows, ld_f32] or NULL
+    __nv_bfloat16* out_bf16; // [rows, ld_bf16] or NULL
     long ld_f32, ld_bf16;
-    int N;                   // valid output columns
-    int act;                 // 0 none, 1 SiLU
+    int N;                   // valid output columns (n-tiling: tile y covers columns [y * bn, ..))
+    int act;                 // 0 none, 1 SiLU, 2 tanh
+    int phases;              // 0: blockIdx.y tiles N;  1: blockIdx.y = transposed-conv phase (all tiles write columns [0, N))
+    RowMap rm;               // output row mapping (rm.p2 is overwritten with the phase when phases = 1)
   };
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
-    const int n0 = slot * g.bn;
+    const int n0 = p.phases ? 0 : slot * g.bn;
     for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (p.bias && i < g.bn && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
   }
   static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
-    const int n0 = slot * g.bn;
+    const int n0 = p.phases ? 0 : slot * g.bn;
     const int ncols = (g.bn + 31) & ~31;   // whole 32-column chunks are staged
     const int pitch = ncols + 4;
 #pragma unroll 1
@@ -65,12 +69,17 @@ struct EpiPlain {
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = siluf_(v[j]);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
       }
       tile_put<32>(tile, pitch, row, c, v);
     }
     epi_bar_sync();
+    RowMap rm = p.rm;
+    if (p.phases) rm.p2 = slot;
     tile_copy_out(tile, pitch, ncols, min(g.bn, p.N - n0), (int)blockIdx.x * BM, g.M, p.out_f32 ? p.out_f32 + n0 : nullptr, p.ld_f32,
-                  p.out_bf16 ? p.out_bf16 + n0 : nullptr, p.ld_bf16, tid);
+                  p.out_bf16 ? p.out_bf16 + n0 : nullptr, p.ld_bf16, tid, rm);
   }
 };
 
@@ -285,6 +294,7 @@ struct EpiCat {
     const float* addend;   // optional fp32 [M, ld_addend] added to the logits (unused by the prior)
     long ld_latent, ld_logits, ld_idx, ld_addend;
     int ld_s, R;
+    RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z always uses the GEMM row
   };
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
     for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (slot * 256 + i < p.R * 32) ? __ldg(p.bias + slot * 256 + i) : 0.f;
@@ -312,7 +322,7 @@ struct EpiCat {
         tile_put<32>(tile, pitch, row, gi * 32, v);
       }
       epi_bar_sync();
-      tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.logits + slot * 256, p.ld_logits, nullptr, 0, tid);
+      tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.logits + slot * 256, p.ld_logits, nullptr, 0, tid, p.rm);
       epi_bar_sync();
     }
     if (p.uniforms == nullptr) return;
@@ -348,13 +358,13 @@ struct EpiCat {
       tile_put<32>(tile, pitch, row, gi * 32, v);
     }
     epi_bar_sync();
-    if (p.latent) tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.latent + slot * 256, p.ld_latent, nullptr, 0, tid);
+    if (p.latent) tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.latent + slot * 256, p.ld_latent, nullptr, 0, tid, p.rm);
     // idx [128 x 8] bytes and the bf16 one-hot [128 x 256] straight from the staged indices
     const int ngrp = ncols >> 5;
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
-        if (m0 + r < g.M && gi < ngrp) p.idx[(long)(m0 + r) * p.ld_idx + slot * 8 + gi] = idx_sm[i];
+        if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * 8 + gi] = idx_sm[i];
       }
     }
     if (p.s_z) {
@@ -395,6 +405,7 @@ struct EpiHeads {
     long ld_act, ld_normals;
     __nv_bfloat16* s_a;    // bf16 action into the a columns of a state buffer [M, ld_s] or NULL
     int ld_s;
+    RowMap rm;             // row mapping of the bucket / sigmoid outputs
   };
   // sm: [bias (256) | buckets (256)]
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
@@ -444,7 +455,7 @@ struct EpiHeads {
       xs[512 + part * 128 + row] = s;
       xs[1024 + part * 128 + row] = ws;
       epi_bar_sync();
-      if (want_logits) tile_copy_out(tile, pitch, 256, NB, m0, g.M, p.logits[slot], p.ld_logits[slot], nullptr, 0, tid);
+      if (want_logits) tile_copy_out(tile, pitch, 256, NB, m0, g.M, p.logits[slot], p.ld_logits[slot], nullptr, 0, tid, p.rm);
       if (part == 0 && live && p.value[slot]) {
         float M = -INFINITY;
 #pragma unroll
@@ -457,7 +468,7 @@ struct EpiHeads {
           S = fmaf(xs[512 + q * 128 + row], f, S);
           WS = fmaf(xs[1024 + q * 128 + row], f, WS);
         }
-        p.value[slot][(long)m * p.ld_value[slot]] = symexpf_(WS / S);
+        p.value[slot][map_row(p.rm, m) * p.ld_value[slot]] = symexpf_(WS / S);
       }
     } else if (kind == HEAD_SIGMOID) {
       if (part != 0) return;
@@ -465,8 +476,8 @@ struct EpiHeads {
       tmem_ld16(taddr, v);
       const float x = v[0] + sm[0];
       if (live) {
-        if (p.value[slot]) p.value[slot][(long)m * p.ld_value[slot]] = 1.0f / (1.0f + expf(-x));
-        if (p.logits[slot]) p.logits[slot][(long)m * p.ld_value[slot]] = x;
+        if (p.value[slot]) p.value[slot][map_row(p.rm, m) * p.ld_value[slot]] = 1.0f / (1.0f + expf(-x));
+        if (p.logits[slot]) p.logits[slot][map_row(p.rm, m) * p.ld_value[slot]] = x;
       }
     } else {
       if (part != 0) return;

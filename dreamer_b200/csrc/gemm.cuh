@@ -202,27 +202,49 @@ __device__ __forceinline__ void tile_put(float* tile, int pitch, int row, int co
 #pragma unroll
   for (int j = 0; j < N; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 }
-// rows [0, 128) x cols [0, ncols) of `tile` -> out_f32[(m0 + r) * ld_f + c] and / or out_bf[(m0 + r) * ld_b + c]
+// Where tile row m (the GEMM row) lands in the output: identity, time-major -> batch-major, or the
+// sub-pixel phase scatter of a stride-2 transposed convolution.
+struct RowMap {
+  int mode;        // 0: row = m;  1: m = t * B + b -> b * T + t;  2: convT phase (NHWC rows);  3: convT phase, NCHW fp32 planes
+  int p0, p1, p2;  // mode 1: B, T;  modes 2/3: Hin, Win, phase (py * 2 + px)
+};
+__device__ __forceinline__ long map_row(const RowMap& rm, int m) {
+  if (rm.mode == 0) return m;
+  if (rm.mode == 1) { const int t = m / rm.p0, b = m - t * rm.p0; return (long)b * rm.p1 + t; }
+  const int hw = rm.p0 * rm.p1;
+  const int n = m / hw, rem = m - n * hw, q = rem / rm.p1, r = rem - q * rm.p1;
+  const int oy = 2 * q + (rm.p2 >> 1), ox = 2 * r + (rm.p2 & 1);
+  if (rm.mode == 2) return (long)n * 4 * hw + (long)oy * 2 * rm.p1 + ox;
+  return (long)n * 4 * hw * 3 + (long)oy * 2 * rm.p1 + ox;   // mode 3: plane 0 of frame n (3 planes of 4 * hw each)
+}
+
+// rows [0, 128) x cols [0, ncols) of `tile` -> out_f32[row(m0 + r) * ld_f + c] and / or out_bf[row(m0 + r) * ld_b + c]
 // for m0 + r < M and c < nvalid (ncols % 4 == 0; full float4 groups take the vector path).
 // Warp w streams rows w, w + 16, ...; its lanes walk the row 16 bytes apiece (no integer division).
 __device__ __forceinline__ void tile_copy_out(const float* tile, int pitch, int ncols, int nvalid, int m0, int M, float* out_f32,
-                                              long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid) {
+                                              long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid, RowMap rm = RowMap{0, 0, 0, 0}) {
   const bool al_f = out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0) && ((ld_f & 3) == 0);
   const bool al_b = out_bf && ((reinterpret_cast<uintptr_t>(out_bf) & 7u) == 0) && ((ld_b & 3) == 0);
   const int lane4 = (tid & 31) << 2;
   const int rows = min(BM, M - m0);
   for (int r = tid >> 5; r < rows; r += EPI_THREADS / 32) {
     const float* trow = tile + r * pitch;
+    const long orow = map_row(rm, m0 + r);
+    if (rm.mode == 3) {   // NCHW fp32: column c is a whole plane apart (3 output channels)
+      const int plane = 4 * rm.p0 * rm.p1;
+      if ((tid & 31) < nvalid) out_f32[orow + (long)(tid & 31) * plane] = trow[tid & 31];
+      continue;
+    }
     for (int c = lane4; c < nvalid; c += 128) {
       const float4 x = *reinterpret_cast<const float4*>(trow + c);
       const bool full = c + 4 <= nvalid;
       if (out_f32) {
-        float* o = out_f32 + (long)(m0 + r) * ld_f + c;
+        float* o = out_f32 + orow * ld_f + c;
         if (full && al_f) *reinterpret_cast<float4*>(o) = x;
         else { o[0] = x.x; if (c + 1 < nvalid) o[1] = x.y; if (c + 2 < nvalid) o[2] = x.z; if (c + 3 < nvalid) o[3] = x.w; }
       }
       if (out_bf) {
-        __nv_bfloat16* o = out_bf + (long)(m0 + r) * ld_b + c;
+        __nv_bfloat16* o = out_bf + orow * ld_b + c;
         if (full && al_b) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
         else {
           o[0] = __float2bfloat16_rn(x.x);

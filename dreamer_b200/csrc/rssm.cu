@@ -10,7 +10,9 @@
 //       Wgru [tiles * 3U, 1088 + DP]  rows of tile j = [r | z | n] of hidden units j*U .. j*U+U-1
 //       Wp1 [bn, DP]  Wp2 [bn, 256]  Wp3 [R*C, 256]
 //       Wh1 [5 * bn, R*C + DP]  Wh2 [5 * bn, 256]  Wh3 [5 * 256, 256]
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -110,6 +112,7 @@ enum Src {
   S_MU_W = S_MLP0 + 60, S_MU_B, S_LS_W, S_LS_B, S_BK_REW, S_BK_CRIT, S_COUNT
 };
 enum { HS_REWARD = 0, HS_CONT = 1, HS_ACTOR = 2, HS_CRITIC = 3, HS_TARGET = 4 };
+enum : unsigned { HAVE_GRU = 1u << 8, HAVE_PRIOR = 1u << 9 };  // bits 0..4 = head slots
 
 struct MatOp { __nv_bfloat16* dst; int ld_dst, row0, nrows, col0, ncols, src, ld_src; int *row_map, *col_map; };
 struct VecOp { float* dst; int n, src; int* map; float fill; };
@@ -133,6 +136,7 @@ struct drm_rssm {
   std::vector<VecOp> vec_ops;
   std::vector<void*> allocs;
   bool packed, has_critic;
+  unsigned have;   // which weight groups have been packed (HAVE_* | 1 << HS_*)
 };
 
 struct drm_rollout {
@@ -214,6 +218,7 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   m->d = d;
   m->packed = false;
   m->has_critic = false;
+  m->have = 0;
   m->ZP = d.R * d.C;
   m->DP = round_up(d.D, 64);
   m->KS = m->ZP + 64 + m->DP;
@@ -346,10 +351,8 @@ extern "C" int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* strea
   }
   src[S_MU_W] = w->actor_mu_w; src[S_MU_B] = w->actor_mu_b; src[S_LS_W] = w->actor_ls_w; src[S_LS_B] = w->actor_ls_b;
   src[S_BK_REW] = w->buckets_rew; src[S_BK_CRIT] = w->buckets_crit;
-  DRM_REQUIRE(w->gru_w_ih && w->gru_w_hh && w->gru_b_ih && w->gru_b_hh, DRM_ERR_ARG, "drm_rssm_pack: GRU weights are NULL");
-  DRM_REQUIRE(w->prior.w0 && w->prior.w2 && w->reward.w0 && w->reward.w2 && w->cont.w0 && w->cont.w2 && w->actor.w0 &&
-                  w->actor_mu_w && w->actor_ls_w && w->buckets_rew,
-              DRM_ERR_ARG, "drm_rssm_pack: prior / reward / continue / actor weights are required");
+  // Any subset of the weight groups may be given (a mirrored module packs only its own slice); each stage
+  // checks that the groups it needs were packed.
   cudaStream_t st = (cudaStream_t)stream;
   for (const MatOp& op : m->mat_ops) {
     if (!src[op.src]) continue;  // optional head (critic) absent
@@ -363,7 +366,14 @@ extern "C" int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* strea
     DRM_LAUNCH_CHECK();
   }
   m->packed = true;
-  m->has_critic = w->critic.w0 != nullptr;
+  if (w->gru_w_ih && w->gru_w_hh && w->gru_b_ih && w->gru_b_hh) m->have |= HAVE_GRU;
+  if (w->prior.w0 && w->prior.w1 && w->prior.w2) m->have |= HAVE_PRIOR;
+  if (w->reward.w0 && w->reward.w2 && w->buckets_rew) m->have |= 1u << HS_REWARD;
+  if (w->cont.w0 && w->cont.w2) m->have |= 1u << HS_CONT;
+  if (w->actor.w0 && w->actor_mu_w && w->actor_ls_w) m->have |= 1u << HS_ACTOR;
+  if (w->critic.w0 && w->critic.w2 && w->buckets_crit) m->have |= 1u << HS_CRITIC;
+  if (w->target_critic.w0 && w->target_critic.w2 && w->buckets_crit) m->have |= 1u << HS_TARGET;
+  m->has_critic = (m->have >> HS_CRITIC) & 1u;
   return DRM_OK;
 }
 
@@ -409,76 +419,94 @@ static GemmCommon common(const CUtensorMap& A, const CUtensorMap& B, int M, int 
   return g;
 }
 
-// GRU: S[cur] = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into S[nxt].h)
-static int stage_gru(drm_rollout* r, int cur, int nxt, const float* h_prev, long ld_hprev, float* h_out, long ld_hout, int M,
-                     cudaStream_t st) {
-  drm_rssm* m = r->m;
-  GemmCommon g = common(r->tmS[cur], m->tmWgru, M, 3 * m->U);
+// A view of "some rows of a state buffer + the hidden-activation buffers": the rollout uses S[sb] from row 0,
+// the observe path uses one time-major buffer with a row offset per step.
+struct WsView {
+  const CUtensorMap* tmS;   // state buffer [rows, KS]
+  __nv_bfloat16* S;         // its base pointer
+  const CUtensorMap *tmY1, *tmY2;
+  __nv_bfloat16 *Y1, *Y2;   // [(MAX_HEADS + 1) * slot_rows, 256]; slot 0 = prior / encoder, 1.. = heads
+  int slot_rows;            // rows per Y slot
+  int row0;                 // first row of this view inside S and inside every Y slot
+};
+static WsView view_of(drm_rollout* r, int sb) {
+  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0};
+}
+
+// GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
+static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
+                     long ld_hout, int M, cudaStream_t st) {
+  GemmCommon g = common(*src.tmS, m->tmWgru, M, 3 * m->U);
+  g.a_row0 = src.row0;
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
   const dim3 grid(ceil_div(M, BM), m->gru_tiles);
+  __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
   if (m->U == 32) {
-    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
+    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gemm<EpiGru<32>>(g, p, grid, st, DRM_STAGE_GRU);
   }
-  EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, r->S[nxt] + m->ZP + 64, ld_hprev, ld_hout, m->KS, m->d.D};
+  EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
   return launch_gemm<EpiGru<64>>(g, p, grid, st, DRM_STAGE_GRU);
 }
 
-// prior MLP on S[sb].h -> logits -> (optional) categorical sample
-static int stage_prior(drm_rollout* r, int sb, const float* uniforms, float* latent, long ld_latent, float* logits,
-                       long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, int M, cudaStream_t st) {
-  drm_rssm* m = r->m;
+// prior MLP on the view's h columns -> logits -> (optional) categorical sample
+static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, float* latent, long ld_latent, float* logits,
+                       long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, RowMap rm, int M, cudaStream_t st) {
   const int mt = ceil_div(M, BM);
   {
-    GemmCommon g = common(r->tmS[sb], m->tmWp1, M, m->bnp1);
+    GemmCommon g = common(*v.tmS, m->tmWp1, M, m->bnp1);
+    g.a_row0 = v.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, r->Y1, 256, 0, r->Mp, m->d.h_prior[0], 1e-5f};
+    EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f};
     RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L1));
   }
   {
-    GemmCommon g = common(r->tmY1, m->tmWp2, M, m->bnp2);
+    GemmCommon g = common(*v.tmY1, m->tmWp2, M, m->bnp2);
+    g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, r->Y2, 256, 0, r->Mp, m->d.h_prior[1], 1e-5f};
+    EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, v.Y2, 256, v.row0, v.slot_rows, m->d.h_prior[1], 1e-5f};
     RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L2));
   }
   {
-    GemmCommon g = common(r->tmY2, m->tmWp3, M, 256);
+    GemmCommon g = common(*v.tmY2, m->tmWp3, M, 256);
+    g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
-    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? r->S[sb] : nullptr, nullptr, ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R};
+    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
+                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
 }
 
-// [h, z] heads on S[sb]: slots listed in `slots` (HS_*)
-static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st) {
-  drm_rssm* m = r->m;
+// [h, z] heads on the view: slots listed in `slots` (HS_*)
+static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st) {
   const int mt = ceil_div(M, BM);
   if (n_slots <= 0) return DRM_OK;
   {
-    GemmCommon g = common(r->tmS[sb], m->tmWh1, M, m->bnh1);
+    GemmCommon g = common(*v.tmS, m->tmWh1, M, m->bnh1);
+    g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = m->ZP / 64;                   // z blocks
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;      // h blocks (the action block is skipped)
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, r->Y1, 256, r->Mp, r->Mp, m->d.h_head[0], 1e-5f};
+    EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f};
     RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L1));
   }
   {
-    GemmCommon g = common(r->tmY1, m->tmWh2, M, m->bnh2);
-    g.a_row0 = r->Mp; g.a_y_stride = r->Mp;
+    GemmCommon g = common(*v.tmY1, m->tmWh2, M, m->bnh2);
+    g.a_row0 = v.slot_rows + v.row0; g.a_y_stride = v.slot_rows;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[0], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, r->Y2, 256, r->Mp, r->Mp, m->d.h_head[1], 1e-5f};
+    EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, v.Y2, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[1], 1e-5f};
     RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L2));
   }
   {
-    GemmCommon g = common(r->tmY2, m->tmWh3, M, 256);
-    g.a_row0 = r->Mp; g.a_y_stride = r->Mp;
+    GemmCommon g = common(*v.tmY2, m->tmWh3, M, 256);
+    g.a_row0 = v.slot_rows + v.row0; g.a_y_stride = v.slot_rows;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[1], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
@@ -492,11 +520,15 @@ static int stage_heads(drm_rollout* r, int sb, const int* slots, int n_slots, Ep
   return DRM_OK;
 }
 
-static int pack_state(drm_rollout* r, int sb, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
-                      long ld_copy, cudaStream_t st) {
-  pack_state_kernel<<<grid_for((long)N * ncols), 256, 0, st>>>(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy);
+static int pack_cols(__nv_bfloat16* S, int ld_s, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
+                     long ld_copy, cudaStream_t st) {
+  pack_state_kernel<<<grid_for((long)N * ncols), 256, 0, st>>>(S, ld_s, col0, src, ld_src, ncols, N, copy, ld_copy);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
+}
+static int pack_state(drm_rollout* r, int sb, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
+                      long ld_copy, cudaStream_t st) {
+  return pack_cols(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy, st);
 }
 
 }  // namespace drm
@@ -509,6 +541,8 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
               DRM_ERR_ARG, "drm_rollout_run: NULL argument");
   drm_rssm* m = r->m;
   DRM_REQUIRE(m->packed, DRM_ERR_ARG, "drm_rollout_run: weights were never packed (call drm_rssm_pack)");
+  DRM_REQUIRE((m->have & (HAVE_GRU | HAVE_PRIOR | 7u)) == (HAVE_GRU | HAVE_PRIOR | 7u), DRM_ERR_ARG,
+              "drm_rollout_run: GRU, prior, reward, continue and actor weights must all be packed");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP, A = m->d.A, R = m->d.R;
   const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D, ldA = (long)H * A;
@@ -522,13 +556,13 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
     memset(&hp, 0, sizeof(hp));
     hp.normals = normals; hp.ld_normals = A; hp.mu = mu; hp.sigma = sigma; hp.action = actions; hp.ld_act = ldA;
     hp.s_a = r->S[0] + ZP; hp.ld_s = m->KS;
-    RC(stage_heads(r, 0, actor_only, 1, hp, B, st));
+    RC(stage_heads(m, view_of(r, 0), actor_only, 1, hp, B, st));
   }
   for (int t = 0; t < H; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    RC(stage_gru(r, cur, nxt, hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st));
-    RC(stage_prior(r, nxt, uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
-                   idx ? idx + (long)t * R : nullptr, (long)H * R, true, B, st));
+    RC(stage_gru(m, view_of(r, cur), view_of(r, nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st));
+    RC(stage_prior(m, view_of(r, nxt), uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
+                   idx ? idx + (long)t * R : nullptr, (long)H * R, true, RowMap{0, 0, 0, 0}, B, st));
     EpiHeads::Params hp;
     memset(&hp, 0, sizeof(hp));
     hp.value[HS_REWARD] = rewards + t; hp.ld_value[HS_REWARD] = H;
@@ -541,7 +575,7 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
       hp.ld_act = ldA;
       hp.s_a = r->S[nxt] + ZP; hp.ld_s = m->KS;
     }
-    RC(stage_heads(r, nxt, all3, more ? 3 : 2, hp, B, st));
+    RC(stage_heads(m, view_of(r, nxt), all3, more ? 3 : 2, hp, B, st));
   }
   return DRM_OK;
 }
@@ -554,14 +588,14 @@ extern "C" int drm_gru_step(drm_rollout* r, const float* z, const float* h, cons
   RC(check_arch());
   DRM_REQUIRE(r && z && h && a && h_out, DRM_ERR_ARG, "drm_gru_step: NULL argument");
   DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_gru_step: N exceeds the workspace rows");
-  DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_gru_step: weights were never packed");
+  DRM_REQUIRE(r->m->packed && (r->m->have & HAVE_GRU), DRM_ERR_ARG, "drm_gru_step: GRU weights were never packed");
   if (N == 0) return DRM_OK;
   drm_rssm* m = r->m;
   cudaStream_t st = (cudaStream_t)stream;
   RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP, a, m->d.A, m->d.A, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
-  return stage_gru(r, 0, 1, h, m->d.D, h_out, m->d.D, N, st);
+  return stage_gru(m, view_of(r, 0), view_of(r, 1), h, m->d.D, h_out, m->d.D, N, st);
 }
 
 extern "C" int drm_prior(drm_rollout* r, const float* h, const float* uniforms, float* logits, float* z_st, uint8_t* idx,
@@ -569,12 +603,12 @@ extern "C" int drm_prior(drm_rollout* r, const float* h, const float* uniforms, 
   RC(check_arch());
   DRM_REQUIRE(r && h, DRM_ERR_ARG, "drm_prior: NULL argument");
   DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_prior: N exceeds the workspace rows");
-  DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_prior: weights were never packed");
+  DRM_REQUIRE(r->m->packed && (r->m->have & HAVE_PRIOR), DRM_ERR_ARG, "drm_prior: prior weights were never packed");
   if (N == 0) return DRM_OK;
   drm_rssm* m = r->m;
   cudaStream_t st = (cudaStream_t)stream;
   RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
-  return stage_prior(r, 0, uniforms, z_st, m->ZP, logits, m->ZP, idx, m->d.R, false, N, st);
+  return stage_prior(m, view_of(r, 0), uniforms, z_st, m->ZP, logits, m->ZP, idx, m->d.R, false, RowMap{0, 0, 0, 0}, N, st);
 }
 
 extern "C" int drm_heads(drm_rollout* r, const float* h, const float* z, const float* normals, int32_t heads,
@@ -584,8 +618,7 @@ extern "C" int drm_heads(drm_rollout* r, const float* h, const float* z, const f
   DRM_REQUIRE(N >= 0 && N <= r->B, DRM_ERR_SHAPE, "drm_heads: N exceeds the workspace rows");
   DRM_REQUIRE(r->m->packed, DRM_ERR_ARG, "drm_heads: weights were never packed");
   drm_rssm* m = r->m;
-  DRM_REQUIRE(!(heads & (DRM_HEAD_CRITIC | DRM_HEAD_TARGET_CRITIC)) || m->has_critic, DRM_ERR_ARG,
-              "drm_heads: critic requested but no critic weights were packed");
+  DRM_REQUIRE(((unsigned)heads & ~m->have & 31u) == 0, DRM_ERR_ARG, "drm_heads: a requested head's weights were never packed");
   if (N == 0) return DRM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
@@ -599,7 +632,7 @@ extern "C" int drm_heads(drm_rollout* r, const float* h, const float* z, const f
   if (heads & DRM_HEAD_ACTOR) { slots[n++] = HS_ACTOR; hp.normals = normals; hp.ld_normals = m->d.A; hp.mu = out->mu; hp.sigma = out->sigma; hp.action = out->action; hp.ld_act = m->d.A; }
   if (heads & DRM_HEAD_CRITIC) { slots[n++] = HS_CRITIC; hp.value[HS_CRITIC] = out->value; hp.ld_value[HS_CRITIC] = 1; hp.logits[HS_CRITIC] = out->value_logits; hp.ld_logits[HS_CRITIC] = NB; }
   if (heads & DRM_HEAD_TARGET_CRITIC) { slots[n++] = HS_TARGET; hp.value[HS_TARGET] = out->target_value; hp.ld_value[HS_TARGET] = 1; }
-  return stage_heads(r, 0, slots, n, hp, N, st);
+  return stage_heads(m, view_of(r, 0), slots, n, hp, N, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -627,7 +660,7 @@ extern "C" int drm_test_gemm(const float* A, const float* W, const float* bias, 
   if (rc == DRM_OK) {
     GemmCommon g = common(tA, tW, M, 256);
     g.ka0 = 0; g.nka0 = Kp / 64;
-    EpiPlain::Params p{bias, out, nullptr, (long)N, 0, N, 0};
+    EpiPlain::Params p{bias, out, nullptr, (long)N, 0, N, 0, 0, RowMap{0, 0, 0, 0}};
     rc = launch_gemm<EpiPlain>(g, p, dim3(Mp / BM, Np / 256), st);
   }
   cudaError_t e = cudaStreamSynchronize(st);
@@ -653,3 +686,5 @@ extern "C" int drm_debug_timeline(int32_t on, unsigned long long* out_host) {
   if (g_timeline) { cudaFree(g_timeline); g_timeline = nullptr; }
   return DRM_OK;
 }
+
+#include "vae.cuh"

@@ -146,7 +146,7 @@ def _mlp_struct(sd: Dict[str, torch.Tensor], prefix: Optional[str], keep: list, 
     if final:
         names += [("w2", "6.weight"), ("b2", "6.bias")]
     for field, key in names:
-        t = L.f32c(sd[f"{prefix}.{key}"])
+        t = L.f32c(sd[f"{prefix}.{key}"].detach())
         L.require_cuda(t, f"{prefix}.{key}")
         keep.append(t)
         setattr(s, field, t.data_ptr())
@@ -167,15 +167,30 @@ class PackedRssm:
         L.check(L.load().drm_rssm_create(C.byref(self.dims), C.byref(self.handle)), "rssm_create")
 
     @classmethod
-    def from_state_dict(cls, sd: Dict[str, torch.Tensor], R: int = 32, C_: int = 32):
-        D = sd["world_model.sequence_model.GRU.weight_hh"].shape[1]
-        A = sd["world_model.sequence_model.GRU.weight_ih"].shape[1] - R * C_
-        NB = sd["world_model.reward_predictor.buckets_rew"].shape[0]
-        hp = (sd["world_model.dynamics_predictor.logit_net.0.weight"].shape[0],
-              sd["world_model.dynamics_predictor.logit_net.3.weight"].shape[0])
-        heads = ["world_model.reward_predictor.logit_net", "world_model.continue_predictor.logit_generator",
-                 "agent.actor.base_net"] + (["agent.critic.value_net"] if "agent.critic.value_net.0.weight" in sd else [])
-        sizes = {(sd[f"{p}.0.weight"].shape[0], sd[f"{p}.3.weight"].shape[0]) for p in heads}
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], R: int = 32, C_: int = 32, D: Optional[int] = None, A: int = 3):
+        """Build from any subset of the reference state_dict (a full Dreamer, or one module's slice)."""
+        g = "world_model.sequence_model.GRU."
+        heads = [p for p in ("world_model.reward_predictor.logit_net", "world_model.continue_predictor.logit_generator",
+                             "agent.actor.base_net", "agent.critic.value_net", "agent.target_critic.value_net")
+                 if f"{p}.0.weight" in sd]
+        if g + "weight_hh" in sd:
+            D = sd[g + "weight_hh"].shape[1]
+            A = sd[g + "weight_ih"].shape[1] - R * C_
+        elif "world_model.dynamics_predictor.logit_net.0.weight" in sd:
+            D = sd["world_model.dynamics_predictor.logit_net.0.weight"].shape[1]
+        elif heads:
+            D = sd[f"{heads[0]}.0.weight"].shape[1] - R * C_
+        if D is None:
+            raise RuntimeError("dreamer_b200: cannot infer the GRU width D from this state_dict")
+        if "agent.actor.mu_head.weight" in sd:
+            A = sd["agent.actor.mu_head.weight"].shape[0]
+        NB = 255
+        for k in ("world_model.reward_predictor.buckets_rew", "agent.critic.buckets_crit", "agent.target_critic.buckets_crit"):
+            if k in sd:
+                NB = sd[k].shape[0]
+        pk = "world_model.dynamics_predictor.logit_net"
+        hp = (sd[f"{pk}.0.weight"].shape[0], sd[f"{pk}.3.weight"].shape[0]) if f"{pk}.0.weight" in sd else (32, 32)
+        sizes = {(sd[f"{p}.0.weight"].shape[0], sd[f"{p}.3.weight"].shape[0]) for p in heads} or {(32, 32)}
         if len(sizes) != 1:
             raise RuntimeError("dreamer_b200: reward / continue / actor / critic MLPs must share hidden sizes "
                                f"(got {sorted(sizes)}); the fused head stage batches them in one launch")
@@ -184,24 +199,34 @@ class PackedRssm:
         return obj
 
     def pack(self, sd: Dict[str, torch.Tensor]):
+        """(Re-)pack whatever weight groups `sd` contains (reference key names)."""
         keep = []
         w = L.DrmRssmWeights()
+
+        def put(field, key):
+            if key in sd:
+                t = L.f32c(sd[key].detach()); L.require_cuda(t, key); keep.append(t); setattr(w, field, t.data_ptr())
+
         g = "world_model.sequence_model.GRU."
         for field, key in (("gru_w_ih", "weight_ih"), ("gru_w_hh", "weight_hh"), ("gru_b_ih", "bias_ih"), ("gru_b_hh", "bias_hh")):
-            t = L.f32c(sd[g + key]); L.require_cuda(t, g + key); keep.append(t); setattr(w, field, t.data_ptr())
-        w.prior = _mlp_struct(sd, "world_model.dynamics_predictor.logit_net", keep)
-        w.reward = _mlp_struct(sd, "world_model.reward_predictor.logit_net", keep)
-        w.cont = _mlp_struct(sd, "world_model.continue_predictor.logit_generator", keep)
-        w.actor = _mlp_struct(sd, "agent.actor.base_net", keep, final=False)
+            put(field, g + key)
+
+        def mlp(prefix, final=True):
+            return _mlp_struct(sd, prefix if f"{prefix}.0.weight" in sd else None, keep, final)
+
+        w.prior = mlp("world_model.dynamics_predictor.logit_net")
+        w.reward = mlp("world_model.reward_predictor.logit_net")
+        w.cont = mlp("world_model.continue_predictor.logit_generator")
+        w.actor = mlp("agent.actor.base_net", final=False)
         for field, key in (("actor_mu_w", "mu_head.weight"), ("actor_mu_b", "mu_head.bias"),
                            ("actor_ls_w", "log_sig_head.weight"), ("actor_ls_b", "log_sig_head.bias")):
-            t = L.f32c(sd["agent.actor." + key]); keep.append(t); setattr(w, field, t.data_ptr())
-        has_c = "agent.critic.value_net.0.weight" in sd
-        w.critic = _mlp_struct(sd, "agent.critic.value_net" if has_c else None, keep)
-        w.target_critic = _mlp_struct(sd, "agent.target_critic.value_net" if "agent.target_critic.value_net.0.weight" in sd else None, keep)
-        t = L.f32c(sd["world_model.reward_predictor.buckets_rew"]); keep.append(t); w.buckets_rew = t.data_ptr()
-        if has_c:
-            t = L.f32c(sd["agent.critic.buckets_crit"]); keep.append(t); w.buckets_crit = t.data_ptr()
+            put(field, "agent.actor." + key)
+        w.critic = mlp("agent.critic.value_net")
+        w.target_critic = mlp("agent.target_critic.value_net")
+        put("buckets_rew", "world_model.reward_predictor.buckets_rew")
+        put("buckets_crit", "agent.critic.buckets_crit")
+        if not w.buckets_crit:
+            put("buckets_crit", "agent.target_critic.buckets_crit")
         L.check(L.load().drm_rssm_pack(self.handle, C.byref(w), L.stream()), "rssm_pack")
         self._keep = keep  # sources must stay alive until the pack kernels have run
 
@@ -313,6 +338,147 @@ class Rollout:
         try:
             if self.handle:
                 L.load().drm_rollout_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------
+# (3) VAE encoder / decoder + observe scan
+# --------------------------------------------------------------------------------------------
+def neg_sse_rows(a: torch.Tensor, b: torch.Tensor, row_dims: int = 3) -> torch.Tensor:
+    """-sum((a - b)^2) over the last `row_dims` dims (WorldModel.py:129)."""
+    L.require_cuda(a, "a")
+    x, y = L.f32c(a), L.f32c(b)
+    lead = x.shape[:-row_dims]
+    length = 1
+    for d in x.shape[-row_dims:]:
+        length *= d
+    out = torch.empty(lead, dtype=torch.float32, device=x.device)
+    L.check(L.load().drm_neg_sse_rows(L.ptr(x), L.ptr(y), L.ptr(out), out.numel(), length, L.stream()), "neg_sse_rows")
+    return out
+
+
+class PackedVae:
+    """drm_vae handle: packed Encoder / Decoder weights (reference keys world_model.encoder.*, world_model.decoder.*)."""
+
+    def __init__(self, model: PackedRssm, H: int, W: int, e1: int, e2: int, d1: int, d2: int, h_enc: int, h_dec: int):
+        self.model = model
+        self.dims = L.DrmVaeDims(H, W, e1, e2, d1, d2, h_enc, h_dec)
+        self.H, self.W = H, W
+        self.handle = C.c_void_p()
+        L.check(L.load().drm_vae_create(model.handle, C.byref(self.dims), C.byref(self.handle)), "vae_create")
+
+    @classmethod
+    def from_state_dict(cls, model: PackedRssm, sd: Dict[str, torch.Tensor], obs_hw=(64, 64)):
+        e = "world_model.encoder."
+        d = "world_model.decoder."
+        e1 = sd[e + "feature_extractor.0.weight"].shape[0]
+        e2 = sd[e + "feature_extractor.2.weight"].shape[0]
+        d2 = sd[d + "image_builder.2.weight"].shape[1]
+        d1 = sd[d + "image_builder.4.weight"].shape[1]
+        obj = cls(model, obs_hw[0], obs_hw[1], e1, e2, d1, d2, sd[e + "latent_mapper.0.weight"].shape[0],
+                  sd[d + "upscaler.0.weight"].shape[0])
+        obj.pack(sd)
+        return obj
+
+    def pack(self, sd: Dict[str, torch.Tensor]):
+        keep = []
+        w = L.DrmVaeWeights()
+
+        def dp(key):
+            t = L.f32c(sd[key].detach()); L.require_cuda(t, key); keep.append(t)
+            return t.data_ptr()
+
+        e = "world_model.encoder."
+        d = "world_model.decoder."
+        for i, k in enumerate((0, 2, 4, 6)):
+            w.enc_conv_w[i] = dp(f"{e}feature_extractor.{k}.weight"); w.enc_conv_b[i] = dp(f"{e}feature_extractor.{k}.bias")
+            w.dec_conv_w[i] = dp(f"{d}image_builder.{k}.weight"); w.dec_conv_b[i] = dp(f"{d}image_builder.{k}.bias")
+        for field, key in (("enc_l1_w", e + "latent_mapper.0.weight"), ("enc_l1_b", e + "latent_mapper.0.bias"),
+                           ("enc_ln_g", e + "latent_mapper.1.weight"), ("enc_ln_b", e + "latent_mapper.1.bias"),
+                           ("enc_l2_w", e + "latent_mapper.3.weight"), ("enc_l2_b", e + "latent_mapper.3.bias"),
+                           ("dec_l1_w", d + "upscaler.0.weight"), ("dec_l1_b", d + "upscaler.0.bias"),
+                           ("dec_ln_g", d + "upscaler.1.weight"), ("dec_ln_b", d + "upscaler.1.bias"),
+                           ("dec_l2_w", d + "upscaler.3.weight"), ("dec_l2_b", d + "upscaler.3.bias")):
+            setattr(w, field, dp(key))
+        L.check(L.load().drm_vae_pack(self.handle, C.byref(w), L.stream()), "vae_pack")
+        self._keep = keep
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().drm_vae_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+class Observe:
+    """drm_observe handle: workspace for B sequences x T steps (posterior scan, batched heads, encoder / decoder calls)."""
+
+    def __init__(self, vae: PackedVae, B: int, T: int):
+        self.vae, self.model, self.B, self.T = vae, vae.model, B, T
+        self.handle = C.c_void_p()
+        L.check(L.load().drm_observe_create(self.model.handle, vae.handle, B, T, C.byref(self.handle)), "observe_create")
+
+    def scan(self, obs, act, uniforms, warm_start: bool = False, want_logits: bool = True, want_idx: bool = True):
+        """obs (B,T,3,H,W) normalised fp32, act (B,T,A), uniforms (T,B,R) -> dict(latent (B,T,R,C), hidden (B,T,D), logits, idx)."""
+        m, B, T = self.model, self.B, self.T
+        L.require_cuda(obs, "obs")
+        o, a, u = L.f32c(obs), L.f32c(act), L.f32c(uniforms)
+        if tuple(o.shape[:2]) != (B, T) or tuple(a.shape[:2]) != (B, T) or tuple(u.shape) != (T, B, m.R):
+            raise RuntimeError(f"dreamer_b200.Observe.scan: expected obs/act with leading {(B, T)} and uniforms {(T, B, m.R)}")
+        f = dict(dtype=torch.float32, device=o.device)
+        latent = torch.empty((B, T, m.R, m.C), **f)
+        hidden = torch.empty((B, T, m.D), **f)
+        logits = torch.empty((B, T, m.R, m.C), **f) if want_logits else None
+        idx = torch.empty((B, T, m.R), dtype=torch.uint8, device=o.device) if want_idx else None
+        L.check(L.load().drm_observe_scan(self.handle, L.ptr(o), L.ptr(a), L.ptr(u), 1 if warm_start else 0, L.ptr(latent), L.ptr(hidden),
+                                          L.ptr(logits), L.ptr(idx), L.stream()), "observe_scan")
+        return dict(latent=latent, hidden=hidden, logits=logits, idx=idx)
+
+    def heads(self, prior=True, decoder=True, reward=True, cont=True):
+        """Batched heads on the states of the last scan (WorldModel.py:116-119)."""
+        m, B, T = self.model, self.B, self.T
+        dev = torch.device("cuda", torch.cuda.current_device())
+        f = dict(dtype=torch.float32, device=dev)
+        out = dict(prior_logits=torch.empty((B, T, m.R, m.C), **f) if prior else None,
+                   dec_mu=torch.empty((B, T, 3, self.vae.H, self.vae.W), **f) if decoder else None,
+                   reward_logits=torch.empty((B, T - 1, m.NB), **f) if reward and T > 1 else None,
+                   cont_logit=torch.empty((B, T - 1, 1), **f) if cont and T > 1 else None)
+        L.check(L.load().drm_observe_heads(self.handle, L.ptr(out["prior_logits"]), L.ptr(out["dec_mu"]), L.ptr(out["reward_logits"]),
+                                           L.ptr(out["cont_logit"]), L.stream()), "observe_heads")
+        return out
+
+    def encode(self, h, obs, uniforms=None):
+        """Encoder.forward / .encode: h (N,D), obs (N,3,H,W) -> dict(logits (N,R,C)[, z, idx])."""
+        m = self.model
+        N = h.shape[0]
+        hf, of = L.f32c(h), L.f32c(obs)
+        f = dict(dtype=torch.float32, device=hf.device)
+        logits = torch.empty((N, m.R, m.C), **f)
+        z = idx = u = None
+        if uniforms is not None:
+            u = L.f32c(uniforms)
+            z = torch.empty((N, m.R, m.C), **f)
+            idx = torch.empty((N, m.R), dtype=torch.uint8, device=hf.device)
+        L.check(L.load().drm_encoder_fwd(self.handle, L.ptr(hf), L.ptr(of), L.ptr(u), L.ptr(logits), L.ptr(z), L.ptr(idx), N, L.stream()),
+                "encoder_fwd")
+        return dict(logits=logits, z=z, idx=idx)
+
+    def decode(self, h, z):
+        """Decoder.forward: h (N,D), z (N,R,C) -> mu (N,3,H,W)."""
+        N = h.shape[0]
+        hf, zf = L.f32c(h), L.f32c(z).reshape(N, -1)
+        mu = torch.empty((N, 3, self.vae.H, self.vae.W), dtype=torch.float32, device=hf.device)
+        L.check(L.load().drm_decoder_fwd(self.handle, L.ptr(hf), L.ptr(zf), L.ptr(mu), N, L.stream()), "decoder_fwd")
+        return mu
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().drm_observe_destroy(self.handle)
                 self.handle = C.c_void_p()
         except Exception:
             pass

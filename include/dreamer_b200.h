@@ -193,6 +193,60 @@ typedef struct drm_heads_out {
 int drm_heads(drm_rollout* r, const float* h, const float* z, const float* normals, int32_t heads,
               const drm_heads_out* out, int32_t N, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* (3) VAE encoder / decoder + the posterior (observe) scan                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct drm_vae_dims {
+  int32_t H, W;         /* observation_dims (multiples of 16)                                     */
+  int32_t e1, e2;       /* encoder_filter_num_1/2: conv channels 3 -> e1 -> e2 -> 2 e2 -> 4 e2    */
+  int32_t d1, d2;       /* decoder_filter_num_1/2: convT channels 4 d2 -> 2 d2 -> d2 -> d1 -> 3   */
+  int32_t h_enc, h_dec; /* encoder / decoder_hidden_layer_nodes (<= 256)                          */
+} drm_vae_dims;
+
+typedef struct drm_vae_weights {
+  /* Encoder.feature_extractor.{0,2,4,6}  VariationalAutoEncoder.py:33-42: Conv2d k4 s2 p1, [co, ci, 4, 4], [co] */
+  const float* enc_conv_w[4];
+  const float* enc_conv_b[4];
+  /* Encoder.latent_mapper.{0,1,3}  :50-55: Linear(feat + D -> h_enc) input [features, h], LN, Linear(h_enc -> R*C) */
+  const float *enc_l1_w, *enc_l1_b, *enc_ln_g, *enc_ln_b, *enc_l2_w, *enc_l2_b;
+  /* Decoder.upscaler.{0,1,3}  :119-125: Linear(R*C + D -> h_dec) input [h, z], LN, Linear(h_dec -> 4 d2 * H/16 * W/16) */
+  const float *dec_l1_w, *dec_l1_b, *dec_ln_g, *dec_ln_b, *dec_l2_w, *dec_l2_b;
+  /* Decoder.image_builder.{0,2,4,6}  :128-137: ConvTranspose2d k4 s2 p1, [ci, co, 4, 4], [co] */
+  const float* dec_conv_w[4];
+  const float* dec_conv_b[4];
+} drm_vae_weights;
+
+typedef struct drm_vae drm_vae;         /* packed conv / dense weights of Encoder + Decoder */
+typedef struct drm_observe drm_observe; /* workspace for B sequences x T steps (time-major bf16 state, conv scratch) */
+
+int drm_vae_create(drm_rssm* m, const drm_vae_dims* dims, drm_vae** out);
+int drm_vae_pack(drm_vae* v, const drm_vae_weights* w, void* stream);
+int drm_vae_destroy(drm_vae* v);
+int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T, drm_observe** out);
+int drm_observe_destroy(drm_observe* o);
+
+/* The posterior scan.  mode 0 = WorldModel.unroll_model's loop  WorldModel.py:92-107 (step 0 runs a GRU  */
+/* step on the all-zero state); mode 1 = Dreamer.warm_start_generator  Dreamer.py:252-261 (frame 0 is       */
+/* encoded with h = 0 and no GRU step).  The conv stack runs once over all B*T frames (it does not depend  */
+/* on h), only GRU + the h part of latent_mapper.0 + LN + latent_mapper.3 + sampling stay in the loop.      */
+/*   obs [B, T, 3, H, W] fp32 already normalised to [-0.5, 0.5]; act [B, T, A]; uniforms [T, B, R]           */
+/*   -> latent [B, T, R*C], hidden [B, T, D], post_logits [B, T, R*C] (fp32), idx [B, T, R] u8 (NULL ok)     */
+int drm_observe_scan(drm_observe* o, const float* obs, const float* act, const float* uniforms, int32_t mode,
+                     float* latent, float* hidden, float* post_logits, uint8_t* idx, void* stream);
+/* The batched heads of WorldModel.unroll_model  WorldModel.py:116-119 on the states of the last scan:      */
+/*   prior_logits [B, T, R*C], dec_mu [B, T, 3, H, W], reward_logits [B, T-1, NB], cont_logit [B, T-1]       */
+/* (reward / continue use steps 1..T-1).  Any output may be NULL.                                           */
+int drm_observe_heads(drm_observe* o, float* prior_logits, float* dec_mu, float* reward_logits, float* cont_logit,
+                      void* stream);
+/* Encoder.forward / .encode  VariationalAutoEncoder.py:57-99 on N <= B*T rows: h [N, D], obs [N, 3, H, W]  */
+/* -> logits [N, R*C]; with uniforms [N, R] also z_st [N, R*C] and idx [N, R].                              */
+int drm_encoder_fwd(drm_observe* o, const float* h, const float* obs, const float* uniforms, float* logits, float* z_st,
+                    uint8_t* idx, int32_t N, void* stream);
+/* Decoder.forward  VariationalAutoEncoder.py:139-161: h [N, D], z [N, R*C] -> mu [N, 3, H, W] (tanh).      */
+int drm_decoder_fwd(drm_observe* o, const float* h, const float* z, float* mu, int32_t N, void* stream);
+/* -sum((a - b)^2) over each row of `len` floats: WorldModel.py:129.  a, b [rows, len] -> out [rows].       */
+int drm_neg_sse_rows(const float* a, const float* b, float* out, int64_t rows, int32_t len, void* stream);
+
 /* Test hook: plain bf16 GEMM  out[M, N] = A[M, K] * W[N, K]^T + bias  through the same TMA /      */
 /* tcgen05 main loop the fused stages use (fp32 inputs are rounded to bf16 on the device).        */
 int drm_test_gemm(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,

@@ -1,0 +1,136 @@
+"""GPU parity of the conv encoder / decoder (patch gather + tcgen05 GEMM), the posterior scan and the batched
+world-model heads against the oracle and the REFERENCE fixtures (tests/golden/observe_*.npz).
+
+bf16 operands, fp32 accumulation: tolerance 1e-2 relative (north star); decoder / SSE sums use a relative check."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rssm as O
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dreamer_b200 import ops as _ops
+    return _ops
+
+
+def _close(got, ref, atol=2e-2, rtol=1e-2, what=""):
+    got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs()
+    assert (err <= atol + rtol * ref.abs()).all(), f"{what}: max abs err {err.max().item():.4g} (ref max {ref.abs().max().item():.3g})"
+
+
+def _build(ops, cfg, seed):
+    sd = W.make_state_dict(cfg, seed=seed)
+    dsd = {k: v.to(DEV) for k, v in sd.items()}
+    model = ops.PackedRssm.from_state_dict(dsd)
+    vae = ops.PackedVae.from_state_dict(model, dsd, tuple(cfg["observation_dims"]))
+    return sd, model, vae
+
+
+CFGS = {"small": W.small_config(), "ref": dict(W.REF_CONFIG)}
+
+
+@pytest.mark.parametrize("name,N", [("small", 5), ("ref", 9), ("ref", 140)])
+def test_encoder_logits_and_decoder(ops, name, N):
+    cfg = CFGS[name]
+    sd, model, vae = _build(ops, cfg, 7)
+    ws = ops.Observe(vae, N, 1)
+    obs, _, _, _, u = W.sequence_inputs(cfg, N, 1, seed=8)
+    obs = obs[:, 0] / 255.0 - 0.5
+    _, h0, _, _ = W.rollout_inputs(cfg, N, 1, seed=9)
+    h = h0[:, 0]
+    ref_logits = O.encoder_logits(sd, h, obs)
+    got = ws.encode(h.to(DEV), obs.to(DEV))
+    _close(got["logits"], ref_logits, atol=3e-2, what="encoder logits")
+    # kernel-boundary sampling contract on the kernel's own logits
+    uu = O.interior_uniforms(O.unimix_probs(got["logits"].cpu()), u[0], 0.0, 1e-5)
+    z_ref, idx_ref, _ = O.categorical_st(got["logits"].cpu(), uu)
+    got2 = ws.encode(h.to(DEV), obs.to(DEV), uu.to(DEV))
+    assert torch.equal(got2["idx"].cpu().long(), idx_ref)
+    # decoder
+    z = z_ref
+    ref_mu = O.decoder_forward(sd, h, z, obs.shape[-2:])
+    mu = ws.decode(h.to(DEV), z.to(DEV))
+    _close(mu, ref_mu, atol=2e-2, what="decoder mu")
+
+
+def test_neg_sse_rows(ops):
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(6, 5, 3, 64, 64, generator=g) - 0.5
+    b = torch.tanh(torch.randn(6, 5, 3, 64, 64, generator=g))
+    ref = -((a - b) ** 2).sum(dim=[-3, -2, -1])
+    got = ops.neg_sse_rows(a.to(DEV), b.to(DEV)).cpu()
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("fixture", ["observe_small.npz", "observe_ref_digest.npz"])
+def test_observe_scan_and_heads_match_reference_fixture(ops, golden_dir, fixture):
+    """WorldModel.unroll_model (scan + batched heads) against the REFERENCE's own outputs."""
+    g = np.load(os.path.join(golden_dir, fixture))
+    cfg = json.loads(str(g["cfg"]))
+    B, T, seed = int(g["B"]), int(g["T"]), int(g["seed"])
+    sd, model, vae = _build(ops, cfg, seed)
+    obs, act, rew, cont, _ = W.sequence_inputs(cfg, B, T, seed=seed + 2)
+    obs_n = obs / 255.0 - 0.5
+    ws = ops.Observe(vae, B, T)
+    sc = ws.scan(obs_n.to(DEV), act.to(DEV), torch.from_numpy(g["uniforms_used"]).to(DEV))
+    assert np.array_equal(sc["idx"].cpu().numpy(), g["idx"])                         # sampled posterior indices: bit-exact
+    _close(sc["hidden"], torch.from_numpy(g["hidden"]), what="hidden")
+    _close(sc["logits"][:, 1:], torch.from_numpy(g["post_logits"]), atol=3e-2, what="posterior logits")
+    hd = ws.heads()
+    _close(hd["prior_logits"][:, 1:], torch.from_numpy(g["prior_logits"]), atol=3e-2, what="prior logits")
+    obs_ll = ops.neg_sse_rows(hd["dec_mu"], obs_n.to(DEV))[:, 1:]
+    ref_ll = torch.from_numpy(g["obs_ll"])
+    assert ((obs_ll.cpu() - ref_ll).abs() <= 1e-2 * ref_ll.abs()).all(), (obs_ll.cpu() - ref_ll).abs().max()
+    buckets = sd["world_model.reward_predictor.buckets_rew"].to(DEV)
+    rew_ll = ops.twohot_ce(hd["reward_logits"], rew[:, :T - 1].to(DEV), buckets)
+    _close(rew_ll, torch.from_numpy(g["rew_ll"]), atol=5e-2, what="reward log-likelihood")
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(hd["cont_logit"].cpu(), cont[:, :T - 1], reduction="none")
+    _close(bce, torch.from_numpy(g["cont_bce"]), what="continue BCE")
+    # KL-balance term through the fused kernel, against the fixture's masked mean
+    kl = ops.categorical32_kl(sc["logits"][:, 1:], hd["prior_logits"][:, 1:]).cpu()
+    mask = cont[:, :T - 1, 0]
+    assert abs((kl * mask).mean().item() - float(g["kl_mean"])) <= 2e-2 * max(1.0, abs(float(g["kl_mean"])))
+    # warm start (Dreamer.warm_start_generator): frame 0 encoded with h = 0 and no GRU step
+    wlen = T // 2
+    ws2 = ops.Observe(vae, B, wlen)
+    w = ws2.scan(obs_n[:, :wlen].to(DEV), act[:, :wlen].to(DEV), torch.from_numpy(g["warm_uniforms_used"]).to(DEV), warm_start=True)
+    assert np.array_equal(w["idx"][:, -1].cpu().numpy(), g["warm_idx"][:, 0])
+    _close(w["hidden"][:, -1:], torch.from_numpy(g["warm_hidden"]), what="warm-start hidden")
+    assert torch.equal(w["hidden"][:, 0].cpu(), torch.zeros(B, cfg["hidden_state_dims"]))
+
+
+def test_observe_c3_shapes_and_teacher_forced(ops):
+    """BASELINE config 3 (batch 16 x seq 64): every posterior step re-derived by the oracle from the kernel's own previous state."""
+    cfg = dict(W.REF_CONFIG, horizon=64, sequence_length=64, batch_size=16)
+    B, T = 16, 64
+    sd, model, vae = _build(ops, cfg, 0)
+    obs, act, rew, cont, u = W.sequence_inputs(cfg, B, T, seed=4321)
+    obs_n = obs / 255.0 - 0.5
+    ws = ops.Observe(vae, B, T)
+    sc = {k: (v.cpu() if v is not None else None) for k, v in ws.scan(obs_n.to(DEV), act.to(DEV), u.to(DEV)).items()}
+    mism = 0
+    for t in (0, 1, 17, 40, 63):
+        zp = sc["latent"][:, t - 1] if t > 0 else torch.zeros(B, 32, 32)
+        hp = sc["hidden"][:, t - 1] if t > 0 else torch.zeros(B, cfg["hidden_state_dims"])
+        ap = act[:, t - 1] if t > 0 else torch.zeros(B, 3)
+        z2, h2, lg, idx, _ = O.observe_step(sd, zp, hp, ap, obs_n[:, t], u[t])
+        _close(sc["hidden"][:, t], h2, what=f"hidden t={t}")
+        _close(sc["logits"][:, t], lg, atol=3e-2, what=f"posterior logits t={t}")
+        mism += (idx != sc["idx"][:, t].long()).sum().item()
+    assert mism <= 0.01 * 5 * B * 32, mism
+    hd = ws.heads(reward=False, cont=False)
+    t = 21
+    dec = O.decoder_forward(sd, sc["hidden"][:, t], sc["latent"][:, t], (64, 64))
+    _close(hd["dec_mu"][:, t], dec, what="decoder mu")
+    _close(hd["prior_logits"][:, t], O.prior_logits(sd, sc["hidden"][:, t]), atol=3e-2, what="prior logits")
