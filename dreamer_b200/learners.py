@@ -1,0 +1,291 @@
+"""WorldModel (WorldModel.py) and Agent (Agent.py) mirrors: same constructors, attributes and methods.
+
+Forward quantities (states, logits, log-likelihoods, returns, losses) come from the sm_100a kernels.
+Gradients for the two optimiser steps come from ``_tail_*`` below: a device-side torch graph over the
+same parameter containers, teacher-forced on the indices the kernels sampled.  That tail is interim
+(BPTT kernels); optimiser / clipping stay in torch by design.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .modules import (Actor, ContinuePredictor, Critic, Decoder, DynamicsPredictor, Encoder, RewardPredictor, SequenceModel,
+                      _Packed, _VaeEngine, symexp, symlog)
+
+
+class WorldModel(nn.Module):
+    def __init__(self, hidden_dims, latent_dims, observation_dims, action_dims, training_horizon, batch_size, WM_lr, WM_betas,
+                 WM_eps, beta_pred, beta_dyn, beta_rep, num_encoder_filters_1, num_encoder_filters_2, encoder_hidden_layer_nodes,
+                 num_decoder_filters_1, num_decoder_filters_2, decoder_hidden_layer_nodes, dyn_pred_hidden_num_nodes_1,
+                 dyn_pred_hidden_num_nodes_2, rew_pred_hidden_num_nodes_1, rew_pred_hidden_num_nodes_2, reward_buckets,
+                 cont_pred_hidden_num_nodes_1, cont_pred_hidden_num_nodes_2, device='cpu'):
+        super().__init__()
+        self.latent_num_rows, self.latent_num_columns = latent_dims
+        self.hidden_dims = hidden_dims
+        self.action_dims = action_dims
+        self.observation_dim_x, self.observation_dim_y = observation_dims
+        self.horizon = training_horizon
+        self.buckets = reward_buckets
+        self.beta_pred, self.beta_dyn, self.beta_rep = beta_pred, beta_dyn, beta_rep
+        self.batch_size = batch_size
+        R, C = latent_dims
+        self.encoder = Encoder(observation_dims, hidden_dims, R, C, num_encoder_filters_1, num_encoder_filters_2, encoder_hidden_layer_nodes, device=device)
+        self.sequence_model = SequenceModel(R, C, hidden_dims, action_dims, num_layers=1, device=device)
+        self.dynamics_predictor = DynamicsPredictor(R, C, hidden_dims, dyn_pred_hidden_num_nodes_1, dyn_pred_hidden_num_nodes_2, device)
+        self.reward_predictor = RewardPredictor(R, C, hidden_dims, rew_pred_hidden_num_nodes_1, rew_pred_hidden_num_nodes_2, reward_buckets, device=device)
+        self.continue_predictor = ContinuePredictor(R, C, hidden_dims, cont_pred_hidden_num_nodes_1, cont_pred_hidden_num_nodes_2, device=device)
+        self.decoder = Decoder(R, C, observation_dims, hidden_dims, num_decoder_filters_1, num_decoder_filters_2, decoder_hidden_layer_nodes, device=device)
+        self.device = device
+        self.optimiser = torch.optim.AdamW(self.parameters(), lr=WM_lr, betas=(WM_betas[0], WM_betas[1]), eps=WM_eps, weight_decay=1e-6)
+        self.scalar = torch.amp.GradScaler(enabled=False)   # kept for API compatibility: the tail runs in fp32/TF32, no loss scaling
+        object.__setattr__(self, "_actor", None)
+        object.__setattr__(self, "_engine", _VaeEngine(self._engine_sd, R, C, hidden_dims, action_dims, tuple(observation_dims)))
+        self.encoder._bind(self)
+        self.decoder._bind(self)
+        self.last = {}
+
+    # ---- engine plumbing -------------------------------------------------------------------
+    def _engine_sd(self):
+        sd = {"world_model." + k: v for k, v in self.state_dict(keep_vars=True).items()}
+        if self._actor is not None:
+            sd.update({"agent.actor." + k: v for k, v in self._actor.state_dict(keep_vars=True).items()})
+        return sd
+
+    def attach_actor(self, actor):
+        """Pack the policy next to the world model so Dreamer.dream_episodes runs as one fused rollout."""
+        if self._actor is not actor:
+            object.__setattr__(self, "_actor", actor)
+            self._engine.versions = None
+
+    # ---- WorldModel.py:72-82 ---------------------------------------------------------------
+    def imagine_step(self, hidden_state, latent_state, action, uniforms=None):
+        B = hidden_state.shape[0]
+        ws = self._engine.rollout(max(128, 1 << (B - 1).bit_length()), 1)
+        h2 = ws.gru_step(latent_state.reshape(B, -1), hidden_state.reshape(B, -1), action.reshape(B, -1))
+        if uniforms is None:
+            uniforms = torch.rand(B, self.latent_num_rows, device=h2.device)
+        pr = ws.prior(h2, uniforms.reshape(B, -1), want_logits=False)
+        hd = ws.heads(h2, pr["z"], L.HEAD_REWARD | L.HEAD_CONT)
+        return h2.unsqueeze(1), pr["z"].unsqueeze(1), hd["reward"].unsqueeze(1), hd["cont_prob"].unsqueeze(1)
+
+    def observe_step(self, last_latent, last_hidden, last_action, observation, uniforms=None):
+        hidden_state = self.sequence_model.forward(last_latent, last_hidden, last_action)
+        latent_state, latent_logits = self.encoder.encode(hidden_state, observation, uniforms)
+        return latent_state, hidden_state, latent_logits
+
+    # ---- WorldModel.py:84-146 --------------------------------------------------------------
+    def unroll_model(self, observation_sequence_batch, action_sequence_batch, reward_sequence_batch, continue_sequence_batch, uniforms=None):
+        B = continue_sequence_batch.shape[0]
+        T = self.horizon
+        obs = L.f32c(observation_sequence_batch[:, :T])
+        dev = obs.device
+        if uniforms is None:
+            uniforms = torch.rand(T, B, self.latent_num_rows, device=dev)
+        ws = self._engine.observe(B, T)
+        sc = ws.scan(obs, action_sequence_batch[:, :T], uniforms)
+        hd = ws.heads()
+        obs_ll = ops.neg_sse_rows(hd["dec_mu"], obs)
+        rew_ll = ops.twohot_ce(hd["reward_logits"], L.f32c(reward_sequence_batch[:, :T - 1]), self.reward_predictor.buckets_rew)
+        x, y = hd["cont_logit"], continue_sequence_batch[:, :T - 1]
+        cont_bce = torch.clamp(x, min=0) - x * y + torch.log1p(torch.exp(-torch.abs(x)))   # BCE-with-logits, elementwise on (B,T-1,1)
+        self.last = dict(scan=sc, heads=hd, uniforms=uniforms)
+        return hd["prior_logits"][:, 1:], sc["logits"][:, 1:], obs_ll[:, 1:], rew_ll, cont_bce
+
+    def loss_forward(self, observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms=None):
+        """The loss of WorldModel.training_step (WorldModel.py:156-188) on the kernels; returns (total, parts)."""
+        T = self.horizon
+        obs = (L.f32c(observation_sequences)[:, :T] / 255.0) - 0.5
+        prior, post, obs_ll, rew_ll, cont_ll = self.unroll_model(obs, action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T], uniforms)
+        mask = continue_sequences[:, :T - 1]
+        m1 = mask.squeeze(-1)
+        kl = ops.categorical32_kl(post, prior)                      # forward value of both KL terms (they differ only in stop-gradients)
+        kl_mean = torch.mean(kl * m1)
+        denom = mask.sum() + 1e-5
+        loss_pred = (-(obs_ll * m1).sum() - (rew_ll * mask).sum() + (cont_ll * mask).sum()) / denom
+        one = torch.ones((), device=kl_mean.device)
+        total = self.beta_pred * loss_pred + self.beta_dyn * torch.maximum(one, kl_mean) + self.beta_rep * torch.maximum(one, kl_mean)
+        return total, dict(loss_pred=loss_pred, kl_mean=kl_mean, obs_norm=obs)
+
+    # ---- WorldModel.py:148-202 -------------------------------------------------------------
+    def training_step(self, observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms=None):
+        total, parts = self.loss_forward(observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms)
+        if torch.isnan(total) or torch.isinf(total):
+            print("World Model loss is nan or inf, skipping update.")
+            return total
+        T = self.horizon
+        self.optimiser.zero_grad()
+        tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
+                                 self.last["scan"]["idx"])
+        tail.backward()
+        nn.utils.clip_grad_norm_(self.parameters(), 100.0)
+        self.optimiser.step()
+        self.last["tail_loss"] = tail.detach()
+        return total
+
+
+def _st_latent(logits, idx, C):
+    """straight-through one-hot on given indices (DynamicsPredictors.py:33-39 with the kernel's draw)"""
+    p = 0.99 * torch.softmax(logits.float(), dim=-1) + 0.01 / C
+    return F.one_hot(idx.long(), C).float() + p - p.detach()
+
+
+def _cat_kl(lp_logits, lq_logits):
+    lp = F.log_softmax(lp_logits.float(), -1)
+    lq = F.log_softmax(lq_logits.float(), -1)
+    return (lp.exp() * (lp - lq)).sum(-1).sum(-1)
+
+
+def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx):
+    """Differentiable restatement of WorldModel.training_step's loss on the kernels' sampled indices (gradients only)."""
+    B, T = obs.shape[:2]
+    R, C, D = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
+    dev = obs.device
+    feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:])).flatten(1).view(B, T, -1)
+    h = torch.zeros(B, D, device=dev)
+    z = torch.zeros(B, R * C, device=dev)
+    hs, zs, post = [], [], []
+    for t in range(T):
+        a = act[:, t - 1] if t > 0 else torch.zeros(B, wm.action_dims, device=dev)
+        h = wm.sequence_model.GRU(torch.cat([z, a], -1), h)
+        lg = wm.encoder.latent_mapper(torch.cat([feats[:, t], h], -1)).view(B, R, C)
+        z = _st_latent(lg, idx[:, t], C).reshape(B, R * C)
+        hs.append(h); zs.append(z); post.append(lg)
+    hseq, zseq, post = torch.stack(hs, 1), torch.stack(zs, 1), torch.stack(post, 1)
+    prior = wm.dynamics_predictor.logit_net(hseq).view(B, T, R, C)
+    hz = torch.cat([hseq, zseq], -1)
+    x = wm.decoder.upscaler(hz.reshape(B * T, -1)).view(B * T, wm.decoder.num_filters_start, wm.decoder.start_height, wm.decoder.start_width)
+    dec = wm.decoder.image_builder(x).view(obs.shape)
+    rl = wm.reward_predictor.logit_net(hz[:, 1:])
+    cl = wm.continue_predictor.logit_generator(hz[:, 1:])
+    mask = cont[:, :T - 1]
+    m1 = mask.squeeze(-1)
+    obs_ll = -((dec.float() - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
+    b = wm.reward_predictor.buckets_rew
+    v = rew[:, :T - 1].clamp(float(b.min()), float(b.max()))
+    lo = torch.clamp(torch.searchsorted(b, v.contiguous(), right=True) - 1, max=len(b) - 2)
+    w = (v - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+    lsm = F.log_softmax(rl, -1)
+    rew_ll = ((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)) * mask
+    cont_ll = F.binary_cross_entropy_with_logits(cl, mask, reduction='none') * mask
+    dyn = torch.mean(_cat_kl(post[:, 1:].detach(), prior[:, 1:]) * m1)
+    rep = torch.mean(_cat_kl(post[:, 1:], prior[:, 1:].detach()) * m1)
+    denom = mask.sum() + 1e-5
+    loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
+    one = torch.ones((), device=dev)
+    return wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn) + wm.beta_rep * torch.maximum(one, rep)
+
+
+class Agent(nn.Module):
+    def __init__(self, action_dim, latent_dims, hidden_state_dim, HL_A1, HL_A2, HL_C1, HL_C2, critic_buckets, A_lr, A_betas, A_eps,
+                 C_lr, C_betas, C_eps, nu, lambda_, gamma, *, device='cpu'):
+        super().__init__()
+        self.device = device
+        self.actor = Actor(action_dim, latent_dims[0], latent_dims[1], hidden_state_dim, HL_A1, HL_A2, device=device)
+        self.critic = Critic(latent_dims[0], latent_dims[1], hidden_state_dim, HL_C1, HL_C2, critic_buckets, device=device)
+        self.target_critic = copy.deepcopy(self.critic)
+        for p in self.target_critic.parameters():
+            p.requires_grad = False
+        self.nu, self.lambda_, self.gamma = nu, lambda_, gamma
+        self.buckets = critic_buckets
+        self.S = 1.0
+        self.smoothing_factor = 0.99
+        self.actor_optimiser = torch.optim.AdamW(params=self.actor.parameters(), lr=A_lr, betas=(A_betas[0], A_betas[1]), eps=A_eps, weight_decay=1e-6)
+        self.critic_optimiser = torch.optim.AdamW(params=self.critic.parameters(), lr=C_lr, betas=(C_betas[0], C_betas[1]), eps=C_eps, weight_decay=1e-6)
+        object.__setattr__(self, "_pk", _Packed(self, "agent.", latent_dims[0], latent_dims[1], hidden_state_dim, action_dim))
+        self.last = {}
+
+    def _heads(self, h, z, heads, want_logits=False):
+        B, S = h.shape[:2]
+        ws = self._pk.workspace(B * S)
+        return ws.heads(h.reshape(B * S, -1), z.reshape(B * S, -1), heads, want_logits=want_logits)
+
+    def update_S(self, lambda_returns):
+        """Agent.py:78-88 (percentiles by sort + linear interpolation, the definition torch.quantile uses)."""
+        flat = lambda_returns.detach().flatten()
+        if torch.isnan(flat).any() or torch.isinf(flat).any():
+            return
+        s, _ = torch.sort(flat)
+        n = s.numel()
+
+        def q(p):
+            pos = p * (n - 1)
+            lo = int(pos)
+            hi = min(lo + 1, n - 1)
+            return s[lo] + (s[hi] - s[lo]) * (pos - lo)
+
+        rng = torch.maximum(q(0.95) - q(0.05), torch.ones((), device=flat.device))
+        alpha = 1.0 - self.smoothing_factor
+        self.S = (1.0 - alpha) * self.S + alpha * rng
+
+    def soft_update_target(self, tau=0.02):
+        with torch.no_grad():
+            for pc, pt in zip(self.critic.parameters(), self.target_critic.parameters()):
+                pt.data.mul_(1.0 - tau)
+                pt.data.add_(tau * pc.data)
+
+    def compute_batched_R_lambda_returns(self, hidden_state_batched_seq, latent_state_batched_seq, reward_batched_seq, continue_batched_seq, seq_length):
+        """Agent.py:156-172: target-critic values on the H+1 states, then the reverse lambda scan (one kernel each)."""
+        B, H1 = hidden_state_batched_seq.shape[:2]
+        v = self._heads(hidden_state_batched_seq, latent_state_batched_seq, L.HEAD_TARGET_CRITIC)["target_value"].view(B, H1, 1)
+        return ops.lambda_return(reward_batched_seq, continue_batched_seq, v, self.gamma, self.lambda_)
+
+    def losses_forward(self, z, h, rew, cont, act, mu, sigma):
+        """Forward values of Agent.train_step (Agent.py:96-135) on the kernels."""
+        B, H1 = h.shape[:2]
+        hd = self._heads(h, z, L.HEAD_CRITIC | L.HEAD_TARGET_CRITIC, want_logits=True)
+        v_t = hd["target_value"].view(B, H1, 1)
+        v = hd["value"].view(B, H1, 1)
+        R = ops.lambda_return(rew, cont, v_t, self.gamma, self.lambda_)
+        adv = (R - v[:, :-1]).squeeze(-1)
+        logp = _tanh_normal_log_prob(act, mu, sigma)
+        self.update_S(R)
+        norm = torch.maximum(torch.as_tensor(self.S, dtype=torch.float32, device=R.device), torch.ones((), device=R.device))
+        loss_actor = torch.mean(-(logp * (adv / norm)) - self.nu * (-logp))
+        ce = -ops.twohot_ce(hd["value_logits"].view(B, H1, -1)[:, :-1], R, self.critic.buckets_crit, apply_symlog=True)
+        loss_critic = ce.mean()
+        return dict(loss_actor=loss_actor, loss_critic=loss_critic, returns=R, values=v, target_values=v_t, advantage=adv, log_prob=logp, norm=norm)
+
+    def train_step(self, z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq):
+        f = self.losses_forward(z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq)
+        la, lc = f["loss_actor"], f["loss_critic"]
+        self.last = f
+        if torch.isnan(la) or torch.isinf(la) or torch.isnan(lc) or torch.isinf(lc):
+            print("Agent loss is nan or inf, skipping update.")
+            return la, lc
+        # gradients (interim torch tail): critic CE on the kernel's returns; policy gradient through mu, sigma recomputed on the
+        # (detached) imagined states -- the through-the-world-model term (about 3 % at init) needs the BPTT kernels.
+        B, H1 = h_batch_seq.shape[:2]
+        hz = torch.cat([h_batch_seq.detach(), z_batch_seq.detach().reshape(B, H1, -1)], -1)
+        self.critic_optimiser.zero_grad()
+        lsm = F.log_softmax(self.critic.value_net(hz[:, :-1]), -1)
+        b = self.critic.buckets_crit
+        tv = symlog(f["returns"]).clamp(float(b.min()), float(b.max()))
+        lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
+        w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+        (-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).mean().backward()
+        self.actor_optimiser.zero_grad()
+        base = self.actor.base_net(hz[:, :-1])
+        mu_t = self.actor.mu_head(base)
+        sg_t = F.softplus(torch.clamp(self.actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
+        logp = _tanh_normal_log_prob(action_batch_seq.detach(), mu_t, sg_t)
+        torch.mean(-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).backward()
+        torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 100.0)
+        torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 100.0)
+        self.critic_optimiser.step()
+        self.actor_optimiser.step()
+        self.soft_update_target()
+        return la, lc
+
+
+def _tanh_normal_log_prob(a, mu, sigma):
+    """Agent.py:110-115: log-prob of the clamped action under tanh(Normal(mu, sigma)), summed over the action dim."""
+    a = torch.clamp(a, -1.0 + 1e-6, 1.0 - 1e-6)
+    y = torch.atanh(a)
+    base = -((y - mu) ** 2) / (2 * sigma ** 2) - torch.log(sigma) - 0.9189385332046727
+    return (base - 2.0 * (0.6931471805599453 - y - F.softplus(-2.0 * y))).sum(-1)

@@ -31,3 +31,14 @@ def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms, normals):
     host = [out[3].to("cpu", non_blocking=True), out[4].to("cpu", non_blocking=True)]
     torch.cuda.current_stream().synchronize()
     return dict(device=out, host=host)
+
+
+def dream_episodes_modules(world_model, agent, starting_latent_state_batch, starting_hidden_state_batch, horizon=None,
+                           uniforms=None, normals=None, generator=None):
+    """Drop-in body for ``Dreamer.dream_episodes`` (Dreamer.py:143-175) on the mirrored modules: one fused rollout instead
+    of ``horizon`` x (Actor.act -> WorldModel.imagine_step).  Returns the reference's 7-tuple."""
+    H = world_model.horizon if horizon is None else horizon
+    B = starting_hidden_state_batch.shape[0]
+    world_model.attach_actor(agent.actor)
+    ro = world_model._engine.rollout(B, H)
+    return dream_episodes(ro, starting_latent_state_batch, starting_hidden_state_batch, uniforms, normals, generator)
