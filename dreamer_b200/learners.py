@@ -14,6 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import dist as D
 from . import ops
 from .modules import (Actor, ContinuePredictor, Critic, Decoder, DynamicsPredictor, Encoder, RewardPredictor, SequenceModel,
                       _Packed, _VaeEngine, symexp, symlog)
@@ -105,24 +106,28 @@ class WorldModel(nn.Module):
         mask = continue_sequences[:, :T - 1]
         m1 = mask.squeeze(-1)
         kl = ops.categorical32_kl(post, prior)                      # forward value of both KL terms (they differ only in stop-gradients)
-        kl_mean = torch.mean(kl * m1)
-        denom = mask.sum() + 1e-5
-        loss_pred = (-(obs_ll * m1).sum() - (rew_ll * mask).sum() + (cont_ll * mask).sum()) / denom
-        one = torch.ones((), device=kl_mean.device)
-        total = self.beta_pred * loss_pred + self.beta_dyn * torch.maximum(one, kl_mean) + self.beta_rep * torch.maximum(one, kl_mean)
-        return total, dict(loss_pred=loss_pred, kl_mean=kl_mean, obs_norm=obs)
+        # per-rank sums -> one packed all-reduce -> the GLOBAL loss on every rank (a no-op for a single process)
+        local = torch.stack([(obs_ll * m1).sum(), (rew_ll * mask).sum(), (cont_ll * mask).sum(), mask.sum(), (kl * m1).sum(),
+                             torch.tensor(float(kl.numel()), device=kl.device)])
+        total, parts = D.world_model_loss_from_sums(local, (self.beta_pred, self.beta_dyn, self.beta_rep))
+        parts["obs_norm"] = obs
+        return total, parts
 
     # ---- WorldModel.py:148-202 -------------------------------------------------------------
     def training_step(self, observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms=None):
         total, parts = self.loss_forward(observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms)
-        if torch.isnan(total) or torch.isinf(total):
+        if D.any_rank_flag(bool(torch.isnan(total) or torch.isinf(total)), total.device):
             print("World Model loss is nan or inf, skipping update.")
             return total
         T = self.horizon
         self.optimiser.zero_grad()
         tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
-                                 self.last["scan"]["idx"])
+                                 self.last["scan"]["idx"], parts)
         tail.backward()
+        if D.is_dist():      # gradients of the global loss = SUM over ranks of the per-rank tails (one flat 31 MB bucket)
+            if self.__dict__.get("_bucket") is None:
+                self.__dict__["_bucket"] = D.FlatBucket(self.parameters())
+            self.__dict__["_bucket"].all_reduce()
         nn.utils.clip_grad_norm_(self.parameters(), 100.0)
         self.optimiser.step()
         self.last["tail_loss"] = tail.detach()
@@ -141,8 +146,11 @@ def _cat_kl(lp_logits, lq_logits):
     return (lp.exp() * (lp - lq)).sum(-1).sum(-1)
 
 
-def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx):
-    """Differentiable restatement of WorldModel.training_step's loss on the kernels' sampled indices (gradients only)."""
+def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx, parts=None):
+    """Differentiable restatement of WorldModel.training_step's loss on the kernels' sampled indices (gradients only).
+
+    With `parts` (the globally reduced denominators) the value is this rank's additive share of the global loss, so the
+    SUM of the per-rank gradients is the gradient of the global loss; on one process it equals the loss itself."""
     B, T = obs.shape[:2]
     R, C, D = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
     dev = obs.device
@@ -173,12 +181,21 @@ def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx):
     lsm = F.log_softmax(rl, -1)
     rew_ll = ((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)) * mask
     cont_ll = F.binary_cross_entropy_with_logits(cl, mask, reduction='none') * mask
-    dyn = torch.mean(_cat_kl(post[:, 1:].detach(), prior[:, 1:]) * m1)
-    rep = torch.mean(_cat_kl(post[:, 1:], prior[:, 1:].detach()) * m1)
-    denom = mask.sum() + 1e-5
+    dyn_sum = (_cat_kl(post[:, 1:].detach(), prior[:, 1:]) * m1).sum()
+    rep_sum = (_cat_kl(post[:, 1:], prior[:, 1:].detach()) * m1).sum()
+    if parts is None:
+        denom, n_el, kl_mean = mask.sum() + 1e-5, float(m1.numel()), None
+    else:
+        denom, n_el, kl_mean = parts["denom"], parts["n_elements"], parts["kl_mean"]
     loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
-    one = torch.ones((), device=dev)
-    return wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn) + wm.beta_rep * torch.maximum(one, rep)
+    dyn, rep = dyn_sum / n_el, rep_sum / n_el
+    if kl_mean is None:
+        one = torch.ones((), device=dev)
+        return wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn) + wm.beta_rep * torch.maximum(one, rep)
+    # free bits on the GLOBAL mean: below 1 the KL terms are the constant 1 (no gradient), above it they are linear in the sums
+    live = 1.0 if float(kl_mean) > 1.0 else 0.0
+    const = 0.0 if live else (wm.beta_dyn + wm.beta_rep) / D.world()
+    return wm.beta_pred * loss_pred + live * (wm.beta_dyn * dyn + wm.beta_rep * rep) + const
 
 
 class Agent(nn.Module):
@@ -207,7 +224,7 @@ class Agent(nn.Module):
 
     def update_S(self, lambda_returns):
         """Agent.py:78-88 (percentiles by sort + linear interpolation, the definition torch.quantile uses)."""
-        flat = lambda_returns.detach().flatten()
+        flat = D.all_gather_cat(lambda_returns.detach().flatten())     # percentiles over the GLOBAL return set
         if torch.isnan(flat).any() or torch.isinf(flat).any():
             return
         s, _ = torch.sort(flat)
@@ -246,16 +263,18 @@ class Agent(nn.Module):
         logp = _tanh_normal_log_prob(act, mu, sigma)
         self.update_S(R)
         norm = torch.maximum(torch.as_tensor(self.S, dtype=torch.float32, device=R.device), torch.ones((), device=R.device))
-        loss_actor = torch.mean(-(logp * (adv / norm)) - self.nu * (-logp))
         ce = -ops.twohot_ce(hd["value_logits"].view(B, H1, -1)[:, :-1], R, self.critic.buckets_crit, apply_symlog=True)
-        loss_critic = ce.mean()
-        return dict(loss_actor=loss_actor, loss_critic=loss_critic, returns=R, values=v, target_values=v_t, advantage=adv, log_prob=logp, norm=norm)
+        sums = D.all_reduce_sum_(torch.stack([(-(logp * (adv / norm)) - self.nu * (-logp)).sum(), ce.sum(),
+                                              torch.tensor(float(logp.numel()), device=R.device)]))
+        n_glob = sums[2]
+        return dict(loss_actor=sums[0] / n_glob, loss_critic=sums[1] / n_glob, returns=R, values=v, target_values=v_t, advantage=adv,
+                    log_prob=logp, norm=norm, n_global=n_glob)
 
     def train_step(self, z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq):
         f = self.losses_forward(z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq)
         la, lc = f["loss_actor"], f["loss_critic"]
         self.last = f
-        if torch.isnan(la) or torch.isinf(la) or torch.isnan(lc) or torch.isinf(lc):
+        if D.any_rank_flag(bool(torch.isnan(la) or torch.isinf(la) or torch.isnan(lc) or torch.isinf(lc)), la.device):
             print("Agent loss is nan or inf, skipping update.")
             return la, lc
         # gradients (interim torch tail): critic CE on the kernel's returns; policy gradient through mu, sigma recomputed on the
@@ -268,13 +287,18 @@ class Agent(nn.Module):
         tv = symlog(f["returns"]).clamp(float(b.min()), float(b.max()))
         lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
         w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
-        (-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).mean().backward()
+        ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / f["n_global"]).backward()
         self.actor_optimiser.zero_grad()
         base = self.actor.base_net(hz[:, :-1])
         mu_t = self.actor.mu_head(base)
         sg_t = F.softplus(torch.clamp(self.actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
         logp = _tanh_normal_log_prob(action_batch_seq.detach(), mu_t, sg_t)
-        torch.mean(-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).backward()
+        ((-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).sum() / f["n_global"]).backward()
+        if D.is_dist():      # SUM of per-rank shares = gradient of the global means (1.67 MB and 1.47 MB buckets)
+            if self.__dict__.get("_buckets") is None:
+                self.__dict__["_buckets"] = (D.FlatBucket(self.critic.parameters()), D.FlatBucket(self.actor.parameters()))
+            for bkt in self.__dict__["_buckets"]:
+                bkt.all_reduce()
         torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 100.0)
         torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 100.0)
         self.critic_optimiser.step()
