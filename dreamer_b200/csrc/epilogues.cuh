@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_const32(float (&v)[32], const float* c) {
 // 119-137), whose GEMM rows are pixels.
 // ------------------------------------------------------------------------------------------
 struct EpiPlain {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
   struct Params {
     const float* bias;       // [slots_or_tiles * bn] when bias_per_slot, else [N]; or NULL
     float* out_f32;          // [rows, ld_f32] or NULL
@@ -95,7 +95,7 @@ struct EpiPlain {
 // ------------------------------------------------------------------------------------------
 template <bool HAS_ADD>
 struct EpiLnSiluT {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
   struct Params {
     const float* bias;   // [slots * bn]
     const float* gamma;  // [slots * bn]
@@ -205,11 +205,14 @@ using EpiLnSiluAdd = EpiLnSiluT<true>;
 // GRU gates + state update (nn.GRUCell, SequenceModel.py:13-24), U hidden units per tile,
 // U / 4 units per thread.  TMEM columns: [r | z | n_x | n_h], each U wide.
 // ------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int CM_ = 1>
 struct EpiGru {
-  static constexpr int B_ROWS_MAX = 3 * U, STAGES = (U == 32 ? 3 : 4), TMEM_COLS = 4 * U, GRU_U = U;
-  static constexpr int MIN_CTAS = (U == 32 ? 2 : 1);  // U = 32: two co-resident CTAs per SM (99 KB smem, 128 TMEM columns each)
-  static constexpr int UP = U / EPI_PARTS;            // units per thread: 8 or 16
+  static constexpr int CLUSTER_M = CM_;   // 2: pairs of m-tiles share the weight tile through TMA multicast (opt-in experiment)
+  // Two CTAs per SM (3 x 28 KB or 2 x 40 KB of stages, 128 / 256 TMEM columns each): one CTA's epilogue and prologue overlap
+  // the other's main loop, which keeps the per-SM operand ingress -- the limiter of this stage -- busy.
+  static constexpr int B_ROWS_MAX = 3 * U, STAGES = (U == 32 ? 3 : 2), TMEM_COLS = 4 * U, GRU_U = U, MIN_CTAS = 2;
+  static constexpr int UP = 8;                          // hidden units per thread per pass
+  static constexpr int PASSES = U / (EPI_PARTS * UP);   // 1 (U = 32) or 2 (U = 64)
   struct Params {
     const float* b_ih;   // [3D] reference layout [r; z; n]
     const float* b_hh;   // [3D]
@@ -231,13 +234,8 @@ struct EpiGru {
       sm[3 * U + i] = ok ? __ldg(p.b_hh + 2 * D + u) : 0.f;
     }
   }
-  static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
-    if constexpr (UP == 8) tmem_ld8_nowait(taddr, v);
-    else tmem_ld16_nowait(taddr, *reinterpret_cast<float(*)[16]>(v));
-  }
   static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
-    const int c = part * UP;
     const int u0 = slot * U;
     const int D = p.D;
     const int m0 = (int)blockIdx.x * BM;
@@ -255,22 +253,26 @@ struct EpiGru {
       }
       *reinterpret_cast<float4*>(hp_tile + r * pitch + cc) = x;
     }
-    float r_[UP], z_[UP], nx[UP], nh[UP];
-    ld(taddr + c, r_);
-    ld(taddr + U + c, z_);
-    ld(taddr + 2 * U + c, nx);
-    ld(taddr + 3 * U + c, nh);
     epi_bar_sync();           // h_prev tile visible
-    tmem_ld_wait();
-    float hn[UP];
+#pragma unroll 1
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int c = (ps * EPI_PARTS + part) * UP;
+      float r_[UP], z_[UP], nx[UP], nh[UP];
+      tmem_ld8_nowait(taddr + c, r_);
+      tmem_ld8_nowait(taddr + U + c, z_);
+      tmem_ld8_nowait(taddr + 2 * U + c, nx);
+      tmem_ld8_nowait(taddr + 3 * U + c, nh);
+      tmem_ld_wait();
+      float hn[UP];
 #pragma unroll
-    for (int j = 0; j < UP; ++j) {
-      const float rr = sigmoidf_(r_[j] + sm[c + j]);
-      const float zz = sigmoidf_(z_[j] + sm[U + c + j]);
-      const float nn = tanhf_(nx[j] + sm[2 * U + c + j] + rr * (nh[j] + sm[3 * U + c + j]));
-      hn[j] = (1.0f - zz) * nn + zz * hp_tile[row * pitch + c + j];
+      for (int j = 0; j < UP; ++j) {
+        const float rr = sigmoidf_(r_[j] + sm[c + j]);
+        const float zz = sigmoidf_(z_[j] + sm[U + c + j]);
+        const float nn = tanhf_(nx[j] + sm[2 * U + c + j] + rr * (nh[j] + sm[3 * U + c + j]));
+        hn[j] = (1.0f - zz) * nn + zz * hp_tile[row * pitch + c + j];
+      }
+      tile_put<UP>(tile, pitch, row, c, hn);
     }
-    tile_put<UP>(tile, pitch, row, c, hn);
     epi_bar_sync();
     tile_copy_out(tile, pitch, U, nvalid, m0, g.M, p.h_out + u0, p.ld_hout, p.s_h + u0, p.ld_s, tid);
   }
@@ -283,7 +285,7 @@ struct EpiGru {
 // owns 2 of them.
 // ------------------------------------------------------------------------------------------
 struct EpiCat {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
   struct Params {
     const float* bias;     // [R * 32]
     const float* uniforms; // [M, R] for this step, or NULL (logits only)
@@ -390,7 +392,7 @@ enum HeadKind { HEAD_BUCKET = 0, HEAD_SIGMOID = 1, HEAD_ACTOR = 2 };
 constexpr int MAX_HEADS = 5;
 
 struct EpiHeads {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
   struct Params {
     const float* bias;  // [MAX_HEADS * 256]
     int kind[MAX_HEADS];

@@ -58,6 +58,9 @@ struct GemmSmem {
 
 // Epi must provide:
 //   static constexpr int B_ROWS_MAX, STAGES, TMEM_COLS;  static constexpr int GRU_U (0 = plain)
+//   static constexpr int CLUSTER_M (1 or 2).  CLUSTER_M = 2: the two CTAs of a cluster are neighbouring m-tiles of the same
+//       n-tile; each loads its own A tile and HALF of the shared B tile, multicast to both (tmB then has box rows bn / 2).
+//       A stage is refilled only after BOTH consumers released it (empty barriers count 2, released by a multicast commit).
 //   struct Params;
 //   static __device__ void stage(const Params&, const GemmCommon&, int slot, float* sm, int tid);
 //       -- the EPI_THREADS epilogue threads copy the tile's constants (biases, LN affine, buckets)
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, Epi::MIN_CTAS)
 fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename Epi::Params ep) {
   using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
   constexpr int STAGES = Epi::STAGES;
+  constexpr int CM = Epi::CLUSTER_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
@@ -96,7 +100,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     tma_prefetch_desc(&g.tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CM);
     }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
@@ -104,6 +108,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, Epi::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");  // producer / MMA warps; epilogue warps wait after staging
@@ -121,7 +126,13 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
         mbar_expect_tx(&full[s], tx);
         tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
-        tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
+        if constexpr (CM == 1) {
+          tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
+        } else {
+          const int half = g.bn >> 1;
+          const int cr = (int)cluster_ctarank();
+          tma_load_2d_mc(sb + cr * half * BK * 2, &g.tmB, kb * BK, b_row + cr * half, &full[s], (uint16_t)0x3);
+        }
         if (kb == 0) probe(g, 2);
       }
     }
@@ -162,7 +173,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
             }
           }
         }
-        umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+        if constexpr (CM == 1) umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
+        else umma_commit_mc(&empty[s], (uint16_t)0x3);   // ... in both CTAs: the peer's producer also writes into it
       }
       umma_commit(tmem_full);    // accumulator complete
       probe(g, 4);
@@ -185,6 +197,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();   // the peer may still arrive on / multicast into this CTA's shared memory
   if (warp == 1) tmem_dealloc(tmem, Epi::TMEM_COLS);
   if (threadIdx.x == 32) probe(g, 7);
 }

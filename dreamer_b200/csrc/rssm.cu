@@ -7,7 +7,7 @@
 //          the prior reads h, the [h, z] heads read z then h.  Ping-pong between steps.
 //   Y1, Y2             bf16 [6 * Mp, 256]    hidden activations; slot 0 = prior, 1.. = heads
 //   packed weights     bf16, K-major, columns permuted to the state layout, rows grouped per tile
-//       Wgru [tiles * 3U, 1088 + DP]  rows of tile j = [r | z | n] of hidden units j*U .. j*U+U-1
+//       Wgru [tiles * 3U, 1088 + DP]  rows of tile j = [r | z | n] of hidden units j*U .. j*U+U-1 (packed for U = 32 and 64)
 //       Wp1 [bn, DP]  Wp2 [bn, 256]  Wp3 [R*C, 256]
 //       Wh1 [5 * bn, R*C + DP]  Wh2 [5 * bn, 256]  Wh3 [5 * 256, 256]
 #include <algorithm>
@@ -91,11 +91,20 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = SL::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this prologue with the previous stage's tail
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (Epi::CLUSTER_M > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;               // pairs of m-tiles (TMA multicast of the weight tile)
+      attr[na].val.clusterDim.x = Epi::CLUSTER_M; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (!profile_on()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this prologue with the previous stage's tail
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = profile_on() ? 0 : 1;
+    cfg.numAttrs = na;
     DRM_CUDA(cudaLaunchKernelEx(&cfg, fused_gemm_kernel<Epi>, g, ep));
   }
   profile_end(stage, st);
@@ -124,14 +133,14 @@ using namespace drm;
 struct drm_rssm {
   drm_dims d;
   int ZP, DP, KS, KG, KH;        // state layout: z cols, padded h cols, state pitch, GRU K, head-L1 K
-  int U, gru_tiles;              // GRU units per tile
+  int gru_tiles2[2];             // GRU n-tiles for U = 32 / 64 (both layouts are packed; the launch picks by grid size)
   int bnp1, bnp2, bnh1, bnh2;    // padded hidden widths (multiples of 16)
-  __nv_bfloat16 *Wgru, *Wp1, *Wp2, *Wp3, *Wh1, *Wh2, *Wh3;
+  __nv_bfloat16 *Wgru2[2], *Wp1, *Wp2, *Wp3, *Wh1, *Wh2, *Wh3;
   float *b_ih, *b_hh;            // [3D]
   float *p1_b, *p1_g, *p1_be, *p2_b, *p2_g, *p2_be, *p3_b;
   float *h1_b, *h1_g, *h1_be, *h2_b, *h2_g, *h2_be, *h3_b;  // [5 * bn]
   float *bk_rew, *bk_crit;       // [NB]
-  CUtensorMap tmWgru, tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
+  CUtensorMap tmWgru2[2], tmWgruHalf2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
   std::vector<VecOp> vec_ops;
   std::vector<void*> allocs;
@@ -187,12 +196,12 @@ static int add_vec(drm_rssm* m, float* dst, int src, const std::vector<int>& map
   return DRM_OK;
 }
 
-static int pick_gru_u(int D) {
+static int pick_gru_u(int) {   // DRM_GRU_U=32|64 forces the GRU tile width (profiling); 0 = automatic
   if (const char* e = getenv("DRM_GRU_U")) {
     const int u = atoi(e);
     if (u == 32 || u == 64) return u;
   }
-  return D >= 1536 ? 64 : 32;
+  return 0;
 }
 
 }  // namespace drm
@@ -224,17 +233,17 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   m->KS = m->ZP + 64 + m->DP;
   m->KG = m->KS;              // GRU consumes [z | a | h]
   m->KH = m->ZP + m->DP;      // head layer 1 consumes [z | h]
-  m->U = pick_gru_u(d.D);
-  m->gru_tiles = ceil_div(d.D, m->U);
+  m->gru_tiles2[0] = ceil_div(d.D, 32);
+  m->gru_tiles2[1] = ceil_div(d.D, 64);
   m->bnp1 = round_up(d.h_prior[0], 32);   // LN tiles: MMA N rounded to 32 so pad columns are exact zeros
   m->bnp2 = round_up(d.h_prior[1], 32);
   m->bnh1 = round_up(d.h_head[0], 32);
   m->bnh2 = round_up(d.h_head[1], 32);
-  const int U = m->U, D = d.D, ZP = m->ZP, DP = m->DP, A = d.A, NB = d.NB;
+  const int D = d.D, ZP = m->ZP, DP = m->DP, A = d.A, NB = d.NB;
   auto& bag = m->allocs;
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
-  TRY(dev_alloc(bag, &m->Wgru, (size_t)m->gru_tiles * 3 * U * m->KG));
+  for (int v = 0; v < 2; ++v) TRY(dev_alloc(bag, &m->Wgru2[v], (size_t)m->gru_tiles2[v] * 3 * (32 << v) * m->KG));
   TRY(dev_alloc(bag, &m->Wp1, (size_t)m->bnp1 * DP));
   TRY(dev_alloc(bag, &m->Wp2, (size_t)m->bnp2 * 256));
   TRY(dev_alloc(bag, &m->Wp3, (size_t)ZP * 256));
@@ -252,10 +261,11 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   TRY(dev_alloc(bag, &m->bk_rew, (size_t)NB));
   TRY(dev_alloc(bag, &m->bk_crit, (size_t)NB));
 
-  // ---- GRU: rows grouped per tile [r | z | n], columns [z | a(pad 64) | h(pad DP)]
-  {
-    std::vector<int> rows((size_t)m->gru_tiles * 3 * U);
-    for (int j = 0; j < m->gru_tiles; ++j)
+  // ---- GRU: rows grouped per tile [r | z | n], columns [z | a(pad 64) | h(pad DP)]; packed for U = 32 and U = 64
+  for (int v = 0; v < 2; ++v) {
+    const int U = 32 << v, nt = m->gru_tiles2[v];
+    std::vector<int> rows((size_t)nt * 3 * U);
+    for (int j = 0; j < nt; ++j)
       for (int gte = 0; gte < 3; ++gte)
         for (int u = 0; u < U; ++u) {
           const int unit = j * U + u;
@@ -263,11 +273,11 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
         }
     std::vector<int> xcols(ZP + 64);
     for (int c = 0; c < ZP + 64; ++c) xcols[c] = c < ZP + A ? c : -1;   // reference x = [z, a]  (SequenceModel.py:21)
-    TRY(add_mat(m, m->Wgru, m->KG, 0, 0, S_GRU_WIH, ZP + A, rows, xcols));
-    TRY(add_mat(m, m->Wgru, m->KG, 0, ZP + 64, S_GRU_WHH, D, rows, iota_lim(DP, D)));
-    TRY(add_vec(m, m->b_ih, S_GRU_BIH, iota_lim(3 * D, 3 * D)));
-    TRY(add_vec(m, m->b_hh, S_GRU_BHH, iota_lim(3 * D, 3 * D)));
+    TRY(add_mat(m, m->Wgru2[v], m->KG, 0, 0, S_GRU_WIH, ZP + A, rows, xcols));
+    TRY(add_mat(m, m->Wgru2[v], m->KG, 0, ZP + 64, S_GRU_WHH, D, rows, iota_lim(DP, D)));
   }
+  TRY(add_vec(m, m->b_ih, S_GRU_BIH, iota_lim(3 * D, 3 * D)));
+  TRY(add_vec(m, m->b_hh, S_GRU_BHH, iota_lim(3 * D, 3 * D)));
   // ---- prior MLP (input h)
   {
     const int h1 = d.h_prior[0], h2 = d.h_prior[1], s = S_MLP0 + 0;
@@ -315,7 +325,11 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
     TRY(add_vec(m, m->bk_crit, S_BK_CRIT, iota_lim(NB, NB)));
   }
   // ---- TMA descriptors of the packed weights (box = {64, rows per tile})
-  TRY(make_tmap_bf16_2d(&m->tmWgru, m->Wgru, (uint64_t)m->gru_tiles * 3 * U, m->KG, m->KG, 3 * U));
+  for (int v = 0; v < 2; ++v) {
+    const int U = 32 << v;
+    TRY(make_tmap_bf16_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U));
+    TRY(make_tmap_bf16_2d(&m->tmWgruHalf2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U / 2));   // multicast halves
+  }
   TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, m->bnp1, DP, DP, m->bnp1));
   TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, m->bnp2, 256, 256, m->bnp2));
   TRY(make_tmap_bf16_2d(&m->tmWp3, m->Wp3, ZP, 256, 256, 256));
@@ -436,18 +450,30 @@ static WsView view_of(drm_rollout* r, int sb) {
 // GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
 static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
                      long ld_hout, int M, cudaStream_t st) {
-  GemmCommon g = common(*src.tmS, m->tmWgru, M, 3 * m->U);
+  // DRM_MULTICAST=1 selects the cluster variant (pairs of m-tiles, weight tile halves multicast by TMA).  Measured on B200 it
+  // is not faster: the stage is bound by per-SM shared-memory ingress, which multicast does not reduce (profiles/README.md).
+  static const bool mc = getenv("DRM_MULTICAST") != nullptr;
+  // tile width: 64 hidden units per tile once that still fills the machine twice over (more FLOPs per operand byte), else 32
+  const int mt = ceil_div(M, BM);
+  int v = (mt * m->gru_tiles2[1] >= 2 * 148) ? 1 : 0;
+  if (const int force = pick_gru_u(0)) v = force == 64 ? 1 : 0;
+  const int U = 32 << v;
+  GemmCommon g = common(*src.tmS, mc ? m->tmWgruHalf2[v] : m->tmWgru2[v], M, 3 * U);
   g.a_row0 = src.row0;
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
-  const dim3 grid(ceil_div(M, BM), m->gru_tiles);
+  const dim3 grid(mc ? round_up(mt, 2) : mt, m->gru_tiles2[v]);
   __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
-  if (m->U == 32) {
-    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
-    return launch_gemm<EpiGru<32>>(g, p, grid, st, DRM_STAGE_GRU);
+#define DRM_GRU_LAUNCH(UU, CC)                                                                              \
+  {                                                                                                         \
+    typename EpiGru<UU, CC>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D}; \
+    return launch_gemm<EpiGru<UU, CC>>(g, p, grid, st, DRM_STAGE_GRU);                                     \
   }
-  EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
-  return launch_gemm<EpiGru<64>>(g, p, grid, st, DRM_STAGE_GRU);
+  if (U == 32) {
+    if (mc) DRM_GRU_LAUNCH(32, 2) else DRM_GRU_LAUNCH(32, 1)
+  }
+  if (mc) DRM_GRU_LAUNCH(64, 2) else DRM_GRU_LAUNCH(64, 1)
+#undef DRM_GRU_LAUNCH
 }
 
 // prior MLP on the view's h columns -> logits -> (optional) categorical sample

@@ -15,8 +15,11 @@ import torch
 import torch.distributed as dist
 
 
+_FORCE_SINGLE = False   # tests flip this to evaluate the single-process (full-batch) path inside a distributed job
+
+
 def is_dist() -> bool:
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (not _FORCE_SINGLE) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def world() -> int:
