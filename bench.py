@@ -264,7 +264,7 @@ def main():
     peaks = measured_peaks()
     gru_us = stages["gru"]["us_per_launch"]
     gru_tf = fl["gru"] * B / (gru_us * 1e-6) / 1e12
-    whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12 / world
+    whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12   # per GPU (B is per rank)
     roofline = dict(bound="tensor", kernel="fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)", achieved=gru_tf, peak=peaks["bf16_burst"],
                     unit="TFLOP/s", frac=gru_tf / peaks["bf16_burst"], traffic=None, peak_source=peaks["source"] + " bf16 burst",
                     flops_per_launch=fl["gru"] * B, us_per_launch=gru_us,

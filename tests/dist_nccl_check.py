@@ -9,13 +9,15 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import torch.distributed as dist
 
 from dreamer_b200 import dist as D
 from dreamer_b200 import rollout
 from oracle import weights as W
-from tests.test_gpu_modules import _dreamer
+import test_gpu_modules as tm
+from test_gpu_modules import _dreamer
 
 
 def main():
@@ -28,7 +30,6 @@ def main():
     B, T = 8, cfg["horizon"]
     obs, act, rew, cont, u = (t.to(dev) for t in W.sequence_inputs(cfg, B, T, seed=78))
     # (1)+(2) world model
-    import tests.test_gpu_modules as tm
     tm.DEV = f"cuda:{local}"
     wm_dp, ag_dp = _dreamer(cfg, sd)
     wm_full, ag_full = _dreamer(cfg, sd)
