@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_const32(float (&v)[32], const float* c) {
 // 119-137), whose GEMM rows are pixels.
 // ------------------------------------------------------------------------------------------
 struct EpiPlain {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;       // [slots_or_tiles * bn] when bias_per_slot, else [N]; or NULL
     float* out_f32;          // [rows, ld_f32] or NULL
@@ -95,7 +95,7 @@ struct EpiPlain {
 // ------------------------------------------------------------------------------------------
 template <bool HAS_ADD>
 struct EpiLnSiluT {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;   // [slots * bn]
     const float* gamma;  // [slots * bn]
@@ -106,13 +106,14 @@ struct EpiLnSiluT {
     int ld_out, out_row0, out_y_stride;
     int n_valid;         // features (<= bn)
     float eps;
+    int cstride;         // bias / gamma / beta entries per slot
   };
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
     for (int i = tid; i < 256; i += EPI_THREADS) {
       const bool ok = i < p.n_valid;
-      sm[i] = ok ? __ldg(p.bias + slot * g.bn + i) : 0.f;
-      sm[256 + i] = ok ? __ldg(p.gamma + slot * g.bn + i) : 0.f;
-      sm[512 + i] = ok ? __ldg(p.beta + slot * g.bn + i) : 0.f;
+      sm[i] = ok ? __ldg(p.bias + slot * p.cstride + i) : 0.f;
+      sm[256 + i] = ok ? __ldg(p.gamma + slot * p.cstride + i) : 0.f;
+      sm[512 + i] = ok ? __ldg(p.beta + slot * p.cstride + i) : 0.f;
     }
   }
   // x = acc + bias (+ addend) for the 32 columns starting at tile column c (pads are exact zeros)
@@ -202,12 +203,138 @@ using EpiLnSilu = EpiLnSiluT<false>;
 using EpiLnSiluAdd = EpiLnSiluT<true>;
 
 // ------------------------------------------------------------------------------------------
+// The same Linear + LayerNorm + SiLU stage for SMALL grids (few m-tiles): the tile's 256 columns are
+// split over a cluster of four CTAs (gridDim.z), 64 columns = one N = 64 MMA each, so the main loop
+// streams a quarter of the weight tile and the epilogue does a quarter of the row work per SM.
+// Row statistics: 4 threads x 16 columns inside a CTA (smem merge), then the four CTAs publish
+// (mean, M2) of their 64 columns into every peer's shared memory (st.shared::cluster) and meet at
+// one barrier.cluster; the 16 values per thread stay in registers across it.
+// ------------------------------------------------------------------------------------------
+template <bool HAS_ADD>
+struct EpiLnSiluN4T {
+  static constexpr int B_ROWS_MAX = 64, STAGES = 8, TMEM_COLS = 64, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 4;   // 8 x 24 KB in flight: the main loop is latency-bound
+  using Params = typename EpiLnSiluT<HAS_ADD>::Params;
+  static constexpr int XST = 2560;   // float offset of the cross-CTA statistics [4 ranks][128 rows][2]
+  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+    const int cr = (int)cluster_ctarank();
+    for (int i = tid; i < 64; i += EPI_THREADS) {
+      const int col = 64 * cr + i;
+      const bool ok = col < p.n_valid;
+      sm[i] = ok ? __ldg(p.bias + slot * p.cstride + col) : 0.f;
+      sm[256 + i] = ok ? __ldg(p.gamma + slot * p.cstride + col) : 0.f;
+      sm[512 + i] = ok ? __ldg(p.beta + slot * p.cstride + col) : 0.f;
+    }
+  }
+  static __device__ __forceinline__ int cnt_of(int nv, int first, int width) { return max(0, min(width, nv - first)); }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int nv = p.n_valid;
+    const int cr = (int)cluster_ctarank();
+    const int c0 = part * 16;                  // CTA-local column of this thread's 16 values
+    const int gc0 = 64 * cr + c0;              // tile column
+    const int cnt = cnt_of(nv, gc0, 16);
+    float v[16];
+    tmem_ld16(taddr + c0, v);
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(sm + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = b4[j];
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    }
+    if constexpr (HAS_ADD) {
+      if (p.addend && m < g.M) {
+        const float* add = p.addend + (long)m * p.ld_addend + gc0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < cnt) v[j] += __ldg(add + j);
+      }
+    }
+    // pads (columns >= n_valid) are exact zeros: shifted sums over all 16, corrected analytically
+    const float shift = v[0];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float d = v[j] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+    const float npad = (float)(16 - cnt);
+    s1 = fmaf(npad, shift, s1);
+    s2 = fmaf(-npad * shift, shift, s2);
+    const float inv_cnt = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+    float* xs = sm + XCHG;
+    xs[part * 128 + row] = shift + s1 * inv_cnt;
+    xs[512 + part * 128 + row] = fmaxf(s2 - s1 * s1 * inv_cnt, 0.f);
+    epi_bar_sync();
+    float* xst = sm + XST;
+    if (part == 0) {   // merge the CTA's four parts, publish to every CTA of the cluster
+      const int cnt_c = cnt_of(nv, 64 * cr, 64);
+      float tot = 0.f;
+#pragma unroll
+      for (int q = 0; q < EPI_PARTS; ++q) tot += xs[q * 128 + row] * (float)cnt_of(nv, 64 * cr + 16 * q, 16);
+      const float mean_c = cnt_c > 0 ? tot / (float)cnt_c : 0.f;
+      float M2c = 0.f;
+#pragma unroll
+      for (int q = 0; q < EPI_PARTS; ++q) {
+        const float d = xs[q * 128 + row] - mean_c;
+        M2c += xs[512 + q * 128 + row] + d * d * (float)cnt_of(nv, 64 * cr + 16 * q, 16);
+      }
+#pragma unroll
+      for (uint32_t dst = 0; dst < 4; ++dst) {
+        st_cluster_f32(xst + (cr * 128 + row) * 2, dst, mean_c);
+        st_cluster_f32(xst + (cr * 128 + row) * 2 + 1, dst, M2c);
+      }
+    }
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tot += xst[(q * 128 + row) * 2] * (float)cnt_of(nv, 64 * q, 64);
+    const float mean = tot / (float)nv;
+    float M2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float d = xst[(q * 128 + row) * 2] - mean;
+      M2 += xst[(q * 128 + row) * 2 + 1] + d * d * (float)cnt_of(nv, 64 * q, 64);
+    }
+    const float rstd = rsqrtf(M2 / (float)nv + p.eps);
+    const float nmr = -mean * rstd;
+    const int ncols_tot = min(p.ld_out, (nv + 63) & ~63);   // the consumer reads ceil64(n_valid) columns
+    const int mine = max(0, min(64, ncols_tot - 64 * cr));  // columns this CTA writes (0 or 64)
+    constexpr int pitch = 64 + 4;
+    {
+      const float4* ga = reinterpret_cast<const float4*>(sm + 256 + c0);
+      const float4* be = reinterpret_cast<const float4*>(sm + 512 + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 G = ga[j], Bt = be[j];
+        v[4 * j] = siluf_(fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x));
+        v[4 * j + 1] = siluf_(fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y));
+        v[4 * j + 2] = siluf_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
+        v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
+      }
+    }
+    tile_put<16>(tile, pitch, row, c0, v);
+    epi_bar_sync();
+    if (mine > 0)
+      tile_copy_out(tile, pitch, 64, mine, (int)blockIdx.x * BM, g.M, nullptr, 0,
+                    p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out + 64 * cr, p.ld_out, tid);
+  }
+};
+using EpiLnSiluN4 = EpiLnSiluN4T<false>;
+using EpiLnSiluAddN4 = EpiLnSiluN4T<true>;
+
+// ------------------------------------------------------------------------------------------
 // GRU gates + state update (nn.GRUCell, SequenceModel.py:13-24), U hidden units per tile,
 // U / 4 units per thread.  TMEM columns: [r | z | n_x | n_h], each U wide.
 // ------------------------------------------------------------------------------------------
 template <int U, int CM_ = 1>
 struct EpiGru {
   static constexpr int CLUSTER_M = CM_;   // 2: pairs of m-tiles share the weight tile through TMA multicast (opt-in experiment)
+  static constexpr int CLUSTER_N = 1;
   // Two CTAs per SM (3 x 28 KB or 2 x 40 KB of stages, 128 / 256 TMEM columns each): one CTA's epilogue and prologue overlap
   // the other's main loop, which keeps the per-SM operand ingress -- the limiter of this stage -- busy.
   static constexpr int B_ROWS_MAX = 3 * U, STAGES = (U == 32 ? 3 : 2), TMEM_COLS = 4 * U, GRU_U = U, MIN_CTAS = 2;
@@ -285,7 +412,7 @@ struct EpiGru {
 // owns 2 of them.
 // ------------------------------------------------------------------------------------------
 struct EpiCat {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;     // [R * 32]
     const float* uniforms; // [M, R] for this step, or NULL (logits only)
@@ -298,39 +425,41 @@ struct EpiCat {
     int ld_s, R;
     RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z always uses the GEMM row
   };
+  // A tile is g.bn = 128 or 256 columns = G = 4 or 8 latent rows of 32 classes; thread (row, part) owns groups part, part + 4.
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
-    for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (slot * 256 + i < p.R * 32) ? __ldg(p.bias + slot * 256 + i) : 0.f;
-    // this tile's uniforms [128 rows x 8 latent rows] -> sm[256 ..), coalesced 32-byte row segments
+    const int G = g.bn >> 5;
+    for (int i = tid; i < g.bn; i += EPI_THREADS) sm[i] = (slot * g.bn + i < p.R * 32) ? __ldg(p.bias + slot * g.bn + i) : 0.f;
+    // this tile's uniforms [128 rows x G latent rows] -> sm[256 ..), coalesced row segments
     const int m0 = (int)blockIdx.x * BM;
-    for (int i = tid; i < BM * 8; i += EPI_THREADS) {
-      const int r = i >> 3, gi = i & 7;
-      const int lrow = slot * 8 + gi;
-      sm[256 + i] = (p.uniforms && m0 + r < g.M && lrow < p.R) ? __ldg(p.uniforms + (long)(m0 + r) * p.R + lrow) : 0.f;
+    for (int i = tid; i < BM * G; i += EPI_THREADS) {
+      const int r = i / G, gi = i - r * G;
+      const int lrow = slot * G + gi;
+      sm[256 + r * 8 + gi] = (p.uniforms && m0 + r < g.M && lrow < p.R) ? __ldg(p.uniforms + (long)(m0 + r) * p.R + lrow) : 0.f;
     }
   }
   static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const int m0 = (int)blockIdx.x * BM;
-    const int ncols = min(256, p.R * 32 - slot * 256);
-    constexpr int pitch = 256 + 4;
-    uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);   // [128 rows][8] (sm[256, 1280) holds the uniforms)
+    const int G = g.bn >> 5;
+    const int col0 = slot * g.bn;                                  // first logit column of this tile
+    const int ncols = max(0, min(g.bn, p.R * 32 - col0));
+    const int pitch = g.bn + 4;
+    uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);       // [128 rows][8] (sm[256, 1280) holds the uniforms)
     if (p.logits) {   // pass A: logits tile out (training paths only)
 #pragma unroll 1
-      for (int gg = 0; gg < 2; ++gg) {
-        const int gi = part * 2 + gg;
+      for (int gi = part; gi < G; gi += EPI_PARTS) {
         float v[32];
         tmem_ld32(taddr + gi * 32, v);
         add_const32(v, sm + gi * 32);
         tile_put<32>(tile, pitch, row, gi * 32, v);
       }
       epi_bar_sync();
-      tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.logits + slot * 256, p.ld_logits, nullptr, 0, tid, p.rm);
+      tile_copy_out(tile, pitch, g.bn, ncols, m0, g.M, p.logits + col0, p.ld_logits, nullptr, 0, tid, p.rm);
       epi_bar_sync();
     }
     if (p.uniforms == nullptr) return;
 #pragma unroll 1
-    for (int gg = 0; gg < 2; ++gg) {
-      const int gi = part * 2 + gg;
+    for (int gi = part; gi < G; gi += EPI_PARTS) {
       float v[32];
       tmem_ld32(taddr + gi * 32, v);
       add_const32(v, sm + gi * 32);
@@ -360,13 +489,13 @@ struct EpiCat {
       tile_put<32>(tile, pitch, row, gi * 32, v);
     }
     epi_bar_sync();
-    if (p.latent) tile_copy_out(tile, pitch, 256, ncols, m0, g.M, p.latent + slot * 256, p.ld_latent, nullptr, 0, tid, p.rm);
-    // idx [128 x 8] bytes and the bf16 one-hot [128 x 256] straight from the staged indices
+    if (p.latent) tile_copy_out(tile, pitch, g.bn, ncols, m0, g.M, p.latent + col0, p.ld_latent, nullptr, 0, tid, p.rm);
+    // idx [128 x G] bytes and the bf16 one-hot [128 x bn] straight from the staged indices
     const int ngrp = ncols >> 5;
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
-        if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * 8 + gi] = idx_sm[i];
+        if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * G + gi] = idx_sm[i];
       }
     }
     if (p.s_z) {
@@ -377,7 +506,7 @@ struct EpiCat {
         uint32_t q[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) q[e] = (idx == j0 + 2 * e ? 0x3F80u : 0u) | (idx == j0 + 2 * e + 1 ? 0x3F800000u : 0u);
-        *reinterpret_cast<uint4*>(p.s_z + (long)(m0 + r) * p.ld_s + slot * 256 + w * 8) = make_uint4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<uint4*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + w * 8) = make_uint4(q[0], q[1], q[2], q[3]);
       }
     }
   }
@@ -392,7 +521,7 @@ enum HeadKind { HEAD_BUCKET = 0, HEAD_SIGMOID = 1, HEAD_ACTOR = 2 };
 constexpr int MAX_HEADS = 5;
 
 struct EpiHeads {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;  // [MAX_HEADS * 256]
     int kind[MAX_HEADS];

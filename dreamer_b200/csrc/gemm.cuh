@@ -28,6 +28,7 @@ struct GemmCommon {
   CUtensorMap tmB;   // packed weights, box {64, bn}
   int M;             // valid rows (epilogues guard their global stores with m < M)
   int bn;            // B rows per tile == UMMA N of the (first) accumulator group
+  int b_slot_rows;   // B rows between consecutive slots (0: == bn)
   int a_row0;        // A row of tile (x = 0, slot = 0)
   int a_y_stride;    // extra A rows per slot
   int ka0, nka0;     // A k-block ranges [ka0, ka0 + nka0) then [ka1, ka1 + nka1); B k-blocks are
@@ -51,8 +52,8 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = B_ROWS_MAX * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + 256;        // 1024 floats of per-tile constants + 2048 of row-stat exchange
-  static constexpr int TOTAL = EPI_OFF + 12288 + 1024; // barriers + epilogue scratch + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + 256;        // 1024 floats of per-tile constants + 3072 of row-stat exchange
+  static constexpr int TOTAL = EPI_OFF + 16384 + 1024; // barriers + epilogue scratch + alignment slack
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
@@ -61,6 +62,9 @@ struct GemmSmem {
 //   static constexpr int CLUSTER_M (1 or 2).  CLUSTER_M = 2: the two CTAs of a cluster are neighbouring m-tiles of the same
 //       n-tile; each loads its own A tile and HALF of the shared B tile, multicast to both (tmB then has box rows bn / 2).
 //       A stage is refilled only after BOTH consumers released it (empty barriers count 2, released by a multicast commit).
+//   static constexpr int CLUSTER_N (1 or 4).  CLUSTER_N = 4: the four CTAs of a cluster (gridDim.z) each own bn = 64 columns
+//       of one 256-column tile; the epilogue exchanges row statistics through distributed shared memory and every thread of
+//       the cluster takes part in ONE barrier.cluster between the two epilogue halves.
 //   struct Params;
 //   static __device__ void stage(const Params&, const GemmCommon&, int slot, float* sm, int tid);
 //       -- the EPI_THREADS epilogue threads copy the tile's constants (biases, LN affine, buckets)
@@ -77,6 +81,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
   constexpr int STAGES = Epi::STAGES;
   constexpr int CM = Epi::CLUSTER_M;
+  constexpr int CN = Epi::CLUSTER_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
@@ -89,7 +94,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int nk = g.nka0 + g.nka1;
   const int slot = g.n_slots > 0 ? g.y_slot[blockIdx.y] : (int)blockIdx.y;
   const int a_row = g.a_row0 + slot * g.a_y_stride + (int)blockIdx.x * BM;
-  const int b_row = slot * g.bn;
+  const int b_row = slot * (g.b_slot_rows ? g.b_slot_rows : g.bn) + (CN > 1 ? (int)cluster_ctarank() * g.bn : 0);
 
   // Programmatic dependent launch: let the next stage's CTAs start their prologue now; everything this CTA
   // reads that an earlier stage produced (activations via TMA, h_prev) is touched only after griddep_wait().
@@ -108,7 +113,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, Epi::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CM > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
+  if constexpr (CM > 1 || CN > 1) cluster_sync_all();   // peers are resident and their barriers initialised before any remote access
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");  // producer / MMA warps; epilogue warps wait after staging
@@ -194,6 +199,13 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     Epi::run(ep, g, epi_sm, reinterpret_cast<float*>(smem), tmem + ((uint32_t)(q * 32) << 16), m, row, part, slot,
              (int)threadIdx.x - 64);
     if (threadIdx.x == 64) probe(g, 6);
+  }
+  if constexpr (CN > 1) {
+    if (warp < 2) {          // the producer / MMA warps take part in the epilogue's single cluster barrier
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -93,9 +93,9 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (Epi::CLUSTER_M > 1) {
-      attr[na].id = cudaLaunchAttributeClusterDimension;               // pairs of m-tiles (TMA multicast of the weight tile)
-      attr[na].val.clusterDim.x = Epi::CLUSTER_M; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    if (Epi::CLUSTER_M > 1 || Epi::CLUSTER_N > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;   // x: pairs of m-tiles (multicast); z: four column quarters of one LN tile
+      attr[na].val.clusterDim.x = Epi::CLUSTER_M; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = Epi::CLUSTER_N;
       ++na;
     }
     if (!profile_on()) {
@@ -140,6 +140,8 @@ struct drm_rssm {
   float *p1_b, *p1_g, *p1_be, *p2_b, *p2_g, *p2_be, *p3_b;
   float *h1_b, *h1_g, *h1_be, *h2_b, *h2_g, *h2_be, *h3_b;  // [5 * bn]
   float *bk_rew, *bk_crit;       // [NB]
+  CUtensorMap tmWp1q, tmWp2q, tmWh1q, tmWh2q;   // box rows 64: the cluster-of-4 LN stage
+  CUtensorMap tmWp3h;                           // box rows 128: half-width categorical tiles for small grids
   CUtensorMap tmWgru2[2], tmWgruHalf2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
   std::vector<VecOp> vec_ops;
@@ -244,11 +246,11 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
   for (int v = 0; v < 2; ++v) TRY(dev_alloc(bag, &m->Wgru2[v], (size_t)m->gru_tiles2[v] * 3 * (32 << v) * m->KG));
-  TRY(dev_alloc(bag, &m->Wp1, (size_t)m->bnp1 * DP));
-  TRY(dev_alloc(bag, &m->Wp2, (size_t)m->bnp2 * 256));
+  TRY(dev_alloc(bag, &m->Wp1, (size_t)256 * DP));                 // LN-stage weights: 256-row slots (zero padded)
+  TRY(dev_alloc(bag, &m->Wp2, (size_t)256 * 256));
   TRY(dev_alloc(bag, &m->Wp3, (size_t)ZP * 256));
-  TRY(dev_alloc(bag, &m->Wh1, (size_t)MAX_HEADS * m->bnh1 * m->KH));
-  TRY(dev_alloc(bag, &m->Wh2, (size_t)MAX_HEADS * m->bnh2 * 256));
+  TRY(dev_alloc(bag, &m->Wh1, (size_t)MAX_HEADS * 256 * m->KH));
+  TRY(dev_alloc(bag, &m->Wh2, (size_t)MAX_HEADS * 256 * 256));
   TRY(dev_alloc(bag, &m->Wh3, (size_t)MAX_HEADS * 256 * 256));
   TRY(dev_alloc(bag, &m->b_ih, (size_t)3 * D));
   TRY(dev_alloc(bag, &m->b_hh, (size_t)3 * D));
@@ -299,11 +301,11 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
     for (int c = 0; c < m->KH; ++c) l1cols[c] = c < ZP ? D + c : (c - ZP < D ? c - ZP : -1);
     for (int hs = 0; hs < MAX_HEADS; ++hs) {
       const int mlp = hs + 1, s = S_MLP0 + 10 * mlp;
-      TRY(add_mat(m, m->Wh1, m->KH, hs * m->bnh1, 0, s + 0, D + ZP, iota_lim(m->bnh1, h1), l1cols));
+      TRY(add_mat(m, m->Wh1, m->KH, hs * 256, 0, s + 0, D + ZP, iota_lim(m->bnh1, h1), l1cols));
       TRY(add_vec(m, m->h1_b + hs * m->bnh1, s + 1, iota_lim(m->bnh1, h1)));
       TRY(add_vec(m, m->h1_g + hs * m->bnh1, s + 2, iota_lim(m->bnh1, h1)));
       TRY(add_vec(m, m->h1_be + hs * m->bnh1, s + 3, iota_lim(m->bnh1, h1)));
-      TRY(add_mat(m, m->Wh2, 256, hs * m->bnh2, 0, s + 4, h1, iota_lim(m->bnh2, h2), iota_lim(256, h1)));
+      TRY(add_mat(m, m->Wh2, 256, hs * 256, 0, s + 4, h1, iota_lim(m->bnh2, h2), iota_lim(256, h1)));
       TRY(add_vec(m, m->h2_b + hs * m->bnh2, s + 5, iota_lim(m->bnh2, h2)));
       TRY(add_vec(m, m->h2_g + hs * m->bnh2, s + 6, iota_lim(m->bnh2, h2)));
       TRY(add_vec(m, m->h2_be + hs * m->bnh2, s + 7, iota_lim(m->bnh2, h2)));
@@ -330,11 +332,16 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
     TRY(make_tmap_bf16_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U));
     TRY(make_tmap_bf16_2d(&m->tmWgruHalf2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U / 2));   // multicast halves
   }
-  TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, m->bnp1, DP, DP, m->bnp1));
-  TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, m->bnp2, 256, 256, m->bnp2));
+  TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, 256, DP, DP, m->bnp1));
+  TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, 256, 256, 256, m->bnp2));
+  TRY(make_tmap_bf16_2d(&m->tmWp1q, m->Wp1, 256, DP, DP, 64));
+  TRY(make_tmap_bf16_2d(&m->tmWp2q, m->Wp2, 256, 256, 256, 64));
+  TRY(make_tmap_bf16_2d(&m->tmWh1q, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, 64));
+  TRY(make_tmap_bf16_2d(&m->tmWh2q, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, 64));
   TRY(make_tmap_bf16_2d(&m->tmWp3, m->Wp3, ZP, 256, 256, 256));
-  TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * m->bnh1, m->KH, m->KH, m->bnh1));
-  TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * m->bnh2, 256, 256, m->bnh2));
+  TRY(make_tmap_bf16_2d(&m->tmWp3h, m->Wp3, ZP, 256, 256, 128));
+  TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1));
+  TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2));
   TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
 #undef TRY
   if (rc != DRM_OK) {
@@ -476,6 +483,22 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
 #undef DRM_GRU_LAUNCH
 }
 
+// One Linear + LayerNorm + SiLU stage.  Small grids (<= 37 tiles) use the cluster-of-4 column split, larger ones one CTA per tile.
+template <bool HAS_ADD>
+static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMap& tmB_q, int bn_full,
+                     typename EpiLnSiluT<HAS_ADD>::Params p, int mt, int n_slots, cudaStream_t st, int stage_id) {
+  static const bool no_n4 = getenv("DRM_NO_LN_CLUSTER") != nullptr;   // A/B switch for profiling
+  g.b_slot_rows = 256;
+  if (!no_n4 && mt * n_slots <= 37) {
+    g.tmB = tmB_q;
+    g.bn = 64;
+    return launch_gemm<EpiLnSiluN4T<HAS_ADD>>(g, p, dim3(mt, n_slots, 4), st, stage_id);
+  }
+  g.tmB = tmB_full;
+  g.bn = bn_full;
+  return launch_gemm<EpiLnSiluT<HAS_ADD>>(g, p, dim3(mt, n_slots, 1), st, stage_id);
+}
+
 // prior MLP on the view's h columns -> logits -> (optional) categorical sample
 static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, float* latent, long ld_latent, float* logits,
                        long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, RowMap rm, int M, cudaStream_t st) {
@@ -485,24 +508,25 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.a_row0 = v.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L1));
+    EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f, m->bnp1};
+    RC(launch_ln<false>(g, m->tmWp1, m->tmWp1q, m->bnp1, p, mt, 1, st, DRM_STAGE_PRIOR_L1));
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWp2, M, m->bnp2);
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, v.Y2, 256, v.row0, v.slot_rows, m->d.h_prior[1], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st, DRM_STAGE_PRIOR_L2));
+    EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, v.Y2, 256, v.row0, v.slot_rows, m->d.h_prior[1], 1e-5f, m->bnp2};
+    RC(launch_ln<false>(g, m->tmWp2, m->tmWp2q, m->bnp2, p, mt, 1, st, DRM_STAGE_PRIOR_L2));
   }
   {
-    GemmCommon g = common(*v.tmY2, m->tmWp3, M, 256);
+    const int bn = (mt * (m->ZP / 256) <= 74) ? 128 : 256;   // small grids: half-width tiles, one 32-class group per thread
+    GemmCommon g = common(*v.tmY2, bn == 128 ? m->tmWp3h : m->tmWp3, M, bn);
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
     EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
                      ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm};
-    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st, DRM_STAGE_PRIOR_CAT));
+    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
 }
@@ -518,8 +542,8 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;      // h blocks (the action block is skipped)
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L1));
+    EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
+    RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWh2, M, m->bnh2);
@@ -527,8 +551,8 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[0], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, v.Y2, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[1], 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, n_slots), st, DRM_STAGE_HEADS_L2));
+    EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, v.Y2, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[1], 1e-5f, m->bnh2};
+    RC(launch_ln<false>(g, m->tmWh2, m->tmWh2q, m->bnh2, p, mt, n_slots, st, DRM_STAGE_HEADS_L2));
   }
   {
     GemmCommon g = common(*v.tmY2, m->tmWh3, M, 256);

@@ -139,7 +139,7 @@ struct drm_vae {
   int bn_he, bn_hd;
   __nv_bfloat16 *We[4], *Wef, *Weh, *We3, *Wd1, *Wd2, *Wdc[4];
   float *be[4], *e1_b, *e1_g, *e1_be, *e3_b, *d1_b, *d1_g, *d1_be, *d2_b, *bdc[4];
-  CUtensorMap tmWe[4], tmWef, tmWeh, tmWe3, tmWd1, tmWd2, tmWdc[4];
+  CUtensorMap tmWe[4], tmWef, tmWeh, tmWehq, tmWe3, tmWe3h, tmWd1, tmWd1q, tmWd2, tmWdc[4];
   std::vector<drm::OffOp> mat_ops;
   std::vector<drm::VecOp> vec_ops;
   std::vector<void*> allocs;
@@ -223,11 +223,11 @@ extern "C" int drm_vae_create(drm_rssm* m, const drm_vae_dims* dims, drm_vae** o
     TRY(dev_alloc(bag, &v->bdc[i], (size_t)v->dbn[i + 1]));
   }
   TRY(dev_alloc(bag, &v->Wef, (size_t)v->bn_he * v->Kf));
-  TRY(dev_alloc(bag, &v->Weh, (size_t)v->bn_he * DP));
+  TRY(dev_alloc(bag, &v->Weh, (size_t)256 * DP));
   TRY(dev_alloc(bag, &v->We3, (size_t)ZP * 256));
   TRY(dev_alloc(bag, &v->e1_b, (size_t)v->bn_he)); TRY(dev_alloc(bag, &v->e1_g, (size_t)v->bn_he)); TRY(dev_alloc(bag, &v->e1_be, (size_t)v->bn_he));
   TRY(dev_alloc(bag, &v->e3_b, (size_t)ZP));
-  TRY(dev_alloc(bag, &v->Wd1, (size_t)v->bn_hd * KH));
+  TRY(dev_alloc(bag, &v->Wd1, (size_t)256 * KH));
   TRY(dev_alloc(bag, &v->Wd2, (size_t)v->hw4 * v->dbn[0] * 256));
   TRY(dev_alloc(bag, &v->d1_b, (size_t)v->bn_hd)); TRY(dev_alloc(bag, &v->d1_g, (size_t)v->bn_hd)); TRY(dev_alloc(bag, &v->d1_be, (size_t)v->bn_hd));
   TRY(dev_alloc(bag, &v->d2_b, (size_t)v->hw4 * v->dbn[0]));
@@ -292,9 +292,12 @@ extern "C" int drm_vae_create(drm_rssm* m, const drm_vae_dims* dims, drm_vae** o
     TRY(make_tmap_bf16_2d(&v->tmWdc[i], v->Wdc[i], 4 * v->dbn[i + 1], v->DK[i], v->DK[i], v->dbn[i + 1]));
   }
   TRY(make_tmap_bf16_2d(&v->tmWef, v->Wef, v->bn_he, v->Kf, v->Kf, v->bn_he));
-  TRY(make_tmap_bf16_2d(&v->tmWeh, v->Weh, v->bn_he, DP, DP, v->bn_he));
+  TRY(make_tmap_bf16_2d(&v->tmWeh, v->Weh, 256, DP, DP, v->bn_he));
+  TRY(make_tmap_bf16_2d(&v->tmWehq, v->Weh, 256, DP, DP, 64));
   TRY(make_tmap_bf16_2d(&v->tmWe3, v->We3, ZP, 256, 256, 256));
-  TRY(make_tmap_bf16_2d(&v->tmWd1, v->Wd1, v->bn_hd, KH, KH, v->bn_hd));
+  TRY(make_tmap_bf16_2d(&v->tmWe3h, v->We3, ZP, 256, 256, 128));
+  TRY(make_tmap_bf16_2d(&v->tmWd1, v->Wd1, 256, KH, KH, v->bn_hd));
+  TRY(make_tmap_bf16_2d(&v->tmWd1q, v->Wd1, 256, KH, KH, 64));
   TRY(make_tmap_bf16_2d(&v->tmWd2, v->Wd2, (uint64_t)v->hw4 * v->dbn[0], 256, 256, 256));
 #undef TRY
   if (rc != DRM_OK) { drm_vae_destroy(v); return rc; }
@@ -479,16 +482,17 @@ static int encoder_head(drm_observe* o, const WsView& vw, const float* addend, c
     g.a_row0 = vw.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSiluAdd::Params p{v->e1_b, v->e1_g, v->e1_be, addend, (long)v->bn_he, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_enc, 1e-5f};
-    RC(launch_gemm<EpiLnSiluAdd>(g, p, dim3(mt, 1), st));
+    EpiLnSiluAdd::Params p{v->e1_b, v->e1_g, v->e1_be, addend, (long)v->bn_he, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_enc, 1e-5f, v->bn_he};
+    RC(launch_ln<true>(g, v->tmWeh, v->tmWehq, v->bn_he, p, mt, 1, st, DRM_STAGE_OTHER));
   }
   {
-    GemmCommon g = common(*vw.tmY1, v->tmWe3, M, 256);
+    const int bn = (mt * (m->ZP / 256) <= 74) ? 128 : 256;
+    GemmCommon g = common(*vw.tmY1, bn == 128 ? v->tmWe3h : v->tmWe3, M, bn);
     g.a_row0 = vw.row0;
     g.ka0 = 0; g.nka0 = ceil_div(v->d.h_enc, 64);
     EpiCat::Params p{v->e3_b, uniforms, latent, logits, idx, write_sz ? vw.S + (long)vw.row0 * m->KS : nullptr, nullptr,
                      ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, RowMap{0, 0, 0, 0}};
-    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / 256), st));
+    RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st));
   }
   return DRM_OK;
 }
@@ -504,8 +508,8 @@ static int decoder_dense(drm_observe* o, const WsView& vw, __nv_bfloat16* act0, 
     g.ka0 = 0; g.nka0 = m->ZP / 64;
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
-    EpiLnSilu::Params p{v->d1_b, v->d1_g, v->d1_be, nullptr, 0, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_dec, 1e-5f};
-    RC(launch_gemm<EpiLnSilu>(g, p, dim3(mt, 1), st));
+    EpiLnSilu::Params p{v->d1_b, v->d1_g, v->d1_be, nullptr, 0, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_dec, 1e-5f, v->bn_hd};
+    RC(launch_ln<false>(g, v->tmWd1, v->tmWd1q, v->bn_hd, p, mt, 1, st, DRM_STAGE_OTHER));
   }
   {
     const int N = v->hw4 * v->dbn[0];

@@ -41,7 +41,7 @@ def _close(got, ref, atol=ATOL, rtol=1e-2, what=""):
 CFGS = {"small": W.small_config(), "ref": dict(W.REF_CONFIG)}
 
 
-@pytest.mark.parametrize("name,N", [("small", 5), ("small", 300), ("ref", 64), ("ref", 1024)])
+@pytest.mark.parametrize("name,N", [("small", 5), ("small", 300), ("ref", 64), ("ref", 1024), ("ref", 4000)])   # 4000 rows: 64-unit GRU tiles
 def test_gru_step(ops, name, N):
     cfg = CFGS[name]
     sd, model = _model(ops, cfg, 1)
@@ -53,7 +53,7 @@ def test_gru_step(ops, name, N):
     _close(got, ref, what="gru h'")
 
 
-@pytest.mark.parametrize("name,N", [("small", 7), ("ref", 200)])
+@pytest.mark.parametrize("name,N", [("small", 7), ("ref", 200), ("ref", 5000)])   # 5000 rows: one-CTA-per-tile LN path, full-width categorical tiles
 def test_prior_logits_and_kernel_boundary_sampling(ops, name, N):
     cfg = CFGS[name]
     sd, model = _model(ops, cfg, 3)
@@ -72,7 +72,7 @@ def test_prior_logits_and_kernel_boundary_sampling(ops, name, N):
     assert torch.allclose(out["z"].cpu(), z_ref, atol=2e-7)
 
 
-@pytest.mark.parametrize("name,N", [("small", 9), ("ref", 130)])
+@pytest.mark.parametrize("name,N", [("small", 9), ("ref", 130), ("ref", 2000)])   # 2000 rows x 5 heads: one-CTA-per-tile LN path
 def test_heads(ops, name, N):
     from dreamer_b200 import _lib as L
     cfg = CFGS[name]
