@@ -100,7 +100,7 @@ class ClockSampler:
 
 
 def make_problem(workload):
-    from oracle import weights as W   # synthetic weights/inputs only (deterministic numpy streams)
+    from dreamer_b200 import synthetic as W   # synthetic weights / inputs (deterministic numpy streams)
     B, H, over, desc = WORKLOADS[workload]
     cfg = dict(W.REF_CONFIG, horizon=H, **over)
     sd = W.make_state_dict(cfg, seed=0, actor_mu_zero=True)
@@ -112,8 +112,8 @@ def run_reference(args, rank, world):
     all host threads, on a bounded sample of the workload.  Rank 0 only."""
     if rank != 0:
         return
-    from oracle import rssm as O
-    from oracle import weights as W
+    from oracle import rssm as O          # the one other place bench.py may execute oracle/: the reference arm
+    from dreamer_b200 import synthetic as W
     cfg, sd, B, H, desc = make_problem(args.workload)
     Bs = min(B, args.cpu_rows)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -138,8 +138,8 @@ def run_reference(args, rank, world):
 
 
 def cpu_baseline(args, cfg, sd, B, H):
-    from oracle import rssm as O
-    from oracle import weights as W
+    from oracle import rssm as O          # cpu_baseline leg: the oracle port timed as the reference's CPU path
+    from dreamer_b200 import synthetic as W
     Bs = min(B, args.cpu_rows)
     torch.set_num_threads(os.cpu_count() or 1)
     z0, h0, _, n = W.rollout_inputs(cfg, Bs, H, seed=1234)
@@ -155,6 +155,62 @@ def cpu_baseline(args, cfg, sd, B, H):
                 sample=f"{Bs} of {B} start states x horizon {H}, median of {len(times)} rollouts after 1 warm-up, stock torch sampler, fp32, no_grad")
 
 
+def secondary_metrics(dev, peaks, flush):
+    """HBM-bound kernels against the measured HBM peak and the world-model (config 3) rates -- extra keys, N = 1 only."""
+    import numpy as np
+    from dreamer_b200 import ops
+    from dreamer_b200 import synthetic as W
+    out = {}
+
+    def dev_time(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts) * 1e-3
+
+    # replay gather (Buffer.sample_sequences, Buffer.py:49-61) at the reference's batch 50 x sequence 50
+    cap, B, L = 20000, 50, 50
+    ring = [torch.randint(0, 256, (cap, 3, 64, 64), dtype=torch.uint8, device=dev), torch.rand(cap, 3, device=dev),
+            torch.rand(cap, 1, device=dev), torch.ones(cap, 1, device=dev)]
+    starts = torch.from_numpy(np.random.RandomState(0).randint(0, cap - L, size=B))
+    t = dev_time(lambda: ops.replay_gather(*ring, starts, L))
+    by = 61480 * B * L
+    out["replay_gather"] = dict(workload="50 x 50 windows of 64x64x3 u8 frames -> fp32", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9,
+                                peak_gbs=peaks["hbm"], frac=by / t / 1e9 / peaks["hbm"], note="153.7 MB per launch: short kernel, launch ramp included")
+    B2 = 1024
+    starts2 = torch.from_numpy(np.random.RandomState(1).randint(0, cap - L, size=B2))
+    t = dev_time(lambda: ops.replay_gather(*ring, starts2, L), reps=5)
+    by = 61480 * B2 * L
+    out["replay_gather_large"] = dict(workload="1024 x 50 windows", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"],
+                                      frac=by / t / 1e9 / peaks["hbm"])
+    del ring
+    # stand-alone categorical (softmax / unimix / sample / one-hot / ST), 4M rows of 32 classes
+    n = 1 << 22
+    lg = torch.randn(n, 32, device=dev); u = torch.rand(n, device=dev)
+    t = dev_time(lambda: ops.categorical32(lg, u), reps=5)
+    by = n * (128 + 4 + 128 + 1)
+    out["categorical32"] = dict(workload="4 Mi rows x 32 classes", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"],
+                                frac=by / t / 1e9 / peaks["hbm"])
+    del lg, u
+    # world model, BASELINE configs[2]: batch 16 x seq 64 of 64x64x3 frames: loss forward on the kernels, and the full training step
+    cfg = dict(W.REF_CONFIG, horizon=64, sequence_length=64, batch_size=16)
+    wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=0), dev)
+    obs, act, rew, cont, uu = (x.to(dev) for x in W.sequence_inputs(cfg, 16, 64, seed=4321))
+    t_f = dev_time(lambda: wm.loss_forward(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
+    t_s = dev_time(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
+    out["world_model_c3"] = dict(workload="batch 16 x seq 64, 64x64x3 frames (BASELINE configs[2])", loss_forward_steps_per_s=1.0 / t_f,
+                                 loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_s, train_step_ms=t_s * 1e3,
+                                 note="training step = kernel forward + interim torch autograd tail + AdamW (DESIGN.md section 6)")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +221,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1024, help="start states in the CPU sample")
     ap.add_argument("--cpu-reps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the auxiliary HBM-kernel / world-model measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -188,7 +245,7 @@ def main():
     L.check(L.load().drm_device_check(), "device_check")
 
     cfg, sd, B, H, desc = make_problem(args.workload)
-    from oracle import weights as W
+    from dreamer_b200 import synthetic as W
     z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=1234 + rank)      # every rank owns different start states
     model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in sd.items()})
     ro = ops.Rollout(model, B, H)
@@ -286,6 +343,11 @@ def main():
                                               parallelism=f"start states sharded over {world} rank(s), no data-path collective"),
                 e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
                 gpu_launches=int(gpu_launches), clocks=clocks, roofline=roofline)
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            line["secondary"] = secondary_metrics(dev, peaks, flush)
+        except Exception as e:     # never lose the headline line to an auxiliary measurement
+            line["secondary"] = dict(error=repr(e)[:200])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, sd, B, H)
     elif rank == 0:

@@ -33,40 +33,93 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------------------------------
 // categorical32: softmax -> unimix -> inverse-CDF sample -> one-hot -> straight-through.
-// DynamicsPredictors.py:33-39 / VariationalAutoEncoder.py:88-98.  Lane = class.
-// Algorithmic bytes per row: 128 B logits + 4 B uniform read; 128 B z_st (+ 1 B idx, + optional
-// 128 B probs, 64 B bf16 one-hot) written.
+// DynamicsPredictors.py:33-39 / VariationalAutoEncoder.py:88-98.
+// A warp owns 32 consecutive rows: the 32 x 32 logit tile is loaded coalesced (float4 per lane) into a padded
+// shared-memory tile, each LANE then processes one ROW in registers (max, exp, sum, the left-to-right fp32 CDF of the
+// contract, the draw -- no shuffles), writes its outputs back into the tile and the warp stores them coalesced.
+// Algorithmic bytes per row: 128 B logits + 4 B uniform read; 128 B z_st (+ 1 B idx, + optional 128 B probs,
+// 64 B bf16 one-hot) written.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restrict__ logits,
                                                             const float* __restrict__ uniforms,
                                                             uint8_t* __restrict__ idx_out, float* __restrict__ z_st,
                                                             float* __restrict__ probs, uint16_t* __restrict__ z_bf16,
                                                             int64_t n_rows) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = warp; row < n_rows; row += nwarps) {
-    const float x = __ldg(logits + row * 32 + lane);
-    const float u = __ldg(uniforms + row);
-    const float m = warp_max(x);
-    const float e = expf(x - m);
-    const float s = warp_sum(e);
-    const float p = 0.99f * (e / s) + 0.01f * (1.0f / 32.0f);
-    // left-to-right fp32 prefix sum (the contract's order): lane k accumulates p_0 .. p_k
+  __shared__ float tiles[8][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float(*t)[33] = tiles[w];
+  const int64_t warp = (int64_t)blockIdx.x * 8 + w;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int64_t ntiles = (n_rows + 31) >> 5;
+  for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+    const int64_t row0 = tile << 5;
+    const int nr = (int)min((int64_t)32, n_rows - row0);
+    // coalesced load: pass k brings rows 4k .. 4k+3 (8 lanes x float4 per row)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) x = __ldg(reinterpret_cast<const float4*>(logits + (row0 + r) * 32 + c));
+      t[r][c] = x.x; t[r][c + 1] = x.y; t[r][c + 2] = x.z; t[r][c + 3] = x.w;
+    }
+    const float u = lane < nr ? __ldg(uniforms + row0 + lane) : 0.f;
+    __syncwarp();
+    float v[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] = t[lane][j]; mx = fmaxf(mx, v[j]); }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
     float cdf = 0.f;
+    int idx = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      if (j <= lane) cdf += pj;
+      v[j] = 0.99f * (v[j] / s) + 0.01f * (1.0f / 32.0f);
+      cdf += v[j];
+      idx += (cdf <= u) ? 1 : 0;
     }
-    const unsigned le = __ballot_sync(0xffffffffu, cdf <= u);
-    int idx = __popc(le);
     idx = idx > 31 ? 31 : idx;
-    const float oh = (lane == idx) ? 1.0f : 0.0f;
-    if (z_st) z_st[row * 32 + lane] = (oh + p) - p;
-    if (probs) probs[row * 32 + lane] = p;
-    if (z_bf16) z_bf16[row * 32 + lane] = (lane == idx) ? (uint16_t)0x3F80 : (uint16_t)0;
-    if (idx_out && lane == 0) idx_out[row] = (uint8_t)idx;
+    if (idx_out && lane < nr) idx_out[row0 + lane] = (uint8_t)idx;   // 32 consecutive bytes per warp
+    if (probs) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[lane][j] = v[j];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
+        if (r < nr) *reinterpret_cast<float4*>(probs + (row0 + r) * 32 + c) = make_float4(t[r][c], t[r][c + 1], t[r][c + 2], t[r][c + 3]);
+      }
+    }
+    if (z_st) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[lane][j] = ((j == idx ? 1.0f : 0.0f) + v[j]) - v[j];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
+        if (r < nr) __stcs(reinterpret_cast<float4*>(z_st + (row0 + r) * 32 + c), make_float4(t[r][c], t[r][c + 1], t[r][c + 2], t[r][c + 3]));
+      }
+    }
+    if (z_bf16) {   // exact one-hot: every lane needs its rows' indices -> broadcast through the tile
+      __syncwarp();
+      t[lane][0] = __int_as_float(idx);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {      // pass k: rows 8k .. 8k+7, 4 lanes x uint4 (8 bf16) per row
+        const int r = 8 * k + (lane >> 2), c = (lane & 3) * 8;
+        if (r < nr) {
+          const int ri = __float_as_int(t[r][0]);
+          uint32_t q[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q[e] = (ri == c + 2 * e ? 0x3F80u : 0u) | (ri == c + 2 * e + 1 ? 0x3F800000u : 0u);
+          *reinterpret_cast<uint4*>(z_bf16 + (row0 + r) * 32 + c) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -279,7 +332,10 @@ extern "C" int drm_categorical32_fwd(const float* logits, const float* uniforms,
   DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_fwd: n_rows < 0");
   if (n_rows == 0) return DRM_OK;  // empty input: nothing to do (pointers may be NULL)
   DRM_REQUIRE(logits && uniforms, DRM_ERR_ARG, "drm_categorical32_fwd: logits/uniforms are NULL");
-  categorical32_kernel<<<rows_grid(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows);
+  DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && (!z_st || (uintptr_t)z_st % 16 == 0) && (!probs || (uintptr_t)probs % 16 == 0) &&
+                  (!z_bf16 || (uintptr_t)z_bf16 % 16 == 0),
+              DRM_ERR_ALIGN, "drm_categorical32_fwd: 16-byte alignment required");
+  categorical32_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

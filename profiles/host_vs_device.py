@@ -3,7 +3,7 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dreamer_b200 import ops
-from oracle import weights as W
+from dreamer_b200 import synthetic as W
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 B, H, over = {"c2": (1024, 15, {}), "c2x16": (16384, 15, {}), "c4": (16384, 15, {"hidden_state_dims": 4096})}[wl]
 cfg = dict(W.REF_CONFIG, horizon=H, **over)

@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dreamer_b200 import ops, _lib as L
-from oracle import weights as W
+from dreamer_b200 import synthetic as W
 B, H = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 15
 cfg = dict(W.REF_CONFIG, horizon=H)
 sd = W.make_state_dict(cfg, seed=0, actor_mu_zero=True)

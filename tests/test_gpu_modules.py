@@ -23,22 +23,7 @@ def _close(got, ref, atol=2e-2, rtol=1e-2, what=""):
 
 def _dreamer(cfg, sd):
     """WorldModel + Agent mirrors built exactly as Dreamer.__init__ does (Dreamer.py:71-118), weights from `sd`."""
-    from dreamer_b200 import learners
-    dev = torch.device(DEV)
-    wm = learners.WorldModel(cfg["hidden_state_dims"], tuple(cfg["latent_state_dims"]), tuple(cfg["observation_dims"]), cfg["action_dims"],
-                             cfg["horizon"], cfg["batch_size"], cfg["world_model_lr"], tuple(cfg["world_model_betas"]), cfg["world_model_eps"],
-                             cfg["beta_prediction"], cfg["beta_dynamics"], cfg["beta_representation"], cfg["encoder_filter_num_1"],
-                             cfg["encoder_filter_num_2"], cfg["encoder_hidden_layer_nodes"], cfg["decoder_filter_num_1"], cfg["decoder_filter_num_2"],
-                             cfg["decoder_hidden_layer_nodes"], cfg["dyn_pred_hidden_num_nodes_1"], cfg["dyn_pred_hidden_num_nodes_2"],
-                             cfg["rew_pred_hidden_num_nodes_1"], cfg["rew_pred_hidden_num_nodes_2"], cfg["critic_reward_buckets"],
-                             cfg["cont_pred_hidden_num_nodes_1"], cfg["cont_pred_hidden_num_nodes_2"], device=dev)
-    ag = learners.Agent(cfg["action_dims"], tuple(cfg["latent_state_dims"]), cfg["hidden_state_dims"], cfg["hidden_layer_actor_1_size"],
-                        cfg["hidden_layer_actor_2_size"], cfg["hidden_layer_critic_1_size"], cfg["hidden_layer_critic_2_size"],
-                        cfg["critic_reward_buckets"], cfg["actor_lr"], tuple(cfg["actor_betas"]), cfg["actor_eps"], cfg["critic_lr"],
-                        tuple(cfg["critic_betas"]), cfg["critic_eps"], cfg["nu"], cfg["lambda_"], cfg["gamma"], device=dev)
-    wm.load_state_dict({k[len("world_model."):]: v for k, v in sd.items() if k.startswith("world_model.")}, strict=True)
-    ag.load_state_dict({k[len("agent."):]: v for k, v in sd.items() if k.startswith("agent.")}, strict=True)
-    return wm, ag
+    return W.build_learners(cfg, sd, DEV)
 
 
 def test_module_forward_surface_matches_oracle():
