@@ -292,7 +292,9 @@ def main():
     gpu_launches = launches * args.steps // (args.steps + args.warmup)
 
     # ---- end to end through the public host-buffer API -------------------------------------------
-    pin = [t.contiguous().pin_memory() for t in (z0, h0, u, n)]
+    # the public call takes the start states (host buffers); the per-step randomness is drawn on the device inside the call,
+    # as Dreamer.dream_episodes does
+    pin = [t.contiguous().pin_memory() for t in (z0, h0)]
     h2d = sum(t.numel() * t.element_size() for t in pin)
     res = {}
 

@@ -23,11 +23,16 @@ def dream_episodes(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, ge
     return rollout.run(z0, h0, uniforms, normals, want_idx=want_idx)
 
 
-def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms, normals):
-    """Host-buffer call: inputs are (pinned) CPU tensors; returns dict(device=7-tuple, host=(rewards, continues))."""
+def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, generator=None):
+    """Host-buffer call: the start states are (pinned) CPU tensors; the draws are made on the device exactly as
+    ``Dreamer.dream_episodes`` does (pass ``uniforms`` / ``normals`` host tensors to supply them instead).
+    Returns dict(device=7-tuple, host=(rewards, continues))."""
     dev = torch.device("cuda", torch.cuda.current_device())
-    d = [t.to(dev, non_blocking=True) for t in (z0, h0, uniforms, normals)]
-    out = rollout.run(*d, want_idx=False)
+    m, B, H = rollout.model, rollout.B, rollout.H
+    zd, hd = z0.to(dev, non_blocking=True), h0.to(dev, non_blocking=True)
+    ud = uniforms.to(dev, non_blocking=True) if uniforms is not None else torch.rand((H, B, m.R), device=dev, generator=generator)
+    nd = normals.to(dev, non_blocking=True) if normals is not None else torch.randn((H, B, m.A), device=dev, generator=generator)
+    out = rollout.run(zd, hd, ud, nd, want_idx=False)
     host = [out[3].to("cpu", non_blocking=True), out[4].to("cpu", non_blocking=True)]
     torch.cuda.current_stream().synchronize()
     return dict(device=out, host=host)

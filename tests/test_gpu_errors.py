@@ -1,0 +1,73 @@
+"""Error behaviour of the C-ABI (negative return code + drm_last_error message, no exception across the boundary, no CPU
+fallback) and run-to-run determinism of the rollout."""
+import ctypes as C
+
+import pytest
+import torch
+
+from dreamer_b200 import synthetic as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def L():
+    from dreamer_b200 import _lib
+    return _lib
+
+
+def test_shape_errors_are_reported_not_computed(L):
+    lib = L.load()
+    bad = L.DrmDims(600, 32, 16, 3, 255, (C.c_int32 * 2)(200, 200), (C.c_int32 * 2)(200, 200))    # classes must be 32
+    h = C.c_void_p()
+    assert lib.drm_rssm_create(C.byref(bad), C.byref(h)) == -1 and b"must be 32" in lib.drm_last_error()
+    big = L.DrmDims(600, 32, 32, 3, 255, (C.c_int32 * 2)(200, 300), (C.c_int32 * 2)(200, 200))     # hidden > 256
+    assert lib.drm_rssm_create(C.byref(big), C.byref(h)) == -1
+    assert lib.drm_rssm_create(None, C.byref(h)) == -5
+
+
+def test_unpacked_and_oversized_calls_fail_loudly(L):
+    from dreamer_b200 import ops
+    cfg = W.small_config()
+    model = ops.PackedRssm(cfg["hidden_state_dims"], 32, 32, 3, 255, (72, 72), (72, 72))           # created, never packed
+    ws = ops.Rollout(model, 128, 2)
+    z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 128, 2, seed=1))
+    with pytest.raises(RuntimeError, match="never packed"):
+        ws.run(z0, h0, u, n)
+    sd = {k: v.to(DEV) for k, v in W.make_state_dict(cfg, seed=2).items()}
+    gru_only = ops.PackedRssm.from_state_dict({k: v for k, v in sd.items() if "sequence_model" in k})
+    ws2 = ops.Rollout(gru_only, 128, 1)
+    ws2.gru_step(z0[:, 0], h0[:, 0], torch.zeros(128, 3, device=DEV))                              # has what it needs
+    with pytest.raises(RuntimeError, match="prior weights"):
+        ws2.prior(h0[:, 0])
+    with pytest.raises(RuntimeError, match="exceeds the workspace"):
+        ws2.gru_step(torch.zeros(200, 1024, device=DEV), torch.zeros(200, cfg["hidden_state_dims"], device=DEV), torch.zeros(200, 3, device=DEV))
+    with pytest.raises(RuntimeError):                                                               # CPU tensors are refused
+        ws2.model.pack({k: v.cpu() for k, v in sd.items()})
+
+
+def test_alignment_and_argument_errors(L):
+    lib = L.load()
+    x = torch.zeros(1024 + 4, device=DEV)
+    mis = C.c_void_p(x.data_ptr() + 4)
+    ok = C.c_void_p(x.data_ptr())
+    assert lib.drm_neg_sse_rows(mis, ok, ok, 1, 64, None) == -2 and b"aligned" in lib.drm_last_error()
+    assert lib.drm_lambda_return(None, ok, ok, ok, 4, 4, 0.99, 0.95, None) == -5
+    assert lib.drm_twohot_ce(ok, ok, ok, ok, 4, 1000, 0, None) == -1                               # NB > 256
+    assert lib.drm_lambda_return(None, None, None, None, 0, 4, 0.99, 0.95, None) == 0              # empty batch is a no-op
+
+
+def test_rollout_is_deterministic():
+    from dreamer_b200 import ops
+    cfg = W.small_config()
+    sd = {k: v.to(DEV) for k, v in W.make_state_dict(cfg, seed=3).items()}
+    model = ops.PackedRssm.from_state_dict(sd)
+    ro = ops.Rollout(model, 300, 5)
+    z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 300, 5, seed=4))
+    a = ro.run(z0, h0, u, n)
+    b = ro.run(z0, h0, u, n)
+    model.pack(sd)                                                                                  # re-packing the same weights changes nothing
+    c = ro.run(z0, h0, u, n)
+    for x, y, w in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, w)
