@@ -59,6 +59,7 @@ SIGNATURES = {
     "drm_last_error": (C.c_char_p, []),
     "drm_device_check": (C.c_int, []),
     "drm_launch_count": (C.c_int64, []),
+    "drm_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "drm_debug_timeline": (C.c_int, [C.c_int32, C.c_void_p]),
     "drm_profile_enable": (C.c_int, [C.c_int32]),
     "drm_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

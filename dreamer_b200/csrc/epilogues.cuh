@@ -423,7 +423,8 @@ struct EpiCat {
     const float* addend;   // optional fp32 [M, ld_addend] added to the logits (unused by the prior)
     long ld_latent, ld_logits, ld_idx, ld_addend;
     int ld_s, R;
-    RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z always uses the GEMM row
+    RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z and zi always use the GEMM row
+    uint8_t* zi;           // sampled indices next to the state buffer [M, R] (feeds the one-hot expander of later stages) or NULL
   };
   // A tile is g.bn = 128 or 256 columns = G = 4 or 8 latent rows of 32 classes; thread (row, part) owns groups part, part + 4.
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
@@ -496,6 +497,12 @@ struct EpiCat {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
         if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * G + gi] = idx_sm[i];
+      }
+    }
+    if (p.zi) {
+      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+        const int r = i >> 3, gi = i & 7;
+        if (m0 + r < g.M && gi < ngrp) p.zi[(long)(m0 + r) * p.R + slot * G + gi] = idx_sm[i];
       }
     }
     if (p.s_z) {

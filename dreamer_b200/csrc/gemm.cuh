@@ -36,6 +36,11 @@ struct GemmCommon {
   int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
   int y_slot[8];
   unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL
+  // One-hot A operand: when zi != NULL the first n_zblocks A k-blocks (2 latent rows of 32 classes each) are NOT loaded by
+  // TMA; the epilogue warps build them in swizzled shared memory from the sampled indices zi[row * zi_ld + latent_row]
+  // (255 = no class set).  Saves 2 KB of bf16 zeros per row per stage.
+  const uint8_t* zi;
+  int zi_ld, n_zblocks;
 };
 
 __device__ __forceinline__ void probe(const GemmCommon& g, int i) {
@@ -53,7 +58,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 256;        // 1024 floats of per-tile constants + 3072 of row-stat exchange
-  static constexpr int TOTAL = EPI_OFF + 16384 + 1024; // barriers + epilogue scratch + alignment slack
+  static constexpr int ZI_OFF = EPI_OFF + 16384;       // 128 rows x 32 sampled indices of this tile's rows
+  static constexpr int TOTAL = ZI_OFF + 4096 + 1024;   // barriers + epilogue scratch + indices + alignment slack
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
 };
 
@@ -104,7 +110,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     tma_prefetch_desc(&g.tmA);
     tma_prefetch_desc(&g.tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], g.zi ? 2 : 1);   // + the one-hot expander's arrival
       mbar_init(&empty[s], CM);
     }
     mbar_init(tmem_full, 1);
@@ -121,7 +127,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       probe(g, 1);
-      const uint32_t tx = A_STAGE_BYTES + (uint32_t)g.bn * BK * 2;
+      const uint32_t tx_b = (uint32_t)g.bn * BK * 2;
+      const int nz = g.zi ? g.n_zblocks : 0;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -129,8 +136,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
         const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
-        mbar_expect_tx(&full[s], tx);
-        tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
+        mbar_expect_tx(&full[s], kb < nz ? tx_b : tx_b + A_STAGE_BYTES);
+        if (kb >= nz) tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);   // one-hot k-blocks: A is built in place by the expander
         if constexpr (CM == 1) {
           tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
         } else {
@@ -188,6 +195,45 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     float* epi_sm = reinterpret_cast<float*>(smem + SL::EPI_OFF);
     Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64);   // weights-derived constants + host inputs only
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (g.zi) {
+      // ---- one-hot expander: the (otherwise idle) epilogue warps build the latent's A tiles in swizzled smem ----
+      const int et = (int)threadIdx.x - 64;
+      uint8_t* zi_sm = smem + SL::ZI_OFF;
+      // this tile's indices: 128 rows x (2 * n_zblocks <= 32) bytes; rows >= M and missing latent rows: 255 = no class set
+      for (int i = et; i < BM * 32; i += EPI_THREADS) {
+        const int rr = i >> 5, lr = i & 31;
+        const bool ok = (int)blockIdx.x * BM + rr < g.M && lr < 2 * g.n_zblocks;
+        zi_sm[i] = ok ? __ldg(g.zi + (long)(a_row + rr) * g.zi_ld + lr) : (uint8_t)255;
+      }
+      epi_bar_sync();
+      const int r = et >> 2, q4 = et & 3;             // row, and which 16 of the k-block's 64 columns
+      const int cls0 = (q4 & 1) * 16;                  // first class of this thread's span inside its latent row
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (kb < g.n_zblocks) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          const int hit = (int)zi_sm[r * 32 + 2 * kb + (q4 >> 1)] - cls0;   // 0..15 if the sampled class is in this span
+          uint8_t* rowp = smem + s * SL::STAGE_BYTES + r * 128;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e0 = hit - 8 * c;               // element inside this 16-byte chunk
+            uint4 v;
+            v.x = e0 == 0 ? 0x3F80u : (e0 == 1 ? 0x3F800000u : 0u);
+            v.y = e0 == 2 ? 0x3F80u : (e0 == 3 ? 0x3F800000u : 0u);
+            v.z = e0 == 4 ? 0x3F80u : (e0 == 5 ? 0x3F800000u : 0u);
+            v.w = e0 == 6 ? 0x3F80u : (e0 == 7 ? 0x3F800000u : 0u);
+            *reinterpret_cast<uint4*>(rowp + (((2 * q4 + c) ^ (r & 7)) << 4)) = v;   // SWIZZLE_128B chunk position
+          }
+          fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
+          epi_bar_sync();
+          if (et == 0) mbar_arrive(&full[s]);
+        } else if (et == 0) {                          // keep the barrier's arrival count uniform for TMA-fed k-blocks
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive(&full[s]);
+        }
+      }
+    }
     epi_bar_sync();                                     // epilogue warps only
     mbar_wait(tmem_full, 0);
     tc_fence_after();

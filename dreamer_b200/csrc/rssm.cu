@@ -69,6 +69,27 @@ __global__ void f32_to_bf16_pad_kernel(__nv_bfloat16* __restrict__ dst, int ld_d
 // debug probe buffer: [DRM_STAGE_COUNT][16] u64 (drm_debug_timeline)
 static unsigned long long* g_timeline = nullptr;
 
+// Runtime options (drm_set_option; initial values from the environment): experiments measured in profiles/README.md.
+struct Options {
+  int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
+  int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
+  int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int gru_u;       // 0: automatic GRU tile width, else 32 / 64
+};
+static Options& opts() {
+  static Options o = [] {
+    Options x;
+    x.zidx = getenv("DRM_ZIDX") != nullptr;
+    x.multicast = getenv("DRM_MULTICAST") != nullptr;
+    x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
+    const char* e = getenv("DRM_GRU_U");
+    x.gru_u = e ? atoi(e) : 0;
+    if (x.gru_u != 32 && x.gru_u != 64) x.gru_u = 0;
+    return x;
+  }();
+  return o;
+}
+
 static int grid_for(long total, int threads = 256) {
   long b = (total + threads - 1) / threads;
   if (b > 148 * 16) b = 148 * 16;
@@ -154,6 +175,7 @@ struct drm_rollout {
   drm_rssm* m;
   int B, H, Mp;
   __nv_bfloat16* S[2];
+  uint8_t* Zi[2];              // sampled latent indices [Mp, R] next to S[i] (one-hot expander input)
   __nv_bfloat16 *Y1, *Y2;
   CUtensorMap tmS[2], tmY1, tmY2;
   std::vector<void*> allocs;
@@ -196,14 +218,6 @@ static int add_vec(drm_rssm* m, float* dst, int src, const std::vector<int>& map
   if (int rc = upload_map(m->allocs, map, &op.map)) return rc;
   m->vec_ops.push_back(op);
   return DRM_OK;
-}
-
-static int pick_gru_u(int) {   // DRM_GRU_U=32|64 forces the GRU tile width (profiling); 0 = automatic
-  if (const char* e = getenv("DRM_GRU_U")) {
-    const int u = atoi(e);
-    if (u == 32 || u == 64) return u;
-  }
-  return 0;
 }
 
 }  // namespace drm
@@ -410,6 +424,7 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
   for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->S[i], (size_t)r->Mp * m->KS));
+  for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->Zi[i], (size_t)r->Mp * m->d.R));
   TRY(dev_alloc(r->allocs, &r->Y1, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
   TRY(dev_alloc(r->allocs, &r->Y2, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
   for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM));
@@ -449,26 +464,35 @@ struct WsView {
   __nv_bfloat16 *Y1, *Y2;   // [(MAX_HEADS + 1) * slot_rows, 256]; slot 0 = prior / encoder, 1.. = heads
   int slot_rows;            // rows per Y slot
   int row0;                 // first row of this view inside S and inside every Y slot
+  uint8_t* Zi;              // sampled indices [rows, R] parallel to S (NULL: none)
 };
 static WsView view_of(drm_rollout* r, int sb) {
-  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0};
+  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0, r->Zi[sb]};
+}
+// Enable the one-hot expander for the view's z k-blocks (only valid when those rows' latents were written by EpiCat).
+static void use_z_indices(drm_rssm* m, GemmCommon& g, const WsView& v) {
+  if (!opts().zidx || !v.Zi) return;
+  g.zi = v.Zi;
+  g.zi_ld = m->d.R;
+  g.n_zblocks = m->ZP / 64;
 }
 
 // GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
 static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
-                     long ld_hout, int M, cudaStream_t st) {
+                     long ld_hout, int M, cudaStream_t st, bool z_idx = false) {
   // DRM_MULTICAST=1 selects the cluster variant (pairs of m-tiles, weight tile halves multicast by TMA).  Measured on B200 it
   // is not faster: the stage is bound by per-SM shared-memory ingress, which multicast does not reduce (profiles/README.md).
-  static const bool mc = getenv("DRM_MULTICAST") != nullptr;
+  const bool mc = opts().multicast != 0;
   // tile width: 64 hidden units per tile once that still fills the machine twice over (more FLOPs per operand byte), else 32
   const int mt = ceil_div(M, BM);
   int v = (mt * m->gru_tiles2[1] >= 2 * 148) ? 1 : 0;
-  if (const int force = pick_gru_u(0)) v = force == 64 ? 1 : 0;
+  if (const int force = opts().gru_u) v = force == 64 ? 1 : 0;
   const int U = 32 << v;
   GemmCommon g = common(*src.tmS, mc ? m->tmWgruHalf2[v] : m->tmWgru2[v], M, 3 * U);
   g.a_row0 = src.row0;
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
+  if (z_idx && !mc) use_z_indices(m, g, src);
   const dim3 grid(mc ? round_up(mt, 2) : mt, m->gru_tiles2[v]);
   __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
@@ -487,9 +511,8 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
 template <bool HAS_ADD>
 static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMap& tmB_q, int bn_full,
                      typename EpiLnSiluT<HAS_ADD>::Params p, int mt, int n_slots, cudaStream_t st, int stage_id) {
-  static const bool no_n4 = getenv("DRM_NO_LN_CLUSTER") != nullptr;   // A/B switch for profiling
   g.b_slot_rows = 256;
-  if (!no_n4 && mt * n_slots <= 37) {
+  if (opts().ln_cluster && mt * n_slots <= 37) {
     g.tmB = tmB_q;
     g.bn = 64;
     return launch_gemm<EpiLnSiluN4T<HAS_ADD>>(g, p, dim3(mt, n_slots, 4), st, stage_id);
@@ -525,14 +548,16 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
     EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
-                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm};
+                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
+                     (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
 }
 
 // [h, z] heads on the view: slots listed in `slots` (HS_*)
-static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st) {
+static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st,
+                       bool z_idx = false) {
   const int mt = ceil_div(M, BM);
   if (n_slots <= 0) return DRM_OK;
   {
@@ -542,6 +567,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;      // h blocks (the action block is skipped)
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    if (z_idx) use_z_indices(m, g, v);
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
     RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
   }
@@ -610,7 +636,8 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
   }
   for (int t = 0; t < H; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    RC(stage_gru(m, view_of(r, cur), view_of(r, nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st));
+    // t = 0 reads the caller's z0 densely; every later latent was sampled here, so its A tiles are expanded from the indices
+    RC(stage_gru(m, view_of(r, cur), view_of(r, nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st, t > 0));
     RC(stage_prior(m, view_of(r, nxt), uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
                    idx ? idx + (long)t * R : nullptr, (long)H * R, true, RowMap{0, 0, 0, 0}, B, st));
     EpiHeads::Params hp;
@@ -625,7 +652,7 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
       hp.ld_act = ldA;
       hp.s_a = r->S[nxt] + ZP; hp.ld_s = m->KS;
     }
-    RC(stage_heads(m, view_of(r, nxt), all3, more ? 3 : 2, hp, B, st));
+    RC(stage_heads(m, view_of(r, nxt), all3, more ? 3 : 2, hp, B, st, true));
   }
   return DRM_OK;
 }
@@ -717,6 +744,18 @@ extern "C" int drm_test_gemm(const float* A, const float* W, const float* bias, 
   for (void* q : bag) cudaFree(q);
   if (rc == DRM_OK && e != cudaSuccess) return fail(DRM_ERR_CUDA, std::string("drm_test_gemm: ") + cudaGetErrorString(e));
   return rc;
+}
+
+extern "C" int drm_set_option(const char* name, int32_t value) {
+  if (!name) return fail(DRM_ERR_ARG, "drm_set_option: NULL name");
+  const std::string n(name);
+  Options& o = opts();
+  if (n == "zidx") o.zidx = value != 0;
+  else if (n == "multicast") o.multicast = value != 0;
+  else if (n == "ln_cluster") o.ln_cluster = value != 0;
+  else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
+  else return fail(DRM_ERR_ARG, "drm_set_option: unknown option '" + n + "'");
+  return DRM_OK;
 }
 
 // Debug: enable (on = 1) the in-kernel probe of CTA (0,0) of every fused stage, or read the last probes back

@@ -61,6 +61,12 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_HEADS_OUT 6
 #define DRM_STAGE_OTHER 7
 #define DRM_STAGE_COUNT 8
+/* Runtime switches for the experimental / alternative kernel paths (all produce identical results):                  */
+/*   "ln_cluster" (default 1)  LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
+/*   "gru_u"      (default 0)  GRU tile width: 0 = automatic, 32 or 64 hidden units per tile                           */
+/*   "multicast"  (default 0)  GRU stage in 2-CTA clusters, weight tile halves multicast by TMA (measured: not faster) */
+/*   "zidx"       (default 0)  one-hot latent A tiles built in shared memory from sampled indices (measured: slower)   */
+int drm_set_option(const char* name, int32_t value);
 /* Debug probe: with on = 1 CTA (0,0) of every fused stage records {globaltimer ns, clock64} at 8 points */
 /* (entry, setup done, first TMA issued, first operands landed, last MMA issued, accumulator ready,     */
 /* epilogue done, TMEM freed); on = 0 copies DRM_STAGE_COUNT * 16 u64 to out_host and disables it.       */
