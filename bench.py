@@ -208,6 +208,33 @@ def secondary_metrics(dev, peaks, flush):
     out["world_model_c3"] = dict(workload="batch 16 x seq 64, 64x64x3 frames (BASELINE configs[2])", loss_forward_steps_per_s=1.0 / t_f,
                                  loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_s, train_step_ms=t_s * 1e3,
                                  note="training step = kernel forward + interim torch autograd tail + AdamW (DESIGN.md section 6)")
+    # the north star's large-batch points: 16 384 start states x horizon 15 on this one GPU (GRU stage vs the measured bf16 peak)
+    import ctypes as C
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    for wl in ("c2x16", "c4"):
+        Bn, Hn, over, desc = WORKLOADS[wl]
+        cfgn = dict(W.REF_CONFIG, horizon=Hn, **over)
+        model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in W.make_state_dict(cfgn, seed=0, actor_mu_zero=True).items()})
+        ro = ops.Rollout(model, Bn, Hn)
+        z0, h0, uu, nn_ = (t.to(dev) for t in W.rollout_inputs(cfgn, Bn, Hn, seed=1234))
+        t = dev_time(lambda: ro.run(z0, h0, uu, nn_, want_idx=False), reps=3, warm=2)
+        lib.drm_profile_enable(1)
+        ro.run(z0, h0, uu, nn_, want_idx=False)
+        torch.cuda.synchronize()
+        lib.drm_profile_enable(0)
+        ms, cnt = C.c_double(), C.c_int64()
+        lib.drm_profile_read(0, C.byref(ms), C.byref(cnt))
+        for i in range(1, 8):
+            lib.drm_profile_read(i, C.byref(C.c_double()), C.byref(C.c_int64()))
+        fl = flops_per_state(cfgn)
+        gru_tf = fl["gru"] * Bn / (ms.value / cnt.value * 1e-3) / 1e12
+        out["rollout_" + wl] = dict(workload=desc, states_per_s=Bn * Hn / t, ms_per_rollout=t * 1e3, gru_stage_us=1e3 * ms.value / cnt.value,
+                                    gru_stage_tflops=gru_tf, gru_frac_of_bf16_burst_peak=gru_tf / peaks["bf16_burst"],
+                                    rollout_tflops=fl["total"] * Bn * Hn / t / 1e12,
+                                    rollout_frac_of_bf16_sustained_peak=fl["total"] * Bn * Hn / t / 1e12 / peaks["bf16_sustained"])
+        del ro, model, z0, h0, uu, nn_
+        torch.cuda.empty_cache()
     return out
 
 
@@ -278,7 +305,7 @@ def main():
     lib = L.load()
     # ---- device-resident throughput ------------------------------------------------------------
     step = lambda: ro.run(z0d, h0d, ud, nd, want_idx=False)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)     # every rank samples its own GPU; rank 0's record is reported
     for _ in range(2):
         step()
     torch.cuda.synchronize()
