@@ -35,6 +35,7 @@ struct GemmCommon {
   int ka1, nka1;     //   consumed sequentially from 0
   int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
   int y_slot[8];
+  unsigned long long* cta_times;  // debug: per-CTA {entry, wait over, exit, smid} records, or NULL
   unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL
   // One-hot A operand: when zi != NULL the first n_zblocks A k-blocks (2 latent rows of 32 classes each) are NOT loaded by
   // TMA; the epilogue warps build them in swizzled shared memory from the sampled indices zi[row * zi_ld + latent_row]
@@ -42,6 +43,23 @@ struct GemmCommon {
   const uint8_t* zi;
   int zi_ld, n_zblocks;
 };
+
+// debug: every CTA records {entry ns, dependency-wait-over ns, exit ns, SM id} behind the 8 stage probes
+// (region: timeline_base + DRM_STAGE_COUNT * 16 + stage * 1024, up to 256 CTAs per stage)
+__device__ __forceinline__ void cta_probe(unsigned long long* stage_timeline, int which) {
+  if (!stage_timeline) return;
+  const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (cta >= 256) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  unsigned long long* rec = stage_timeline + 4 * cta;
+  rec[which] = t;
+  if (which == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    rec[3] = smid;
+  }
+}
 
 __device__ __forceinline__ void probe(const GemmCommon& g, int i) {
   if (g.timeline && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -107,6 +125,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     probe(g, 0);
+    cta_probe(g.cta_times, 0);
     tma_prefetch_desc(&g.tmA);
     tma_prefetch_desc(&g.tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -127,6 +146,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       probe(g, 1);
+      cta_probe(g.cta_times, 1);
       const uint32_t tx_b = (uint32_t)g.bn * BK * 2;
       const int nz = g.zi ? g.n_zblocks : 0;
       for (int kb = 0; kb < nk; ++kb) {
@@ -257,7 +277,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   __syncthreads();
   if constexpr (CM > 1) cluster_sync_all();   // the peer may still arrive on / multicast into this CTA's shared memory
   if (warp == 1) tmem_dealloc(tmem, Epi::TMEM_COLS);
-  if (threadIdx.x == 32) probe(g, 7);
+  if (threadIdx.x == 32) { probe(g, 7); cta_probe(g.cta_times, 2); }
 }
 
 // ------------------------------------------------------------------------------------------

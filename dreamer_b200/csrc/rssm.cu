@@ -74,6 +74,8 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int lanes;       // rollouts: 0 / 1 one lane (default), 2 two half-batches on two internal streams
+  int chain;       // 1: small grids run each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel (default 1)
   int gru_u;       // 0: automatic GRU tile width, else 32 / 64
 };
 static Options& opts() {
@@ -82,6 +84,8 @@ static Options& opts() {
     x.zidx = getenv("DRM_ZIDX") != nullptr;
     x.multicast = getenv("DRM_MULTICAST") != nullptr;
     x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
+    x.chain = getenv("DRM_CHAIN") != nullptr;
+    x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
     x.gru_u = e ? atoi(e) : 0;
     if (x.gru_u != 32 && x.gru_u != 64) x.gru_u = 0;
@@ -105,7 +109,10 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
     attr_set = true;
   }
   profile_begin(stage, st);
-  if (g_timeline) const_cast<GemmCommon&>(g).timeline = g_timeline + 16 * stage;
+  if (g_timeline) {
+    const_cast<GemmCommon&>(g).timeline = g_timeline + 16 * stage;
+    const_cast<GemmCommon&>(g).cta_times = g_timeline + 16 * DRM_STAGE_COUNT + 1024 * stage;
+  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -163,6 +170,7 @@ struct drm_rssm {
   float *bk_rew, *bk_crit;       // [NB]
   CUtensorMap tmWp1q, tmWp2q, tmWh1q, tmWh2q;   // box rows 64: the cluster-of-4 LN stage
   CUtensorMap tmWp3h;                           // box rows 128: half-width categorical tiles for small grids
+  CUtensorMap tmWh3q;                           // box rows 64: output layer of the chained heads kernel
   CUtensorMap tmWgru2[2], tmWgruHalf2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
   std::vector<VecOp> vec_ops;
@@ -178,6 +186,8 @@ struct drm_rollout {
   uint8_t* Zi[2];              // sampled latent indices [Mp, R] next to S[i] (one-hot expander input)
   __nv_bfloat16 *Y1, *Y2;
   CUtensorMap tmS[2], tmY1, tmY2;
+  cudaStream_t lane_st[2] = {nullptr, nullptr};   // two-lane rollouts (created on first use)
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
 };
 
@@ -357,6 +367,7 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1));
   TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2));
   TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
+  TRY(make_tmap_bf16_2d(&m->tmWh3q, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 64));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rssm_destroy(m);
@@ -441,6 +452,11 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
 
 extern "C" int drm_rollout_destroy(drm_rollout* r) {
   if (!r) return DRM_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (r->lane_st[i]) cudaStreamDestroy(r->lane_st[i]);
+    if (r->ev_join[i]) cudaEventDestroy(r->ev_join[i]);
+  }
+  if (r->ev_fork) cudaEventDestroy(r->ev_fork);
   for (void* p : r->allocs) cudaFree(p);
   delete r;
   return DRM_OK;
@@ -507,6 +523,44 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
 #undef DRM_GRU_LAUNCH
 }
 
+}  // namespace drm
+#include "chain.cuh"
+namespace drm {
+
+static int launch_chain(const ChainParams& p, int mt, int n_slots, cudaStream_t st, int stage_id) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    attr_set = true;
+  }
+  if (g_timeline) {
+    const_cast<ChainParams&>(p).timeline = g_timeline + 16 * stage_id;
+    const_cast<ChainParams&>(p).cta_times = g_timeline + 16 * DRM_STAGE_COUNT + 1024 * stage_id;
+  }
+  profile_begin(stage_id, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(mt, n_slots, CH_CN);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = CH_CN;
+  ++na;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, p));
+  profile_end(stage_id, st);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
 // One Linear + LayerNorm + SiLU stage.  Small grids (<= 37 tiles) use the cluster-of-4 column split, larger ones one CTA per tile.
 template <bool HAS_ADD>
 static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMap& tmB_q, int bn_full,
@@ -526,6 +580,25 @@ static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMa
 static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, float* latent, long ld_latent, float* logits,
                        long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, RowMap rm, int M, cudaStream_t st) {
   const int mt = ceil_div(M, BM);
+  if (opts().chain && mt <= 37 && m->ZP == 1024) {
+    // small grid: h -> LN -> LN -> logits -> sample as ONE 4-CTA cluster kernel per m-tile (256 logit columns per CTA)
+    ChainParams c;
+    memset(&c, 0, sizeof(c));
+    c.tmA = *v.tmS; c.tmW0 = m->tmWp1q; c.tmW1 = m->tmWp2q; c.tmW2 = m->tmWp3h;
+    c.M = M; c.a_row0 = v.row0;
+    c.ka0 = m->ZP / 64 + 1; c.nka0 = m->DP / 64;
+    c.nk1 = ceil_div(m->d.h_prior[0], 64); c.nk2 = ceil_div(m->d.h_prior[1], 64);
+    c.nv0 = m->d.h_prior[0]; c.nv1 = m->d.h_prior[1];
+    c.bn2 = 128; c.passes = 2;
+    c.b0 = m->p1_b; c.g0 = m->p1_g; c.be0 = m->p1_be; c.cs0 = m->bnp1;
+    c.b1 = m->p2_b; c.g1 = m->p2_g; c.be1 = m->p2_be; c.cs1 = m->bnp2;
+    c.n_slots = 1; c.y_slot[0] = 0;
+    c.eps = 1e-5f; c.kind = CHAIN_PRIOR;
+    c.cat = EpiCat::Params{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
+                           ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
+                           (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
+    return launch_chain(c, mt, 1, st, DRM_STAGE_PRIOR_L1);
+  }
   {
     GemmCommon g = common(*v.tmS, m->tmWp1, M, m->bnp1);
     g.a_row0 = v.row0;
@@ -560,6 +633,29 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
                        bool z_idx = false) {
   const int mt = ceil_div(M, BM);
   if (n_slots <= 0) return DRM_OK;
+  if (opts().chain && mt * n_slots <= 37) {
+    // small grid: [z | h] -> LN -> LN -> output layer as ONE 4-CTA cluster kernel per (m-tile, head)
+    ChainParams c;
+    memset(&c, 0, sizeof(c));
+    c.tmA = *v.tmS; c.tmW0 = m->tmWh1q; c.tmW1 = m->tmWh2q; c.tmW2 = m->tmWh3q;
+    c.M = M; c.a_row0 = v.row0;
+    c.ka0 = 0; c.nka0 = m->ZP / 64; c.ka1 = m->ZP / 64 + 1; c.nka1 = m->DP / 64;
+    c.nk1 = ceil_div(m->d.h_head[0], 64); c.nk2 = ceil_div(m->d.h_head[1], 64);
+    c.nv0 = m->d.h_head[0]; c.nv1 = m->d.h_head[1];
+    c.bn2 = 64; c.passes = 1;
+    c.b0 = m->h1_b; c.g0 = m->h1_g; c.be0 = m->h1_be; c.cs0 = m->bnh1;
+    c.b1 = m->h2_b; c.g1 = m->h2_g; c.be1 = m->h2_be; c.cs1 = m->bnh2;
+    c.n_slots = n_slots;
+    for (int i = 0; i < n_slots; ++i) c.y_slot[i] = slots[i];
+    c.eps = 1e-5f; c.kind = CHAIN_HEADS;
+    hp.bias = m->h3_b;
+    hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
+    hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
+    hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
+    hp.NB = m->d.NB; hp.A = m->d.A;
+    c.heads = hp;
+    return launch_chain(c, mt, n_slots, st, DRM_STAGE_HEADS_L1);
+  }
   {
     GemmCommon g = common(*v.tmS, m->tmWh1, M, m->bnh1);
     g.a_row0 = v.row0;
@@ -607,6 +703,54 @@ static int pack_state(drm_rollout* r, int sb, int col0, const float* src, long l
   return pack_cols(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy, st);
 }
 
+// One lane of an imagination rollout: start states [b0, b0 + M) of the workspace, every pointer is the FULL tensor's base.
+static int rollout_lane(drm_rollout* r, int b0, int M, const float* z0, const float* h0, const float* uniforms, const float* normals,
+                        float* latent, float* hidden, float* actions, float* rewards, float* continues, float* mu, float* sigma,
+                        uint8_t* idx, cudaStream_t st) {
+  drm_rssm* m = r->m;
+  const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP, A = m->d.A, R = m->d.R;
+  const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D, ldA = (long)H * A;
+  z0 += (long)b0 * ZP; h0 += (long)b0 * D; uniforms += (long)b0 * R; normals += (long)b0 * A;
+  latent += b0 * ldL; hidden += b0 * ldH; actions += b0 * ldA; mu += b0 * ldA; sigma += b0 * ldA;
+  rewards += (long)b0 * H; continues += (long)b0 * H;
+  if (idx) idx += (long)b0 * H * R;
+  auto view = [&](int sb) { WsView v = view_of(r, sb); v.row0 = b0; return v; };
+  auto S_rows = [&](int sb) { return r->S[sb] + (long)b0 * m->KS; };
+  // t = 0 state into S[0]; latent[:, 0] = z0, hidden[:, 0] = h0
+  RC(pack_cols(S_rows(0), m->KS, 0, z0, ZP, ZP, M, latent, ldL, st));
+  RC(pack_cols(S_rows(0), m->KS, ZP + 64, h0, D, D, M, hidden, ldH, st));
+  const int actor_only[1] = {HS_ACTOR};
+  const int all3[3] = {HS_REWARD, HS_CONT, HS_ACTOR};
+  {
+    EpiHeads::Params hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.normals = normals; hp.ld_normals = A; hp.mu = mu; hp.sigma = sigma; hp.action = actions; hp.ld_act = ldA;
+    hp.s_a = S_rows(0) + ZP; hp.ld_s = m->KS;
+    RC(stage_heads(m, view(0), actor_only, 1, hp, M, st));
+  }
+  for (int t = 0; t < H; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    // t = 0 reads the caller's z0 densely; every later latent was sampled here, so its A tiles are expanded from the indices
+    RC(stage_gru(m, view(cur), view(nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, M, st, t > 0));
+    RC(stage_prior(m, view(nxt), uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
+                   idx ? idx + (long)t * R : nullptr, (long)H * R, true, RowMap{0, 0, 0, 0}, M, st));
+    EpiHeads::Params hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.value[HS_REWARD] = rewards + t; hp.ld_value[HS_REWARD] = H;
+    hp.value[HS_CONT] = continues + t; hp.ld_value[HS_CONT] = H;
+    const bool more = t + 1 < H;
+    if (more) {
+      hp.normals = normals + (long)(t + 1) * B * A;  // [B, A] slab of step t + 1
+      hp.ld_normals = A;
+      hp.mu = mu + (long)(t + 1) * A; hp.sigma = sigma + (long)(t + 1) * A; hp.action = actions + (long)(t + 1) * A;
+      hp.ld_act = ldA;
+      hp.s_a = S_rows(nxt) + ZP; hp.ld_s = m->KS;
+    }
+    RC(stage_heads(m, view(nxt), all3, more ? 3 : 2, hp, M, st, true));
+  }
+  return DRM_OK;
+}
+
 }  // namespace drm
 
 extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const float* uniforms, const float* normals,
@@ -620,39 +764,29 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
   DRM_REQUIRE((m->have & (HAVE_GRU | HAVE_PRIOR | 7u)) == (HAVE_GRU | HAVE_PRIOR | 7u), DRM_ERR_ARG,
               "drm_rollout_run: GRU, prior, reward, continue and actor weights must all be packed");
   cudaStream_t st = (cudaStream_t)stream;
-  const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP, A = m->d.A, R = m->d.R;
-  const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D, ldA = (long)H * A;
-  // t = 0 state into S[0]; latent[:, 0] = z0, hidden[:, 0] = h0
-  RC(pack_state(r, 0, 0, z0, ZP, ZP, B, latent, ldL, st));
-  RC(pack_state(r, 0, ZP + 64, h0, D, D, B, hidden, ldH, st));
-  const int actor_only[1] = {HS_ACTOR};
-  const int all3[3] = {HS_REWARD, HS_CONT, HS_ACTOR};
-  {
-    EpiHeads::Params hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.normals = normals; hp.ld_normals = A; hp.mu = mu; hp.sigma = sigma; hp.action = actions; hp.ld_act = ldA;
-    hp.s_a = r->S[0] + ZP; hp.ld_s = m->KS;
-    RC(stage_heads(m, view_of(r, 0), actor_only, 1, hp, B, st));
-  }
-  for (int t = 0; t < H; ++t) {
-    const int cur = t & 1, nxt = cur ^ 1;
-    // t = 0 reads the caller's z0 densely; every later latent was sampled here, so its A tiles are expanded from the indices
-    RC(stage_gru(m, view_of(r, cur), view_of(r, nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, B, st, t > 0));
-    RC(stage_prior(m, view_of(r, nxt), uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
-                   idx ? idx + (long)t * R : nullptr, (long)H * R, true, RowMap{0, 0, 0, 0}, B, st));
-    EpiHeads::Params hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.value[HS_REWARD] = rewards + t; hp.ld_value[HS_REWARD] = H;
-    hp.value[HS_CONT] = continues + t; hp.ld_value[HS_CONT] = H;
-    const bool more = t + 1 < H;
-    if (more) {
-      hp.normals = normals + (long)(t + 1) * B * A;  // [B, A] slab of step t + 1
-      hp.ld_normals = A;
-      hp.mu = mu + (long)(t + 1) * A; hp.sigma = sigma + (long)(t + 1) * A; hp.action = actions + (long)(t + 1) * A;
-      hp.ld_act = ldA;
-      hp.s_a = r->S[nxt] + ZP; hp.ld_s = m->KS;
+  const int B = r->B;
+  // Two lanes (opt-in, "lanes" = 2): the start states are independent, and at a few hundred rows every stage of the step is a
+  // small, latency-bound grid (24 .. 152 CTAs); two half-batches on two streams interleave their stages.  Measured at
+  // 1024 x 15: 1.12 ms against 1.06 ms for one lane (the interleaved stages contend for TMEM and L2), so one lane stays default.
+  int lanes = opts().lanes;
+  if (lanes == 0) lanes = 1;
+  if (profile_on() || g_timeline || opts().zidx || B < 2 * BM) lanes = 1;
+  if (lanes == 1) return rollout_lane(r, 0, B, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
+  if (!r->lane_st[0]) {
+    for (int i = 0; i < 2; ++i) {
+      DRM_CUDA(cudaStreamCreateWithFlags(&r->lane_st[i], cudaStreamNonBlocking));
+      DRM_CUDA(cudaEventCreateWithFlags(&r->ev_join[i], cudaEventDisableTiming));
     }
-    RC(stage_heads(m, view_of(r, nxt), all3, more ? 3 : 2, hp, B, st, true));
+    DRM_CUDA(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
+  }
+  const int M0 = round_up(ceil_div(B, 2), BM);
+  DRM_CUDA(cudaEventRecord(r->ev_fork, st));
+  for (int i = 0; i < 2; ++i) {
+    DRM_CUDA(cudaStreamWaitEvent(r->lane_st[i], r->ev_fork, 0));
+    const int b0 = i ? M0 : 0, M = i ? B - M0 : M0;
+    RC(rollout_lane(r, b0, M, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, r->lane_st[i]));
+    DRM_CUDA(cudaEventRecord(r->ev_join[i], r->lane_st[i]));
+    DRM_CUDA(cudaStreamWaitEvent(st, r->ev_join[i], 0));
   }
   return DRM_OK;
 }
@@ -753,24 +887,27 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   if (n == "zidx") o.zidx = value != 0;
   else if (n == "multicast") o.multicast = value != 0;
   else if (n == "ln_cluster") o.ln_cluster = value != 0;
+  else if (n == "chain") o.chain = value != 0;
+  else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
   else return fail(DRM_ERR_ARG, "drm_set_option: unknown option '" + n + "'");
   return DRM_OK;
 }
 
 // Debug: enable (on = 1) the in-kernel probe of CTA (0,0) of every fused stage, or read the last probes back
-// (on = 0 with out != NULL: copies DRM_STAGE_COUNT * 16 u64 = {globaltimer ns, clock64} x 8 points per stage).
+// (on = 0 with out != NULL: copies DRM_STAGE_COUNT * (16 + 1024) u64: {globaltimer ns, clock64} x 8 points per stage, then
+// per stage 256 CTA records {entry ns, dependency wait over ns, exit ns, SM id}).
 extern "C" int drm_debug_timeline(int32_t on, unsigned long long* out_host) {
   if (on) {
     if (!g_timeline) {
-      DRM_CUDA(cudaMalloc(&g_timeline, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long)));
-      DRM_CUDA(cudaMemset(g_timeline, 0, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long)));
+      DRM_CUDA(cudaMalloc(&g_timeline, DRM_STAGE_COUNT * (16 + 1024) * sizeof(unsigned long long)));
+      DRM_CUDA(cudaMemset(g_timeline, 0, DRM_STAGE_COUNT * (16 + 1024) * sizeof(unsigned long long)));
     }
     return DRM_OK;
   }
   if (g_timeline && out_host) {
     DRM_CUDA(cudaDeviceSynchronize());
-    DRM_CUDA(cudaMemcpy(out_host, g_timeline, DRM_STAGE_COUNT * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    DRM_CUDA(cudaMemcpy(out_host, g_timeline, DRM_STAGE_COUNT * (16 + 1024) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   }
   if (g_timeline) { cudaFree(g_timeline); g_timeline = nullptr; }
   return DRM_OK;

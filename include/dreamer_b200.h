@@ -63,13 +63,19 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_COUNT 8
 /* Runtime switches for the experimental / alternative kernel paths (all produce identical results):                  */
 /*   "ln_cluster" (default 1)  LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
+/*   "lanes"      (default 0)  rollouts: 2 = two half-batches on two internal streams (bit-identical; measured: slower) */
+/*   "chain"      (default 0)  small grids: each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel, activations */
+/*                             kept in shared memory and exchanged through DSMEM (3 launches per imagined step, not 7;  */
+/*                             measured: the in-kernel exchanges cost more than the launch boundaries they remove)     */
 /*   "gru_u"      (default 0)  GRU tile width: 0 = automatic, 32 or 64 hidden units per tile                           */
 /*   "multicast"  (default 0)  GRU stage in 2-CTA clusters, weight tile halves multicast by TMA (measured: not faster) */
 /*   "zidx"       (default 0)  one-hot latent A tiles built in shared memory from sampled indices (measured: slower)   */
 int drm_set_option(const char* name, int32_t value);
 /* Debug probe: with on = 1 CTA (0,0) of every fused stage records {globaltimer ns, clock64} at 8 points */
 /* (entry, setup done, first TMA issued, first operands landed, last MMA issued, accumulator ready,     */
-/* epilogue done, TMEM freed); on = 0 copies DRM_STAGE_COUNT * 16 u64 to out_host and disables it.       */
+/* epilogue done, TMEM freed) and every CTA records {entry ns, dependency wait over ns, exit ns, SM id};  */
+/* on = 0 copies DRM_STAGE_COUNT * (16 + 1024) u64 to out_host (probes, then 256 CTA records per stage)  */
+/* and disables it.                                                                                     */
 int drm_debug_timeline(int32_t on, unsigned long long* out_host);
 int drm_profile_enable(int32_t on);
 int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches);
@@ -252,6 +258,22 @@ int drm_encoder_fwd(drm_observe* o, const float* h, const float* obs, const floa
 int drm_decoder_fwd(drm_observe* o, const float* h, const float* z, float* mu, int32_t N, void* stream);
 /* -sum((a - b)^2) over each row of `len` floats: WorldModel.py:129.  a, b [rows, len] -> out [rows].       */
 int drm_neg_sse_rows(const float* a, const float* b, float* out, int64_t rows, int32_t len, void* stream);
+
+/* ---- fused optimiser tail on a FLAT parameter group ------------------------------------------------ */
+/* Replaces nn.utils.clip_grad_norm_(params, 100) + torch.optim.AdamW.step (WorldModel.py:195-200; Agent.py:141-151) and,   */
+/* with ema_target, Agent.soft_update_target (Agent.py:90-94).  All buffers are device fp32 [n], 16-byte aligned:            */
+/*   g' = g * min(1, max_norm / (||g||_2 + 1e-6));  p *= 1 - lr*wd;  m += (1-b1)(g'-m);  v = b2 v + (1-b2) g'^2;            */
+/*   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps);   ema = (1-tau) ema + tau p;   g = 0 when zero_grad                */
+/* state: 8 device floats owned by the caller, zero-initialised: [0] step count t (advanced here), [1] gradient norm,        */
+/* [2] clip coefficient, [3] 1.0 when the step was SKIPPED because the norm was not finite (p, m, v, ema, t untouched),       */
+/* [4], [5] bias-correction terms.  scratch: drm_adamw_scratch_bytes() device bytes.  max_norm <= 0 disables clipping.       */
+/* Three launches, no host synchronisation: safe inside CUDA-graph capture.                                                  */
+int64_t drm_adamw_scratch_bytes(void);
+int drm_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state, void* scratch,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float* ema_target,
+                   float tau, int32_t zero_grad, void* stream);
+/* ||grad||_2 over the flat buffer -> norm_out[0] (device float).  Deterministic two-stage reduction (fp64 partials).        */
+int drm_grad_norm(const float* grad, int64_t n, void* scratch, float* norm_out, void* stream);
 
 /* Test hook: plain bf16 GEMM  out[M, N] = A[M, K] * W[N, K]^T + bias  through the same TMA /      */
 /* tcgen05 main loop the fused stages use (fp32 inputs are rounded to bf16 on the device).        */

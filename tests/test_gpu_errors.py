@@ -73,7 +73,7 @@ def test_rollout_is_deterministic():
         assert torch.equal(x, y) and torch.equal(x, w)
 
 
-@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("gru_u", 64), ("gru_u", 32)])
+@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("gru_u", 64), ("gru_u", 32)])
 def test_alternative_kernel_paths_give_identical_results(L, option, value):
     """Every switchable path reproduces the default path on a whole rollout: bit for bit for the one-hot expander, the TMA
     multicast clusters and both GRU tile widths (same per-element accumulation order); to fp32 rounding for the one-CTA LN
@@ -87,13 +87,13 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 200, 4, seed=6))
     base = ro.run(z0, h0, u, n)
     assert lib.drm_set_option(b"nonsense", 1) == -5
-    defaults = dict(zidx=0, multicast=0, ln_cluster=1, gru_u=0)
+    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, gru_u=0)
     try:
         L.check(lib.drm_set_option(option.encode(), value), "set_option")
         alt = ro.run(z0, h0, u, n)
     finally:
         lib.drm_set_option(option.encode(), defaults[option])
-    if option == "ln_cluster":
+    if option in ("ln_cluster", "chain"):
         assert (base[7] != alt[7]).float().mean().item() < 0.01
         same = (base[7] == alt[7]).all(dim=-1).all(dim=-1)          # trajectories whose draws all agree
         for a, b in zip(base[1:7], alt[1:7]):
@@ -101,3 +101,27 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     else:
         for a, b in zip(base, alt):
             assert torch.equal(a, b), option
+
+
+def test_two_lane_rollout_is_bit_identical_to_one_lane(L):
+    """Option "lanes" = 2 runs a rollout as two half-batches on two internal streams (independent rows, the same kernels per
+    row): the outputs must not change, including for a batch that does not split evenly into 128-row tiles."""
+    from dreamer_b200 import ops
+    lib = L.load()
+    cfg = W.small_config()
+    sd = {k: v.to(DEV) for k, v in W.make_state_dict(cfg, seed=5).items()}
+    model = ops.PackedRssm.from_state_dict(sd)
+    for B in (512, 700):
+        ro = ops.Rollout(model, B, 3)
+        z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, 3, seed=B))
+        try:
+            L.check(lib.drm_set_option(b"lanes", 1), "set_option")
+            one = ro.run(z0, h0, u, n)
+            L.check(lib.drm_set_option(b"lanes", 2), "set_option")
+            two = ro.run(z0, h0, u, n)
+        finally:
+            lib.drm_set_option(b"lanes", 0)
+        auto = ro.run(z0, h0, u, n)
+        for a, b, c in zip(one, two, auto):
+            assert torch.equal(a, b) and torch.equal(a, c), B
+    assert lib.drm_set_option(b"lanes", 3) == -5
