@@ -135,3 +135,28 @@ def test_sharded_rollout_concatenates():
         parts = [O.dream_episodes(sd, z0[s], h0[s], u[:, s], n[:, s]) for s in (slice(0, 4), slice(4, 8))]
     assert torch.equal(torch.cat([p[7] for p in parts]), full[7])
     assert torch.allclose(torch.cat([p[1] for p in parts]), full[1], atol=1e-6)
+
+
+def test_optim_oracle_matches_torch():
+    """oracle/optim.py (clip_grad_norm_ + AdamW + soft target update) against the installed torch on CPU."""
+    import torch
+    from oracle import optim as O
+    torch.manual_seed(0)
+    ps = [torch.randn(33, 7), torch.randn(19)]
+    ref = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.AdamW(ref, lr=4e-3, betas=(0.9, 0.95), eps=1e-7, weight_decay=1e-2)
+    p = [x.numpy().copy() for x in ps]
+    m, v, step = [np.zeros_like(x) for x in p], [np.zeros_like(x) for x in p], 0
+    for it in range(6):
+        gs = [torch.randn_like(x) * (50 if it % 2 else 1) for x in ps]     # odd steps: the clip at 100 is active
+        for r, g in zip(ref, gs):
+            r.grad = g.clone()
+        tn = torch.nn.utils.clip_grad_norm_(ref, 100.0)
+        opt.step()
+        step, total = O.adamw_step(p, [g.numpy() for g in gs], m, v, step, 4e-3, (0.9, 0.95), 1e-7, 1e-2, 100.0)
+        assert abs(float(tn) - float(total)) <= 1e-6 * float(tn)
+        for a, b in zip(p, ref):
+            assert np.allclose(a, b.detach().numpy(), rtol=1e-6, atol=1e-7)
+    tgt = [np.ones_like(x) for x in p]
+    O.soft_update(tgt, p, 0.02)
+    assert np.allclose(tgt[0], 0.98 + 0.02 * p[0])
