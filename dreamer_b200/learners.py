@@ -3,7 +3,8 @@
 Forward quantities (states, logits, log-likelihoods, returns, losses) come from the sm_100a kernels.
 Gradients for the two optimiser steps come from ``_tail_*`` below: a device-side torch graph over the
 same parameter containers, teacher-forced on the indices the kernels sampled.  That tail is interim
-(BPTT kernels); optimiser / clipping stay in torch by design.
+(BPTT kernels).  Clipping, AdamW, the target-critic EMA and gradient zeroing run as the fused
+flat-bucket kernels of optim.FlatAdamW (section 8f rank 2).
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import torch.nn.functional as F
 from . import _lib as L
 from . import dist as D
 from . import ops
+from .optim import FlatAdamW, make_adamw
 from .modules import (Actor, ContinuePredictor, Critic, Decoder, DynamicsPredictor, Encoder, RewardPredictor, SequenceModel,
                       _Packed, _VaeEngine, symexp, symlog)
 
@@ -43,7 +45,8 @@ class WorldModel(nn.Module):
         self.continue_predictor = ContinuePredictor(R, C, hidden_dims, cont_pred_hidden_num_nodes_1, cont_pred_hidden_num_nodes_2, device=device)
         self.decoder = Decoder(R, C, observation_dims, hidden_dims, num_decoder_filters_1, num_decoder_filters_2, decoder_hidden_layer_nodes, device=device)
         self.device = device
-        self.optimiser = torch.optim.AdamW(self.parameters(), lr=WM_lr, betas=(WM_betas[0], WM_betas[1]), eps=WM_eps, weight_decay=1e-6)
+        # clip(100) + AdamW(wd 1e-6) fused on one flat 31 MB bucket (WorldModel.py:46,198-199)
+        self.optimiser = make_adamw(self.parameters(), WM_lr, (WM_betas[0], WM_betas[1]), WM_eps, weight_decay=1e-6, max_norm=100.0)
         self.scalar = torch.amp.GradScaler(enabled=False)   # kept for API compatibility: the tail runs in fp32/TF32, no loss scaling
         object.__setattr__(self, "_actor", None)
         object.__setattr__(self, "_engine", _VaeEngine(self._engine_sd, R, C, hidden_dims, action_dims, tuple(observation_dims)))
@@ -124,12 +127,17 @@ class WorldModel(nn.Module):
         tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
                                  self.last["scan"]["idx"], parts)
         tail.backward()
-        if D.is_dist():      # gradients of the global loss = SUM over ranks of the per-rank tails (one flat 31 MB bucket)
-            if self.__dict__.get("_bucket") is None:
-                self.__dict__["_bucket"] = D.FlatBucket(self.parameters())
-            self.__dict__["_bucket"].all_reduce()
-        nn.utils.clip_grad_norm_(self.parameters(), 100.0)
-        self.optimiser.step()
+        if isinstance(self.optimiser, FlatAdamW):
+            # gradients of the global loss = SUM over ranks of the per-rank tails: all-reduce of the flat 31 MB bucket the
+            # gradients were accumulated into, then clip + AdamW + zeroing in three launches
+            self.optimiser.step(all_reduce=True)
+        else:                # parameters moved to the GPU after construction: stock torch optimiser
+            if D.is_dist():
+                if self.__dict__.get("_bucket") is None:
+                    self.__dict__["_bucket"] = D.FlatBucket(self.parameters())
+                self.__dict__["_bucket"].all_reduce()
+            nn.utils.clip_grad_norm_(self.parameters(), 100.0)
+            self.optimiser.step()
         self.last["tail_loss"] = tail.detach()
         return total
 
@@ -212,8 +220,10 @@ class Agent(nn.Module):
         self.buckets = critic_buckets
         self.S = 1.0
         self.smoothing_factor = 0.99
-        self.actor_optimiser = torch.optim.AdamW(params=self.actor.parameters(), lr=A_lr, betas=(A_betas[0], A_betas[1]), eps=A_eps, weight_decay=1e-6)
-        self.critic_optimiser = torch.optim.AdamW(params=self.critic.parameters(), lr=C_lr, betas=(C_betas[0], C_betas[1]), eps=C_eps, weight_decay=1e-6)
+        # Agent.py:30-31,147-153: clip(100) + AdamW per group; the critic's pass also applies the target EMA (Agent.py:90-94)
+        self.actor_optimiser = make_adamw(self.actor.parameters(), A_lr, (A_betas[0], A_betas[1]), A_eps, weight_decay=1e-6, max_norm=100.0)
+        self.critic_optimiser = make_adamw(self.critic.parameters(), C_lr, (C_betas[0], C_betas[1]), C_eps, weight_decay=1e-6, max_norm=100.0,
+                                           ema_params=self.target_critic.parameters(), tau=0.02)
         object.__setattr__(self, "_pk", _Packed(self, "agent.", latent_dims[0], latent_dims[1], hidden_state_dim, action_dim))
         self.last = {}
 
@@ -294,16 +304,22 @@ class Agent(nn.Module):
         sg_t = F.softplus(torch.clamp(self.actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
         logp = _tanh_normal_log_prob(action_batch_seq.detach(), mu_t, sg_t)
         ((-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).sum() / f["n_global"]).backward()
-        if D.is_dist():      # SUM of per-rank shares = gradient of the global means (1.67 MB and 1.47 MB buckets)
-            if self.__dict__.get("_buckets") is None:
-                self.__dict__["_buckets"] = (D.FlatBucket(self.critic.parameters()), D.FlatBucket(self.actor.parameters()))
-            for bkt in self.__dict__["_buckets"]:
-                bkt.all_reduce()
-        torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 100.0)
-        torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 100.0)
-        self.critic_optimiser.step()
-        self.actor_optimiser.step()
-        self.soft_update_target()
+        if isinstance(self.critic_optimiser, FlatAdamW) and isinstance(self.actor_optimiser, FlatAdamW):
+            # SUM of per-rank shares = gradient of the global means (flat 1.67 MB and 1.47 MB buckets); the critic's pass also
+            # moves the target critic: target = 0.98 target + 0.02 updated critic
+            self.critic_optimiser.step(all_reduce=True)
+            self.actor_optimiser.step(all_reduce=True)
+        else:
+            if D.is_dist():
+                if self.__dict__.get("_buckets") is None:
+                    self.__dict__["_buckets"] = (D.FlatBucket(self.critic.parameters()), D.FlatBucket(self.actor.parameters()))
+                for bkt in self.__dict__["_buckets"]:
+                    bkt.all_reduce()
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 100.0)
+            torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 100.0)
+            self.critic_optimiser.step()
+            self.actor_optimiser.step()
+            self.soft_update_target()
         return la, lc
 
 

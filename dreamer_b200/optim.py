@@ -62,12 +62,13 @@ class FlatAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.opt_state = torch.zeros(8, dtype=torch.float32, device=self.flat.device)   # see drm_adamw_step
         self._scratch = torch.zeros(int(L.load().drm_adamw_scratch_bytes()) // 8, dtype=torch.float64, device=self.flat.device)
-        self.ema = None
+        self.ema, self._ema_params = None, None
         if ema_params is not None:
             ema_params = [p for p in ema_params]
             if [p.shape for p in ema_params] != [p.shape for p in params]:
                 raise ValueError("FlatAdamW: ema_params must mirror params")
             self.ema, _ = _flatten(ema_params)
+            self._ema_params = ema_params
         for p, o in zip(params, self._offs):
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
             self.state[p] = {"step": self.opt_state[0], "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape),
@@ -102,6 +103,14 @@ class FlatAdamW(torch.optim.Optimizer):
                                         self.flat.numel(), L.ptr(self.opt_state), L.ptr(self._scratch), g["lr"], g["betas"][0],
                                         g["betas"][1], g["eps"], g["weight_decay"], g["max_norm"] or 0.0, L.ptr(self.ema),
                                         g["tau"], 1 if zero_grad else 0, L.stream()), "adamw_step")
+        self.mark_updated()
+
+    def mark_updated(self):
+        """The kernel writes through raw pointers: bump the autograd version counters so packed-weight caches
+        (modules._Packed, _VaeEngine) see the update.  Call it after replaying a CUDA graph that contains step()."""
+        torch.autograd.graph.increment_version(self._params)
+        if self._ema_params is not None:
+            torch.autograd.graph.increment_version(self._ema_params)
 
     def grad_norm(self) -> torch.Tensor:
         """||g||_2 of the flat bucket (device scalar; after step(): the norm that step saw is ``last_grad_norm``)."""
@@ -135,3 +144,12 @@ class FlatAdamW(torch.optim.Optimizer):
                 self.state[p]["exp_avg"].copy_(st["exp_avg"])
                 self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
                 self.opt_state[0] = float(st["step"])
+
+
+def make_adamw(params, lr, betas, eps, weight_decay=1e-6, max_norm=100.0, ema_params=None, tau=0.02):
+    """FlatAdamW for parameters that live on the GPU.  Modules constructed on the CPU (state_dict / surface work only:
+    no kernel accepts CPU tensors) get a plain torch.optim.AdamW so that construction itself never needs a device."""
+    params = list(params)
+    if params and params[0].is_cuda:
+        return FlatAdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm, ema_params=ema_params, tau=tau)
+    return torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
