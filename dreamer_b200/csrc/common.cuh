@@ -253,13 +253,13 @@ __device__ __forceinline__ float tanhf_(float x) {  // 1 - 2 / (1 + e^{2x}); sat
 }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float symexpf_(float x) {  // DreamerUtils.py:35-37
-  x = fminf(fmaxf(x, -20.0f), 20.0f);
-  float e = expf(fabsf(x)) - 1.0f;
-  return x > 0.f ? e : (x < 0.f ? -e : 0.f);
+  const float c = fminf(fmaxf(x, -20.0f), 20.0f);   // fminf / fmaxf drop a NaN; torch.clamp keeps it -> x * 0 below restores it
+  float e = expf(fabsf(c)) - 1.0f;
+  return c > 0.f ? e : (c < 0.f ? -e : x * 0.f);
 }
 __device__ __forceinline__ float symlogf_(float x) {  // DreamerUtils.py:29-30
   float l = logf(1.0f + fabsf(x));
-  return x > 0.f ? l : (x < 0.f ? -l : 0.f);
+  return x > 0.f ? l : (x < 0.f ? -l : x * 0.f);   // NaN stays NaN (torch: sign(x) * log(1 + |x|))
 }
 __device__ __forceinline__ float softplusf_(float x) {  // torch softplus, beta=1, threshold=20
   return x > 20.0f ? x : log1pf(expf(x));

@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(256) twohot_ce_kernel(const float* __restrict_
       if (apply_symlog) v = symlogf_(v);
       int idx; float w;
       twohot_index_weight(sb, NB, v, idx, w);
-      ll[row] = (1.0f - w) * (__ldg(x + idx) - lse) + w * (__ldg(x + idx + 1) - lse);
+      // a NaN target stays NaN (torch.clamp / the two-hot weights propagate it, DreamerUtils.py:41-49): the caller's skip sees it
+      ll[row] = (v != v) ? v : (1.0f - w) * (__ldg(x + idx) - lse) + w * (__ldg(x + idx + 1) - lse);
     }
   }
 }

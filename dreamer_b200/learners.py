@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from . import _lib as L
 from . import dist as D
 from . import ops
+from .graphs import StepGraph
 from .optim import FlatAdamW, make_adamw
 from .modules import (Actor, ContinuePredictor, Critic, Decoder, DynamicsPredictor, Encoder, RewardPredictor, SequenceModel,
                       _Packed, _VaeEngine, symexp, symlog)
@@ -111,17 +112,26 @@ class WorldModel(nn.Module):
         kl = ops.categorical32_kl(post, prior)                      # forward value of both KL terms (they differ only in stop-gradients)
         # per-rank sums -> one packed all-reduce -> the GLOBAL loss on every rank (a no-op for a single process)
         local = torch.stack([(obs_ll * m1).sum(), (rew_ll * mask).sum(), (cont_ll * mask).sum(), mask.sum(), (kl * m1).sum(),
-                             torch.tensor(float(kl.numel()), device=kl.device)])
+                             torch.full((), float(kl.numel()), device=kl.device)])
         total, parts = D.world_model_loss_from_sums(local, (self.beta_pred, self.beta_dyn, self.beta_rep))
         parts["obs_norm"] = obs
         return total, parts
 
     # ---- WorldModel.py:148-202 -------------------------------------------------------------
     def training_step(self, observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms=None):
+        graphs = self.__dict__.get("_graphs")
+        if graphs is not None:                 # enable_cuda_graphs(): eager warm-up calls, then one captured step replayed
+            if uniforms is None:
+                uniforms = torch.rand(self.horizon, continue_sequences.shape[0], self.latent_num_rows, device=continue_sequences.device)
+            return graphs(L.f32c(observation_sequences), L.f32c(action_sequences), L.f32c(reward_sequences),
+                          L.f32c(continue_sequences), uniforms).clone()
         total, parts = self.loss_forward(observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms)
         if D.any_rank_flag(bool(torch.isnan(total) or torch.isinf(total)), total.device):
             print("World Model loss is nan or inf, skipping update.")
             return total
+        return self._backward_and_step(total, parts, action_sequences, reward_sequences, continue_sequences)
+
+    def _backward_and_step(self, total, parts, action_sequences, reward_sequences, continue_sequences):
         T = self.horizon
         self.optimiser.zero_grad()
         tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
@@ -140,6 +150,23 @@ class WorldModel(nn.Module):
             self.optimiser.step()
         self.last["tail_loss"] = tail.detach()
         return total
+
+    def _step_body(self, obs, act, rew, cont, uniforms):
+        """One whole training step with no host synchronisation (capturable).  The reference's host-side NaN/Inf check
+        (WorldModel.py:191) becomes the optimiser's device-side skip: a non-finite loss gives a non-finite gradient norm."""
+        total, parts = self.loss_forward(obs, act, rew, cont, uniforms)
+        return self._backward_and_step(total, parts, act, rew, cont)
+
+    def enable_cuda_graphs(self, warmup: int = 3):
+        """Replay training_step as one CUDA graph per input shape after `warmup` eager steps (graphs.StepGraph)."""
+        if not isinstance(self.optimiser, FlatAdamW):
+            raise RuntimeError("enable_cuda_graphs needs the flat fused optimiser (construct the WorldModel on the GPU)")
+
+        def before_capture():
+            self._engine.versions = None           # the captured step must contain the weight re-pack
+
+        self.__dict__["_graphs"] = StepGraph(self._step_body, warmup, before_capture, self.optimiser.mark_updated)
+        return self
 
 
 def _st_latent(logits, idx, C):
@@ -160,10 +187,10 @@ def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx, parts=None):
     With `parts` (the globally reduced denominators) the value is this rank's additive share of the global loss, so the
     SUM of the per-rank gradients is the gradient of the global loss; on one process it equals the loss itself."""
     B, T = obs.shape[:2]
-    R, C, D = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
+    R, C, Dh = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
     dev = obs.device
     feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:])).flatten(1).view(B, T, -1)
-    h = torch.zeros(B, D, device=dev)
+    h = torch.zeros(B, Dh, device=dev)
     z = torch.zeros(B, R * C, device=dev)
     hs, zs, post = [], [], []
     for t in range(T):
@@ -183,7 +210,7 @@ def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx, parts=None):
     m1 = mask.squeeze(-1)
     obs_ll = -((dec.float() - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
     b = wm.reward_predictor.buckets_rew
-    v = rew[:, :T - 1].clamp(float(b.min()), float(b.max()))
+    v = torch.maximum(torch.minimum(rew[:, :T - 1], b[-1]), b[0])       # clamp to the (sorted) bucket range, no host read
     lo = torch.clamp(torch.searchsorted(b, v.contiguous(), right=True) - 1, max=len(b) - 2)
     w = (v - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
     lsm = F.log_softmax(rl, -1)
@@ -201,8 +228,8 @@ def _tail_world_model(wm: WorldModel, obs, act, rew, cont, idx, parts=None):
         one = torch.ones((), device=dev)
         return wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn) + wm.beta_rep * torch.maximum(one, rep)
     # free bits on the GLOBAL mean: below 1 the KL terms are the constant 1 (no gradient), above it they are linear in the sums
-    live = 1.0 if float(kl_mean) > 1.0 else 0.0
-    const = 0.0 if live else (wm.beta_dyn + wm.beta_rep) / D.world()
+    live = (kl_mean > 1.0).to(loss_pred.dtype)               # device-side: no host read of the global mean
+    const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
     return wm.beta_pred * loss_pred + live * (wm.beta_dyn * dyn + wm.beta_rep * rep) + const
 
 
@@ -233,10 +260,10 @@ class Agent(nn.Module):
         return ws.heads(h.reshape(B * S, -1), z.reshape(B * S, -1), heads, want_logits=want_logits)
 
     def update_S(self, lambda_returns):
-        """Agent.py:78-88 (percentiles by sort + linear interpolation, the definition torch.quantile uses)."""
+        """Agent.py:78-88 (percentiles by sort + linear interpolation, the definition torch.quantile uses).  S lives on the
+        device and is updated in place; a non-finite return set leaves it unchanged (Agent.py:80-81) -- decided on the device."""
         flat = D.all_gather_cat(lambda_returns.detach().flatten())     # percentiles over the GLOBAL return set
-        if torch.isnan(flat).any() or torch.isinf(flat).any():
-            return
+        ok = torch.isfinite(flat).all()
         s, _ = torch.sort(flat)
         n = s.numel()
 
@@ -248,7 +275,9 @@ class Agent(nn.Module):
 
         rng = torch.maximum(q(0.95) - q(0.05), torch.ones((), device=flat.device))
         alpha = 1.0 - self.smoothing_factor
-        self.S = (1.0 - alpha) * self.S + alpha * rng
+        if not isinstance(self.S, torch.Tensor):
+            self.S = torch.full((), float(self.S), dtype=torch.float32, device=flat.device)
+        self.S.copy_(torch.where(ok, (1.0 - alpha) * self.S + alpha * rng, self.S))
 
     def soft_update_target(self, tau=0.02):
         with torch.no_grad():
@@ -272,21 +301,52 @@ class Agent(nn.Module):
         adv = (R - v[:, :-1]).squeeze(-1)
         logp = _tanh_normal_log_prob(act, mu, sigma)
         self.update_S(R)
-        norm = torch.maximum(torch.as_tensor(self.S, dtype=torch.float32, device=R.device), torch.ones((), device=R.device))
+        norm = torch.maximum(self.S, torch.ones((), device=R.device))
         ce = -ops.twohot_ce(hd["value_logits"].view(B, H1, -1)[:, :-1], R, self.critic.buckets_crit, apply_symlog=True)
         sums = D.all_reduce_sum_(torch.stack([(-(logp * (adv / norm)) - self.nu * (-logp)).sum(), ce.sum(),
-                                              torch.tensor(float(logp.numel()), device=R.device)]))
+                                              torch.full((), float(logp.numel()), device=R.device)]))
         n_glob = sums[2]
         return dict(loss_actor=sums[0] / n_glob, loss_critic=sums[1] / n_glob, returns=R, values=v, target_values=v_t, advantage=adv,
                     log_prob=logp, norm=norm, n_global=n_glob)
 
     def train_step(self, z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq):
+        graphs = self.__dict__.get("_graphs")
+        if graphs is not None:                 # enable_cuda_graphs(): eager warm-up calls, then one captured step replayed
+            la, lc = graphs(*(L.f32c(t) for t in (z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq,
+                                                  a_mu_batch_seq, a_sigma_batch_seq)))
+            return la.clone(), lc.clone()
         f = self.losses_forward(z_batch_seq, h_batch_seq, reward_batch_seq, continue_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq)
         la, lc = f["loss_actor"], f["loss_critic"]
         self.last = f
         if D.any_rank_flag(bool(torch.isnan(la) or torch.isinf(la) or torch.isnan(lc) or torch.isinf(lc)), la.device):
             print("Agent loss is nan or inf, skipping update.")
             return la, lc
+        return self._backward_and_step(f, z_batch_seq, h_batch_seq, action_batch_seq)
+
+    def _step_body(self, z, h, rew, cont, act, mu, sigma):
+        """One whole Agent.train_step with no host synchronisation (capturable); non-finite losses are skipped by the
+        optimisers' device-side check instead of Agent.py:137-139."""
+        f = self.losses_forward(z, h, rew, cont, act, mu, sigma)
+        self.last = f
+        return self._backward_and_step(f, z, h, act)
+
+    def enable_cuda_graphs(self, warmup: int = 3):
+        """Replay train_step as one CUDA graph per input shape after `warmup` eager steps (graphs.StepGraph)."""
+        if not (isinstance(self.critic_optimiser, FlatAdamW) and isinstance(self.actor_optimiser, FlatAdamW)):
+            raise RuntimeError("enable_cuda_graphs needs the flat fused optimisers (construct the Agent on the GPU)")
+
+        def before_capture():
+            self._pk.invalidate()                  # the captured step must contain the weight re-pack
+
+        def after_replay():
+            self.critic_optimiser.mark_updated()
+            self.actor_optimiser.mark_updated()
+
+        self.__dict__["_graphs"] = StepGraph(self._step_body, warmup, before_capture, after_replay)
+        return self
+
+    def _backward_and_step(self, f, z_batch_seq, h_batch_seq, action_batch_seq):
+        la, lc = f["loss_actor"], f["loss_critic"]
         # gradients (interim torch tail): critic CE on the kernel's returns; policy gradient through mu, sigma recomputed on the
         # (detached) imagined states -- the through-the-world-model term (about 3 % at init, SURVEY.md section 3C) needs the BPTT kernels.
         B, H1 = h_batch_seq.shape[:2]
@@ -294,7 +354,7 @@ class Agent(nn.Module):
         self.critic_optimiser.zero_grad()
         lsm = F.log_softmax(self.critic.value_net(hz[:, :-1]), -1)
         b = self.critic.buckets_crit
-        tv = symlog(f["returns"]).clamp(float(b.min()), float(b.max()))
+        tv = torch.maximum(torch.minimum(symlog(f["returns"]), b[-1]), b[0])   # clamp to the (sorted) bucket range, no host read
         lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
         w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
         ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / f["n_global"]).backward()

@@ -88,6 +88,10 @@ class _Packed:
             self.versions = vers
         return self.model
 
+    def invalidate(self):
+        """Force the next use to re-pack (a captured CUDA graph must contain the pack kernels)."""
+        self.versions = None
+
     def workspace(self, n_rows: int) -> ops.Rollout:
         model = self.get()
         cap = max(128, 1 << (max(n_rows, 1) - 1).bit_length())

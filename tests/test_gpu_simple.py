@@ -143,3 +143,18 @@ def test_tcgen05_gemm_mainloop(ops, M, N, K):
     ref = A.bfloat16().float() @ Wt.bfloat16().float().T + bias
     got = ops.test_gemm(A.to(DEV), Wt.to(DEV), bias.to(DEV)).cpu()
     assert torch.allclose(got, ref, rtol=1e-4, atol=2e-4), (got - ref).abs().max()
+
+
+def test_nan_targets_propagate_like_torch():
+    """torch.clamp / sign * log keep a NaN (DreamerUtils.py:29-50): the two-hot CE of a NaN target is NaN, so the reference's
+    NaN-loss skip (and the fused optimiser's device-side skip) sees it; finite rows are untouched."""
+    from dreamer_b200 import ops
+    r = torch.randn(4, 5, 1, device=DEV)
+    r[0, 0, 0] = float("nan")
+    R = ops.lambda_return(r, torch.ones_like(r), torch.randn(4, 6, 1, device=DEV), 0.99, 0.95)
+    assert torch.isnan(R[0, 0, 0]) and torch.isfinite(R[1:]).all()
+    b = torch.linspace(-20, 20, 255, device=DEV)
+    lg = torch.randn(4, 5, 255, device=DEV)
+    for sym in (False, True):
+        ce = ops.twohot_ce(lg, R, b, apply_symlog=sym)
+        assert torch.isnan(ce[0, 0, 0]) and torch.isfinite(ce[1:]).all() and torch.isfinite(ce[0, 1:]).all()
