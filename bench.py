@@ -205,9 +205,28 @@ def secondary_metrics(dev, peaks, flush):
     obs, act, rew, cont, uu = (x.to(dev) for x in W.sequence_inputs(cfg, 16, 64, seed=4321))
     t_f = dev_time(lambda: wm.loss_forward(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
     t_s = dev_time(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
+    wm.enable_cuda_graphs(warmup=1)          # the same step replayed as ONE CUDA graph (dreamer_b200/graphs.py)
+    t_g = dev_time(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu), reps=10, warm=3)
     out["world_model_c3"] = dict(workload="batch 16 x seq 64, 64x64x3 frames (BASELINE configs[2])", loss_forward_steps_per_s=1.0 / t_f,
-                                 loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_s, train_step_ms=t_s * 1e3,
-                                 note="training step = kernel forward + interim torch autograd tail + AdamW (DESIGN.md section 6)")
+                                 loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_g, train_step_ms=t_g * 1e3,
+                                 eager_train_step_ms=t_s * 1e3,
+                                 note="training step = kernel forward + interim torch autograd tail + fused clip/AdamW on the flat bucket, "
+                                      "replayed as one CUDA graph (DESIGN.md section 6); eager_train_step_ms is the same step issued launch by launch")
+    del wm
+    # actor-critic update on a config-2 rollout (1024 x 15): Agent.train_step, eager and as one CUDA graph
+    cfg2 = dict(W.REF_CONFIG, horizon=15)
+    _, ag = W.build_learners(cfg2, W.make_state_dict(cfg2, seed=0), dev)
+    zz = torch.nn.functional.one_hot(torch.randint(0, 32, (1024, 16, 32), device=dev), 32).float()
+    hh = torch.tanh(torch.randn(1024, 16, cfg2["hidden_state_dims"], device=dev))
+    rr, cc = torch.randn(1024, 15, 1, device=dev), torch.ones(1024, 15, 1, device=dev)
+    mu_, sg_ = torch.randn(1024, 15, 3, device=dev) * 0.3, torch.rand(1024, 15, 3, device=dev) * 0.5 + 0.1
+    aa = torch.tanh(mu_ + sg_ * torch.randn_like(mu_))
+    t_a = dev_time(lambda: ag.train_step(zz, hh, rr, cc, aa, mu_, sg_), reps=5, warm=2)
+    ag.enable_cuda_graphs(warmup=1)
+    t_ag = dev_time(lambda: ag.train_step(zz, hh, rr, cc, aa, mu_, sg_), reps=10, warm=3)
+    out["agent_step_c2"] = dict(workload="Agent.train_step on 1024 x 15 imagined states", train_step_ms=t_ag * 1e3, eager_train_step_ms=t_a * 1e3,
+                                states_per_s=1024 * 15 / t_ag)
+    del ag, zz, hh
     # the north star's large-batch points: 16 384 start states x horizon 15 on this one GPU (GRU stage vs the measured bf16 peak)
     import ctypes as C
     from dreamer_b200 import _lib as L

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
                                                             const float* __restrict__ uniforms,
                                                             uint8_t* __restrict__ idx_out, float* __restrict__ z_st,
                                                             float* __restrict__ probs, uint16_t* __restrict__ z_bf16,
-                                                            int64_t n_rows) {
+                                                            int64_t n_rows, const uint8_t* __restrict__ idx_in) {
   __shared__ float tiles[8][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float(*t)[33] = tiles[w];
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
       if (r < nr) x = __ldg(reinterpret_cast<const float4*>(logits + (row0 + r) * 32 + c));
       t[r][c] = x.x; t[r][c + 1] = x.y; t[r][c + 2] = x.z; t[r][c + 3] = x.w;
     }
-    const float u = lane < nr ? __ldg(uniforms + row0 + lane) : 0.f;
+    const float u = (uniforms && lane < nr) ? __ldg(uniforms + row0 + lane) : 0.f;
     __syncwarp();
     float v[32];
     float mx = -INFINITY;
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
       idx += (cdf <= u) ? 1 : 0;
     }
     idx = idx > 31 ? 31 : idx;
+    if (idx_in && lane < nr) idx = min((int)idx_in[row0 + lane], 31);   // teacher forcing: the class is given, not drawn
     if (idx_out && lane < nr) idx_out[row0 + lane] = (uint8_t)idx;   // 32 consecutive bytes per warp
     if (probs) {
       __syncwarp();
@@ -118,6 +119,58 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
           *reinterpret_cast<uint4*>(z_bf16 + (row0 + r) * 32 + c) = make_uint4(q[0], q[1], q[2], q[3]);
         }
       }
+    }
+    __syncwarp();
+  }
+}
+
+// Backward of the straight-through sample z = onehot + p - stopgrad(p), p = 0.99 softmax(l) + 0.01 / 32
+// (DynamicsPredictors.py:33-39, VariationalAutoEncoder.py:88-98):  dl = 0.99 * s * (g - sum_j s_j g_j), s = softmax(l), g = dz.
+// Same tiling as the forward: a warp owns 32 rows, coalesced float4 tile loads, one row per lane.
+__global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dz,
+                                                                float* __restrict__ dlogits, int64_t n_rows) {
+  __shared__ float tiles[8][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float(*t)[33] = tiles[w];
+  const int64_t warp = (int64_t)blockIdx.x * 8 + w;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int64_t ntiles = (n_rows + 31) >> 5;
+  for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+    const int64_t row0 = tile << 5;
+    const int nr = (int)min((int64_t)32, n_rows - row0);
+    float s[32], g[32];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* src = pass ? dz : logits;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) x = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * 32 + c));
+        t[r][c] = x.x; t[r][c + 1] = x.y; t[r][c + 2] = x.z; t[r][c + 3] = x.w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) (pass ? g : s)[j] = t[lane][j];
+      __syncwarp();
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, s[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s[j] *= inv; dot = fmaf(s[j], g[j], dot); }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[lane][j] = 0.99f * s[j] * (g[j] - dot);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
+      if (r < nr) *reinterpret_cast<float4*>(dlogits + (row0 + r) * 32 + c) = make_float4(t[r][c], t[r][c + 1], t[r][c + 2], t[r][c + 3]);
     }
     __syncwarp();
   }
@@ -336,7 +389,31 @@ extern "C" int drm_categorical32_fwd(const float* logits, const float* uniforms,
   DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && (!z_st || (uintptr_t)z_st % 16 == 0) && (!probs || (uintptr_t)probs % 16 == 0) &&
                   (!z_bf16 || (uintptr_t)z_bf16 % 16 == 0),
               DRM_ERR_ALIGN, "drm_categorical32_fwd: 16-byte alignment required");
-  categorical32_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows);
+  categorical32_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, uniforms, idx, z_st, probs, z_bf16, n_rows, nullptr);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_categorical32_st(const float* logits, const uint8_t* idx, float* z_st, float* probs, int64_t n_rows, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_st: n_rows < 0");
+  if (n_rows == 0) return DRM_OK;
+  DRM_REQUIRE(logits && idx, DRM_ERR_ARG, "drm_categorical32_st: logits/idx are NULL");
+  DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && (!z_st || (uintptr_t)z_st % 16 == 0) && (!probs || (uintptr_t)probs % 16 == 0), DRM_ERR_ALIGN,
+              "drm_categorical32_st: 16-byte alignment required");
+  categorical32_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, nullptr, nullptr, z_st, probs, nullptr, n_rows, idx);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_categorical32_bwd(const float* logits, const float* dz, float* dlogits, int64_t n_rows, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_bwd: n_rows < 0");
+  if (n_rows == 0) return DRM_OK;
+  DRM_REQUIRE(logits && dz && dlogits, DRM_ERR_ARG, "drm_categorical32_bwd: NULL pointer");
+  DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)dlogits % 16 == 0), DRM_ERR_ALIGN,
+              "drm_categorical32_bwd: 16-byte alignment required");
+  categorical32_bwd_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dlogits, n_rows);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -43,6 +43,37 @@ def categorical32(logits: torch.Tensor, uniforms: torch.Tensor, want_probs: bool
     return out
 
 
+class _StraightThrough(torch.autograd.Function):
+    """z = onehot(idx) + p - stopgrad(p) on GIVEN classes, one kernel forward and one backward
+    (drm_categorical32_st / drm_categorical32_bwd) instead of ~8 + ~12 elementwise launches per call."""
+
+    @staticmethod
+    def forward(ctx, logits, idx):
+        lg = L.f32c(logits)
+        ix = idx.to(torch.uint8).contiguous()
+        z = torch.empty_like(lg)
+        L.check(L.load().drm_categorical32_st(L.ptr(lg), L.ptr(ix), L.ptr(z), None, lg.numel() // 32, L.stream()), "categorical32_st")
+        ctx.save_for_backward(lg)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        (lg,) = ctx.saved_tensors
+        g = L.f32c(dz)
+        out = torch.empty_like(lg)
+        L.check(L.load().drm_categorical32_bwd(L.ptr(lg), L.ptr(g), L.ptr(out), lg.numel() // 32, L.stream()), "categorical32_bwd")
+        return out, None
+
+
+def straight_through(logits: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Differentiable straight-through latent on given classes: logits (..., 32), idx (...) -> z (..., 32).
+    DynamicsPredictors.py:33-39 / VariationalAutoEncoder.py:88-98 with the draw replaced by `idx` (teacher forcing)."""
+    L.require_cuda(logits, "logits")
+    if logits.shape[-1] != 32 or tuple(idx.shape) != tuple(logits.shape[:-1]):
+        raise RuntimeError("dreamer_b200.straight_through: logits (..., 32) and idx (...) are required")
+    return _StraightThrough.apply(logits, idx)
+
+
 def categorical32_kl(post_logits: torch.Tensor, prior_logits: torch.Tensor) -> torch.Tensor:
     """(..., R, 32) x2 -> (...) sum over R of KL(Cat(post)||Cat(prior)).  WorldModel.py:175-181."""
     L.require_cuda(post_logits, "post_logits")

@@ -90,6 +90,11 @@ int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches);
 /*   z_bf16 [n_rows, 32] bf16 one-hot (raw uint16 storage).                                     */
 int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* idx, float* z_st, float* probs,
                           uint16_t* z_bf16, int64_t n_rows, void* stream);
+/* Teacher-forced forward (the class idx [n_rows] u8 is given, not drawn): z_st = (onehot(idx) + p) - p and/or  */
+/* probs p = 0.99 softmax + 0.01/32.  Used by the gradient tail, which replays the classes the scan sampled.    */
+int drm_categorical32_st(const float* logits, const uint8_t* idx, float* z_st, float* probs, int64_t n_rows, void* stream);
+/* Backward of the straight-through sample: dlogits = 0.99 * s * (dz - sum_j s_j dz_j), s = softmax(logits).    */
+int drm_categorical32_bwd(const float* logits, const float* dz, float* dlogits, int64_t n_rows, void* stream);
 /* KL balance terms of WorldModel.training_step  WorldModel.py:175-181:                         */
 /*   kl[g] = sum over the `rows_per_group` categorical rows of group g of KL(Cat(post)||Cat(prior)) */
 /* post/prior logits [n_groups * rows_per_group, 32] fp32 -> kl [n_groups] fp32.                 */

@@ -158,3 +158,23 @@ def test_nan_targets_propagate_like_torch():
     for sym in (False, True):
         ce = ops.twohot_ce(lg, R, b, apply_symlog=sym)
         assert torch.isnan(ce[0, 0, 0]) and torch.isfinite(ce[1:]).all() and torch.isfinite(ce[0, 1:]).all()
+
+
+def test_straight_through_forward_and_backward_match_autograd():
+    """ops.straight_through (teacher-forced ST latent, one kernel each way) against the torch expression the reference
+    differentiates (DynamicsPredictors.py:33-39): value bit-exact, gradient to fp32 rounding; ragged row count."""
+    from dreamer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n in (1, 37, 4096 + 5):
+        lg = (torch.randn(n, 32, device=DEV, generator=g) * 3).requires_grad_(True)
+        idx = torch.randint(0, 32, (n,), device=DEV, generator=g, dtype=torch.uint8)
+        w = torch.randn(n, 32, device=DEV, generator=g)
+        z = ops.straight_through(lg, idx)
+        (z * w).sum().backward()
+        g_kernel = lg.grad.clone()
+        lg.grad = None
+        p = 0.99 * torch.softmax(lg, -1) + 0.01 / 32
+        z_ref = (torch.nn.functional.one_hot(idx.long(), 32).float() + p) - p.detach()
+        (z_ref * w).sum().backward()
+        assert torch.equal(z.detach() != 0, z_ref.detach() != 0) and torch.allclose(z.detach(), z_ref.detach(), atol=1e-7)
+        assert torch.allclose(g_kernel, lg.grad, rtol=1e-4, atol=1e-6)
