@@ -1,0 +1,154 @@
+"""Hand-scheduled back-propagation through time for WorldModel.training_step (first stage).
+
+The loss of WorldModel.py:156-188 has ONE recurrent dependency: h_t = GRU([z_{t-1}, a_{t-1}], h_{t-1})
+(SequenceModel.py:19-24); everything else -- encoder convs, posterior MLP, prior MLP, decoder, reward / continue heads, KL --
+is a function of (h_t, z_t, obs_t) at one time step.  A torch autograd graph over the Python scan spends ~70 launches per time
+step (3 850 per step at batch 16 x sequence 64) on 16-row tensors.  Here instead:
+
+  1. everything non-recurrent is evaluated ONCE, batched over all B*T rows, on the teacher-forced trajectory the scan kernels
+     produced (hidden states and sampled classes); autograd handles that batched graph (decoder / encoder convs, heads);
+  2. the recurrence is walked backwards with 7 launches per step: the straight-through backward (drm_categorical32_bwd), the
+     posterior MLP's input gradient (2 library GEMMs + drm_ln_silu_bwd), the GRU cell backward (drm_gru_bwd) and 2 library GEMMs;
+  3. every weight gradient is a batched GEMM over all B*T rows after the walk.
+
+Gradients are accumulated into the parameters' ``.grad`` (the flat bucket of optim.FlatAdamW).  The autograd tail
+(learners._tail_world_model) stays as the reference this is tested against (tests/test_gpu_bptt.py).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as D
+from . import ops
+
+
+def _acc(p: torch.nn.Parameter, g: torch.Tensor):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    p.grad.add_(g.view_as(p))
+
+
+def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
+    """p.grad += a_t^T @ b   (a_t [rows, out], b [rows, in])"""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    p.grad.addmm_(a_t.t(), b)
+
+
+def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
+    """Accumulate d(loss)/d(parameters) of WorldModel.training_step into ``.grad``; returns the (detached) loss value of the
+    batched fp32 re-evaluation.
+
+    obs (B,T,3,H,W) normalised, act (B,T,A), rew / cont (B,T,1), idx (B,T,R) classes the scan sampled, hidden (B,T,D) its h_t.
+    `parts` as in learners._tail_world_model (globally reduced denominators for data-parallel shares)."""
+    B, T = obs.shape[:2]
+    R, C, Dh = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
+    if C != 32:
+        raise RuntimeError("world_model_backward: 32-class latents are required (drm_categorical32_bwd)")
+    dev = obs.device
+    Z = R * C
+    gru = wm.sequence_model.GRU
+    lin1, ln1, _, lin2 = wm.encoder.latent_mapper
+    n_feat = lin1.weight.shape[1] - Dh
+
+    # ---- (1a) teacher-forced trajectory and the recurrent pre-activations, batched (no autograd) ----------------------------
+    with torch.no_grad():
+        Hk = hidden.detach().to(torch.float32)
+        z_oh = F.one_hot(idx.long(), C).to(torch.float32).view(B, T, Z)
+        H_tm = Hk.transpose(0, 1).contiguous()                                  # (T,B,D)   h_t
+        Hprev = torch.zeros_like(H_tm)
+        Hprev[1:] = H_tm[:-1]                                                   # h_{t-1}, h_{-1} = 0 (WorldModel.py:92-95)
+        X = torch.zeros(T, B, Z + act.shape[-1], device=dev)
+        X[1:, :, :Z] = z_oh.transpose(0, 1)[:-1]
+        X[1:, :, Z:] = act.transpose(0, 1)[:-1]                                 # x_t = [z_{t-1}, a_{t-1}], zeros at t = 0
+        GI = torch.addmm(gru.bias_ih, X.view(T * B, -1), gru.weight_ih.t()).view(T, B, 3 * Dh)
+        GH = torch.addmm(gru.bias_hh, Hprev.view(T * B, -1), gru.weight_hh.t()).view(T, B, 3 * Dh)
+    # encoder convs: the one autograd graph that is closed later with d(loss)/d(features)
+    feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:])).flatten(1)          # (B*T, n_feat)
+    with torch.no_grad():
+        X1 = torch.cat([feats.detach().view(B, T, n_feat).transpose(0, 1), H_tm], -1).contiguous()   # (T,B,n_feat+D)
+        A1 = torch.addmm(lin1.bias, X1.view(T * B, -1), lin1.weight.t())
+        Y1 = F.silu(F.layer_norm(A1, (A1.shape[-1],), ln1.weight, ln1.bias, ln1.eps))
+        LG = torch.addmm(lin2.bias, Y1, lin2.weight.t()).view(T, B, Z)          # posterior logits, time-major
+
+    # ---- (1b) everything that reads (h_t, z_t) at one step: batched autograd on leaves --------------------------------------
+    Hl = Hk.clone().requires_grad_(True)                                        # (B,T,D)
+    Zl = z_oh.clone().requires_grad_(True)                                      # (B,T,Z)
+    LGl = LG.transpose(0, 1).reshape(B, T, R, C).clone().requires_grad_(True)   # posterior logits as a leaf (KL terms)
+    prior = wm.dynamics_predictor.logit_net(Hl).view(B, T, R, C)
+    hz = torch.cat([Hl, Zl], -1)
+    x = wm.decoder.upscaler(hz.reshape(B * T, -1)).view(B * T, wm.decoder.num_filters_start, wm.decoder.start_height, wm.decoder.start_width)
+    dec = wm.decoder.image_builder(x).view(obs.shape)
+    rl = wm.reward_predictor.logit_net(hz[:, 1:])
+    cl = wm.continue_predictor.logit_generator(hz[:, 1:])
+    mask = cont[:, :T - 1]
+    m1 = mask.squeeze(-1)
+    obs_ll = -((dec.float() - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
+    b = wm.reward_predictor.buckets_rew
+    v = torch.maximum(torch.minimum(rew[:, :T - 1], b[-1]), b[0])
+    lo = torch.clamp(torch.searchsorted(b, v.contiguous(), right=True) - 1, max=len(b) - 2)
+    w = (v - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+    lsm = F.log_softmax(rl, -1)
+    rew_ll = ((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)) * mask
+    cont_ll = F.binary_cross_entropy_with_logits(cl, mask, reduction='none') * mask
+
+    def cat_kl(lp_logits, lq_logits):
+        lp = F.log_softmax(lp_logits, -1)
+        lq = F.log_softmax(lq_logits, -1)
+        return (lp.exp() * (lp - lq)).sum(-1).sum(-1)
+
+    dyn_sum = (cat_kl(LGl[:, 1:].detach(), prior[:, 1:]) * m1).sum()
+    rep_sum = (cat_kl(LGl[:, 1:], prior[:, 1:].detach()) * m1).sum()
+    if parts is None:
+        denom, n_el = mask.sum() + 1e-5, float(m1.numel())
+        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
+        one = torch.ones((), device=dev)
+        loss = wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn_sum / n_el) + wm.beta_rep * torch.maximum(one, rep_sum / n_el)
+    else:
+        denom, n_el, kl_mean = parts["denom"], parts["n_elements"], parts["kl_mean"]
+        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
+        live = (kl_mean > 1.0).to(loss_pred.dtype)
+        const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
+        loss = wm.beta_pred * loss_pred + live * (wm.beta_dyn * (dyn_sum / n_el) + wm.beta_rep * (rep_sum / n_el)) + const
+    loss.backward()          # parameter gradients of prior / decoder / heads; d/dh, d/dz, d/dlogits at every step
+
+    with torch.no_grad():
+        gH = Hl.grad.transpose(0, 1).contiguous()                               # (T,B,D)  accumulates the total d/dh_t
+        gZ = Zl.grad.transpose(0, 1).contiguous()                               # (T,B,Z)  direct d/dz_t (decoder, reward, continue)
+        gLG = LGl.grad.view(B, T, Z).transpose(0, 1).contiguous()               # (T,B,Z)  KL terms on the posterior logits
+        # ---- (2) the recurrence, backwards: 7 launches per step ---------------------------------------------------------
+        dLG = torch.empty(T, B, Z, device=dev)
+        dGI = torch.empty(T, B, 3 * Dh, device=dev)
+        dGH = torch.empty(T, B, 3 * Dh, device=dev)
+        W2 = lin2.weight                                                        # (Z, Hn)
+        W1h = lin1.weight[:, n_feat:].contiguous()                              # (Hn, D)
+        Wih_z = gru.weight_ih[:, :Z].contiguous()                               # (3D, Z)
+        Whh = gru.weight_hh                                                     # (3D, D)
+        A1_tm = A1.view(T, B, -1)
+        dz_carry = None
+        for t in range(T - 1, -1, -1):
+            ops.categorical32_bwd(LG[t], gZ[t], dz_carry, gLG[t], out=dLG[t])   # through the ST sample, + the KL term
+            dA1 = ops.ln_silu_bwd(dLG[t] @ W2, A1_tm[t], ln1.weight, ln1.bias, ln1.eps)
+            gH[t].addmm_(dA1, W1h)                                              # d/dh_t is complete
+            ops.gru_bwd(gH[t], GI[t], GH[t], Hprev[t], dGI[t], dGH[t], gH[t - 1] if t > 0 else None, accumulate=True)
+            if t > 0:
+                gH[t - 1].addmm_(dGH[t], Whh)
+                dz_carry = dGI[t] @ Wih_z
+        # ---- (3) weight gradients: batched GEMMs over all B*T rows ----------------------------------------------------
+        dGI2, dGH2, dLG2 = dGI.view(T * B, -1), dGH.view(T * B, -1), dLG.view(T * B, -1)
+        _acc_mm(gru.weight_ih, dGI2, X.view(T * B, -1))
+        _acc(gru.bias_ih, dGI2.sum(0))
+        _acc_mm(gru.weight_hh, dGH2, Hprev.view(T * B, -1))
+        _acc(gru.bias_hh, dGH2.sum(0))
+        _acc_mm(lin2.weight, dLG2, Y1)
+        _acc(lin2.bias, dLG2.sum(0))
+        dA1_all, dln = ops.ln_silu_bwd(dLG2 @ W2, A1, ln1.weight, ln1.bias, ln1.eps, want_dln=True)
+        xhat = F.layer_norm(A1, (A1.shape[-1],), None, None, ln1.eps)
+        _acc(ln1.weight, (dln * xhat).sum(0))
+        _acc(ln1.bias, dln.sum(0))
+        _acc_mm(lin1.weight, dA1_all, X1.view(T * B, -1))
+        _acc(lin1.bias, dA1_all.sum(0))
+        dfeat = (dA1_all @ lin1.weight[:, :n_feat]).view(T, B, n_feat).transpose(0, 1).reshape(B * T, n_feat)
+    feats.backward(dfeat)    # encoder convs
+    return loss.detach()

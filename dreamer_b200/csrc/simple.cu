@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
 // Backward of the straight-through sample z = onehot + p - stopgrad(p), p = 0.99 softmax(l) + 0.01 / 32
 // (DynamicsPredictors.py:33-39, VariationalAutoEncoder.py:88-98):  dl = 0.99 * s * (g - sum_j s_j g_j), s = softmax(l), g = dz.
 // Same tiling as the forward: a warp owns 32 rows, coalesced float4 tile loads, one row per lane.
+// Optional addends (the sequential BPTT step fuses its two accumulations): g = dz + dz2, dl += dl_add.
 __global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dz,
+                                                                const float* __restrict__ dz2, const float* __restrict__ dl_add,
                                                                 float* __restrict__ dlogits, int64_t n_rows) {
   __shared__ float tiles[8][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -146,7 +148,13 @@ __global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __r
       for (int k = 0; k < 8; ++k) {
         const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nr) x = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * 32 + c));
+        if (r < nr) {
+          x = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * 32 + c));
+          if (pass && dz2) {
+            const float4 y = __ldg(reinterpret_cast<const float4*>(dz2 + (row0 + r) * 32 + c));
+            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+          }
+        }
         t[r][c] = x.x; t[r][c + 1] = x.y; t[r][c + 2] = x.z; t[r][c + 3] = x.w;
       }
       __syncwarp();
@@ -170,9 +178,105 @@ __global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __r
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int r = 4 * k + (lane >> 3), c = (lane & 7) * 4;
-      if (r < nr) *reinterpret_cast<float4*>(dlogits + (row0 + r) * 32 + c) = make_float4(t[r][c], t[r][c + 1], t[r][c + 2], t[r][c + 3]);
+      if (r < nr) {
+        float4 o = make_float4(t[r][c], t[r][c + 1], t[r][c + 2], t[r][c + 3]);
+        if (dl_add) {
+          const float4 y = __ldg(reinterpret_cast<const float4*>(dl_add + (row0 + r) * 32 + c));
+          o.x += y.x; o.y += y.y; o.z += y.z; o.w += y.w;
+        }
+        *reinterpret_cast<float4*>(dlogits + (row0 + r) * 32 + c) = o;
+      }
     }
     __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of y = SiLU(LayerNorm(a) * gamma + beta) for rows of n <= 1024 features (one warp per row; statistics are
+// recomputed from the pre-activation a, two-pass like torch):  dln = dy * silu'(ln);  dxh = dln * gamma;
+//   da = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)).   dln (optional) feeds the batched dgamma / dbeta sums.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ da, float* __restrict__ dln_out, int64_t rows, int n, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_n = 1.0f / (float)n;
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    const float* ar = a + row * n;
+    const float* dr = dy + row * n;
+    float x[32], d[32];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = lane + 32 * j;
+      x[j] = c < n ? __ldg(ar + c) : 0.f;
+      s += x[j];
+    }
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = lane + 32 * j;
+      const float t = c < n ? x[j] - mean : 0.f;
+      q = fmaf(t, t, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = lane + 32 * j;
+      float dxh = 0.f, xh = 0.f;
+      if (c < n) {
+        xh = (x[j] - mean) * rstd;
+        const float g = __ldg(gamma + c);
+        const float ln = fmaf(xh, g, __ldg(beta + c));
+        const float sg = 1.0f / (1.0f + expf(-ln));
+        const float dl = __ldg(dr + c) * (sg * (1.0f + ln * (1.0f - sg)));   // silu'(x) = sig (1 + x (1 - sig))
+        if (dln_out) dln_out[row * n + c] = dl;
+        dxh = dl * g;
+      }
+      x[j] = xh; d[j] = dxh;
+      s1 += dxh;
+      s2 = fmaf(dxh, xh, s2);
+    }
+    const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n) da[row * n + c] = rstd * (d[j] - m1 - x[j] * m2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of one nn.GRUCell step (SequenceModel.py:13,19-24; gates [r; u; n], n = tanh(gi_n + r * gh_n), h' = (1 - u) n + u h)
+// from the forward pre-activations gi = x W_ih^T + b_ih and gh = h W_hh^T + b_hh:
+//   dgi = [dr_pre, du_pre, dn_pre],  dgh = [dr_pre, du_pre, dn_pre * r],  dh_prev (+)= dh * u      (elementwise part only;
+//   the caller adds dgh W_hh to dh_prev and takes dx = dgi W_ih).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gru_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ gi,
+                                                      const float* __restrict__ gh, const float* __restrict__ h_prev,
+                                                      float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev,
+                                                      int accumulate, int64_t rows, int D) {
+  const int64_t total = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / D;
+    const int k = (int)(i - b * D);
+    const int64_t g0 = b * 3 * D + k;
+    const float ghn = gh[g0 + 2 * D];
+    const float r = 1.0f / (1.0f + expf(-(gi[g0] + gh[g0])));
+    const float u = 1.0f / (1.0f + expf(-(gi[g0 + D] + gh[g0 + D])));
+    const float n = tanhf(gi[g0 + 2 * D] + r * ghn);
+    const float hp = h_prev ? h_prev[i] : 0.f;
+    const float g = dh[i];
+    const float dn_pre = g * (1.0f - u) * (1.0f - n * n);
+    const float du_pre = g * (hp - n) * u * (1.0f - u);
+    const float dr_pre = dn_pre * ghn * r * (1.0f - r);
+    dgi[g0] = dr_pre; dgi[g0 + D] = du_pre; dgi[g0 + 2 * D] = dn_pre;
+    dgh[g0] = dr_pre; dgh[g0 + D] = du_pre; dgh[g0 + 2 * D] = dn_pre * r;
+    if (dh_prev) dh_prev[i] = (accumulate ? dh_prev[i] : 0.f) + g * u;
   }
 }
 
@@ -406,14 +510,40 @@ extern "C" int drm_categorical32_st(const float* logits, const uint8_t* idx, flo
   return DRM_OK;
 }
 
-extern "C" int drm_categorical32_bwd(const float* logits, const float* dz, float* dlogits, int64_t n_rows, void* stream) {
+extern "C" int drm_categorical32_bwd(const float* logits, const float* dz, const float* dz2, const float* dl_add, float* dlogits,
+                                     int64_t n_rows, void* stream) {
   if (int rc = check_arch()) return rc;
   DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_categorical32_bwd: n_rows < 0");
   if (n_rows == 0) return DRM_OK;
   DRM_REQUIRE(logits && dz && dlogits, DRM_ERR_ARG, "drm_categorical32_bwd: NULL pointer");
-  DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)dlogits % 16 == 0), DRM_ERR_ALIGN,
-              "drm_categorical32_bwd: 16-byte alignment required");
-  categorical32_bwd_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dlogits, n_rows);
+  DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)dlogits % 16 == 0) &&
+                  (!dz2 || (uintptr_t)dz2 % 16 == 0) && (!dl_add || (uintptr_t)dl_add % 16 == 0),
+              DRM_ERR_ALIGN, "drm_categorical32_bwd: 16-byte alignment required");
+  categorical32_bwd_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dz2, dl_add, dlogits, n_rows);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const float* beta, float* da, float* dln,
+                               int64_t rows, int32_t n, float eps, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 0 && n >= 1 && n <= 1024, DRM_ERR_SHAPE, "drm_ln_silu_bwd: n must be in [1, 1024]");
+  if (rows == 0) return DRM_OK;
+  DRM_REQUIRE(dy && a && gamma && beta && da, DRM_ERR_ARG, "drm_ln_silu_bwd: NULL pointer");
+  ln_silu_bwd_kernel<<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
+                           float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 0 && D >= 1, DRM_ERR_SHAPE, "drm_gru_bwd: bad shape");
+  if (rows == 0) return DRM_OK;
+  DRM_REQUIRE(dh && gi && gh && dgi && dgh, DRM_ERR_ARG, "drm_gru_bwd: NULL pointer");
+  const int64_t total = rows * D;
+  const int64_t want = (total + 255) / 256;
+  gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -1,9 +1,10 @@
 """WorldModel (WorldModel.py) and Agent (Agent.py) mirrors: same constructors, attributes and methods.
 
 Forward quantities (states, logits, log-likelihoods, returns, losses) come from the sm_100a kernels.
-Gradients for the two optimiser steps come from ``_tail_*`` below: a device-side torch graph over the
-same parameter containers, teacher-forced on the indices the kernels sampled.  That tail is interim
-(BPTT kernels).  Clipping, AdamW, the target-critic EMA and gradient zeroing run as the fused
+The world model's gradient comes from bptt.world_model_backward: a hand-scheduled back-propagation through time on the
+trajectory the scan kernels produced (batched non-recurrent graph, 7 launches per time step for the recurrence, batched
+weight-gradient GEMMs).  ``_tail_world_model`` below -- a torch autograd graph over the Python scan, teacher-forced on the
+sampled classes -- is the reference implementation of that gradient (``grad_mode = "autograd"``) and the Agent's tail.  Clipping, AdamW, the target-critic EMA and gradient zeroing run as the fused
 flat-bucket kernels of optim.FlatAdamW (section 8f rank 2).
 """
 from __future__ import annotations
@@ -15,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import bptt
 from . import dist as D
 from . import ops
 from .graphs import StepGraph
@@ -134,9 +136,14 @@ class WorldModel(nn.Module):
     def _backward_and_step(self, total, parts, action_sequences, reward_sequences, continue_sequences):
         T = self.horizon
         self.optimiser.zero_grad()
-        tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
-                                 self.last["scan"]["idx"], parts)
-        tail.backward()
+        if self.__dict__.get("grad_mode", "bptt") == "bptt" and self.latent_num_columns == 32:
+            # hand-scheduled BPTT on the scan's own trajectory: batched non-recurrent graph + 7 launches per time step (bptt.py)
+            tail = bptt.world_model_backward(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T],
+                                             continue_sequences[:, :T], self.last["scan"]["idx"], self.last["scan"]["hidden"], parts)
+        else:                # reference implementation of the gradient: autograd over the Python scan (~70 launches per time step)
+            tail = _tail_world_model(self, parts["obs_norm"], action_sequences[:, :T], reward_sequences[:, :T], continue_sequences[:, :T],
+                                     self.last["scan"]["idx"], parts)
+            tail.backward()
         if isinstance(self.optimiser, FlatAdamW):
             # gradients of the global loss = SUM over ranks of the per-rank tails: all-reduce of the flat 31 MB bucket the
             # gradients were accumulated into, then clip + AdamW + zeroing in three launches

@@ -61,8 +61,47 @@ class _StraightThrough(torch.autograd.Function):
         (lg,) = ctx.saved_tensors
         g = L.f32c(dz)
         out = torch.empty_like(lg)
-        L.check(L.load().drm_categorical32_bwd(L.ptr(lg), L.ptr(g), L.ptr(out), lg.numel() // 32, L.stream()), "categorical32_bwd")
+        L.check(L.load().drm_categorical32_bwd(L.ptr(lg), L.ptr(g), None, None, L.ptr(out), lg.numel() // 32, L.stream()), "categorical32_bwd")
         return out, None
+
+
+def categorical32_bwd(logits, dz, dz2=None, dl_add=None, out=None):
+    """dlogits = ST-backward(logits, dz [+ dz2]) [+ dl_add]; all (..., 32) fp32 contiguous (no copies are made)."""
+    n = logits.numel() // 32
+    if out is None:
+        out = torch.empty_like(logits)
+    for t in (logits, dz, dz2, dl_add, out):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == n * 32):
+            raise RuntimeError("dreamer_b200.categorical32_bwd: fp32 contiguous CUDA tensors of one shape are required")
+    L.check(L.load().drm_categorical32_bwd(L.ptr(logits), L.ptr(dz), L.ptr(dz2), L.ptr(dl_add), L.ptr(out), n, L.stream()), "categorical32_bwd")
+    return out
+
+
+def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, out=None):
+    """Backward of SiLU(LayerNorm(a) * gamma + beta): dy, a (..., n) -> da (..., n) [, dln]."""
+    n = a.shape[-1]
+    for t in (dy, a, gamma, beta):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError("dreamer_b200.ln_silu_bwd: fp32 contiguous CUDA tensors are required")
+    if dy.shape != a.shape or gamma.numel() != n or beta.numel() != n:
+        raise RuntimeError("dreamer_b200.ln_silu_bwd: shape mismatch")
+    da = torch.empty_like(a) if out is None else out
+    dln = torch.empty_like(a) if want_dln else None
+    L.check(L.load().drm_ln_silu_bwd(L.ptr(dy), L.ptr(a), L.ptr(gamma), L.ptr(beta), L.ptr(da), L.ptr(dln), a.numel() // n, n, eps, L.stream()),
+            "ln_silu_bwd")
+    return (da, dln) if want_dln else da
+
+
+def gru_bwd(dh, gi, gh, h_prev, dgi, dgh, dh_prev=None, accumulate: bool = False):
+    """Elementwise backward of one GRUCell step (drm_gru_bwd); writes dgi, dgh (rows, 3D) and dh_prev (=|+=) dh * u."""
+    rows, Dh = dh.shape
+    for t in (dh, gi, gh, h_prev, dgi, dgh, dh_prev):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError("dreamer_b200.gru_bwd: fp32 contiguous CUDA tensors are required")
+    if gi.shape != (rows, 3 * Dh) or gh.shape != gi.shape or dgi.shape != gi.shape or dgh.shape != gi.shape:
+        raise RuntimeError("dreamer_b200.gru_bwd: shape mismatch")
+    L.check(L.load().drm_gru_bwd(L.ptr(dh), L.ptr(gi), L.ptr(gh), L.ptr(h_prev), L.ptr(dgi), L.ptr(dgh), L.ptr(dh_prev),
+                                 1 if accumulate else 0, rows, Dh, L.stream()), "gru_bwd")
 
 
 def straight_through(logits: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

@@ -93,8 +93,23 @@ int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* i
 /* Teacher-forced forward (the class idx [n_rows] u8 is given, not drawn): z_st = (onehot(idx) + p) - p and/or  */
 /* probs p = 0.99 softmax + 0.01/32.  Used by the gradient tail, which replays the classes the scan sampled.    */
 int drm_categorical32_st(const float* logits, const uint8_t* idx, float* z_st, float* probs, int64_t n_rows, void* stream);
-/* Backward of the straight-through sample: dlogits = 0.99 * s * (dz - sum_j s_j dz_j), s = softmax(logits).    */
-int drm_categorical32_bwd(const float* logits, const float* dz, float* dlogits, int64_t n_rows, void* stream);
+/* Backward of the straight-through sample: dlogits = 0.99 * s * (g - sum_j s_j g_j) [+ dl_add], s = softmax(logits),         */
+/* g = dz [+ dz2]; the two optional addends let one BPTT step fuse its accumulations.  All [n_rows, 32] fp32.               */
+int drm_categorical32_bwd(const float* logits, const float* dz, const float* dz2, const float* dl_add, float* dlogits,
+                          int64_t n_rows, void* stream);
+
+/* ---- elementwise pieces of the hand-scheduled BPTT (the GEMMs between them are library GEMMs) ------- */
+/* Backward of y = SiLU(LayerNorm(a) * gamma + beta) (the Linear-LN-SiLU blocks of every MLP, e.g.                           */
+/* VariationalAutoEncoder.py:48-52): dy, a [rows, n] (n <= 1024) -> da [rows, n]; dln (optional) = dy * silu'(ln) for the     */
+/* batched dgamma = sum(dln * xhat), dbeta = sum(dln).  Statistics are recomputed from a (eps as in the forward, 1e-5).       */
+int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const float* beta, float* da, float* dln,
+                    int64_t rows, int32_t n, float eps, void* stream);
+/* Backward of one nn.GRUCell step (SequenceModel.py:13,19-24) from its pre-activations gi = x W_ih^T + b_ih,                */
+/* gh = h W_hh^T + b_hh [rows, 3D] (gate order r, u, n), h_prev [rows, D] (NULL = zeros) and dh [rows, D]:                    */
+/*   dgi = [dr, du, dn], dgh = [dr, du, dn * r] (pre-activation gradients), dh_prev (=, or += when accumulate) dh * u.        */
+/* The caller completes dh_prev += dgh W_hh and dx = dgi W_ih with library GEMMs.                                             */
+int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
+                float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
 /* KL balance terms of WorldModel.training_step  WorldModel.py:175-181:                         */
 /*   kl[g] = sum over the `rows_per_group` categorical rows of group g of KL(Cat(post)||Cat(prior)) */
 /* post/prior logits [n_groups * rows_per_group, 32] fp32 -> kl [n_groups] fp32.                 */

@@ -1,0 +1,99 @@
+"""Hand-scheduled BPTT (dreamer_b200/bptt.py and its elementwise kernels) against torch autograd."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dreamer_b200 import synthetic as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_ln_silu_bwd_matches_autograd():
+    from dreamer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for rows, n in ((1, 7), (16, 200), (77, 256), (5, 1024)):
+        a = (torch.randn(rows, n, device=DEV, generator=g) * 2 + 0.3).requires_grad_(True)
+        gamma = (torch.randn(n, device=DEV, generator=g) * 0.5 + 1).requires_grad_(True)
+        beta = (torch.randn(n, device=DEV, generator=g) * 0.2).requires_grad_(True)
+        dy = torch.randn(rows, n, device=DEV, generator=g)
+        y = F.silu(F.layer_norm(a, (n,), gamma, beta, 1e-5))
+        y.backward(dy)
+        da, dln = ops.ln_silu_bwd(dy, a.detach(), gamma.detach(), beta.detach(), 1e-5, want_dln=True)
+        assert torch.allclose(da, a.grad, rtol=2e-4, atol=2e-5), (rows, n)
+        xhat = F.layer_norm(a.detach(), (n,), None, None, 1e-5)
+        assert torch.allclose((dln * xhat).sum(0), gamma.grad, rtol=2e-4, atol=2e-4)
+        assert torch.allclose(dln.sum(0), beta.grad, rtol=2e-4, atol=2e-4)
+
+
+def test_gru_bwd_matches_autograd_grucell():
+    from dreamer_b200 import ops
+    torch.manual_seed(1)
+    B, Din, D = 9, 21, 40
+    cell = torch.nn.GRUCell(Din, D, device=DEV)
+    x = torch.randn(B, Din, device=DEV, requires_grad=True)
+    h = torch.randn(B, D, device=DEV, requires_grad=True)
+    dh = torch.randn(B, D, device=DEV)
+    cell(x, h).backward(dh)
+    with torch.no_grad():
+        gi = torch.addmm(cell.bias_ih, x, cell.weight_ih.t())
+        gh = torch.addmm(cell.bias_hh, h, cell.weight_hh.t())
+        dgi, dgh = torch.empty_like(gi), torch.empty_like(gh)
+        dhp = torch.full_like(h, 0.5)
+        ops.gru_bwd(dh, gi, gh, h.detach(), dgi, dgh, dhp, accumulate=True)
+        dhp.addmm_(dgh, cell.weight_hh)
+        assert torch.allclose(dhp - 0.5, h.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(dgi @ cell.weight_ih, x.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(dgi.t() @ x, cell.weight_ih.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(dgh.t() @ h, cell.weight_hh.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(dgi.sum(0), cell.bias_ih.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(dgh.sum(0), cell.bias_hh.grad, rtol=1e-4, atol=1e-5)
+
+
+def _grads(wm):
+    return {k: p.grad.detach().clone() for k, p in wm.named_parameters()}
+
+
+@pytest.mark.parametrize("B,T", [(3, 6), (5, 9)])
+def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
+    """Same loss, same teacher-forced classes: the hand-scheduled BPTT and the autograd tail must give the same parameter
+    gradients when both walk the SAME hidden-state trajectory (the tail's own fp32 one), for every one of the 7.8 M-layout
+    parameter tensors; on the scan kernels' bf16-GEMM trajectory the gradients stay close."""
+    from dreamer_b200 import bptt, learners
+    cfg = W.small_config(batch_size=B, sequence_length=T, horizon=T)
+    wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=11), DEV)
+    obs, act, rew, cont, u = (x.to(DEV) for x in W.sequence_inputs(cfg, B, T, seed=12))
+    total, parts = wm.loss_forward(obs, act, rew, cont, u)
+    idx, hidden_k = wm.last["scan"]["idx"], wm.last["scan"]["hidden"]
+    # reference gradient: autograd over the Python scan
+    wm.optimiser.zero_grad()
+    tail = learners._tail_world_model(wm, parts["obs_norm"], act, rew, cont, idx, parts)
+    tail.backward()
+    g_ref = _grads(wm)
+    # the tail's own fp32 trajectory (recomputed here without autograd)
+    with torch.no_grad():
+        R, C, Dh = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
+        feats = wm.encoder.feature_extractor(parts["obs_norm"].reshape(B * T, 3, 64, 64)).flatten(1).view(B, T, -1)
+        h, z, hs = torch.zeros(B, Dh, device=DEV), torch.zeros(B, R * C, device=DEV), []
+        for t in range(T):
+            a = act[:, t - 1] if t > 0 else torch.zeros(B, wm.action_dims, device=DEV)
+            h = wm.sequence_model.GRU(torch.cat([z, a], -1), h)
+            z = F.one_hot(idx[:, t].long(), C).float().reshape(B, R * C)
+            hs.append(h)
+        hidden_fp32 = torch.stack(hs, 1)
+    assert torch.allclose(hidden_fp32, hidden_k, atol=3e-2, rtol=3e-2)          # the scan kernels' h_t line up with the tail's
+    wm.optimiser.zero_grad()
+    val = bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_fp32, parts)
+    g_new = _grads(wm)
+    assert torch.allclose(val, tail.detach(), rtol=1e-4, atol=1e-4)
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max()) + 1e-8
+        err = float((g_ref[k] - g_new[k]).abs().max()) / scale
+        assert err < 2e-3, (k, err, scale)
+    # on the kernels' trajectory: same gradient up to the bf16 state rounding
+    wm.optimiser.zero_grad()
+    bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_k, parts)
+    g_k = _grads(wm)
+    num = sum(float(((g_ref[k] - g_k[k]) ** 2).sum()) for k in g_ref)
+    den = sum(float((g_ref[k] ** 2).sum()) for k in g_ref)
+    assert (num / den) ** 0.5 < 5e-2
