@@ -36,12 +36,20 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
     p.grad.addmm_(a_t.t(), b)
 
 
-def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
+def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
     """Accumulate d(loss)/d(parameters) of WorldModel.training_step into ``.grad``; returns the (detached) loss value of the
     batched fp32 re-evaluation.
 
     obs (B,T,3,H,W) normalised, act (B,T,A), rew / cont (B,T,1), idx (B,T,R) classes the scan sampled, hidden (B,T,D) its h_t.
-    `parts` as in learners._tail_world_model (globally reduced denominators for data-parallel shares)."""
+    `parts` as in learners._tail_world_model (globally reduced denominators for data-parallel shares).
+    `marks` (a list) receives (name, cuda event) pairs at the phase boundaries (profiles/wm_step_time.py)."""
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
     B, T = obs.shape[:2]
     R, C, Dh = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
     if C != 32:
@@ -52,6 +60,7 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
     lin1, ln1, _, lin2 = wm.encoder.latent_mapper
     n_feat = lin1.weight.shape[1] - Dh
 
+    mark("start")
     # ---- (1a) teacher-forced trajectory and the recurrent pre-activations, batched (no autograd) ----------------------------
     with torch.no_grad():
         Hk = hidden.detach().to(torch.float32)
@@ -72,6 +81,7 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
         Y1 = F.silu(F.layer_norm(A1, (A1.shape[-1],), ln1.weight, ln1.bias, ln1.eps))
         LG = torch.addmm(lin2.bias, Y1, lin2.weight.t()).view(T, B, Z)          # posterior logits, time-major
 
+    mark("recurrent pre-activations + posterior MLP forward (batched)")
     # ---- (1b) everything that reads (h_t, z_t) at one step: batched autograd on leaves --------------------------------------
     Hl = Hk.clone().requires_grad_(True)                                        # (B,T,D)
     Zl = z_oh.clone().requires_grad_(True)                                      # (B,T,Z)
@@ -111,8 +121,10 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
         live = (kl_mean > 1.0).to(loss_pred.dtype)
         const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
         loss = wm.beta_pred * loss_pred + live * (wm.beta_dyn * (dyn_sum / n_el) + wm.beta_rep * (rep_sum / n_el)) + const
+    mark("batched heads / decoder forward")
     loss.backward()          # parameter gradients of prior / decoder / heads; d/dh, d/dz, d/dlogits at every step
 
+    mark("batched heads / decoder backward")
     with torch.no_grad():
         gH = Hl.grad.transpose(0, 1).contiguous()                               # (T,B,D)  accumulates the total d/dh_t
         gZ = Zl.grad.transpose(0, 1).contiguous()                               # (T,B,Z)  direct d/dz_t (decoder, reward, continue)
@@ -135,6 +147,7 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
             if t > 0:
                 gH[t - 1].addmm_(dGH[t], Whh)
                 dz_carry = dGI[t] @ Wih_z
+        mark("recurrence backward (T steps)")
         # ---- (3) weight gradients: batched GEMMs over all B*T rows ----------------------------------------------------
         dGI2, dGH2, dLG2 = dGI.view(T * B, -1), dGH.view(T * B, -1), dLG.view(T * B, -1)
         _acc_mm(gru.weight_ih, dGI2, X.view(T * B, -1))
@@ -150,5 +163,7 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None):
         _acc_mm(lin1.weight, dA1_all, X1.view(T * B, -1))
         _acc(lin1.bias, dA1_all.sum(0))
         dfeat = (dA1_all @ lin1.weight[:, :n_feat]).view(T, B, n_feat).transpose(0, 1).reshape(B * T, n_feat)
+    mark("batched weight-gradient GEMMs")
     feats.backward(dfeat)    # encoder convs
+    mark("encoder conv backward")
     return loss.detach()

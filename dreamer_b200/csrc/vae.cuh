@@ -87,6 +87,86 @@ __global__ void patch_gather_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
   }
 }
 
+// Last decoder layer (ConvTranspose2d k4 s2 p1 to <= 3 image channels + tanh, VariationalAutoEncoder.py:134-137) WITHOUT the
+// patch matrix: with 3 output channels the GEMM formulation is all overhead (K = 4 taps x cp, N = 3: 32 768 tiles of 128 rows at
+// config 3, 1 GB of patches written and read back).  One thread per INPUT pixel produces the 2 x 2 output pixels it is the
+// centre of (sub-pixel phases py, px): 16 (neighbour, phase) pairs x cp channels x co FMAs from the 3 x 3 neighbourhood, read
+// as 16-byte NHWC vectors through L1; weights (the packed bf16 phase matrices of the GEMM path, so both paths round alike) sit
+// in shared memory as one float4 per (phase, tap, channel) and are read as warp-wide broadcasts.
+//   in  NHWC bf16 [nf, Hin, Win, cp];  Wp bf16 [(phase * co_pad + co)][tap * cp + c] (row pitch ldw);  out fp32 NCHW.
+template <int CP>
+__global__ void __launch_bounds__(256) convt_last_direct_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ Wp,
+                                                                const float* __restrict__ bias, float* __restrict__ out, long npix,
+                                                                int Hin, int Win, int co_pad, int co_n, int ldw) {
+  __shared__ float4 w_s[16 * CP];
+  for (int i = threadIdx.x; i < 16 * CP; i += blockDim.x) {
+    const int ph = i / (4 * CP), r = i - ph * 4 * CP;           // r = tap * CP + c
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < co_n && co < 3; ++co) w[co] = __bfloat162float(Wp[(long)(ph * co_pad + co) * ldw + r]);
+    w_s[i] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const float b0 = co_n > 0 ? bias[0] : 0.f, b1 = co_n > 1 ? bias[1] : 0.f, b2 = co_n > 2 ? bias[2] : 0.f;   // co_n <= 3 image channels
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(pix % Win);
+    const int i = (int)((pix / Win) % Hin);
+    const long f = pix / ((long)Win * Hin);
+    float acc[4][3];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) { acc[ph][0] = b0; acc[ph][1] = b1; acc[ph][2] = b2; }
+#pragma unroll
+    for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll
+      for (int dxi = 0; dxi < 3; ++dxi) {
+        const int dy = dyi - 1, dx = dxi - 1;
+        const int iy = i + dy, ix = j + dx;
+        const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+        const uint4* src = reinterpret_cast<const uint4*>(in + ((f * Hin + iy) * Win + ix) * CP);
+#pragma unroll
+        for (int c8 = 0; c8 < CP / 8; ++c8) {
+          uint4 raw = make_uint4(0, 0, 0, 0);
+          if (ok) raw = __ldg(src + c8);
+          float xv[8];
+          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { xv[2 * e] = __uint_as_float(rw[e] << 16); xv[2 * e + 1] = __uint_as_float(rw[e] & 0xFFFF0000u); }
+          // phases this neighbour feeds: dy = 0 -> tap ty = 0 of both py; dy = -1 -> py = 0, ty = 1; dy = +1 -> py = 1, ty = 1
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            if (!(dy == 0 || (dy == -1 && py == 0) || (dy == 1 && py == 1))) continue;
+            const int ty = dy == 0 ? 0 : 1;
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+              if (!(dx == 0 || (dx == -1 && px == 0) || (dx == 1 && px == 1))) continue;
+              const int tx = dx == 0 ? 0 : 1;
+              const int ph = py * 2 + px;
+              const float4* wp = w_s + (ph * 4 + ty * 2 + tx) * CP + c8 * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 w = wp[e];
+                acc[ph][0] = fmaf(xv[e], w.x, acc[ph][0]);
+                acc[ph][1] = fmaf(xv[e], w.y, acc[ph][1]);
+                acc[ph][2] = fmaf(xv[e], w.z, acc[ph][2]);
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int co = 0; co < co_n; ++co) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        float* o = out + ((f * co_n + co) * Ho + 2 * i + py) * Wo + 2 * j;
+        float v0 = acc[py * 2][0], v1 = acc[py * 2 + 1][0];
+        if (co == 1) { v0 = acc[py * 2][1]; v1 = acc[py * 2 + 1][1]; }
+        if (co == 2) { v0 = acc[py * 2][2]; v1 = acc[py * 2 + 1][2]; }
+        *reinterpret_cast<float2*>(o) = make_float2(tanhf_(v0), tanhf_(v1));
+      }
+    }
+  }
+}
+
 // act[b, t, :] -> the action columns of slab t + 1
 __global__ void pack_actions_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int col0, const float* __restrict__ act, int B, int T, int A) {
   const long total = (long)B * T * A;
@@ -344,7 +424,11 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
   o->rows = (T + 1) * B;
   o->rows_p = round_up(o->rows, BM) + BM;
   const int NF = T * B;
-  o->FC = NF < 128 ? NF : 128;
+  {
+    const char* e = getenv("DRM_FC");
+    const int fc = e ? atoi(e) : 128;
+    o->FC = NF < fc ? NF : fc;
+  }
   const int H = v->d.H, W = v->d.W;
   long pe = 0, ae = 0;
   {
@@ -447,6 +531,15 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
       tp.t[ph].n = 4;
       for (int ty = 0; ty < 2; ++ty)
         for (int tx = 0; tx < 2; ++tx) { tp.t[ph].dy[ty * 2 + tx] = ct_d(ph >> 1, ty); tp.t[ph].dx[ty * 2 + tx] = ct_d(ph & 1, tx); }
+    }
+    if (j == 3 && (v->dbn[3] == 32 || v->dbn[3] == 16 || v->dbn[3] == 8 || v->dbn[3] == 64) && !getenv("DRM_NO_DIRECT_CONVT")) {
+      // image layer: direct kernel, no patch matrix (see convt_last_direct_kernel)
+      const int grid = grid_for(rows);
+#define DRM_CT_LAST(CPV) convt_last_direct_kernel<CPV><<<grid, 256, 0, st>>>(src, v->Wdc[3], v->bdc[3], mu_out, rows, hs, ws, v->dbn[4], 3, v->DK[3])
+      if (v->dbn[3] == 64) DRM_CT_LAST(64); else if (v->dbn[3] == 32) DRM_CT_LAST(32); else if (v->dbn[3] == 16) DRM_CT_LAST(16); else DRM_CT_LAST(8);
+#undef DRM_CT_LAST
+      DRM_LAUNCH_CHECK();
+      break;
     }
     patch_gather_kernel<<<dim3(grid_for(rows * 4 * (v->dbn[j] / 8)), 4), 256, 0, st>>>(src, o->patch, rows, hs, ws, v->dbn[j], hs, ws, 1, tp, rows, v->DK[j]);
     DRM_LAUNCH_CHECK();

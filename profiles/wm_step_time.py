@@ -28,3 +28,23 @@ for mode in ("autograd", "bptt"):
     g = t(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu))
     print(f"{mode:9s} eager {e:7.2f} ms   graph {g:7.2f} ms   ({1e3/g:.1f} steps/s)")
     del wm
+
+# phase times of the BPTT gradient (eager, device time between phase marks)
+from dreamer_b200 import bptt
+wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=0), dev)
+for _ in range(3):
+    wm.training_step(obs, act, rew, cont, uniforms=uu)
+a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a0.record()
+total, parts = wm.loss_forward(obs, act, rew, cont, uu)
+a1.record()
+marks = []
+wm.optimiser.zero_grad()
+bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, wm.last["scan"]["idx"], wm.last["scan"]["hidden"], parts, marks=marks)
+b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+b0.record(); wm.optimiser.step(); b1.record()
+torch.cuda.synchronize()
+print(f"  {a0.elapsed_time(a1):7.2f} ms  loss forward (scan + heads kernels)")
+for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+    print(f"  {e0.elapsed_time(e1):7.2f} ms  {n1}")
+print(f"  {b0.elapsed_time(b1):7.2f} ms  clip + AdamW (fused)")
