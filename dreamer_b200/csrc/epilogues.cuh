@@ -83,6 +83,13 @@ struct EpiPlain {
   }
 };
 
+// EpiPlain for narrow outputs (bn <= 64: the conv layers with <= 64 output channels).  Those GEMMs are thousands of tiles with
+// 1 .. 8 k-blocks each, so a tile's life is mostly fixed cost (barrier init, TMEM allocation, pipeline fill, epilogue); with a
+// third of the shared memory and a quarter of the TMEM columns two CTAs share an SM and hide each other's fixed cost.
+struct EpiPlainS : EpiPlain {
+  static constexpr int B_ROWS_MAX = 64, STAGES = 3, TMEM_COLS = 64, MIN_CTAS = 2;
+};
+
 // ------------------------------------------------------------------------------------------
 // Linear + LayerNorm(eps) + SiLU -> bf16 (the hidden layers of every MLP head:
 // DynamicsPredictors.py:15-23, 52-60, 85-93; Agent.py:178-185, 219-227;
