@@ -37,6 +37,12 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
 
 
 def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
+    # the batched conv graph has fixed shapes: let cuDNN pick its fastest (TF32 tensor-core) algorithms during the eager warm-up
+    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True):
+        return _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts, marks)
+
+
+def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
     """Accumulate d(loss)/d(parameters) of WorldModel.training_step into ``.grad``; returns the (detached) loss value of the
     batched fp32 re-evaluation.
 
@@ -74,7 +80,10 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks
         GI = torch.addmm(gru.bias_ih, X.view(T * B, -1), gru.weight_ih.t()).view(T, B, 3 * Dh)
         GH = torch.addmm(gru.bias_hh, Hprev.view(T * B, -1), gru.weight_hh.t()).view(T, B, 3 * Dh)
     # encoder convs: the one autograd graph that is closed later with d(loss)/d(features)
-    feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:])).flatten(1)          # (B*T, n_feat)
+    conv_dtype = wm.__dict__.get("conv_grad_dtype", torch.bfloat16)     # the reference trains these convs under fp16 autocast
+    with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
+        feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:]).contiguous(memory_format=torch.channels_last))
+    feats = feats.float().flatten(1)                                                               # (B*T, n_feat)
     with torch.no_grad():
         X1 = torch.cat([feats.detach().view(B, T, n_feat).transpose(0, 1), H_tm], -1).contiguous()   # (T,B,n_feat+D)
         A1 = torch.addmm(lin1.bias, X1.view(T * B, -1), lin1.weight.t())
@@ -89,7 +98,9 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks
     prior = wm.dynamics_predictor.logit_net(Hl).view(B, T, R, C)
     hz = torch.cat([Hl, Zl], -1)
     x = wm.decoder.upscaler(hz.reshape(B * T, -1)).view(B * T, wm.decoder.num_filters_start, wm.decoder.start_height, wm.decoder.start_width)
-    dec = wm.decoder.image_builder(x).view(obs.shape)
+    with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
+        dec = wm.decoder.image_builder(x.contiguous(memory_format=torch.channels_last))
+    dec = dec.float().view(obs.shape)
     rl = wm.reward_predictor.logit_net(hz[:, 1:])
     cl = wm.continue_predictor.logit_generator(hz[:, 1:])
     mask = cont[:, :T - 1]

@@ -62,6 +62,7 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
     from dreamer_b200 import bptt, learners
     cfg = W.small_config(batch_size=B, sequence_length=T, horizon=T)
     wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=11), DEV)
+    wm.conv_grad_dtype = torch.float32          # exact comparison first; the default bf16 conv graph is checked at the end
     obs, act, rew, cont, u = (x.to(DEV) for x in W.sequence_inputs(cfg, B, T, seed=12))
     total, parts = wm.loss_forward(obs, act, rew, cont, u)
     idx, hidden_k = wm.last["scan"]["idx"], wm.last["scan"]["hidden"]
@@ -97,3 +98,10 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
     num = sum(float(((g_ref[k] - g_k[k]) ** 2).sum()) for k in g_ref)
     den = sum(float((g_ref[k] ** 2).sum()) for k in g_ref)
     assert (num / den) ** 0.5 < 5e-2
+    # default: the batched encoder / decoder conv graphs under bf16 autocast (the reference runs them under fp16 autocast)
+    wm.conv_grad_dtype = torch.bfloat16
+    wm.optimiser.zero_grad()
+    bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_fp32, parts)
+    g_b = _grads(wm)
+    num = sum(float(((g_ref[k] - g_b[k]) ** 2).sum()) for k in g_ref)
+    assert (num / den) ** 0.5 < 3e-2
