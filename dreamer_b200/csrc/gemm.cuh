@@ -35,6 +35,7 @@ struct GemmCommon {
   int ka1, nka1;     //   consumed sequentially from 0
   int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
   int y_slot[8];
+  int a_bytes;             // bytes one A k-block load delivers: 0 = the full 128-row tile; SMALL_A_ROWS * 128 when tmA has a short box
   unsigned long long* cta_times;  // debug: per-CTA {entry, wait over, exit, smid} records, or NULL
   unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL
   // One-hot A operand: when zi != NULL the first n_zblocks A k-blocks (2 latent rows of 32 classes each) are NOT loaded by
@@ -148,6 +149,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
       probe(g, 1);
       cta_probe(g.cta_times, 1);
       const uint32_t tx_b = (uint32_t)g.bn * BK * 2;
+      const uint32_t tx_a = g.a_bytes ? (uint32_t)g.a_bytes : (uint32_t)A_STAGE_BYTES;
       const int nz = g.zi ? g.n_zblocks : 0;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
@@ -156,7 +158,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
         const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
-        mbar_expect_tx(&full[s], kb < nz ? tx_b : tx_b + A_STAGE_BYTES);
+        mbar_expect_tx(&full[s], kb < nz ? tx_b : tx_b + tx_a);
         if (kb >= nz) tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);   // one-hot k-blocks: A is built in place by the expander
         if constexpr (CM == 1) {
           tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);

@@ -74,6 +74,7 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int small_a;     // 1: stages with <= 32 rows load 32-row A boxes (default 1)
   int lanes;       // rollouts: 0 / 1 one lane (default), 2 two half-batches on two internal streams
   int chain;       // 1: small grids run each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel (default 1)
   int gru_u;       // 0: automatic GRU tile width, else 32 / 64
@@ -85,6 +86,7 @@ static Options& opts() {
     x.multicast = getenv("DRM_MULTICAST") != nullptr;
     x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
     x.chain = getenv("DRM_CHAIN") != nullptr;
+    x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
     x.gru_u = e ? atoi(e) : 0;
@@ -179,6 +181,8 @@ struct drm_rssm {
   unsigned have;   // which weight groups have been packed (HAVE_* | 1 << HS_*)
 };
 
+constexpr int SMALL_A_ROWS = 32;   // box rows of the short A tensor maps (see small_a)
+
 struct drm_rollout {
   drm_rssm* m;
   int B, H, Mp;
@@ -186,6 +190,7 @@ struct drm_rollout {
   uint8_t* Zi[2];              // sampled latent indices [Mp, R] next to S[i] (one-hot expander input)
   __nv_bfloat16 *Y1, *Y2;
   CUtensorMap tmS[2], tmY1, tmY2;
+  CUtensorMap tmS_s[2], tmY1_s, tmY2_s;           // short-box twins (SMALL_A_ROWS rows)
   cudaStream_t lane_st[2] = {nullptr, nullptr};   // two-lane rollouts (created on first use)
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
@@ -441,6 +446,9 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
   for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM));
   TRY(make_tmap_bf16_2d(&r->tmY1, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
   TRY(make_tmap_bf16_2d(&r->tmY2, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
+  for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS_s[i], r->S[i], r->Mp, m->KS, m->KS, SMALL_A_ROWS));
+  TRY(make_tmap_bf16_2d(&r->tmY1_s, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS));
+  TRY(make_tmap_bf16_2d(&r->tmY2_s, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rollout_destroy(r);
@@ -481,9 +489,19 @@ struct WsView {
   int slot_rows;            // rows per Y slot
   int row0;                 // first row of this view inside S and inside every Y slot
   uint8_t* Zi;              // sampled indices [rows, R] parallel to S (NULL: none)
+  const CUtensorMap *tmS_s, *tmY1_s, *tmY2_s;   // the same buffers with a SMALL_A_ROWS-row box (NULL: none)
 };
 static WsView view_of(drm_rollout* r, int sb) {
-  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0, r->Zi[sb]};
+  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0, r->Zi[sb], &r->tmS_s[sb], &r->tmY1_s, &r->tmY2_s};
+}
+// Few rows (one acting environment, a 16-sequence scan step): load only SMALL_A_ROWS rows of every A k-block.  The MMA still
+// reads a 128-row tile; rows beyond the box hold stale shared memory, give garbage accumulator rows, and every epilogue writes
+// only rows < M.  Cuts the A bytes per k-block from 16 KB to 4 KB on stages that are bound by shared-memory ingress.
+static void small_a(GemmCommon& g, const CUtensorMap* small) {
+  if (small && g.M <= SMALL_A_ROWS && !g.zi && opts().small_a) {
+    g.tmA = *small;
+    g.a_bytes = SMALL_A_ROWS * BK * 2;
+  }
 }
 // Enable the one-hot expander for the view's z k-blocks (only valid when those rows' latents were written by EpiCat).
 static void use_z_indices(drm_rssm* m, GemmCommon& g, const WsView& v) {
@@ -509,6 +527,7 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
   if (z_idx && !mc) use_z_indices(m, g, src);
+  if (!mc) small_a(g, src.tmS_s);
   const dim3 grid(mc ? round_up(mt, 2) : mt, m->gru_tiles2[v]);
   __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
@@ -601,6 +620,7 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
   }
   {
     GemmCommon g = common(*v.tmS, m->tmWp1, M, m->bnp1);
+    small_a(g, v.tmS_s);
     g.a_row0 = v.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
@@ -609,6 +629,7 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWp2, M, m->bnp2);
+    small_a(g, v.tmY1_s);
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
     g.n_slots = 1; g.y_slot[0] = 0;
@@ -618,6 +639,7 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
   {
     const int bn = (mt * (m->ZP / 256) <= 74) ? 128 : 256;   // small grids: half-width tiles, one 32-class group per thread
     GemmCommon g = common(*v.tmY2, bn == 128 ? m->tmWp3h : m->tmWp3, M, bn);
+    small_a(g, v.tmY2_s);
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
     EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
@@ -664,11 +686,13 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
     if (z_idx) use_z_indices(m, g, v);
+    small_a(g, v.tmS_s);
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
     RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWh2, M, m->bnh2);
+    small_a(g, v.tmY1_s);
     g.a_row0 = v.slot_rows + v.row0; g.a_y_stride = v.slot_rows;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[0], 64);
     g.n_slots = n_slots;
@@ -678,6 +702,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
   }
   {
     GemmCommon g = common(*v.tmY2, m->tmWh3, M, 256);
+    small_a(g, v.tmY2_s);
     g.a_row0 = v.slot_rows + v.row0; g.a_y_stride = v.slot_rows;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[1], 64);
     g.n_slots = n_slots;
@@ -888,6 +913,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "multicast") o.multicast = value != 0;
   else if (n == "ln_cluster") o.ln_cluster = value != 0;
   else if (n == "chain") o.chain = value != 0;
+  else if (n == "small_a") o.small_a = value != 0;
   else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
   else return fail(DRM_ERR_ARG, "drm_set_option: unknown option '" + n + "'");

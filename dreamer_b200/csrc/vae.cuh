@@ -234,6 +234,7 @@ struct drm_observe {
   uint8_t* Zi;               // sampled posterior indices [rows_p, R] parallel to S
   float *zero_h, *featpart;
   CUtensorMap tmS, tmY1, tmY2, tmFeat, tmPatchE[4], tmPatchD[4];
+  CUtensorMap tmS_s, tmY1_s, tmY2_s;   // short-box twins (SMALL_A_ROWS rows) for steps with few sequences
   long patch_elems, act_elems;
   std::vector<void*> allocs;
   bool scanned;
@@ -261,7 +262,7 @@ static std::vector<int> scaled(int n, int limit, int scale, int offset = 0) {  /
   return r;
 }
 static WsView view_of(drm_observe* o, int row0) {
-  return WsView{&o->tmS, o->S, &o->tmY1, &o->tmY2, o->Y1, o->Y2, o->rows_p, row0, o->Zi};
+  return WsView{&o->tmS, o->S, &o->tmY1, &o->tmY2, o->Y1, o->Y2, o->rows_p, row0, o->Zi, &o->tmS_s, &o->tmY1_s, &o->tmY2_s};
 }
 // sub-pixel decomposition of ConvTranspose2d(k4, s2, p1): output o = 2 q + p gets taps
 //   p = 0: (input q, kernel 1), (q - 1, kernel 3);   p = 1: (q, kernel 2), (q + 1, kernel 0)
@@ -464,6 +465,9 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
   TRY(make_tmap_bf16_2d(&o->tmS, o->S, o->rows_p, m->KS, m->KS, BM));
   TRY(make_tmap_bf16_2d(&o->tmY1, o->Y1, (uint64_t)(MAX_HEADS + 1) * o->rows_p, 256, 256, BM));
   TRY(make_tmap_bf16_2d(&o->tmY2, o->Y2, (uint64_t)(MAX_HEADS + 1) * o->rows_p, 256, 256, BM));
+  TRY(make_tmap_bf16_2d(&o->tmS_s, o->S, o->rows_p, m->KS, m->KS, SMALL_A_ROWS));
+  TRY(make_tmap_bf16_2d(&o->tmY1_s, o->Y1, (uint64_t)(MAX_HEADS + 1) * o->rows_p, 256, 256, SMALL_A_ROWS));
+  TRY(make_tmap_bf16_2d(&o->tmY2_s, o->Y2, (uint64_t)(MAX_HEADS + 1) * o->rows_p, 256, 256, SMALL_A_ROWS));
   TRY(make_tmap_bf16_2d(&o->tmFeat, o->feat, round_up(NF, BM) + BM, v->Kf, v->Kf, BM));
   for (int i = 0; i < 4; ++i) {
     TRY(make_tmap_bf16_2d(&o->tmPatchE[i], o->patch, (uint64_t)(o->patch_elems / v->EK[i]), v->EK[i], v->EK[i], BM));
@@ -576,6 +580,7 @@ static int encoder_head(drm_observe* o, const WsView& vw, const float* addend, c
   const int mt = ceil_div(M, BM);
   {
     GemmCommon g = common(*vw.tmS, v->tmWeh, M, v->bn_he);
+    small_a(g, vw.tmS_s);
     g.a_row0 = vw.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
@@ -585,6 +590,7 @@ static int encoder_head(drm_observe* o, const WsView& vw, const float* addend, c
   {
     const int bn = (mt * (m->ZP / 256) <= 74) ? 128 : 256;
     GemmCommon g = common(*vw.tmY1, bn == 128 ? v->tmWe3h : v->tmWe3, M, bn);
+    small_a(g, vw.tmY1_s);
     g.a_row0 = vw.row0;
     g.ka0 = 0; g.nka0 = ceil_div(v->d.h_enc, 64);
     EpiCat::Params p{v->e3_b, uniforms, latent, logits, idx, write_sz ? vw.S + (long)vw.row0 * m->KS : nullptr, nullptr,
@@ -607,12 +613,14 @@ static int decoder_dense(drm_observe* o, const WsView& vw, __nv_bfloat16* act0, 
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
     if (z_idx) use_z_indices(m, g, vw);
+    small_a(g, vw.tmS_s);
     EpiLnSilu::Params p{v->d1_b, v->d1_g, v->d1_be, nullptr, 0, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_dec, 1e-5f, v->bn_hd};
     RC(launch_ln<false>(g, v->tmWd1, v->tmWd1q, v->bn_hd, p, mt, 1, st, DRM_STAGE_OTHER));
   }
   {
     const int N = v->hw4 * v->dbn[0];
     GemmCommon g = common(*vw.tmY1, v->tmWd2, M, 256);
+    small_a(g, vw.tmY1_s);
     g.a_row0 = vw.row0;
     g.ka0 = 0; g.nka0 = ceil_div(v->d.h_dec, 64);
     EpiPlain::Params p{v->d2_b, nullptr, act0, 0, (long)N, N, 1, 0, rm};
