@@ -227,6 +227,46 @@ def secondary_metrics(dev, peaks, flush):
     out["agent_step_c2"] = dict(workload="Agent.train_step on 1024 x 15 imagined states", train_step_ms=t_ag * 1e3, eager_train_step_ms=t_a * 1e3,
                                 states_per_s=1024 * 15 / t_ag)
     del ag, zz, hh
+    # fused optimiser tail on a flat bucket (drm_adamw_step: norm pass + update pass), 64 Mi parameters
+    from dreamer_b200 import _lib as L_
+    lib_ = L_.load()
+    n_p = 1 << 26
+    bufs = [torch.randn(n_p, device=dev) * 0.01 for _ in range(2)] + [torch.zeros(n_p, device=dev) for _ in range(2)]
+    st_ = torch.zeros(8, device=dev)
+    scr_ = torch.zeros(int(lib_.drm_adamw_scratch_bytes()) // 8, dtype=torch.float64, device=dev)
+    t = dev_time(lambda: L_.check(lib_.drm_adamw_step(L_.ptr(bufs[0]), L_.ptr(bufs[1]), L_.ptr(bufs[2]), L_.ptr(bufs[3]), n_p, L_.ptr(st_), L_.ptr(scr_),
+                                                       1e-4, 0.9, 0.999, 1e-8, 1e-6, 100.0, None, 0.0, 0, L_.stream()), "adamw"), reps=5)
+    by = n_p * (4 + 16 + 12)
+    out["adamw_flat"] = dict(workload="clip + AdamW on a flat bucket of 64 Mi fp32 parameters (3 launches)", bytes_per_launch=by, us=t * 1e6,
+                             achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"], frac=by / t / 1e9 / peaks["hbm"],
+                             note="algorithmic bytes: 4 B/param norm pass + 16 B read + 12 B written in the update pass")
+    del bufs
+    # B = 1 acting path (Dreamer.rollout_policy inner loop): record -> observe_step -> act per environment step, host frame in, action out
+    import numpy as np
+    import time as _time
+    from dreamer_b200.acting import ActingPath
+    from dreamer_b200.modules import Buffer
+    cfg1 = dict(W.REF_CONFIG)
+    wm1, ag1 = W.build_learners(cfg1, W.make_state_dict(cfg1, seed=0), dev)
+    ring1 = Buffer(4096, 50, cfg1["action_dims"], tuple(cfg1["observation_dims"]), device=dev)
+    frames = np.random.default_rng(0).integers(0, 256, size=(64, 3, 64, 64)).astype(np.uint8)
+    rates = {}
+    for mode, use_graphs in (("graph", True), ("eager", False)):
+        ap = ActingPath(wm1, ag1, ring1, use_graphs=use_graphs)
+        ap.reset(frames[0]); ap.act()
+        for i in range(8):
+            ap.step(frames[i % 64], 0.1, 1.0)
+        torch.cuda.synchronize()
+        n_steps = 300
+        t0 = _time.perf_counter()
+        for i in range(n_steps):
+            ap.step(frames[i % 64], 0.1, 1.0)
+        torch.cuda.synchronize()
+        rates[mode] = n_steps / (_time.perf_counter() - t0)
+    out["acting_b1"] = dict(workload="one environment: pinned u8 frame in -> ring insert + observe_step + act -> action out, per step",
+                            env_steps_per_s=rates["graph"], us_per_step=1e6 / rates["graph"], eager_env_steps_per_s=rates["eager"],
+                            note="wall clock over 300 steps including the host read-back every step (the environment needs the action)")
+    del wm1, ag1, ring1
     # the north star's large-batch points: 16 384 start states x horizon 15 on this one GPU (GRU stage vs the measured bf16 peak)
     import ctypes as C
     from dreamer_b200 import _lib as L

@@ -8,7 +8,13 @@ does (Dreamer.py:71-125) and re-implements only the four methods on the hot path
     dream_episodes        Dreamer.py:143-175   ONE fused rollout instead of horizon x (Actor.act -> imagine_step)
     train_Agent           Dreamer.py:264-287   sample -> warm start -> dream -> Agent.train_step, AC_epochs times
 
-Environment stepping, evaluation, checkpoints and logging stay in the reference's ``Dreamer.py`` (out of scope).  Under
+plus the two file formats either side of it:
+
+    save_trained_Dreamer / load_pretrained_dreamer   Dreamer.py:289-293   the reference's ``.pth``: state_dict with its 97 keys
+    save_training_state / load_training_state        (the reference saves none of this)  optimisers, return scale S, RNG, ring
+
+and ``acting()`` -- the B = 1 acting path of Dreamer.rollout_policy / evaluate_agent (acting.ActingPath, 8f rank 3).
+Environment stepping, evaluation and logging stay in the reference's ``Dreamer.py`` (out of scope).  Under
 ``torch.distributed`` every rank draws its own replay windows / start states (data parallel).
 """
 from __future__ import annotations
@@ -67,6 +73,78 @@ class HotPath:
             loss_actor, loss_critic = self.agent.train_step(z, h, r, c, a, mu, sg)
             la.append(loss_actor); lc.append(loss_critic)
         return torch.stack(la).mean(dim=0), torch.stack(lc).mean(dim=0)
+
+
+    # ---- 8f rank 3: the acting path -------------------------------------------------------------------------------------
+    def acting(self, deterministic: bool = False, use_graphs: bool = True):
+        """ActingPath on this HotPath's models and replay ring (one per policy mode; cached)."""
+        from .acting import ActingPath
+        key = (bool(deterministic), bool(use_graphs))
+        cache = self.__dict__.setdefault("_acting", {})
+        if key not in cache:
+            cache[key] = ActingPath(self.world_model, self.agent, self.buffer, deterministic=deterministic, use_graphs=use_graphs)
+        return cache[key]
+
+    # ---- 8f rank 4: checkpoint formats ---------------------------------------------------------------------------------
+    def state_dict(self):
+        """The reference Dreamer's state_dict: ``world_model.*`` then ``agent.*`` (97 keys at the reference config)."""
+        sd = {"world_model." + k: v for k, v in self.world_model.state_dict().items()}
+        sd.update({"agent." + k: v for k, v in self.agent.state_dict().items()})
+        return sd
+
+    def load_state_dict(self, sd, strict: bool = True):
+        self.world_model.load_state_dict({k[len("world_model."):]: v for k, v in sd.items() if k.startswith("world_model.")}, strict=strict)
+        self.agent.load_state_dict({k[len("agent."):]: v for k, v in sd.items() if k.startswith("agent.")}, strict=strict)
+        if strict:
+            extra = [k for k in sd if not (k.startswith("world_model.") or k.startswith("agent."))]
+            if extra:
+                raise RuntimeError(f"unexpected keys in checkpoint: {extra[:5]}")
+
+    def save_trained_Dreamer(self, save_path):                       # Dreamer.py:292-293
+        torch.save({k: v.detach().cpu() for k, v in self.state_dict().items()}, save_path)
+
+    def load_pretrained_dreamer(self, path):                         # Dreamer.py:289-290
+        self.load_state_dict(torch.load(path, weights_only=True, map_location=self.device))
+
+    def save_training_state(self, path, include_buffer: bool = False):
+        """Everything a bit-exact resume needs and the reference omits: optimiser moments and step counts, the return scale S,
+        torch / numpy RNG states, replay cursor (and, optionally, the ring contents)."""
+        import numpy as np
+        buf = self.buffer
+        state = dict(model={k: v.detach().cpu() for k, v in self.state_dict().items()},
+                     optim=dict(world_model=self.world_model.optimiser.state_dict(), actor=self.agent.actor_optimiser.state_dict(),
+                                critic=self.agent.critic_optimiser.state_dict()),
+                     S=float(self.agent.S), torch_rng=torch.get_rng_state(),
+                     cuda_rng=torch.cuda.get_rng_state(self.device) if self.device.type == "cuda" else None,
+                     numpy_rng=np.random.get_state(), buffer=dict(size=buf.size, next_idx=buf.next_idx, capacity=buf.capacity))
+        if include_buffer:
+            n = buf.size
+            state["buffer"].update(observation=buf.observation_buffer[:n].cpu(), action=buf.action_buffer[:n].cpu(),
+                                   reward=buf.reward_buffer[:n].cpu(), cont=buf.continue_buffer[:n].cpu())
+        torch.save(state, path)
+
+    def load_training_state(self, path):
+        import numpy as np
+        state = torch.load(path, weights_only=False, map_location="cpu")
+        self.load_state_dict({k: v.to(self.device) for k, v in state["model"].items()})
+        self.world_model.optimiser.load_state_dict(state["optim"]["world_model"])
+        self.agent.actor_optimiser.load_state_dict(state["optim"]["actor"])
+        self.agent.critic_optimiser.load_state_dict(state["optim"]["critic"])
+        if isinstance(self.agent.S, torch.Tensor):
+            self.agent.S.fill_(state["S"])
+        else:
+            self.agent.S = state["S"]
+        torch.set_rng_state(state["torch_rng"])
+        if state.get("cuda_rng") is not None and self.device.type == "cuda":
+            torch.cuda.set_rng_state(state["cuda_rng"], self.device)
+        np.random.set_state(state["numpy_rng"])
+        b = state["buffer"]
+        if "observation" in b:
+            n = b["size"]
+            buf = self.buffer
+            buf.observation_buffer[:n].copy_(b["observation"]); buf.action_buffer[:n].copy_(b["action"])
+            buf.reward_buffer[:n].copy_(b["reward"]); buf.continue_buffer[:n].copy_(b["cont"])
+            buf.size, buf.next_idx = b["size"], b["next_idx"]
 
 
 def _build(cfg, device):

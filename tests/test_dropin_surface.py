@@ -55,3 +55,45 @@ def test_mirrors_match_reference_default_init_shapes():
     assert c.buckets_crit.shape == (255,) and float(c.buckets_crit[127]) != 0.0
     ag = learners.Agent(3, (32, 32), 96, 72, 72, 72, 72, 255, 8e-5, (0.9, 0.999), 1e-5, 1e-4, (0.9, 0.999), 1e-5, 3e-4, 0.95, 0.99, device="cpu")
     assert not any(p.requires_grad for p in ag.target_critic.parameters()) and ag.S == 1.0
+
+
+def test_hotpath_checkpoint_is_the_reference_pth_format(tmp_path):
+    """HotPath.save_trained_Dreamer writes what Dreamer.save_trained_Dreamer writes (Dreamer.py:289-293): a state_dict with the
+    reference's keys in its order; load_pretrained_dreamer reads it back.  When the reference tree is present, the file is
+    loaded by the reference's OWN unmodified classes with strict=True, and a file the reference wrote loads here."""
+    from dreamer_b200.hotpath import HotPath
+    from oracle import weights as W
+    cfg = W.small_config()
+    hp = HotPath(cfg, "cpu")
+    sd = W.make_state_dict(cfg, seed=3)
+    hp.load_state_dict(sd)
+    path = str(tmp_path / "agent.pth")
+    hp.save_trained_Dreamer(path)
+    on_disk = torch.load(path, weights_only=True)
+    assert list(on_disk.keys()) == list(sd.keys())
+    assert all(torch.equal(on_disk[k], sd[k]) for k in sd)
+    hp2 = HotPath(cfg, "cpu")
+    hp2.load_pretrained_dreamer(path)
+    assert all(torch.equal(a, b) for a, b in zip(hp.state_dict().values(), hp2.state_dict().values()))
+    with pytest.raises(RuntimeError):
+        hp2.load_state_dict({**sd, "bogus.key": torch.zeros(1)})
+    if not os.path.exists(os.path.join(REF, "Dreamer.py")):
+        return
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k in ("Dreamer", "WorldModel", "Agent", "Buffer", "SequenceModel",
+                                                                          "DynamicsPredictors", "VariationalAutoEncoder", "DreamerUtils")}
+    sys.path.insert(0, REF)
+    try:
+        import Dreamer as D                                  # the genuine reference classes, no drop-in
+        d = D.Dreamer(dict(cfg), torch.device("cpu"))
+        assert not type(d.world_model).__module__.startswith("dreamer_b200")
+        d.load_pretrained_dreamer(path)                      # our file -> reference (strict)
+        ref_path = str(tmp_path / "ref.pth")
+        d.save_trained_Dreamer(ref_path)                     # reference file -> us
+        hp3 = HotPath(cfg, "cpu")
+        hp3.load_pretrained_dreamer(ref_path)
+        assert all(torch.equal(a, b) for a, b in zip(hp.state_dict().values(), hp3.state_dict().values()))
+    finally:
+        sys.path.remove(REF)
+        for k in ("Dreamer", "WorldModel", "Agent", "Buffer", "SequenceModel", "DynamicsPredictors", "VariationalAutoEncoder", "DreamerUtils"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)

@@ -64,3 +64,35 @@ def test_warm_start_matches_oracle_and_iteration_trains():
         hp.world_model.training_step(o2, a2, r2, c2, uniforms=uu)
     l1 = hp.world_model.loss_forward(o2, a2, r2, c2, uniforms=uu)[0].item()
     assert l1 < l0, (l0, l1)
+
+
+def test_training_state_resume_continues_the_run(tmp_path):
+    """save_training_state / load_training_state (optimiser moments + step counts, S, RNG, ring): a run resumed from the file
+    draws the same replay windows and latents, so its first loss is bit-identical to the original run's next loss, and it stays
+    on the original run's trajectory (to the rounding of cuDNN's non-deterministic conv-gradient reductions)."""
+    from dreamer_b200.hotpath import HotPath
+    cfg = W.small_config(batch_size=4, sequence_length=8, horizon=4, buffer_size=64)
+    torch.manual_seed(0)
+    a = HotPath(cfg, DEV)
+    _fill(a.buffer, cfg, 48)
+    np.random.seed(3)
+    a.train_world_model(); a.train_Agent()
+    path = str(tmp_path / "state.pt")
+    a.save_training_state(path, include_buffer=True)
+    m_a, v_a = a.world_model.optimiser.exp_avg.clone(), a.agent.critic_optimiser.exp_avg_sq.clone()
+    t_a = float(a.world_model.optimiser.opt_state[0])
+    la, aa = a.train_world_model(), a.train_Agent()       # the original run goes on (the RNG streams are process-global) ...
+    torch.manual_seed(1)
+    b = HotPath(cfg, DEV)
+    b.load_training_state(path)                           # ... then a fresh process state is rewound to the checkpoint
+    assert b.buffer.size == a.buffer.size and torch.equal(b.buffer.observation_buffer[:48], a.buffer.observation_buffer[:48])
+    assert float(b.world_model.optimiser.opt_state[0]) == t_a > 0
+    assert torch.equal(m_a, b.world_model.optimiser.exp_avg) and torch.equal(v_a, b.agent.critic_optimiser.exp_avg_sq)
+    lb, ab = b.train_world_model(), b.train_Agent()
+    assert torch.equal(la[0], lb[0])
+    assert all(torch.allclose(x, y, rtol=1e-3) for x, y in zip(la, lb))
+    assert torch.allclose(aa[0], ab[0], rtol=1e-2, atol=1e-3) and torch.allclose(aa[1], ab[1], rtol=1e-3)
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.allclose(x, y, rtol=1e-3, atol=1e-4), k
+    assert abs(float(a.agent.S) - float(b.agent.S)) < 1e-5
+    assert float(a.world_model.optimiser.opt_state[0]) == float(b.world_model.optimiser.opt_state[0])
