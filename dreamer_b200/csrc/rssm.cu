@@ -74,6 +74,7 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
   int small_a;     // 1: stages with <= 32 rows load 32-row A boxes (default 1)
   int lanes;       // rollouts: 0 / 1 one lane (default), 2 two half-batches on two internal streams
   int chain;       // 1: small grids run each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel (default 1)
@@ -87,6 +88,7 @@ static Options& opts() {
     x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
     x.chain = getenv("DRM_CHAIN") != nullptr;
     x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
+    x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
     x.gru_u = e ? atoi(e) : 0;
@@ -142,6 +144,43 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
   return DRM_OK;
 }
 
+}  // namespace drm
+#include "gru_pair.cuh"
+namespace drm {
+
+template <int U>
+static int launch_gru_pair(const GemmCommon& g, const typename EpiGru<U, 1>::Params& ep, int mt, int tiles, cudaStream_t st) {
+  using SL = GruPairSmem<U>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(gru_pair_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
+    attr_set = true;
+  }
+  profile_begin(DRM_STAGE_GRU, st);
+  if (g_timeline) const_cast<GemmCommon&>(g).cta_times = g_timeline + 16 * DRM_STAGE_COUNT + 1024 * DRM_STAGE_GRU;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(round_up(mt, 2), tiles);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SL::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, gru_pair_kernel<U>, g, ep));
+  profile_end(DRM_STAGE_GRU, st);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // packed model
 // ------------------------------------------------------------------------------------------
@@ -173,6 +212,7 @@ struct drm_rssm {
   CUtensorMap tmWp1q, tmWp2q, tmWh1q, tmWh2q;   // box rows 64: the cluster-of-4 LN stage
   CUtensorMap tmWp3h;                           // box rows 128: half-width categorical tiles for small grids
   CUtensorMap tmWh3q;                           // box rows 64: output layer of the chained heads kernel
+  CUtensorMap tmWgruQ[2];                      // box rows U / 2: the CTA-pair GRU kernel stages gate blocks and n halves separately
   CUtensorMap tmWgru2[2], tmWgruHalf2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
   std::vector<VecOp> vec_ops;
@@ -360,6 +400,7 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
     const int U = 32 << v;
     TRY(make_tmap_bf16_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U));
     TRY(make_tmap_bf16_2d(&m->tmWgruHalf2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U / 2));   // multicast halves
+    TRY(make_tmap_bf16_2d(&m->tmWgruQ[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, U / 2));
   }
   TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, 256, DP, DP, m->bnp1));
   TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, 256, 256, 256, m->bnp2));
@@ -530,6 +571,20 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
   if (!mc) small_a(g, src.tmS_s);
   const dim3 grid(mc ? round_up(mt, 2) : mt, m->gru_tiles2[v]);
   __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
+  // CTA pairs (cta_group::2): two m-tiles issue one M = 256 MMA, each SM stages half of the weight tile (gru_pair.cuh).
+  // Measured: 16 384 rows, D = 4096: 897 -> 1057 TFLOP/s; D = 600: 647 -> 720; 1024 rows (76 pairs of U = 32 tiles): 21.6 -> 24.4 us,
+  // so the automatic choice pairs only the wide-tile (large-grid) configuration.
+  const bool pair = opts().gru_pair < 0 ? v == 1 : opts().gru_pair != 0;
+  if (pair && !mc && !g.zi && mt >= 2) {
+    g.tmB = m->tmWgruQ[v];
+    g.a_bytes = 0;
+    if (U == 32) {
+      EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+      return launch_gru_pair<32>(g, p, mt, m->gru_tiles2[v], st);
+    }
+    EpiGru<64, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+    return launch_gru_pair<64>(g, p, mt, m->gru_tiles2[v], st);
+  }
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
   {                                                                                                         \
     typename EpiGru<UU, CC>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D}; \
@@ -914,6 +969,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "ln_cluster") o.ln_cluster = value != 0;
   else if (n == "chain") o.chain = value != 0;
   else if (n == "small_a") o.small_a = value != 0;
+  else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
   else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
   else return fail(DRM_ERR_ARG, "drm_set_option: unknown option '" + n + "'");

@@ -63,6 +63,8 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_COUNT 8
 /* Runtime switches for the experimental / alternative kernel paths (all produce identical results):                  */
 /*   "ln_cluster" (default 1)  LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
+/*   "gru_pair"   (default -1) GRU stage on CTA pairs (tcgen05 cta_group::2, M = 256 MMAs, each SM stages half the weight tile):  */
+/*                             -1 = automatic (large grids, where it is 11-18 % faster), 0 = never, 1 = whenever >= 2 m-tiles      */
 /*   "small_a"    (default 1)  stages with <= 32 rows load 32-row A boxes by TMA instead of whole 128-row tiles          */
 /*   "lanes"      (default 0)  rollouts: 2 = two half-batches on two internal streams (bit-identical; measured: slower) */
 /*   "chain"      (default 0)  small grids: each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel, activations */
