@@ -372,7 +372,7 @@ struct EpiGru {
                                              int row, int part, int slot, int tid) {
     const int u0 = slot * U;
     const int D = p.D;
-    const int m0 = (int)blockIdx.x * BM;
+    const int m0 = m - row;   // first row of this tile (the CTA-pair kernel remaps tiles, so not blockIdx.x * BM)
     constexpr int pitch = U + 4;
     // h_prev tile [128 x U] -> smem, coalesced (consecutive threads on consecutive 16 bytes of a row)
     float* hp_tile = tile + BM * pitch;

@@ -74,8 +74,27 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int nk = g.nka0 + g.nka1;
-  const int slot = (int)blockIdx.y;
-  const int a_row = g.a_row0 + (int)blockIdx.x * BM;
+  // Tile order: CTAs become resident in linear blockIdx order (x fastest).  Walking all m-tiles of one n-tile first makes
+  // a resident wave (2 x 148 CTAs) cover every state row but only ~2 weight tiles, so the state buffer streams from DRAM
+  // once per ~2 n-tiles (ncu: 5.6 GB read for a 1 GB problem).  Bands of GM m-tiles x all n-tiles keep a wave's state rows
+  // and weight tiles both L2-resident.  GM is even, so the two CTAs of a cluster stay neighbouring m-tiles of one n-tile.
+  int m_tile = (int)blockIdx.x, slot = (int)blockIdx.y;
+  {
+    constexpr int GM = 16;
+    const int GX = (int)gridDim.x, NT = (int)gridDim.y;
+    const int full_bands = GX / GM;
+    const int id = (int)blockIdx.x + GX * (int)blockIdx.y;
+    if (id < full_bands * GM * NT) {
+      const int band = id / (GM * NT), r = id - band * GM * NT;
+      slot = r / GM;
+      m_tile = band * GM + (r - slot * GM);
+    } else {                      // the remaining (GX % GM) m-tiles: plain order over the tail columns of the grid
+      const int rem = GX - full_bands * GM, r = id - full_bands * GM * NT;
+      slot = r / rem;
+      m_tile = full_bands * GM + (r - slot * rem);
+    }
+  }
+  const int a_row = g.a_row0 + m_tile * BM;
   const int b_row = slot * 3 * U;
 
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
@@ -147,7 +166,7 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
     tc_fence_after();
     const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int m = (int)blockIdx.x * BM + row;
+    const int m = m_tile * BM + row;
     Epi::run(ep, g, epi_sm, reinterpret_cast<float*>(smem), tmem + ((uint32_t)(q * 32) << 16), m, row, part, slot, (int)threadIdx.x - 64);
   }
   tc_fence_before();
