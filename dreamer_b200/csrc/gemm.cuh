@@ -35,6 +35,7 @@ struct GemmCommon {
   int ka1, nka1;     //   consumed sequentially from 0
   int n_slots;       // 0: slot = blockIdx.y;  > 0: slot = y_slot[blockIdx.y]
   int y_slot[8];
+  int band;                // CTA-pair GRU kernel: m-tiles per band of the tile order (even; 0 = 16)
   int a_bytes;             // bytes one A k-block load delivers: 0 = the full 128-row tile; SMALL_A_ROWS * 128 when tmA has a short box
   unsigned long long* cta_times;  // debug: per-CTA {entry, wait over, exit, smid} records, or NULL
   unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL

@@ -80,7 +80,7 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
   // and weight tiles both L2-resident.  GM is even, so the two CTAs of a cluster stay neighbouring m-tiles of one n-tile.
   int m_tile = (int)blockIdx.x, slot = (int)blockIdx.y;
   {
-    constexpr int GM = 16;
+    const int GM = g.band > 0 ? g.band : 16;
     const int GX = (int)gridDim.x, NT = (int)gridDim.y;
     const int full_bands = GX / GM;
     const int id = (int)blockIdx.x + GX * (int)blockIdx.y;

@@ -578,6 +578,7 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
   if (pair && !mc && !g.zi && mt >= 2) {
     g.tmB = m->tmWgruQ[v];
     g.a_bytes = 0;
+    { static const int band = getenv("DRM_GRU_BAND") ? atoi(getenv("DRM_GRU_BAND")) : 0; g.band = band & ~1; }
     if (U == 32) {
       EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
       return launch_gru_pair<32>(g, p, mt, m->gru_tiles2[v], st);
