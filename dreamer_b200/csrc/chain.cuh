@@ -80,9 +80,6 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
                : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t remote_addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 __device__ __forceinline__ void cprobe(const ChainParams& p, int i) {
   if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {

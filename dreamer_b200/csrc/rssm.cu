@@ -52,11 +52,6 @@ __global__ void pack_state_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int c
     if (copy) copy[(long)r * ld_copy + c] = v;
   }
 }
-__global__ void zero_cols_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int col0, int ncols, int N) {
-  const long total = (long)N * ncols;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
-    S[(long)(i / ncols) * ld_s + col0 + (int)(i % ncols)] = __float2bfloat16_rn(0.f);
-}
 __global__ void f32_to_bf16_pad_kernel(__nv_bfloat16* __restrict__ dst, int ld_dst, const float* __restrict__ src, int rows,
                                        int cols) {
   const long total = (long)rows * ld_dst;

@@ -22,7 +22,7 @@ from . import ops
 from .graphs import StepGraph
 from .optim import FlatAdamW, make_adamw
 from .modules import (Actor, ContinuePredictor, Critic, Decoder, DynamicsPredictor, Encoder, RewardPredictor, SequenceModel,
-                      _Packed, _VaeEngine, symexp, symlog)
+                      _Packed, _VaeEngine, symlog)
 
 
 class WorldModel(nn.Module):

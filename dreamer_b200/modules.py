@@ -18,7 +18,6 @@ replace it are the first "next" row of SURVEY.md section 8f.
 """
 from __future__ import annotations
 
-import copy
 from typing import Dict, Optional
 
 import numpy as np
@@ -100,7 +99,7 @@ class _Packed:
         return self.ws[cap]
 
 
-def _flat2(x, keep_last=1):
+def _flat2(x):
     """(B, S, ...) -> (B*S, ...)"""
     return x.reshape((x.shape[0] * x.shape[1],) + tuple(x.shape[2:]))
 

@@ -16,7 +16,6 @@ It is a ``torch.optim.Optimizer``: ``param_groups`` (lr, betas, eps, weight_deca
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, Optional
 
 import torch
