@@ -210,12 +210,13 @@ def secondary_metrics(dev, peaks, flush):
     out["world_model_c3"] = dict(workload="batch 16 x seq 64, 64x64x3 frames (BASELINE configs[2])", loss_forward_steps_per_s=1.0 / t_f,
                                  loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_g, train_step_ms=t_g * 1e3,
                                  eager_train_step_ms=t_s * 1e3,
-                                 note="training step = kernel forward + interim torch autograd tail + fused clip/AdamW on the flat bucket, "
+                                 note="training step = kernel forward + hand-scheduled BPTT (bptt.py) + fused clip/AdamW on the flat bucket, "
                                       "replayed as one CUDA graph (DESIGN.md section 6); eager_train_step_ms is the same step issued launch by launch")
     del wm
     # actor-critic update on a config-2 rollout (1024 x 15): Agent.train_step, eager and as one CUDA graph
     cfg2 = dict(W.REF_CONFIG, horizon=15)
-    _, ag = W.build_learners(cfg2, W.make_state_dict(cfg2, seed=0), dev)
+    wm2, ag = W.build_learners(cfg2, W.make_state_dict(cfg2, seed=0), dev)
+    ag.attach_world_model(wm2)               # actor gradient through the imagined states (bptt.actor_backward), as the reference's autograd
     zz = torch.nn.functional.one_hot(torch.randint(0, 32, (1024, 16, 32), device=dev), 32).float()
     hh = torch.tanh(torch.randn(1024, 16, cfg2["hidden_state_dims"], device=dev))
     rr, cc = torch.randn(1024, 15, 1, device=dev), torch.ones(1024, 15, 1, device=dev)
@@ -226,7 +227,7 @@ def secondary_metrics(dev, peaks, flush):
     t_ag = dev_time(lambda: ag.train_step(zz, hh, rr, cc, aa, mu_, sg_), reps=10, warm=3)
     out["agent_step_c2"] = dict(workload="Agent.train_step on 1024 x 15 imagined states", train_step_ms=t_ag * 1e3, eager_train_step_ms=t_a * 1e3,
                                 states_per_s=1024 * 15 / t_ag)
-    del ag, zz, hh
+    del ag, wm2, zz, hh
     # fused optimiser tail on a flat bucket (drm_adamw_step: norm pass + update pass), 64 Mi parameters
     from dreamer_b200 import _lib as L_
     lib_ = L_.load()

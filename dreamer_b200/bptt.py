@@ -178,3 +178,118 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
     feats.backward(dfeat)    # encoder convs
     mark("encoder conv backward")
     return loss.detach()
+
+
+def _tanh_normal_log_prob(a, mu, sigma):
+    """Agent.py:110-115 (same expression as learners._tanh_normal_log_prob; duplicated to keep this module import-free)."""
+    a = torch.clamp(a, -1.0 + 1e-6, 1.0 - 1e-6)
+    y = torch.atanh(a)
+    base = -((y - mu) ** 2) / (2 * sigma ** 2) - torch.log(sigma) - 0.9189385332046727
+    return (base - 2.0 * (0.6931471805599453 - y - F.softplus(-2.0 * y))).sum(-1)
+
+
+def _mlp_fwd(x, lin_a, ln_a, lin_b, ln_b):
+    """Linear-LN-SiLU x2 keeping the pre-LayerNorm activations (the backward kernels recompute the statistics from them)."""
+    a1 = torch.addmm(lin_a.bias, x, lin_a.weight.t())
+    y1 = F.silu(F.layer_norm(a1, (a1.shape[-1],), ln_a.weight, ln_a.bias, ln_a.eps))
+    a2 = torch.addmm(lin_b.bias, y1, lin_b.weight.t())
+    y2 = F.silu(F.layer_norm(a2, (a2.shape[-1],), ln_b.weight, ln_b.bias, ln_b.eps))
+    return a1, y1, a2, y2
+
+
+def actor_backward(agent, wm, z, h, act, mu, sigma, coef):
+    """Accumulate into the ACTOR parameters' ``.grad`` the gradient of   sum_{b,t} coef[b,t] * log pi(a_t | h_t, z_t)
+    (Agent.py:110-126 with coef = (-advantage / max(S,1) + nu) / N) as the reference's autograd computes it: mu_t, sigma_t
+    depend on the actor parameters directly AND through the imagined state, because (h_t, z_t) were produced from the
+    reparameterised earlier actions a_s = tanh(mu_s + sigma_s eps_s) by the world model (Dreamer.py:158-164; the states are
+    not detached in Agent.py:110).  World-model parameters receive nothing (their gradients from this loss are discarded
+    by the reference's next WorldModel.zero_grad).
+
+    z (B,H+1,R,C) straight-through one-hot latents, h (B,H+1,D), act / mu / sigma (B,H,A) of the rollout, coef (B,H).
+    Structure: batched fp32 re-evaluation of every pre-activation on the rollout's trajectory, a backward walk over the H
+    steps (prior ST + MLP, GRU cell, actor MLP input gradients: ~27 launches per step on B rows), batched weight gradients."""
+    B, H1 = h.shape[:2]
+    H = H1 - 1
+    actor = agent.actor
+    l1, n1, _, l2, n2, _ = actor.base_net
+    gru = wm.sequence_model.GRU
+    p1, q1, _, p2, q2, _, p3 = wm.dynamics_predictor.logit_net
+    Dh, A = h.shape[-1], act.shape[-1]
+    if z.shape[-1] != 32:
+        raise RuntimeError("actor_backward: 32-class latents are required (drm_categorical32_bwd)")
+    with torch.no_grad():
+        Htm = h.detach().transpose(0, 1).contiguous()                                   # (H+1,B,D)
+        Ztm = z.detach().reshape(B, H1, -1).transpose(0, 1).contiguous()                # (H+1,B,Z)
+        Atm = act.detach().transpose(0, 1).contiguous()                                 # (H,B,A)
+        Z = Ztm.shape[-1]
+        Xa = torch.cat([Htm[:H], Ztm[:H]], -1).view(H * B, Dh + Z)                      # actor input [h, z] (Agent.py:196-198)
+        A1, Y1, A2, Y2 = _mlp_fwd(Xa, l1, n1, l2, n2)
+        LS = torch.addmm(actor.log_sig_head.bias, Y2, actor.log_sig_head.weight.t())
+        mu_k = mu.detach().transpose(0, 1).reshape(H * B, A)
+        sg_k = sigma.detach().transpose(0, 1).reshape(H * B, A)
+        a_flat = Atm.view(H * B, A)
+        EPS = ((torch.atanh(torch.clamp(a_flat, -1.0 + 1e-6, 1.0 - 1e-6)) - mu_k) / sg_k).view(H, B, A)   # the draw behind a_t
+    # direct d/d(mu, sigma) of the objective (closed-form expression differentiated by autograd on two leaves, batched)
+    mu_l, sg_l = mu_k.clone().requires_grad_(True), sg_k.clone().requires_grad_(True)
+    (coef.detach().transpose(0, 1).reshape(-1) * _tanh_normal_log_prob(a_flat, mu_l, sg_l)).sum().backward()
+    with torch.no_grad():
+        gMU, gSG = mu_l.grad.view(H, B, A), sg_l.grad.view(H, B, A)
+        # world-model pre-activations of the transitions s -> s+1, s = 0..H-1 (needed for s <= H-2)
+        X = torch.cat([Ztm[:H], Atm], -1).view(H * B, Z + A)
+        GI = torch.addmm(gru.bias_ih, X, gru.weight_ih.t()).view(H, B, 3 * Dh)
+        GH = torch.addmm(gru.bias_hh, Htm[:H].reshape(H * B, Dh), gru.weight_hh.t()).view(H, B, 3 * Dh)
+        P1, _, P2, PY2 = _mlp_fwd(Htm[1:].reshape(H * B, Dh), p1, q1, p2, q2)
+        LG = torch.addmm(p3.bias, PY2, p3.weight.t()).view(H, B, Z)                     # prior logits of states 1..H
+        P1, P2 = P1.view(H, B, -1), P2.view(H, B, -1)
+        A1s, A2s, LSs = A1.view(H, B, -1), A2.view(H, B, -1), LS.view(H, B, A)
+        Wih_z, Wih_a = gru.weight_ih[:, :Z].contiguous(), gru.weight_ih[:, Z:].contiguous()
+        W1_h, W1_z = l1.weight[:, :Dh].contiguous(), l1.weight[:, Dh:].contiguous()
+        Whead = torch.cat([actor.mu_head.weight, actor.log_sig_head.weight], 0)         # (2A, h2)
+        dHEAD = torch.empty(H, B, 2 * A, device=h.device)                               # d/d[mu | log-sigma pre-activation]
+        dY2s, dY1s = torch.empty_like(A2s), torch.empty_like(A1s)
+        dgi, dgh = torch.empty(B, 3 * Dh, device=h.device), torch.empty(B, 3 * Dh, device=h.device)
+        Gh = Gz = None                                                                  # gradient w.r.t. state s + 1 (zero for s + 1 = H)
+        for s in range(H - 1, -1, -1):
+            da = None
+            ch = cz = None                                                              # carried into state s from the transition s -> s + 1
+            if Gh is not None:
+                dlg = ops.categorical32_bwd(LG[s], Gz)                                  # z_{s+1} = ST(prior(h_{s+1}))
+                dP2 = ops.ln_silu_bwd(dlg @ p3.weight, P2[s], q2.weight, q2.bias, q2.eps)
+                dP1 = ops.ln_silu_bwd(dP2 @ p2.weight, P1[s], q1.weight, q1.bias, q1.eps)
+                Gh.addmm_(dP1, p1.weight)                                               # total d/dh_{s+1}
+                ch = torch.empty_like(Gh)
+                ops.gru_bwd(Gh, GI[s], GH[s], Htm[s], dgi, dgh, ch, accumulate=False)   # h_{s+1} = GRU([z_s, a_s], h_s)
+                ch.addmm_(dgh, gru.weight_hh)
+                cz = dgi @ Wih_z
+                da = dgi @ Wih_a
+            # actor at state s: a_s = tanh(mu_s + sigma_s eps_s), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209)
+            dmu, dsg = gMU[s], gSG[s]
+            if da is not None:
+                du = da * (1.0 - Atm[s] * Atm[s])
+                dmu, dsg = dmu + du, dsg + du * EPS[s]
+            ls = LSs[s]
+            dls = dsg * torch.sigmoid(torch.clamp(ls, -5.0, 2.0)) * ((ls > -5.0) & (ls < 2.0))
+            torch.cat([dmu, dls], -1, out=dHEAD[s])
+            torch.mm(dHEAD[s], Whead, out=dY2s[s])
+            dA2 = ops.ln_silu_bwd(dY2s[s], A2s[s], n2.weight, n2.bias, n2.eps)
+            torch.mm(dA2, l2.weight, out=dY1s[s])
+            if s > 0:                                                                   # state 0 is an input: nothing upstream
+                dA1 = ops.ln_silu_bwd(dY1s[s], A1s[s], n1.weight, n1.bias, n1.eps)
+                Gh = torch.mm(dA1, W1_h) if ch is None else ch.addmm_(dA1, W1_h)
+                Gz = torch.mm(dA1, W1_z) if cz is None else cz.addmm_(dA1, W1_z)
+        # ---- actor weight gradients: batched GEMMs over all B*H rows ----------------------------------------------------
+        dH2 = dHEAD.view(H * B, 2 * A)
+        _acc_mm(actor.mu_head.weight, dH2[:, :A], Y2)
+        _acc(actor.mu_head.bias, dH2[:, :A].sum(0))
+        _acc_mm(actor.log_sig_head.weight, dH2[:, A:], Y2)
+        _acc(actor.log_sig_head.bias, dH2[:, A:].sum(0))
+        dA2_all, dln2 = ops.ln_silu_bwd(dY2s.view(H * B, -1), A2, n2.weight, n2.bias, n2.eps, want_dln=True)
+        _acc(n2.weight, (dln2 * F.layer_norm(A2, (A2.shape[-1],), None, None, n2.eps)).sum(0))
+        _acc(n2.bias, dln2.sum(0))
+        _acc_mm(l2.weight, dA2_all, Y1)
+        _acc(l2.bias, dA2_all.sum(0))
+        dA1_all, dln1 = ops.ln_silu_bwd(dY1s.view(H * B, -1), A1, n1.weight, n1.bias, n1.eps, want_dln=True)
+        _acc(n1.weight, (dln1 * F.layer_norm(A1, (A1.shape[-1],), None, None, n1.eps)).sum(0))
+        _acc(n1.bias, dln1.sum(0))
+        _acc_mm(l1.weight, dA1_all, Xa)
+        _acc(l1.bias, dA1_all.sum(0))

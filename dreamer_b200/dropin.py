@@ -62,6 +62,7 @@ def uninstall():
 def patch_dreamer(dreamer_cls):
     """Replace the per-step Python loop of Dreamer.dream_episodes (Dreamer.py:143-175) by the fused rollout."""
     def dream_episodes(self, starting_latent_state_batch, starting_hidden_state_batch):
+        self.agent.attach_world_model(self.world_model)       # Agent.train_step: actor gradient through the imagined states
         return rollout.dream_episodes_modules(self.world_model, self.agent, starting_latent_state_batch, starting_hidden_state_batch, self.horizon)
     dreamer_cls.dream_episodes = dream_episodes
     return dreamer_cls

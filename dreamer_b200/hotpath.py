@@ -30,6 +30,7 @@ class HotPath:
         self.device = torch.device(device)
         from .modules import Buffer
         self.world_model, self.agent = _build(self.cfg, self.device)
+        self.agent.attach_world_model(self.world_model)      # actor gradient through the imagined states (bptt.actor_backward)
         self.buffer = Buffer(config["buffer_size"], config["sequence_length"], config["action_dims"], tuple(config["observation_dims"]),
                              device=self.device)
         self.horizon = config["horizon"]

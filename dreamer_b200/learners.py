@@ -330,14 +330,14 @@ class Agent(nn.Module):
         if D.any_rank_flag(bool(torch.isnan(la) or torch.isinf(la) or torch.isnan(lc) or torch.isinf(lc)), la.device):
             print("Agent loss is nan or inf, skipping update.")
             return la, lc
-        return self._backward_and_step(f, z_batch_seq, h_batch_seq, action_batch_seq)
+        return self._backward_and_step(f, z_batch_seq, h_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq)
 
     def _step_body(self, z, h, rew, cont, act, mu, sigma):
         """One whole Agent.train_step with no host synchronisation (capturable); non-finite losses are skipped by the
         optimisers' device-side check instead of Agent.py:137-139."""
         f = self.losses_forward(z, h, rew, cont, act, mu, sigma)
         self.last = f
-        return self._backward_and_step(f, z, h, act)
+        return self._backward_and_step(f, z, h, act, mu, sigma)
 
     def enable_cuda_graphs(self, warmup: int = 3):
         """Replay train_step as one CUDA graph per input shape after `warmup` eager steps (graphs.StepGraph)."""
@@ -354,10 +354,16 @@ class Agent(nn.Module):
         self.__dict__["_graphs"] = StepGraph(self._step_body, warmup, before_capture, after_replay)
         return self
 
-    def _backward_and_step(self, f, z_batch_seq, h_batch_seq, action_batch_seq):
+    def attach_world_model(self, world_model):
+        """Give train_step access to the world model the rollout came from, so the actor gradient includes the path through
+        the imagined states (bptt.actor_backward).  HotPath and dropin.patch_dreamer call this; without it the gradient is the
+        detached-state policy gradient."""
+        object.__setattr__(self, "_world_model", world_model)
+        return self
+
+    def _backward_and_step(self, f, z_batch_seq, h_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq):
         la, lc = f["loss_actor"], f["loss_critic"]
-        # gradients (interim torch tail): critic CE on the kernel's returns; policy gradient through mu, sigma recomputed on the
-        # (detached) imagined states -- the through-the-world-model term (about 3 % at init) needs the BPTT kernels.
+        # critic: two-hot CE on the kernel's lambda-returns (torch autograd on the batched MLP)
         B, H1 = h_batch_seq.shape[:2]
         hz = torch.cat([h_batch_seq.detach(), z_batch_seq.detach().reshape(B, H1, -1)], -1)
         self.critic_optimiser.zero_grad()
@@ -368,11 +374,20 @@ class Agent(nn.Module):
         w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
         ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / f["n_global"]).backward()
         self.actor_optimiser.zero_grad()
-        base = self.actor.base_net(hz[:, :-1])
-        mu_t = self.actor.mu_head(base)
-        sg_t = F.softplus(torch.clamp(self.actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
-        logp = _tanh_normal_log_prob(action_batch_seq.detach(), mu_t, sg_t)
-        ((-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).sum() / f["n_global"]).backward()
+        wm = self.__dict__.get("_world_model")
+        if wm is not None and self.__dict__.get("grad_mode", "bptt") == "bptt" and z_batch_seq.shape[-1] == 32:
+            # the reference's actor gradient: through mu_t, sigma_t directly AND through the imagined states' dependence on the
+            # earlier reparameterised actions (the states are not detached in Agent.py:110) -- hand-scheduled BPTT over the rollout
+            coef = (-(f["advantage"] / f["norm"]) + self.nu) / f["n_global"]
+            bptt.actor_backward(self, wm, z_batch_seq, h_batch_seq, action_batch_seq, a_mu_batch_seq, a_sigma_batch_seq, coef)
+        else:
+            # no world model attached: policy gradient through mu, sigma recomputed on the detached imagined states (omits the
+            # through-the-world-model term, about 3 % of the gradient at initialisation)
+            base = self.actor.base_net(hz[:, :-1])
+            mu_t = self.actor.mu_head(base)
+            sg_t = F.softplus(torch.clamp(self.actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
+            logp = _tanh_normal_log_prob(action_batch_seq.detach(), mu_t, sg_t)
+            ((-(logp * (f["advantage"] / f["norm"])) - self.nu * (-logp)).sum() / f["n_global"]).backward()
         if isinstance(self.critic_optimiser, FlatAdamW) and isinstance(self.actor_optimiser, FlatAdamW):
             # SUM of per-rank shares = gradient of the global means (flat 1.67 MB and 1.47 MB buckets); the critic's pass also
             # moves the target critic: target = 0.98 target + 0.02 updated critic

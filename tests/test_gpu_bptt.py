@@ -105,3 +105,54 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
     g_b = _grads(wm)
     num = sum(float(((g_ref[k] - g_b[k]) ** 2).sum()) for k in g_ref)
     assert (num / den) ** 0.5 < 3e-2
+
+
+def test_actor_gradient_through_the_imagined_states_matches_autograd():
+    """bptt.actor_backward against torch autograd over a pure-torch imagination (Dreamer.py:158-164 + Agent.py:110-126) on the
+    same classes and draws: the reference's actor gradient, INCLUDING the path through the imagined states.  Also shows that the
+    detached-state gradient (no world model attached) differs from it, i.e. that the through-the-world-model term is real."""
+    from dreamer_b200 import bptt
+    cfg = W.small_config(horizon=6)
+    sd = W.make_state_dict(cfg, seed=31, actor_mu_zero=False)
+    wm, ag = W.build_learners(cfg, sd, DEV)
+    B, H, D, A = 24, cfg["horizon"], cfg["hidden_state_dims"], cfg["action_dims"]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    z = F.one_hot(torch.randint(0, 32, (B, 32), device=DEV, generator=g), 32).float().reshape(B, 1024)
+    h = torch.tanh(torch.randn(B, D, device=DEV, generator=g))
+    idx = torch.randint(0, 32, (H, B, 32), device=DEV, generator=g)
+    eps = torch.randn(H, B, A, device=DEV, generator=g)
+    coef = torch.randn(B, H, device=DEV, generator=g) / (B * H)
+    actor, gru, prior = ag.actor, wm.sequence_model.GRU, wm.dynamics_predictor.logit_net
+    zs, hs, acts, mus, sgs = [z], [h], [], [], []
+    for t in range(H):
+        base = actor.base_net(torch.cat([h, z], -1))
+        mu = actor.mu_head(base)
+        sg = F.softplus(torch.clamp(actor.log_sig_head(base), -5.0, 2.0)) + 1e-3
+        a = torch.tanh(mu + sg * eps[t])
+        h = gru(torch.cat([z, a], -1), h)
+        lg = prior(h).view(B, 32, 32)
+        p = 0.99 * torch.softmax(lg, -1) + 0.01 / 32
+        z = (F.one_hot(idx[t], 32).float() + p - p.detach()).reshape(B, 1024)
+        zs.append(z); hs.append(h); acts.append(a); mus.append(mu); sgs.append(sg)
+    Z, Hh = torch.stack(zs, 1), torch.stack(hs, 1)
+    Aa, MU, SG = torch.stack(acts, 1), torch.stack(mus, 1), torch.stack(sgs, 1)
+    logp = bptt._tanh_normal_log_prob(Aa.detach(), MU, SG)
+    for p_ in ag.actor.parameters():
+        p_.grad = None
+    (coef * logp).sum().backward()
+    g_ref = {k: p_.grad.detach().clone() for k, p_ in ag.actor.named_parameters()}
+    ag.actor_optimiser.zero_grad()
+    bptt.actor_backward(ag, wm, Z.detach().view(B, H + 1, 32, 32), Hh.detach(), Aa.detach(), MU.detach(), SG.detach(), coef)
+    g_new = {k: p_.grad.detach().clone() for k, p_ in ag.actor.named_parameters()}
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max()) + 1e-12
+        assert float((g_ref[k] - g_new[k]).abs().max()) / scale < 2e-3, k
+    # detached-state gradient: same objective, states treated as constants
+    ag.actor_optimiser.zero_grad()
+    hz = torch.cat([Hh.detach(), Z.detach()], -1)[:, :-1]
+    base = actor.base_net(hz)
+    lp = bptt._tanh_normal_log_prob(Aa.detach(), actor.mu_head(base), F.softplus(torch.clamp(actor.log_sig_head(base), -5.0, 2.0)) + 1e-3)
+    (coef * lp).sum().backward()
+    num = sum(float(((g_ref[k] - p_.grad) ** 2).sum()) for k, p_ in ag.actor.named_parameters())
+    den = sum(float((g_ref[k] ** 2).sum()) for k in g_ref)
+    assert (num / den) ** 0.5 > 1e-3
