@@ -23,6 +23,20 @@ from . import dist as D
 from . import ops
 
 
+# The backward's library GEMMs run on the tensor cores in TF32 (10-bit mantissa, what the reference's fp16 autocast keeps,
+# WorldModel.py:162); set to False for bit-for-bit fp32 GEMMs (the gradient tests compare both ways against fp32 autograd).
+MATMUL_TF32 = True
+
+
+class _matmul_precision:
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(MATMUL_TF32)
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 def _acc(p: torch.nn.Parameter, g: torch.Tensor):
     if p.grad is None:
         p.grad = torch.zeros_like(p)
@@ -38,7 +52,7 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
 
 def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
     # the batched conv graph has fixed shapes: let cuDNN pick its fastest (TF32 tensor-core) algorithms during the eager warm-up
-    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True):
+    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True), _matmul_precision():
         return _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts, marks)
 
 
@@ -198,6 +212,11 @@ def _mlp_fwd(x, lin_a, ln_a, lin_b, ln_b):
 
 
 def actor_backward(agent, wm, z, h, act, mu, sigma, coef):
+    with _matmul_precision():
+        return _actor_backward(agent, wm, z, h, act, mu, sigma, coef)
+
+
+def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
     """Accumulate into the ACTOR parameters' ``.grad`` the gradient of   sum_{b,t} coef[b,t] * log pi(a_t | h_t, z_t)
     (Agent.py:110-126 with coef = (-advantage / max(S,1) + nu) / N) as the reference's autograd computes it: mu_t, sigma_t
     depend on the actor parameters directly AND through the imagined state, because (h_t, z_t) were produced from the
