@@ -135,8 +135,10 @@ struct EpiLnSiluT {
       }
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
-                                             int row, int part, int slot, int tid) {
+  // LayerNorm + SiLU of this thread's 64 columns; every 32-column chunk of the ceil64(n_valid) output columns goes to emit(c, v).
+  template <class Emit>
+  static __device__ __forceinline__ void normalise(const Params& p, const GemmCommon& g, float* sm, uint32_t taddr, int m, int row,
+                                                   int part, int ncols, Emit&& emit) {
     const int nv = p.n_valid;
     const int c0 = part * 64;
     const int cnt = max(0, min(64, nv - c0));          // this part's valid columns
@@ -177,8 +179,6 @@ struct EpiLnSiluT {
     }
     const float rstd = rsqrtf(M2 / (float)nv + p.eps);
     const float nmr = -mean * rstd;
-    const int ncols = min(p.ld_out, (nv + 63) & ~63);  // the consumer reads ceil64(n_valid) columns: pad with zeros
-    const int pitch = ncols + 4;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int c = c0 + 32 * h;
@@ -199,8 +199,14 @@ struct EpiLnSiluT {
         v[4 * j + 2] = siluf_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
         v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
       }
-      tile_put<32>(tile, pitch, row, c, v);
+      emit(c, v);
     }
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int ncols = min(p.ld_out, (p.n_valid + 63) & ~63);  // the consumer reads ceil64(n_valid) columns: pad with zeros
+    const int pitch = ncols + 4;
+    normalise(p, g, sm, taddr, m, row, part, ncols, [&](int c, float (&v)[32]) { tile_put<32>(tile, pitch, row, c, v); });
     epi_bar_sync();
     tile_copy_out(tile, pitch, ncols, ncols, (int)blockIdx.x * BM, g.M, nullptr, 0,
                   p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out, p.ld_out, tid);

@@ -69,6 +69,7 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int chain2;      // 1: small grids run (LN layer -> output stage) pairs as one kernel, activations kept in shared memory (default 0)
   int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
   int small_a;     // 1: stages with <= 32 rows load 32-row A boxes (default 1)
   int lanes;       // rollouts: 0 / 1 one lane (default), 2 two half-batches on two internal streams
@@ -83,6 +84,7 @@ static Options& opts() {
     x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
     x.chain = getenv("DRM_CHAIN") != nullptr;
     x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
+    x.chain2 = getenv("DRM_CHAIN2") != nullptr;
     x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
@@ -646,6 +648,48 @@ static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMa
   return launch_gemm<EpiLnSiluT<HAS_ADD>>(g, p, dim3(mt, n_slots, 1), st, stage_id);
 }
 
+}  // namespace drm
+#include "chain2.cuh"
+namespace drm {
+
+template <class EpiB, bool HAS_ADD>
+static int launch_chain2(const Chain2Common& c, const typename EpiLnSiluT<HAS_ADD>::Params& pa, const typename EpiB::Params& pb, dim3 grid,
+                         cudaStream_t st, int stage_id) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(chain2_kernel<EpiB, HAS_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
+    attr_set = true;
+  }
+  profile_begin(stage_id, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = C2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA((cudaLaunchKernelEx(&cfg, chain2_kernel<EpiB, HAS_ADD>, c, pa, pb)));
+  profile_end(stage_id, st);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+// small grids only (every layer-B column tile recomputes layer A).  Opt-in: measured 1.051 vs 1.059 ms per 1024 x 15 rollout --
+// the serial LN -> shared memory -> second MMA phase inside the kernel costs what the removed launch boundary cost.
+static bool use_chain2(int ctas) { return opts().chain2 && ctas <= 148; }
+static void chain2_small_a(Chain2Common& c, const CUtensorMap* small) {
+  if (small && c.M <= SMALL_A_ROWS && opts().small_a) {
+    c.tmA = *small;
+    c.a_bytes = SMALL_A_ROWS * BK * 2;
+  }
+}
+
 // prior MLP on the view's h columns -> logits -> (optional) categorical sample
 static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, float* latent, long ld_latent, float* logits,
                        long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, RowMap rm, int M, cudaStream_t st) {
@@ -677,6 +721,21 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.n_slots = 1; g.y_slot[0] = 0;
     EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f, m->bnp1};
     RC(launch_ln<false>(g, m->tmWp1, m->tmWp1q, m->bnp1, p, mt, 1, st, DRM_STAGE_PRIOR_L1));
+  }
+  if (use_chain2(mt * (m->ZP / 128))) {
+    // prior L2 (LN) -> logits + sample in ONE kernel per (m-tile, 128-logit column tile): the hidden activations stay in shared memory
+    Chain2Common c;
+    memset(&c, 0, sizeof(c));
+    c.tmA = *v.tmY1; c.tmWA = m->tmWp2; c.tmWB = m->tmWp3h;
+    c.M = M; c.a_row0 = v.row0;
+    c.ka0 = 0; c.nka0 = ceil_div(m->d.h_prior[0], 64);
+    c.bnA = m->bnp2; c.nkB = ceil_div(m->d.h_prior[1], 64); c.bnB = 128; c.wb_tile_rows = 128;
+    chain2_small_a(c, v.tmY1_s);
+    EpiLnSilu::Params pa{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, nullptr, 256, 0, 0, m->d.h_prior[1], 1e-5f, m->bnp2};
+    EpiCat::Params pb{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
+                      ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
+                      (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
+    return launch_chain2<EpiCat, false>(c, pa, pb, dim3(mt, m->ZP / 128), st, DRM_STAGE_PRIOR_CAT);
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWp2, M, m->bnp2);
@@ -740,6 +799,25 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     small_a(g, v.tmS_s);
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
     RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
+  }
+  hp.bias = m->h3_b;
+  hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
+  hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
+  hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
+  hp.NB = m->d.NB; hp.A = m->d.A;
+  if (use_chain2(mt * n_slots)) {
+    // head L2 (LN) -> head outputs in ONE kernel per (m-tile, head)
+    Chain2Common c;
+    memset(&c, 0, sizeof(c));
+    c.tmA = *v.tmY1; c.tmWA = m->tmWh2; c.tmWB = m->tmWh3;
+    c.M = M; c.a_row0 = v.slot_rows + v.row0; c.a_y_stride = v.slot_rows;
+    c.ka0 = 0; c.nka0 = ceil_div(m->d.h_head[0], 64);
+    c.bnA = m->bnh2; c.wa_slot_rows = 256; c.nkB = ceil_div(m->d.h_head[1], 64); c.bnB = 256; c.wb_tile_rows = 256;
+    c.per_slot = 1; c.n_slots = n_slots;
+    for (int i = 0; i < n_slots; ++i) c.y_slot[i] = slots[i];
+    chain2_small_a(c, v.tmY1_s);
+    EpiLnSilu::Params pa{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, nullptr, 256, 0, 0, m->d.h_head[1], 1e-5f, m->bnh2};
+    return launch_chain2<EpiHeads, false>(c, pa, hp, dim3(mt, n_slots), st, DRM_STAGE_HEADS_OUT);
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWh2, M, m->bnh2);
@@ -965,6 +1043,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "ln_cluster") o.ln_cluster = value != 0;
   else if (n == "chain") o.chain = value != 0;
   else if (n == "small_a") o.small_a = value != 0;
+  else if (n == "chain2") o.chain2 = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
   else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }

@@ -73,7 +73,7 @@ def test_rollout_is_deterministic():
         assert torch.equal(x, y) and torch.equal(x, w)
 
 
-@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("small_a", 0), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32)])
+@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("small_a", 0), ("chain2", 1), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32)])
 def test_alternative_kernel_paths_give_identical_results(L, option, value):
     """Every switchable path reproduces the default path on a whole rollout: bit for bit for the one-hot expander, the TMA
     multicast clusters and both GRU tile widths (same per-element accumulation order); to fp32 rounding for the one-CTA LN
@@ -87,13 +87,13 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 200, 4, seed=6))
     base = ro.run(z0, h0, u, n)
     assert lib.drm_set_option(b"nonsense", 1) == -5
-    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, small_a=1, gru_pair=-1, gru_u=0)
+    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, small_a=1, chain2=0, gru_pair=-1, gru_u=0)
     try:
         L.check(lib.drm_set_option(option.encode(), value), "set_option")
         alt = ro.run(z0, h0, u, n)
     finally:
         lib.drm_set_option(option.encode(), defaults[option])
-    if option in ("ln_cluster", "chain"):
+    if option in ("ln_cluster", "chain", "chain2"):
         assert (base[7] != alt[7]).float().mean().item() < 0.01
         same = (base[7] == alt[7]).all(dim=-1).all(dim=-1)          # trajectories whose draws all agree
         for a, b in zip(base[1:7], alt[1:7]):
