@@ -35,14 +35,25 @@ __global__ void im2col_first_kernel(const float* __restrict__ obs, __nv_bfloat16
                                     int W, int tmB, int tmT) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long total = n_frames * Ho * Wo * 8;  // 8 vectors of 8 bf16 per row
+  const bool pow2 = !(Wo & (Wo - 1)) && !(Ho & (Ho - 1)) && (total >> 3) < (1l << 31);
+  const int s_wo = __ffs(Wo) - 1, s_ho = __ffs(Ho) - 1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int v = (int)(i & 7);
     const long row = i >> 3;
-    const int ox = (int)(row % Wo);
-    const int oy = (int)((row / Wo) % Ho);
-    const long n = row / ((long)Wo * Ho);
-    const long gn = f0 + n;
-    const long sn = tmB > 0 ? (gn % tmB) * tmT + gn / tmB : gn;
+    int ox, oy;
+    long n;
+    if (pow2) {                               // 32-bit shifts / masks instead of 64-bit div / mod (image sides are powers of two)
+      const unsigned r32 = (unsigned)row;
+      ox = (int)(r32 & (unsigned)(Wo - 1));
+      oy = (int)((r32 >> s_wo) & (unsigned)(Ho - 1));
+      n = r32 >> (s_wo + s_ho);
+    } else {
+      ox = (int)(row % Wo);
+      oy = (int)((row / Wo) % Ho);
+      n = row / ((long)Wo * Ho);
+    }
+    const unsigned gn = (unsigned)(f0 + n);
+    const long sn = tmB > 0 ? (long)(gn % (unsigned)tmB) * tmT + gn / (unsigned)tmB : (long)gn;
     const float* fr = obs + sn * 3 * H * W;
     float e[8];
 #pragma unroll
