@@ -458,7 +458,7 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
   const int NF = T * B;
   {
     const char* e = getenv("DRM_FC");
-    const int fc = e ? atoi(e) : 128;
+    const int fc = e ? atoi(e) : 512;   // frames per conv chunk: 512 measured best (4.37 -> 3.94 ms per 1024-frame forward vs 128); scratch ~0.5 GB
     o->FC = NF < fc ? NF : fc;
   }
   const int H = v->d.H, W = v->d.W;
