@@ -6,6 +6,10 @@ step eagerly -- real steps on real data, which also creates every workspace, cuD
 captures ONE call (the kernels of this package, the torch autograd tail, the flat-bucket all-reduce and the fused optimiser
 are all sync-free) and replays it for every later call with the same input shapes.  Inputs are copied into the captured
 static buffers; outputs are the captured static tensors (overwritten by the next call).
+
+Under torch.distributed the NCCL all-reduces are part of the capture (tests/dist_nccl_check.py, 2 GPUs): the capture runs in
+thread-local error mode because the NCCL watchdog thread polls CUDA events meanwhile, and the graphs must be dropped
+(``module.__dict__["_graphs"] = None``) before ``destroy_process_group()`` -- they hold NCCL work.
 """
 from __future__ import annotations
 
@@ -42,7 +46,8 @@ class StepGraph:
                 self.before_capture()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread-local capture mode: under torch.distributed the NCCL watchdog thread polls events while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self.body(*static)
             ent.update(graph=graph, static=static, out=out)
         with torch.no_grad():

@@ -4,7 +4,8 @@
 
 Each rank owns half of the sequences / start states.  Checks: (1) the sharded WorldModel loss equals the full-batch loss
 evaluated by the same rank with collectives disabled; (2) after one DP training step the parameters are bit-identical on
-all ranks and match a single-process full-batch step; (3) rollout shards concatenate to the full-batch rollout."""
+all ranks and match a single-process full-batch step; (3) rollout shards concatenate to the full-batch rollout; (4) the same
+training steps replayed as CUDA graphs (NCCL inside the capture) keep the ranks' parameters identical."""
 import os
 import sys
 
@@ -61,9 +62,33 @@ def main():
     la_f, lc_f = ag_full.train_step(full[0], full[1], full[3], full[4], full[2], full[5], full[6])
     D._FORCE_SINGLE = False
     assert abs(lc.item() - lc_f.item()) < 1e-4 * abs(lc_f.item()) and abs(la.item() - la_f.item()) < 1e-4 * max(1.0, abs(la_f.item()))
+    # (4) the data-parallel training steps as captured CUDA graphs (NCCL all-reduces inside the capture) and the actor gradient
+    # through the imagined states: replayed steps keep every rank's parameters identical
+    ag_dp.attach_world_model(wm_dp)
+    wm_dp.enable_cuda_graphs(warmup=1)
+    ag_dp.enable_cuda_graphs(warmup=1)
+    roll = (full[0], full[1], full[3], full[4], full[2], full[5], full[6])
+    for it in range(4):
+        wm_dp.training_step(sh(obs), sh(act), sh(rew), sh(cont), uniforms=sh(u, 1))
+        ag_dp.train_step(*(sh(t) for t in roll))
+    torch.cuda.synchronize()
+    assert wm_dp._graphs.captured(sh(obs), sh(act), sh(rew), sh(cont), sh(u, 1))
+    for mod in (wm_dp, ag_dp):
+        for k, a in mod.state_dict().items():
+            g = [torch.empty_like(a) for _ in range(world)]
+            dist.all_gather(g, a.contiguous())
+            assert all(torch.equal(g[0], x) for x in g), f"{k} differs across ranks after graph replays"
+            assert torch.isfinite(a.float()).all(), k
     if rank == 0:
         print(f"dist_nccl_check ok: world={world} wm loss dp={loss_dp.item():.6f} full={loss_full.item():.6f} max |dW|={worst:.2e} "
               f"critic loss dp={lc.item():.6f} full={lc_f.item():.6f}")
+    # captured graphs hold NCCL work: release them before tearing the communicator down
+    wm_dp.__dict__["_graphs"] = None
+    ag_dp.__dict__["_graphs"] = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 
