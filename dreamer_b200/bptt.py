@@ -50,18 +50,22 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
     p.grad.addmm_(a_t.t(), b)
 
 
-def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
+def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None, on_loss=None):
     # the batched conv graph has fixed shapes: let cuDNN pick its fastest (TF32 tensor-core) algorithms during the eager warm-up
     with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True), _matmul_precision():
-        return _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts, marks)
+        return _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts, marks, on_loss)
 
 
-def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None):
+def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None, on_loss=None):
     """Accumulate d(loss)/d(parameters) of WorldModel.training_step into ``.grad``; returns the (detached) loss value of the
     batched fp32 re-evaluation.
 
     obs (B,T,3,H,W) normalised, act (B,T,A), rew / cont (B,T,1), idx (B,T,R) classes the scan sampled, hidden (B,T,D) its h_t.
-    `parts` as in learners._tail_world_model (globally reduced denominators for data-parallel shares).
+    `parts` as in learners._tail_world_model (globally reduced denominators for data-parallel shares), or the string
+    "reduce": the per-rank sums of this batched re-evaluation are all-reduced here (dist.world_model_loss_from_sums) and the
+    GLOBAL loss is returned -- the training step then needs no separate loss forward (the decoder / heads are evaluated once,
+    in the graph that is differentiated).  `on_loss(total) -> bool` (optional) is called before any gradient work; returning
+    False aborts (the reference's NaN / Inf early return, WorldModel.py:191) and the function returns (total, False).
     `marks` (a list) receives (name, cuda event) pairs at the phase boundaries (profiles/wm_step_time.py)."""
 
     def mark(name):
@@ -135,6 +139,13 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
 
     dyn_sum = (cat_kl(LGl[:, 1:].detach(), prior[:, 1:]) * m1).sum()
     rep_sum = (cat_kl(LGl[:, 1:], prior[:, 1:].detach()) * m1).sum()
+    total = None
+    if isinstance(parts, str):
+        if parts != "reduce":
+            raise ValueError("world_model_backward: parts must be a dict, None or 'reduce'")
+        # forward values of this rank's sums -> one packed all-reduce -> global denominators and the global loss on every rank
+        local = torch.stack([obs_ll.sum(), rew_ll.sum(), cont_ll.sum(), mask.sum(), dyn_sum, torch.full((), float(m1.numel()), device=dev)]).detach()
+        total, parts = D.world_model_loss_from_sums(local, (wm.beta_pred, wm.beta_dyn, wm.beta_rep))
     if parts is None:
         denom, n_el = mask.sum() + 1e-5, float(m1.numel())
         loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
@@ -146,6 +157,8 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         live = (kl_mean > 1.0).to(loss_pred.dtype)
         const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
         loss = wm.beta_pred * loss_pred + live * (wm.beta_dyn * (dyn_sum / n_el) + wm.beta_rep * (rep_sum / n_el)) + const
+    if total is not None and on_loss is not None and not on_loss(total):
+        return total, False
     mark("batched heads / decoder forward")
     loss.backward()          # parameter gradients of prior / decoder / heads; d/dh, d/dz, d/dlogits at every step
 
@@ -191,7 +204,7 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
     mark("batched weight-gradient GEMMs")
     feats.backward(dfeat)    # encoder convs
     mark("encoder conv backward")
-    return loss.detach()
+    return (total, True) if total is not None else loss.detach()
 
 
 def _tanh_normal_log_prob(a, mu, sigma):

@@ -127,11 +127,42 @@ class WorldModel(nn.Module):
                 uniforms = torch.rand(self.horizon, continue_sequences.shape[0], self.latent_num_rows, device=continue_sequences.device)
             return graphs(L.f32c(observation_sequences), L.f32c(action_sequences), L.f32c(reward_sequences),
                           L.f32c(continue_sequences), uniforms).clone()
+        if self._fused_step_ok():
+            return self._scan_bptt_step(observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms, host_check=True)
         total, parts = self.loss_forward(observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms)
         if D.any_rank_flag(bool(torch.isnan(total) or torch.isinf(total)), total.device):
             print("World Model loss is nan or inf, skipping update.")
             return total
         return self._backward_and_step(total, parts, action_sequences, reward_sequences, continue_sequences)
+
+    def _fused_step_ok(self):
+        return (self.__dict__.get("grad_mode", "bptt") == "bptt" and self.latent_num_columns == 32 and isinstance(self.optimiser, FlatAdamW))
+
+    def _scan_bptt_step(self, observation_sequences, action_sequences, reward_sequences, continue_sequences, uniforms, host_check):
+        """The training step without evaluating anything twice: the posterior scan runs on the kernels (it fixes the trajectory:
+        hidden states and sampled classes), then bptt.world_model_backward evaluates decoder / heads / KL ONCE in the batched graph
+        it differentiates, reduces the loss sums over ranks itself and returns the global loss (WorldModel.py:156-202)."""
+        T = self.horizon
+        B = continue_sequences.shape[0]
+        obs = (L.f32c(observation_sequences)[:, :T] / 255.0) - 0.5
+        if uniforms is None:
+            uniforms = torch.rand(T, B, self.latent_num_rows, device=obs.device)
+        sc = self._engine.observe(B, T).scan(obs, action_sequences[:, :T], uniforms)
+        self.last = dict(scan=sc, uniforms=uniforms)
+        self.optimiser.zero_grad()
+        on_loss = None
+        if host_check:
+            def on_loss(total):
+                bad = D.any_rank_flag(bool(torch.isnan(total) or torch.isinf(total)), total.device)
+                if bad:
+                    print("World Model loss is nan or inf, skipping update.")
+                return not bad
+        total, done = bptt.world_model_backward(self, obs, L.f32c(action_sequences)[:, :T], L.f32c(reward_sequences)[:, :T],
+                                                L.f32c(continue_sequences)[:, :T], sc["idx"], sc["hidden"], parts="reduce", on_loss=on_loss)
+        if done:
+            self.optimiser.step(all_reduce=True)
+        self.last["tail_loss"] = total.detach()
+        return total
 
     def _backward_and_step(self, total, parts, action_sequences, reward_sequences, continue_sequences):
         T = self.horizon
@@ -161,6 +192,8 @@ class WorldModel(nn.Module):
     def _step_body(self, obs, act, rew, cont, uniforms):
         """One whole training step with no host synchronisation (capturable).  The reference's host-side NaN/Inf check
         (WorldModel.py:191) becomes the optimiser's device-side skip: a non-finite loss gives a non-finite gradient norm."""
+        if self._fused_step_ok():
+            return self._scan_bptt_step(obs, act, rew, cont, uniforms, host_check=False)
         total, parts = self.loss_forward(obs, act, rew, cont, uniforms)
         return self._backward_and_step(total, parts, act, rew, cont)
 
