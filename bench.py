@@ -268,6 +268,28 @@ def secondary_metrics(dev, peaks, flush):
                             env_steps_per_s=rates["graph"], us_per_step=1e6 / rates["graph"], eager_env_steps_per_s=rates["eager"],
                             note="wall clock over 300 steps including the host read-back every step (the environment needs the action)")
     del wm1, ag1, ring1
+    # one whole training iteration at the reference's own configuration (car_racer_config.yaml: batch 50 x sequence 50, horizon 30,
+    # WM_epochs = AC_epochs = 2): replay sample -> world-model step (x2), replay sample -> warm start -> imagination -> agent step (x2)
+    from dreamer_b200.hotpath import HotPath
+    cfg_it = dict(W.REF_CONFIG, buffer_size=8192)
+    hp_it = HotPath(cfg_it, dev)
+    rng_it = np.random.default_rng(1)
+    n_it = 4096
+    hp_it.buffer.add_batch(rng_it.integers(0, 256, size=(n_it, 3, 64, 64)).astype(np.uint8), rng_it.uniform(-1, 1, (n_it, 3)).astype(np.float32),
+                           rng_it.standard_normal(n_it).astype(np.float32), (rng_it.random(n_it) > 0.02).astype(np.float32))
+
+    def iteration():
+        hp_it.train_world_model()
+        hp_it.train_Agent()
+    t_e = dev_time(iteration, reps=3, warm=2)
+    hp_it.world_model.enable_cuda_graphs(warmup=1)
+    hp_it.agent.enable_cuda_graphs(warmup=1)
+    t_gi = dev_time(iteration, reps=5, warm=3)
+    out["training_iteration_ref"] = dict(workload="car_racer_config.yaml: batch 50 x seq 50, horizon 30, 2 world-model + 2 actor-critic epochs per iteration "
+                                                  "(Dreamer.py:228-287), synthetic replay", ms_per_iteration=t_gi * 1e3, iterations_per_s=1.0 / t_gi,
+                                         eager_ms_per_iteration=t_e * 1e3,
+                                         note="environment stepping excluded; training steps replayed as CUDA graphs (eager = launch by launch)")
+    del hp_it
     # the north star's large-batch points: 16 384 start states x horizon 15 on this one GPU (GRU stage vs the measured bf16 peak)
     import ctypes as C
     from dreamer_b200 import _lib as L
