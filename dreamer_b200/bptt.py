@@ -295,13 +295,7 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
                 cz = dgi @ Wih_z
                 da = dgi @ Wih_a
             # actor at state s: a_s = tanh(mu_s + sigma_s eps_s), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209)
-            dmu, dsg = gMU[s], gSG[s]
-            if da is not None:
-                du = da * (1.0 - Atm[s] * Atm[s])
-                dmu, dsg = dmu + du, dsg + du * EPS[s]
-            ls = LSs[s]
-            dls = dsg * torch.sigmoid(torch.clamp(ls, -5.0, 2.0)) * ((ls > -5.0) & (ls < 2.0))
-            torch.cat([dmu, dls], -1, out=dHEAD[s])
+            ops.actor_head_bwd(gMU[s], gSG[s], da, Atm[s], EPS[s], LSs[s], dHEAD[s])
             torch.mm(dHEAD[s], Whead, out=dY2s[s])
             dA2 = ops.ln_silu_bwd(dY2s[s], A2s[s], n2.weight, n2.bias, n2.eps)
             torch.mm(dA2, l2.weight, out=dY1s[s])

@@ -280,6 +280,35 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of the actor head a = tanh(mu + sigma eps), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209) for one
+// BPTT step:  given the direct gradients g_mu, g_sigma and da (NULL at the last step):
+//   du = da (1 - a^2);  dmu = g_mu + du;  dsigma = g_sigma + du eps;  dls = dsigma * sigmoid(ls) * [-5 < ls < 2]
+// writes d_head [rows, 2A] = [dmu | dls].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) actor_head_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ g_sg,
+                                                             const float* __restrict__ da, const float* __restrict__ a,
+                                                             const float* __restrict__ eps, const float* __restrict__ ls,
+                                                             float* __restrict__ d_head, int64_t rows, int A) {
+  const int64_t total = rows * A;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / A;
+    const int j = (int)(i - r * A);
+    float dmu = g_mu[i], dsg = g_sg[i];
+    if (da) {
+      const float av = a[i];
+      const float du = da[i] * (1.0f - av * av);
+      dmu += du;
+      dsg = fmaf(du, eps[i], dsg);
+    }
+    const float l = ls[i];
+    const float lc = fminf(fmaxf(l, -5.0f), 2.0f);
+    const float dls = (l > -5.0f && l < 2.0f) ? dsg / (1.0f + expf(-lc)) : 0.f;
+    d_head[r * 2 * A + j] = dmu;
+    d_head[r * 2 * A + A + j] = dls;
+  }
+}
+
 // KL(Cat(post) || Cat(prior)) summed over the rows of a group (one warp per group).
 // WorldModel.py:175-181.
 __global__ void __launch_bounds__(256) categorical32_kl_kernel(const float* __restrict__ post,
@@ -544,6 +573,18 @@ extern "C" int drm_gru_bwd(const float* dh, const float* gi, const float* gh, co
   const int64_t total = rows * D;
   const int64_t want = (total + 255) / 256;
   gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const float* da, const float* a, const float* eps,
+                                  const float* log_sigma, float* d_head, int64_t rows, int32_t A, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 0 && A >= 1, DRM_ERR_SHAPE, "drm_actor_head_bwd: bad shape");
+  if (rows == 0) return DRM_OK;
+  DRM_REQUIRE(g_mu && g_sigma && log_sigma && d_head && (!da || (a && eps)), DRM_ERR_ARG, "drm_actor_head_bwd: NULL pointer");
+  const int64_t want = (rows * A + 255) / 256;
+  actor_head_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(g_mu, g_sigma, da, a, eps, log_sigma, d_head, rows, A);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -552,3 +552,16 @@ class Observe:
                 self.handle = C.c_void_p()
         except Exception:
             pass
+
+
+def actor_head_bwd(g_mu, g_sigma, da, a, eps, log_sigma, out):
+    """d_head (rows, 2A) = [dmu | dls] of one BPTT step through the actor head (drm_actor_head_bwd); da may be None."""
+    rows, A = g_mu.shape
+    for t in (g_mu, g_sigma, da, a, eps, log_sigma, out):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError("dreamer_b200.actor_head_bwd: fp32 contiguous CUDA tensors are required")
+    if out.shape != (rows, 2 * A):
+        raise RuntimeError("dreamer_b200.actor_head_bwd: out must be (rows, 2A)")
+    L.check(L.load().drm_actor_head_bwd(L.ptr(g_mu), L.ptr(g_sigma), L.ptr(da), L.ptr(a), L.ptr(eps), L.ptr(log_sigma), L.ptr(out), rows, A,
+                                        L.stream()), "actor_head_bwd")
+    return out

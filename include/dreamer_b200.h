@@ -113,6 +113,10 @@ int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const f
 /* gh = h W_hh^T + b_hh [rows, 3D] (gate order r, u, n), h_prev [rows, D] (NULL = zeros) and dh [rows, D]:                    */
 /*   dgi = [dr, du, dn], dgh = [dr, du, dn * r] (pre-activation gradients), dh_prev (=, or += when accumulate) dh * u.        */
 /* The caller completes dh_prev += dgh W_hh and dx = dgi W_ih with library GEMMs.                                             */
+/* Backward of the actor head a = tanh(mu + sigma eps), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209) for one BPTT */
+/* step: d_head [rows, 2A] = [g_mu + du | (g_sigma + du eps) sigmoid(ls) 1(-5 < ls < 2)], du = da (1 - a^2); da may be NULL (= 0).   */
+int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const float* da, const float* a, const float* eps,
+                       const float* log_sigma, float* d_head, int64_t rows, int32_t A, void* stream);
 int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
                 float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
 /* KL balance terms of WorldModel.training_step  WorldModel.py:175-181:                         */
