@@ -125,3 +125,29 @@ def test_two_lane_rollout_is_bit_identical_to_one_lane(L):
         for a, b, c in zip(one, two, auto):
             assert torch.equal(a, b) and torch.equal(a, c), B
     assert lib.drm_set_option(b"lanes", 3) == -5
+
+
+@pytest.mark.parametrize("B", [2179, 4100])
+def test_cta_pair_gru_band_order_on_ragged_grids(L, B):
+    """The CTA-pair GRU kernel walks tiles in bands of 16 m-tiles; grids whose m-tile count is odd / not a multiple of the band
+    (17 + 1 padding tile, 33 tiles) exercise the tail mapping and the all-padding peer CTA.  Results must equal the single-CTA
+    kernel's bit for bit, for both tile widths."""
+    from dreamer_b200 import ops
+    lib = L.load()
+    cfg = W.small_config()
+    sd = {k: v.to(DEV) for k, v in W.make_state_dict(cfg, seed=9).items()}
+    model = ops.PackedRssm.from_state_dict(sd)
+    ro = ops.Rollout(model, B, 2)
+    z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, 2, seed=B))
+    try:
+        L.check(lib.drm_set_option(b"gru_pair", 0), "set_option")
+        base = ro.run(z0, h0, u, n)
+        for width in (32, 64):
+            L.check(lib.drm_set_option(b"gru_u", width), "set_option")
+            L.check(lib.drm_set_option(b"gru_pair", 1), "set_option")
+            alt = ro.run(z0, h0, u, n)
+            for a, b in zip(base, alt):
+                assert torch.equal(a, b), (B, width)
+    finally:
+        lib.drm_set_option(b"gru_pair", -1)
+        lib.drm_set_option(b"gru_u", 0)
