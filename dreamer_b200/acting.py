@@ -47,9 +47,11 @@ class ActingPath:
         if use_graphs:
             self._reset = StepGraph(self._reset_body, warmup)
             self._observe_act = StepGraph(self._observe_act_body, warmup)
+            self._observe = StepGraph(self._observe_body, warmup)
             self._act = StepGraph(self._act_body, warmup)
         else:
-            self._reset, self._observe_act, self._act = self._reset_body, self._observe_act_body, self._act_body
+            self._reset, self._observe_act, self._observe, self._act = (self._reset_body, self._observe_act_body, self._observe_body,
+                                                                        self._act_body)
 
     # ---- captured bodies: device tensors in, device tensors updated in place, no host synchronisation ----------------------
     def _obs(self):
@@ -66,10 +68,14 @@ class ActingPath:
         self.action.copy_(a.view_as(self.action))
         return self.action
 
-    def _observe_act_body(self, uniforms=None, normals=None):
+    def _observe_body(self, uniforms=None):
         z, h, _ = self.wm.observe_step(self.latent, self.hidden, self.action, self._obs(), uniforms)
         self.hidden.copy_(h.view_as(self.hidden))
         self.latent.copy_(z.view_as(self.latent))
+        return self.latent
+
+    def _observe_act_body(self, uniforms=None, normals=None):
+        self._observe_body(uniforms)
         return self._act_body(normals)
 
     # ---- host API -----------------------------------------------------------------------------------------------------
@@ -100,6 +106,16 @@ class ActingPath:
         """Agent.py:202-210 on the current state; returns the action as a host array."""
         self._act(normals)
         return self._download_action()
+
+    def set_action(self, action):
+        """Use an externally chosen action (Dreamer.rollout_policy's random_policy branch, Dreamer.py:195-198) as the last action."""
+        self._action_host.copy_(torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1)))
+        self.action.view(-1).copy_(self._action_host, non_blocking=True)
+
+    def observe(self, next_frame_u8_chw, uniforms: Optional[torch.Tensor] = None):
+        """observe_step on the new frame with the last action, without choosing the next one (WorldModel.py:79-82)."""
+        self._upload(next_frame_u8_chw)
+        self._observe(uniforms)
 
     def record(self, reward: float, continue_: float):
         """buffer.add_to_buffer(current frame, last action, reward, continue) without leaving the device (Dreamer.py:211-212)."""

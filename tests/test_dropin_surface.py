@@ -34,6 +34,19 @@ def test_reference_dreamer_builds_on_dropin_modules_and_state_dict_interchanges(
         for name in ("actor", "critic", "target_critic", "S", "train_step", "compute_batched_R_lambda_returns", "update_S", "soft_update_target"):
             assert hasattr(d.agent, name), name
         assert d.buffer.capacity == cfg["buffer_size"] and d.buffer.size == 0 and d.buffer.next_idx == 0
+        # patch_dreamer swaps the four hot call sites without changing their signatures
+        import inspect
+        names = ("dream_episodes", "warm_start_generator", "rollout_policy", "evaluate_agent")
+        sigs = {n: list(inspect.signature(getattr(D.Dreamer, n)).parameters) for n in names}
+        originals = {n: getattr(D.Dreamer, n) for n in names}
+        try:
+            dropin.patch_dreamer(D.Dreamer)
+            for n in names:
+                assert getattr(D.Dreamer, n) is not originals[n]
+                assert list(inspect.signature(getattr(D.Dreamer, n)).parameters) == sigs[n], n
+        finally:
+            for n in names:
+                setattr(D.Dreamer, n, originals[n])
         # no CPU path: a data call on CPU tensors must raise, not silently compute
         with pytest.raises(RuntimeError):
             d.world_model.sequence_model(torch.zeros(2, 1, 32, 32), torch.zeros(2, 1, cfg["hidden_state_dims"]), torch.zeros(2, 1, 3))

@@ -76,3 +76,86 @@ def test_acting_path_sees_weight_updates_and_draws_on_device():
     sto.reset(frame, u)
     draws = np.stack([sto.act() for _ in range(6)])
     assert len({tuple(np.round(d, 6)) for d in draws}) > 3
+
+
+class _FakeEnv:
+    """A gymnasium-shaped environment with HWC uint8 frames, fixed episode length and a counter-derived reward."""
+
+    class _Space:
+        def __init__(self, rng):
+            self.rng = rng
+
+        def sample(self):
+            return self.rng.uniform(-1, 1, 3).astype(np.float32)
+
+    def __init__(self, episode_len, seed=0):
+        self.rng = np.random.default_rng(seed)
+        self.action_space = self._Space(self.rng)
+        self.episode_len, self.t, self.frames, self.actions = episode_len, 0, [], []
+
+    def _frame(self):
+        f = self.rng.integers(0, 256, size=(64, 64, 3)).astype(np.uint8)
+        self.frames.append(f)
+        return f
+
+    def reset(self, seed=None):
+        self.t = 0
+        return self._frame(), {}
+
+    def step(self, action):
+        self.actions.append(np.asarray(action, dtype=np.float32).copy())
+        self.t += 1
+        done = self.t >= self.episode_len
+        return self._frame(), 0.5 * self.t, done, False, {}
+
+
+class _DreamerShell:
+    """The attributes of the reference's Dreamer that rollout_policy / evaluate_agent / warm_start_generator touch
+    (Dreamer.py:119-139); the methods themselves come from dropin.patch_dreamer."""
+
+    def __init__(self, cfg):
+        from dreamer_b200.modules import Buffer
+        self.world_model, self.agent = W.build_learners(cfg, W.make_state_dict(cfg, seed=41), DEV)
+        self.buffer = Buffer(256, cfg["sequence_length"], cfg["action_dims"], tuple(cfg["observation_dims"]), device=DEV)
+        self.sequence_length, self.horizon, self.seed, self.agent_obs = cfg["sequence_length"], cfg["horizon"], 7, None
+
+
+def test_patched_rollout_policy_and_evaluate_agent_follow_the_reference_loop():
+    """dropin.patch_dreamer's rollout_policy / evaluate_agent (Dreamer.py:177-226, 295-322 on acting.ActingPath): every
+    transition (obs_t, a_t, r_t, c_t) the environment saw lands in the ring in order, episodes restart on done, the random
+    policy's actions are the environment's samples, and evaluation returns the mean episode return without touching the ring."""
+    from dreamer_b200 import dropin
+    cfg = W.small_config(sequence_length=6, horizon=4)
+    Shell = dropin.patch_dreamer(type("Shell", (_DreamerShell,), {}))
+    d = Shell(cfg)
+    env = _FakeEnv(episode_len=4)
+    d.rollout_policy(env, random_policy=True)
+    d.rollout_policy(env, random_policy=False)
+    n = 2 * cfg["sequence_length"]
+    assert d.buffer.size == n and len(env.actions) == n
+    # frames: env.frames holds reset frames and step frames in order; the transition stored at step i is the frame the action was chosen on
+    stored = d.buffer.observation_buffer[:n].cpu().numpy()
+    seen, k = [], 0
+    cur = env.frames[0]
+    idx = 1
+    for i in range(n):
+        seen.append(cur.transpose(2, 0, 1))
+        nxt = env.frames[idx]; idx += 1
+        if (i + 1) % 4 == 0:            # episode ended: the next stored frame is the reset frame that follows
+            cur = env.frames[idx]; idx += 1
+        else:
+            cur = nxt
+    assert np.array_equal(stored, np.stack(seen))
+    assert np.allclose(d.buffer.action_buffer[:n].cpu().numpy(), np.stack(env.actions), atol=1e-6)
+    cont = d.buffer.continue_buffer[:n].cpu().numpy().reshape(-1)
+    assert np.array_equal(cont, np.array([0.0 if (i + 1) % 4 == 0 else 1.0 for i in range(n)], dtype=np.float32))
+    assert np.all(np.abs(np.stack(env.actions[cfg["sequence_length"]:])) <= 1.0) and d.seed == 7 + n // 4
+    before = d.buffer.size
+    mean_ret = d.evaluate_agent(_FakeEnv(episode_len=3, seed=1), eval_episodes=2)
+    assert d.buffer.size == before and abs(float(mean_ret) - 0.5 * (1 + 2 + 3)) < 1e-6
+    # warm start + imagination through the patched methods keep the reference's shapes
+    np.random.seed(0)
+    obs, act, _, _, L = d.buffer.sample_sequences(3)
+    z0, h0 = d.warm_start_generator(obs, act, L)
+    out = d.dream_episodes(z0, h0)
+    assert z0.shape == (3, 1, 32, 32) and out[0].shape == (3, cfg["horizon"] + 1, 32, 32) and out[2].shape == (3, cfg["horizon"], 3)
