@@ -11,6 +11,7 @@ does (Dreamer.py:71-125) and re-implements only the four methods on the hot path
 plus the two file formats either side of it:
 
     save_trained_Dreamer / load_pretrained_dreamer   Dreamer.py:289-293   the reference's ``.pth``: state_dict with its 97 keys
+    save_training_logs                               Dreamer.py:356-364   the reference's ``training_logs.npz`` (same four keys)
     save_training_state / load_training_state        (the reference saves none of this)  optimisers, return scale S, RNG, ring
 
 and ``acting()`` -- the B = 1 acting path of Dreamer.rollout_policy / evaluate_agent (acting.ActingPath, 8f rank 3).
@@ -106,6 +107,14 @@ class HotPath:
 
     def load_pretrained_dreamer(self, path):                         # Dreamer.py:289-290
         self.load_state_dict(torch.load(path, weights_only=True, map_location=self.device))
+
+    @staticmethod
+    def save_training_logs(path, world_model_loss, actor_loss, critic_loss, rewards):
+        """The reference's ``training_logs.npz`` (Dreamer.py:356-364): the same four keys, tensors reduced to floats."""
+        import numpy as np
+        from .dropin import _sanitize_for_save
+        np.savez(path, world_model_loss=_sanitize_for_save(world_model_loss), actor_loss=_sanitize_for_save(actor_loss),
+                 critic_loss=_sanitize_for_save(critic_loss), rewards=_sanitize_for_save(rewards))
 
     def save_training_state(self, path, include_buffer: bool = False):
         """Everything a bit-exact resume needs and the reference omits: optimiser moments and step counts, the return scale S,

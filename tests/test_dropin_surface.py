@@ -110,3 +110,13 @@ def test_hotpath_checkpoint_is_the_reference_pth_format(tmp_path):
         for k in ("Dreamer", "WorldModel", "Agent", "Buffer", "SequenceModel", "DynamicsPredictors", "VariationalAutoEncoder", "DreamerUtils"):
             sys.modules.pop(k, None)
         sys.modules.update(saved)
+
+
+def test_training_logs_npz_has_the_reference_keys(tmp_path):
+    import numpy as np
+    from dreamer_b200.hotpath import HotPath
+    path = str(tmp_path / "training_logs.npz")
+    HotPath.save_training_logs(path, [[torch.tensor(1.5), torch.tensor(2.5)], [torch.tensor(2.0), 3.0]], [torch.tensor(0.1)], [0.2, torch.tensor(0.3)], [10.0])
+    z = np.load(path, allow_pickle=True)
+    assert sorted(z.files) == ["actor_loss", "critic_loss", "rewards", "world_model_loss"]       # Dreamer.py:358-363
+    assert float(z["actor_loss"][0]) == pytest.approx(0.1) and float(z["rewards"][0]) == 10.0 and z["world_model_loss"].shape == (2, 2)
