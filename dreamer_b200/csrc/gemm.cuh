@@ -314,22 +314,30 @@ __device__ __forceinline__ long map_row(const RowMap& rm, int m) {
 
 // rows [0, 128) x cols [0, ncols) of `tile` -> out_f32[row(m0 + r) * ld_f + c] and / or out_bf[row(m0 + r) * ld_b + c]
 // for m0 + r < M and c < nvalid (ncols % 4 == 0; full float4 groups take the vector path).
-// Warp w streams rows w, w + 16, ...; its lanes walk the row 16 bytes apiece (no integer division).
+// Warp w streams rows in passes of 32 / lpr rows; its lanes walk a row 16 bytes apiece.
 __device__ __forceinline__ void tile_copy_out(const float* tile, int pitch, int ncols, int nvalid, int m0, int M, float* out_f32,
                                               long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid, RowMap rm = RowMap{0, 0, 0, 0}) {
   const bool al_f = out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0) && ((ld_f & 3) == 0);
   const bool al_b = out_bf && ((reinterpret_cast<uintptr_t>(out_bf) & 7u) == 0) && ((ld_b & 3) == 0);
-  const int lane4 = (tid & 31) << 2;
   const int rows = min(BM, M - m0);
-  for (int r = tid >> 5; r < rows; r += EPI_THREADS / 32) {
+  if (rm.mode == 3) {     // NCHW fp32: column c is a whole plane apart (3 output channels); one row per warp pass
+    const int plane = 4 * rm.p0 * rm.p1;
+    for (int r = tid >> 5; r < rows; r += EPI_THREADS / 32) {
+      const long orow = map_row(rm, m0 + r);
+      if ((tid & 31) < nvalid) out_f32[orow + (long)(tid & 31) * plane] = tile[r * pitch + (tid & 31)];
+    }
+    return;
+  }
+  // Narrow tiles (<= 64 columns) would leave most lanes idle at one row per warp pass and make every lane redo the row
+  // mapping (three integer divisions for the transposed-conv scatter) for each of its warp's rows: pack 32 / lpr rows into a pass.
+  const int lpr = ncols >= 128 ? 32 : (ncols >= 64 ? 16 : (ncols >= 32 ? 8 : 4));   // lanes per row, 4 columns per lane
+  const int rpp = 32 / lpr;                                                        // rows per warp pass
+  const int lane = tid & 31;
+  const int sub = lane / lpr, lane4 = (lane - sub * lpr) << 2;
+  for (int r = (tid >> 5) * rpp + sub; r < rows; r += (EPI_THREADS / 32) * rpp) {
     const float* trow = tile + r * pitch;
     const long orow = map_row(rm, m0 + r);
-    if (rm.mode == 3) {   // NCHW fp32: column c is a whole plane apart (3 output channels)
-      const int plane = 4 * rm.p0 * rm.p1;
-      if ((tid & 31) < nvalid) out_f32[orow + (long)(tid & 31) * plane] = trow[tid & 31];
-      continue;
-    }
-    for (int c = lane4; c < nvalid; c += 128) {
+    for (int c = lane4; c < nvalid; c += lpr * 4) {
       const float4 x = *reinterpret_cast<const float4*>(trow + c);
       const bool full = c + 4 <= nvalid;
       if (out_f32) {

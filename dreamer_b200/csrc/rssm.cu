@@ -1070,4 +1070,44 @@ extern "C" int drm_debug_timeline(int32_t on, unsigned long long* out_host) {
   return DRM_OK;
 }
 
+#include "conv_persist.cuh"
+namespace drm {
+// narrow conv layers (<= 64 output channels): one persistent CTA per SM walks the tiles (conv_persist.cuh)
+static int launch_conv_persist(const GemmCommon& g, const EpiPlain::Params& p, int phases, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM));
+    attr_set = true;
+  }
+  ConvPersist c;
+  memset(&c, 0, sizeof(c));
+  c.tmA = g.tmA; c.tmB = g.tmB;
+  c.M = g.M; c.n_mtiles = ceil_div(g.M, BM); c.phases = phases; c.a_phase_rows = g.a_y_stride;
+  c.bn = g.bn; c.nk = g.nka0;
+  c.bias = p.bias; c.out = p.out_bf16; c.ld = p.ld_bf16; c.n_valid = p.N; c.act = p.act; c.rm = p.rm;
+  const int n_tiles = c.n_mtiles * phases;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_tiles < 148 ? n_tiles : 148);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = CP_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, conv_persist_kernel, c));
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+static bool use_conv_persist(const GemmCommon& g, const EpiPlain::Params& p) {
+  static const bool off = getenv("DRM_NO_CONV_PERSIST") != nullptr;
+  return !off && (g.bn == 32 || g.bn == 64) && p.out_bf16 && !p.out_f32 && g.nka1 == 0 && g.ka0 == 0 && g.a_row0 == 0;
+}
+}  // namespace drm
+
 #include "vae.cuh"

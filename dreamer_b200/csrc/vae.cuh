@@ -536,7 +536,8 @@ static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, 
     g.n_slots = 1; g.y_slot[0] = 0;
     __nv_bfloat16* dst = i == 3 ? o->feat + (long)f0 * v->Kf : cur;
     EpiPlain::Params p{v->be[i], nullptr, dst, 0, (long)v->ebn[i + 1], v->ebn[i + 1], 1, 0, RowMap{0, 0, 0, 0}};
-    if (v->ebn[i + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
+    if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 1, st));
+    else if (v->ebn[i + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div(M, BM), 1), st));
     if (i == 3) break;
     Taps4 tp;
@@ -585,7 +586,8 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
     g.ka0 = 0; g.nka0 = v->DK[j] / 64;
     EpiPlain::Params p{v->bdc[j], nullptr, dst, 0, (long)v->dbn[j + 1], v->dbn[j + 1], 1, 1, RowMap{2, hs, ws, 0}};
     if (j == 3) { p.out_f32 = mu_out; p.out_bf16 = nullptr; p.ld_f32 = 0; p.N = 3; p.act = 2; p.rm = RowMap{3, hs, ws, 0}; }
-    if (v->dbn[j + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
+    if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 4, st));
+    else if (v->dbn[j + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     hs <<= 1; ws <<= 1;
     src = dst;
