@@ -16,6 +16,13 @@
 
 namespace drm {
 
+// debug switches read once per process (A/B runs of the conv-path variants)
+static bool env_off(const char* name, int slot) {
+  static int cache[2] = {-1, -1};
+  if (cache[slot] < 0) cache[slot] = getenv(name) != nullptr;
+  return cache[slot] != 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -537,7 +544,7 @@ static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, 
     __nv_bfloat16* dst = i == 3 ? o->feat + (long)f0 * v->Kf : cur;
     EpiPlain::Params p{v->be[i], nullptr, dst, 0, (long)v->ebn[i + 1], v->ebn[i + 1], 1, 0, RowMap{0, 0, 0, 0}};
     if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 1, st));
-    else if (v->ebn[i + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
+    else if (v->ebn[i + 1] <= 64 && !env_off("DRM_NO_PLAIN_S", 0)) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div(M, BM), 1), st));
     if (i == 3) break;
     Taps4 tp;
@@ -569,7 +576,7 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
       for (int ty = 0; ty < 2; ++ty)
         for (int tx = 0; tx < 2; ++tx) { tp.t[ph].dy[ty * 2 + tx] = ct_d(ph >> 1, ty); tp.t[ph].dx[ty * 2 + tx] = ct_d(ph & 1, tx); }
     }
-    if (j == 3 && (v->dbn[3] == 32 || v->dbn[3] == 16 || v->dbn[3] == 8 || v->dbn[3] == 64) && !getenv("DRM_NO_DIRECT_CONVT")) {
+    if (j == 3 && (v->dbn[3] == 32 || v->dbn[3] == 16 || v->dbn[3] == 8 || v->dbn[3] == 64) && !env_off("DRM_NO_DIRECT_CONVT", 1)) {
       // image layer: direct kernel, no patch matrix (see convt_last_direct_kernel)
       const int grid = grid_for(rows);
 #define DRM_CT_LAST(CPV) convt_last_direct_kernel<CPV><<<grid, 256, 0, st>>>(src, v->Wdc[3], v->bdc[3], mu_out, rows, hs, ws, v->dbn[4], 3, v->DK[3])
@@ -587,7 +594,7 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
     EpiPlain::Params p{v->bdc[j], nullptr, dst, 0, (long)v->dbn[j + 1], v->dbn[j + 1], 1, 1, RowMap{2, hs, ws, 0}};
     if (j == 3) { p.out_f32 = mu_out; p.out_bf16 = nullptr; p.ld_f32 = 0; p.N = 3; p.act = 2; p.rm = RowMap{3, hs, ws, 0}; }
     if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 4, st));
-    else if (v->dbn[j + 1] <= 64 && !getenv("DRM_NO_PLAIN_S")) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
+    else if (v->dbn[j + 1] <= 64 && !env_off("DRM_NO_PLAIN_S", 0)) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     hs <<= 1; ws <<= 1;
     src = dst;
