@@ -69,6 +69,7 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int conv_persist;  // 1: narrow conv layers on the persistent GEMM (default 1)
   int chain2;      // 1: small grids run (LN layer -> output stage) pairs as one kernel, activations kept in shared memory (default 0)
   int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
   int small_a;     // 1: stages with <= 32 rows load 32-row A boxes (default 1)
@@ -85,6 +86,7 @@ static Options& opts() {
     x.chain = getenv("DRM_CHAIN") != nullptr;
     x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
     x.chain2 = getenv("DRM_CHAIN2") != nullptr;
+    x.conv_persist = getenv("DRM_NO_CONV_PERSIST") == nullptr;
     x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
@@ -1044,6 +1046,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "chain") o.chain = value != 0;
   else if (n == "small_a") o.small_a = value != 0;
   else if (n == "chain2") o.chain2 = value != 0;
+  else if (n == "conv_persist") o.conv_persist = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
   else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
@@ -1105,8 +1108,7 @@ static int launch_conv_persist(const GemmCommon& g, const EpiPlain::Params& p, i
   return DRM_OK;
 }
 static bool use_conv_persist(const GemmCommon& g, const EpiPlain::Params& p) {
-  static const bool off = getenv("DRM_NO_CONV_PERSIST") != nullptr;
-  return !off && (g.bn == 32 || g.bn == 64) && p.out_bf16 && !p.out_f32 && g.nka1 == 0 && g.ka0 == 0 && g.a_row0 == 0;
+  return opts().conv_persist && (g.bn == 32 || g.bn == 64) && p.out_bf16 && !p.out_f32 && g.nka1 == 0 && g.ka0 == 0 && g.a_row0 == 0;
 }
 }  // namespace drm
 

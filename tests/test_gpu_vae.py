@@ -134,3 +134,27 @@ def test_observe_c3_shapes_and_teacher_forced(ops):
     dec = O.decoder_forward(sd, sc["hidden"][:, t], sc["latent"][:, t], (64, 64))
     _close(hd["dec_mu"][:, t], dec, what="decoder mu")
     _close(hd["prior_logits"][:, t], O.prior_logits(sd, sc["hidden"][:, t]), atol=3e-2, what="prior logits")
+
+
+def test_persistent_conv_gemm_is_bit_identical_to_one_tile_per_cta(ops):
+    """Option "conv_persist": the narrow conv layers on the persistent double-buffered GEMM versus one tile per CTA -- same
+    operands, same k order, same epilogue arithmetic, so encoder logits and decoder images must not change by a bit
+    (ragged frame counts: partial last tile, more tiles than CTAs)."""
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    for name, N in (("small", 37), ("ref", 300)):
+        cfg = CFGS[name]
+        _, _, vae = _build(ops, cfg, 13)
+        ws = ops.Observe(vae, N, 1)
+        g = torch.Generator(device="cuda").manual_seed(N)
+        h = torch.tanh(torch.randn(N, cfg["hidden_state_dims"], device=DEV, generator=g))
+        obs = torch.rand(N, 3, 64, 64, device=DEV, generator=g) - 0.5
+        z = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device=DEV, generator=g), 32).float().reshape(N, 1024)
+        outs = []
+        try:
+            for flag in (1, 0):
+                L.check(lib.drm_set_option(b"conv_persist", flag), "set_option")
+                outs.append((ws.encode(h, obs)["logits"].clone(), ws.decode(h, z).clone()))
+        finally:
+            lib.drm_set_option(b"conv_persist", 1)
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), name
