@@ -26,12 +26,17 @@ from . import rollout
 
 
 class HotPath:
-    def __init__(self, config: dict, device):
+    def __init__(self, config: dict, device, cuda_graphs: bool = False):
+        """`cuda_graphs=True` replays WorldModel.training_step and Agent.train_step as CUDA graphs after three eager steps per
+        input shape (learners.enable_cuda_graphs; needs a CUDA device)."""
         self.cfg = dict(config)
         self.device = torch.device(device)
         from .modules import Buffer
         self.world_model, self.agent = _build(self.cfg, self.device)
         self.agent.attach_world_model(self.world_model)      # actor gradient through the imagined states (bptt.actor_backward)
+        if cuda_graphs:
+            self.world_model.enable_cuda_graphs()
+            self.agent.enable_cuda_graphs()
         self.buffer = Buffer(config["buffer_size"], config["sequence_length"], config["action_dims"], tuple(config["observation_dims"]),
                              device=self.device)
         self.horizon = config["horizon"]
