@@ -153,3 +153,34 @@ def test_rollout_shards_concatenate(ops):
              for s in (slice(0, B // 2), slice(B // 2, B))]
     for i in range(8):
         assert torch.equal(torch.cat([p[i] for p in parts]), full[i]), i
+
+
+def test_rollout_c4_sizes_teacher_forced(ops):
+    """BASELINE config 4 sizes (GRU deter 4096): every step of a 300-row rollout re-derived by the oracle from the kernel's own
+    previous state.  300 rows = 3 m-tiles with 64-unit tiles -> exercises the wide-tile weight packing at K = 5184 and, forced on,
+    the CTA-pair (cta_group::2) GRU kernel with a padding peer tile."""
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    cfg = dict(W.REF_CONFIG, horizon=3, hidden_state_dims=4096)
+    B, H = 300, 3
+    sd, model = _model(ops, cfg, 2)
+    z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=99)
+    ro = ops.Rollout(model, B, H)
+    outs = {}
+    try:
+        for pair in (0, 1):
+            L.check(lib.drm_set_option(b"gru_pair", pair), "set_option")
+            outs[pair] = [t.cpu() for t in ro.run(z0.to(DEV), h0.to(DEV), u.to(DEV), n.to(DEV))]
+    finally:
+        lib.drm_set_option(b"gru_pair", -1)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)                                              # same k order per element: bit-identical
+    lat, hid, act, rew, con, mu, sg, idx = outs[1]
+    mismatch = 0
+    for t in range(H):
+        a, m_, s_ = O.actor_act(sd, hid[:, t], lat[:, t], n[t])
+        _close(act[:, t], a, what=f"action t={t}"); _close(mu[:, t], m_, what="mu"); _close(sg[:, t], s_, what="sigma")
+        h2, z2, r, c, _, i2, _ = O.imagine_step(sd, hid[:, t], lat[:, t], act[:, t], u[t])
+        _close(hid[:, t + 1], h2, what=f"hidden t={t}")
+        mismatch += (i2 != idx[:, t].long()).sum().item()
+    assert mismatch <= 0.005 * B * H * 32                                      # draws on bf16-vs-fp32 logits: a few bin-edge flips at most
