@@ -225,7 +225,7 @@ using EpiLnSiluAdd = EpiLnSiluT<true>;
 // ------------------------------------------------------------------------------------------
 template <bool HAS_ADD>
 struct EpiLnSiluN4T {
-  static constexpr int B_ROWS_MAX = 64, STAGES = 8, TMEM_COLS = 64, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 4;   // 8 x 24 KB in flight: the main loop is latency-bound
+  static constexpr int B_ROWS_MAX = 64, STAGES = 2, KPS = 4, TMEM_COLS = 64, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 4;   // 2 stages x 4 k-blocks x 24 KB in flight; one full / empty handshake per 4 k-blocks
   using Params = typename EpiLnSiluT<HAS_ADD>::Params;
   static constexpr int XST = 2560;   // float offset of the cross-CTA statistics [4 ranks][128 rows][2]
   static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {

@@ -11,6 +11,7 @@
 // split the tile's columns four ways (`part`), exchanging partial row statistics through smem.
 // Pipeline: STAGES-deep smem ring (full/empty mbarriers), one tmem_full barrier.
 #pragma once
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -72,10 +73,17 @@ __device__ __forceinline__ void probe(const GemmCommon& g, int i) {
   }
 }
 
-template <int B_ROWS_MAX, int STAGES>
+// k-blocks per pipeline stage: Epi::KPS when the epilogue declares it, else 1
+template <class E, class = void>
+struct kps_of { static constexpr int value = 1; };
+template <class E>
+struct kps_of<E, std::void_t<decltype(E::KPS)>> { static constexpr int value = E::KPS; };
+
+template <int B_ROWS_MAX, int STAGES, int KPS = 1>
 struct GemmSmem {
   static constexpr int B_STAGE_BYTES = B_ROWS_MAX * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SUB_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;    // one k-block: [A 16 KB | B]
+  static constexpr int STAGE_BYTES = KPS * SUB_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 256;        // 1024 floats of per-tile constants + 3072 of row-stat exchange
   static constexpr int ZI_OFF = EPI_OFF + 16384;       // 128 rows x 32 sampled indices of this tile's rows
@@ -104,7 +112,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;\n
 template <class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, Epi::MIN_CTAS)
 fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename Epi::Params ep) {
-  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
+  constexpr int KPS = kps_of<Epi>::value;
+  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES, KPS>;
   constexpr int STAGES = Epi::STAGES;
   constexpr int CM = Epi::CLUSTER_M;
   constexpr int CN = Epi::CLUSTER_N;
@@ -152,6 +161,25 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
       const uint32_t tx_b = (uint32_t)g.bn * BK * 2;
       const uint32_t tx_a = g.a_bytes ? (uint32_t)g.a_bytes : (uint32_t)A_STAGE_BYTES;
       const int nz = g.zi ? g.n_zblocks : 0;
+      if constexpr (KPS > 1) {
+        // KPS k-blocks per stage: one full / empty handshake per KPS k-blocks.  The main loop of the small-grid stages is bound by
+        // the MMA thread's per-handshake chain (~210 ns), not by operand delivery, so halve the handshakes.
+        const int n_st = (nk + KPS - 1) / KPS;
+        for (int st = 0; st < n_st; ++st) {
+          const int s = st % STAGES;
+          mbar_wait(&empty[s], ((st / STAGES) & 1) ^ 1u);
+          const int n_sub = min(KPS, nk - st * KPS);
+          mbar_expect_tx(&full[s], (uint32_t)n_sub * (tx_a + tx_b));
+          for (int j = 0; j < n_sub; ++j) {
+            const int kb = st * KPS + j;
+            uint8_t* sa = smem + s * SL::STAGE_BYTES + j * SL::SUB_BYTES;
+            const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
+            tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
+            tma_load_2d(sa + A_STAGE_BYTES, &g.tmB, kb * BK, b_row, &full[s]);
+          }
+          if (st == 0) probe(g, 2);
+        }
+      } else {
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -170,9 +198,28 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         }
         if (kb == 0) probe(g, 2);
       }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      if constexpr (KPS > 1) {
+        const uint32_t idesc = umma_idesc_bf16(g.bn);
+        const int n_st = (nk + KPS - 1) / KPS;
+        for (int st = 0; st < n_st; ++st) {
+          const int s = st % STAGES;
+          mbar_wait(&full[s], (st / STAGES) & 1);
+          tc_fence_after();
+          if (st == 0) probe(g, 3);
+          const int n_sub = min(KPS, nk - st * KPS);
+          for (int j = 0; j < n_sub; ++j) {
+            const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES + j * SL::SUB_BYTES);
+            const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (st | j | k) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+      } else {
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -210,6 +257,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
         }
         if constexpr (CM == 1) umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
         else umma_commit_mc(&empty[s], (uint16_t)0x3);   // ... in both CTAs: the peer's producer also writes into it
+      }
       }
       umma_commit(tmem_full);    // accumulator complete
       probe(g, 4);

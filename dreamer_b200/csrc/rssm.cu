@@ -105,7 +105,7 @@ static int grid_for(long total, int threads = 256) {
 
 template <class Epi>
 static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3 grid, cudaStream_t st, int stage = DRM_STAGE_OTHER) {
-  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES>;
+  using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES, kps_of<Epi>::value>;
   static bool attr_set = false;
   if (!attr_set) {
     DRM_CUDA(cudaFuncSetAttribute(fused_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
@@ -643,10 +643,12 @@ static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMa
   if (opts().ln_cluster && mt * n_slots <= 37) {
     g.tmB = tmB_q;
     g.bn = 64;
+    g.zi = nullptr;   // the one-hot expander (opt-in) walks single-k-block stages; this kernel pairs k-blocks per stage
     return launch_gemm<EpiLnSiluN4T<HAS_ADD>>(g, p, dim3(mt, n_slots, 4), st, stage_id);
   }
   g.tmB = tmB_full;
   g.bn = bn_full;
+  g.zi = nullptr;     // (see above)
   return launch_gemm<EpiLnSiluT<HAS_ADD>>(g, p, dim3(mt, n_slots, 1), st, stage_id);
 }
 
