@@ -1,0 +1,170 @@
+// GRU stage for SMALL grids, split over K across a 2-CTA cluster.  Included from rssm.cu.
+//
+// At 1024 rows x D = 600 the GRU stage is 152 tiles whose main loop (26 k-blocks, 148 MMA issues by ONE thread) takes ~10 us
+// no matter how the operands arrive (knock-out experiments).  The lever is fewer MMA issues per CTA:
+//   rank 0 accumulates the x part (z | a k-blocks:  gi = x W_ih^T),  rank 1 the h part (gh = h W_hh^T) of the SAME 128 x 3U tile,
+// each with one N = 3U MMA per k-step into its own TMEM accumulator [r | z | n] -- the h part no longer needs the split
+// r,z / n MMAs because n_h lives in the other CTA.  Then the CTAs swap halves: rank 0 finishes rows 0..63, rank 1 rows 64..127;
+// every epilogue thread whose row belongs to the peer writes its 3 x 8 partial sums into the peer's shared memory
+// (st.shared::cluster), one cluster barrier, and the owner combines  r = sig(r_x + r_h + b), z likewise,
+// n = tanh(n_x + b_in + r (n_h + b_hn)),  h' = (1 - z) n + z h  (nn.GRUCell, SequenceModel.py:13-24).
+// 304 CTAs of ~110 KB: two per SM, so the x and h halves of different tiles share tensor cores.
+#pragma once
+
+namespace drm {
+
+template <int U>
+struct GruKsSmem {
+  static constexpr int STAGES = 3;
+  static constexpr int SUB = A_STAGE_BYTES + 3 * U * BK * 2;       // 28 KB (U = 32)
+  static constexpr int XBUF_OFF = STAGES * SUB;                    // incoming peer partials: [64 rows][3U] fp32
+  static constexpr int XBUF_BYTES = 64 * 3 * U * 4;
+  static constexpr int BAR_OFF = XBUF_OFF + XBUF_BYTES;
+  static constexpr int CONST_OFF = BAR_OFF + 128;
+  static constexpr int TOTAL = CONST_OFF + 4 * U * 4;
+  static_assert(SUB % 1024 == 0, "stages must keep 1024-byte alignment");
+};
+
+template <int U>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename EpiGru<U, 1>::Params ep) {
+  using SL = GruKsSmem<U>;
+  constexpr int STAGES = SL::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  float* xbuf = reinterpret_cast<float*>(smem + SL::XBUF_OFF);
+  float* cst = reinterpret_cast<float*>(smem + SL::CONST_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();            // 0: x part, 1: h part
+  const int slot = (int)blockIdx.y;
+  const int a_row = g.a_row0 + (int)blockIdx.x * BM;
+  const int b_row = slot * 3 * U;
+  const int kb0 = rank == 0 ? 0 : g.nka0, nkb = rank == 0 ? g.nka0 : g.nka1;
+
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.tmA);
+    tma_prefetch_desc(&g.tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer is resident before anybody writes into its shared memory
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (g.a_bytes ? (uint32_t)g.a_bytes : (uint32_t)A_STAGE_BYTES) + (uint32_t)(3 * U) * BK * 2;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1u);
+        uint8_t* sa = smem + s * SL::SUB;
+        const int ka = rank == 0 ? g.ka0 + i : g.ka1 + i;
+        mbar_expect_tx(&full[s], tx);
+        tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
+        tma_load_2d(sa + A_STAGE_BYTES, &g.tmB, (kb0 + i) * BK, b_row, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(3 * U);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&full[s], (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * SL::SUB);
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  }
+
+  float acc[3][8];          // this CTA's partial sums of the thread's row and 8 units: [r | z | n]
+  const int tid = (int)threadIdx.x - 64;
+  const int q = warp & 3, part = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
+  const int c = part * (U / 4);                      // first of this thread's U / 4 = 8 units inside the tile
+  const bool epi = warp >= 2;
+  const bool mine = epi && (row >> 6) == rank;       // rows 0..63 are finished by rank 0, rows 64..127 by rank 1
+  if (epi) {
+    EpiGru<U, 1>::stage(ep, g, slot, cst, tid);
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    epi_bar_sync();
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    tmem_ld8_nowait(tlane + (uint32_t)c, acc[0]);
+    tmem_ld8_nowait(tlane + (uint32_t)(U + c), acc[1]);
+    tmem_ld8_nowait(tlane + (uint32_t)(2 * U + c), acc[2]);
+    tmem_ld_wait();
+    if (!mine) {             // hand the partials of this row to the peer that finishes it
+      const uint32_t base = smem_u32(xbuf + (row & 63) * 3 * U + c);
+#pragma unroll
+      for (int gte = 0; gte < 3; ++gte) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t remote;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(base + (uint32_t)((gte * U + 4 * h) * 4)), "r"(rank ^ 1));
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(remote), "f"(acc[gte][4 * h]), "f"(acc[gte][4 * h + 1]),
+                       "f"(acc[gte][4 * h + 2]), "f"(acc[gte][4 * h + 3])
+                       : "memory");
+        }
+      }
+    }
+  }
+  __syncwarp();
+  cluster_arrive_release();  // every thread of both CTAs, exactly once
+  cluster_wait_acquire();
+  if (mine) {
+    const int m = (int)blockIdx.x * BM + row;
+    const int u0 = slot * U + c;
+    if (m < g.M) {
+      const float* px = xbuf + (row & 63) * 3 * U + c;      // the peer's partials of this row
+      const int nvalid = min(8, ep.D - u0);
+      float hp[8], hn[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hp[j] = j < nvalid ? __ldg(ep.h_prev + (long)m * ep.ld_hprev + u0 + j) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pr = px[j], pz = px[U + j], pn = px[2 * U + j];
+        const float nx = rank == 0 ? acc[2][j] : pn, nh = rank == 0 ? pn : acc[2][j];
+        const float rr = sigmoidf_(acc[0][j] + pr + cst[c + j]);
+        const float zz = sigmoidf_(acc[1][j] + pz + cst[U + c + j]);
+        const float nn = tanhf_(nx + cst[2 * U + c + j] + rr * (nh + cst[3 * U + c + j]));
+        hn[j] = (1.0f - zz) * nn + zz * hp[j];
+      }
+      float* o = ep.h_out + (long)m * ep.ld_hout + u0;
+      __nv_bfloat16* ob = ep.s_h + (long)m * ep.ld_s + u0;
+      if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(ob) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        *reinterpret_cast<uint4*>(ob) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
+                                                   pack_bf16x2(hn[6], hn[7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nvalid) { o[j] = hn[j]; ob[j] = __float2bfloat16_rn(hn[j]); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace drm

@@ -69,6 +69,7 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
+  int gru_ksplit;  // 1: small grids split the GRU tile's K range over a 2-CTA cluster (default 1)
   int conv_persist;  // 1: narrow conv layers on the persistent GEMM (default 1)
   int chain2;      // 1: small grids run (LN layer -> output stage) pairs as one kernel, activations kept in shared memory (default 0)
   int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
@@ -87,6 +88,7 @@ static Options& opts() {
     x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
     x.chain2 = getenv("DRM_CHAIN2") != nullptr;
     x.conv_persist = getenv("DRM_NO_CONV_PERSIST") == nullptr;
+    x.gru_ksplit = getenv("DRM_NO_GRU_KSPLIT") == nullptr;
     x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
@@ -145,7 +147,40 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
 
 }  // namespace drm
 #include "gru_pair.cuh"
+#include "gru_ksplit.cuh"
 namespace drm {
+
+template <int U>
+static int launch_gru_ksplit(const GemmCommon& g, const typename EpiGru<U, 1>::Params& ep, int mt, int tiles, cudaStream_t st) {
+  using SL = GruKsSmem<U>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(gru_ksplit_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
+    attr_set = true;
+  }
+  profile_begin(DRM_STAGE_GRU, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(mt, tiles, 2);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SL::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 2;
+  ++na;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, gru_ksplit_kernel<U>, g, ep));
+  profile_end(DRM_STAGE_GRU, st);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
 
 template <int U>
 static int launch_gru_pair(const GemmCommon& g, const typename EpiGru<U, 1>::Params& ep, int mt, int tiles, cudaStream_t st) {
@@ -584,6 +619,11 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
     }
     EpiGru<64, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_pair<64>(g, p, mt, m->gru_tiles2[v], st);
+  }
+  if (!mc && !g.zi && U == 32 && opts().gru_ksplit && mt * m->gru_tiles2[v] <= 148) {
+    // small grid: x part and h part of every tile on two CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh)
+    EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+    return launch_gru_ksplit<32>(g, p, mt, m->gru_tiles2[v], st);
   }
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
   {                                                                                                         \
@@ -1049,6 +1089,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "small_a") o.small_a = value != 0;
   else if (n == "chain2") o.chain2 = value != 0;
   else if (n == "conv_persist") o.conv_persist = value != 0;
+  else if (n == "gru_ksplit") o.gru_ksplit = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
   else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }

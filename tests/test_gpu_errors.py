@@ -73,7 +73,7 @@ def test_rollout_is_deterministic():
         assert torch.equal(x, y) and torch.equal(x, w)
 
 
-@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("small_a", 0), ("chain2", 1), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32)])
+@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("small_a", 0), ("chain2", 1), ("gru_ksplit", 0), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32)])
 def test_alternative_kernel_paths_give_identical_results(L, option, value):
     """Every switchable path reproduces the default path on a whole rollout: bit for bit for the one-hot expander, the TMA
     multicast clusters and both GRU tile widths (same per-element accumulation order); to fp32 rounding for the one-CTA LN
@@ -85,15 +85,20 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     model = ops.PackedRssm.from_state_dict(sd)
     ro = ops.Rollout(model, 200, 4)
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 200, 4, seed=6))
-    base = ro.run(z0, h0, u, n)
     assert lib.drm_set_option(b"nonsense", 1) == -5
-    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, small_a=1, chain2=0, gru_pair=-1, gru_u=0)
+    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, small_a=1, chain2=0, gru_ksplit=1, gru_pair=-1, gru_u=0)
+    # the K-split GRU kernel (default on small grids) sums the x and h parts in a different order than every other GRU path, and
+    # several options fall back from it: hold it off for the bit-exact comparisons, and compare it against the rest to rounding
+    ksplit_base = 1 if option == "gru_ksplit" else 0
     try:
+        L.check(lib.drm_set_option(b"gru_ksplit", ksplit_base), "set_option")
+        base = ro.run(z0, h0, u, n)
         L.check(lib.drm_set_option(option.encode(), value), "set_option")
         alt = ro.run(z0, h0, u, n)
     finally:
         lib.drm_set_option(option.encode(), defaults[option])
-    if option in ("ln_cluster", "chain", "chain2"):
+        lib.drm_set_option(b"gru_ksplit", 1)
+    if option in ("ln_cluster", "chain", "chain2", "gru_ksplit"):
         assert (base[7] != alt[7]).float().mean().item() < 0.01
         same = (base[7] == alt[7]).all(dim=-1).all(dim=-1)          # trajectories whose draws all agree
         for a, b in zip(base[1:7], alt[1:7]):
@@ -140,6 +145,7 @@ def test_cta_pair_gru_band_order_on_ragged_grids(L, B):
     ro = ops.Rollout(model, B, 2)
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, 2, seed=B))
     try:
+        L.check(lib.drm_set_option(b"gru_ksplit", 0), "set_option")     # compare against the single-CTA kernel (same summation order)
         L.check(lib.drm_set_option(b"gru_pair", 0), "set_option")
         base = ro.run(z0, h0, u, n)
         for width in (32, 64):
@@ -151,3 +157,4 @@ def test_cta_pair_gru_band_order_on_ragged_grids(L, B):
     finally:
         lib.drm_set_option(b"gru_pair", -1)
         lib.drm_set_option(b"gru_u", 0)
+        lib.drm_set_option(b"gru_ksplit", 1)
