@@ -69,7 +69,8 @@ struct Options {
   int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
   int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
   int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
-  int gru_ksplit;  // 1: small grids split the GRU tile's K range over a 2-CTA cluster (default 1)
+  int gru_ksplit;  // 1: tiny grids split the GRU tile's K range over a 2-CTA cluster (default 1)
+  int gru_ksplit_mt;  // ... up to this many m-tiles (default 1)
   int conv_persist;  // 1: narrow conv layers on the persistent GEMM (default 1)
   int chain2;      // 1: small grids run (LN layer -> output stage) pairs as one kernel, activations kept in shared memory (default 0)
   int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
@@ -89,6 +90,7 @@ static Options& opts() {
     x.chain2 = getenv("DRM_CHAIN2") != nullptr;
     x.conv_persist = getenv("DRM_NO_CONV_PERSIST") == nullptr;
     x.gru_ksplit = getenv("DRM_NO_GRU_KSPLIT") == nullptr;
+    x.gru_ksplit_mt = getenv("DRM_GRU_KSPLIT_MT") ? atoi(getenv("DRM_GRU_KSPLIT_MT")) : 1;
     x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
     x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
     const char* e = getenv("DRM_GRU_U");
@@ -620,10 +622,14 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
     EpiGru<64, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_pair<64>(g, p, mt, m->gru_tiles2[v], st);
   }
-  if (!mc && !g.zi && U == 32 && opts().gru_ksplit && mt * m->gru_tiles2[v] <= 148) {
-    // small grid: x part and h part of every tile on two CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh)
+  if (!mc && !g.zi && opts().gru_ksplit && mt <= opts().gru_ksplit_mt && mt * m->gru_tiles2[0] <= 148) {
+    // tiny grid (the 16-sequence posterior scan, the B = 1 acting path, warm starts): x part and h part of every tile on two
+    // CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh).  Measured per imagined step at D = 600: 128 rows
+    // 62.1 -> 59.4 us, 256 rows 62.9 -> 65.1 us, 512 rows 66.2 -> 67.7 us, 896 rows 66.0 -> 66.8 us; a 48-unit-tile variant that
+    // fits 1024 rows (104 tiles x 2 CTAs) was 8 us slower there -- so only single-m-tile grids take this path.
+    g.tmB = m->tmWgru2[0]; g.bn = 96;
     EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
-    return launch_gru_ksplit<32>(g, p, mt, m->gru_tiles2[v], st);
+    return launch_gru_ksplit<32>(g, p, mt, m->gru_tiles2[0], st);
   }
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
   {                                                                                                         \

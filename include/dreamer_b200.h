@@ -63,7 +63,7 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_COUNT 8
 /* Runtime switches for the experimental / alternative kernel paths (all produce identical results):                  */
 /*   "ln_cluster" (default 1)  LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
-/*   "gru_ksplit" (default 1)  small grids: the x part and the h part of every GRU tile on two CTAs of a cluster (half the MMA issues  */
+/*   "gru_ksplit" (default 1)  single-m-tile grids: the x part and the h part of every GRU tile on two CTAs of a cluster (half the MMA issues */
 /*                             per CTA), rows swapped through distributed shared memory for the epilogue                             */
 /*   "conv_persist" (default 1) conv layers with <= 64 output channels on the persistent double-buffered GEMM (0: one tile per CTA)   */
 /*   "chain2"     (default 0)  small grids: (prior L2 -> logits + sample) and (head L2 -> head outputs) as ONE kernel each, the  */
