@@ -10,7 +10,8 @@
 // (st.shared::cluster), one cluster barrier, and the owner combines  r = sig(r_x + r_h + b), z likewise,
 // n = tanh(n_x + b_in + r (n_h + b_hn)),  h' = (1 - z) n + z h  (nn.GRUCell, SequenceModel.py:13-24).
 // Measured (D = 600, per imagined step): 128 rows 62.1 -> 59.4 us; from two m-tiles on it is slower (256 rows 62.9 -> 65.1 us,
-// 1024 rows with 48-unit tiles +8 us), so the launch takes this path only for single-m-tile grids.
+// 1024 rows with 48-unit tiles +8 us), so the launch takes this path only for single-m-tile grids of the posterior scan and of
+// drm_gru_step (imagination rollouts keep batch-size-independent per-row arithmetic: shards concatenate bit-exactly).
 #pragma once
 
 namespace drm {

@@ -590,7 +590,7 @@ static void use_z_indices(drm_rssm* m, GemmCommon& g, const WsView& v) {
 
 // GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
 static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
-                     long ld_hout, int M, cudaStream_t st, bool z_idx = false) {
+                     long ld_hout, int M, cudaStream_t st, bool z_idx = false, bool allow_ksplit = false) {
   // DRM_MULTICAST=1 selects the cluster variant (pairs of m-tiles, weight tile halves multicast by TMA).  Measured on B200 it
   // is not faster: the stage is bound by per-SM shared-memory ingress, which multicast does not reduce (profiles/README.md).
   const bool mc = opts().multicast != 0;
@@ -622,7 +622,9 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
     EpiGru<64, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_pair<64>(g, p, mt, m->gru_tiles2[v], st);
   }
-  if (!mc && !g.zi && opts().gru_ksplit && mt <= opts().gru_ksplit_mt && mt * m->gru_tiles2[0] <= 148) {
+  // (allow_ksplit: the posterior scan and the step-level entry point; drm_rollout_run keeps kernels whose per-row arithmetic does
+  // not depend on the batch size, so that shards of a rollout concatenate bit-exactly to the full batch)
+  if (allow_ksplit && !mc && !g.zi && opts().gru_ksplit && mt <= opts().gru_ksplit_mt && mt * m->gru_tiles2[0] <= 148) {
     // tiny grid (the 16-sequence posterior scan, the B = 1 acting path, warm starts): x part and h part of every tile on two
     // CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh).  Measured per imagined step at D = 600: 128 rows
     // 62.1 -> 59.4 us, 256 rows 62.9 -> 65.1 us, 512 rows 66.2 -> 67.7 us, 896 rows 66.0 -> 66.8 us; a 48-unit-tile variant that
@@ -1010,7 +1012,7 @@ extern "C" int drm_gru_step(drm_rollout* r, const float* z, const float* h, cons
   RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP, a, m->d.A, m->d.A, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
-  return stage_gru(m, view_of(r, 0), view_of(r, 1), h, m->d.D, h_out, m->d.D, N, st);
+  return stage_gru(m, view_of(r, 0), view_of(r, 1), h, m->d.D, h_out, m->d.D, N, st, false, true);
 }
 
 extern "C" int drm_prior(drm_rollout* r, const float* h, const float* uniforms, float* logits, float* z_st, uint8_t* idx,

@@ -696,7 +696,7 @@ extern "C" int drm_observe_scan(drm_observe* o, const float* obs, const float* a
     if (t == 0 && mode == 1) {
       DRM_CUDA(cudaMemset2DAsync(hidden, ldH * sizeof(float), 0, (size_t)D * sizeof(float), B, st));   // h_0 = 0, no GRU step
     } else {
-      RC(stage_gru(m, prev, cur, t == 0 ? o->zero_h : hidden + (long)(t - 1) * D, t == 0 ? (long)D : ldH, hidden + (long)t * D, ldH, B, st, t > 0));
+      RC(stage_gru(m, prev, cur, t == 0 ? o->zero_h : hidden + (long)(t - 1) * D, t == 0 ? (long)D : ldH, hidden + (long)t * D, ldH, B, st, t > 0, true));
     }
     RC(encoder_head(o, cur, o->featpart + (long)t * B * v->bn_he, uniforms + (long)t * B * R, latent + (long)t * ZP, ldL,
                     post_logits ? post_logits + (long)t * ZP : nullptr, ldL, idx ? idx + (long)t * R : nullptr, (long)T * R, true, B, st));

@@ -158,3 +158,29 @@ def test_persistent_conv_gemm_is_bit_identical_to_one_tile_per_cta(ops):
         finally:
             lib.drm_set_option(b"conv_persist", 1)
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), name
+
+
+def test_ksplit_gru_scan_agrees_with_single_cta_scan(ops):
+    """Option "gru_ksplit" (x part / h part of every GRU tile on two CTAs of a cluster, used by the posterior scan and
+    drm_gru_step on single-m-tile grids): same draws, hidden states equal to fp32 summation-order rounding."""
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    cfg = CFGS["ref"]
+    _, _, vae = _build(ops, cfg, 17)
+    B, T = 16, 6
+    ws = ops.Observe(vae, B, T)
+    obs, act, _, _, u = (t.to(DEV) for t in W.sequence_inputs(cfg, B, T, seed=18))
+    obs = obs / 255.0 - 0.5
+    outs = []
+    try:
+        for flag in (1, 0):
+            L.check(lib.drm_set_option(b"gru_ksplit", flag), "set_option")
+            sc = ws.scan(obs, act, u)
+            outs.append({k: v.clone() for k, v in sc.items()})
+    finally:
+        lib.drm_set_option(b"gru_ksplit", 1)
+    assert (outs[0]["idx"] != outs[1]["idx"]).float().mean().item() < 0.01
+    same = (outs[0]["idx"] == outs[1]["idx"]).all(dim=-1).all(dim=-1)
+    assert same.any()
+    assert torch.allclose(outs[0]["hidden"][same], outs[1]["hidden"][same], atol=2e-3, rtol=2e-3)
+    assert not torch.equal(outs[0]["hidden"], outs[1]["hidden"])          # the two paths really are different kernels
