@@ -184,3 +184,22 @@ def test_rollout_c4_sizes_teacher_forced(ops):
         _close(hid[:, t + 1], h2, what=f"hidden t={t}")
         mismatch += (i2 != idx[:, t].long()).sum().item()
     assert mismatch <= 0.005 * B * H * 32                                      # draws on bf16-vs-fp32 logits: a few bin-edge flips at most
+
+
+def test_host_buffer_rollout_call_matches_device_call_across_graph_capture(ops):
+    """rollout.dream_episodes_host (pinned host inputs, pinned host results, the rollout replayed as one CUDA graph after two
+    eager calls) returns exactly what the device-resident call returns, before and after the capture."""
+    from dreamer_b200.rollout import dream_episodes_host
+    cfg = W.small_config()
+    sd, model = _model(ops, cfg, 3)
+    B, H = 130, 4
+    ro = ops.Rollout(model, B, H)
+    for call in range(5):
+        z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=100 + call)
+        ref = [t.clone() for t in ro.run(z0.to(DEV), h0.to(DEV), u.to(DEV), n.to(DEV), want_idx=False)]
+        got = dream_episodes_host(ro, z0.pin_memory(), h0.pin_memory(), uniforms=u.pin_memory(), normals=n.pin_memory())
+        for a, b in zip(ref, got["device"]):
+            if a is not None:
+                assert torch.equal(a, b), call
+        assert torch.equal(got["host"][0], ref[3].cpu()) and torch.equal(got["host"][1], ref[4].cpu())
+    assert ro.__dict__["_host_state"]["graph"].captured(*[ro.__dict__["_host_state"][k] for k in ("z", "h", "u", "n")])
