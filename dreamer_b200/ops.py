@@ -317,6 +317,16 @@ class Rollout:
         self.handle = C.c_void_p()
         L.check(L.load().drm_rollout_create(model.handle, B, H, C.byref(self.handle)), "rollout_create")
 
+    def run_graphed(self, z0, h0, uniforms, normals, want_idx: bool = True):
+        """`run` replayed as ONE CUDA graph after two eager calls (graphs.StepGraph): the inputs are copied into static device
+        buffers and the ~110 launches of a rollout become one graph launch (0.99 -> 0.94 ms at 1024 x 15, and no host launch
+        work).  The returned tensors are the graph's static outputs: they are overwritten by the next call."""
+        from .graphs import StepGraph
+        cache = self.__dict__.setdefault("_graphs", {})
+        if want_idx not in cache:
+            cache[want_idx] = StepGraph(lambda a, b, c, d: self.run(a, b, c, d, want_idx=want_idx), warmup=2)
+        return cache[want_idx](L.f32c(z0), L.f32c(h0), L.f32c(uniforms), L.f32c(normals))
+
     def run(self, z0, h0, uniforms, normals, want_idx: bool = True):
         """Dreamer.dream_episodes (Dreamer.py:143-175).
 

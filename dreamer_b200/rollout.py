@@ -31,15 +31,13 @@ def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=Non
     The workspace keeps static device inputs and, after two eager calls, replays the rollout's ~110 launches as ONE CUDA graph
     (graphs.StepGraph): the host then issues two copies, two RNG fills, one graph launch and two read-backs per call instead of
     half a millisecond of kernel launches, so the call's wall time is the device time plus the host link."""
-    from .graphs import StepGraph
     dev = torch.device("cuda", torch.cuda.current_device())
     m, B, H = rollout.model, rollout.B, rollout.H
     st = rollout.__dict__.get("_host_state")
     if st is None:
         f = dict(dtype=torch.float32, device=dev)
         st = dict(z=torch.empty((B,) + tuple(z0.shape[1:]), **f), h=torch.empty((B,) + tuple(h0.shape[1:]), **f),
-                  u=torch.empty((H, B, m.R), **f), n=torch.empty((H, B, m.A), **f),
-                  graph=StepGraph(lambda z, h, u, n: rollout.run(z, h, u, n, want_idx=False), warmup=2), host=None)
+                  u=torch.empty((H, B, m.R), **f), n=torch.empty((H, B, m.A), **f), host=None)
         rollout.__dict__["_host_state"] = st
     st["z"].copy_(z0, non_blocking=True)
     st["h"].copy_(h0, non_blocking=True)
@@ -51,7 +49,7 @@ def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=Non
         st["n"].copy_(normals, non_blocking=True)
     else:
         st["n"].normal_(generator=generator)
-    out = st["graph"](st["z"], st["h"], st["u"], st["n"])
+    out = rollout.run_graphed(st["z"], st["h"], st["u"], st["n"], want_idx=False)
     # results come back into PINNED host buffers owned by the workspace (a pageable destination would be staged and synchronous)
     if st["host"] is None:
         st["host"] = [torch.empty(out[3].shape, dtype=out[3].dtype).pin_memory(), torch.empty(out[4].shape, dtype=out[4].dtype).pin_memory()]

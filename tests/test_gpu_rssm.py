@@ -202,4 +202,4 @@ def test_host_buffer_rollout_call_matches_device_call_across_graph_capture(ops):
             if a is not None:
                 assert torch.equal(a, b), call
         assert torch.equal(got["host"][0], ref[3].cpu()) and torch.equal(got["host"][1], ref[4].cpu())
-    assert ro.__dict__["_host_state"]["graph"].captured(*[ro.__dict__["_host_state"][k] for k in ("z", "h", "u", "n")])
+    assert ro.__dict__["_graphs"][False].captured(*[ro.__dict__["_host_state"][k] for k in ("z", "h", "u", "n")])
