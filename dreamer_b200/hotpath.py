@@ -34,6 +34,7 @@ class HotPath:
         from .modules import Buffer
         self.world_model, self.agent = _build(self.cfg, self.device)
         self.agent.attach_world_model(self.world_model)      # actor gradient through the imagined states (bptt.actor_backward)
+        self.cuda_graphs = bool(cuda_graphs)
         if cuda_graphs:
             self.world_model.enable_cuda_graphs()
             self.agent.enable_cuda_graphs()
@@ -66,9 +67,9 @@ class HotPath:
         return sc["latent"][:, -1:].contiguous(), sc["hidden"][:, -1:].contiguous()
 
     # Dreamer.py:143-175
-    def dream_episodes(self, starting_latent_state_batch, starting_hidden_state_batch, uniforms=None, normals=None):
+    def dream_episodes(self, starting_latent_state_batch, starting_hidden_state_batch, uniforms=None, normals=None, graphed=False):
         return rollout.dream_episodes_modules(self.world_model, self.agent, starting_latent_state_batch, starting_hidden_state_batch,
-                                              self.horizon, uniforms, normals)
+                                              self.horizon, uniforms, normals, graphed=graphed)
 
     # Dreamer.py:264-287
     def train_Agent(self):
@@ -76,7 +77,8 @@ class HotPath:
         for _ in range(self.AC_epochs):
             obs, act, _, _, L = self.buffer.sample_sequences(batch_size=self.batch_size)
             z0, h0 = self.warm_start_generator(obs, act, L)
-            z, h, a, r, c, mu, sg = self.dream_episodes(z0, h0)
+            # with cuda_graphs the rollout is one graph replay; its static outputs are consumed by train_step before the next call
+            z, h, a, r, c, mu, sg = self.dream_episodes(z0, h0, graphed=self.cuda_graphs)
             loss_actor, loss_critic = self.agent.train_step(z, h, r, c, a, mu, sg)
             la.append(loss_actor); lc.append(loss_critic)
         return torch.stack(la).mean(dim=0), torch.stack(lc).mean(dim=0)

@@ -11,16 +11,19 @@ import torch
 from . import ops
 
 
-def dream_episodes(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, generator=None, want_idx=False):
+def dream_episodes(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, generator=None, want_idx=False, graphed=False):
     """Returns (latent (B,H+1,R,C), hidden (B,H+1,D), actions, rewards, continues, mu, sigma) exactly like
-    the reference.  ``uniforms`` (H,B,R) / ``normals`` (H,B,A) default to fresh device-side draws."""
+    the reference.  ``uniforms`` (H,B,R) / ``normals`` (H,B,A) default to fresh device-side draws.
+    ``graphed``: replay the rollout as one CUDA graph (ops.Rollout.run_graphed); the returned tensors are then the graph's
+    static outputs and are overwritten by the next call on this workspace."""
     m, B, H = rollout.model, rollout.B, rollout.H
     dev = z0.device
     if uniforms is None:
         uniforms = torch.rand((H, B, m.R), device=dev, generator=generator)
     if normals is None:
         normals = torch.randn((H, B, m.A), device=dev, generator=generator)
-    return rollout.run(z0, h0, uniforms, normals, want_idx=want_idx)
+    run = rollout.run_graphed if graphed else rollout.run
+    return run(z0, h0, uniforms, normals, want_idx=want_idx)
 
 
 def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, generator=None):
@@ -60,11 +63,11 @@ def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=Non
 
 
 def dream_episodes_modules(world_model, agent, starting_latent_state_batch, starting_hidden_state_batch, horizon=None,
-                           uniforms=None, normals=None, generator=None):
+                           uniforms=None, normals=None, generator=None, graphed=False):
     """Drop-in body for ``Dreamer.dream_episodes`` (Dreamer.py:143-175) on the mirrored modules: one fused rollout instead
     of ``horizon`` x (Actor.act -> WorldModel.imagine_step).  Returns the reference's 7-tuple."""
     H = world_model.horizon if horizon is None else horizon
     B = starting_hidden_state_batch.shape[0]
     world_model.attach_actor(agent.actor)
     ro = world_model._engine.rollout(B, H)
-    return dream_episodes(ro, starting_latent_state_batch, starting_hidden_state_batch, uniforms, normals, generator)
+    return dream_episodes(ro, starting_latent_state_batch, starting_hidden_state_batch, uniforms, normals, generator, graphed=graphed)

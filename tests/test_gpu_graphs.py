@@ -83,3 +83,23 @@ def test_agent_train_step_graph_matches_eager_and_skips_nonfinite_on_device():
     # and the next clean batch trains again
     ag_g.train_step(*batch())
     assert not bool(ag_g.critic_optimiser.last_step_skipped)
+
+
+def test_graphed_rollout_follows_weight_updates():
+    """Rollout.run_graphed: the captured rollout reads the packed weights in place, so after a parameter update (re-packed by
+    the engine outside the graph) the replay must equal a fresh eager rollout bit for bit."""
+    from dreamer_b200 import rollout as R
+    cfg = W.small_config(horizon=6)
+    wm, ag = W.build_learners(cfg, W.make_state_dict(cfg, seed=5), DEV)
+    B, H = 40, cfg["horizon"]
+    for it in range(5):
+        z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, H, seed=60 + it))
+        got = [t.clone() for t in R.dream_episodes_modules(wm, ag, z0, h0, H, u, n, graphed=True)]
+        ref = R.dream_episodes_modules(wm, ag, z0, h0, H, u, n)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b), it
+        with torch.no_grad():                       # "training": every weight moves, versions bump -> the engine re-packs
+            for p in list(wm.parameters()) + list(ag.actor.parameters()):
+                p.mul_(1.0 + 0.01 * (it + 1))
+    ro = wm._engine.rollout(B, H)
+    assert ro._graphs[False].captured(z0.float(), h0.float(), u, n)
