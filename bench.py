@@ -469,6 +469,11 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs are released before the process group (a live graph at NCCL teardown has hung the exit before)
+        import gc
+        ro.__dict__.pop("_graphs", None)
+        gc.collect()
+        barrier()
         dist.destroy_process_group()
 
 
