@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chain_kernel(const __grid_con
   const int w_row = slot * 256 + rank * 64;                                    // LN layers
   const int w2_row = p.kind == CHAIN_PRIOR ? rank * 256 : slot * 256 + rank * 64; // output layer (first pass)
 
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     cprobe(p, 0);
     cta_probe(p.cta_times, 0);
@@ -231,6 +230,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chain_kernel(const __grid_con
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  // (after the TMEM allocation: see fused_gemm_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   cluster_sync_all();   // peers are resident and their barriers initialised before any remote access
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;

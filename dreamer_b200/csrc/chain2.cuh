@@ -60,7 +60,6 @@ chain2_kernel(const __grid_constant__ Chain2Common c, const __grid_constant__ ty
   const int wb_row = (c.per_slot ? slot : by) * c.wb_tile_rows;
   const int nkA = c.nka0 + c.nka1;
 
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&c.tmA); tma_prefetch_desc(&c.tmWA); tma_prefetch_desc(&c.tmWB);
     for (int s = 0; s < C2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -71,6 +70,8 @@ chain2_kernel(const __grid_constant__ Chain2Common c, const __grid_constant__ ty
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  // (after the TMEM allocation: see fused_gemm_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");

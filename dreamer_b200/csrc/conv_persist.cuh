@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_persist_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = c.n_mtiles * c.phases;
 
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&c.tmA);
     tma_prefetch_desc(&c.tmB);
@@ -60,6 +59,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_persist_kernel(const __g
   if (warp == 1) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
+  // (after the TMEM allocation: see fused_gemm_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");

@@ -131,9 +131,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int a_row = g.a_row0 + slot * g.a_y_stride + (int)blockIdx.x * BM;
   const int b_row = slot * (g.b_slot_rows ? g.b_slot_rows : g.bn) + (CN > 1 ? (int)cluster_ctarank() * g.bn : 0);
 
-  // Programmatic dependent launch: let the next stage's CTAs start their prologue now; everything this CTA
-  // reads that an earlier stage produced (activations via TMA, h_prev) is touched only after griddep_wait().
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  // (everything this CTA reads that an earlier stage produced -- activations via TMA, h_prev -- is touched only after
+  // griddepcontrol.wait; the trigger that lets the next stage's CTAs start their prologue follows the TMEM allocation below)
   if (threadIdx.x == 0) {
     probe(g, 0);
     cta_probe(g.cta_times, 0);
@@ -149,6 +148,10 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, Epi::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  // Programmatic dependent launch, triggered only now that this CTA HOLDS its TMEM columns: the next stage's CTAs allocate TMEM in
+  // their prologue and then block in griddepcontrol.wait until this grid has finished, so a dependent CTA that reached an SM before
+  // a CTA of this grid had allocated could starve it of columns for good.
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if constexpr (CM > 1 || CN > 1) cluster_sync_all();   // peers are resident and their barriers initialised before any remote access
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;

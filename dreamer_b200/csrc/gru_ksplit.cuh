@@ -51,7 +51,6 @@ gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int b_row = slot * 3 * U;
   const int kb0 = rank == 0 ? 0 : g.nka0, nkb = rank == 0 ? g.nka0 : g.nka1;
 
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&g.tmA);
     tma_prefetch_desc(&g.tmB);
@@ -62,6 +61,8 @@ gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
+  // (after the TMEM allocation: see fused_gemm_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   cluster_sync_all();     // the peer is resident before anybody writes into its shared memory
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;

@@ -97,7 +97,6 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
   const int a_row = g.a_row0 + m_tile * BM;
   const int b_row = slot * 3 * U;
 
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (threadIdx.x == 0) {
     cta_probe(g.cta_times, 0);
     tma_prefetch_desc(&g.tmA);
@@ -109,6 +108,8 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
   if (warp == 1) tmem_alloc_2cta(tmem_slot, 4 * U);
   tc_fence_before();
   __syncthreads();
+  // (after the TMEM allocation: see fused_gemm_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   cluster_sync_all();   // both CTAs' barriers exist and both allocations are done before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
