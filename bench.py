@@ -436,14 +436,15 @@ def main():
     gru_us = stages["gru"]["us_per_launch"]
     gru_tf = fl["gru"] * B / (gru_us * 1e-6) / 1e12
     whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12   # per GPU (B is per rank)
-    traffic = None
+    traffic, gru_kernel = None, "fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)"
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         traffic = tj and tj["dram_bytes_per_launch"]        # dram__bytes_read + write of one launch, ncu --set full (profiles/)
+        gru_kernel = (tj and tj.get("kernel")) or gru_kernel   # the GRU kernel the launch code picks at this grid size
     except Exception:
         pass
     share = stages["gru"]["ms_per_step"] / sum(v["ms_per_step"] for v in stages.values())
-    roofline = dict(bound="tensor", kernel="fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)", achieved=gru_tf, peak=peaks["bf16_burst"],
+    roofline = dict(bound="tensor", kernel=gru_kernel, achieved=gru_tf, peak=peaks["bf16_burst"],
                     unit="TFLOP/s", frac=gru_tf / peaks["bf16_burst"], traffic=traffic, peak_source=peaks["source"] + " bf16 burst",
                     share_of_step=share,
                     flops_per_launch=fl["gru"] * B, us_per_launch=gru_us,
