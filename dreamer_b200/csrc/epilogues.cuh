@@ -330,6 +330,16 @@ struct EpiLnSiluN4T {
         v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
       }
     }
+    __nv_bfloat16* orow = p.out + (long)(p.out_row0 + slot * p.out_y_stride + m) * p.ld_out + 64 * cr + c0;
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 && (p.ld_out & 7) == 0) {      // uniform over the CTA: every row is 16-byte aligned
+      // this thread's 16 activations are 32 contiguous bytes of its row: two 16-byte stores straight from registers (whole
+      // sectors), instead of a shared-memory transpose, a barrier and a coalesced copy-out -- the tile is only 64 columns wide
+      if (mine > 0 && m < g.M) {
+        *reinterpret_cast<uint4*>(orow) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(orow + 8) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
+      return;
+    }
     tile_put<16>(tile, pitch, row, c0, v);
     epi_bar_sync();
     if (mine > 0)
