@@ -15,3 +15,10 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 t0 = time.perf_counter(); a.record(); total, _ = wm.loss_forward(obs, act, rew, cont, uniforms=u); b.record(); t1 = time.perf_counter()
 torch.cuda.synchronize()
 print(f"wm loss forward B={B} T={T}: host enqueue {1e3*(t1-t0):.2f} ms, device {a.elapsed_time(b):.2f} ms, loss {total.item():.4f}")
+import statistics
+ts = []
+for _ in range(20):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); wm.loss_forward(obs, act, rew, cont, uniforms=u); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+print(f"median of 20: device {statistics.median(ts):.3f} ms (min {min(ts):.3f})")
