@@ -384,15 +384,11 @@ struct EpiGru {
       sm[3 * U + i] = ok ? __ldg(p.b_hh + 2 * D + u) : 0.f;
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
-                                             int row, int part, int slot, int tid) {
-    const int u0 = slot * U;
-    const int D = p.D;
-    const int m0 = m - row;   // first row of this tile (the CTA-pair kernel remaps tiles, so not blockIdx.x * BM)
+  // h_prev tile [128 x U] -> smem (pitch U + 4), coalesced: consecutive threads on consecutive 16 bytes of a row
+  static constexpr int HP_OFF = 4 * U;   // float offset inside the epilogue scratch, behind the tile constants (U = 32: 18 KB)
+  static __device__ __forceinline__ void load_hprev(const Params& p, const GemmCommon& g, int u0, int m0, float* hp_tile, int tid) {
     constexpr int pitch = U + 4;
-    // h_prev tile [128 x U] -> smem, coalesced (consecutive threads on consecutive 16 bytes of a row)
-    float* hp_tile = tile + BM * pitch;
-    const int nvalid = min(U, D - u0);
+    const int nvalid = min(U, p.D - u0);
     for (int i = tid; i < BM * (U / 4); i += EPI_THREADS) {
       const int r = i / (U / 4), cc = (i % (U / 4)) * 4;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -403,7 +399,21 @@ struct EpiGru {
       }
       *reinterpret_cast<float4*>(hp_tile + r * pitch + cc) = x;
     }
-    epi_bar_sync();           // h_prev tile visible
+  }
+  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    const int u0 = slot * U;
+    const int D = p.D;
+    const int m0 = m - row;   // first row of this tile (the CTA-pair kernel remaps tiles, so not blockIdx.x * BM)
+    constexpr int pitch = U + 4;
+    const int nvalid = min(U, D - u0);
+    // h_prev tile [128 x U]: already in the epilogue scratch (fetched under the main loop, load_hprev below), else staged now
+    // in the idle pipeline buffers
+    float* hp_tile = g.hp_pre ? sm + HP_OFF : tile + BM * pitch;
+    if (!g.hp_pre) {
+      load_hprev(p, g, u0, m0, hp_tile, tid);
+      epi_bar_sync();           // h_prev tile visible
+    }
 #pragma unroll 1
     for (int ps = 0; ps < PASSES; ++ps) {
       const int c = (ps * EPI_PARTS + part) * UP;

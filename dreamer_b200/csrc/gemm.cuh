@@ -45,6 +45,9 @@ struct GemmCommon {
   // (255 = no class set).  Saves 2 KB of bf16 zeros per row per stage.
   const uint8_t* zi;
   int zi_ld, n_zblocks;
+  // 32-unit GRU tiles in fused_gemm_kernel: 1 = the epilogue warps fetch the tile's h_prev into the epilogue scratch while the main
+  // loop runs (the scratch's index area is free when zi == NULL), so the GRU epilogue starts with h_prev already on chip
+  int hp_pre;
 };
 
 // debug: every CTA records {entry ns, dependency-wait-over ns, exit ns, SM id} behind the 8 stage probes
@@ -269,6 +272,9 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     float* epi_sm = reinterpret_cast<float*>(smem + SL::EPI_OFF);
     Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64);   // weights-derived constants + host inputs only
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if constexpr (Epi::GRU_U == 32) {     // h_prev is final once the dependency wait is over: fetch it under the main loop
+      if (g.hp_pre) Epi::load_hprev(ep, g, slot * 32, (int)blockIdx.x * BM, epi_sm + Epi::HP_OFF, (int)threadIdx.x - 64);
+    }
     if (g.zi) {
       // ---- one-hot expander: the (otherwise idle) epilogue warps build the latent's A tiles in swizzled smem ----
       const int et = (int)threadIdx.x - 64;

@@ -633,6 +633,7 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
     EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_ksplit<32>(g, p, mt, m->gru_tiles2[0], st);
   }
+  g.hp_pre = (U == 32 && !g.zi) ? 1 : 0;   // fused_gemm_kernel only: h_prev tile prefetched into the epilogue scratch (18 of its 20 KB)
 #define DRM_GRU_LAUNCH(UU, CC)                                                                              \
   {                                                                                                         \
     typename EpiGru<UU, CC>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D}; \
