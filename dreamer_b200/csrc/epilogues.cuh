@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_const32(float (&v)[32], const float* c) {
 // 119-137), whose GEMM rows are pixels.
 // ------------------------------------------------------------------------------------------
 struct EpiPlain {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;       // [slots_or_tiles * bn] when bias_per_slot, else [N]; or NULL
     float* out_f32;          // [rows, ld_f32] or NULL
@@ -50,11 +50,11 @@ struct EpiPlain {
     int phases;              // 0: blockIdx.y tiles N;  1: blockIdx.y = transposed-conv phase (all tiles write columns [0, N))
     RowMap rm;               // output row mapping (rm.p2 is overwritten with the phase when phases = 1)
   };
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     const int n0 = p.phases ? 0 : slot * g.bn;
     for (int i = tid; i < 256; i += EPI_THREADS) sm[i] = (p.bias && i < g.bn && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const int n0 = p.phases ? 0 : slot * g.bn;
     const int ncols = (g.bn + 31) & ~31;   // whole 32-column chunks are staged
@@ -78,7 +78,7 @@ struct EpiPlain {
     epi_bar_sync();
     RowMap rm = p.rm;
     if (p.phases) rm.p2 = slot;
-    tile_copy_out(tile, pitch, ncols, min(g.bn, p.N - n0), (int)blockIdx.x * BM, g.M, p.out_f32 ? p.out_f32 + n0 : nullptr, p.ld_f32,
+    tile_copy_out(tile, pitch, ncols, min(g.bn, p.N - n0), (m - row), g.M, p.out_f32 ? p.out_f32 + n0 : nullptr, p.ld_f32,
                   p.out_bf16 ? p.out_bf16 + n0 : nullptr, p.ld_bf16, tid, rm);
   }
 };
@@ -102,7 +102,7 @@ struct EpiPlainS : EpiPlain {
 // ------------------------------------------------------------------------------------------
 template <bool HAS_ADD>
 struct EpiLnSiluT {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;   // [slots * bn]
     const float* gamma;  // [slots * bn]
@@ -115,7 +115,7 @@ struct EpiLnSiluT {
     float eps;
     int cstride;         // bias / gamma / beta entries per slot
   };
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     for (int i = tid; i < 256; i += EPI_THREADS) {
       const bool ok = i < p.n_valid;
       sm[i] = ok ? __ldg(p.bias + slot * p.cstride + i) : 0.f;
@@ -137,7 +137,7 @@ struct EpiLnSiluT {
   }
   // LayerNorm + SiLU of this thread's 64 columns; every 32-column chunk of the ceil64(n_valid) output columns goes to emit(c, v).
   template <class Emit>
-  static __device__ __forceinline__ void normalise(const Params& p, const GemmCommon& g, float* sm, uint32_t taddr, int m, int row,
+  static __device__ __forceinline__ void normalise(const Params& p, const TileG& g, float* sm, uint32_t taddr, int m, int row,
                                                    int part, int ncols, Emit&& emit) {
     const int nv = p.n_valid;
     const int c0 = part * 64;
@@ -202,13 +202,13 @@ struct EpiLnSiluT {
       emit(c, v);
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const int ncols = min(p.ld_out, (p.n_valid + 63) & ~63);  // the consumer reads ceil64(n_valid) columns: pad with zeros
     const int pitch = ncols + 4;
     normalise(p, g, sm, taddr, m, row, part, ncols, [&](int c, float (&v)[32]) { tile_put<32>(tile, pitch, row, c, v); });
     epi_bar_sync();
-    tile_copy_out(tile, pitch, ncols, ncols, (int)blockIdx.x * BM, g.M, nullptr, 0,
+    tile_copy_out(tile, pitch, ncols, ncols, (m - row), g.M, nullptr, 0,
                   p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out, p.ld_out, tid);
   }
 };
@@ -225,10 +225,10 @@ using EpiLnSiluAdd = EpiLnSiluT<true>;
 // ------------------------------------------------------------------------------------------
 template <bool HAS_ADD>
 struct EpiLnSiluN4T {
-  static constexpr int B_ROWS_MAX = 64, STAGES = 2, KPS = 4, TMEM_COLS = 64, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 4;   // 2 stages x 4 k-blocks x 24 KB in flight; one full / empty handshake per 4 k-blocks
+  static constexpr int B_ROWS_MAX = 64, STAGES = 2, KPS = 4, TMEM_COLS = 64, GRU_U = 0, MIN_CTAS = 1, CLUSTER_N = 4;   // 2 stages x 4 k-blocks x 24 KB in flight; one full / empty handshake per 4 k-blocks
   using Params = typename EpiLnSiluT<HAS_ADD>::Params;
   static constexpr int XST = 2560;   // float offset of the cross-CTA statistics [4 ranks][128 rows][2]
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     const int cr = (int)cluster_ctarank();
     for (int i = tid; i < 64; i += EPI_THREADS) {
       const int col = 64 * cr + i;
@@ -239,7 +239,7 @@ struct EpiLnSiluN4T {
     }
   }
   static __device__ __forceinline__ int cnt_of(int nv, int first, int width) { return max(0, min(width, nv - first)); }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const int nv = p.n_valid;
     const int cr = (int)cluster_ctarank();
@@ -343,7 +343,7 @@ struct EpiLnSiluN4T {
     tile_put<16>(tile, pitch, row, c0, v);
     epi_bar_sync();
     if (mine > 0)
-      tile_copy_out(tile, pitch, 64, mine, (int)blockIdx.x * BM, g.M, nullptr, 0,
+      tile_copy_out(tile, pitch, 64, mine, (m - row), g.M, nullptr, 0,
                     p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out + 64 * cr, p.ld_out, tid);
   }
 };
@@ -354,9 +354,8 @@ using EpiLnSiluAddN4 = EpiLnSiluN4T<true>;
 // GRU gates + state update (nn.GRUCell, SequenceModel.py:13-24), U hidden units per tile,
 // U / 4 units per thread.  TMEM columns: [r | z | n_x | n_h], each U wide.
 // ------------------------------------------------------------------------------------------
-template <int U, int CM_ = 1>
+template <int U>
 struct EpiGru {
-  static constexpr int CLUSTER_M = CM_;   // 2: pairs of m-tiles share the weight tile through TMA multicast (opt-in experiment)
   static constexpr int CLUSTER_N = 1;
   // Two CTAs per SM (3 x 28 KB or 2 x 40 KB of stages, 128 / 256 TMEM columns each): one CTA's epilogue and prologue overlap
   // the other's main loop, which keeps the per-SM operand ingress -- the limiter of this stage -- busy.
@@ -373,7 +372,7 @@ struct EpiGru {
     int ld_s, D;
   };
   // sm: [b_r (U) | b_z (U) | b_in (U) | b_hn (U)] with b_r = b_ir + b_hr, b_z = b_iz + b_hz
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     const int D = p.D;
     for (int i = tid; i < U; i += EPI_THREADS) {
       const int u = slot * U + i;
@@ -386,7 +385,7 @@ struct EpiGru {
   }
   // h_prev tile [128 x U] -> smem (pitch U + 4), coalesced: consecutive threads on consecutive 16 bytes of a row
   static constexpr int HP_OFF = 4 * U;   // float offset inside the epilogue scratch, behind the tile constants (U = 32: 18 KB)
-  static __device__ __forceinline__ void load_hprev(const Params& p, const GemmCommon& g, int u0, int m0, float* hp_tile, int tid) {
+  static __device__ __forceinline__ void load_hprev(const Params& p, const TileG& g, int u0, int m0, float* hp_tile, int tid) {
     constexpr int pitch = U + 4;
     const int nvalid = min(U, p.D - u0);
     for (int i = tid; i < BM * (U / 4); i += EPI_THREADS) {
@@ -400,7 +399,7 @@ struct EpiGru {
       *reinterpret_cast<float4*>(hp_tile + r * pitch + cc) = x;
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const int u0 = slot * U;
     const int D = p.D;
@@ -445,7 +444,7 @@ struct EpiGru {
 // owns 2 of them.
 // ------------------------------------------------------------------------------------------
 struct EpiCat {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;     // [R * 32]
     const float* uniforms; // [M, R] for this step, or NULL (logits only)
@@ -456,24 +455,22 @@ struct EpiCat {
     const float* addend;   // optional fp32 [M, ld_addend] added to the logits (unused by the prior)
     long ld_latent, ld_logits, ld_idx, ld_addend;
     int ld_s, R;
-    RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z and zi always use the GEMM row
-    uint8_t* zi;           // sampled indices next to the state buffer [M, R] (feeds the one-hot expander of later stages) or NULL
+    RowMap rm;             // row mapping of the fp32 outputs (latent, logits, idx); s_z always uses the GEMM row
   };
   // A tile is g.bn = 128 or 256 columns = G = 4 or 8 latent rows of 32 classes; thread (row, part) owns groups part, part + 4.
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     const int G = g.bn >> 5;
     for (int i = tid; i < g.bn; i += EPI_THREADS) sm[i] = (slot * g.bn + i < p.R * 32) ? __ldg(p.bias + slot * g.bn + i) : 0.f;
     // this tile's uniforms [128 rows x G latent rows] -> sm[256 ..), coalesced row segments
-    const int m0 = (int)blockIdx.x * BM;
     for (int i = tid; i < BM * G; i += EPI_THREADS) {
       const int r = i / G, gi = i - r * G;
       const int lrow = slot * G + gi;
       sm[256 + r * 8 + gi] = (p.uniforms && m0 + r < g.M && lrow < p.R) ? __ldg(p.uniforms + (long)(m0 + r) * p.R + lrow) : 0.f;
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
-    const int m0 = (int)blockIdx.x * BM;
+    const int m0 = (m - row);
     const int G = g.bn >> 5;
     const int col0 = slot * g.bn;                                  // first logit column of this tile
     const int ncols = max(0, min(g.bn, p.R * 32 - col0));
@@ -532,12 +529,6 @@ struct EpiCat {
         if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * G + gi] = idx_sm[i];
       }
     }
-    if (p.zi) {
-      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
-        const int r = i >> 3, gi = i & 7;
-        if (m0 + r < g.M && gi < ngrp) p.zi[(long)(m0 + r) * p.R + slot * G + gi] = idx_sm[i];
-      }
-    }
     if (p.s_z) {
       for (int i = tid; i < BM * 32; i += EPI_THREADS) {    // one uint4 (8 bf16) per item
         const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
@@ -561,7 +552,7 @@ enum HeadKind { HEAD_BUCKET = 0, HEAD_SIGMOID = 1, HEAD_ACTOR = 2 };
 constexpr int MAX_HEADS = 5;
 
 struct EpiHeads {
-  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_M = 1, CLUSTER_N = 1;
+  static constexpr int B_ROWS_MAX = 256, STAGES = 4, TMEM_COLS = 256, GRU_U = 0, MIN_CTAS = 1, CLUSTER_N = 1;
   struct Params {
     const float* bias;  // [MAX_HEADS * 256]
     int kind[MAX_HEADS];
@@ -579,18 +570,18 @@ struct EpiHeads {
     RowMap rm;             // row mapping of the bucket / sigmoid outputs
   };
   // sm: [bias (256) | buckets (256)]
-  static __device__ __forceinline__ void stage(const Params& p, const GemmCommon& g, int slot, float* sm, int tid) {
+  static __device__ __forceinline__ void stage(const Params& p, const TileG& g, int slot, float* sm, int tid, int m0) {
     const bool bucket = p.kind[slot] == HEAD_BUCKET;
     for (int i = tid; i < 256; i += EPI_THREADS) {
       sm[i] = __ldg(p.bias + slot * 256 + i);
       sm[256 + i] = (bucket && i < p.NB) ? __ldg(p.buckets[slot] + i) : 0.f;
     }
   }
-  static __device__ __forceinline__ void run(const Params& p, const GemmCommon& g, float* sm, float* tile, uint32_t taddr, int m,
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
                                              int row, int part, int slot, int tid) {
     const bool live = m < g.M;
     const int kind = p.kind[slot];
-    const int m0 = (int)blockIdx.x * BM;
+    const int m0 = (m - row);
     if (kind == HEAD_BUCKET) {
       const int NB = p.NB;
       const int c0 = part * 64;

@@ -24,11 +24,17 @@ constexpr int EPI_THREADS = 128 * EPI_PARTS;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
-struct GemmCommon {
-  CUtensorMap tmA;   // activations, box {64, 128}
-  CUtensorMap tmB;   // packed weights, box {64, bn}
+// What an epilogue functor needs to know about the tile it finishes (the launch-per-stage kernels pass their GemmCommon,
+// the persistent rollout kernel builds one per task).
+struct TileG {
   int M;             // valid rows (epilogues guard their global stores with m < M)
   int bn;            // B rows per tile == UMMA N of the (first) accumulator group
+  int hp_pre;        // 32-unit GRU tiles: 1 = the tile's h_prev was fetched into the epilogue scratch under the main loop
+};
+
+struct GemmCommon : TileG {
+  CUtensorMap tmA;   // activations, box {64, 128}
+  CUtensorMap tmB;   // packed weights, box {64, bn}
   int b_slot_rows;   // B rows between consecutive slots (0: == bn)
   int a_row0;        // A row of tile (x = 0, slot = 0)
   int a_y_stride;    // extra A rows per slot
@@ -40,14 +46,6 @@ struct GemmCommon {
   int a_bytes;             // bytes one A k-block load delivers: 0 = the full 128-row tile; SMALL_A_ROWS * 128 when tmA has a short box
   unsigned long long* cta_times;  // debug: per-CTA {entry, wait over, exit, smid} records, or NULL
   unsigned long long* timeline;  // debug: CTA (0,0) writes {globaltimer ns, clock64} pairs at 8 probe points, or NULL
-  // One-hot A operand: when zi != NULL the first n_zblocks A k-blocks (2 latent rows of 32 classes each) are NOT loaded by
-  // TMA; the epilogue warps build them in swizzled shared memory from the sampled indices zi[row * zi_ld + latent_row]
-  // (255 = no class set).  Saves 2 KB of bf16 zeros per row per stage.
-  const uint8_t* zi;
-  int zi_ld, n_zblocks;
-  // 32-unit GRU tiles in fused_gemm_kernel: 1 = the epilogue warps fetch the tile's h_prev into the epilogue scratch while the main
-  // loop runs (the scratch's index area is free when zi == NULL), so the GRU epilogue starts with h_prev already on chip
-  int hp_pre;
 };
 
 // debug: every CTA records {entry ns, dependency-wait-over ns, exit ns, SM id} behind the 8 stage probes
@@ -96,17 +94,14 @@ struct GemmSmem {
 
 // Epi must provide:
 //   static constexpr int B_ROWS_MAX, STAGES, TMEM_COLS;  static constexpr int GRU_U (0 = plain)
-//   static constexpr int CLUSTER_M (1 or 2).  CLUSTER_M = 2: the two CTAs of a cluster are neighbouring m-tiles of the same
-//       n-tile; each loads its own A tile and HALF of the shared B tile, multicast to both (tmB then has box rows bn / 2).
-//       A stage is refilled only after BOTH consumers released it (empty barriers count 2, released by a multicast commit).
 //   static constexpr int CLUSTER_N (1 or 4).  CLUSTER_N = 4: the four CTAs of a cluster (gridDim.z) each own bn = 64 columns
 //       of one 256-column tile; the epilogue exchanges row statistics through distributed shared memory and every thread of
 //       the cluster takes part in ONE barrier.cluster between the two epilogue halves.
 //   struct Params;
-//   static __device__ void stage(const Params&, const GemmCommon&, int slot, float* sm, int tid);
+//   static __device__ void stage(const Params&, const TileG&, int slot, float* sm, int tid, int m0);
 //       -- the EPI_THREADS epilogue threads copy the tile's constants (biases, LN affine, buckets)
 //          into shared memory while the main loop runs
-//   static __device__ void run(const Params&, const GemmCommon&, float* sm, float* tile, uint32_t taddr, int m,
+//   static __device__ void run(const Params&, const TileG&, float* sm, float* tile, uint32_t taddr, int m,
 //                              int row, int part, int slot, int tid);
 //       -- sm + 1024 = exchange scratch [.][128 rows]; `tile` = the pipeline stages' shared memory, free once the
 //          accumulator is complete, used to transpose the output tile so that global stores are fully coalesced
@@ -118,7 +113,6 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   constexpr int KPS = kps_of<Epi>::value;
   using SL = GemmSmem<Epi::B_ROWS_MAX, Epi::STAGES, KPS>;
   constexpr int STAGES = Epi::STAGES;
-  constexpr int CM = Epi::CLUSTER_M;
   constexpr int CN = Epi::CLUSTER_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -131,7 +125,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int nk = g.nka0 + g.nka1;
   const int slot = g.n_slots > 0 ? g.y_slot[blockIdx.y] : (int)blockIdx.y;
-  const int a_row = g.a_row0 + slot * g.a_y_stride + (int)blockIdx.x * BM;
+  const int m0 = (int)blockIdx.x * BM;
+  const int a_row = g.a_row0 + slot * g.a_y_stride + m0;
   const int b_row = slot * (g.b_slot_rows ? g.b_slot_rows : g.bn) + (CN > 1 ? (int)cluster_ctarank() * g.bn : 0);
 
   // (everything this CTA reads that an earlier stage produced -- activations via TMA, h_prev -- is touched only after
@@ -142,8 +137,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     tma_prefetch_desc(&g.tmA);
     tma_prefetch_desc(&g.tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], g.zi ? 2 : 1);   // + the one-hot expander's arrival
-      mbar_init(&empty[s], CM);
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
@@ -155,7 +150,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   // their prologue and then block in griddepcontrol.wait until this grid has finished, so a dependent CTA that reached an SM before
   // a CTA of this grid had allocated could starve it of columns for good.
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  if constexpr (CM > 1 || CN > 1) cluster_sync_all();   // peers are resident and their barriers initialised before any remote access
+  if constexpr (CN > 1) cluster_sync_all();   // peers are resident and their barriers initialised before any remote access
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 2) asm volatile("griddepcontrol.wait;\n" ::: "memory");  // producer / MMA warps; epilogue warps wait after staging
@@ -166,7 +161,6 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
       cta_probe(g.cta_times, 1);
       const uint32_t tx_b = (uint32_t)g.bn * BK * 2;
       const uint32_t tx_a = g.a_bytes ? (uint32_t)g.a_bytes : (uint32_t)A_STAGE_BYTES;
-      const int nz = g.zi ? g.n_zblocks : 0;
       if constexpr (KPS > 1) {
         // KPS k-blocks per stage: one full / empty handshake per KPS k-blocks.  The main loop of the small-grid stages is bound by
         // the MMA thread's per-handshake chain (~210 ns), not by operand delivery, so halve the handshakes.
@@ -186,24 +180,18 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
           if (st == 0) probe(g, 2);
         }
       } else {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* sa = smem + s * SL::STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
-        mbar_expect_tx(&full[s], kb < nz ? tx_b : tx_b + tx_a);
-        if (kb >= nz) tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);   // one-hot k-blocks: A is built in place by the expander
-        if constexpr (CM == 1) {
+        for (int kb = 0; kb < nk; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sa = smem + s * SL::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
+          mbar_expect_tx(&full[s], tx_b + tx_a);
+          tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
           tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
-        } else {
-          const int half = g.bn >> 1;
-          const int cr = (int)cluster_ctarank();
-          tma_load_2d_mc(sb + cr * half * BK * 2, &g.tmB, kb * BK, b_row + cr * half, &full[s], (uint16_t)0x3);
+          if (kb == 0) probe(g, 2);
         }
-        if (kb == 0) probe(g, 2);
-      }
       }
     }
   } else if (warp == 1) {
@@ -226,93 +214,53 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
           umma_commit(&empty[s]);
         }
       } else {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        if (kb == 0) probe(g, 3);
-        const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-        if constexpr (Epi::GRU_U == 0) {
-          const uint32_t idesc = umma_idesc_bf16(g.bn);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        } else {
-          // GRU tile: B rows = [r(U) | z(U) | n(U)], TMEM cols = [r | z | n_x | n_h].
-          // x-part k-blocks feed r, z, n_x in one N = 3U MMA; h-part k-blocks feed r, z (N = 2U)
-          // and n_h (N = U, B rows 2U.., TMEM cols 3U..) because r multiplies only W_hn h.
-          constexpr int U = Epi::GRU_U;
-          if (kb < g.nka0) {
-            const uint32_t idesc = umma_idesc_bf16(3 * U);
+        for (int kb = 0; kb < nk; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (kb == 0) probe(g, 3);
+          const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          if constexpr (Epi::GRU_U == 0) {
+            const uint32_t idesc = umma_idesc_bf16(g.bn);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           } else {
-            const uint32_t idesc_rz = umma_idesc_bf16(2 * U);
-            const uint32_t idesc_n = umma_idesc_bf16(U);
-            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            // GRU tile: B rows = [r(U) | z(U) | n(U)], TMEM cols = [r | z | n_x | n_h].
+            // x-part k-blocks feed r, z, n_x in one N = 3U MMA; h-part k-blocks feed r, z (N = 2U)
+            // and n_h (N = U, B rows 2U.., TMEM cols 3U..) because r multiplies only W_hn h.
+            constexpr int U = Epi::GRU_U;
+            if (kb < g.nka0) {
+              const uint32_t idesc = umma_idesc_bf16(3 * U);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
-              umma_bf16(tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > g.nka0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            } else {
+              const uint32_t idesc_rz = umma_idesc_bf16(2 * U);
+              const uint32_t idesc_n = umma_idesc_bf16(U);
+              const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
+                umma_bf16(tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > g.nka0 || k > 0) ? 1u : 0u);
+              }
             }
           }
+          umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
         }
-        if constexpr (CM == 1) umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
-        else umma_commit_mc(&empty[s], (uint16_t)0x3);   // ... in both CTAs: the peer's producer also writes into it
-      }
       }
       umma_commit(tmem_full);    // accumulator complete
       probe(g, 4);
     }
   } else {
     float* epi_sm = reinterpret_cast<float*>(smem + SL::EPI_OFF);
-    Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64);   // weights-derived constants + host inputs only
+    Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64, m0);   // weights-derived constants + host inputs only
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     if constexpr (Epi::GRU_U == 32) {     // h_prev is final once the dependency wait is over: fetch it under the main loop
-      if (g.hp_pre) Epi::load_hprev(ep, g, slot * 32, (int)blockIdx.x * BM, epi_sm + Epi::HP_OFF, (int)threadIdx.x - 64);
-    }
-    if (g.zi) {
-      // ---- one-hot expander: the (otherwise idle) epilogue warps build the latent's A tiles in swizzled smem ----
-      const int et = (int)threadIdx.x - 64;
-      uint8_t* zi_sm = smem + SL::ZI_OFF;
-      // this tile's indices: 128 rows x (2 * n_zblocks <= 32) bytes; rows >= M and missing latent rows: 255 = no class set
-      for (int i = et; i < BM * 32; i += EPI_THREADS) {
-        const int rr = i >> 5, lr = i & 31;
-        const bool ok = (int)blockIdx.x * BM + rr < g.M && lr < 2 * g.n_zblocks;
-        zi_sm[i] = ok ? __ldg(g.zi + (long)(a_row + rr) * g.zi_ld + lr) : (uint8_t)255;
-      }
-      epi_bar_sync();
-      const int r = et >> 2, q4 = et & 3;             // row, and which 16 of the k-block's 64 columns
-      const int cls0 = (q4 & 1) * 16;                  // first class of this thread's span inside its latent row
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (kb < g.n_zblocks) {
-          mbar_wait(&empty[s], ph ^ 1u);
-          const int hit = (int)zi_sm[r * 32 + 2 * kb + (q4 >> 1)] - cls0;   // 0..15 if the sampled class is in this span
-          uint8_t* rowp = smem + s * SL::STAGE_BYTES + r * 128;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int e0 = hit - 8 * c;               // element inside this 16-byte chunk
-            uint4 v;
-            v.x = e0 == 0 ? 0x3F80u : (e0 == 1 ? 0x3F800000u : 0u);
-            v.y = e0 == 2 ? 0x3F80u : (e0 == 3 ? 0x3F800000u : 0u);
-            v.z = e0 == 4 ? 0x3F80u : (e0 == 5 ? 0x3F800000u : 0u);
-            v.w = e0 == 6 ? 0x3F80u : (e0 == 7 ? 0x3F800000u : 0u);
-            *reinterpret_cast<uint4*>(rowp + (((2 * q4 + c) ^ (r & 7)) << 4)) = v;   // SWIZZLE_128B chunk position
-          }
-          fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
-          epi_bar_sync();
-          if (et == 0) mbar_arrive(&full[s]);
-        } else if (et == 0) {                          // keep the barrier's arrival count uniform for TMA-fed k-blocks
-          mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive(&full[s]);
-        }
-      }
+      if (g.hp_pre) Epi::load_hprev(ep, g, slot * 32, m0, epi_sm + Epi::HP_OFF, (int)threadIdx.x - 64);
     }
     epi_bar_sync();                                     // epilogue warps only
     mbar_wait(tmem_full, 0);
@@ -321,7 +269,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
     const int q = warp & 3;                             // TMEM lane quadrant this warp may access
     const int part = (warp - 2) >> 2;                   // which quarter of the columns
     const int row = q * 32 + lane;
-    const int m = (int)blockIdx.x * BM + row;
+    const int m = m0 + row;
     Epi::run(ep, g, epi_sm, reinterpret_cast<float*>(smem), tmem + ((uint32_t)(q * 32) << 16), m, row, part, slot,
              (int)threadIdx.x - 64);
     if (threadIdx.x == 64) probe(g, 6);
@@ -335,7 +283,6 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CM > 1) cluster_sync_all();   // the peer may still arrive on / multicast into this CTA's shared memory
   if (warp == 1) tmem_dealloc(tmem, Epi::TMEM_COLS);
   if (threadIdx.x == 32) { probe(g, 7); cta_probe(g.cta_times, 2); }
 }

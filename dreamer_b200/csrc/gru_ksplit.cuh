@@ -30,7 +30,7 @@ struct GruKsSmem {
 
 template <int U>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename EpiGru<U, 1>::Params ep) {
+gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename EpiGru<U>::Params ep) {
   using SL = GruKsSmem<U>;
   constexpr int STAGES = SL::STAGES;
   constexpr int UP = U / 4;                            // units per epilogue thread: 8 (U = 32) or 12 (U = 48)
@@ -108,7 +108,7 @@ gru_ksplit_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const bool epi = warp >= 2;
   const bool mine = epi && (row >> 6) == rank;       // rows 0..63 are finished by rank 0, rows 64..127 by rank 1
   if (epi) {
-    EpiGru<U, 1>::stage(ep, g, slot, cst, tid);
+    EpiGru<U>::stage(ep, g, slot, cst, tid, (int)blockIdx.x * BM);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     epi_bar_sync();
     mbar_wait(tfull, 0);

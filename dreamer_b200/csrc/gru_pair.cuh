@@ -60,8 +60,8 @@ struct GruPairSmem {
 // grid (2 * ceil(m_tiles / 2), n_tiles), cluster (2, 1, 1).  g.tmB must have box rows U / 2.
 template <int U>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename EpiGru<U, 1>::Params ep) {
-  using Epi = EpiGru<U, 1>;
+gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ typename EpiGru<U>::Params ep) {
+  using Epi = EpiGru<U>;
   using SL = GruPairSmem<U>;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -160,7 +160,7 @@ gru_pair_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ ty
     }
   } else {
     float* epi_sm = reinterpret_cast<float*>(smem + SL::EPI_OFF);
-    Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64);
+    Epi::stage(ep, g, slot, epi_sm, (int)threadIdx.x - 64, m_tile * BM);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     epi_bar_sync();
     mbar_wait(tmem_full, 0);

@@ -64,40 +64,19 @@ __global__ void f32_to_bf16_pad_kernel(__nv_bfloat16* __restrict__ dst, int ld_d
 // debug probe buffer: [DRM_STAGE_COUNT][16] u64 (drm_debug_timeline)
 static unsigned long long* g_timeline = nullptr;
 
-// Runtime options (drm_set_option; initial values from the environment): experiments measured in profiles/README.md.
+// Runtime options (drm_set_option): alternative kernel paths, all producing the same results (profiles/README.md).
 struct Options {
-  int zidx;        // 1: build the one-hot latent A tiles in smem from sampled indices instead of streaming them (default 0: slower)
-  int multicast;   // 1: GRU stage in clusters of 2 m-tiles with the weight tile halves multicast by TMA (default 0: not faster)
-  int ln_cluster;  // 1: LN stages of small grids split over clusters of 4 CTAs (default 1)
-  int gru_ksplit;  // 1: tiny grids split the GRU tile's K range over a 2-CTA cluster (default 1)
-  int gru_ksplit_mt;  // ... up to this many m-tiles (default 1)
-  int conv_persist;  // 1: narrow conv layers on the persistent GEMM (default 1)
-  int chain2;      // 1: small grids run (LN layer -> output stage) pairs as one kernel, activations kept in shared memory (default 0)
-  int gru_pair;    // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
-  int small_a;     // 1: stages with <= 32 rows load 32-row A boxes (default 1)
-  int lanes;       // rollouts: 0 / 1 one lane (default), 2 two half-batches on two internal streams
-  int chain;       // 1: small grids run each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel (default 1)
-  int gru_u;       // 0: automatic GRU tile width, else 32 / 64
+  int ln_cluster = 1;  // LN stages of small grids split over clusters of 4 CTAs
+  int gru_ksplit = 1;  // single-m-tile grids split the GRU tile's K range over a 2-CTA cluster
+  int conv_persist = 1;  // narrow conv layers on the persistent GEMM
+  int gru_pair = -1;   // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
+  int small_a = 1;     // stages with <= 32 rows load 32-row A boxes
+  int gru_u = 0;       // 0: automatic GRU tile width, else 32 / 64
+  int gru_band = 0;    // CTA-pair GRU kernel: m-tiles per band of the tile order (0 = 16)
+  int persist = 1;     // rollouts: one persistent kernel for the whole horizon when the schedule fits the machine (rollout_persist.cuh)
 };
 static Options& opts() {
-  static Options o = [] {
-    Options x;
-    x.zidx = getenv("DRM_ZIDX") != nullptr;
-    x.multicast = getenv("DRM_MULTICAST") != nullptr;
-    x.ln_cluster = getenv("DRM_NO_LN_CLUSTER") == nullptr;
-    x.chain = getenv("DRM_CHAIN") != nullptr;
-    x.small_a = getenv("DRM_NO_SMALL_A") == nullptr;
-    x.chain2 = getenv("DRM_CHAIN2") != nullptr;
-    x.conv_persist = getenv("DRM_NO_CONV_PERSIST") == nullptr;
-    x.gru_ksplit = getenv("DRM_NO_GRU_KSPLIT") == nullptr;
-    x.gru_ksplit_mt = getenv("DRM_GRU_KSPLIT_MT") ? atoi(getenv("DRM_GRU_KSPLIT_MT")) : 1;
-    x.gru_pair = getenv("DRM_GRU_PAIR") ? atoi(getenv("DRM_GRU_PAIR")) : -1;
-    x.lanes = getenv("DRM_LANES") ? atoi(getenv("DRM_LANES")) : 0;
-    const char* e = getenv("DRM_GRU_U");
-    x.gru_u = e ? atoi(e) : 0;
-    if (x.gru_u != 32 && x.gru_u != 64) x.gru_u = 0;
-    return x;
-  }();
+  static Options o;
   return o;
 }
 
@@ -128,9 +107,9 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (Epi::CLUSTER_M > 1 || Epi::CLUSTER_N > 1) {
-      attr[na].id = cudaLaunchAttributeClusterDimension;   // x: pairs of m-tiles (multicast); z: four column quarters of one LN tile
-      attr[na].val.clusterDim.x = Epi::CLUSTER_M; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = Epi::CLUSTER_N;
+    if (Epi::CLUSTER_N > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;   // z: four column quarters of one LN tile
+      attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = Epi::CLUSTER_N;
       ++na;
     }
     if (!profile_on()) {
@@ -153,7 +132,7 @@ static int launch_gemm(const GemmCommon& g, const typename Epi::Params& ep, dim3
 namespace drm {
 
 template <int U>
-static int launch_gru_ksplit(const GemmCommon& g, const typename EpiGru<U, 1>::Params& ep, int mt, int tiles, cudaStream_t st) {
+static int launch_gru_ksplit(const GemmCommon& g, const typename EpiGru<U>::Params& ep, int mt, int tiles, cudaStream_t st) {
   using SL = GruKsSmem<U>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -185,7 +164,7 @@ static int launch_gru_ksplit(const GemmCommon& g, const typename EpiGru<U, 1>::P
 }
 
 template <int U>
-static int launch_gru_pair(const GemmCommon& g, const typename EpiGru<U, 1>::Params& ep, int mt, int tiles, cudaStream_t st) {
+static int launch_gru_pair(const GemmCommon& g, const typename EpiGru<U>::Params& ep, int mt, int tiles, cudaStream_t st) {
   using SL = GruPairSmem<U>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -247,9 +226,8 @@ struct drm_rssm {
   float *bk_rew, *bk_crit;       // [NB]
   CUtensorMap tmWp1q, tmWp2q, tmWh1q, tmWh2q;   // box rows 64: the cluster-of-4 LN stage
   CUtensorMap tmWp3h;                           // box rows 128: half-width categorical tiles for small grids
-  CUtensorMap tmWh3q;                           // box rows 64: output layer of the chained heads kernel
   CUtensorMap tmWgruQ[2];                      // box rows U / 2: the CTA-pair GRU kernel stages gate blocks and n halves separately
-  CUtensorMap tmWgru2[2], tmWgruHalf2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
+  CUtensorMap tmWgru2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
   std::vector<VecOp> vec_ops;
   std::vector<void*> allocs;
@@ -259,16 +237,16 @@ struct drm_rssm {
 
 constexpr int SMALL_A_ROWS = 32;   // box rows of the short A tensor maps (see small_a)
 
+struct drm_persist;   // schedule + hand-over counters of the persistent rollout kernel (rollout_persist.cuh)
+
 struct drm_rollout {
   drm_rssm* m;
+  drm_persist* ps = nullptr;
   int B, H, Mp;
   __nv_bfloat16* S[2];
-  uint8_t* Zi[2];              // sampled latent indices [Mp, R] next to S[i] (one-hot expander input)
   __nv_bfloat16 *Y1, *Y2;
   CUtensorMap tmS[2], tmY1, tmY2;
   CUtensorMap tmS_s[2], tmY1_s, tmY2_s;           // short-box twins (SMALL_A_ROWS rows)
-  cudaStream_t lane_st[2] = {nullptr, nullptr};   // two-lane rollouts (created on first use)
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
 };
 
@@ -435,7 +413,6 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   for (int v = 0; v < 2; ++v) {
     const int U = 32 << v;
     TRY(make_tmap_bf16_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U));
-    TRY(make_tmap_bf16_2d(&m->tmWgruHalf2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U / 2));   // multicast halves
     TRY(make_tmap_bf16_2d(&m->tmWgruQ[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, U / 2));
   }
   TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, 256, DP, DP, m->bnp1));
@@ -449,7 +426,6 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1));
   TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2));
   TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
-  TRY(make_tmap_bf16_2d(&m->tmWh3q, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 64));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rssm_destroy(m);
@@ -517,7 +493,6 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
   for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->S[i], (size_t)r->Mp * m->KS));
-  for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->Zi[i], (size_t)r->Mp * m->d.R));
   TRY(dev_alloc(r->allocs, &r->Y1, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
   TRY(dev_alloc(r->allocs, &r->Y2, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
   for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM));
@@ -535,13 +510,11 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
   return DRM_OK;
 }
 
+namespace drm { static void persist_free(drm_persist* ps); }
+
 extern "C" int drm_rollout_destroy(drm_rollout* r) {
   if (!r) return DRM_OK;
-  for (int i = 0; i < 2; ++i) {
-    if (r->lane_st[i]) cudaStreamDestroy(r->lane_st[i]);
-    if (r->ev_join[i]) cudaEventDestroy(r->ev_join[i]);
-  }
-  if (r->ev_fork) cudaEventDestroy(r->ev_fork);
+  persist_free(r->ps);
   for (void* p : r->allocs) cudaFree(p);
   delete r;
   return DRM_OK;
@@ -565,123 +538,68 @@ struct WsView {
   __nv_bfloat16 *Y1, *Y2;   // [(MAX_HEADS + 1) * slot_rows, 256]; slot 0 = prior / encoder, 1.. = heads
   int slot_rows;            // rows per Y slot
   int row0;                 // first row of this view inside S and inside every Y slot
-  uint8_t* Zi;              // sampled indices [rows, R] parallel to S (NULL: none)
   const CUtensorMap *tmS_s, *tmY1_s, *tmY2_s;   // the same buffers with a SMALL_A_ROWS-row box (NULL: none)
 };
 static WsView view_of(drm_rollout* r, int sb) {
-  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0, r->Zi[sb], &r->tmS_s[sb], &r->tmY1_s, &r->tmY2_s};
+  return WsView{&r->tmS[sb], r->S[sb], &r->tmY1, &r->tmY2, r->Y1, r->Y2, r->Mp, 0, &r->tmS_s[sb], &r->tmY1_s, &r->tmY2_s};
 }
 // Few rows (one acting environment, a 16-sequence scan step): load only SMALL_A_ROWS rows of every A k-block.  The MMA still
 // reads a 128-row tile; rows beyond the box hold stale shared memory, give garbage accumulator rows, and every epilogue writes
 // only rows < M.  Cuts the A bytes per k-block from 16 KB to 4 KB on stages that are bound by shared-memory ingress.
 static void small_a(GemmCommon& g, const CUtensorMap* small) {
-  if (small && g.M <= SMALL_A_ROWS && !g.zi && opts().small_a) {
+  if (small && g.M <= SMALL_A_ROWS && opts().small_a) {
     g.tmA = *small;
     g.a_bytes = SMALL_A_ROWS * BK * 2;
   }
 }
-// Enable the one-hot expander for the view's z k-blocks (only valid when those rows' latents were written by EpiCat).
-static void use_z_indices(drm_rssm* m, GemmCommon& g, const WsView& v) {
-  if (!opts().zidx || !v.Zi) return;
-  g.zi = v.Zi;
-  g.zi_ld = m->d.R;
-  g.n_zblocks = m->ZP / 64;
-}
-
 // GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
 static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
-                     long ld_hout, int M, cudaStream_t st, bool z_idx = false, bool allow_ksplit = false) {
-  // DRM_MULTICAST=1 selects the cluster variant (pairs of m-tiles, weight tile halves multicast by TMA).  Measured on B200 it
-  // is not faster: the stage is bound by per-SM shared-memory ingress, which multicast does not reduce (profiles/README.md).
-  const bool mc = opts().multicast != 0;
+                     long ld_hout, int M, cudaStream_t st, bool allow_ksplit = false) {
   // tile width: 64 hidden units per tile once that still fills the machine twice over (more FLOPs per operand byte), else 32
   const int mt = ceil_div(M, BM);
   int v = (mt * m->gru_tiles2[1] >= 2 * 148) ? 1 : 0;
   if (const int force = opts().gru_u) v = force == 64 ? 1 : 0;
   const int U = 32 << v;
-  GemmCommon g = common(*src.tmS, mc ? m->tmWgruHalf2[v] : m->tmWgru2[v], M, 3 * U);
+  GemmCommon g = common(*src.tmS, m->tmWgru2[v], M, 3 * U);
   g.a_row0 = src.row0;
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
-  if (z_idx && !mc) use_z_indices(m, g, src);
-  if (!mc) small_a(g, src.tmS_s);
-  const dim3 grid(mc ? round_up(mt, 2) : mt, m->gru_tiles2[v]);
+  small_a(g, src.tmS_s);
+  const dim3 grid(mt, m->gru_tiles2[v]);
   __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
   // CTA pairs (cta_group::2): two m-tiles issue one M = 256 MMA, each SM stages half of the weight tile (gru_pair.cuh).
   // Measured: 16 384 rows, D = 4096: 897 -> 1057 TFLOP/s; D = 600: 647 -> 720; 1024 rows (76 pairs of U = 32 tiles): 21.6 -> 24.4 us,
   // so the automatic choice pairs only the wide-tile (large-grid) configuration.
   const bool pair = opts().gru_pair < 0 ? v == 1 : opts().gru_pair != 0;
-  if (pair && !mc && !g.zi && mt >= 2) {
+  if (pair && mt >= 2) {
     g.tmB = m->tmWgruQ[v];
     g.a_bytes = 0;
-    { static const int band = getenv("DRM_GRU_BAND") ? atoi(getenv("DRM_GRU_BAND")) : 0; g.band = band & ~1; }
+    g.band = opts().gru_band & ~1;
     if (U == 32) {
-      EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+      EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
       return launch_gru_pair<32>(g, p, mt, m->gru_tiles2[v], st);
     }
-    EpiGru<64, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+    EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_pair<64>(g, p, mt, m->gru_tiles2[v], st);
   }
   // (allow_ksplit: the posterior scan and the step-level entry point; drm_rollout_run keeps kernels whose per-row arithmetic does
   // not depend on the batch size, so that shards of a rollout concatenate bit-exactly to the full batch)
-  if (allow_ksplit && !mc && !g.zi && opts().gru_ksplit && mt <= opts().gru_ksplit_mt && mt * m->gru_tiles2[0] <= 148) {
+  if (allow_ksplit && opts().gru_ksplit && mt <= 1 && mt * m->gru_tiles2[0] <= 148) {
     // tiny grid (the 16-sequence posterior scan, the B = 1 acting path, warm starts): x part and h part of every tile on two
     // CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh).  Measured per imagined step at D = 600: 128 rows
     // 62.1 -> 59.4 us, 256 rows 62.9 -> 65.1 us, 512 rows 66.2 -> 67.7 us, 896 rows 66.0 -> 66.8 us; a 48-unit-tile variant that
     // fits 1024 rows (104 tiles x 2 CTAs) was 8 us slower there -- so only single-m-tile grids take this path.
     g.tmB = m->tmWgru2[0]; g.bn = 96;
-    EpiGru<32, 1>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
     return launch_gru_ksplit<32>(g, p, mt, m->gru_tiles2[0], st);
   }
-  g.hp_pre = (U == 32 && !g.zi) ? 1 : 0;   // fused_gemm_kernel only: h_prev tile prefetched into the epilogue scratch (18 of its 20 KB)
-#define DRM_GRU_LAUNCH(UU, CC)                                                                              \
-  {                                                                                                         \
-    typename EpiGru<UU, CC>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D}; \
-    return launch_gemm<EpiGru<UU, CC>>(g, p, grid, st, DRM_STAGE_GRU);                                     \
-  }
+  g.hp_pre = U == 32 ? 1 : 0;   // h_prev tile prefetched into the epilogue scratch (18 of its 20 KB) under the main loop
   if (U == 32) {
-    if (mc) DRM_GRU_LAUNCH(32, 2) else DRM_GRU_LAUNCH(32, 1)
+    EpiGru<32>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+    return launch_gemm<EpiGru<32>>(g, p, grid, st, DRM_STAGE_GRU);
   }
-  if (mc) DRM_GRU_LAUNCH(64, 2) else DRM_GRU_LAUNCH(64, 1)
-#undef DRM_GRU_LAUNCH
-}
-
-}  // namespace drm
-#include "chain.cuh"
-namespace drm {
-
-static int launch_chain(const ChainParams& p, int mt, int n_slots, cudaStream_t st, int stage_id) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DRM_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-    attr_set = true;
-  }
-  if (g_timeline) {
-    const_cast<ChainParams&>(p).timeline = g_timeline + 16 * stage_id;
-    const_cast<ChainParams&>(p).cta_times = g_timeline + 16 * DRM_STAGE_COUNT + 1024 * stage_id;
-  }
-  profile_begin(stage_id, st);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(mt, n_slots, CH_CN);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = CH_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = CH_CN;
-  ++na;
-  if (!profile_on()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  DRM_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, p));
-  profile_end(stage_id, st);
-  DRM_LAUNCH_CHECK();
-  return DRM_OK;
+  EpiGru<64>::Params p{m->b_ih, m->b_hh, h_prev, h_out, s_h, ld_hprev, ld_hout, m->KS, m->d.D};
+  return launch_gemm<EpiGru<64>>(g, p, grid, st, DRM_STAGE_GRU);
 }
 
 // One Linear + LayerNorm + SiLU stage.  Small grids (<= 37 tiles) use the cluster-of-4 column split, larger ones one CTA per tile.
@@ -692,80 +610,17 @@ static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMa
   if (opts().ln_cluster && mt * n_slots <= 37) {
     g.tmB = tmB_q;
     g.bn = 64;
-    g.zi = nullptr;   // the one-hot expander (opt-in) walks single-k-block stages; this kernel pairs k-blocks per stage
     return launch_gemm<EpiLnSiluN4T<HAS_ADD>>(g, p, dim3(mt, n_slots, 4), st, stage_id);
   }
   g.tmB = tmB_full;
   g.bn = bn_full;
-  g.zi = nullptr;     // (see above)
   return launch_gemm<EpiLnSiluT<HAS_ADD>>(g, p, dim3(mt, n_slots, 1), st, stage_id);
-}
-
-}  // namespace drm
-#include "chain2.cuh"
-namespace drm {
-
-template <class EpiB, bool HAS_ADD>
-static int launch_chain2(const Chain2Common& c, const typename EpiLnSiluT<HAS_ADD>::Params& pa, const typename EpiB::Params& pb, dim3 grid,
-                         cudaStream_t st, int stage_id) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DRM_CUDA(cudaFuncSetAttribute(chain2_kernel<EpiB, HAS_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
-    attr_set = true;
-  }
-  profile_begin(stage_id, st);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = C2_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  int na = 0;
-  if (!profile_on()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  DRM_CUDA((cudaLaunchKernelEx(&cfg, chain2_kernel<EpiB, HAS_ADD>, c, pa, pb)));
-  profile_end(stage_id, st);
-  DRM_LAUNCH_CHECK();
-  return DRM_OK;
-}
-// small grids only (every layer-B column tile recomputes layer A).  Opt-in: measured 1.051 vs 1.059 ms per 1024 x 15 rollout --
-// the serial LN -> shared memory -> second MMA phase inside the kernel costs what the removed launch boundary cost.
-static bool use_chain2(int ctas) { return opts().chain2 && ctas <= 148; }
-static void chain2_small_a(Chain2Common& c, const CUtensorMap* small) {
-  if (small && c.M <= SMALL_A_ROWS && opts().small_a) {
-    c.tmA = *small;
-    c.a_bytes = SMALL_A_ROWS * BK * 2;
-  }
 }
 
 // prior MLP on the view's h columns -> logits -> (optional) categorical sample
 static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, float* latent, long ld_latent, float* logits,
                        long ld_logits, uint8_t* idx, long ld_idx, bool write_sz, RowMap rm, int M, cudaStream_t st) {
   const int mt = ceil_div(M, BM);
-  if (opts().chain && mt <= 37 && m->ZP == 1024) {
-    // small grid: h -> LN -> LN -> logits -> sample as ONE 4-CTA cluster kernel per m-tile (256 logit columns per CTA)
-    ChainParams c;
-    memset(&c, 0, sizeof(c));
-    c.tmA = *v.tmS; c.tmW0 = m->tmWp1q; c.tmW1 = m->tmWp2q; c.tmW2 = m->tmWp3h;
-    c.M = M; c.a_row0 = v.row0;
-    c.ka0 = m->ZP / 64 + 1; c.nka0 = m->DP / 64;
-    c.nk1 = ceil_div(m->d.h_prior[0], 64); c.nk2 = ceil_div(m->d.h_prior[1], 64);
-    c.nv0 = m->d.h_prior[0]; c.nv1 = m->d.h_prior[1];
-    c.bn2 = 128; c.passes = 2;
-    c.b0 = m->p1_b; c.g0 = m->p1_g; c.be0 = m->p1_be; c.cs0 = m->bnp1;
-    c.b1 = m->p2_b; c.g1 = m->p2_g; c.be1 = m->p2_be; c.cs1 = m->bnp2;
-    c.n_slots = 1; c.y_slot[0] = 0;
-    c.eps = 1e-5f; c.kind = CHAIN_PRIOR;
-    c.cat = EpiCat::Params{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
-                           ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
-                           (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
-    return launch_chain(c, mt, 1, st, DRM_STAGE_PRIOR_L1);
-  }
   {
     GemmCommon g = common(*v.tmS, m->tmWp1, M, m->bnp1);
     small_a(g, v.tmS_s);
@@ -774,21 +629,6 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.n_slots = 1; g.y_slot[0] = 0;
     EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f, m->bnp1};
     RC(launch_ln<false>(g, m->tmWp1, m->tmWp1q, m->bnp1, p, mt, 1, st, DRM_STAGE_PRIOR_L1));
-  }
-  if (use_chain2(mt * (m->ZP / 128))) {
-    // prior L2 (LN) -> logits + sample in ONE kernel per (m-tile, 128-logit column tile): the hidden activations stay in shared memory
-    Chain2Common c;
-    memset(&c, 0, sizeof(c));
-    c.tmA = *v.tmY1; c.tmWA = m->tmWp2; c.tmWB = m->tmWp3h;
-    c.M = M; c.a_row0 = v.row0;
-    c.ka0 = 0; c.nka0 = ceil_div(m->d.h_prior[0], 64);
-    c.bnA = m->bnp2; c.nkB = ceil_div(m->d.h_prior[1], 64); c.bnB = 128; c.wb_tile_rows = 128;
-    chain2_small_a(c, v.tmY1_s);
-    EpiLnSilu::Params pa{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, nullptr, 256, 0, 0, m->d.h_prior[1], 1e-5f, m->bnp2};
-    EpiCat::Params pb{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
-                      ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
-                      (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
-    return launch_chain2<EpiCat, false>(c, pa, pb, dim3(mt, m->ZP / 128), st, DRM_STAGE_PRIOR_CAT);
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWp2, M, m->bnp2);
@@ -806,41 +646,24 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
     EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
-                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm,
-                     (write_sz && v.Zi) ? v.Zi + (long)v.row0 * m->d.R : nullptr};
+                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st, DRM_STAGE_PRIOR_CAT));
   }
   return DRM_OK;
 }
 
+static void fill_heads(drm_rssm* m, EpiHeads::Params& hp) {
+  hp.bias = m->h3_b;
+  hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
+  hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
+  hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
+  hp.NB = m->d.NB; hp.A = m->d.A;
+}
+
 // [h, z] heads on the view: slots listed in `slots` (HS_*)
-static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st,
-                       bool z_idx = false) {
+static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slots, EpiHeads::Params hp, int M, cudaStream_t st) {
   const int mt = ceil_div(M, BM);
   if (n_slots <= 0) return DRM_OK;
-  if (opts().chain && mt * n_slots <= 37) {
-    // small grid: [z | h] -> LN -> LN -> output layer as ONE 4-CTA cluster kernel per (m-tile, head)
-    ChainParams c;
-    memset(&c, 0, sizeof(c));
-    c.tmA = *v.tmS; c.tmW0 = m->tmWh1q; c.tmW1 = m->tmWh2q; c.tmW2 = m->tmWh3q;
-    c.M = M; c.a_row0 = v.row0;
-    c.ka0 = 0; c.nka0 = m->ZP / 64; c.ka1 = m->ZP / 64 + 1; c.nka1 = m->DP / 64;
-    c.nk1 = ceil_div(m->d.h_head[0], 64); c.nk2 = ceil_div(m->d.h_head[1], 64);
-    c.nv0 = m->d.h_head[0]; c.nv1 = m->d.h_head[1];
-    c.bn2 = 64; c.passes = 1;
-    c.b0 = m->h1_b; c.g0 = m->h1_g; c.be0 = m->h1_be; c.cs0 = m->bnh1;
-    c.b1 = m->h2_b; c.g1 = m->h2_g; c.be1 = m->h2_be; c.cs1 = m->bnh2;
-    c.n_slots = n_slots;
-    for (int i = 0; i < n_slots; ++i) c.y_slot[i] = slots[i];
-    c.eps = 1e-5f; c.kind = CHAIN_HEADS;
-    hp.bias = m->h3_b;
-    hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
-    hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
-    hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
-    hp.NB = m->d.NB; hp.A = m->d.A;
-    c.heads = hp;
-    return launch_chain(c, mt, n_slots, st, DRM_STAGE_HEADS_L1);
-  }
   {
     GemmCommon g = common(*v.tmS, m->tmWh1, M, m->bnh1);
     g.a_row0 = v.row0;
@@ -848,29 +671,9 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;      // h blocks (the action block is skipped)
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    if (z_idx) use_z_indices(m, g, v);
     small_a(g, v.tmS_s);
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
     RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
-  }
-  hp.bias = m->h3_b;
-  hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
-  hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
-  hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
-  hp.NB = m->d.NB; hp.A = m->d.A;
-  if (use_chain2(mt * n_slots)) {
-    // head L2 (LN) -> head outputs in ONE kernel per (m-tile, head)
-    Chain2Common c;
-    memset(&c, 0, sizeof(c));
-    c.tmA = *v.tmY1; c.tmWA = m->tmWh2; c.tmWB = m->tmWh3;
-    c.M = M; c.a_row0 = v.slot_rows + v.row0; c.a_y_stride = v.slot_rows;
-    c.ka0 = 0; c.nka0 = ceil_div(m->d.h_head[0], 64);
-    c.bnA = m->bnh2; c.wa_slot_rows = 256; c.nkB = ceil_div(m->d.h_head[1], 64); c.bnB = 256; c.wb_tile_rows = 256;
-    c.per_slot = 1; c.n_slots = n_slots;
-    for (int i = 0; i < n_slots; ++i) c.y_slot[i] = slots[i];
-    chain2_small_a(c, v.tmY1_s);
-    EpiLnSilu::Params pa{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, nullptr, 256, 0, 0, m->d.h_head[1], 1e-5f, m->bnh2};
-    return launch_chain2<EpiHeads, false>(c, pa, hp, dim3(mt, n_slots), st, DRM_STAGE_HEADS_OUT);
   }
   {
     GemmCommon g = common(*v.tmY1, m->tmWh2, M, m->bnh2);
@@ -889,11 +692,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[1], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
-    hp.bias = m->h3_b;
-    hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
-    hp.kind[HS_CRITIC] = HEAD_BUCKET; hp.kind[HS_TARGET] = HEAD_BUCKET;
-    hp.buckets[HS_REWARD] = m->bk_rew; hp.buckets[HS_CRITIC] = m->bk_crit; hp.buckets[HS_TARGET] = m->bk_crit;
-    hp.NB = m->d.NB; hp.A = m->d.A;
+    fill_heads(m, hp);
     RC(launch_gemm<EpiHeads>(g, hp, dim3(mt, n_slots), st, DRM_STAGE_HEADS_OUT));
   }
   return DRM_OK;
@@ -937,8 +736,7 @@ static int rollout_lane(drm_rollout* r, int b0, int M, const float* z0, const fl
   }
   for (int t = 0; t < H; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
-    // t = 0 reads the caller's z0 densely; every later latent was sampled here, so its A tiles are expanded from the indices
-    RC(stage_gru(m, view(cur), view(nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, M, st, t > 0));
+    RC(stage_gru(m, view(cur), view(nxt), hidden + (long)t * D, ldH, hidden + (long)(t + 1) * D, ldH, M, st));
     RC(stage_prior(m, view(nxt), uniforms + (long)t * B * R, latent + (long)(t + 1) * ZP, ldL, nullptr, 0,
                    idx ? idx + (long)t * R : nullptr, (long)H * R, true, RowMap{0, 0, 0, 0}, M, st));
     EpiHeads::Params hp;
@@ -953,12 +751,14 @@ static int rollout_lane(drm_rollout* r, int b0, int M, const float* z0, const fl
       hp.ld_act = ldA;
       hp.s_a = S_rows(nxt) + ZP; hp.ld_s = m->KS;
     }
-    RC(stage_heads(m, view(nxt), all3, more ? 3 : 2, hp, M, st, true));
+    RC(stage_heads(m, view(nxt), all3, more ? 3 : 2, hp, M, st));
   }
   return DRM_OK;
 }
 
 }  // namespace drm
+
+#include "rollout_persist.cuh"
 
 extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const float* uniforms, const float* normals,
                                float* latent, float* hidden, float* actions, float* rewards, float* continues, float* mu,
@@ -971,29 +771,31 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
   DRM_REQUIRE((m->have & (HAVE_GRU | HAVE_PRIOR | 7u)) == (HAVE_GRU | HAVE_PRIOR | 7u), DRM_ERR_ARG,
               "drm_rollout_run: GRU, prior, reward, continue and actor weights must all be packed");
   cudaStream_t st = (cudaStream_t)stream;
-  const int B = r->B;
-  // Two lanes (opt-in, "lanes" = 2): the start states are independent, and at a few hundred rows every stage of the step is a
-  // small, latency-bound grid (24 .. 152 CTAs); two half-batches on two streams interleave their stages.  Measured at
-  // 1024 x 15: 1.12 ms against 1.06 ms for one lane (the interleaved stages contend for TMEM and L2), so one lane stays default.
-  int lanes = opts().lanes;
-  if (lanes == 0) lanes = 1;
-  if (profile_on() || g_timeline || opts().zidx || B < 2 * BM) lanes = 1;
-  if (lanes == 1) return rollout_lane(r, 0, B, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
-  if (!r->lane_st[0]) {
-    for (int i = 0; i < 2; ++i) {
-      DRM_CUDA(cudaStreamCreateWithFlags(&r->lane_st[i], cudaStreamNonBlocking));
-      DRM_CUDA(cudaEventCreateWithFlags(&r->ev_join[i], cudaEventDisableTiming));
-    }
-    DRM_CUDA(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
-  }
-  const int M0 = round_up(ceil_div(B, 2), BM);
-  DRM_CUDA(cudaEventRecord(r->ev_fork, st));
-  for (int i = 0; i < 2; ++i) {
-    DRM_CUDA(cudaStreamWaitEvent(r->lane_st[i], r->ev_fork, 0));
-    const int b0 = i ? M0 : 0, M = i ? B - M0 : M0;
-    RC(rollout_lane(r, b0, M, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, r->lane_st[i]));
-    DRM_CUDA(cudaEventRecord(r->ev_join[i], r->lane_st[i]));
-    DRM_CUDA(cudaStreamWaitEvent(st, r->ev_join[i], 0));
+  // One persistent kernel for the whole horizon when its static schedule fits the machine (rollout_persist.cuh); the
+  // launch-per-stage chain otherwise (large batches, where every stage fills the machine and is throughput bound), while the
+  // per-stage profiler / timeline probes are on, or with option "persist" = 0.
+  if (opts().persist && !profile_on() && !g_timeline && persist_eligible(r))
+    return rollout_persist(r, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
+  return rollout_lane(r, 0, r->B, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
+}
+
+// Which path the next drm_rollout_run takes (1 = persistent kernel) and its geometry; the timeout records of the persistent kernel
+// (host-mapped, so they survive a trapped launch): out[0] = 1 / 0, out[1..4] = U, sampling tile width, CTAs, timeouts recorded,
+// then up to 8 records {code, seen, want, thread, cta}.
+extern "C" int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n) {
+  DRM_REQUIRE(r && out && n >= 5, DRM_ERR_ARG, "drm_rollout_info: bad argument");
+  for (int i = 0; i < n; ++i) out[i] = 0;
+  if (!(r->ps && r->ps->tried)) RC(check_arch());   // (no CUDA call once the plan exists: this must still answer after a trapped launch)
+  const bool ok = opts().persist && persist_eligible(r);
+  out[0] = ok ? 1u : 0u;
+  if (!r->ps || !r->ps->ok) return DRM_OK;
+  out[1] = (uint32_t)r->ps->U; out[2] = (uint32_t)r->ps->bn_cat; out[3] = (uint32_t)r->ps->n_cta;
+  out[4] = r->ps->dbg[8 * 160];
+  int k = 5;
+  for (int c = 0; c < 160 && k + 5 <= n; ++c) {
+    const unsigned* rec = r->ps->dbg + 8 * c;
+    if (rec[0] == 0 && rec[2] == 0) continue;
+    for (int j = 0; j < 5; ++j) out[k++] = rec[j];
   }
   return DRM_OK;
 }
@@ -1013,7 +815,7 @@ extern "C" int drm_gru_step(drm_rollout* r, const float* z, const float* h, cons
   RC(pack_state(r, 0, 0, z, m->ZP, m->ZP, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP, a, m->d.A, m->d.A, N, nullptr, 0, st));
   RC(pack_state(r, 0, m->ZP + 64, h, m->d.D, m->d.D, N, nullptr, 0, st));
-  return stage_gru(m, view_of(r, 0), view_of(r, 1), h, m->d.D, h_out, m->d.D, N, st, false, true);
+  return stage_gru(m, view_of(r, 0), view_of(r, 1), h, m->d.D, h_out, m->d.D, N, st, true);
 }
 
 extern "C" int drm_prior(drm_rollout* r, const float* h, const float* uniforms, float* logits, float* z_st, uint8_t* idx,
@@ -1091,16 +893,13 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   if (!name) return fail(DRM_ERR_ARG, "drm_set_option: NULL name");
   const std::string n(name);
   Options& o = opts();
-  if (n == "zidx") o.zidx = value != 0;
-  else if (n == "multicast") o.multicast = value != 0;
-  else if (n == "ln_cluster") o.ln_cluster = value != 0;
-  else if (n == "chain") o.chain = value != 0;
+  if (n == "ln_cluster") o.ln_cluster = value != 0;
   else if (n == "small_a") o.small_a = value != 0;
-  else if (n == "chain2") o.chain2 = value != 0;
   else if (n == "conv_persist") o.conv_persist = value != 0;
   else if (n == "gru_ksplit") o.gru_ksplit = value != 0;
+  else if (n == "persist") o.persist = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
-  else if (n == "lanes") { DRM_REQUIRE(value >= 0 && value <= 2, DRM_ERR_ARG, "drm_set_option: lanes must be 0, 1 or 2"); o.lanes = value; }
+  else if (n == "gru_band") { DRM_REQUIRE(value >= 0 && value <= 64, DRM_ERR_ARG, "drm_set_option: gru_band must be in [0, 64]"); o.gru_band = value; }
   else if (n == "gru_u") { DRM_REQUIRE(value == 0 || value == 32 || value == 64, DRM_ERR_ARG, "drm_set_option: gru_u must be 0, 32 or 64"); o.gru_u = value; }
   else return fail(DRM_ERR_ARG, "drm_set_option: unknown option '" + n + "'");
   return DRM_OK;

@@ -269,7 +269,6 @@ struct drm_observe {
   drm_vae* v;
   int B, T, rows, rows_p, FC;
   __nv_bfloat16 *S, *Y1, *Y2, *feat, *dec0, *patch, *actA, *actB;
-  uint8_t* Zi;               // sampled posterior indices [rows_p, R] parallel to S
   float *zero_h, *featpart;
   CUtensorMap tmS, tmY1, tmY2, tmFeat, tmPatchE[4], tmPatchD[4];
   CUtensorMap tmS_s, tmY1_s, tmY2_s;   // short-box twins (SMALL_A_ROWS rows) for steps with few sequences
@@ -300,7 +299,7 @@ static std::vector<int> scaled(int n, int limit, int scale, int offset = 0) {  /
   return r;
 }
 static WsView view_of(drm_observe* o, int row0) {
-  return WsView{&o->tmS, o->S, &o->tmY1, &o->tmY2, o->Y1, o->Y2, o->rows_p, row0, o->Zi, &o->tmS_s, &o->tmY1_s, &o->tmY2_s};
+  return WsView{&o->tmS, o->S, &o->tmY1, &o->tmY2, o->Y1, o->Y2, o->rows_p, row0, &o->tmS_s, &o->tmY1_s, &o->tmY2_s};
 }
 // sub-pixel decomposition of ConvTranspose2d(k4, s2, p1): output o = 2 q + p gets taps
 //   p = 0: (input q, kernel 1), (q - 1, kernel 3);   p = 1: (q, kernel 2), (q + 1, kernel 0)
@@ -490,7 +489,6 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
   TRY(dev_alloc(o->allocs, &o->S, (size_t)o->rows_p * m->KS));
-  TRY(dev_alloc(o->allocs, &o->Zi, (size_t)o->rows_p * m->d.R));
   TRY(dev_alloc(o->allocs, &o->Y1, (size_t)(MAX_HEADS + 1) * o->rows_p * 256));
   TRY(dev_alloc(o->allocs, &o->Y2, (size_t)(MAX_HEADS + 1) * o->rows_p * 256));
   TRY(dev_alloc(o->allocs, &o->feat, (size_t)(round_up(NF, BM) + BM) * v->Kf));
@@ -634,8 +632,7 @@ static int encoder_head(drm_observe* o, const WsView& vw, const float* addend, c
     g.a_row0 = vw.row0;
     g.ka0 = 0; g.nka0 = ceil_div(v->d.h_enc, 64);
     EpiCat::Params p{v->e3_b, uniforms, latent, logits, idx, write_sz ? vw.S + (long)vw.row0 * m->KS : nullptr, nullptr,
-                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, RowMap{0, 0, 0, 0},
-                     (write_sz && vw.Zi) ? vw.Zi + (long)vw.row0 * m->d.R : nullptr};
+                     ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, RowMap{0, 0, 0, 0}};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st));
   }
   return DRM_OK;
@@ -652,7 +649,6 @@ static int decoder_dense(drm_observe* o, const WsView& vw, __nv_bfloat16* act0, 
     g.ka0 = 0; g.nka0 = m->ZP / 64;
     g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
-    if (z_idx) use_z_indices(m, g, vw);
     small_a(g, vw.tmS_s);
     EpiLnSilu::Params p{v->d1_b, v->d1_g, v->d1_be, nullptr, 0, vw.Y1, 256, vw.row0, vw.slot_rows, v->d.h_dec, 1e-5f, v->bn_hd};
     RC(launch_ln<false>(g, v->tmWd1, v->tmWd1q, v->bn_hd, p, mt, 1, st, DRM_STAGE_OTHER));
@@ -696,7 +692,7 @@ extern "C" int drm_observe_scan(drm_observe* o, const float* obs, const float* a
     if (t == 0 && mode == 1) {
       DRM_CUDA(cudaMemset2DAsync(hidden, ldH * sizeof(float), 0, (size_t)D * sizeof(float), B, st));   // h_0 = 0, no GRU step
     } else {
-      RC(stage_gru(m, prev, cur, t == 0 ? o->zero_h : hidden + (long)(t - 1) * D, t == 0 ? (long)D : ldH, hidden + (long)t * D, ldH, B, st, t > 0, true));
+      RC(stage_gru(m, prev, cur, t == 0 ? o->zero_h : hidden + (long)(t - 1) * D, t == 0 ? (long)D : ldH, hidden + (long)t * D, ldH, B, st, true));
     }
     RC(encoder_head(o, cur, o->featpart + (long)t * B * v->bn_he, uniforms + (long)t * B * R, latent + (long)t * ZP, ldL,
                     post_logits ? post_logits + (long)t * ZP : nullptr, ldL, idx ? idx + (long)t * R : nullptr, (long)T * R, true, B, st));
@@ -740,7 +736,7 @@ extern "C" int drm_observe_heads(drm_observe* o, float* prior_logits, float* dec
     hp.rm = RowMap{1, B, T - 1, 0};
     if (reward_logits) { slots[n++] = HS_REWARD; hp.logits[HS_REWARD] = reward_logits; hp.ld_logits[HS_REWARD] = m->d.NB; }
     if (cont_logit) { slots[n++] = HS_CONT; hp.logits[HS_CONT] = cont_logit; hp.ld_value[HS_CONT] = 1; }
-    RC(stage_heads(m, view_of(o, 2 * B), slots, n, hp, (T - 1) * B, st, true));
+    RC(stage_heads(m, view_of(o, 2 * B), slots, n, hp, (T - 1) * B, st));
   }
   return DRM_OK;
 }

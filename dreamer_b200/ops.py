@@ -317,6 +317,14 @@ class Rollout:
         self.handle = C.c_void_p()
         L.check(L.load().drm_rollout_create(model.handle, B, H, C.byref(self.handle)), "rollout_create")
 
+    def info(self):
+        """Which kernel path `run` takes: dict(persistent, gru_tile, sample_tile, ctas, timeouts=[(code, seen, want, thread, cta), ...])."""
+        buf = (C.c_uint32 * 45)()
+        L.check(L.load().drm_rollout_info(self.handle, buf, 45), "rollout_info")
+        recs = [tuple(buf[5 + 5 * i + k] for k in range(5)) for i in range(8)]
+        return dict(persistent=bool(buf[0]), gru_tile=int(buf[1]), sample_tile=int(buf[2]), ctas=int(buf[3]), n_timeouts=int(buf[4]),
+                    timeouts=[r for r in recs if any(r)])
+
     def run_graphed(self, z0, h0, uniforms, normals, want_idx: bool = True):
         """`run` replayed as ONE CUDA graph after two eager calls (graphs.StepGraph): the inputs are copied into static device
         buffers and the ~110 launches of a rollout become one graph launch (0.99 -> 0.94 ms at 1024 x 15, and no host launch

@@ -61,23 +61,19 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_HEADS_OUT 6
 #define DRM_STAGE_OTHER 7
 #define DRM_STAGE_COUNT 8
-/* Runtime switches for the experimental / alternative kernel paths (all produce identical results):                  */
-/*   "ln_cluster" (default 1)  LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
+/* Runtime switches between kernel paths that compute the same thing (tests/test_gpu_errors.py compares them):           */
+/*   "persist"    (default 1)  drm_rollout_run as ONE persistent kernel for the whole horizon (rollout_persist.cuh) whenever its */
+/*                             static schedule fits the machine (e.g. <= 1024 start states at the reference sizes); 0 = always */
+/*                             the launch-per-stage chain (7 launches per imagined step)                                      */
+/*   "ln_cluster" (default 1)  launch-per-stage LN-SiLU stages of small grids split over clusters of 4 CTAs (DSMEM statistics exchange) */
 /*   "gru_ksplit" (default 1)  single-m-tile grids: the x part and the h part of every GRU tile on two CTAs of a cluster (half the MMA issues */
 /*                             per CTA), rows swapped through distributed shared memory for the epilogue                             */
 /*   "conv_persist" (default 1) conv layers with <= 64 output channels on the persistent double-buffered GEMM (0: one tile per CTA)   */
-/*   "chain2"     (default 0)  small grids: (prior L2 -> logits + sample) and (head L2 -> head outputs) as ONE kernel each, the  */
-/*                             hidden activations staying in shared memory (5 launches per step instead of 7; measured: +0.8 %)  */
 /*   "gru_pair"   (default -1) GRU stage on CTA pairs (tcgen05 cta_group::2, M = 256 MMAs, each SM stages half the weight tile):  */
 /*                             -1 = automatic (large grids, where it is 11-18 % faster), 0 = never, 1 = whenever >= 2 m-tiles      */
+/*   "gru_band"   (default 0)  CTA-pair GRU kernel: m-tiles per band of the tile order (0 = 16)                           */
 /*   "small_a"    (default 1)  stages with <= 32 rows load 32-row A boxes by TMA instead of whole 128-row tiles          */
-/*   "lanes"      (default 0)  rollouts: 2 = two half-batches on two internal streams (bit-identical; measured: slower) */
-/*   "chain"      (default 0)  small grids: each MLP head (LN, LN, output layer) as ONE 4-CTA cluster kernel, activations */
-/*                             kept in shared memory and exchanged through DSMEM (3 launches per imagined step, not 7;  */
-/*                             measured: the in-kernel exchanges cost more than the launch boundaries they remove)     */
-/*   "gru_u"      (default 0)  GRU tile width: 0 = automatic, 32 or 64 hidden units per tile                           */
-/*   "multicast"  (default 0)  GRU stage in 2-CTA clusters, weight tile halves multicast by TMA (measured: not faster) */
-/*   "zidx"       (default 0)  one-hot latent A tiles built in shared memory from sampled indices (measured: slower)   */
+/*   "gru_u"      (default 0)  GRU tile width of the launch-per-stage path: 0 = automatic, 32 or 64 hidden units per tile */
 int drm_set_option(const char* name, int32_t value);
 /* Debug probe: with on = 1 CTA (0,0) of every fused stage records {globaltimer ns, clock64} at 8 points */
 /* (entry, setup done, first TMA issued, first operands landed, last MMA issued, accumulator ready,     */
@@ -211,6 +207,11 @@ int drm_rollout_destroy(drm_rollout* r);
 int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const float* uniforms, const float* normals,
                     float* latent, float* hidden, float* actions, float* rewards, float* continues, float* mu,
                     float* sigma, uint8_t* idx, void* stream);
+
+/* Which path the next drm_rollout_run takes and, after a failed launch, what the persistent kernel was waiting for:        */
+/* out[0] = 1 persistent kernel / 0 launch-per-stage chain, out[1] = GRU tile width, out[2] = sampling tile width,           */
+/* out[3] = CTAs, out[4] = number of timed-out waits recorded, then records {code, seen, want, thread, cta} (n >= 5 words). */
+int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n);
 
 /* Step-level entry points behind the drop-in classes.  They run on the rollout workspace (any   */
 /* N <= B of drm_rollout_create).                                                                */

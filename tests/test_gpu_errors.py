@@ -73,11 +73,11 @@ def test_rollout_is_deterministic():
         assert torch.equal(x, y) and torch.equal(x, w)
 
 
-@pytest.mark.parametrize("option,value", [("zidx", 1), ("multicast", 1), ("ln_cluster", 0), ("chain", 1), ("small_a", 0), ("chain2", 1), ("gru_ksplit", 0), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32)])
+@pytest.mark.parametrize("option,value", [("ln_cluster", 0), ("small_a", 0), ("gru_ksplit", 0), ("gru_pair", 1), ("gru_u", 64), ("gru_u", 32), ("persist", 1)])
 def test_alternative_kernel_paths_give_identical_results(L, option, value):
-    """Every switchable path reproduces the default path on a whole rollout: bit for bit for the one-hot expander, the TMA
-    multicast clusters and both GRU tile widths (same per-element accumulation order); to fp32 rounding for the one-CTA LN
-    tiles, whose LayerNorm statistics are merged in a different order than in the 4-CTA cluster."""
+    """Every switchable path reproduces the launch-per-stage default on a whole rollout: bit for bit for both GRU tile widths and
+    the CTA pairs (same per-element accumulation order); to fp32 rounding for the one-CTA LN tiles and the persistent kernel
+    (LayerNorm statistics merged in a different order; the action term of the GRU added in the epilogue)."""
     from dreamer_b200 import ops
     lib = L.load()
     cfg = W.small_config()
@@ -86,19 +86,23 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     ro = ops.Rollout(model, 200, 4)
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, 200, 4, seed=6))
     assert lib.drm_set_option(b"nonsense", 1) == -5
-    defaults = dict(zidx=0, multicast=0, ln_cluster=1, chain=0, small_a=1, chain2=0, gru_ksplit=1, gru_pair=-1, gru_u=0)
+    defaults = dict(ln_cluster=1, small_a=1, gru_ksplit=1, gru_pair=-1, gru_u=0, persist=1)
     # the K-split GRU kernel (default on small grids) sums the x and h parts in a different order than every other GRU path, and
     # several options fall back from it: hold it off for the bit-exact comparisons, and compare it against the rest to rounding
     ksplit_base = 1 if option == "gru_ksplit" else 0
     try:
+        L.check(lib.drm_set_option(b"persist", 0), "set_option")
         L.check(lib.drm_set_option(b"gru_ksplit", ksplit_base), "set_option")
         base = ro.run(z0, h0, u, n)
         L.check(lib.drm_set_option(option.encode(), value), "set_option")
+        if option == "persist":
+            assert ro.info()["persistent"]
         alt = ro.run(z0, h0, u, n)
     finally:
         lib.drm_set_option(option.encode(), defaults[option])
         lib.drm_set_option(b"gru_ksplit", 1)
-    if option in ("ln_cluster", "chain", "chain2", "gru_ksplit"):
+        lib.drm_set_option(b"persist", 1)
+    if option in ("ln_cluster", "gru_ksplit", "persist"):
         assert (base[7] != alt[7]).float().mean().item() < 0.01
         same = (base[7] == alt[7]).all(dim=-1).all(dim=-1)          # trajectories whose draws all agree
         for a, b in zip(base[1:7], alt[1:7]):
@@ -106,30 +110,6 @@ def test_alternative_kernel_paths_give_identical_results(L, option, value):
     else:
         for a, b in zip(base, alt):
             assert torch.equal(a, b), option
-
-
-def test_two_lane_rollout_is_bit_identical_to_one_lane(L):
-    """Option "lanes" = 2 runs a rollout as two half-batches on two internal streams (independent rows, the same kernels per
-    row): the outputs must not change, including for a batch that does not split evenly into 128-row tiles."""
-    from dreamer_b200 import ops
-    lib = L.load()
-    cfg = W.small_config()
-    sd = {k: v.to(DEV) for k, v in W.make_state_dict(cfg, seed=5).items()}
-    model = ops.PackedRssm.from_state_dict(sd)
-    for B in (512, 700):
-        ro = ops.Rollout(model, B, 3)
-        z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, 3, seed=B))
-        try:
-            L.check(lib.drm_set_option(b"lanes", 1), "set_option")
-            one = ro.run(z0, h0, u, n)
-            L.check(lib.drm_set_option(b"lanes", 2), "set_option")
-            two = ro.run(z0, h0, u, n)
-        finally:
-            lib.drm_set_option(b"lanes", 0)
-        auto = ro.run(z0, h0, u, n)
-        for a, b, c in zip(one, two, auto):
-            assert torch.equal(a, b) and torch.equal(a, c), B
-    assert lib.drm_set_option(b"lanes", 3) == -5
 
 
 @pytest.mark.parametrize("B", [2179, 4100])
@@ -145,6 +125,7 @@ def test_cta_pair_gru_band_order_on_ragged_grids(L, B):
     ro = ops.Rollout(model, B, 2)
     z0, h0, u, n = (t.to(DEV) for t in W.rollout_inputs(cfg, B, 2, seed=B))
     try:
+        L.check(lib.drm_set_option(b"persist", 0), "set_option")        # the launch-per-stage GRU kernels are what is compared here
         L.check(lib.drm_set_option(b"gru_ksplit", 0), "set_option")     # compare against the single-CTA kernel (same summation order)
         L.check(lib.drm_set_option(b"gru_pair", 0), "set_option")
         base = ro.run(z0, h0, u, n)
@@ -158,3 +139,4 @@ def test_cta_pair_gru_band_order_on_ragged_grids(L, B):
         lib.drm_set_option(b"gru_pair", -1)
         lib.drm_set_option(b"gru_u", 0)
         lib.drm_set_option(b"gru_ksplit", 1)
+        lib.drm_set_option(b"persist", 1)
