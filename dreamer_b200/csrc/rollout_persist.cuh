@@ -1,29 +1,34 @@
 // The imagination rollout (Dreamer.dream_episodes, Dreamer.py:143-175) as ONE persistent kernel: the time loop, the actor,
 // the GRU step, the prior head + categorical sample and the reward / continue heads of every step run inside a single
-// cooperative launch of one CTA per SM.  Included from rssm.cu.
+// launch of 4-CTA clusters, one CTA per SM.  Included from rssm.cu.
 //
 // Why it is shaped like this (DESIGN.md section 4 has the numbers):
 //   * At 1024 start states a step is 9 GFLOP = 6.5 us of tensor work but SEVEN dependent GEMM stages; launched one by one each
 //     stage pays a prologue (barrier init, TMEM allocation, descriptor fetch), a launch boundary and a cold pipeline.  Here the
-//     CTAs stay resident: barriers, TMEM and the tile constants live across steps, and stages hand over through per-m-tile
-//     counters in global memory (release / acquire) instead of kernel boundaries -- an m-tile moves on as soon as ITS
-//     producers are done, there is no grid-wide barrier anywhere.
-//   * CTAs are specialised.  "GRU" CTAs own one (m-tile, n-tile) of the GRU for the whole horizon; "prior", "sample" and
-//     "head" CTAs own one m-tile's MLP chain.  The action enters the GRU through 3 (A <= 4) input columns only, so the GRU
-//     CTAs run the whole [z | h] contraction (26 of the 27 k-blocks at the reference sizes) on the tensor cores WHILE the actor
-//     chain of the same step is still running, keep the accumulator in TMEM, and add the action term in the epilogue on the
-//     CUDA cores once the action is there.  The per-step critical path is actor chain -> GRU epilogue -> prior chain; the GRU
-//     main loop, the reward and the continue head are off it.
+//     CTAs stay resident: barriers, TMEM and descriptors live across steps.
+//   * CTAs are specialised:
+//       "chain" clusters (one 4-CTA cluster per m-tile of 128 start states) run the serial MLP chain of every state: prior L1 ->
+//       prior L2 -> logits + sample -> actor L1 -> actor L2 -> actor output.  The four CTAs split every layer's output columns
+//       (64 LayerNorm columns / 256 logit columns each); LayerNorm statistics cross the cluster through distributed shared
+//       memory, and layers hand over with ONE barrier.cluster (release / acquire) -- no global flag, no kernel boundary.
+//       "GRU" CTAs own one (m-tile, n-tile) of the GRU for the whole horizon.  The action enters the GRU through A <= 4 input
+//       columns only, so they run the whole [z | h] contraction (26 of the 27 k-blocks at the reference sizes) on the tensor
+//       cores WHILE the actor chain of the same step is still running, keep the accumulator in TMEM, and add the action term in
+//       the epilogue on the CUDA cores once the action is there.
+//       "head" CTAs (whatever SMs are left) run the reward and continue heads of every sampled state; nothing waits for them.
+//     Per-step critical path: chain cluster (6 layers) -> GRU epilogue; three global release / acquire hand-overs per step
+//     (h ready, z ready, action ready) through per-m-tile counters, everything else inside a cluster.
+//   * The state buffer keeps ALL H + 1 states (time-major slabs of bf16 [z | a | h] rows), so no buffer is ever overwritten
+//     while somebody may still read it: the only dependencies are true (read-after-write) ones.
 //   * Weights stay L2-resident and are streamed by TMA every step.  Holding them in shared memory across steps (north-star item
 //     1 read literally) needs an N-partition in which every CTA re-reads ALL state rows each step: >= 38 partitions x 3.4 MB
 //     = 129 MB of L2 -> SM traffic per step against 117 MB for the output-stationary tiling used here -- the weights (6.2 MB
 //     GRU + 3.9 MB heads) and the state (3.4 MB) are the same order of magnitude at this batch size, so residency buys nothing.
 //
-// Ordering / deadlock freedom: every CTA walks its items in the total order (state j; prior L1/L2 < sample < heads < GRU);
-// every wait is on a task that is earlier in that order, so the globally earliest unfinished task can always run.  A GRU CTA
-// blocks early (it starts its main loop before the actor of the same step is done), which is safe because GRU CTAs hold GRU
-// items only.  All spins are bounded: after ~2 s a waiter records who / what it was waiting for in a host-mapped debug buffer
-// and traps, so a scheduling bug fails the launch instead of hanging the GPU.
+// Deadlock freedom: every wait is on work of an EARLIER point of the chain (state j: prior < sample < actor < GRU < state j + 1),
+// every CTA walks its own work in that order, and all CTAs are co-resident (the host checks cudaOccupancyMaxActiveClusters).
+// All spins are bounded: after ~2 s a waiter records who / what it was waiting for in a host-mapped debug buffer and traps, so
+// a scheduling bug fails the launch instead of hanging the GPU.
 #pragma once
 
 namespace drm {
@@ -44,25 +49,31 @@ static_assert(PS_WA_OFF + 3 * 64 * 16 <= PS_BAR_OFF, "GRU aux region overflows")
 static_assert(PS_SCHED_STRIDE * 4 <= 256, "schedule record too large");
 static_assert(PS_TOTAL <= 232448, "persistent rollout kernel exceeds the 227 KB shared-memory limit");
 
-enum { PS_P12 = 0, PS_P3 = 1, PS_HEAD = 2, PS_GRU = 3 };
-enum { PF_H = 0, PF_Z = 1, PF_A = 2, PF_HL1 = 3, PF_P2 = 4, PF_COUNT = 5 };   // per-m-tile counters (one 128-byte line each)
+enum { PS_CHAIN = 0, PS_RC = 2, PS_GRU = 3 };   // CTA roles (the record's first item kind)
+// per-m-tile counters (one 128-byte line each): GRU tiles finished (h_{j+1} ready), sampling tiles finished (z_j ready),
+// actor outputs finished (a_j ready).  Producers of a counter never run a state ahead of one another, so "counter >= c(j)"
+// means exactly "everything of states <= j".
+enum { PF_H = 0, PF_Z = 1, PF_A = 2, PF_COUNT = 3 };
 constexpr int PS_DBG_WORDS = 8 * 160 + 8;
+constexpr int PS_TRACE_SLOTS = 32;
 
 struct PersistParams {
-  CUtensorMap tmS[2], tmY1, tmY2, tmWgru, tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
+  CUtensorMap tmS, tmY1, tmY2, tmWgru, tmWp1q, tmWp2q, tmWp3, tmWh1q, tmWh2q, tmWh3a, tmWh1, tmWh2, tmWh3;
   int B, H, D, DP, ZP, R, A, NB, KS, Mp, mt;
-  int U, nt, bn_cat, nq;
+  int U, nt, nq;   // GRU tile width, GRU n-tiles, 256-column sampling tiles
   int bnp1, bnp2, bnh1, bnh2, hp1, hp2, hh1, hh2;
   const float *b_ih, *b_hh, *p1_b, *p1_g, *p1_be, *p2_b, *p2_g, *p2_be, *p3_b;
   const float *h1_b, *h1_g, *h1_be, *h2_b, *h2_g, *h2_be, *h3_b, *bk_rew;
   const __nv_bfloat16* Wgru;
-  __nv_bfloat16 *S[2], *Y1, *Y2;
+  __nv_bfloat16 *S, *Y1, *Y2;   // S: time-major state slabs [(H + 1) * B (+ pad), KS]
   const float *uniforms, *normals;
   float *latent, *hidden, *actions, *rewards, *continues, *mu, *sigma;
   uint8_t* idx;
   unsigned* flags;
   unsigned* dbg;
   const int* sched;
+  unsigned long long* trace;   // debug: [cta][PS_TRACE_SLOTS][8] timestamps of the tiles of states [trace_j0, trace_j1), or NULL
+  int trace_j0, trace_j1;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -223,9 +234,10 @@ struct PsCtx {
   uint8_t* smem;
   uint64_t *full, *empty, *tmem_full;
   uint32_t tmem;
-  uint32_t it;        // k-blocks issued so far (ring position / phase), identical in every thread
+  uint32_t it;        // pipeline stages issued so far (ring position / phase), identical in every thread
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
   unsigned* dbg;
+  unsigned long long* tr;   // this tile's trace record (8 x u64) or NULL
 };
 struct PsTile {
   const CUtensorMap *tmA, *tmB;
@@ -233,74 +245,95 @@ struct PsTile {
   int ka0, nka0, ka1, nka1;   // A k-block ranges [ka0, ka0 + nka0) then [ka1, ka1 + nka1)
   int b_follows_a;            // 1: the B k-block index equals the A k-block index (GRU weights keep the state's column layout)
   int bn;                     // B rows per k-block (GRU: 3U)
+  int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
   int stage_bytes;            // ring stride of this CTA's role
-  const unsigned* w0; unsigned t0;               // before the first A load
-  const unsigned *e0, *e1; unsigned et0, et1;    // before the epilogue reads produced data / overwrites consumed data
-  unsigned* sig;                                  // += 1 once the tile's outputs are visible
-  unsigned code;                                  // (kind << 24) | (j << 8) | m-tile, for the timeout record
+  int cbar;                   // cluster barriers the epilogue executes (the producer / MMA warps mirror them)
+  const unsigned* w0; unsigned t0;     // before the first A load
+  const unsigned* e0; unsigned et0;    // before the epilogue reads data another CTA produced
+  unsigned* sig;                       // += 1 (device-scope release) once the tile's outputs are visible
+  unsigned code;                       // (role << 24) | (layer << 16) | (j << 8) | m-tile, for the timeout / trace records
 };
 
-// GRU_U = 0: plain N = bn accumulator.  Fn epilogue(tid) runs on the EPI_THREADS epilogue threads between the tmem_full wait and
-// the publication of the tile; pre(tid) runs on them while the main loop is in flight.
+__device__ __forceinline__ int ps_ka(const PsTile& t, int kb) { return kb < t.nka0 ? t.ka0 + kb : t.ka1 + (kb - t.nka0); }
+
+// GRU_U = 0: plain N = bn accumulator.  pre(tid) runs on the EPI_THREADS epilogue threads while the main loop is in flight,
+// epilogue(tid) between the accumulator-complete wait and the publication of the tile.
 template <int GRU_U, class Pre, class Epi>
 __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = t.nka0 + t.nka1;
+  const int kps = t.kps;
+  const int n_st = (nk + kps - 1) / kps;
+  const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;   // one k-block: [A 16 KB | B]
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)A_STAGE_BYTES + (uint32_t)t.bn * BK * 2;
-      const int npre = min(nk, PS_STAGES);
+      const int npre = min(n_st, PS_STAGES);
+      if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
       // weights first: they do not depend on anything, so the ring is pre-filled with them while the dependency is still open
-      for (int kb = 0; kb < npre; ++kb) {
-        const uint32_t i = c.it + kb, s = i % PS_STAGES;
+      for (int st = 0; st < npre; ++st) {
+        const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
-        mbar_expect_tx(&c.full[s], tx);
-        const int ka = kb < t.nka0 ? t.ka0 + kb : t.ka1 + (kb - t.nka0);
-        tma_load_2d(c.smem + s * t.stage_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
+        const int n_sub = min(kps, nk - st * kps);
+        mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
+        for (int u = 0; u < n_sub; ++u) {
+          const int kb = st * kps + u;
+          tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+        }
       }
       ps_flag_wait(t.w0, t.t0, c.dbg, t.code | (2u << 20));
       fence_proxy_async_all();   // the A operand was written through the generic proxy (possibly by another SM): order it before the TMA reads
-      for (int kb = 0; kb < npre; ++kb) {
-        const uint32_t s = (c.it + kb) % PS_STAGES;
-        const int ka = kb < t.nka0 ? t.ka0 + kb : t.ka1 + (kb - t.nka0);
-        tma_load_2d(c.smem + s * t.stage_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
+      if (c.tr) c.tr[2] = ps_now();
+      for (int st = 0; st < npre; ++st) {
+        const uint32_t s = (c.it + st) % PS_STAGES;
+        const int n_sub = min(kps, nk - st * kps);
+        for (int u = 0; u < n_sub; ++u)
+          tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, st * kps + u) * BK, t.a_row, &c.full[s]);
       }
-      for (int kb = npre; kb < nk; ++kb) {
-        const uint32_t i = c.it + kb, s = i % PS_STAGES;
+      for (int st = npre; st < n_st; ++st) {
+        const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
-        mbar_expect_tx(&c.full[s], tx);
-        const int ka = kb < t.nka0 ? t.ka0 + kb : t.ka1 + (kb - t.nka0);
-        tma_load_2d(c.smem + s * t.stage_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
-        tma_load_2d(c.smem + s * t.stage_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
+        const int n_sub = min(kps, nk - st * kps);
+        mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
+        for (int u = 0; u < n_sub; ++u) {
+          const int kb = st * kps + u, ka = ps_ka(t, kb);
+          uint8_t* sa = c.smem + s * t.stage_bytes + u * sub_bytes;
+          tma_load_2d(sa, t.tmA, ka * BK, t.a_row, &c.full[s]);
+          tma_load_2d(sa + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const uint32_t i = c.it + kb, s = i % PS_STAGES;
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(c.smem + s * t.stage_bytes);
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-        if constexpr (GRU_U == 0) {
-          const uint32_t idesc = umma_idesc_bf16(t.bn);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        } else {
-          // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U)
-          constexpr int U = GRU_U;
-          if (kb < t.nka0) {
-            const uint32_t idesc = umma_idesc_bf16(3 * U);
+        if (c.tr && st == 0) c.tr[3] = ps_now();
+        const int n_sub = min(kps, nk - st * kps);
+        for (int u = 0; u < n_sub; ++u) {
+          const int kb = st * kps + u;
+          const uint32_t a_addr = smem_u32(c.smem + s * t.stage_bytes + u * sub_bytes);
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          if constexpr (GRU_U == 0) {
+            const uint32_t idesc = umma_idesc_bf16(t.bn);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           } else {
-            const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U);
-            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U)
+            constexpr int U = GRU_U;
+            if (kb < t.nka0) {
+              const uint32_t idesc = umma_idesc_bf16(3 * U);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
-              umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > t.nka0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            } else {
+              const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U);
+              const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
+                umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > t.nka0 || k > 0) ? 1u : 0u);
+              }
             }
           }
         }
@@ -311,28 +344,44 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   } else {
     const int tid = (int)threadIdx.x - 64;
     pre(tid);
-    if (lane == 0) {
-      ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
-      ps_flag_wait(t.e1, t.et1, c.dbg, t.code | (6u << 20));
-    }
+    if (lane == 0) ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
     __syncwarp();
     epi_bar_sync();
+    if (c.tr && tid == 0) c.tr[4] = ps_now();
     if (lane == 0) ps_mbar_wait(c.tmem_full, c.tile_no & 1u, c.dbg, t.code | (7u << 20));
     __syncwarp();
     tc_fence_after();
+    if (c.tr && tid == 0) c.tr[5] = ps_now();
     epilogue(tid);
-    // publish: this thread's global stores are made visible device-wide (and to the async proxy of the consumers' TMA loads)
-    __threadfence();
-    fence_proxy_async_all();
-    epi_bar_sync();
-    if (tid == 0 && t.sig) red_release_add(t.sig, 1u);
+    if (c.tr && tid == 0) c.tr[6] = ps_now();
+    if (t.sig) {   // publish to other CTAs' waiters: CTA barrier, then one device-scope fence + release (cumulative over the CTA's stores)
+      epi_bar_sync();
+      if (tid == 0) {
+        __threadfence();
+        red_release_add(t.sig, 1u);
+      }
+    }
+    fence_proxy_async_all();   // this thread's generic-proxy accesses to the ring / its global stores vs the next tile's TMA traffic
+    if (c.tr && tid == 0) c.tr[7] = ps_now();
   }
-  c.it += (uint32_t)nk;
+  if (warp < 2) {   // mirror the cluster barriers of the epilogue (barrier.cluster counts every thread of the cluster)
+    __syncwarp();
+    for (int b = 0; b < t.cbar; ++b) { cluster_arrive_release(); cluster_wait_acquire(); }
+  }
+  c.it += (uint32_t)n_st;
   c.tile_no += 1;
+  if (c.tr) c.tr += 8;
   // the next tile reuses the ring (the epilogue's transposition buffer) and the TMEM accumulator
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+}
+
+// hand-over between two layers of a chain cluster: every thread of the four CTAs; release / acquire at cluster scope orders the
+// global stores of the finished layer before the TMA loads of the next one (plus the proxy fence in ps_run_tile)
+__device__ __forceinline__ void ps_cluster_handover() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const __grid_constant__ PersistParams P) {
@@ -347,9 +396,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   const int warp = threadIdx.x >> 5;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&P.tmS[0]); tma_prefetch_desc(&P.tmS[1]); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
-    tma_prefetch_desc(&P.tmWgru); tma_prefetch_desc(&P.tmWp1); tma_prefetch_desc(&P.tmWp2); tma_prefetch_desc(&P.tmWp3);
-    tma_prefetch_desc(&P.tmWh1); tma_prefetch_desc(&P.tmWh2); tma_prefetch_desc(&P.tmWh3);
+    tma_prefetch_desc(&P.tmS); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
     for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
@@ -361,8 +408,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr;
   const int n_items = sched[0];
+  const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
   const int nkz = ZP / 64, nkh = P.DP / 64, kh0 = nkz + 1;
   const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D, ldA = (long)H * A;
@@ -371,107 +419,127 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   const uint32_t taddr = c.tmem + ((uint32_t)(q * 32) << 16);
   float* tile = reinterpret_cast<float*>(smem);
   auto flag = [&](int kind, int m) { return P.flags + (long)(kind * mt + m) * 32; };
+  auto tile_init = [&](PsTile& t, int layer, int j, int m_tile) {
+    t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0;
+    t.w0 = nullptr; t.t0 = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
+    t.code = ((unsigned)role << 24) | ((unsigned)layer << 16) | ((unsigned)j << 8) | (unsigned)m_tile;
+  };
+  auto trace_window = [&](int j) {   // (at most PS_TRACE_SLOTS tiles per CTA are recorded)
+    if (P.trace) {
+      if (j == P.trace_j0) c.tr = P.trace + (long)blockIdx.x * PS_TRACE_SLOTS * 8;
+      if (j == P.trace_j1) c.tr = nullptr;
+    }
+  };
+  // the [h, z] heads' output layer (EpiHeads) is parameterised once; only the per-state output pointers move
+  EpiHeads::Params hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.bias = P.h3_b;
+  hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
+  hp.buckets[HS_REWARD] = P.bk_rew;
+  hp.NB = P.NB; hp.A = A;
+  hp.ld_normals = A; hp.ld_act = ldA; hp.ld_value[HS_REWARD] = H; hp.ld_value[HS_CONT] = H;
 
-  for (int j = 0; j <= H; ++j) {
-    const int sb = j & 1;
-#pragma unroll 1
-    for (int it = 0; it < n_items; ++it) {
-      const int kind = sched[1 + 3 * it], m_tile = sched[2 + 3 * it], x = sched[3 + 3 * it];
-      const int m0 = m_tile * BM;
-      const int m = m0 + row;
+  if (role == PS_CHAIN) {
+    // ---- one 4-CTA cluster per m-tile: prior L1 -> L2 -> logits + sample -> actor L1 -> L2 -> output, for every state ----
+    const int m_tile = sched[2];
+    const int rank = (int)cluster_ctarank();
+    const int m0 = m_tile * BM, m = m0 + row;
+    const int ya = (1 + HS_ACTOR) * Mp;   // the actor's slot of the hidden-activation buffers (slot 0 = prior)
+    for (int j = 0; j <= H; ++j) {
+      trace_window(j);
+      const int s_row = j * B + m0;       // this m-tile's rows of state j in the time-major state buffer
       PsTile t;
-      t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka1 = 0; t.nka1 = 0;
-      t.w0 = nullptr; t.t0 = 0; t.e0 = nullptr; t.e1 = nullptr; t.et0 = 0; t.et1 = 0; t.sig = nullptr;
-      t.code = ((unsigned)kind << 24) | ((unsigned)j << 8) | (unsigned)m_tile;
-      if (kind == PS_P12) {
-        if (j == 0) continue;
-        {   // prior L1: h_j -> Y1[slot 0]   (DynamicsPredictors.py:15-18)
-          t.tmA = &P.tmS[sb]; t.tmB = &P.tmWp1; t.a_row = m0; t.b_row = 0; t.ka0 = kh0; t.nka0 = nkh; t.bn = P.bnp1;
+      if (j >= 1) {
+        {   // prior L1: h_j -> Y1[slot 0], this CTA's 64 columns   (DynamicsPredictors.py:15-18)
+          tile_init(t, 0, j, m_tile);
+          t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
           t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
-          const TileG g{B, P.bnp1, 0};
+          const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+          ps_cluster_handover();
         }
-        {   // prior L2: Y1 -> Y2[slot 0]   (:19-22); same CTA, so program order + the publication fences order the hand-over
-          t.tmA = &P.tmY1; t.tmB = &P.tmWp2; t.a_row = m0; t.b_row = 0; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = P.bnp2;
-          t.w0 = nullptr; t.t0 = 0; t.sig = flag(PF_P2, m_tile);
-          t.code |= 1u << 16;
-          const TileG g{B, P.bnp2, 0};
+        {   // prior L2: Y1 -> Y2[slot 0]   (:19-22)
+          tile_init(t, 1, j, m_tile);
+          t.tmA = &P.tmY1; t.tmB = &P.tmWp2q; t.a_row = m0; t.b_row = 64 * rank; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 1;
+          const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p2_b, P.p2_g, P.p2_be, nullptr, 0, P.Y2, 256, 0, 0, P.hp2, 1e-5f, P.bnp2};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+          ps_cluster_handover();
         }
-      } else if (kind == PS_P3) {
-        if (j == 0) continue;
-        // prior logits + sample of latent rows [x * bn_cat / 32, ..): z_j -> S[sb] z columns, latent[:, j], idx[:, j - 1]   (:23, 31-40)
-        t.tmA = &P.tmY2; t.tmB = &P.tmWp3; t.a_row = m0; t.b_row = x * P.bn_cat; t.ka0 = 0; t.nka0 = (P.hp2 + 63) / 64; t.bn = P.bn_cat;
-        t.w0 = flag(PF_P2, m_tile); t.t0 = (unsigned)j;
-        t.sig = flag(PF_Z, m_tile);
-        const TileG g{B, P.bn_cat, 0};
-        const EpiCat::Params p{P.p3_b, P.uniforms + (long)(j - 1) * B * R, P.latent + (long)j * ZP, nullptr,
-                               P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S[sb], nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
-                               RowMap{0, 0, 0, 0}};
-        ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
-                       [&](int tid) { EpiCat::run(p, g, epi_sm, tile, taddr, m, row, part, x, tid); });
-      } else if (kind == PS_HEAD) {
-        const int head = x;
-        if (head == HS_ACTOR ? j >= H : j == 0) continue;   // actor on states 0 .. H-1, reward / continue on states 1 .. H
-        {   // L1: [z_j | h_j] -> Y1[slot 1 + head]
-          t.tmA = &P.tmS[sb]; t.tmB = &P.tmWh1; t.a_row = m0; t.b_row = head * 256;
-          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = P.bnh1;
-          t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);
-          t.sig = flag(PF_HL1, m_tile);
-          const TileG g{B, P.bnh1, 0};
-          const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, head, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, head, tid); });
-        }
-        {   // L2: Y1 -> Y2
-          t.tmA = &P.tmY1; t.tmB = &P.tmWh2; t.a_row = Mp + head * Mp + m0; t.b_row = head * 256;
-          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.ka1 = 0; t.nka1 = 0; t.bn = P.bnh2;
-          t.w0 = nullptr; t.t0 = 0; t.sig = nullptr;
-          t.code |= 1u << 16;
-          const TileG g{B, P.bnh2, 0};
-          const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, head, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, head, tid); });
-        }
-        {   // output layer
-          t.tmA = &P.tmY2; t.tmB = &P.tmWh3; t.a_row = Mp + head * Mp + m0; t.b_row = head * 256;
-          t.ka0 = 0; t.nka0 = (P.hh2 + 63) / 64; t.bn = 256;
-          t.sig = head == HS_ACTOR ? flag(PF_A, m_tile) : nullptr;
-          t.code |= 2u << 16;
+        // prior logits + sample: 256 logit columns (8 latent rows) per tile, tiles rank, rank + 4, ...   (:23, 31-40)
+        // -> z_j into the state buffer, latent[:, j], idx[:, j - 1]
+        for (int x = rank; x < P.nq; x += 4) {
+          tile_init(t, 2, j, m_tile);
+          t.tmA = &P.tmY2; t.tmB = &P.tmWp3; t.a_row = m0; t.b_row = x * 256; t.ka0 = 0; t.nka0 = (P.hp2 + 63) / 64; t.bn = 256;
+          t.sig = flag(PF_Z, m_tile);
           const TileG g{B, 256, 0};
-          EpiHeads::Params hp;
-          memset(&hp, 0, sizeof(hp));
-          hp.bias = P.h3_b;
-          hp.kind[HS_REWARD] = HEAD_BUCKET; hp.kind[HS_CONT] = HEAD_SIGMOID; hp.kind[HS_ACTOR] = HEAD_ACTOR;
-          hp.buckets[HS_REWARD] = P.bk_rew;
-          hp.NB = P.NB; hp.A = A;
-          if (head == HS_ACTOR) {
-            hp.normals = P.normals + (long)j * B * A; hp.ld_normals = A;
-            hp.mu = P.mu + (long)j * A; hp.sigma = P.sigma + (long)j * A; hp.action = P.actions + (long)j * A; hp.ld_act = ldA;
-          } else {
-            hp.value[HS_REWARD] = P.rewards + (j - 1); hp.ld_value[HS_REWARD] = H;
-            hp.value[HS_CONT] = P.continues + (j - 1); hp.ld_value[HS_CONT] = H;
-          }
-          ps_run_tile<0>(c, t, [&](int tid) { EpiHeads::stage(hp, g, head, epi_sm, tid, m0); },
-                         [&](int tid) { EpiHeads::run(hp, g, epi_sm, tile, taddr, m, row, part, head, tid); });
+          const EpiCat::Params p{P.p3_b, P.uniforms + (long)(j - 1) * B * R, P.latent + (long)j * ZP, nullptr,
+                                 P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
+                                 RowMap{0, 0, 0, 0}};
+          ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
+                         [&](int tid) { EpiCat::run(p, g, epi_sm, tile, taddr, m, row, part, x, tid); });
         }
-      } else {   // PS_GRU: h_{j+1} = GRU([z_j, a_j], h_j)   (SequenceModel.py:19-24)
-        if (j >= H) continue;
-        const int n_tile = x;
+        ps_cluster_handover();
+      }
+      if (j < H) {
+        {   // actor L1: [z_j | h_j] -> Y1[actor slot]   (Agent.py:178-181)
+          tile_init(t, 0, j, m_tile);
+          t.code |= 1u << 19;
+          t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
+          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          const TileG g{B, 64, 0};
+          const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
+          ps_cluster_handover();
+        }
+        {   // actor L2   (:182-185)
+          tile_init(t, 1, j, m_tile);
+          t.code |= 1u << 19;
+          t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
+          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 1;
+          const TileG g{B, 64, 0};
+          const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
+          ps_cluster_handover();
+        }
+        if (rank == 0) {   // mu / log-sigma rows (32 packed rows) -> a_j = tanh(mu + sigma * eps)   (Agent.py:186-187, 199-209)
+          tile_init(t, 2, j, m_tile);
+          t.code |= 1u << 19;
+          t.tmA = &P.tmY2; t.tmB = &P.tmWh3a; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256; t.ka0 = 0; t.nka0 = (P.hh2 + 63) / 64; t.bn = 32;
+          t.sig = flag(PF_A, m_tile);
+          const TileG g{B, 32, 0};
+          hp.normals = P.normals + (long)j * B * A;
+          hp.mu = P.mu + (long)j * A; hp.sigma = P.sigma + (long)j * A; hp.action = P.actions + (long)j * A;
+          ps_run_tile<0>(c, t, [&](int tid) { EpiHeads::stage(hp, g, HS_ACTOR, epi_sm, tid, m0); },
+                         [&](int tid) { EpiHeads::run(hp, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
+        }
+      }
+    }
+    ps_cluster_handover();   // nobody leaves while a peer may still write into its shared memory
+  } else if (role == PS_GRU) {
+    // ---- h_{j+1} = GRU([z_j, a_j], h_j)   (SequenceModel.py:19-24): one (m-tile, n-tile) per item ----
+    float4* wa = reinterpret_cast<float4*>(smem + PS_WA_OFF);
+    float* hp_tile = reinterpret_cast<float*>(smem + PS_HP_OFF);
+    for (int j = 0; j < H; ++j) {
+      trace_window(j);
+#pragma unroll 1
+      for (int it = 0; it < n_items; ++it) {
+        const int m_tile = sched[2 + 3 * it], n_tile = sched[3 + 3 * it];
+        const int m0 = m_tile * BM, m = m0 + row;
+        PsTile t;
+        tile_init(t, 0, j, m_tile);
         t.stage_bytes = PS_GRU_STAGE_BYTES;
-        t.tmA = &P.tmS[sb]; t.tmB = &P.tmWgru; t.a_row = m0; t.b_row = n_tile * 3 * P.U;
+        t.tmA = &P.tmS; t.tmB = &P.tmWgru; t.a_row = j * B + m0; t.b_row = n_tile * 3 * P.U;
         t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.b_follows_a = 1; t.bn = 3 * P.U;
         t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);            // z_j sampled (implies h_j)
         t.e0 = flag(PF_A, m_tile); t.et0 = (unsigned)(j + 1);               // a_j
-        t.e1 = flag(PF_HL1, m_tile); t.et1 = j >= 1 ? (unsigned)(1 + 3 * (j - 1)) : 0u;   // every head of state j - 1 has read the buffer h_{j+1} overwrites
         t.sig = flag(PF_H, m_tile);
-        float4* wa = reinterpret_cast<float4*>(smem + PS_WA_OFF);
-        float* hp_tile = reinterpret_cast<float*>(smem + PS_HP_OFF);
-        __nv_bfloat16* s_h = P.S[sb ^ 1] + ZP + 64;
+        __nv_bfloat16* s_h = P.S + (long)(j + 1) * B * P.KS + ZP + 64;
         if (P.U == 32) {
           const EpiGruP<32>::Params p{P.b_ih, P.b_hh, P.hidden + (long)j * D, P.hidden + (long)(j + 1) * D, s_h, ldH, P.KS, D,
                                       P.Wgru + ZP, P.KS, A, P.actions + (long)j * A, ldA};
@@ -482,6 +550,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                                       P.Wgru + ZP, P.KS, A, P.actions + (long)j * A, ldA};
           ps_run_tile<64>(c, t, [&](int tid) { EpiGruP<64>::stage(p, n_tile, m0, B, epi_sm, wa, hp_tile, tid); },
                           [&](int tid) { EpiGruP<64>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); });
+        }
+      }
+    }
+  } else if (role == PS_RC) {
+    // ---- reward / continue heads of the sampled states 1 .. H (DynamicsPredictors.py:64-74, 95-105): nothing waits for these ----
+    for (int j = 1; j <= H; ++j) {
+      trace_window(j);
+#pragma unroll 1
+      for (int it = 0; it < n_items; ++it) {
+        const int m_tile = sched[2 + 3 * it], head = sched[3 + 3 * it];
+        const int m0 = m_tile * BM, m = m0 + row;
+        const int yr = (1 + head) * Mp + m0;
+        PsTile t;
+        {   // L1: [z_j | h_j] -> Y1[slot 1 + head]
+          tile_init(t, 0, j, m_tile);
+          t.tmA = &P.tmS; t.tmB = &P.tmWh1; t.a_row = j * B + m0; t.b_row = head * 256;
+          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = P.bnh1;
+          t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);
+          const TileG g{B, P.bnh1, 0};
+          const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, head, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, head, tid); });
+        }
+        {   // L2: Y1 -> Y2 (same CTA: program order + the fences at the end of a tile order the hand-over)
+          tile_init(t, 1, j, m_tile);
+          t.tmA = &P.tmY1; t.tmB = &P.tmWh2; t.a_row = yr; t.b_row = head * 256; t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = P.bnh2;
+          const TileG g{B, P.bnh2, 0};
+          const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, head, epi_sm, tid, m0); },
+                         [&](int tid) { EpiLnSilu::run(p, g, epi_sm, tile, taddr, m, row, part, head, tid); });
+        }
+        {   // output layer: bucket softmax -> symexp (reward), sigmoid (continue)
+          tile_init(t, 2, j, m_tile);
+          t.tmA = &P.tmY2; t.tmB = &P.tmWh3; t.a_row = yr; t.b_row = head * 256; t.ka0 = 0; t.nka0 = (P.hh2 + 63) / 64; t.bn = 256;
+          const TileG g{B, 256, 0};
+          hp.value[HS_REWARD] = P.rewards + (j - 1);
+          hp.value[HS_CONT] = P.continues + (j - 1);
+          ps_run_tile<0>(c, t, [&](int tid) { EpiHeads::stage(hp, g, head, epi_sm, tid, m0); },
+                         [&](int tid) { EpiHeads::run(hp, g, epi_sm, tile, taddr, m, row, part, head, tid); });
         }
       }
     }
@@ -497,11 +604,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
 // host side: static schedule, launch
 // ------------------------------------------------------------------------------------------
 struct drm_persist {
-  int U = 0, bn_cat = 0, nt = 0, nq = 0, n_cta = 0;
+  int U = 0, nt = 0, nq = 0, n_cta = 0;
   int* sched = nullptr;        // device [n_cta * PS_SCHED_STRIDE]
   unsigned* flags = nullptr;   // device [PF_COUNT * mt * 32]
   unsigned* dbg = nullptr;     // host-mapped [PS_DBG_WORDS]
   size_t flag_bytes = 0;
+  __nv_bfloat16* S = nullptr;  // time-major state slabs [(H + 1) * B + 128, KS]
+  CUtensorMap tmS;
+  unsigned long long* trace = nullptr;   // device [n_cta * PS_TRACE_SLOTS * 8] while tracing
+  int trace_j0 = 0, trace_j1 = 0;
   bool tried = false, ok = false;
 };
 
@@ -513,60 +624,75 @@ static void persist_free(drm_persist* ps) {
   delete ps;
 }
 
-static int persist_sm_count() {
+static void persist_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_cta, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(n_cta);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = PS_TOTAL;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
+// clusters of 4 CTAs of this kernel the device can hold at once (0: the kernel cannot run here)
+static int persist_cluster_capacity() {
   static int n = -1;
   if (n < 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
-    int per_sm = 0;
-    if (sms > 0 && cudaFuncSetAttribute(rollout_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_TOTAL) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_persist_kernel, GEMM_THREADS, PS_TOTAL) == cudaSuccess && per_sm >= 1)
-      n = sms;
-    else
-      n = 0;
+    n = 0;
+    if (cudaFuncSetAttribute(rollout_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_TOTAL) == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute attr[1];
+      int sms = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      persist_launch_config(cfg, attr, (sms / 4) * 4, nullptr);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, rollout_persist_kernel, &cfg) == cudaSuccess) n = nc;
+    }
     cudaGetLastError();
   }
   return n;
 }
 
-// Static schedule: one GRU tile, one prior chain, one sampling tile or one actor chain per CTA (the per-step critical path and
-// the GRU accumulators never queue behind other work); the reward / continue chains share whatever CTAs are left.
+// Static schedule.  Cluster c < mt: the MLP chain of m-tile c.  Then the GRU tiles, one per CTA.  Every CTA left over takes
+// reward / continue chains (m-tile, head) round-robin.
 static bool persist_plan(drm_rollout* r, drm_persist* ps) {
   drm_rssm* m = r->m;
-  const int n_sm = persist_sm_count();
+  const int cap = persist_cluster_capacity();
   const int mt = r->Mp / BM;
-  if (n_sm <= 0 || m->d.A > 4) return false;
-  static const int cand[4][2] = {{32, 128}, {64, 128}, {32, 256}, {64, 256}};
-  for (int ci = 0; ci < 4; ++ci) {
-    const int U = cand[ci][0], bn_cat = cand[ci][1];
-    if (m->ZP % bn_cat) continue;
-    const int nt = ceil_div(m->d.D, U), nq = m->ZP / bn_cat;
-    const int crit = mt * nt + mt + mt * nq + mt;
-    const int rest = n_sm - crit;
-    if (rest < 1 || ceil_div(2 * mt, rest) > PS_MAX_ITEMS) continue;
-    ps->U = U; ps->bn_cat = bn_cat; ps->nt = nt; ps->nq = nq;
-    std::vector<int> sc((size_t)n_sm * PS_SCHED_STRIDE, 0);
-    int cta = 0;
+  if (cap <= 0 || m->d.A > 4 || m->ZP % 256) return false;
+  const size_t s_rows = (size_t)(r->H + 1) * r->B + BM;
+  if (s_rows * m->KS * sizeof(__nv_bfloat16) > ((size_t)2 << 30)) return false;
+  for (int U = 32; U <= 64; U *= 2) {
+    const int nt = ceil_div(m->d.D, U);
+    const int gru_cl = ceil_div(mt * nt, 4);
+    const int spare = (cap - mt - gru_cl) * 4 + (gru_cl * 4 - mt * nt);   // CTAs left for the reward / continue chains
+    if (cap < mt + gru_cl || spare < 1 || ceil_div(2 * mt, spare) > PS_MAX_ITEMS) continue;
+    ps->U = U; ps->nt = nt; ps->nq = m->ZP / 256;
+    const int n_rc = std::min(spare, 2 * mt);
+    const int n_cta = round_up(4 * mt + mt * nt + n_rc, 4);
+    std::vector<int> sc((size_t)n_cta * PS_SCHED_STRIDE, 0);
     auto add = [&](int c, int kind, int mm, int x) {
       int* rec = sc.data() + (size_t)c * PS_SCHED_STRIDE;
       const int n = rec[0]++;
       rec[1 + 3 * n] = kind; rec[2 + 3 * n] = mm; rec[3 + 3 * n] = x;
     };
-    // critical-path roles first so that they land on distinct SMs; m-tile-major so that an m-tile's chain is spread over the chip
-    for (int mm = 0; mm < mt; ++mm) add(cta++, PS_HEAD, mm, HS_ACTOR);
-    for (int mm = 0; mm < mt; ++mm) add(cta++, PS_P12, mm, 0);
     for (int mm = 0; mm < mt; ++mm)
-      for (int qq = 0; qq < nq; ++qq) add(cta++, PS_P3, mm, qq);
-    for (int mm = 0; mm < mt; ++mm)
-      for (int n = 0; n < nt; ++n) add(cta++, PS_GRU, mm, n);
-    const int first_rest = cta;
+      for (int k = 0; k < 4; ++k) add(4 * mm + k, PS_CHAIN, mm, 0);
+    int cta = 4 * mt;
+    for (int n = 0; n < nt; ++n)          // n-major: the GRU tiles of one m-tile are spread over the chip's clusters
+      for (int mm = 0; mm < mt; ++mm) add(cta++, PS_GRU, mm, n);
     for (int mm = 0, k = 0; mm < mt; ++mm)
-      for (int hd = 0; hd < 2; ++hd, ++k) add(first_rest + k % rest, PS_HEAD, mm, hd == 0 ? HS_REWARD : HS_CONT);
-    ps->n_cta = std::min(n_sm, first_rest + std::min(rest, 2 * mt));
+      for (int hd = 0; hd < 2; ++hd, ++k) add(cta + k % n_rc, PS_RC, mm, hd == 0 ? HS_REWARD : HS_CONT);
+    ps->n_cta = n_cta;
     if (dev_alloc(r->allocs, &ps->sched, sc.size()) != DRM_OK) return false;
     if (cudaMemcpy(ps->sched, sc.data(), sc.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
     ps->flag_bytes = (size_t)PF_COUNT * mt * 32 * sizeof(unsigned);
     if (dev_alloc(r->allocs, &ps->flags, ps->flag_bytes / sizeof(unsigned)) != DRM_OK) return false;
+    if (dev_alloc(r->allocs, &ps->S, s_rows * m->KS) != DRM_OK) return false;
+    if (make_tmap_bf16_2d(&ps->tmS, ps->S, s_rows, m->KS, m->KS, BM) != DRM_OK) return false;
     if (cudaHostAlloc((void**)&ps->dbg, PS_DBG_WORDS * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
     memset(ps->dbg, 0, PS_DBG_WORDS * sizeof(unsigned));
     return true;
@@ -591,17 +717,17 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   drm_persist* ps = r->ps;
   const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP;
   const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D;
-  RC(pack_cols(r->S[0], m->KS, 0, z0, ZP, ZP, B, latent, ldL, st));
-  RC(pack_cols(r->S[0], m->KS, ZP + 64, h0, D, D, B, hidden, ldH, st));
+  RC(pack_cols(ps->S, m->KS, 0, z0, ZP, ZP, B, latent, ldL, st));
+  RC(pack_cols(ps->S, m->KS, ZP + 64, h0, D, D, B, hidden, ldH, st));
   DRM_CUDA(cudaMemsetAsync(ps->flags, 0, ps->flag_bytes, st));
   PersistParams P;
   memset(&P, 0, sizeof(P));
   const int v = ps->U == 64 ? 1 : 0;
-  P.tmS[0] = r->tmS[0]; P.tmS[1] = r->tmS[1]; P.tmY1 = r->tmY1; P.tmY2 = r->tmY2;
-  P.tmWgru = m->tmWgru2[v]; P.tmWp1 = m->tmWp1; P.tmWp2 = m->tmWp2; P.tmWp3 = ps->bn_cat == 128 ? m->tmWp3h : m->tmWp3;
-  P.tmWh1 = m->tmWh1; P.tmWh2 = m->tmWh2; P.tmWh3 = m->tmWh3;
+  P.tmS = ps->tmS; P.tmY1 = r->tmY1; P.tmY2 = r->tmY2;
+  P.tmWgru = m->tmWgru2[v]; P.tmWp1q = m->tmWp1q; P.tmWp2q = m->tmWp2q; P.tmWp3 = m->tmWp3;
+  P.tmWh1q = m->tmWh1q; P.tmWh2q = m->tmWh2q; P.tmWh3a = m->tmWh3a; P.tmWh1 = m->tmWh1; P.tmWh2 = m->tmWh2; P.tmWh3 = m->tmWh3;
   P.B = B; P.H = H; P.D = D; P.DP = m->DP; P.ZP = ZP; P.R = m->d.R; P.A = m->d.A; P.NB = m->d.NB; P.KS = m->KS; P.Mp = r->Mp; P.mt = r->Mp / BM;
-  P.U = ps->U; P.nt = ps->nt; P.bn_cat = ps->bn_cat; P.nq = ps->nq;
+  P.U = ps->U; P.nt = ps->nt; P.nq = ps->nq;
   P.bnp1 = m->bnp1; P.bnp2 = m->bnp2; P.bnh1 = m->bnh1; P.bnh2 = m->bnh2;
   P.hp1 = m->d.h_prior[0]; P.hp2 = m->d.h_prior[1]; P.hh1 = m->d.h_head[0]; P.hh2 = m->d.h_head[1];
   P.b_ih = m->b_ih; P.b_hh = m->b_hh;
@@ -609,21 +735,15 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   P.h1_b = m->h1_b; P.h1_g = m->h1_g; P.h1_be = m->h1_be; P.h2_b = m->h2_b; P.h2_g = m->h2_g; P.h2_be = m->h2_be; P.h3_b = m->h3_b;
   P.bk_rew = m->bk_rew;
   P.Wgru = m->Wgru2[v];
-  P.S[0] = r->S[0]; P.S[1] = r->S[1]; P.Y1 = r->Y1; P.Y2 = r->Y2;
+  P.S = ps->S; P.Y1 = r->Y1; P.Y2 = r->Y2;
   P.uniforms = uniforms; P.normals = normals;
   P.latent = latent; P.hidden = hidden; P.actions = actions; P.rewards = rewards; P.continues = continues; P.mu = mu; P.sigma = sigma;
   P.idx = idx;
   P.flags = ps->flags; P.dbg = ps->dbg; P.sched = ps->sched;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ps->n_cta);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = PS_TOTAL;
-  cfg.stream = st;
+  P.trace = ps->trace; P.trace_j0 = ps->trace_j0; P.trace_j1 = ps->trace_j1;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident, or the launch fails: the in-kernel hand-overs need every producer running
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  persist_launch_config(cfg, attr, ps->n_cta, st);   // (co-residency of all clusters was checked against the device's capacity in persist_plan)
   DRM_CUDA(cudaLaunchKernelEx(&cfg, rollout_persist_kernel, P));
   DRM_LAUNCH_CHECK();
   return DRM_OK;

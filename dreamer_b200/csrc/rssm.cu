@@ -226,6 +226,7 @@ struct drm_rssm {
   float *bk_rew, *bk_crit;       // [NB]
   CUtensorMap tmWp1q, tmWp2q, tmWh1q, tmWh2q;   // box rows 64: the cluster-of-4 LN stage
   CUtensorMap tmWp3h;                           // box rows 128: half-width categorical tiles for small grids
+  CUtensorMap tmWh3a;                           // box rows 32: the actor's mu / log-sigma rows (persistent rollout kernel)
   CUtensorMap tmWgruQ[2];                      // box rows U / 2: the CTA-pair GRU kernel stages gate blocks and n halves separately
   CUtensorMap tmWgru2[2], tmWp1, tmWp2, tmWp3, tmWh1, tmWh2, tmWh3;
   std::vector<MatOp> mat_ops;
@@ -426,6 +427,7 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1));
   TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2));
   TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
+  TRY(make_tmap_bf16_2d(&m->tmWh3a, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 32));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rssm_destroy(m);
@@ -789,7 +791,7 @@ extern "C" int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n) {
   const bool ok = opts().persist && persist_eligible(r);
   out[0] = ok ? 1u : 0u;
   if (!r->ps || !r->ps->ok) return DRM_OK;
-  out[1] = (uint32_t)r->ps->U; out[2] = (uint32_t)r->ps->bn_cat; out[3] = (uint32_t)r->ps->n_cta;
+  out[1] = (uint32_t)r->ps->U; out[2] = 256u; out[3] = (uint32_t)r->ps->n_cta;
   out[4] = r->ps->dbg[8 * 160];
   int k = 5;
   for (int c = 0; c < 160 && k + 5 <= n; ++c) {
@@ -797,6 +799,30 @@ extern "C" int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n) {
     if (rec[0] == 0 && rec[2] == 0) continue;
     for (int j = 0; j < 5; ++j) out[k++] = rec[j];
   }
+  return DRM_OK;
+}
+
+// Debug: per-tile timestamps of the persistent kernel.  out == NULL: record the tiles of states [j0, j0 + nj) of the following
+// rollouts (nj small: 32 tiles per CTA are kept).  out != NULL: copy n_cta * 32 records of 8 u64
+// {code, start, dependency seen, first operands, epilogue ready, accumulator ready, epilogue done, published} (globaltimer ns;
+// code = kind << 24 | layer << 16 | state << 8 | m-tile) to the host buffer (n_words >= n_cta * 256) and stop recording.
+extern "C" int drm_rollout_trace(drm_rollout* r, int32_t j0, int32_t nj, unsigned long long* out, int64_t n_words) {
+  DRM_REQUIRE(r, DRM_ERR_ARG, "drm_rollout_trace: NULL workspace");
+  RC(check_arch());
+  DRM_REQUIRE(persist_eligible(r), DRM_ERR_ARG, "drm_rollout_trace: this workspace does not use the persistent kernel");
+  drm_persist* ps = r->ps;
+  const size_t words = (size_t)ps->n_cta * PS_TRACE_SLOTS * 8;
+  if (!out) {
+    if (!ps->trace) RC(dev_alloc(r->allocs, &ps->trace, words));
+    DRM_CUDA(cudaMemset(ps->trace, 0, words * sizeof(unsigned long long)));
+    ps->trace_j0 = j0; ps->trace_j1 = j0 + nj;
+    return DRM_OK;
+  }
+  DRM_REQUIRE(ps->trace && n_words >= (int64_t)words, DRM_ERR_ARG, "drm_rollout_trace: tracing is off or the buffer is too small");
+  DRM_CUDA(cudaDeviceSynchronize());
+  DRM_CUDA(cudaMemcpy(out, ps->trace, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ps->trace_j0 = ps->trace_j1 = 0;
+  ps->trace = nullptr;   // (the buffer stays in the workspace's allocation bag)
   return DRM_OK;
 }
 

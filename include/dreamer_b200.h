@@ -213,6 +213,12 @@ int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0, const floa
 /* out[3] = CTAs, out[4] = number of timed-out waits recorded, then records {code, seen, want, thread, cta} (n >= 5 words). */
 int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n);
 
+/* Debug: per-tile timestamps of the persistent kernel.  out == NULL: record the tiles of states [j0, j0 + nj) of the rollouts   */
+/* that follow (32 tiles per CTA are kept).  out != NULL: copy CTAs * 32 records of 8 u64 {code, start, dependency seen, first  */
+/* operands landed, epilogue ready, accumulator ready, epilogue done, published} (globaltimer ns; code = kind << 24 | layer << 16 */
+/* | state << 8 | m-tile) into out (n_words >= CTAs * 256) and stop recording.                                               */
+int drm_rollout_trace(drm_rollout* r, int32_t j0, int32_t nj, unsigned long long* out, int64_t n_words);
+
 /* Step-level entry points behind the drop-in classes.  They run on the rollout workspace (any   */
 /* N <= B of drm_rollout_create).                                                                */
 /* SequenceModel.forward  SequenceModel.py:19-24:  z [N, R*C], h [N, D], a [N, A] -> h_out [N, D] */
