@@ -239,14 +239,14 @@ struct EpiLnSiluN4T {
     }
   }
   static __device__ __forceinline__ int cnt_of(int nv, int first, int width) { return max(0, min(width, nv - first)); }
-  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
-                                             int row, int part, int slot, int tid) {
+  // accumulator -> LayerNorm + SiLU of this thread's 16 columns (v); contains the cluster's ONE statistics barrier
+  static __device__ __forceinline__ void compute(const Params& p, const TileG& g, float* sm, uint32_t taddr, int m, int row, int part,
+                                                 float (&v)[16]) {
     const int nv = p.n_valid;
     const int cr = (int)cluster_ctarank();
     const int c0 = part * 16;                  // CTA-local column of this thread's 16 values
     const int gc0 = 64 * cr + c0;              // tile column
     const int cnt = cnt_of(nv, gc0, 16);
-    float v[16];
     tmem_ld16(taddr + c0, v);
     {
       const float4* b4 = reinterpret_cast<const float4*>(sm + c0);
@@ -315,9 +315,6 @@ struct EpiLnSiluN4T {
     }
     const float rstd = rsqrtf(M2 / (float)nv + p.eps);
     const float nmr = -mean * rstd;
-    const int ncols_tot = min(p.ld_out, (nv + 63) & ~63);   // the consumer reads ceil64(n_valid) columns
-    const int mine = max(0, min(64, ncols_tot - 64 * cr));  // columns this CTA writes (0 or 64)
-    constexpr int pitch = 64 + 4;
     {
       const float4* ga = reinterpret_cast<const float4*>(sm + 256 + c0);
       const float4* be = reinterpret_cast<const float4*>(sm + 512 + c0);
@@ -330,6 +327,15 @@ struct EpiLnSiluN4T {
         v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
       }
     }
+  }
+  // v -> bf16 columns [64 * rank + 16 * part, + 16) of the output row
+  static __device__ __forceinline__ void store(const Params& p, const TileG& g, float* tile, int m, int row, int part, int slot, int tid,
+                                               const float (&v)[16]) {
+    const int cr = (int)cluster_ctarank();
+    const int c0 = part * 16;
+    const int ncols_tot = min(p.ld_out, (p.n_valid + 63) & ~63);   // the consumer reads ceil64(n_valid) columns
+    const int mine = max(0, min(64, ncols_tot - 64 * cr));  // columns this CTA writes (0 or 64)
+    constexpr int pitch = 64 + 4;
     __nv_bfloat16* orow = p.out + (long)(p.out_row0 + slot * p.out_y_stride + m) * p.ld_out + 64 * cr + c0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 && (p.ld_out & 7) == 0) {      // uniform over the CTA: every row is 16-byte aligned
       // this thread's 16 activations are 32 contiguous bytes of its row: two 16-byte stores straight from registers (whole
@@ -345,6 +351,12 @@ struct EpiLnSiluN4T {
     if (mine > 0)
       tile_copy_out(tile, pitch, 64, mine, (m - row), g.M, nullptr, 0,
                     p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out + 64 * cr, p.ld_out, tid);
+  }
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
+                                             int row, int part, int slot, int tid) {
+    float v[16];
+    compute(p, g, sm, taddr, m, row, part, v);
+    store(p, g, tile, m, row, part, slot, tid, v);
   }
 };
 using EpiLnSiluN4 = EpiLnSiluN4T<false>;

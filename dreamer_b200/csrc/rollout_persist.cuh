@@ -65,6 +65,7 @@ struct PersistParams {
   const float *b_ih, *b_hh, *p1_b, *p1_g, *p1_be, *p2_b, *p2_g, *p2_be, *p3_b;
   const float *h1_b, *h1_g, *h1_be, *h2_b, *h2_g, *h2_be, *h3_b, *bk_rew;
   const __nv_bfloat16* Wgru;
+  const __nv_bfloat16* Wh3;   // packed output-layer weights [MAX_HEADS * 256, 256]
   __nv_bfloat16 *S, *Y1, *Y2;   // S: time-major state slabs [(H + 1) * B (+ pad), KS]
   const float *uniforms, *normals;
   float *latent, *hidden, *actions, *rewards, *continues, *mu, *sigma;
@@ -131,7 +132,8 @@ __device__ __forceinline__ void ps_mbar_wait(uint64_t* bar, uint32_t parity, uns
 
 // ------------------------------------------------------------------------------------------
 // GRU epilogue of the persistent kernel: EpiGru's gate math + the action term
-//   gi = W_ih [z, a] + b_ih: the z columns were contracted on the tensor cores, the A (<= 4) action columns are added here.
+//   gi = W_ih [z, a] + b_ih: the z columns were contracted on the tensor cores, the A (<= 3) action columns are added here; the
+//   biases b_r, b_z, b_in ride in the fourth lane of the action-term weights (the action vector is padded with a constant 1).
 // The action and its weights are rounded to bf16 exactly as the state buffer / packed weights of the launch-per-stage path
 // round them, so both paths agree to fp32 summation order.
 // ------------------------------------------------------------------------------------------
@@ -152,24 +154,21 @@ struct EpiGruP {
     const float* actions;     // fp32 [M, ld_act]: this step's action (written by the actor head of the same step)
     long ld_act;
   };
-  // constants [b_r | b_z | b_in | b_hn] -> sm;  action weights -> wa[3U] float4;  h_prev tile -> hp (pitch U + 4)
+  // b_hn -> sm[U];  action weights + biases -> wa[3U] float4 {w_a0, w_a1, w_a2, bias};  h_prev tile -> hp (pitch U + 4)
   static __device__ __forceinline__ void stage(const Params& p, int n_tile, int m0, int M, float* sm, float4* wa, float* hp, int tid) {
     const int D = p.D;
     for (int i = tid; i < U; i += EPI_THREADS) {
       const int u = n_tile * U + i;
-      const bool ok = u < D;
-      sm[i] = ok ? __ldg(p.b_ih + u) + __ldg(p.b_hh + u) : 0.f;
-      sm[U + i] = ok ? __ldg(p.b_ih + D + u) + __ldg(p.b_hh + D + u) : 0.f;
-      sm[2 * U + i] = ok ? __ldg(p.b_ih + 2 * D + u) : 0.f;
-      sm[3 * U + i] = ok ? __ldg(p.b_hh + 2 * D + u) : 0.f;
+      sm[i] = u < D ? __ldg(p.b_hh + 2 * D + u) : 0.f;
     }
     for (int i = tid; i < 3 * U; i += EPI_THREADS) {   // packed rows of this tile: [r (U) | z (U) | n (U)]
       const __nv_bfloat16* w = p.w_a + (long)(n_tile * 3 * U + i) * p.ldw;
+      const int gate = i / U, u = n_tile * U + (i - gate * U);
       float4 v;
       v.x = p.A > 0 ? __bfloat162float(w[0]) : 0.f;
       v.y = p.A > 1 ? __bfloat162float(w[1]) : 0.f;
       v.z = p.A > 2 ? __bfloat162float(w[2]) : 0.f;
-      v.w = p.A > 3 ? __bfloat162float(w[3]) : 0.f;
+      v.w = u < D ? (gate < 2 ? __ldg(p.b_ih + gate * D + u) + __ldg(p.b_hh + gate * D + u) : __ldg(p.b_ih + 2 * D + u)) : 0.f;
       wa[i] = v;
     }
     const int u0 = n_tile * U;
@@ -191,13 +190,12 @@ struct EpiGruP {
     const int u0 = n_tile * U;
     const int m0 = m - row;
     const int nvalid = min(U, p.D - u0);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = make_float4(0.f, 0.f, 0.f, 1.f);
     if (m < M) {
       const float* ap = p.actions + (long)m * p.ld_act;
       a.x = bf16r(__ldcg(ap));
       if (p.A > 1) a.y = bf16r(__ldcg(ap + 1));
       if (p.A > 2) a.z = bf16r(__ldcg(ap + 2));
-      if (p.A > 3) a.w = bf16r(__ldcg(ap + 3));
     }
 #pragma unroll 1
     for (int ps = 0; ps < PASSES; ++ps) {
@@ -212,18 +210,164 @@ struct EpiGruP {
 #pragma unroll
       for (int j = 0; j < UP; ++j) {
         const float4 wr = wa[c + j], wz = wa[U + c + j], wn = wa[2 * U + c + j];
-        const float ar = fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, a.w * wr.w)));
-        const float az = fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, a.w * wz.w)));
-        const float an = fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, a.w * wn.w)));
-        const float rr = sigmoidf_(r_[j] + ar + sm[c + j]);
-        const float zz = sigmoidf_(z_[j] + az + sm[U + c + j]);
-        const float nn = tanhf_(nx[j] + an + sm[2 * U + c + j] + rr * (nh[j] + sm[3 * U + c + j]));
+        const float ar = fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, wr.w)));   // action term + bias
+        const float az = fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, wz.w)));
+        const float an = fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, wn.w)));
+        const float rr = sigmoidf_(r_[j] + ar);
+        const float zz = sigmoidf_(z_[j] + az);
+        const float nn = tanhf_(nx[j] + an + rr * (nh[j] + sm[c + j]));
         hn[j] = (1.0f - zz) * nn + zz * hp[row * PITCH + c + j];
       }
       tile_put<UP>(tile, PITCH, row, c, hn);
     }
     epi_bar_sync();
     tile_copy_out(tile, PITCH, U, nvalid, m0, M, p.h_out + u0, p.ld_h, p.s_h + u0, p.ld_s, tid);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// prior logits -> sample (EpiCat's arithmetic, DynamicsPredictors.py:31-40) for the persistent kernel.  The straight-through
+// latent (onehot + p) - p is exactly 0 off the sampled class, so the fp32 `latent` output is zero-filled once per rollout
+// (cudaMemsetAsync) and the epilogue stores ONE float per 32-class row -- no 128 x 256 fp32 tile through shared memory.
+// ------------------------------------------------------------------------------------------
+struct EpiCatP {
+  using Params = EpiCat::Params;
+  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, uint32_t taddr, int m, int row, int part,
+                                             int slot, int tid) {
+    const int m0 = m - row;
+    const int G = g.bn >> 5;
+    const int col0 = slot * g.bn;
+    const int ncols = max(0, min(g.bn, p.R * 32 - col0));
+    uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);       // [128 rows][8] (sm[256, 1280) holds the uniforms)
+#pragma unroll 1
+    for (int gi = part; gi < G; gi += EPI_PARTS) {
+      float v[32];
+      tmem_ld32(taddr + gi * 32, v);
+      add_const32(v, sm + gi * 32);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = fexpf_(v[j] - mx);
+        s += v[j];
+      }
+      const float u = sm[256 + row * 8 + gi];
+      const float k = 0.99f / s;
+      float cdf = 0.f, phit = 0.f;
+      int idx = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pj = fmaf(v[j], k, 0.01f * (1.0f / 32.0f));
+        phit = (j == 0 || cdf <= u) ? pj : phit;    // cdf (of the classes before j) <= u  <=>  j <= idx: the last hit is p[idx]
+        cdf += pj;
+        idx += (cdf <= u) ? 1 : 0;
+      }
+      idx = idx > 31 ? 31 : idx;
+      idx_sm[row * 8 + gi] = (uint8_t)idx;
+      if (p.latent && m < g.M && gi * 32 < ncols) p.latent[(long)m * p.ld_latent + col0 + gi * 32 + idx] = (1.0f + phit) - phit;
+    }
+    epi_bar_sync();
+    const int ngrp = ncols >> 5;
+    if (p.idx) {
+      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+        const int r = i >> 3, gi = i & 7;
+        if (m0 + r < g.M && gi < ngrp) p.idx[(long)(m0 + r) * p.ld_idx + slot * G + gi] = idx_sm[i];
+      }
+    }
+    if (p.s_z) {
+      for (int i = tid; i < BM * 32; i += EPI_THREADS) {    // one uint4 (8 bf16) per item
+        const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
+        if (m0 + r >= g.M || gi >= ngrp) continue;
+        const int idx = idx_sm[r * 8 + gi];
+        uint32_t q[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = (idx == j0 + 2 * e ? 0x3F80u : 0u) | (idx == j0 + 2 * e + 1 ? 0x3F800000u : 0u);
+        *reinterpret_cast<uint4*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + w * 8) = make_uint4(q[0], q[1], q[2], q[3]);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// actor L2 + output layer in one epilogue (Agent.py:182-187, 199-209).  The output layer is 2A <= 6 rows of 200 weights: instead
+// of a seventh GEMM stage, every thread multiplies its 16 bf16-rounded activations with the 2A weight rows on the CUDA cores,
+// the row's partial sums cross the cluster through distributed shared memory (like the LayerNorm statistics), and rank 0 turns
+// them into mu, sigma and the action.  One more barrier.cluster, one hand-over, one TMA round trip and one epilogue less per step.
+// ------------------------------------------------------------------------------------------
+struct PsActorOut {
+  const __nv_bfloat16* w3;   // packed output weights of the actor slot: row k = mu_k, row 16 + k = log-sigma_k; 256 columns
+  const float* b3;           // [32] packed the same way
+  const float* normals;      // [M, A] of this state
+  float *mu, *sigma, *action;   // [M, ld_act]
+  long ld_act;
+  int A, M;
+  static constexpr int WOFF = 3584;   // float offset of the staged weight rows [2A][64] inside the epilogue scratch
+  __device__ __forceinline__ void stage(float* sm, int tid) const {
+    const int cr = (int)cluster_ctarank();
+    for (int i = tid; i < 2 * A * 64; i += EPI_THREADS) {
+      const int k = i >> 6, c = i & 63;
+      const int wrow = k < A ? k : 16 + (k - A);
+      sm[WOFF + i] = __bfloat162float(w3[(long)wrow * 256 + 64 * cr + c]);
+    }
+  }
+  // v: this thread's 16 activations (columns 64 * rank + 16 * part ..).  red / xact: two 16 KB areas of the (idle) pipeline ring.
+  __device__ __forceinline__ void run(const float (&v)[16], float* sm, float* red, float* xact, int m, int row, int part) const {
+    const int cr = (int)cluster_ctarank();
+    float pa[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pa[k] = 0.f;
+    float vb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vb[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // what the next GEMM stage would have read
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < 2 * A) {
+        const float4* w4 = reinterpret_cast<const float4*>(sm + WOFF + k * 64 + part * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = w4[j];
+          pa[k] = fmaf(vb[4 * j], w.x, fmaf(vb[4 * j + 1], w.y, fmaf(vb[4 * j + 2], w.z, fmaf(vb[4 * j + 3], w.w, pa[k]))));
+        }
+      }
+    }
+    float4* r4 = reinterpret_cast<float4*>(red + (part * 128 + row) * 8);
+    r4[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    r4[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
+    epi_bar_sync();
+    if (part == 0) {   // the row's sum over this CTA's 64 columns -> rank 0
+      float sacc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sacc[k] = 0.f;
+#pragma unroll
+      for (int q = 0; q < EPI_PARTS; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8), y = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8 + 4);
+        sacc[0] += x.x; sacc[1] += x.y; sacc[2] += x.z; sacc[3] += x.w; sacc[4] += y.x; sacc[5] += y.y; sacc[6] += y.z; sacc[7] += y.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) st_cluster_f32(xact + (cr * 128 + row) * 8 + k, 0u, sacc[k]);
+    }
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (cr == 0 && part == 0 && m < M) {
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = (xact[(0 * 128 + row) * 8 + k] + xact[(1 * 128 + row) * 8 + k]) + (xact[(2 * 128 + row) * 8 + k] + xact[(3 * 128 + row) * 8 + k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < A) {
+          const float muv = t[k] + __ldg(b3 + k);
+          float ls = t[A + k] + __ldg(b3 + 16 + k);
+          ls = fminf(fmaxf(ls, -5.0f), 2.0f);
+          const float sg = softplusf_(ls) + 1e-3f;
+          mu[(long)m * ld_act + k] = muv;
+          sigma[(long)m * ld_act + k] = sg;
+          action[(long)m * ld_act + k] = tanhf(muv + sg * __ldg(normals + (long)m * A + k));
+        }
+      }
+    }
   }
 };
 
@@ -269,6 +413,9 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     if (lane == 0) {
       const int npre = min(n_st, PS_STAGES);
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
+      // (the A operand was written through the generic proxy, possibly by another SM: order it before the TMA reads.  The fence also
+      // waits for this thread's TMA loads in flight, so when the dependency is already resolved it goes BEFORE the weight prefetch.)
+      if (t.w0 == nullptr) fence_proxy_async_all();
       // weights first: they do not depend on anything, so the ring is pre-filled with them while the dependency is still open
       for (int st = 0; st < npre; ++st) {
         const uint32_t i = c.it + st, s = i % PS_STAGES;
@@ -280,8 +427,10 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
         }
       }
-      ps_flag_wait(t.w0, t.t0, c.dbg, t.code | (2u << 20));
-      fence_proxy_async_all();   // the A operand was written through the generic proxy (possibly by another SM): order it before the TMA reads
+      if (t.w0 != nullptr) {
+        ps_flag_wait(t.w0, t.t0, c.dbg, t.code | (2u << 20));
+        fence_proxy_async_all();
+      }
       if (c.tr) c.tr[2] = ps_now();
       for (int st = 0; st < npre; ++st) {
         const uint32_t s = (c.it + st) % PS_STAGES;
@@ -480,7 +629,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                                  P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
                                  RowMap{0, 0, 0, 0}};
           ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
-                         [&](int tid) { EpiCat::run(p, g, epi_sm, tile, taddr, m, row, part, x, tid); });
+                         [&](int tid) { EpiCatP::run(p, g, epi_sm, taddr, m, row, part, x, tid); });
         }
         ps_cluster_handover();
       }
@@ -496,27 +645,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                          [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
           ps_cluster_handover();
         }
-        {   // actor L2   (:182-185)
+        {   // actor L2 + output layer -> a_j = tanh(mu + sigma * eps)   (Agent.py:182-187, 199-209)
           tile_init(t, 1, j, m_tile);
           t.code |= 1u << 19;
           t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
-          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 2;
+          t.sig = rank == 0 ? flag(PF_A, m_tile) : nullptr;
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
-          ps_cluster_handover();
-        }
-        if (rank == 0) {   // mu / log-sigma rows (32 packed rows) -> a_j = tanh(mu + sigma * eps)   (Agent.py:186-187, 199-209)
-          tile_init(t, 2, j, m_tile);
-          t.code |= 1u << 19;
-          t.tmA = &P.tmY2; t.tmB = &P.tmWh3a; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256; t.ka0 = 0; t.nka0 = (P.hh2 + 63) / 64; t.bn = 32;
-          t.sig = flag(PF_A, m_tile);
-          const TileG g{B, 32, 0};
-          hp.normals = P.normals + (long)j * B * A;
-          hp.mu = P.mu + (long)j * A; hp.sigma = P.sigma + (long)j * A; hp.action = P.actions + (long)j * A;
-          ps_run_tile<0>(c, t, [&](int tid) { EpiHeads::stage(hp, g, HS_ACTOR, epi_sm, tid, m0); },
-                         [&](int tid) { EpiHeads::run(hp, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
+          const PsActorOut ao{P.Wh3 + (long)HS_ACTOR * 256 * 256, P.h3_b + HS_ACTOR * 256, P.normals + (long)j * B * A,
+                              P.mu + (long)j * A, P.sigma + (long)j * A, P.actions + (long)j * A, ldA, A, B};
+          float* red = reinterpret_cast<float*>(smem);
+          float* xact = reinterpret_cast<float*>(smem + 16384);
+          ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); ao.stage(epi_sm, tid); },
+                         [&](int tid) {
+                           float v[16];
+                           EpiLnSiluN4::compute(p, g, epi_sm, taddr, m, row, part, v);
+                           ao.run(v, epi_sm, red, xact, m, row, part);
+                         });
         }
       }
     }
@@ -662,7 +808,7 @@ static bool persist_plan(drm_rollout* r, drm_persist* ps) {
   drm_rssm* m = r->m;
   const int cap = persist_cluster_capacity();
   const int mt = r->Mp / BM;
-  if (cap <= 0 || m->d.A > 4 || m->ZP % 256) return false;
+  if (cap <= 0 || m->d.A > 3 || m->ZP % 256) return false;
   const size_t s_rows = (size_t)(r->H + 1) * r->B + BM;
   if (s_rows * m->KS * sizeof(__nv_bfloat16) > ((size_t)2 << 30)) return false;
   for (int U = 32; U <= 64; U *= 2) {
@@ -717,6 +863,7 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   drm_persist* ps = r->ps;
   const int B = r->B, H = r->H, D = m->d.D, ZP = m->ZP;
   const long ldL = (long)(H + 1) * ZP, ldH = (long)(H + 1) * D;
+  DRM_CUDA(cudaMemsetAsync(latent, 0, (size_t)B * ldL * sizeof(float), st));   // the sampling epilogue stores only the sampled class of every latent row
   RC(pack_cols(ps->S, m->KS, 0, z0, ZP, ZP, B, latent, ldL, st));
   RC(pack_cols(ps->S, m->KS, ZP + 64, h0, D, D, B, hidden, ldH, st));
   DRM_CUDA(cudaMemsetAsync(ps->flags, 0, ps->flag_bytes, st));
@@ -735,6 +882,7 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   P.h1_b = m->h1_b; P.h1_g = m->h1_g; P.h1_be = m->h1_be; P.h2_b = m->h2_b; P.h2_g = m->h2_g; P.h2_be = m->h2_be; P.h3_b = m->h3_b;
   P.bk_rew = m->bk_rew;
   P.Wgru = m->Wgru2[v];
+  P.Wh3 = m->Wh3;
   P.S = ps->S; P.Y1 = r->Y1; P.Y2 = r->Y2;
   P.uniforms = uniforms; P.normals = normals;
   P.latent = latent; P.hidden = hidden; P.actions = actions; P.rewards = rewards; P.continues = continues; P.mu = mu; P.sigma = sigma;
