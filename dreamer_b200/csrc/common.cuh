@@ -93,6 +93,17 @@ __device__ __forceinline__ void st_cluster_f32(float* local_ptr, uint32_t cta, f
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(cta));
   asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(ra), "f"(v) : "memory");
 }
+// vector forms: a remote CTA's shared memory takes one packet per store instruction, so statistics / partial sums travel as v2 / v4
+__device__ __forceinline__ void st_cluster_v2f32(float* local_ptr, uint32_t cta, float a, float b) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};\n" ::"r"(ra), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4f32(float* local_ptr, uint32_t cta, float a, float b, float c, float d) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(ra), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------

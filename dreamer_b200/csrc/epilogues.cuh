@@ -295,10 +295,7 @@ struct EpiLnSiluN4T {
         M2c += xs[512 + q * 128 + row] + d * d * (float)cnt_of(nv, 64 * cr + 16 * q, 16);
       }
 #pragma unroll
-      for (uint32_t dst = 0; dst < 4; ++dst) {
-        st_cluster_f32(xst + (cr * 128 + row) * 2, dst, mean_c);
-        st_cluster_f32(xst + (cr * 128 + row) * 2 + 1, dst, M2c);
-      }
+      for (uint32_t dst = 0; dst < 4; ++dst) st_cluster_v2f32(xst + (cr * 128 + row) * 2, dst, mean_c, M2c);
     }
     __syncwarp();
     cluster_arrive_release();

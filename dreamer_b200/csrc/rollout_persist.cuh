@@ -50,10 +50,10 @@ static_assert(PS_SCHED_STRIDE * 4 <= 256, "schedule record too large");
 static_assert(PS_TOTAL <= 232448, "persistent rollout kernel exceeds the 227 KB shared-memory limit");
 
 enum { PS_CHAIN = 0, PS_RC = 2, PS_GRU = 3 };   // CTA roles (the record's first item kind)
-// per-m-tile counters (one 128-byte line each): GRU tiles finished (h_{j+1} ready), sampling tiles finished (z_j ready),
-// actor outputs finished (a_j ready).  Producers of a counter never run a state ahead of one another, so "counter >= c(j)"
+// per-m-tile counters (one 128-byte line each): GRU tiles finished (h_{j+1} ready), sampling tiles finished (z_j ready); the
+// action a_j travels as per-row records that carry their own ready tag (PsActorOut).  Producers of a counter never run a state ahead of one another, so "counter >= c(j)"
 // means exactly "everything of states <= j".
-enum { PF_H = 0, PF_Z = 1, PF_A = 2, PF_COUNT = 3 };
+enum { PF_H = 0, PF_Z = 1, PF_COUNT = 2 };
 constexpr int PS_DBG_WORDS = 8 * 160 + 8;
 constexpr int PS_TRACE_SLOTS = 32;
 
@@ -71,6 +71,8 @@ struct PersistParams {
   float *latent, *hidden, *actions, *rewards, *continues, *mu, *sigma;
   uint8_t* idx;
   unsigned* flags;
+  unsigned long long* apack;   // [H, Mp] action records (zeroed with the counters before every launch)
+  uint8_t* idx_prev;           // [(H + 1), B, R] classes whose one-hot is currently set in S (255 = none)
   unsigned* dbg;
   const int* sched;
   unsigned long long* trace;   // debug: [cta][PS_TRACE_SLOTS][8] timestamps of the tiles of states [trace_j0, trace_j1), or NULL
@@ -130,6 +132,14 @@ __device__ __forceinline__ void ps_mbar_wait(uint64_t* bar, uint32_t parity, uns
   }
 }
 
+// debug laps inside an epilogue (thread tid == 0 only): the current tile's lap record (8 x u64) is published in shared memory
+// 128 bytes below the epilogue scratch; NULL when tracing is off
+__device__ __forceinline__ void ps_lap(const float* epi_sm, int tid, int k) {
+  if (tid != 0) return;
+  unsigned long long* lap = *reinterpret_cast<unsigned long long* const*>(reinterpret_cast<const uint8_t*>(epi_sm) - 128);
+  if (lap) lap[k] = ps_now();
+}
+
 // ------------------------------------------------------------------------------------------
 // GRU epilogue of the persistent kernel: EpiGru's gate math + the action term
 //   gi = W_ih [z, a] + b_ih: the z columns were contracted on the tensor cores, the A (<= 3) action columns are added here; the
@@ -151,8 +161,8 @@ struct EpiGruP {
     int ld_s, D;
     const __nv_bfloat16* w_a; // packed GRU weights, first action column (row pitch ldw)
     int ldw, A;
-    const float* actions;     // fp32 [M, ld_act]: this step's action (written by the actor head of the same step)
-    long ld_act;
+    const unsigned long long* apack;   // [M] action records of this state {bf16 a0, a1, a2, tag}: polled until the tag is set
+    unsigned* dbg; unsigned code;
   };
   // b_hn -> sm[U];  action weights + biases -> wa[3U] float4 {w_a0, w_a1, w_a2, bias};  h_prev tile -> hp (pitch U + 4)
   static __device__ __forceinline__ void stage(const Params& p, int n_tile, int m0, int M, float* sm, float4* wa, float* hp, int tid) {
@@ -184,19 +194,30 @@ struct EpiGruP {
       *reinterpret_cast<float4*>(hp + r * PITCH + cc) = x;
     }
   }
-  static __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
   static __device__ __forceinline__ void run(const Params& p, int n_tile, int M, const float* sm, const float4* wa, const float* hp,
                                              float* tile, uint32_t taddr, int m, int row, int part, int tid) {
     const int u0 = n_tile * U;
     const int m0 = m - row;
     const int nvalid = min(U, p.D - u0);
     float4 a = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (m < M) {
-      const float* ap = p.actions + (long)m * p.ld_act;
-      a.x = bf16r(__ldcg(ap));
-      if (p.A > 1) a.y = bf16r(__ldcg(ap + 1));
-      if (p.A > 2) a.z = bf16r(__ldcg(ap + 2));
+    if (m < M) {   // the action arrives as one 8-byte record per row whose top half-word is the ready tag: no separate flag, no second round trip
+      unsigned long long rec;
+      unsigned n = 0;
+      unsigned long long t0 = 0;
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(rec) : "l"(p.apack + m) : "memory");
+        if (rec >> 48) break;
+        if ((++n & 255u) == 0) {
+          const unsigned long long t = ps_now();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > PS_TIMEOUT_NS) ps_timeout(p.dbg, p.code | (5u << 20), 0u, 1u);
+        }
+      }
+      a.x = __uint_as_float(((unsigned)rec & 0xFFFFu) << 16);
+      a.y = __uint_as_float((unsigned)rec & 0xFFFF0000u);
+      a.z = __uint_as_float(((unsigned)(rec >> 32) & 0xFFFFu) << 16);
     }
+    ps_lap(sm, tid, 0);
 #pragma unroll 1
     for (int ps = 0; ps < PASSES; ++ps) {
       const int c = (ps * EPI_PARTS + part) * UP;
@@ -220,8 +241,11 @@ struct EpiGruP {
       }
       tile_put<UP>(tile, PITCH, row, c, hn);
     }
+    ps_lap(sm, tid, 1);
     epi_bar_sync();
+    ps_lap(sm, tid, 2);
     tile_copy_out(tile, PITCH, U, nvalid, m0, M, p.h_out + u0, p.ld_h, p.s_h + u0, p.ld_s, tid);
+    ps_lap(sm, tid, 3);
   }
 };
 
@@ -232,8 +256,8 @@ struct EpiGruP {
 // ------------------------------------------------------------------------------------------
 struct EpiCatP {
   using Params = EpiCat::Params;
-  static __device__ __forceinline__ void run(const Params& p, const TileG& g, float* sm, uint32_t taddr, int m, int row, int part,
-                                             int slot, int tid) {
+  static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, const TileG& g, float* sm, uint32_t taddr, int m, int row,
+                                             int part, int slot, int tid) {
     const int m0 = m - row;
     const int G = g.bn >> 5;
     const int col0 = slot * g.bn;
@@ -267,8 +291,10 @@ struct EpiCatP {
       idx = idx > 31 ? 31 : idx;
       idx_sm[row * 8 + gi] = (uint8_t)idx;
       if (p.latent && m < g.M && gi * 32 < ncols) p.latent[(long)m * p.ld_latent + col0 + gi * 32 + idx] = (1.0f + phit) - phit;
+      ps_lap(sm, tid, gi < 4 ? 0 : 1);
     }
     epi_bar_sync();
+    ps_lap(sm, tid, 2);
     const int ngrp = ncols >> 5;
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
@@ -277,16 +303,22 @@ struct EpiCatP {
       }
     }
     if (p.s_z) {
-      for (int i = tid; i < BM * 32; i += EPI_THREADS) {    // one uint4 (8 bf16) per item
-        const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
+      // The z columns of this slab hold the one-hots of the previous rollout (zeros at first): clear the old class, set the new one
+      // -- two 2-byte stores per latent row instead of rewriting 64 bytes of zeros (idx_prev remembers what is set; 255 = nothing)
+      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+        const int r = i >> 3, gi = i & 7;
         if (m0 + r >= g.M || gi >= ngrp) continue;
-        const int idx = idx_sm[r * 8 + gi];
-        uint32_t q[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) q[e] = (idx == j0 + 2 * e ? 0x3F80u : 0u) | (idx == j0 + 2 * e + 1 ? 0x3F800000u : 0u);
-        *reinterpret_cast<uint4*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + w * 8) = make_uint4(q[0], q[1], q[2], q[3]);
+        uint8_t* pv = idx_prev + (long)(m0 + r) * p.R + slot * G + gi;
+        const int old = *pv, idx = idx_sm[i];
+        unsigned short* zrow = reinterpret_cast<unsigned short*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + gi * 32);
+        if (old != idx) {
+          if (old != 255) zrow[old] = 0;
+          zrow[idx] = 0x3F80;
+          *pv = (uint8_t)idx;
+        }
       }
     }
+    ps_lap(sm, tid, 3);
   }
 };
 
@@ -301,6 +333,7 @@ struct PsActorOut {
   const float* b3;           // [32] packed the same way
   const float* normals;      // [M, A] of this state
   float *mu, *sigma, *action;   // [M, ld_act]
+  unsigned long long* apack;    // [M] this state's action records {bf16 a0, a1, a2, tag 1}: one 8-byte store = data + ready flag for the GRU CTAs
   long ld_act;
   int A, M;
   static constexpr int WOFF = 3584;   // float offset of the staged weight rows [2A][64] inside the epilogue scratch
@@ -313,7 +346,7 @@ struct PsActorOut {
     }
   }
   // v: this thread's 16 activations (columns 64 * rank + 16 * part ..).  red / xact: two 16 KB areas of the (idle) pipeline ring.
-  __device__ __forceinline__ void run(const float (&v)[16], float* sm, float* red, float* xact, int m, int row, int part) const {
+  __device__ __forceinline__ void run(const float (&v)[16], float* sm, float* red, float* xact, int m, int row, int part, int tid) const {
     const int cr = (int)cluster_ctarank();
     float pa[8];
 #pragma unroll
@@ -335,7 +368,9 @@ struct PsActorOut {
     float4* r4 = reinterpret_cast<float4*>(red + (part * 128 + row) * 8);
     r4[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
     r4[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
+    ps_lap(sm, tid, 0);
     epi_bar_sync();
+    ps_lap(sm, tid, 1);
     if (part == 0) {   // the row's sum over this CTA's 64 columns -> rank 0
       float sacc[8];
 #pragma unroll
@@ -345,13 +380,16 @@ struct PsActorOut {
         const float4 x = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8), y = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8 + 4);
         sacc[0] += x.x; sacc[1] += x.y; sacc[2] += x.z; sacc[3] += x.w; sacc[4] += y.x; sacc[5] += y.y; sacc[6] += y.z; sacc[7] += y.w;
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) st_cluster_f32(xact + (cr * 128 + row) * 8 + k, 0u, sacc[k]);
+      st_cluster_v4f32(xact + (cr * 128 + row) * 8, 0u, sacc[0], sacc[1], sacc[2], sacc[3]);
+      st_cluster_v4f32(xact + (cr * 128 + row) * 8 + 4, 0u, sacc[4], sacc[5], sacc[6], sacc[7]);
     }
+    ps_lap(sm, tid, 2);
     __syncwarp();
     cluster_arrive_release();
     cluster_wait_acquire();
+    ps_lap(sm, tid, 3);
     if (cr == 0 && part == 0 && m < M) {
+      float av[3] = {0.f, 0.f, 0.f};
       float t[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) t[k] = (xact[(0 * 128 + row) * 8 + k] + xact[(1 * 128 + row) * 8 + k]) + (xact[(2 * 128 + row) * 8 + k] + xact[(3 * 128 + row) * 8 + k]);
@@ -364,9 +402,13 @@ struct PsActorOut {
           const float sg = softplusf_(ls) + 1e-3f;
           mu[(long)m * ld_act + k] = muv;
           sigma[(long)m * ld_act + k] = sg;
-          action[(long)m * ld_act + k] = tanhf(muv + sg * __ldg(normals + (long)m * A + k));
+          const float ak = tanhf(muv + sg * __ldg(normals + (long)m * A + k));
+          action[(long)m * ld_act + k] = ak;
+          if (k < 3) av[k] = ak;
         }
       }
+      const unsigned long long rec = (unsigned long long)pack_bf16x2(av[0], av[1]) | ((unsigned long long)(pack_bf16x2(av[2], 0.f) & 0xFFFFu) << 32) | (1ull << 48);
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(apack + m), "l"(rec) : "memory");
     }
   }
 };
@@ -382,6 +424,7 @@ struct PsCtx {
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
   unsigned* dbg;
   unsigned long long* tr;   // this tile's trace record (8 x u64) or NULL
+  long lap_off;             // distance (u64 words) from a tile's trace record to its lap record
 };
 struct PsTile {
   const CUtensorMap *tmA, *tmB;
@@ -413,32 +456,33 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     if (lane == 0) {
       const int npre = min(n_st, PS_STAGES);
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
-      // (the A operand was written through the generic proxy, possibly by another SM: order it before the TMA reads.  The fence also
-      // waits for this thread's TMA loads in flight, so when the dependency is already resolved it goes BEFORE the weight prefetch.)
-      if (t.w0 == nullptr) fence_proxy_async_all();
-      // weights first: they do not depend on anything, so the ring is pre-filled with them while the dependency is still open
-      for (int st = 0; st < npre; ++st) {
-        const uint32_t i = c.it + st, s = i % PS_STAGES;
-        ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
-        const int n_sub = min(kps, nk - st * kps);
-        mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
-        for (int u = 0; u < n_sub; ++u) {
-          const int kb = st * kps + u;
-          tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
-        }
-      }
       if (t.w0 != nullptr) {
+        // the dependency may still be open: weights first (they depend on nothing), so the ring is pre-filled while waiting
+        for (int st = 0; st < npre; ++st) {
+          const uint32_t i = c.it + st, s = i % PS_STAGES;
+          ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+          const int n_sub = min(kps, nk - st * kps);
+          mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
+          for (int u = 0; u < n_sub; ++u) {
+            const int kb = st * kps + u;
+            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+          }
+        }
         ps_flag_wait(t.w0, t.t0, c.dbg, t.code | (2u << 20));
+        // the A operand was written through the generic proxy by another SM: order it before the TMA reads
         fence_proxy_async_all();
+        if (c.tr) c.tr[2] = ps_now();
+        for (int st = 0; st < npre; ++st) {
+          const uint32_t s = (c.it + st) % PS_STAGES;
+          const int n_sub = min(kps, nk - st * kps);
+          for (int u = 0; u < n_sub; ++u)
+            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, st * kps + u) * BK, t.a_row, &c.full[s]);
+        }
+      } else {
+        fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
+        if (c.tr) c.tr[2] = ps_now();
       }
-      if (c.tr) c.tr[2] = ps_now();
-      for (int st = 0; st < npre; ++st) {
-        const uint32_t s = (c.it + st) % PS_STAGES;
-        const int n_sub = min(kps, nk - st * kps);
-        for (int u = 0; u < n_sub; ++u)
-          tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, st * kps + u) * BK, t.a_row, &c.full[s]);
-      }
-      for (int st = npre; st < n_st; ++st) {
+      for (int st = (t.w0 != nullptr ? npre : 0); st < n_st; ++st) {
         const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
         const int n_sub = min(kps, nk - st * kps);
@@ -492,6 +536,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     }
   } else {
     const int tid = (int)threadIdx.x - 64;
+    if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 128) = c.tr ? c.tr + c.lap_off : nullptr;
     pre(tid);
     if (lane == 0) ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
     __syncwarp();
@@ -557,7 +602,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
@@ -629,7 +674,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                                  P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
                                  RowMap{0, 0, 0, 0}};
           ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
-                         [&](int tid) { EpiCatP::run(p, g, epi_sm, taddr, m, row, part, x, tid); });
+                         [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, g, epi_sm, taddr, m, row, part, x, tid); });
         }
         ps_cluster_handover();
       }
@@ -650,18 +695,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           t.code |= 1u << 19;
           t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
           t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 2;
-          t.sig = rank == 0 ? flag(PF_A, m_tile) : nullptr;
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
           const PsActorOut ao{P.Wh3 + (long)HS_ACTOR * 256 * 256, P.h3_b + HS_ACTOR * 256, P.normals + (long)j * B * A,
-                              P.mu + (long)j * A, P.sigma + (long)j * A, P.actions + (long)j * A, ldA, A, B};
+                              P.mu + (long)j * A, P.sigma + (long)j * A, P.actions + (long)j * A, P.apack + (long)j * Mp, ldA, A, B};
           float* red = reinterpret_cast<float*>(smem);
           float* xact = reinterpret_cast<float*>(smem + 16384);
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); ao.stage(epi_sm, tid); },
                          [&](int tid) {
                            float v[16];
                            EpiLnSiluN4::compute(p, g, epi_sm, taddr, m, row, part, v);
-                           ao.run(v, epi_sm, red, xact, m, row, part);
+                           ao.run(v, epi_sm, red, xact, m, row, part, tid);
                          });
         }
       }
@@ -683,17 +727,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         t.tmA = &P.tmS; t.tmB = &P.tmWgru; t.a_row = j * B + m0; t.b_row = n_tile * 3 * P.U;
         t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.b_follows_a = 1; t.bn = 3 * P.U;
         t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);            // z_j sampled (implies h_j)
-        t.e0 = flag(PF_A, m_tile); t.et0 = (unsigned)(j + 1);               // a_j
-        t.sig = flag(PF_H, m_tile);
+        t.sig = flag(PF_H, m_tile);     // (a_j is awaited inside the epilogue, row by row: EpiGruP::run)
         __nv_bfloat16* s_h = P.S + (long)(j + 1) * B * P.KS + ZP + 64;
         if (P.U == 32) {
           const EpiGruP<32>::Params p{P.b_ih, P.b_hh, P.hidden + (long)j * D, P.hidden + (long)(j + 1) * D, s_h, ldH, P.KS, D,
-                                      P.Wgru + ZP, P.KS, A, P.actions + (long)j * A, ldA};
+                                      P.Wgru + ZP, P.KS, A, P.apack + (long)j * Mp, P.dbg, t.code};
           ps_run_tile<32>(c, t, [&](int tid) { EpiGruP<32>::stage(p, n_tile, m0, B, epi_sm, wa, hp_tile, tid); },
                           [&](int tid) { EpiGruP<32>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); });
         } else {
           const EpiGruP<64>::Params p{P.b_ih, P.b_hh, P.hidden + (long)j * D, P.hidden + (long)(j + 1) * D, s_h, ldH, P.KS, D,
-                                      P.Wgru + ZP, P.KS, A, P.actions + (long)j * A, ldA};
+                                      P.Wgru + ZP, P.KS, A, P.apack + (long)j * Mp, P.dbg, t.code};
           ps_run_tile<64>(c, t, [&](int tid) { EpiGruP<64>::stage(p, n_tile, m0, B, epi_sm, wa, hp_tile, tid); },
                           [&](int tid) { EpiGruP<64>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); });
         }
@@ -752,7 +795,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
 struct drm_persist {
   int U = 0, nt = 0, nq = 0, n_cta = 0;
   int* sched = nullptr;        // device [n_cta * PS_SCHED_STRIDE]
-  unsigned* flags = nullptr;   // device [PF_COUNT * mt * 32]
+  unsigned* flags = nullptr;   // device [PF_COUNT * mt * 32] counters, then [H * Mp] 8-byte action records (zeroed together before every launch)
+  uint8_t* idx_prev = nullptr; // device [(H + 1) * B * R]
   unsigned* dbg = nullptr;     // host-mapped [PS_DBG_WORDS]
   size_t flag_bytes = 0;
   __nv_bfloat16* S = nullptr;  // time-major state slabs [(H + 1) * B + 128, KS]
@@ -835,8 +879,11 @@ static bool persist_plan(drm_rollout* r, drm_persist* ps) {
     ps->n_cta = n_cta;
     if (dev_alloc(r->allocs, &ps->sched, sc.size()) != DRM_OK) return false;
     if (cudaMemcpy(ps->sched, sc.data(), sc.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    ps->flag_bytes = (size_t)PF_COUNT * mt * 32 * sizeof(unsigned);
+    ps->flag_bytes = (size_t)PF_COUNT * mt * 32 * sizeof(unsigned) + (size_t)r->H * r->Mp * sizeof(unsigned long long);
     if (dev_alloc(r->allocs, &ps->flags, ps->flag_bytes / sizeof(unsigned)) != DRM_OK) return false;
+    const size_t n_prev = (size_t)(r->H + 1) * r->B * m->d.R;
+    if (dev_alloc(r->allocs, &ps->idx_prev, n_prev) != DRM_OK) return false;
+    if (cudaMemset(ps->idx_prev, 255, n_prev) != cudaSuccess) return false;
     if (dev_alloc(r->allocs, &ps->S, s_rows * m->KS) != DRM_OK) return false;
     if (make_tmap_bf16_2d(&ps->tmS, ps->S, s_rows, m->KS, m->KS, BM) != DRM_OK) return false;
     if (cudaHostAlloc((void**)&ps->dbg, PS_DBG_WORDS * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -888,6 +935,8 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   P.latent = latent; P.hidden = hidden; P.actions = actions; P.rewards = rewards; P.continues = continues; P.mu = mu; P.sigma = sigma;
   P.idx = idx;
   P.flags = ps->flags; P.dbg = ps->dbg; P.sched = ps->sched;
+  P.apack = reinterpret_cast<unsigned long long*>(ps->flags + (size_t)PF_COUNT * P.mt * 32);
+  P.idx_prev = ps->idx_prev;
   P.trace = ps->trace; P.trace_j0 = ps->trace_j0; P.trace_j1 = ps->trace_j1;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];

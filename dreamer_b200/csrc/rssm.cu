@@ -811,7 +811,7 @@ extern "C" int drm_rollout_trace(drm_rollout* r, int32_t j0, int32_t nj, unsigne
   RC(check_arch());
   DRM_REQUIRE(persist_eligible(r), DRM_ERR_ARG, "drm_rollout_trace: this workspace does not use the persistent kernel");
   drm_persist* ps = r->ps;
-  const size_t words = (size_t)ps->n_cta * PS_TRACE_SLOTS * 8;
+  const size_t words = (size_t)ps->n_cta * PS_TRACE_SLOTS * 8 * 2;   // tile records, then the epilogue-lap records
   if (!out) {
     if (!ps->trace) RC(dev_alloc(r->allocs, &ps->trace, words));
     DRM_CUDA(cudaMemset(ps->trace, 0, words * sizeof(unsigned long long)));

@@ -33,10 +33,11 @@ torch.cuda.synchronize()
 L.check(lib.drm_rollout_trace(ro.handle, J0, 2, None, 0), "trace on")
 ro.run(z0, h0, u, n, want_idx=False)
 torch.cuda.synchronize()
-nw = info["ctas"] * 32 * 8
+nw = info["ctas"] * 32 * 8 * 2
 buf = np.zeros(nw, dtype=np.uint64)
 L.check(lib.drm_rollout_trace(ro.handle, 0, 0, buf.ctypes.data_as(C.c_void_p), nw), "trace read")
-rec = buf.reshape(info["ctas"], 32, 8)
+rec = buf[: nw // 2].reshape(info["ctas"], 32, 8)
+laps = buf[nw // 2:].reshape(info["ctas"], 32, 8)
 KIND = {0: "chain", 2: "rc", 3: "gru"}
 LAYER = {0: "prior1", 1: "prior2", 2: "sample", 8: "actor1", 9: "actor2", 10: "actor3"}
 rows = []
@@ -47,21 +48,24 @@ for cta in range(rec.shape[0]):
             continue
         code = int(r[0])
         kind, layer, j, m = code >> 24, (code >> 16) & 15, (code >> 8) & 255, code & 255
-        rows.append((int(r[1]), kind, layer, j, m, cta, [int(x) for x in r[1:8]]))
+        rows.append((int(r[1]), kind, layer, j, m, cta, [int(x) for x in r[1:8]], [int(x) for x in laps[cta, s]]))
 t0 = min(r[0] for r in rows)
 print(f"{len(rows)} tiles recorded; us relative to the first")
 print(f"{'tile':<18}{'cta':>4} {'start':>8}{'dep':>8}{'operands':>9}{'epi rdy':>8}{'acc':>8}{'epi end':>8}{'publ':>8}   main  epi  publ")
 gru_done = {}
-for t_start, kind, layer, j, m, cta, ts in sorted(rows):
+for t_start, kind, layer, j, m, cta, ts, lp in sorted(rows):
     if m != MT:
         continue
     rel = [(x - t0) / 1e3 if x else float("nan") for x in ts]
     name = f"{LAYER.get(layer, layer) if kind == 0 else KIND[kind] + str(layer)} j={j}"
     if kind == 3:
         gru_done.setdefault(j, []).append(rel)
+        if cta % 8 == 0 and any(lp):
+            print(f"  gru cta {cta} j={j} laps(vs acc) " + " ".join(f"{(x - ts[4]) / 1e3:.2f}" for x in lp if x))
         continue
     print(f"{name:<18}{cta:>4} " + "".join(f"{x:>8.2f}" if i != 2 else f"{x:>9.2f}" for i, x in enumerate(rel)) +
-          f"   {rel[4] - rel[2]:5.2f} {rel[5] - rel[4]:4.2f} {rel[6] - rel[5]:4.2f}")
+          f"   {rel[4] - rel[2]:5.2f} {rel[5] - rel[4]:4.2f} {rel[6] - rel[5]:4.2f}" +
+          ("   laps(vs acc) " + " ".join(f"{(x - ts[4]) / 1e3:.2f}" for x in lp if x) if any(lp) else ""))
 for j, lst in sorted(gru_done.items()):
     a = np.array(lst)
     print(f"gru j={j}: {len(lst)} tiles; start {a[:,0].min():.2f}..{a[:,0].max():.2f}  dep {a[:,1].min():.2f}..{a[:,1].max():.2f}  operands {a[:,2].min():.2f}..{a[:,2].max():.2f}  "
