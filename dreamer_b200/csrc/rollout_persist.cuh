@@ -53,7 +53,7 @@ enum { PS_CHAIN = 0, PS_RC = 2, PS_GRU = 3 };   // CTA roles (the record's first
 // per-m-tile counters (one 128-byte line each): GRU tiles finished (h_{j+1} ready), sampling tiles finished (z_j ready); the
 // action a_j travels as per-row records that carry their own ready tag (PsActorOut).  Producers of a counter never run a state ahead of one another, so "counter >= c(j)"
 // means exactly "everything of states <= j".
-enum { PF_H = 0, PF_Z = 1, PF_COUNT = 2 };
+enum { PF_H = 0, PF_Z = 1, PF_LP = 2, PF_LA = 3, PF_COUNT = 4 };   // + loads landed: prior L1 / actor L1 of a state (bandwidth gates of the GRU CTAs)
 constexpr int PS_DBG_WORDS = 8 * 160 + 8;
 constexpr int PS_TRACE_SLOTS = 32;
 
@@ -263,6 +263,15 @@ struct EpiCatP {
     const int col0 = slot * g.bn;
     const int ncols = max(0, min(g.bn, p.R * 32 - col0));
     uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);       // [128 rows][8] (sm[256, 1280) holds the uniforms)
+    const int ngrp = ncols >> 5;
+    int old2[2] = {255, 255};                                      // what is set in S for the (row, latent row) pairs this thread updates below
+    if (p.s_z) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = tid + e * EPI_THREADS, r = i >> 3, gi = i & 7;
+        if (m0 + r < g.M && gi < ngrp) old2[e] = __ldcg(idx_prev + (long)(m0 + r) * p.R + slot * G + gi);
+      }
+    }
 #pragma unroll 1
     for (int gi = part; gi < G; gi += EPI_PARTS) {
       float v[32];
@@ -295,7 +304,6 @@ struct EpiCatP {
     }
     epi_bar_sync();
     ps_lap(sm, tid, 2);
-    const int ngrp = ncols >> 5;
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
@@ -305,11 +313,12 @@ struct EpiCatP {
     if (p.s_z) {
       // The z columns of this slab hold the one-hots of the previous rollout (zeros at first): clear the old class, set the new one
       // -- two 2-byte stores per latent row instead of rewriting 64 bytes of zeros (idx_prev remembers what is set; 255 = nothing)
-      for (int i = tid; i < BM * 8; i += EPI_THREADS) {
-        const int r = i >> 3, gi = i & 7;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = tid + e * EPI_THREADS, r = i >> 3, gi = i & 7;
         if (m0 + r >= g.M || gi >= ngrp) continue;
         uint8_t* pv = idx_prev + (long)(m0 + r) * p.R + slot * G + gi;
-        const int old = *pv, idx = idx_sm[i];
+        const int old = old2[e], idx = idx_sm[i];
         unsigned short* zrow = reinterpret_cast<unsigned short*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + gi * 32);
         if (old != idx) {
           if (old != 255) zrow[old] = 0;
@@ -384,6 +393,12 @@ struct PsActorOut {
       st_cluster_v4f32(xact + (cr * 128 + row) * 8 + 4, 0u, sacc[4], sacc[5], sacc[6], sacc[7]);
     }
     ps_lap(sm, tid, 2);
+    float bm[4] = {0.f, 0.f, 0.f, 0.f}, bl[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cr == 0 && part == 0 && m < M) {   // (fetched under the barrier)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < A) { bm[k] = __ldg(b3 + k); bl[k] = __ldg(b3 + 16 + k); ep[k] = __ldg(normals + (long)m * A + k); }
+    }
     __syncwarp();
     cluster_arrive_release();
     cluster_wait_acquire();
@@ -396,13 +411,13 @@ struct PsActorOut {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < A) {
-          const float muv = t[k] + __ldg(b3 + k);
-          float ls = t[A + k] + __ldg(b3 + 16 + k);
+          const float muv = t[k] + bm[k];
+          float ls = t[A + k] + bl[k];
           ls = fminf(fmaxf(ls, -5.0f), 2.0f);
           const float sg = softplusf_(ls) + 1e-3f;
           mu[(long)m * ld_act + k] = muv;
           sigma[(long)m * ld_act + k] = sg;
-          const float ak = tanhf(muv + sg * __ldg(normals + (long)m * A + k));
+          const float ak = tanhf(muv + sg * ep[k]);
           action[(long)m * ld_act + k] = ak;
           if (k < 3) av[k] = ak;
         }
@@ -430,12 +445,17 @@ struct PsTile {
   const CUtensorMap *tmA, *tmB;
   int a_row, b_row;
   int ka0, nka0, ka1, nka1;   // A k-block ranges [ka0, ka0 + nka0) then [ka1, ka1 + nka1)
+  int h_first;                // GRU tiles: 1 = the first range is the h part (r, z, n_h accumulators start there), the second the z part
   int b_follows_a;            // 1: the B k-block index equals the A k-block index (GRU weights keep the state's column layout)
   int bn;                     // B rows per k-block (GRU: 3U)
   int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
   int stage_bytes;            // ring stride of this CTA's role
   int cbar;                   // cluster barriers the epilogue executes (the producer / MMA warps mirror them)
-  const unsigned* w0; unsigned t0;     // before the first A load
+  const unsigned* w0; unsigned t0;     // data dependency of the first A k-block range (NULL: resolved by a barrier / program order)
+  const unsigned* g0; unsigned gt0;    // bandwidth gate of the first range: wait until the chain's loads of that phase have landed
+  const unsigned* w1; unsigned t1;     // the same two for the second range (only honoured with kps == 1)
+  const unsigned* g1; unsigned gt1;
+  unsigned* lsig;                      // += 1 (relaxed) once every operand of this tile has landed in shared memory
   const unsigned* e0; unsigned et0;    // before the epilogue reads data another CTA produced
   unsigned* sig;                       // += 1 (device-scope release) once the tile's outputs are visible
   unsigned code;                       // (role << 24) | (layer << 16) | (j << 8) | m-tile, for the timeout / trace records
@@ -454,45 +474,55 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;   // one k-block: [A 16 KB | B]
   if (warp == 0) {
     if (lane == 0) {
-      const int npre = min(n_st, PS_STAGES);
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
-      if (t.w0 != nullptr) {
-        // the dependency may still be open: weights first (they depend on nothing), so the ring is pre-filled while waiting
-        for (int st = 0; st < npre; ++st) {
+      // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
+      // pre-filled while waiting; otherwise A and B of a stage are issued together
+      auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
+        int st = st0;
+        if (w != nullptr || gte != nullptr) {
+          const int npre = min(st1 - st0, PS_STAGES);
+          for (; st < st0 + npre; ++st) {
+            const uint32_t i = c.it + st, s = i % PS_STAGES;
+            ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+            const int n_sub = min(kps, nk - st * kps);
+            mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
+            for (int u = 0; u < n_sub; ++u) {
+              const int kb = st * kps + u;
+              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+            }
+          }
+          ps_flag_wait(gte, tg, c.dbg, t.code | (6u << 20));
+          ps_flag_wait(w, tw, c.dbg, t.code | (2u << 20));
+          fence_proxy_async_all();   // the A operand was written through the generic proxy by another SM: order it before the TMA reads
+          if (mark && c.tr) c.tr[2] = ps_now();
+          for (int s2 = st0; s2 < st0 + npre; ++s2) {
+            const uint32_t s = (c.it + s2) % PS_STAGES;
+            const int n_sub = min(kps, nk - s2 * kps);
+            for (int u = 0; u < n_sub; ++u)
+              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
+          }
+        } else if (mark) {
+          fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
+          if (c.tr) c.tr[2] = ps_now();
+        }
+        for (; st < st1; ++st) {
           const uint32_t i = c.it + st, s = i % PS_STAGES;
-          ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+          ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
           const int n_sub = min(kps, nk - st * kps);
           mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
           for (int u = 0; u < n_sub; ++u) {
-            const int kb = st * kps + u;
-            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+            const int kb = st * kps + u, ka = ps_ka(t, kb);
+            uint8_t* sa = c.smem + s * t.stage_bytes + u * sub_bytes;
+            tma_load_2d(sa, t.tmA, ka * BK, t.a_row, &c.full[s]);
+            tma_load_2d(sa + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
           }
         }
-        ps_flag_wait(t.w0, t.t0, c.dbg, t.code | (2u << 20));
-        // the A operand was written through the generic proxy by another SM: order it before the TMA reads
-        fence_proxy_async_all();
-        if (c.tr) c.tr[2] = ps_now();
-        for (int st = 0; st < npre; ++st) {
-          const uint32_t s = (c.it + st) % PS_STAGES;
-          const int n_sub = min(kps, nk - st * kps);
-          for (int u = 0; u < n_sub; ++u)
-            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, st * kps + u) * BK, t.a_row, &c.full[s]);
-        }
+      };
+      if (t.w1 != nullptr || t.g1 != nullptr) {   // two separately released k ranges (kps == 1)
+        issue(0, t.nka0, t.w0, t.t0, t.g0, t.gt0, true);
+        issue(t.nka0, nk, t.w1, t.t1, t.g1, t.gt1, false);
       } else {
-        fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
-        if (c.tr) c.tr[2] = ps_now();
-      }
-      for (int st = (t.w0 != nullptr ? npre : 0); st < n_st; ++st) {
-        const uint32_t i = c.it + st, s = i % PS_STAGES;
-        ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
-        const int n_sub = min(kps, nk - st * kps);
-        mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
-        for (int u = 0; u < n_sub; ++u) {
-          const int kb = st * kps + u, ka = ps_ka(t, kb);
-          uint8_t* sa = c.smem + s * t.stage_bytes + u * sub_bytes;
-          tma_load_2d(sa, t.tmA, ka * BK, t.a_row, &c.full[s]);
-          tma_load_2d(sa + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
-        }
+        issue(0, n_st, t.w0, t.t0, t.g0, t.gt0, true);
       }
     }
   } else if (warp == 1) {
@@ -513,24 +543,33 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           } else {
-            // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U)
+            // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U).
+            // The h part comes first (h_j is there long before z_j): the very first z MMA must START n_x while ADDING to r, z, so it is
+            // issued as an N = 2U and an N = U instruction.
             constexpr int U = GRU_U;
-            if (kb < t.nka0) {
-              const uint32_t idesc = umma_idesc_bf16(3 * U);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            } else {
-              const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U);
-              const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U), idesc_3 = umma_idesc_bf16(3 * U);
+            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            if (kb < t.nka0) {   // h part
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
-                umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > t.nka0 || k > 0) ? 1u : 0u);
+                umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, (kb | k) != 0);
+                umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb | k) != 0);
+              }
+            } else {             // z part
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                if (kb == t.nka0 && k == 0) {
+                  umma_bf16(c.tmem, adesc, bdesc, idesc_rz, 1u);
+                  umma_bf16(c.tmem + 2 * U, adesc, bdesc_n, idesc_n, 0u);
+                } else {
+                  umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_3, 1u);
+                }
               }
             }
           }
         }
         umma_commit(&c.empty[s]);
+        if (st == n_st - 1 && t.lsig) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;\n" ::"l"(t.lsig), "r"(1u) : "memory");   // every operand of the tile is in shared memory
       }
       umma_commit(c.tmem_full);
     }
@@ -615,7 +654,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   auto flag = [&](int kind, int m) { return P.flags + (long)(kind * mt + m) * 32; };
   auto tile_init = [&](PsTile& t, int layer, int j, int m_tile) {
     t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0;
-    t.w0 = nullptr; t.t0 = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
+    t.w0 = nullptr; t.t0 = 0; t.g0 = nullptr; t.gt0 = 0; t.w1 = nullptr; t.t1 = 0; t.g1 = nullptr; t.gt1 = 0; t.lsig = nullptr;
+    t.h_first = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
     t.code = ((unsigned)role << 24) | ((unsigned)layer << 16) | ((unsigned)j << 8) | (unsigned)m_tile;
   };
   auto trace_window = [&](int j) {   // (at most PS_TRACE_SLOTS tiles per CTA are recorded)
@@ -648,6 +688,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           tile_init(t, 0, j, m_tile);
           t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
           t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
+          t.lsig = flag(PF_LP, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
@@ -684,6 +725,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           t.code |= 1u << 19;
           t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
           t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.lsig = flag(PF_LA, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
@@ -725,8 +767,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         tile_init(t, 0, j, m_tile);
         t.stage_bytes = PS_GRU_STAGE_BYTES;
         t.tmA = &P.tmS; t.tmB = &P.tmWgru; t.a_row = j * B + m0; t.b_row = n_tile * 3 * P.U;
-        t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.b_follows_a = 1; t.bn = 3 * P.U;
-        t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);            // z_j sampled (implies h_j)
+        t.ka0 = kh0; t.nka0 = nkh; t.ka1 = 0; t.nka1 = nkz; t.b_follows_a = 1; t.bn = 3 * P.U; t.h_first = 1;
+        // The GRU CTAs move 83 MB per step -- alone they would saturate the L2 -> SM fabric for 6 us and starve the chain's small
+        // loads exactly when those are on the critical path.  So each half waits until the chain layer that reads the same data has
+        // its operands: the h part (needs h_j) behind prior L1 of state j, the z part (needs z_j) behind actor L1 of state j.
+        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
+        t.g0 = flag(PF_LP, m_tile); t.gt0 = (unsigned)(4 * j);
+        t.w1 = flag(PF_Z, m_tile); t.t1 = (unsigned)(P.nq * j);
+        t.g1 = flag(PF_LA, m_tile); t.gt1 = (unsigned)(4 * (j + 1));
         t.sig = flag(PF_H, m_tile);     // (a_j is awaited inside the epilogue, row by row: EpiGruP::run)
         __nv_bfloat16* s_h = P.S + (long)(j + 1) * B * P.KS + ZP + 64;
         if (P.U == 32) {
