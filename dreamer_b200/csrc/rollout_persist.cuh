@@ -39,6 +39,7 @@ constexpr int PS_RING_BYTES = PS_STAGES * PS_STAGE_BYTES;          // 192 KB
 constexpr int PS_GRU_STAGE_BYTES = A_STAGE_BYTES + 192 * BK * 2;   // 40 KB: GRU CTAs (<= 192 weight rows per k-block)
 constexpr int PS_HP_OFF = PS_STAGES * PS_GRU_STAGE_BYTES;          // GRU CTAs: h_prev tile, 128 x 68 fp32, behind their ring
 constexpr int PS_WA_OFF = PS_HP_OFF + BM * 68 * 4;                 // GRU CTAs: action-term weights [3U] float4
+constexpr int PS_ZIDX_OFF = PS_RING_BYTES;                        // chain CTAs: sampled classes of the current state, [128 rows][32 latent rows] bytes
 constexpr int PS_BAR_OFF = PS_RING_BYTES + 16384;
 constexpr int PS_EPI_OFF = PS_BAR_OFF + 256;
 constexpr int PS_SCHED_OFF = PS_EPI_OFF + 16384;
@@ -256,8 +257,10 @@ struct EpiGruP {
 // ------------------------------------------------------------------------------------------
 struct EpiCatP {
   using Params = EpiCat::Params;
-  static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, const TileG& g, float* sm, uint32_t taddr, int m, int row,
-                                             int part, int slot, int tid) {
+  // zidx_sm (chain clusters): every CTA of the cluster keeps the classes of the whole state, [128 rows][32 latent rows] bytes, in its
+  // shared memory -- the actor's first layer builds its one-hot A tiles from them -- so this tile's 8 columns go to all four.
+  static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, uint8_t* zidx_sm, const TileG& g, float* sm, uint32_t taddr,
+                                             int m, int row, int part, int slot, int tid) {
     const int m0 = m - row;
     const int G = g.bn >> 5;
     const int col0 = slot * g.bn;
@@ -304,6 +307,16 @@ struct EpiCatP {
     }
     epi_bar_sync();
     ps_lap(sm, tid, 2);
+    if (zidx_sm && tid < BM) {
+      const unsigned long long v = *reinterpret_cast<const unsigned long long*>(idx_sm + tid * 8);
+      const uint32_t local = smem_u32(zidx_sm + tid * 32 + slot * 8);
+#pragma unroll
+      for (uint32_t dst = 0; dst < 4; ++dst) {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local), "r"(dst));
+        asm volatile("st.shared::cluster.u64 [%0], %1;\n" ::"r"(ra), "l"(v) : "memory");
+      }
+    }
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
@@ -433,7 +446,8 @@ struct PsActorOut {
 // ------------------------------------------------------------------------------------------
 struct PsCtx {
   uint8_t* smem;
-  uint64_t *full, *empty, *tmem_full;
+  uint64_t *full, *empty, *tmem_full, *zfull;
+  uint32_t zpar;      // bit s = parity of the next wait on zfull[s] (one-hot A tiles built in shared memory), identical in every thread
   uint32_t tmem;
   uint32_t it;        // pipeline stages issued so far (ring position / phase), identical in every thread
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
@@ -447,7 +461,13 @@ struct PsTile {
   int ka0, nka0, ka1, nka1;   // A k-block ranges [ka0, ka0 + nka0) then [ka1, ka1 + nka1)
   int h_first;                // GRU tiles: 1 = the first range is the h part (r, z, n_h accumulators start there), the second the z part
   int b_follows_a;            // 1: the B k-block index equals the A k-block index (GRU weights keep the state's column layout)
-  int bn;                     // B rows per k-block (GRU: 3U)
+  int bn;                     // B rows per k-block (GRU: 3U); with tmB2: rows of BOTH weight blocks (the MMA's N)
+  const CUtensorMap* tmB2;    // second weight block stacked under the first in shared memory (rows bn - n1), or NULL
+  int n1, b2_row, b2_koff;    // rows of the first block; row / k-block offset of the second
+  int tcol;                   // TMEM column of the accumulator
+  int acc0;                   // 1: the accumulator already holds a partial sum (the first MMA accumulates)
+  const uint8_t* zidx;        // != NULL: the A tiles are one-hot rows built in shared memory from these classes [128][zld] (k-block kb =
+  int zld;                    //          latent rows 2 kb, 2 kb + 1) by the epilogue warps; the producer loads the weights only
   int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
   int stage_bytes;            // ring stride of this CTA's role
   int cbar;                   // cluster barriers the epilogue executes (the producer / MMA warps mirror them)
@@ -477,6 +497,12 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
       // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
       // pre-filled while waiting; otherwise A and B of a stage are issued together
+      const int tx_sub = t.zidx ? t.bn * BK * 2 : sub_bytes;   // bytes TMA delivers per k-block
+      auto load_b = [&](uint32_t s, int u, int kb) {
+        uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES;
+        tma_load_2d(sb, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+        if (t.tmB2) tma_load_2d(sb + t.n1 * BK * 2, t.tmB2, (kb + t.b2_koff) * BK, t.b2_row, &c.full[s]);
+      };
       auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
         int st = st0;
         if (w != nullptr || gte != nullptr) {
@@ -485,11 +511,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
             const uint32_t i = c.it + st, s = i % PS_STAGES;
             ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
             const int n_sub = min(kps, nk - st * kps);
-            mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
-            for (int u = 0; u < n_sub; ++u) {
-              const int kb = st * kps + u;
-              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
-            }
+            mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
+            for (int u = 0; u < n_sub; ++u) load_b(s, u, st * kps + u);
           }
           ps_flag_wait(gte, tg, c.dbg, t.code | (6u << 20));
           ps_flag_wait(w, tw, c.dbg, t.code | (2u << 20));
@@ -499,7 +522,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
             const uint32_t s = (c.it + s2) % PS_STAGES;
             const int n_sub = min(kps, nk - s2 * kps);
             for (int u = 0; u < n_sub; ++u)
-              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
+              if (!t.zidx) tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
           }
         } else if (mark) {
           fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
@@ -509,12 +532,11 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           const uint32_t i = c.it + st, s = i % PS_STAGES;
           ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
           const int n_sub = min(kps, nk - st * kps);
-          mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * sub_bytes));
+          mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
           for (int u = 0; u < n_sub; ++u) {
             const int kb = st * kps + u, ka = ps_ka(t, kb);
-            uint8_t* sa = c.smem + s * t.stage_bytes + u * sub_bytes;
-            tma_load_2d(sa, t.tmA, ka * BK, t.a_row, &c.full[s]);
-            tma_load_2d(sa + A_STAGE_BYTES, t.tmB, (t.b_follows_a ? ka : kb) * BK, t.b_row, &c.full[s]);
+            if (!t.zidx) tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
+            load_b(s, u, kb);
           }
         }
       };
@@ -527,9 +549,14 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      uint32_t zp = c.zpar;
       for (int st = 0; st < n_st; ++st) {
         const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
+        if (t.zidx) {   // ... and the one-hot A tiles of this stage have been written
+          ps_mbar_wait(&c.zfull[s], (zp >> s) & 1u, c.dbg, t.code | (9u << 20));
+          zp ^= 1u << s;
+        }
         tc_fence_after();
         if (c.tr && st == 0) c.tr[3] = ps_now();
         const int n_sub = min(kps, nk - st * kps);
@@ -541,7 +568,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           if constexpr (GRU_U == 0) {
             const uint32_t idesc = umma_idesc_bf16(t.bn);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem + t.tcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k | t.acc0) != 0);
           } else {
             // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U).
             // The h part comes first (h_j is there long before z_j): the very first z MMA must START n_x while ADDING to r, z, so it is
@@ -577,6 +604,37 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     const int tid = (int)threadIdx.x - 64;
     if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 128) = c.tr ? c.tr + c.lap_off : nullptr;
     pre(tid);
+    if (t.zidx) {
+      // one-hot expander: the A tile of k-block kb is 128 rows x (2 latent rows x 32 classes) with one 1.0 per latent row.  Thread
+      // (r = tid / 4, q4 = tid % 4) writes 16-byte chunks 2 q4, 2 q4 + 1 of row r: 32 KB of zeros never cross the L2 -> SM fabric.
+      const int r = tid >> 2, q4 = tid & 3;
+      const int cls0 = (q4 & 1) * 16;                  // first class of this thread's span inside its latent row
+      const uint8_t* zr = t.zidx + r * t.zld + (q4 >> 1);
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t i = c.it + st, s = i % PS_STAGES;
+        if (lane == 0) ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (10u << 20));
+        __syncwarp();
+        const int n_sub = min(kps, nk - st * kps);
+        for (int u = 0; u < n_sub; ++u) {
+          const int kb = st * kps + u;
+          const int hit = (int)zr[2 * kb] - cls0;      // 0..15 if the sampled class is in this span
+          uint8_t* rowp = c.smem + s * t.stage_bytes + u * sub_bytes + r * 128;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int e0 = hit - 8 * cc;               // element inside this 16-byte chunk
+            uint4 v;
+            v.x = e0 == 0 ? 0x3F80u : (e0 == 1 ? 0x3F800000u : 0u);
+            v.y = e0 == 2 ? 0x3F80u : (e0 == 3 ? 0x3F800000u : 0u);
+            v.z = e0 == 4 ? 0x3F80u : (e0 == 5 ? 0x3F800000u : 0u);
+            v.w = e0 == 6 ? 0x3F80u : (e0 == 7 ? 0x3F800000u : 0u);
+            *reinterpret_cast<uint4*>(rowp + (((2 * q4 + cc) ^ (r & 7)) << 4)) = v;   // SWIZZLE_128B chunk position
+          }
+        }
+        fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core (async proxy)
+        epi_bar_sync();
+        if (tid == 0) mbar_arrive(&c.zfull[s]);
+      }
+    }
     if (lane == 0) ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
     __syncwarp();
     epi_bar_sync();
@@ -601,6 +659,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     __syncwarp();
     for (int b = 0; b < t.cbar; ++b) { cluster_arrive_release(); cluster_wait_acquire(); }
   }
+  if (t.zidx)
+    for (int st = 0; st < n_st; ++st) c.zpar ^= 1u << ((c.it + st) % PS_STAGES);
   c.it += (uint32_t)n_st;
   c.tile_no += 1;
   if (c.tr) c.tr += 8;
@@ -624,6 +684,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   uint64_t* empty = full + PS_STAGES;
   uint64_t* tmem_full = empty + PS_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* zfull = full + 12;   // (byte 96 of the barrier block; the lap pointer sits at byte 128)
   float* epi_sm = reinterpret_cast<float*>(smem + PS_EPI_OFF);
   int* sched = reinterpret_cast<int*>(smem + PS_SCHED_OFF);
   const int warp = threadIdx.x >> 5;
@@ -632,16 +693,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     tma_prefetch_desc(&P.tmS); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
     for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    for (int s = 0; s < PS_STAGES; ++s) mbar_init(&zfull[s], 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < PS_SCHED_STRIDE; i += GEMM_THREADS) sched[i] = __ldg(P.sched + (long)blockIdx.x * PS_SCHED_STRIDE + i);
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.zfull = zfull; c.zpar = 0; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
@@ -655,7 +717,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   auto tile_init = [&](PsTile& t, int layer, int j, int m_tile) {
     t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0;
     t.w0 = nullptr; t.t0 = 0; t.g0 = nullptr; t.gt0 = 0; t.w1 = nullptr; t.t1 = 0; t.g1 = nullptr; t.gt1 = 0; t.lsig = nullptr;
-    t.h_first = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
+    t.h_first = 0; t.tmB2 = nullptr; t.n1 = 0; t.b2_row = 0; t.b2_koff = 0; t.tcol = 0; t.acc0 = 0; t.zidx = nullptr; t.zld = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
     t.code = ((unsigned)role << 24) | ((unsigned)layer << 16) | ((unsigned)j << 8) | (unsigned)m_tile;
   };
   auto trace_window = [&](int j) {   // (at most PS_TRACE_SLOTS tiles per CTA are recorded)
@@ -687,12 +749,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         {   // prior L1: h_j -> Y1[slot 0], this CTA's 64 columns   (DynamicsPredictors.py:15-18)
           tile_init(t, 0, j, m_tile);
           t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.tcol = 256;
+          if (j < H) {
+            // the actor's first layer reads the same h k-blocks: its 64 weight rows ride along under the prior's (one N = 128 MMA per
+            // k-step), so the h part of actor L1 is already in TMEM columns [320, 384) when z_j arrives -- 10 of its 26 k-blocks
+            // leave the critical path for 8 KB more per k-block here
+            t.tmB2 = &P.tmWh1q; t.n1 = 64; t.b2_row = HS_ACTOR * 256 + 64 * rank; t.b2_koff = nkz; t.bn = 128; t.kps = 1;
+          }
           t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
           t.lsig = flag(PF_LP, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr + 256, m, row, part, 0, tid); });
           ps_cluster_handover();
         }
         {   // prior L2: Y1 -> Y2[slot 0]   (:19-22)
@@ -715,7 +784,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                                  P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
                                  RowMap{0, 0, 0, 0}};
           ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
-                         [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, g, epi_sm, taddr, m, row, part, x, tid); });
+                         [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, smem + PS_ZIDX_OFF, g, epi_sm, taddr, m, row, part, x, tid); });
         }
         ps_cluster_handover();
       }
@@ -725,11 +794,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           t.code |= 1u << 19;
           t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
           t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          if (j >= 1) {   // sampled state: the h part is already accumulated (prior L1 above), the z part's A tiles are built from the classes
+            t.nka1 = 0; t.tcol = 320; t.acc0 = 1;
+            t.zidx = smem + PS_ZIDX_OFF; t.zld = 32;
+          }
           t.lsig = flag(PF_LA, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
+          const uint32_t ta = taddr + (uint32_t)t.tcol;
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, HS_ACTOR, tid); });
+                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, ta, m, row, part, HS_ACTOR, tid); });
           ps_cluster_handover();
         }
         {   // actor L2 + output layer -> a_j = tanh(mu + sigma * eps)   (Agent.py:182-187, 199-209)
@@ -832,7 +906,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(c.tmem, 256);
+  if (warp == 1) tmem_dealloc(c.tmem, 512);
 }
 
 }  // namespace drm
