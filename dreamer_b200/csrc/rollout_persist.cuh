@@ -39,7 +39,6 @@ constexpr int PS_RING_BYTES = PS_STAGES * PS_STAGE_BYTES;          // 192 KB
 constexpr int PS_GRU_STAGE_BYTES = A_STAGE_BYTES + 192 * BK * 2;   // 40 KB: GRU CTAs (<= 192 weight rows per k-block)
 constexpr int PS_HP_OFF = PS_STAGES * PS_GRU_STAGE_BYTES;          // GRU CTAs: h_prev tile, 128 x 68 fp32, behind their ring
 constexpr int PS_WA_OFF = PS_HP_OFF + BM * 68 * 4;                 // GRU CTAs: action-term weights [3U] float4
-constexpr int PS_ZIDX_OFF = PS_RING_BYTES;                        // chain CTAs: sampled classes of the current state, [128 rows][32 latent rows] bytes
 constexpr int PS_BAR_OFF = PS_RING_BYTES + 16384;
 constexpr int PS_EPI_OFF = PS_BAR_OFF + 256;
 constexpr int PS_SCHED_OFF = PS_EPI_OFF + 16384;
@@ -235,9 +234,9 @@ struct EpiGruP {
         const float ar = fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, wr.w)));   // action term + bias
         const float az = fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, wz.w)));
         const float an = fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, wn.w)));
-        const float rr = sigmoidf_(r_[j] + ar);
-        const float zz = sigmoidf_(z_[j] + az);
-        const float nn = tanhf_(nx[j] + an + rr * (nh[j] + sm[c + j]));
+        const float rr = sigmoid_fast_(r_[j] + ar);   // (one MUFU operation per gate: common.cuh)
+        const float zz = sigmoid_fast_(z_[j] + az);
+        const float nn = tanh_fast_(nx[j] + an + rr * (nh[j] + sm[c + j]));
         hn[j] = (1.0f - zz) * nn + zz * hp[row * PITCH + c + j];
       }
       tile_put<UP>(tile, PITCH, row, c, hn);
@@ -257,9 +256,7 @@ struct EpiGruP {
 // ------------------------------------------------------------------------------------------
 struct EpiCatP {
   using Params = EpiCat::Params;
-  // zidx_sm (chain clusters): every CTA of the cluster keeps the classes of the whole state, [128 rows][32 latent rows] bytes, in its
-  // shared memory -- the actor's first layer builds its one-hot A tiles from them -- so this tile's 8 columns go to all four.
-  static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, uint8_t* zidx_sm, const TileG& g, float* sm, uint32_t taddr,
+  static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, const TileG& g, float* sm, uint32_t taddr,
                                              int m, int row, int part, int slot, int tid) {
     const int m0 = m - row;
     const int G = g.bn >> 5;
@@ -307,16 +304,6 @@ struct EpiCatP {
     }
     epi_bar_sync();
     ps_lap(sm, tid, 2);
-    if (zidx_sm && tid < BM) {
-      const unsigned long long v = *reinterpret_cast<const unsigned long long*>(idx_sm + tid * 8);
-      const uint32_t local = smem_u32(zidx_sm + tid * 32 + slot * 8);
-#pragma unroll
-      for (uint32_t dst = 0; dst < 4; ++dst) {
-        uint32_t ra;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local), "r"(dst));
-        asm volatile("st.shared::cluster.u64 [%0], %1;\n" ::"r"(ra), "l"(v) : "memory");
-      }
-    }
     if (p.idx) {
       for (int i = tid; i < BM * 8; i += EPI_THREADS) {
         const int r = i >> 3, gi = i & 7;
@@ -446,8 +433,7 @@ struct PsActorOut {
 // ------------------------------------------------------------------------------------------
 struct PsCtx {
   uint8_t* smem;
-  uint64_t *full, *empty, *tmem_full, *zfull;
-  uint32_t zpar;      // bit s = parity of the next wait on zfull[s] (one-hot A tiles built in shared memory), identical in every thread
+  uint64_t *full, *empty, *tmem_full;
   uint32_t tmem;
   uint32_t it;        // pipeline stages issued so far (ring position / phase), identical in every thread
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
@@ -466,11 +452,10 @@ struct PsTile {
   int n1, b2_row, b2_koff;    // rows of the first block; row / k-block offset of the second
   int tcol;                   // TMEM column of the accumulator
   int acc0;                   // 1: the accumulator already holds a partial sum (the first MMA accumulates)
-  const uint8_t* zidx;        // != NULL: the A tiles are one-hot rows built in shared memory from these classes [128][zld] (k-block kb =
-  int zld;                    //          latent rows 2 kb, 2 kb + 1) by the epilogue warps; the producer loads the weights only
   int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
   int stage_bytes;            // ring stride of this CTA's role
   int cbar;                   // cluster barriers the epilogue executes (the producer / MMA warps mirror them)
+  int chain;                  // 1: a cluster hand-over follows this tile
   const unsigned* w0; unsigned t0;     // data dependency of the first A k-block range (NULL: resolved by a barrier / program order)
   const unsigned* g0; unsigned gt0;    // bandwidth gate of the first range: wait until the chain's loads of that phase have landed
   const unsigned* w1; unsigned t1;     // the same two for the second range (only honoured with kps == 1)
@@ -497,7 +482,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
       // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
       // pre-filled while waiting; otherwise A and B of a stage are issued together
-      const int tx_sub = t.zidx ? t.bn * BK * 2 : sub_bytes;   // bytes TMA delivers per k-block
+      const int tx_sub = sub_bytes;
       auto load_b = [&](uint32_t s, int u, int kb) {
         uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES;
         tma_load_2d(sb, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
@@ -522,7 +507,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
             const uint32_t s = (c.it + s2) % PS_STAGES;
             const int n_sub = min(kps, nk - s2 * kps);
             for (int u = 0; u < n_sub; ++u)
-              if (!t.zidx) tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
+              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
           }
         } else if (mark) {
           fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
@@ -535,7 +520,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
           for (int u = 0; u < n_sub; ++u) {
             const int kb = st * kps + u, ka = ps_ka(t, kb);
-            if (!t.zidx) tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
+            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
             load_b(s, u, kb);
           }
         }
@@ -549,14 +534,9 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t zp = c.zpar;
       for (int st = 0; st < n_st; ++st) {
         const uint32_t i = c.it + st, s = i % PS_STAGES;
         ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
-        if (t.zidx) {   // ... and the one-hot A tiles of this stage have been written
-          ps_mbar_wait(&c.zfull[s], (zp >> s) & 1u, c.dbg, t.code | (9u << 20));
-          zp ^= 1u << s;
-        }
         tc_fence_after();
         if (c.tr && st == 0) c.tr[3] = ps_now();
         const int n_sub = min(kps, nk - st * kps);
@@ -604,37 +584,6 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     const int tid = (int)threadIdx.x - 64;
     if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 128) = c.tr ? c.tr + c.lap_off : nullptr;
     pre(tid);
-    if (t.zidx) {
-      // one-hot expander: the A tile of k-block kb is 128 rows x (2 latent rows x 32 classes) with one 1.0 per latent row.  Thread
-      // (r = tid / 4, q4 = tid % 4) writes 16-byte chunks 2 q4, 2 q4 + 1 of row r: 32 KB of zeros never cross the L2 -> SM fabric.
-      const int r = tid >> 2, q4 = tid & 3;
-      const int cls0 = (q4 & 1) * 16;                  // first class of this thread's span inside its latent row
-      const uint8_t* zr = t.zidx + r * t.zld + (q4 >> 1);
-      for (int st = 0; st < n_st; ++st) {
-        const uint32_t i = c.it + st, s = i % PS_STAGES;
-        if (lane == 0) ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (10u << 20));
-        __syncwarp();
-        const int n_sub = min(kps, nk - st * kps);
-        for (int u = 0; u < n_sub; ++u) {
-          const int kb = st * kps + u;
-          const int hit = (int)zr[2 * kb] - cls0;      // 0..15 if the sampled class is in this span
-          uint8_t* rowp = c.smem + s * t.stage_bytes + u * sub_bytes + r * 128;
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int e0 = hit - 8 * cc;               // element inside this 16-byte chunk
-            uint4 v;
-            v.x = e0 == 0 ? 0x3F80u : (e0 == 1 ? 0x3F800000u : 0u);
-            v.y = e0 == 2 ? 0x3F80u : (e0 == 3 ? 0x3F800000u : 0u);
-            v.z = e0 == 4 ? 0x3F80u : (e0 == 5 ? 0x3F800000u : 0u);
-            v.w = e0 == 6 ? 0x3F80u : (e0 == 7 ? 0x3F800000u : 0u);
-            *reinterpret_cast<uint4*>(rowp + (((2 * q4 + cc) ^ (r & 7)) << 4)) = v;   // SWIZZLE_128B chunk position
-          }
-        }
-        fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core (async proxy)
-        epi_bar_sync();
-        if (tid == 0) mbar_arrive(&c.zfull[s]);
-      }
-    }
     if (lane == 0) ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
     __syncwarp();
     epi_bar_sync();
@@ -652,15 +601,14 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
         red_release_add(t.sig, 1u);
       }
     }
-    fence_proxy_async_all();   // this thread's generic-proxy accesses to the ring / its global stores vs the next tile's TMA traffic
+    if (!t.chain) fence_proxy_async_all();   // this thread's generic-proxy accesses to the ring / its global stores vs the next tile's TMA traffic
+                                             // (chain tiles: the cluster hand-over's release / acquire + the consumer's proxy fence order them)
     if (c.tr && tid == 0) c.tr[7] = ps_now();
   }
   if (warp < 2) {   // mirror the cluster barriers of the epilogue (barrier.cluster counts every thread of the cluster)
     __syncwarp();
     for (int b = 0; b < t.cbar; ++b) { cluster_arrive_release(); cluster_wait_acquire(); }
   }
-  if (t.zidx)
-    for (int st = 0; st < n_st; ++st) c.zpar ^= 1u << ((c.it + st) % PS_STAGES);
   c.it += (uint32_t)n_st;
   c.tile_no += 1;
   if (c.tr) c.tr += 8;
@@ -684,7 +632,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   uint64_t* empty = full + PS_STAGES;
   uint64_t* tmem_full = empty + PS_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  uint64_t* zfull = full + 12;   // (byte 96 of the barrier block; the lap pointer sits at byte 128)
   float* epi_sm = reinterpret_cast<float*>(smem + PS_EPI_OFF);
   int* sched = reinterpret_cast<int*>(smem + PS_SCHED_OFF);
   const int warp = threadIdx.x >> 5;
@@ -693,7 +640,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     tma_prefetch_desc(&P.tmS); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
     for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
-    for (int s = 0; s < PS_STAGES; ++s) mbar_init(&zfull[s], 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < PS_SCHED_STRIDE; i += GEMM_THREADS) sched[i] = __ldg(P.sched + (long)blockIdx.x * PS_SCHED_STRIDE + i);
@@ -703,7 +649,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.zfull = zfull; c.zpar = 0; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
@@ -715,9 +661,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   float* tile = reinterpret_cast<float*>(smem);
   auto flag = [&](int kind, int m) { return P.flags + (long)(kind * mt + m) * 32; };
   auto tile_init = [&](PsTile& t, int layer, int j, int m_tile) {
-    t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0;
+    t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0; t.chain = role == PS_CHAIN ? 1 : 0;
     t.w0 = nullptr; t.t0 = 0; t.g0 = nullptr; t.gt0 = 0; t.w1 = nullptr; t.t1 = 0; t.g1 = nullptr; t.gt1 = 0; t.lsig = nullptr;
-    t.h_first = 0; t.tmB2 = nullptr; t.n1 = 0; t.b2_row = 0; t.b2_koff = 0; t.tcol = 0; t.acc0 = 0; t.zidx = nullptr; t.zld = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
+    t.h_first = 0; t.tmB2 = nullptr; t.n1 = 0; t.b2_row = 0; t.b2_koff = 0; t.tcol = 0; t.acc0 = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
     t.code = ((unsigned)role << 24) | ((unsigned)layer << 16) | ((unsigned)j << 8) | (unsigned)m_tile;
   };
   auto trace_window = [&](int j) {   // (at most PS_TRACE_SLOTS tiles per CTA are recorded)
@@ -761,7 +707,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr + 256, m, row, part, 0, tid); });
+                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, taddr + 256, m, row, part, 0, tid); });
           ps_cluster_handover();
         }
         {   // prior L2: Y1 -> Y2[slot 0]   (:19-22)
@@ -770,7 +716,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p2_b, P.p2_g, P.p2_be, nullptr, 0, P.Y2, 256, 0, 0, P.hp2, 1e-5f, P.bnp2};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
           ps_cluster_handover();
         }
         // prior logits + sample: 256 logit columns (8 latent rows) per tile, tiles rank, rank + 4, ...   (:23, 31-40)
@@ -784,7 +730,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
                                  P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
                                  RowMap{0, 0, 0, 0}};
           ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
-                         [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, smem + PS_ZIDX_OFF, g, epi_sm, taddr, m, row, part, x, tid); });
+                         [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, g, epi_sm, taddr, m, row, part, x, tid); });
         }
         ps_cluster_handover();
       }
@@ -794,16 +740,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           t.code |= 1u << 19;
           t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
           t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
-          if (j >= 1) {   // sampled state: the h part is already accumulated (prior L1 above), the z part's A tiles are built from the classes
+          if (j >= 1) {   // the h part is already accumulated (prior L1 above): z k-blocks only
             t.nka1 = 0; t.tcol = 320; t.acc0 = 1;
-            t.zidx = smem + PS_ZIDX_OFF; t.zld = 32;
           }
           t.lsig = flag(PF_LA, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
           const uint32_t ta = taddr + (uint32_t)t.tcol;
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run(p, g, epi_sm, tile, ta, m, row, part, HS_ACTOR, tid); });
+                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, ta, m, row, part, HS_ACTOR, tid); });
           ps_cluster_handover();
         }
         {   // actor L2 + output layer -> a_j = tanh(mu + sigma * eps)   (Agent.py:182-187, 199-209)
@@ -811,6 +756,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           t.code |= 1u << 19;
           t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
           t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 2;
+          t.chain = 0;   // (no hand-over follows, and its epilogue used the ring as scratch: keep the proxy fence before the next tile's TMA loads)
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
           const PsActorOut ao{P.Wh3 + (long)HS_ACTOR * 256 * 256, P.h3_b + HS_ACTOR * 256, P.normals + (long)j * B * A,
@@ -820,7 +766,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); ao.stage(epi_sm, tid); },
                          [&](int tid) {
                            float v[16];
-                           EpiLnSiluN4::compute(p, g, epi_sm, taddr, m, row, part, v);
+                           EpiLnSiluN4::compute<true>(p, g, epi_sm, taddr, m, row, part, v);
                            ao.run(v, epi_sm, red, xact, m, row, part, tid);
                          });
         }
