@@ -14,11 +14,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _close(got, ref, atol=2e-2, rtol=1e-2, what=""):
-    got, ref = got.detach().cpu().float(), torch.as_tensor(ref).detach().cpu().float()
+def _close(got, ref, rel=1e-2, what="", **_):
+    """North-star bound for bf16-operand quantities: max |got - ref| <= 1e-2 of the reference tensor's scale (profiles/parity_r2.md)."""
+    got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
-    err = (got - ref).abs()
-    assert (err <= atol + rtol * ref.abs()).all(), f"{what}: max abs err {err.max().item():.4g}"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= rel * max(scale, 1e-6), f"{what}: max abs err {err:.4g} = {err / max(scale, 1e-6):.3g} of the tensor's scale {scale:.3g}"
 
 
 def _dreamer(cfg, sd):
@@ -58,7 +60,7 @@ def test_module_forward_surface_matches_oracle():
     _close(ag.critic.value(hd, zd), O.critic_value(sd, h0[:, 0], z0[:, 0]).unsqueeze(1), what="Critic.value")
     # Encoder / Decoder
     obs = (W.sequence_inputs(cfg, B, 1, seed=15)[0] / 255.0 - 0.5)
-    _close(wm.encoder(hd, obs.to(DEV)), O.encoder_logits(sd, h0[:, 0], obs[:, 0]).reshape(B, 1, -1), atol=3e-2, what="Encoder.forward")
+    _close(wm.encoder(hd, obs.to(DEV)), O.encoder_logits(sd, h0[:, 0], obs[:, 0]).reshape(B, 1, -1), what="Encoder.forward")
     _close(wm.decoder(hd, zd), O.decoder_forward(sd, h0[:, 0], z0[:, 0], (64, 64)).unsqueeze(1), what="Decoder.forward")
     # imagine_step / observe_step return shapes and values
     h2, z2, r, c = wm.imagine_step(hd, zd, a.to(DEV), uniforms=u[0].to(DEV))

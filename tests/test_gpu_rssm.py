@@ -1,6 +1,7 @@
 """GPU parity of the tcgen05 RSSM stages and the imagination rollout against the oracle / golden fixtures.
 
-Tolerances: GEMM operands are bf16 with fp32 accumulation -> 1e-2 (north star "bf16 <= 1e-2 relative");
+Tolerances: GEMM operands are bf16 with fp32 accumulation -> max |err| <= 1e-2 of the tensor's scale (north star "bf16 <= 1e-2
+relative"; achieved values in profiles/parity_r2.md);
 sampled indices are compared bit-exactly (i) at the kernel boundary, from the kernel's own fp32 logits,
 and (ii) over whole trajectories on fixtures whose uniforms sit in the middle half of the selected CDF bin.
 """
@@ -16,7 +17,6 @@ from oracle import weights as W
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-ATOL = 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -31,11 +31,15 @@ def _model(ops, cfg, seed):
     return sd, model
 
 
-def _close(got, ref, atol=ATOL, rtol=1e-2, what=""):
+def _close(got, ref, rel=1e-2, what="", **_):
+    """North-star bound for bf16-operand quantities: max |got - ref| <= 1e-2 of the reference tensor's scale (max |ref|).
+    The achieved values per quantity and configuration are tabulated by tests/test_gpu_parity_table.py (profiles/parity_r2.md:
+    worst case 5.5e-3)."""
     got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
-    err = (got - ref).abs()
-    assert (err <= atol + rtol * ref.abs()).all(), f"{what}: max abs err {err.max().item():.4g}"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= rel * max(scale, 1e-6), f"{what}: max abs err {err:.4g} = {err / max(scale, 1e-6):.3g} of the tensor's scale {scale:.3g}"
 
 
 CFGS = {"small": W.small_config(), "ref": dict(W.REF_CONFIG)}
@@ -109,7 +113,7 @@ def test_rollout_matches_reference_fixture(ops, golden_dir, fixture):
         _close(out[i], torch.from_numpy(g[key]), what=key)
     if "hidden" in g.files:
         _close(out[1], torch.from_numpy(g["hidden"]), what="hidden")
-        _close(out[0][:, -1], torch.from_numpy(g["latent_last"]).reshape(B, 32, 32), atol=1e-6, what="latent")
+        _close(out[0][:, -1], torch.from_numpy(g["latent_last"]).reshape(B, 32, 32), rel=1e-6, what="latent")
     else:
         _close(out[1][:, -1], torch.from_numpy(g["hidden_last"]), what="hidden_last")
     # latent is a straight-through one-hot of idx; hidden[:,0] / latent[:,0] echo the inputs

@@ -22,11 +22,15 @@ def ops():
     return _ops
 
 
-def _close(got, ref, atol=2e-2, rtol=1e-2, what=""):
+def _close(got, ref, rel=1e-2, what="", **_):
+    """North-star bound for bf16-operand quantities: max |got - ref| <= 1e-2 of the reference tensor's scale (max |ref|).
+    The achieved values per quantity and configuration are tabulated by tests/test_gpu_parity_table.py (profiles/parity_r2.md:
+    worst case 5.5e-3)."""
     got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
-    err = (got - ref).abs()
-    assert (err <= atol + rtol * ref.abs()).all(), f"{what}: max abs err {err.max().item():.4g} (ref max {ref.abs().max().item():.3g})"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= rel * max(scale, 1e-6), f"{what}: max abs err {err:.4g} = {err / max(scale, 1e-6):.3g} of the tensor's scale {scale:.3g}"
 
 
 def _build(ops, cfg, seed):
@@ -51,7 +55,7 @@ def test_encoder_logits_and_decoder(ops, name, N):
     h = h0[:, 0]
     ref_logits = O.encoder_logits(sd, h, obs)
     got = ws.encode(h.to(DEV), obs.to(DEV))
-    _close(got["logits"], ref_logits, atol=3e-2, what="encoder logits")
+    _close(got["logits"], ref_logits, what="encoder logits")
     # kernel-boundary sampling contract on the kernel's own logits
     uu = O.interior_uniforms(O.unimix_probs(got["logits"].cpu()), u[0], 0.0, 1e-5)
     z_ref, idx_ref, _ = O.categorical_st(got["logits"].cpu(), uu)
@@ -61,7 +65,7 @@ def test_encoder_logits_and_decoder(ops, name, N):
     z = z_ref
     ref_mu = O.decoder_forward(sd, h, z, obs.shape[-2:])
     mu = ws.decode(h.to(DEV), z.to(DEV))
-    _close(mu, ref_mu, atol=2e-2, what="decoder mu")
+    _close(mu, ref_mu, what="decoder mu")
 
 
 def test_neg_sse_rows(ops):
@@ -86,15 +90,15 @@ def test_observe_scan_and_heads_match_reference_fixture(ops, golden_dir, fixture
     sc = ws.scan(obs_n.to(DEV), act.to(DEV), torch.from_numpy(g["uniforms_used"]).to(DEV))
     assert np.array_equal(sc["idx"].cpu().numpy(), g["idx"])                         # sampled posterior indices: bit-exact
     _close(sc["hidden"], torch.from_numpy(g["hidden"]), what="hidden")
-    _close(sc["logits"][:, 1:], torch.from_numpy(g["post_logits"]), atol=3e-2, what="posterior logits")
+    _close(sc["logits"][:, 1:], torch.from_numpy(g["post_logits"]), what="posterior logits")
     hd = ws.heads()
-    _close(hd["prior_logits"][:, 1:], torch.from_numpy(g["prior_logits"]), atol=3e-2, what="prior logits")
+    _close(hd["prior_logits"][:, 1:], torch.from_numpy(g["prior_logits"]), what="prior logits")
     obs_ll = ops.neg_sse_rows(hd["dec_mu"], obs_n.to(DEV))[:, 1:]
     ref_ll = torch.from_numpy(g["obs_ll"])
     assert ((obs_ll.cpu() - ref_ll).abs() <= 1e-2 * ref_ll.abs()).all(), (obs_ll.cpu() - ref_ll).abs().max()
     buckets = sd["world_model.reward_predictor.buckets_rew"].to(DEV)
     rew_ll = ops.twohot_ce(hd["reward_logits"], rew[:, :T - 1].to(DEV), buckets)
-    _close(rew_ll, torch.from_numpy(g["rew_ll"]), atol=5e-2, what="reward log-likelihood")
+    _close(rew_ll, torch.from_numpy(g["rew_ll"]), what="reward log-likelihood")
     bce = torch.nn.functional.binary_cross_entropy_with_logits(hd["cont_logit"].cpu(), cont[:, :T - 1], reduction="none")
     _close(bce, torch.from_numpy(g["cont_bce"]), what="continue BCE")
     # KL-balance term through the fused kernel, against the fixture's masked mean
@@ -126,14 +130,14 @@ def test_observe_c3_shapes_and_teacher_forced(ops):
         ap = act[:, t - 1] if t > 0 else torch.zeros(B, 3)
         z2, h2, lg, idx, _ = O.observe_step(sd, zp, hp, ap, obs_n[:, t], u[t])
         _close(sc["hidden"][:, t], h2, what=f"hidden t={t}")
-        _close(sc["logits"][:, t], lg, atol=3e-2, what=f"posterior logits t={t}")
+        _close(sc["logits"][:, t], lg, what=f"posterior logits t={t}")
         mism += (idx != sc["idx"][:, t].long()).sum().item()
     assert mism <= 0.01 * 5 * B * 32, mism
     hd = ws.heads(reward=False, cont=False)
     t = 21
     dec = O.decoder_forward(sd, sc["hidden"][:, t], sc["latent"][:, t], (64, 64))
     _close(hd["dec_mu"][:, t], dec, what="decoder mu")
-    _close(hd["prior_logits"][:, t], O.prior_logits(sd, sc["hidden"][:, t]), atol=3e-2, what="prior logits")
+    _close(hd["prior_logits"][:, t], O.prior_logits(sd, sc["hidden"][:, t]), what="prior logits")
 
 
 def test_persistent_conv_gemm_is_bit_identical_to_one_tile_per_cta(ops):
