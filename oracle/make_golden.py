@@ -191,6 +191,98 @@ def golden_agent(cfg, tag, B, H, seed):
     return errs
 
 
+def grad_digest(named, prefix, out, n=1024):
+    """Compact, elementwise-checkable digest of a set of tensors: every element of small tensors, a fixed random sample of
+    `n` elements of large ones (indices from a crc32(key)-seeded stream), plus each tensor's L2 norm."""
+    import zlib
+    for key, t in named:
+        t = t.detach().reshape(-1).double()
+        if t.numel() <= n:
+            ix = np.arange(t.numel())
+        else:
+            ix = np.sort(np.random.RandomState(zlib.crc32(key.encode()) & 0x7FFFFFFF).choice(t.numel(), n, replace=False))
+        out[f"{prefix}::{key}::idx"] = ix.astype(np.int32)
+        out[f"{prefix}::{key}::val"] = t.numpy()[ix].astype(np.float32)
+        out[f"{prefix}::{key}::norm"] = np.float64(t.norm().item())
+
+
+@contextlib.contextmanager
+def capture_preclip_grads(store):
+    """The reference clips right after backward (WorldModel.py:198, Agent.py:147-148): snapshot every parameter's gradient on
+    entry to clip_grad_norm_, i.e. the raw autograd result."""
+    orig = torch.nn.utils.clip_grad_norm_
+
+    def hook(parameters, max_norm, *a, **k):
+        params = list(parameters)
+        store.append([None if p.grad is None else p.grad.detach().clone() for p in params])
+        return orig(params, max_norm, *a, **k)
+
+    torch.nn.utils.clip_grad_norm_ = hook
+    try:
+        yield
+    finally:
+        torch.nn.utils.clip_grad_norm_ = orig
+
+
+def golden_wm_grads(cfg, tag, B, T, seed, margin=0.25):
+    """Per-parameter gradients and post-step weights of the REFERENCE's WorldModel.training_step (WorldModel.py:148-202,
+    autocast off = fp32) on the trajectory fixed by `uniforms_used`."""
+    sd = W.make_state_dict(cfg, seed=seed)
+    cfg = dict(cfg, horizon=T, batch_size=B, sequence_length=T)
+    ref = build_reference(cfg, sd)
+    obs, act, rew, cont, u = W.sequence_inputs(cfg, B, T, seed=seed + 2)
+    with torch.no_grad():
+        total, parts, extras = O.world_model_loss(sd, obs, act, rew, cont, u, T, margin_frac=margin, delta=1e-5)
+    used = extras[3]
+    wm = ref.world_model
+    before = {k: p.detach().clone() for k, p in wm.named_parameters()}
+    st = Streams(); st.u = [used[t] for t in range(T)]
+    snaps = []
+    with patched_reference(st), capture_preclip_grads(snaps):
+        ref_total = wm.training_step(obs, act, rew, cont).detach()
+    assert len(snaps) == 1 and not st.u
+    names = [k for k, _ in wm.named_parameters()]
+    assert len(names) == len(snaps[0])
+    pack = dict(cfg=json.dumps(cfg), seed=seed, B=B, T=T, margin=margin, uniforms_used=used.numpy(), total_loss=ref_total.numpy(),
+                idx=extras[2].numpy().astype(np.uint8), lr=np.float64(cfg["world_model_lr"]))
+    grad_digest([(k, g) for k, g in zip(names, snaps[0]) if g is not None], "grad", pack)
+    grad_digest([(k, p.detach() - before[k]) for k, p in wm.named_parameters()], "dw", pack)
+    np.savez_compressed(os.path.join(GOLD, f"{tag}.npz"), **pack)
+    err = check(f"{tag}.total_loss", ref_total, total, tol=1e-4)
+    gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in snaps[0] if g is not None)))
+    return dict(total_loss=err, grad_norm=gnorm, n_params=len(names))
+
+
+def golden_agent_grads(cfg, tag, B, H, seed):
+    """Actor and critic gradients / post-step weights of the REFERENCE's Agent.train_step (Agent.py:96-154) on a rollout made with
+    gradients enabled, exactly as Dreamer.train_Agent does (Dreamer.py:264-287): the actor gradient includes the path through
+    the imagined states."""
+    sd = W.make_state_dict(cfg, seed=seed)
+    ref = build_reference(cfg, sd)
+    ref.horizon = H
+    z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=seed + 1)
+    with torch.no_grad():
+        out = O.dream_episodes(sd, z0, h0, u, n, margin_frac=0.25, delta=1e-5)
+    used = out[9]
+    st = Streams(); st.u = [used[t] for t in range(H)]; st.n = [n[t] for t in range(H)]
+    ag = ref.agent
+    before = {k: p.detach().clone() for k, p in ag.named_parameters()}
+    snaps = []
+    with patched_reference(st), capture_preclip_grads(snaps):
+        r = ref.dream_episodes(z0, h0)                                   # with autograd (Dreamer.py:274)
+        la, lc = ag.train_step(r[0], r[1], r[3], r[4], r[2], r[5], r[6])   # Agent.py:96-154
+    assert len(snaps) == 2                                                # critic, then actor (Agent.py:147-148)
+    pack = dict(cfg=json.dumps(cfg), seed=seed, B=B, H=H, uniforms_used=used.numpy(), loss_actor=la.detach().numpy(),
+                loss_critic=lc.detach().numpy(), S=np.float32(ag.S))
+    grad_digest([("critic." + k, g) for (k, _), g in zip(ag.critic.named_parameters(), snaps[0])], "grad", pack)
+    grad_digest([("actor." + k, g) for (k, _), g in zip(ag.actor.named_parameters(), snaps[1])], "grad", pack)
+    grad_digest([(k, p.detach() - before[k]) for k, p in ag.named_parameters() if not k.startswith("target_critic")], "dw", pack)
+    np.savez_compressed(os.path.join(GOLD, f"{tag}.npz"), **pack)
+    return dict(loss_actor=float(la), loss_critic=float(lc),
+                actor_grad_norm=float(torch.sqrt(sum((g.double() ** 2).sum() for g in snaps[1]))),
+                critic_grad_norm=float(torch.sqrt(sum((g.double() ** 2).sum() for g in snaps[0]))))
+
+
 def golden_replay(tag):
     sys.path.insert(0, REF)
     from Buffer import Buffer  # Buffer.py:5
@@ -243,6 +335,8 @@ def main():
     report["observe_small"] = golden_observe(small, "observe_small", B=3, T=6, seed=21)
     report["agent_small"] = golden_agent(small, "agent_small", B=6, H=5, seed=31)
     report["replay_small"] = golden_replay("replay_small")
+    report["wm_grads_small"] = golden_wm_grads(small, "wm_grads_small", B=3, T=6, seed=61)
+    report["agent_grads_small"] = golden_agent_grads(small, "agent_grads_small", B=6, H=5, seed=71)
     # full reference sizes: compared here, only a digest is committed
     full = dict(W.REF_CONFIG, horizon=15)
     errs, r, out = golden_rollout(full, "rollout_ref", B=32, H=15, seed=41, save_full=False)
