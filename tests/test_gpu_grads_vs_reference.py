@@ -59,7 +59,7 @@ def test_world_model_gradient_and_step_match_the_reference(golden_dir):
     wm.optimiser.zero_grad()
     bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_k, parts)
     got = {k: p.grad for k, p in wm.named_parameters() if p.grad is not None}
-    rel, worst = _compare(_digest(g, "grad"), got, "world-model gradient", rel_bound=6e-2, norm_bound=8e-2)
+    rel, worst = _compare(_digest(g, "grad"), got, "world-model gradient", rel_bound=1e-2, norm_bound=2e-2)     # measured: 3.3e-3 / 2.5e-3
     print(f"world-model gradient vs reference autograd: relative L2 {rel:.3g}, worst norm ratio off by {worst[0]:.3g} ({worst[1]})")
     # the whole step (clip(100) + AdamW, first step): the update of every element whose (clipped) gradient is clearly non-zero is
     # -lr * g / (|g| + eps) ~ -lr * sign(g)
@@ -101,6 +101,6 @@ def test_agent_gradients_match_the_reference(golden_dir):
     got = {"actor." + k: p.grad for k, p in ag.actor.named_parameters()}
     got.update({"critic." + k: p.grad for k, p in ag.critic.named_parameters()})
     ref = _digest(g, "grad")
-    rel_a, worst_a = _compare({k: v for k, v in ref.items() if k.startswith("actor.")}, got, "actor gradient", rel_bound=6e-2, norm_bound=8e-2)
-    rel_c, worst_c = _compare({k: v for k, v in ref.items() if k.startswith("critic.")}, got, "critic gradient", rel_bound=3e-2, norm_bound=5e-2)
+    rel_a, worst_a = _compare({k: v for k, v in ref.items() if k.startswith("actor.")}, got, "actor gradient", rel_bound=1e-2, norm_bound=2e-2)    # measured 1.6e-3
+    rel_c, worst_c = _compare({k: v for k, v in ref.items() if k.startswith("critic.")}, got, "critic gradient", rel_bound=1e-2, norm_bound=2e-2)  # measured 1.3e-3
     print(f"actor gradient vs reference autograd: relative L2 {rel_a:.3g}; critic: {rel_c:.3g}")
