@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- imagined latent states/s of the RSSM imagination rollout (BASELINE.json metric).
+"""bench.py -- the BASELINE.json metrics of the RSSM hot path: imagined latent states/s and world-model train steps/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2x16|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2x16|c3|c4|c5] [--impl ours|reference|reference-cuda]
 
-A "step" is one pass of the hot path over one batch: Dreamer.dream_episodes (Dreamer.py:143-175) for
-B start states x H imagined steps with random-init weights of the reference architecture and
-synthetic inputs.  Default workload = BASELINE.json configs[1]: 1024 start states
-x horizon 15 at car_racer_config.yaml sizes, per GPU (weak scaling: every rank owns its own 1024
-start states; the rollout needs no collective).
+Workloads (BASELINE.json `configs`; a "step" is one pass of the hot path over one batch of synthetic input):
+    c2     (default) imagination rollout, 1024 start states x horizon 15 per GPU, car_racer_config sizes   -> imagined states/s, weak scaling
+    c2x16  the same with 16 384 start states per GPU
+    c3     WorldModel.training_step, batch 16 x seq 64 of 64x64x3 frames per GPU (data parallel: flat-bucket gradient all-reduce
+           + packed-scalar all-reduce over NCCL)                                                          -> train steps/s, weak scaling
+    c4     16 384 start states x horizon 15 with GRU deter 4096, split over the N GPUs                   -> imagined states/s, STRONG scaling
+    c5     one whole synthetic training iteration (replay gather -> 2 world-model steps -> warm start -> rollout -> 2 agent
+           steps) with the gradient all-reduces at N GPUs                                                -> iterations/s, weak scaling
 
-One JSON line is printed by rank 0.  `value` = device-timed whole-job states/s with inputs resident
-in HBM; `e2e` = the same through the public host-buffer API (pinned-host inputs copied H2D and the
-rewards/continues read back D2H inside the timed region); `roofline` = the dominant kernel (the fused
-tcgen05 GRU stage) against the measured bf16 peak; `cpu_baseline` = the CPU port of the reference
-(oracle/, stock sampler) on this box's host cores, bounded sample.
+Arms: `ours` = this repository on the GPU; `reference` = the UNMODIFIED reference (oracle/_ref, a byte-for-byte copy of its Python
+modules made by oracle/make_ref.py) on the host cores, bounded sample; `reference-cuda` = the same unmodified code through stock
+PyTorch on the B200 (its real deployment mode) -- context, not the target.
+
+One JSON line is printed by rank 0.  `value` = device-timed whole-job throughput with inputs resident in HBM; `e2e` = the same
+through the public host-buffer call (pinned-host inputs copied H2D and results read back D2H inside the timed region);
+`roofline` = the dominant kernel against the measured bf16 peak (MEASURED_PEAKS.json); `cpu_baseline` = the reference on this
+box's host cores (N = 1 only).
 """
 from __future__ import annotations
 
@@ -31,11 +37,14 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (B per GPU, H, config overrides, description)
-    "c2": (1024, 15, {}, "imagination rollout 1024 start states x horizon 15, car_racer_config sizes (BASELINE configs[1])"),
-    "c2x16": (16384, 15, {}, "imagination rollout 16384 start states x horizon 15, car_racer_config sizes"),
-    "c4": (16384, 15, {"hidden_state_dims": 4096}, "imagination rollout 16384 start states x horizon 15, GRU deter 4096 (BASELINE configs[3])"),
+    # name: (kind, B per GPU (c4: total), H / T, config overrides, description)
+    "c2": ("rollout", 1024, 15, {}, "imagination rollout 1024 start states x horizon 15, car_racer_config sizes (BASELINE configs[1])"),
+    "c2x16": ("rollout", 16384, 15, {}, "imagination rollout 16384 start states x horizon 15, car_racer_config sizes"),
+    "c4": ("rollout", 16384, 15, {"hidden_state_dims": 4096}, "imagination rollout 16384 start states x horizon 15, GRU deter 4096, start states split over the GPUs (BASELINE configs[3])"),
+    "c3": ("wm", 16, 64, {}, "WorldModel.training_step, batch 16 x seq 64 of 64x64x3 frames per GPU (BASELINE configs[2])"),
+    "c5": ("iter", 50, 50, {}, "one training iteration at car_racer_config.yaml (batch 50 x seq 50 per GPU, horizon 30, 2 world-model + 2 actor-critic epochs), gradient all-reduce over the GPUs (BASELINE configs[4])"),
 }
+WM_FLOPS_PER_BT = 3 * 119.7e6      # 119.7 MFLOP forward per (b, t), x3 for forward + backward
 
 
 def flops_per_state(cfg):
@@ -99,67 +108,434 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
 
 
-def make_problem(workload):
+def make_problem(workload, world=1):
     from dreamer_b200 import synthetic as W   # synthetic weights / inputs (deterministic numpy streams)
-    B, H, over, desc = WORKLOADS[workload]
-    cfg = dict(W.REF_CONFIG, horizon=H, **over)
+    kind, B, H, over, desc = WORKLOADS[workload]
+    if workload == "c4":
+        B = max(1, B // world)                # strong scaling: the 16 384 start states are split over the ranks
+    cfg = dict(W.REF_CONFIG, **over)
+    if kind == "rollout":
+        cfg["horizon"] = H
+    elif kind == "wm":
+        cfg.update(horizon=H, sequence_length=H, batch_size=B)
     sd = W.make_state_dict(cfg, seed=0, actor_mu_zero=True)
-    return cfg, sd, B, H, desc
+    return kind, cfg, sd, B, H, desc
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port with the stock sampler),
-    all host threads, on a bounded sample of the workload.  Rank 0 only."""
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference arms: the UNMODIFIED reference from oracle/_ref (CPU, or CUDA through stock PyTorch)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _load_reference(cfg, sd, device):
+    """-> (Dreamer instance, kind).  oracle/_ref holds byte-for-byte copies of the reference's modules (oracle/make_ref.py)."""
+    from oracle import make_ref                                   # the reference arm may execute oracle/ (tier rule 4)
+    if not make_ref.available():
+        return None, "port"
+    return make_ref.load_dreamer(cfg, sd, device), "reference"
+
+
+def _fill_reference_buffer(d, cfg, n, seed=1):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        d.buffer.add_to_buffer(rng.integers(0, 256, size=(3, 64, 64)).astype(np.uint8), rng.uniform(-1, 1, 3).astype(np.float32),
+                               float(rng.standard_normal()), float(rng.random() > 0.02))
+
+
+def run_reference(args, rank, world, cuda):
+    """--impl reference / reference-cuda.  Rank 0 only; every step is a bounded sample of the workload."""
     if rank != 0:
         return
-    from oracle import rssm as O          # the one other place bench.py may execute oracle/: the reference arm
     from dreamer_b200 import synthetic as W
-    cfg, sd, B, H, desc = make_problem(args.workload)
-    Bs = min(B, args.cpu_rows)
-    torch.set_num_threads(os.cpu_count() or 1)
-    z0, h0, _, n = W.rollout_inputs(cfg, Bs, H, seed=1234)
+    kind, cfg, sd, B, H, desc = make_problem(args.workload, world)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if cuda else torch.device("cpu")
+    if cuda:
+        torch.cuda.set_device(dev)
+        torch.set_float32_matmul_precision("high")               # train_car_racer.py:13
+    else:
+        torch.set_num_threads(os.cpu_count() or 1)
+    metric = {"rollout": "imagined latent states/sec", "wm": "world-model train steps/sec", "iter": "training iterations/sec"}[kind]
+    unit = {"rollout": "states/s", "wm": "steps/s", "iter": "iterations/s"}[kind]
+    rows = B if cuda else min(B, args.cpu_rows)
+    note = ""
+    if kind == "rollout":
+        d, rkind = _load_reference(cfg, sd, dev)
+        z0, h0, _, n = W.rollout_inputs(cfg, rows, H, seed=1234)
+        if d is None:                                              # oracle/_ref missing: the oracle's port with the stock sampler
+            from oracle import rssm as O
+            fn = lambda: O.dream_episodes(sd, z0, h0, None, n)
+        else:
+            d.horizon = H
+            z0, h0 = z0.to(dev), h0.to(dev)
+            fn = lambda: d.dream_episodes(z0, h0)                  # Dreamer.py:143-175, unmodified, under no_grad as evaluate/rollout do
+        units = rows * H
+        sample = f"{rows} of {B} start states x horizon {H}, stock torch sampler, {'TF32 matmuls on the GPU' if cuda else 'fp32'}, no_grad"
+        ctx = torch.no_grad()
+    elif kind == "wm":
+        Bs, Ts = (B, H) if cuda else (min(B, args.cpu_wm_batch), min(H, args.cpu_wm_seq))
+        cfg_s = dict(cfg, batch_size=Bs, horizon=Ts, sequence_length=Ts)
+        d, rkind = _load_reference(cfg_s, sd, dev)
+        if d is None:
+            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref missing: run python -m oracle.make_ref in the build container")), flush=True)
+            return
+        obs, act, rew, cont, _ = (x.to(dev) for x in W.sequence_inputs(cfg_s, Bs, Ts, seed=4321))
+        fn = lambda: d.world_model.training_step(obs, act, rew, cont)     # WorldModel.py:148-202 as shipped (fp16 autocast + GradScaler)
+        units = 1.0 * (Bs * Ts) / (B * H)                           # fraction of a full-size step one sample step does
+        sample = f"batch {Bs} x seq {Ts} of the batch {B} x seq {H} step, as shipped (fp16 autocast{'' if cuda else ': pathologically slow backward on CPU, SURVEY 8a a9'}); value scaled by the sample's share of (b, t) pairs"
+        ctx = torch.enable_grad()
+    else:
+        bs, sl, hz = (cfg["batch_size"], cfg["sequence_length"], cfg["horizon"]) if cuda else (args.cpu_wm_batch, 16, 8)
+        cfg_s = dict(cfg, batch_size=bs, sequence_length=sl, horizon=hz, buffer_size=2048)
+        d, rkind = _load_reference(cfg_s, sd, dev)
+        if d is None:
+            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref missing: run python -m oracle.make_ref in the build container")), flush=True)
+            return
+        _fill_reference_buffer(d, cfg_s, 512)
+
+        def fn():
+            d.train_world_model()                                   # Dreamer.py:228-242
+            d.train_Agent()                                         # Dreamer.py:264-287
+        units = 1.0 * (bs * sl) / (cfg["batch_size"] * cfg["sequence_length"])
+        sample = f"batch {bs} x seq {sl}, horizon {hz} of the batch 50 x seq 50, horizon 30 iteration, as shipped; value scaled by the sample's share of (b, t) pairs"
+        ctx = torch.enable_grad()
     times = []
-    with torch.no_grad():
+    with ctx:
         for i in range(args.warmup + args.steps):
+            if cuda:
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
-            O.dream_episodes(sd, z0, h0, None, n)
+            fn()
+            if cuda:
+                torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 times.append(dt)
     total = sum(times)
-    val = Bs * H * len(times) / total
-    sample = f"{Bs} of {B} start states x horizon {H}, {len(times)} timed rollouts, stock torch sampler, fp32, no_grad"
-    line = dict(impl="reference", metric="imagined latent states/sec", value=val, unit="states/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", config=dict(workload=desc, l2="n/a (CPU)"),
-                cpu_baseline=dict(value=val, unit="states/s", cores=torch.get_num_threads(), kind="port", sample=sample),
-                e2e=dict(value=val, unit="states/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    val = units * len(times) / total
+    cores = torch.get_num_threads()
+    line = dict(impl="reference-cuda" if cuda else "reference", metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="strong" if args.workload == "c4" else "weak",
+                vs_baseline=None, dtype="tf32" if cuda else "f32", data="synthetic", config=dict(workload=desc, l2="n/a"),
+                cpu_baseline=None if cuda else dict(value=val, unit=unit, cores=cores, kind=rkind, sample=sample),
+                sample=sample, reference_kind=rkind,
+                e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(args, cfg, sd, B, H):
-    from oracle import rssm as O          # cpu_baseline leg: the oracle port timed as the reference's CPU path
+def cpu_baseline(args, kind, cfg, sd, B, H):
+    """The reference (unmodified, oracle/_ref; the oracle's port if that copy is missing) on this box's host cores, bounded sample."""
     from dreamer_b200 import synthetic as W
-    Bs = min(B, args.cpu_rows)
     torch.set_num_threads(os.cpu_count() or 1)
+    if kind != "rollout":
+        Bs, Ts = min(B, args.cpu_wm_batch), min(H, args.cpu_wm_seq)
+        cfg_s = dict(cfg, batch_size=Bs, horizon=Ts, sequence_length=Ts)
+        d, rkind = _load_reference(cfg_s, sd, "cpu")
+        if d is None:
+            return None
+        obs, act, rew, cont, _ = W.sequence_inputs(cfg_s, Bs, Ts, seed=4321)
+        times = []
+        for i in range(1 + max(1, args.cpu_reps // 2)):
+            t0 = time.perf_counter()
+            d.world_model.training_step(obs, act, rew, cont)
+            if i:
+                times.append(time.perf_counter() - t0)
+        share = (Bs * Ts) / (B * H)
+        return dict(value=share / statistics.median(times), unit="steps/s", cores=torch.get_num_threads(), kind=rkind,
+                    sample=f"WorldModel.training_step as shipped (fp16 autocast) at batch {Bs} x seq {Ts}, scaled by its share of the batch {B} x seq {H} step's (b, t) pairs")
+    Bs = min(B, args.cpu_rows)
     z0, h0, _, n = W.rollout_inputs(cfg, Bs, H, seed=1234)
+    d, rkind = _load_reference(cfg, sd, "cpu")
+    if d is None:
+        from oracle import rssm as O
+        fn = lambda: O.dream_episodes(sd, z0, h0, None, n)
+    else:
+        d.horizon = H
+        fn = lambda: d.dream_episodes(z0, h0)
     times = []
     with torch.no_grad():
         for i in range(1 + args.cpu_reps):
             t0 = time.perf_counter()
-            O.dream_episodes(sd, z0, h0, None, n)
+            fn()
             if i:
                 times.append(time.perf_counter() - t0)
-    val = Bs * H / statistics.median(times)
-    return dict(value=val, unit="states/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{Bs} of {B} start states x horizon {H}, median of {len(times)} rollouts after 1 warm-up, stock torch sampler, fp32, no_grad")
+    return dict(value=Bs * H / statistics.median(times), unit="states/s", cores=torch.get_num_threads(), kind=rkind,
+                sample=f"{Bs} of {B} start states x horizon {H}, median of {len(times)} rollouts after 1 warm-up, Dreamer.dream_episodes unmodified, fp32, no_grad")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------------
+class Harness:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args, self.dist = args, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed + K timed calls, L2 flushed (untimed) before each, CUDA events, max over ranks -> total ms."""
+        for _ in range(warmup):
+            self.flush.zero_(); fn()
+        self.barrier()
+        evs = []
+        for _ in range(steps):
+            self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        self.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def finish(self, holders=()):
+        if self.world > 1:
+            import gc
+            for h in holders:                       # captured graphs hold NCCL work: release them before the process group
+                h.__dict__.pop("_graphs", None)
+            gc.collect()
+            self.barrier()
+            self.dist.destroy_process_group()
+
+
+def bench_rollout(hs, args, cfg, sd, B, H, desc):
+    import ctypes as C
+    from dreamer_b200 import _lib as L, ops, synthetic as W
+    from dreamer_b200.rollout import dream_episodes_host
+    lib = L.load()
+    dev, world, rank = hs.dev, hs.world, hs.rank
+    seed = 1234 + (rank if args.workload != "c4" else 0)
+    z0, h0, u, n = W.rollout_inputs(cfg, B * (world if args.workload == "c4" else 1), H, seed=seed)
+    if args.workload == "c4":                                            # this rank's shard of the global batch
+        sl = slice(rank * B, (rank + 1) * B)
+        z0, h0, u, n = z0[sl], h0[sl], u[:, sl].contiguous(), n[:, sl].contiguous()
+    model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in sd.items()})
+    ro = ops.Rollout(model, B, H)
+    z0d, h0d, ud, nd = (t.to(dev) for t in (z0, h0, u, n))
+    info = ro.info()
+    launches0 = lib.drm_launch_count()
+    ro.run(z0d, h0d, ud, nd, want_idx=False)
+    launches_per_rollout = lib.drm_launch_count() - launches0
+    step = lambda: ro.run_graphed(z0d, h0d, ud, nd, want_idx=False)
+    sampler = ClockSampler(hs.local)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    sampler.start()
+    total_ms = hs.timed(step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    states = B * H * world
+    value = states * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public host-buffer call: start states from pinned host memory (the latent as its 32 class
+    # indices per state -- it is a one-hot -- and h0 as fp32), rewards / continues read back into pinned host memory
+    z0_idx = z0.reshape(B, -1, 32).argmax(-1).to(torch.uint8).contiguous().pin_memory()
+    h0_pin = h0.contiguous().pin_memory()
+    h2d = z0_idx.numel() + h0_pin.numel() * 4
+    res = {}
+
+    def e2e_step():
+        out = dream_episodes_host(ro, z0_idx, h0_pin)
+        res["d2h"] = sum(t.numel() * t.element_size() for t in out["host"])
+    e2e_ms = hs.timed(e2e_step, args.steps, args.warmup)
+    e2e_val = states * args.steps / (e2e_ms * 1e-3)
+
+    # ---- the dominant kernel, timed live with CUDA events on its stream (the library brackets it while profiling is on) ----
+    fl = flops_per_state(cfg)
+    peaks = measured_peaks()
+    lib.drm_profile_enable(1)
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        hs.flush.zero_(); ro.run(z0d, h0d, ud, nd, want_idx=False)
+    torch.cuda.synchronize()
+    lib.drm_profile_enable(0)
+    names = ["gru", "prior_l1", "prior_l2", "prior_cat", "heads_l1", "heads_l2", "heads_out", "other", "rollout_persist"]
+    stages = {}
+    for i, nm in enumerate(names):
+        ms, cnt = C.c_double(), C.c_int64()
+        lib.drm_profile_read(i, C.byref(ms), C.byref(cnt))
+        if cnt.value:
+            stages[nm] = dict(ms_per_step=ms.value / prof_steps, launches_per_step=cnt.value / prof_steps, us_per_launch=1e3 * ms.value / cnt.value)
+    whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12   # per GPU (B is per rank)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ("_persist" if info["persistent"] else ""))
+        traffic = tj and tj["dram_bytes_per_launch"]        # dram__bytes_read + write of one launch, ncu --set full (profiles/)
+    except Exception:
+        pass
+    if info["persistent"]:
+        k_us = stages["rollout_persist"]["us_per_launch"]
+        k_tf = fl["total"] * B * H / (k_us * 1e-6) / 1e12
+        roofline = dict(bound="tensor", kernel="rollout_persist_kernel (whole horizon: GRU + prior + sample + actor + reward/continue heads, tcgen05)",
+                        achieved=k_tf, peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=k_tf / peaks["bf16_sustained"], traffic=traffic,
+                        peak_source=peaks["source"] + " bf16 sustained (the kernel spans the whole step)",
+                        flops_per_launch=fl["total"] * B * H, us_per_launch=k_us, share_of_step=(k_us * 1e-3) / (total_ms / args.steps),
+                        gru_flops_share=fl["gru"] / fl["total"],
+                        note="latency-bound by construction: 15 steps x (6 dependent layers of one m-tile's MLP chain + the GRU epilogue); "
+                             "per-tile timeline in profiles/persist_trace_r2.txt",
+                        ctas=info["ctas"], gru_tile=info["gru_tile"])
+    else:
+        gru_us = stages["gru"]["us_per_launch"]
+        gru_tf = fl["gru"] * B / (gru_us * 1e-6) / 1e12
+        share = stages["gru"]["ms_per_step"] / sum(v["ms_per_step"] for v in stages.values())
+        roofline = dict(bound="tensor", kernel="gru_pair_kernel / fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)", achieved=gru_tf, peak=peaks["bf16_burst"],
+                        unit="TFLOP/s", frac=gru_tf / peaks["bf16_burst"], traffic=traffic, peak_source=peaks["source"] + " bf16 burst",
+                        share_of_step=share, share_note="share of the eager per-stage event times (PDL overlap is off while profiling)",
+                        flops_per_launch=fl["gru"] * B, us_per_launch=gru_us,
+                        whole_rollout=dict(achieved=whole_tf, peak=peaks["bf16_sustained"], frac=whole_tf / peaks["bf16_sustained"]), stages=stages)
+    line = dict(metric="imagined latent states/sec", value=value, unit="states/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong" if args.workload == "c4" else "weak", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload=desc, start_states_per_gpu=B, horizon=H, l2="flushed (256 MiB write) between timed iterations",
+                            launch=("one CUDA graph per rollout: flag reset + latent zero-fill + 2 pack kernels + ONE persistent kernel for the whole horizon"
+                                    if info["persistent"] else "one CUDA graph replay per rollout (7 launches per imagined step)"),
+                            parallelism=f"start states sharded over {world} rank(s), no data-path collective"),
+                e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
+                gpu_launches=int(launches_per_rollout * args.steps), clocks=clocks, roofline=roofline,
+                whole_rollout=dict(achieved_tflops=whole_tf, frac_of_bf16_sustained=whole_tf / peaks["bf16_sustained"], flops_per_state=fl["total"]))
+    return line, [ro]
+
+
+def bench_wm(hs, args, cfg, sd, B, T, desc):
+    """WorldModel.training_step (WorldModel.py:148-202): kernel forward + hand-scheduled BPTT + fused clip/AdamW, one CUDA graph."""
+    from dreamer_b200 import _lib as L, synthetic as W
+    lib = L.load()
+    dev, world, rank = hs.dev, hs.world, hs.rank
+    wm, _ = W.build_learners(cfg, sd, dev)
+    obs, act, rew, cont, uu = (x.to(dev) for x in W.sequence_inputs(cfg, B, T, seed=4321 + rank))
+    launches0 = lib.drm_launch_count()
+    wm.training_step(obs, act, rew, cont, uniforms=uu)
+    launches_per_step = lib.drm_launch_count() - launches0
+    wm.enable_cuda_graphs(warmup=2)
+    step = lambda: wm.training_step(obs, act, rew, cont, uniforms=uu)
+    sampler = ClockSampler(hs.local)
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    sampler.start()
+    total_ms = hs.timed(step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    value = args.steps / (total_ms * 1e-3)
+    # end to end: u8 frames + actions / rewards / continues from pinned host memory, the loss read back
+    obs_u8 = obs.to(torch.uint8).cpu().pin_memory()
+    host = [t.cpu().pin_memory() for t in (act, rew, cont)]
+    h2d = obs_u8.numel() + sum(t.numel() * 4 for t in host)
+    st_obs = torch.empty_like(obs_u8, device=dev)
+    st = [torch.empty_like(t, device=dev) for t in host]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        st_obs.copy_(obs_u8, non_blocking=True)
+        for d_, h_ in zip(st, host):
+            d_.copy_(h_, non_blocking=True)
+        loss = wm.training_step(st_obs.float(), st[0], st[1], st[2], uniforms=uu)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_ms = hs.timed(e2e_step, args.steps, args.warmup)
+    peaks = measured_peaks()
+    flops = WM_FLOPS_PER_BT * B * T
+    tf = flops * args.steps / (total_ms * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="whole training step (kernel forward + BPTT + optimiser) as one CUDA graph", achieved=tf,
+                    peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=tf / peaks["bf16_sustained"], traffic=None,
+                    peak_source=peaks["source"] + " bf16 sustained", flops_per_launch=flops,
+                    note="119.7 MFLOP forward per (b, t) x 3 (SURVEY.md section 8d); the backward's GEMMs / convolutions are library calls (DESIGN.md section 6)")
+    line = dict(metric="world-model train steps/sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=desc, batch_per_gpu=B, seq=T, global_batch=B * world, l2="flushed (256 MiB write) between timed iterations",
+                            launch="one CUDA graph replay per step (captured after 2 eager steps)",
+                            parallelism=f"data parallel over {world} rank(s): flat 31 MB gradient bucket + packed loss scalars all-reduced over NCCL"),
+                samples_per_s=value * B * world,
+                e2e=dict(value=args.steps / (e2e_ms * 1e-3), unit="steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
+                gpu_launches=int(launches_per_step * args.steps), gpu_launches_note="kernels of this library per step (the torch autograd tail adds library kernels)",
+                clocks=clocks, roofline=roofline)
+    return line, [wm]
+
+
+def bench_iteration(hs, args, cfg, desc):
+    """One training iteration of Dreamer.train (Dreamer.py:340-341): train_world_model() + train_Agent() on a synthetic replay ring."""
+    import numpy as np
+    from dreamer_b200 import _lib as L
+    from dreamer_b200.hotpath import HotPath
+    lib = L.load()
+    dev, world, rank = hs.dev, hs.world, hs.rank
+    cfg_it = dict(cfg, buffer_size=8192)
+    hp = HotPath(cfg_it, dev)
+    rng = np.random.default_rng(1 + rank)
+    n_it = 4096
+    hp.buffer.add_batch(rng.integers(0, 256, size=(n_it, 3, 64, 64)).astype(np.uint8), rng.uniform(-1, 1, (n_it, 3)).astype(np.float32),
+                        rng.standard_normal(n_it).astype(np.float32), (rng.random(n_it) > 0.02).astype(np.float32))
+
+    def iteration():
+        hp.train_world_model()
+        hp.train_Agent()
+    launches0 = lib.drm_launch_count()
+    iteration()
+    launches_per_it = lib.drm_launch_count() - launches0
+    iteration()
+    hp.world_model.enable_cuda_graphs(warmup=1)
+    hp.agent.enable_cuda_graphs(warmup=1)
+    hp.cuda_graphs = True
+    sampler = ClockSampler(hs.local)
+    for _ in range(3):
+        iteration()
+    torch.cuda.synchronize()
+    sampler.start()
+    total_ms = hs.timed(iteration, args.steps, args.warmup)
+    clocks = sampler.stop()
+    value = args.steps / (total_ms * 1e-3)
+    # the collective inside it, timed alone: the world model's flat gradient bucket (all-reduce SUM)
+    coll = None
+    if world > 1:
+        n_wm = sum(p.numel() for p in hp.world_model.parameters())
+        buf = torch.zeros(n_wm, device=dev)
+        for _ in range(5):
+            hs.dist.all_reduce(buf)
+        hs.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        a.record()
+        for _ in range(reps):
+            hs.dist.all_reduce(buf)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        hs.dist.all_reduce(t, op=hs.dist.ReduceOp.MAX)
+        ms = float(t.item())
+        by = n_wm * 4
+        coll = dict(bucket_bytes=by, all_reduce_ms=ms, bus_gbs=2 * (world - 1) / world * by / (ms * 1e-3) / 1e9,
+                    per_iteration=f"{cfg['WM_epochs']} x this bucket + {cfg['AC_epochs']} x (1.47 MB actor + 1.67 MB critic) + packed scalars",
+                    share_of_iteration=cfg["WM_epochs"] * ms / (total_ms / args.steps))
+    line = dict(metric="training iterations/sec", value=value, unit="iterations/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=desc, l2="flushed (256 MiB write) between timed iterations",
+                            launch="training steps and rollouts replayed as CUDA graphs", parallelism=f"data parallel over {world} rank(s); environment stepping excluded"),
+                e2e=dict(value=value, unit="iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                         note="the replay ring is HBM-resident (Buffer mirror): an iteration moves no host data"),
+                gpu_launches=int(launches_per_it * args.steps), clocks=clocks, collective=coll,
+                roofline=dict(bound="tensor", kernel="whole iteration", achieved=None, peak=measured_peaks()["bf16_sustained"], unit="TFLOP/s", frac=None, traffic=None))
+    return line, [hp.world_model, hp.agent]
 
 
 def secondary_metrics(dev, peaks, flush):
-    """HBM-bound kernels against the measured HBM peak and the world-model (config 3) rates -- extra keys, N = 1 only."""
+    """HBM-bound kernels against the measured HBM peak and the large-batch rollout points -- extra keys, N = 1 only."""
+    import ctypes as C
     import numpy as np
-    from dreamer_b200 import ops
-    from dreamer_b200 import synthetic as W
+    from dreamer_b200 import _lib as L, ops, synthetic as W
+    lib = L.load()
     out = {}
 
     def dev_time(fn, reps=10, warm=3):
@@ -175,23 +551,15 @@ def secondary_metrics(dev, peaks, flush):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts) * 1e-3
 
-    # replay gather (Buffer.sample_sequences, Buffer.py:49-61) at the reference's batch 50 x sequence 50
-    cap, B, L = 20000, 50, 50
+    cap, B, Ls = 20000, 1024, 50
     ring = [torch.randint(0, 256, (cap, 3, 64, 64), dtype=torch.uint8, device=dev), torch.rand(cap, 3, device=dev),
             torch.rand(cap, 1, device=dev), torch.ones(cap, 1, device=dev)]
-    starts = torch.from_numpy(np.random.RandomState(0).randint(0, cap - L, size=B))
-    t = dev_time(lambda: ops.replay_gather(*ring, starts, L))
-    by = 61480 * B * L
-    out["replay_gather"] = dict(workload="50 x 50 windows of 64x64x3 u8 frames -> fp32", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9,
-                                peak_gbs=peaks["hbm"], frac=by / t / 1e9 / peaks["hbm"], note="153.7 MB per launch: short kernel, launch ramp included")
-    B2 = 1024
-    starts2 = torch.from_numpy(np.random.RandomState(1).randint(0, cap - L, size=B2))
-    t = dev_time(lambda: ops.replay_gather(*ring, starts2, L), reps=5)
-    by = 61480 * B2 * L
-    out["replay_gather_large"] = dict(workload="1024 x 50 windows", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"],
-                                      frac=by / t / 1e9 / peaks["hbm"])
+    starts = torch.from_numpy(np.random.RandomState(1).randint(0, cap - Ls, size=B))
+    t = dev_time(lambda: ops.replay_gather(*ring, starts, Ls), reps=5)
+    by = 61480 * B * Ls
+    out["replay_gather"] = dict(workload="1024 x 50 windows of 64x64x3 u8 frames -> fp32", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9,
+                                peak_gbs=peaks["hbm"], frac=by / t / 1e9 / peaks["hbm"])
     del ring
-    # stand-alone categorical (softmax / unimix / sample / one-hot / ST), 4M rows of 32 classes
     n = 1 << 22
     lg = torch.randn(n, 32, device=dev); u = torch.rand(n, device=dev)
     t = dev_time(lambda: ops.categorical32(lg, u), reps=5)
@@ -199,107 +567,26 @@ def secondary_metrics(dev, peaks, flush):
     out["categorical32"] = dict(workload="4 Mi rows x 32 classes", bytes_per_launch=by, us=t * 1e6, achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"],
                                 frac=by / t / 1e9 / peaks["hbm"])
     del lg, u
-    # world model, BASELINE configs[2]: batch 16 x seq 64 of 64x64x3 frames: loss forward on the kernels, and the full training step
-    cfg = dict(W.REF_CONFIG, horizon=64, sequence_length=64, batch_size=16)
-    wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=0), dev)
-    obs, act, rew, cont, uu = (x.to(dev) for x in W.sequence_inputs(cfg, 16, 64, seed=4321))
-    t_f = dev_time(lambda: wm.loss_forward(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
-    t_s = dev_time(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu), reps=5, warm=2)
-    wm.enable_cuda_graphs(warmup=1)          # the same step replayed as ONE CUDA graph (dreamer_b200/graphs.py)
-    t_g = dev_time(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu), reps=10, warm=3)
-    out["world_model_c3"] = dict(workload="batch 16 x seq 64, 64x64x3 frames (BASELINE configs[2])", loss_forward_steps_per_s=1.0 / t_f,
-                                 loss_forward_ms=t_f * 1e3, train_steps_per_s=1.0 / t_g, train_step_ms=t_g * 1e3,
-                                 eager_train_step_ms=t_s * 1e3,
-                                 note="training step = kernel forward + hand-scheduled BPTT (bptt.py) + fused clip/AdamW on the flat bucket, "
-                                      "replayed as one CUDA graph (DESIGN.md section 6); eager_train_step_ms is the same step issued launch by launch")
-    del wm
-    # actor-critic update on a config-2 rollout (1024 x 15): Agent.train_step, eager and as one CUDA graph
+    # the launch-per-stage chain on the default workload, for comparison with the persistent kernel
     cfg2 = dict(W.REF_CONFIG, horizon=15)
-    wm2, ag = W.build_learners(cfg2, W.make_state_dict(cfg2, seed=0), dev)
-    ag.attach_world_model(wm2)               # actor gradient through the imagined states (bptt.actor_backward), as the reference's autograd
-    zz = torch.nn.functional.one_hot(torch.randint(0, 32, (1024, 16, 32), device=dev), 32).float()
-    hh = torch.tanh(torch.randn(1024, 16, cfg2["hidden_state_dims"], device=dev))
-    rr, cc = torch.randn(1024, 15, 1, device=dev), torch.ones(1024, 15, 1, device=dev)
-    mu_, sg_ = torch.randn(1024, 15, 3, device=dev) * 0.3, torch.rand(1024, 15, 3, device=dev) * 0.5 + 0.1
-    aa = torch.tanh(mu_ + sg_ * torch.randn_like(mu_))
-    t_a = dev_time(lambda: ag.train_step(zz, hh, rr, cc, aa, mu_, sg_), reps=5, warm=2)
-    ag.enable_cuda_graphs(warmup=1)
-    t_ag = dev_time(lambda: ag.train_step(zz, hh, rr, cc, aa, mu_, sg_), reps=10, warm=3)
-    out["agent_step_c2"] = dict(workload="Agent.train_step on 1024 x 15 imagined states", train_step_ms=t_ag * 1e3, eager_train_step_ms=t_a * 1e3,
-                                states_per_s=1024 * 15 / t_ag)
-    del ag, wm2, zz, hh
-    # fused optimiser tail on a flat bucket (drm_adamw_step: norm pass + update pass), 64 Mi parameters
-    from dreamer_b200 import _lib as L_
-    lib_ = L_.load()
-    n_p = 1 << 26
-    bufs = [torch.randn(n_p, device=dev) * 0.01 for _ in range(2)] + [torch.zeros(n_p, device=dev) for _ in range(2)]
-    st_ = torch.zeros(8, device=dev)
-    scr_ = torch.zeros(int(lib_.drm_adamw_scratch_bytes()) // 8, dtype=torch.float64, device=dev)
-    t = dev_time(lambda: L_.check(lib_.drm_adamw_step(L_.ptr(bufs[0]), L_.ptr(bufs[1]), L_.ptr(bufs[2]), L_.ptr(bufs[3]), n_p, L_.ptr(st_), L_.ptr(scr_),
-                                                       1e-4, 0.9, 0.999, 1e-8, 1e-6, 100.0, None, 0.0, 0, L_.stream()), "adamw"), reps=5)
-    by = n_p * (4 + 16 + 12)
-    out["adamw_flat"] = dict(workload="clip + AdamW on a flat bucket of 64 Mi fp32 parameters (3 launches)", bytes_per_launch=by, us=t * 1e6,
-                             achieved_gbs=by / t / 1e9, peak_gbs=peaks["hbm"], frac=by / t / 1e9 / peaks["hbm"],
-                             note="algorithmic bytes: 4 B/param norm pass + 16 B read + 12 B written in the update pass")
-    del bufs
-    # B = 1 acting path (Dreamer.rollout_policy inner loop): record -> observe_step -> act per environment step, host frame in, action out
-    import numpy as np
-    import time as _time
-    from dreamer_b200.acting import ActingPath
-    from dreamer_b200.modules import Buffer
-    cfg1 = dict(W.REF_CONFIG)
-    wm1, ag1 = W.build_learners(cfg1, W.make_state_dict(cfg1, seed=0), dev)
-    ring1 = Buffer(4096, 50, cfg1["action_dims"], tuple(cfg1["observation_dims"]), device=dev)
-    frames = np.random.default_rng(0).integers(0, 256, size=(64, 3, 64, 64)).astype(np.uint8)
-    rates = {}
-    for mode, use_graphs in (("graph", True), ("eager", False)):
-        ap = ActingPath(wm1, ag1, ring1, use_graphs=use_graphs)
-        ap.reset(frames[0]); ap.act()
-        for i in range(8):
-            ap.step(frames[i % 64], 0.1, 1.0)
-        torch.cuda.synchronize()
-        n_steps = 300
-        t0 = _time.perf_counter()
-        for i in range(n_steps):
-            ap.step(frames[i % 64], 0.1, 1.0)
-        torch.cuda.synchronize()
-        rates[mode] = n_steps / (_time.perf_counter() - t0)
-    out["acting_b1"] = dict(workload="one environment: pinned u8 frame in -> ring insert + observe_step + act -> action out, per step",
-                            env_steps_per_s=rates["graph"], us_per_step=1e6 / rates["graph"], eager_env_steps_per_s=rates["eager"],
-                            note="wall clock over 300 steps including the host read-back every step (the environment needs the action)")
-    del wm1, ag1, ring1
-    # one whole training iteration at the reference's own configuration (car_racer_config.yaml: batch 50 x sequence 50, horizon 30,
-    # WM_epochs = AC_epochs = 2): replay sample -> world-model step (x2), replay sample -> warm start -> imagination -> agent step (x2)
-    from dreamer_b200.hotpath import HotPath
-    cfg_it = dict(W.REF_CONFIG, buffer_size=8192)
-    hp_it = HotPath(cfg_it, dev)
-    rng_it = np.random.default_rng(1)
-    n_it = 4096
-    hp_it.buffer.add_batch(rng_it.integers(0, 256, size=(n_it, 3, 64, 64)).astype(np.uint8), rng_it.uniform(-1, 1, (n_it, 3)).astype(np.float32),
-                           rng_it.standard_normal(n_it).astype(np.float32), (rng_it.random(n_it) > 0.02).astype(np.float32))
-
-    def iteration():
-        hp_it.train_world_model()
-        hp_it.train_Agent()
-    t_e = dev_time(iteration, reps=3, warm=2)
-    hp_it.world_model.enable_cuda_graphs(warmup=1)
-    hp_it.agent.enable_cuda_graphs(warmup=1)
-    t_gi = dev_time(iteration, reps=5, warm=3)
-    out["training_iteration_ref"] = dict(workload="car_racer_config.yaml: batch 50 x seq 50, horizon 30, 2 world-model + 2 actor-critic epochs per iteration "
-                                                  "(Dreamer.py:228-287), synthetic replay", ms_per_iteration=t_gi * 1e3, iterations_per_s=1.0 / t_gi,
-                                         eager_ms_per_iteration=t_e * 1e3,
-                                         note="environment stepping excluded; training steps replayed as CUDA graphs (eager = launch by launch)")
-    del hp_it
-    # the north star's large-batch points: 16 384 start states x horizon 15 on this one GPU (GRU stage vs the measured bf16 peak)
-    import ctypes as C
-    from dreamer_b200 import _lib as L
-    lib = L.load()
+    model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in W.make_state_dict(cfg2, seed=0, actor_mu_zero=True).items()})
+    ro = ops.Rollout(model, 1024, 15)
+    z0, h0, uu, nn_ = (x.to(dev) for x in W.rollout_inputs(cfg2, 1024, 15, seed=1234))
+    lib.drm_set_option(b"persist", 0)
+    try:
+        t_chain = dev_time(lambda: ro.run_graphed(z0, h0, uu, nn_, want_idx=False), reps=10, warm=4)
+    finally:
+        lib.drm_set_option(b"persist", 1)
+    out["rollout_c2_launch_per_stage"] = dict(workload="1024 x 15 with option persist = 0 (7 launches per imagined step, one graph replay)",
+                                               ms_per_rollout=t_chain * 1e3, states_per_s=1024 * 15 / t_chain)
+    del ro, model
+    # the north star's large-batch points on this one GPU (GRU stage vs the measured bf16 burst peak)
     for wl in ("c2x16", "c4"):
-        Bn, Hn, over, desc = WORKLOADS[wl]
+        _, Bn, Hn, over, desc = WORKLOADS[wl]
         cfgn = dict(W.REF_CONFIG, horizon=Hn, **over)
         model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in W.make_state_dict(cfgn, seed=0, actor_mu_zero=True).items()})
         ro = ops.Rollout(model, Bn, Hn)
-        z0, h0, uu, nn_ = (t.to(dev) for t in W.rollout_inputs(cfgn, Bn, Hn, seed=1234))
+        z0, h0, uu, nn_ = (x.to(dev) for x in W.rollout_inputs(cfgn, Bn, Hn, seed=1234))
         t = dev_time(lambda: ro.run(z0, h0, uu, nn_, want_idx=False), reps=3, warm=2)
         lib.drm_profile_enable(1)
         ro.run(z0, h0, uu, nn_, want_idx=False)
@@ -307,7 +594,7 @@ def secondary_metrics(dev, peaks, flush):
         lib.drm_profile_enable(0)
         ms, cnt = C.c_double(), C.c_int64()
         lib.drm_profile_read(0, C.byref(ms), C.byref(cnt))
-        for i in range(1, 8):
+        for i in range(1, 9):
             lib.drm_profile_read(i, C.byref(C.c_double()), C.byref(C.c_int64()))
         fl = flops_per_state(cfgn)
         gru_tf = fl["gru"] * Bn / (ms.value / cnt.value * 1e-3) / 1e12
@@ -326,156 +613,44 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--cpu-rows", type=int, default=1024, help="start states in the CPU sample")
     ap.add_argument("--cpu-reps", type=int, default=5)
+    ap.add_argument("--cpu-wm-batch", type=int, default=2, help="batch of the CPU world-model sample")
+    ap.add_argument("--cpu-wm-seq", type=int, default=8, help="sequence length of the CPU world-model sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the auxiliary HBM-kernel / world-model measurements")
+    ap.add_argument("--secondary", action="store_true", help="add the auxiliary HBM-kernel / large-batch measurements (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
+    if args.impl != "ours":
+        run_reference(args, rank, world, cuda=args.impl == "reference-cuda")
         return
 
-    import torch.distributed as dist
     from dreamer_b200 import _lib as L
-    from dreamer_b200 import ops
-    from dreamer_b200.rollout import dream_episodes_host
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    hs = Harness(args)
     L.check(L.load().drm_device_check(), "device_check")
-
-    cfg, sd, B, H, desc = make_problem(args.workload)
-    from dreamer_b200 import synthetic as W
-    z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=1234 + rank)      # every rank owns different start states
-    model = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in sd.items()})
-    ro = ops.Rollout(model, B, H)
-    z0d, h0d, ud, nd = (t.to(dev) for t in (z0, h0, u, n))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            flush.zero_(); fn()
-        barrier()
-        evs = []
-        for _ in range(steps):
-            flush.zero_()                                              # L2 flush between timed iterations (untimed)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            evs.append((a, b))
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
-        return float(t.item())
-
-    lib = L.load()
-    # ---- device-resident throughput ------------------------------------------------------------
-    # the rollout's launch sequence is replayed as one CUDA graph (Rollout.run_graphed: two eager calls, then capture); the kernels
-    # launched per rollout are counted on an eager call, since replays do not pass through the launch counter
-    launches0 = lib.drm_launch_count()
-    ro.run(z0d, h0d, ud, nd, want_idx=False)
-    launches_per_rollout = lib.drm_launch_count() - launches0
-    step = lambda: ro.run_graphed(z0d, h0d, ud, nd, want_idx=False)
-    sampler = ClockSampler(local)     # every rank samples its own GPU; rank 0's record is reported
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    sampler.start()
-    total_ms = timed(step, args.steps, args.warmup)
-    clocks = sampler.stop()
-    states = B * H * world
-    value = states * args.steps / (total_ms * 1e-3)
-    gpu_launches = launches_per_rollout * args.steps
-
-    # ---- end to end through the public host-buffer API -------------------------------------------
-    # the public call takes the start states (host buffers); the per-step randomness is drawn on the device inside the call,
-    # as Dreamer.dream_episodes does
-    pin = [t.contiguous().pin_memory() for t in (z0, h0)]
-    h2d = sum(t.numel() * t.element_size() for t in pin)
-    res = {}
-
-    def e2e_step():
-        out = dream_episodes_host(ro, *pin)
-        res["d2h"] = sum(t.numel() * t.element_size() for t in out["host"])
-    e2e_ms = timed(e2e_step, args.steps, args.warmup)
-    e2e_val = states * args.steps / (e2e_ms * 1e-3)
-
-    # ---- per-stage device times (separate profiled pass over the same workload) -----------------
-    import ctypes as C
-    lib.drm_profile_enable(1)
-    prof_steps = max(3, min(args.steps, 10))
-    for _ in range(prof_steps):
-        flush.zero_(); ro.run(z0d, h0d, ud, nd, want_idx=False)      # eager: the stage events are recorded by the launch code
-    torch.cuda.synchronize()
-    lib.drm_profile_enable(0)
-    names = ["gru", "prior_l1", "prior_l2", "prior_cat", "heads_l1", "heads_l2", "heads_out", "other"]
-    stages = {}
-    for i, nm in enumerate(names):
-        ms, cnt = C.c_double(), C.c_int64()
-        lib.drm_profile_read(i, C.byref(ms), C.byref(cnt))
-        if cnt.value:
-            stages[nm] = dict(ms_per_step=ms.value / prof_steps, launches_per_step=cnt.value / prof_steps, us_per_launch=1e3 * ms.value / cnt.value)
-    fl = flops_per_state(cfg)
-    peaks = measured_peaks()
-    gru_us = stages["gru"]["us_per_launch"]
-    gru_tf = fl["gru"] * B / (gru_us * 1e-6) / 1e12
-    whole_tf = fl["total"] * B * H * args.steps / (total_ms * 1e-3) / 1e12   # per GPU (B is per rank)
-    traffic, gru_kernel = None, "fused_gemm_kernel<EpiGru> (GRU gates, tcgen05)"
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        traffic = tj and tj["dram_bytes_per_launch"]        # dram__bytes_read + write of one launch, ncu --set full (profiles/)
-        gru_kernel = (tj and tj.get("kernel")) or gru_kernel   # the GRU kernel the launch code picks at this grid size
-    except Exception:
-        pass
-    share = stages["gru"]["ms_per_step"] / sum(v["ms_per_step"] for v in stages.values())
-    roofline = dict(bound="tensor", kernel=gru_kernel, achieved=gru_tf, peak=peaks["bf16_burst"],
-                    unit="TFLOP/s", frac=gru_tf / peaks["bf16_burst"], traffic=traffic, peak_source=peaks["source"] + " bf16 burst",
-                    share_of_step=share,
-                    flops_per_launch=fl["gru"] * B, us_per_launch=gru_us,
-                    whole_rollout=dict(achieved=whole_tf, peak=peaks["bf16_sustained"], frac=whole_tf / peaks["bf16_sustained"],
-                                       flops_per_state=fl["total"]),
-                    stages=stages)
-
-    line = dict(metric="imagined latent states/sec", value=value, unit="states/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                data="synthetic", config=dict(workload=desc, start_states_per_gpu=B, horizon=H, l2="flushed (256 MiB write) between timed iterations", launch="one CUDA graph replay per rollout (captured after 2 eager calls)",
-                                              parallelism=f"start states sharded over {world} rank(s), no data-path collective"),
-                e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
-                gpu_launches=int(gpu_launches), clocks=clocks, roofline=roofline)
-    if rank == 0 and world == 1 and not args.no_secondary:
+    kind, cfg, sd, B, H, desc = make_problem(args.workload, world)
+    if kind == "rollout":
+        line, holders = bench_rollout(hs, args, cfg, sd, B, H, desc)
+    elif kind == "wm":
+        line, holders = bench_wm(hs, args, cfg, sd, B, H, desc)
+    else:
+        line, holders = bench_iteration(hs, args, cfg, desc)
+    if rank == 0 and world == 1 and args.secondary:
         try:
-            line["secondary"] = secondary_metrics(dev, peaks, flush)
+            line["secondary"] = secondary_metrics(hs.dev, measured_peaks(), hs.flush)
         except Exception as e:     # never lose the headline line to an auxiliary measurement
             line["secondary"] = dict(error=repr(e)[:200])
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, cfg, sd, B, H)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and kind != "iter":
+        line["cpu_baseline"] = cpu_baseline(args, kind, cfg, sd, B, H)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        # captured graphs are released before the process group (a live graph at NCCL teardown has hung the exit before)
-        import gc
-        ro.__dict__.pop("_graphs", None)
-        gc.collect()
-        barrier()
-        dist.destroy_process_group()
+    hs.finish(holders)
 
 
 if __name__ == "__main__":

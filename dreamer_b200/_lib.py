@@ -64,6 +64,7 @@ SIGNATURES = {
     "drm_profile_enable": (C.c_int, [C.c_int32]),
     "drm_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "drm_categorical32_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_stream]),
+    "drm_onehot32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_stream]),
     "drm_categorical32_st": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, c_stream]),
     "drm_categorical32_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, c_stream]),
     "drm_ln_silu_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, c_stream]),

@@ -43,6 +43,9 @@ class ActingPath:
         self._frame_host = torch.zeros(3, H, W, dtype=torch.uint8).pin_memory()
         self._meta_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self._action_host = torch.zeros(A, dtype=torch.float32).pin_memory()
+        self._action_in_host = torch.zeros(A, dtype=torch.float32).pin_memory()      # host -> device staging of set_action (not the read-back buffer)
+        # one event per pinned staging buffer: recorded after its asynchronous copy is enqueued, waited for before the buffer is rewritten
+        self._staged = {"frame": None, "meta": None, "action": None}
         world_model.attach_actor(agent.actor)
         if use_graphs:
             self._reset = StepGraph(self._reset_body, warmup)
@@ -87,9 +90,20 @@ class ActingPath:
         self.wm.sequence_model._pk.get()
         self.agent.actor._pk.get()
 
+    def _stage(self, which, host, dev_view, value):
+        """Write `value` into the pinned buffer `host` and enqueue its copy to the device -- after the PREVIOUS copy out of that
+        buffer has executed (the GPU may still hold a backlog, e.g. a replayed training step)."""
+        ev = self._staged[which]
+        if ev is not None:
+            ev.synchronize()
+        host.copy_(value)
+        dev_view.copy_(host, non_blocking=True)
+        if ev is None:
+            ev = self._staged[which] = torch.cuda.Event()
+        ev.record()
+
     def _upload(self, frame_u8_chw):
-        self._frame_host.copy_(torch.as_tensor(np.ascontiguousarray(frame_u8_chw), dtype=torch.uint8))
-        self.frame.copy_(self._frame_host, non_blocking=True)
+        self._stage("frame", self._frame_host, self.frame, torch.as_tensor(np.ascontiguousarray(frame_u8_chw), dtype=torch.uint8))
 
     def _download_action(self) -> np.ndarray:
         self._action_host.copy_(self.action.view(-1), non_blocking=True)
@@ -109,8 +123,7 @@ class ActingPath:
 
     def set_action(self, action):
         """Use an externally chosen action (Dreamer.rollout_policy's random_policy branch, Dreamer.py:195-198) as the last action."""
-        self._action_host.copy_(torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1)))
-        self.action.view(-1).copy_(self._action_host, non_blocking=True)
+        self._stage("action", self._action_in_host, self.action.view(-1), torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1)))
 
     def observe(self, next_frame_u8_chw, uniforms: Optional[torch.Tensor] = None):
         """observe_step on the new frame with the last action, without choosing the next one (WorldModel.py:79-82)."""
@@ -121,8 +134,7 @@ class ActingPath:
         """buffer.add_to_buffer(current frame, last action, reward, continue) without leaving the device (Dreamer.py:211-212)."""
         if self.buffer is None:
             return
-        self._meta_host[0], self._meta_host[1] = float(reward), float(continue_)
-        self.meta.copy_(self._meta_host, non_blocking=True)
+        self._stage("meta", self._meta_host, self.meta, torch.tensor([float(reward), float(continue_)], dtype=torch.float32))
         self.buffer.add_batch(self.frame[None], self.action.view(1, -1), self.meta[0:1], self.meta[1:2])
 
     def step(self, next_frame_u8_chw, reward: float, continue_: float, uniforms: Optional[torch.Tensor] = None,

@@ -1009,7 +1009,9 @@ static int rollout_persist(drm_rollout* r, const float* z0, const float* h0, con
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   persist_launch_config(cfg, attr, ps->n_cta, st);   // (co-residency of all clusters was checked against the device's capacity in persist_plan)
+  profile_begin(DRM_STAGE_ROLLOUT, st);
   DRM_CUDA(cudaLaunchKernelEx(&cfg, rollout_persist_kernel, P));
+  profile_end(DRM_STAGE_ROLLOUT, st);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

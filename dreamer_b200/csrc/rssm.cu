@@ -775,8 +775,8 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
   cudaStream_t st = (cudaStream_t)stream;
   // One persistent kernel for the whole horizon when its static schedule fits the machine (rollout_persist.cuh); the
   // launch-per-stage chain otherwise (large batches, where every stage fills the machine and is throughput bound), while the
-  // per-stage profiler / timeline probes are on, or with option "persist" = 0.
-  if (opts().persist && !profile_on() && !g_timeline && persist_eligible(r))
+  // launch-per-stage timeline probe is on, or with option "persist" = 0.
+  if (opts().persist && !g_timeline && persist_eligible(r))
     return rollout_persist(r, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
   return rollout_lane(r, 0, r->B, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
 }

@@ -658,6 +658,29 @@ extern "C" int drm_twohot_ce(const float* logits, const float* value, const floa
   return DRM_OK;
 }
 
+// one-hot expansion of sampled classes: idx [n_rows] u8 (class < 32) -> out [n_rows, 32] fp32 (one float4 per thread)
+__global__ void onehot32_kernel(const uint8_t* __restrict__ idx, float* __restrict__ out, int64_t n_rows) {
+  const int64_t total = n_rows * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 3;
+    const int c0 = (int)(i & 7) * 4, k = (int)idx[r] - c0;
+    reinterpret_cast<float4*>(out)[i] = make_float4(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f, k == 3 ? 1.f : 0.f);
+  }
+}
+
+extern "C" int drm_onehot32(const uint8_t* idx, float* out, int64_t n_rows, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(n_rows >= 0, DRM_ERR_SHAPE, "drm_onehot32: negative row count");
+  if (n_rows == 0) return DRM_OK;
+  DRM_REQUIRE(idx && out, DRM_ERR_ARG, "drm_onehot32: NULL pointer");
+  DRM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, DRM_ERR_ALIGN, "drm_onehot32: out must be 16-byte aligned");
+  int64_t blocks = (n_rows * 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  onehot32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(idx, out, n_rows);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
 extern "C" int drm_bucket_value(const float* logits, const float* buckets, float* value, int64_t N, int32_t NB, void* stream) {
   if (int rc = check_arch()) return rc;
   DRM_REQUIRE(N >= 0 && NB >= 1 && NB <= 256, DRM_ERR_SHAPE, "drm_bucket_value: NB must be in [1, 256]");

@@ -96,6 +96,9 @@ def patch_dreamer(dreamer_cls):
 
     def rollout_policy(self, env, random_policy=False):
         ap = _acting(self, False)
+        # an episode continues across training phases (Dreamer.py:340-343 trains between two calls): act with the CURRENT weights,
+        # as the reference does -- a cheap version check, the re-pack writes in place so the captured graphs pick it up
+        ap.sync_weights()
         if self.agent_obs is None:                              # first call: start an episode (Dreamer.py:184-191)
             observation, _ = env.reset(seed=self.seed)
             ap.reset(_chw(observation))
@@ -118,6 +121,7 @@ def patch_dreamer(dreamer_cls):
 
     def evaluate_agent(self, env, eval_episodes):
         ap = _acting(self, True)
+        ap.sync_weights()
         totals = []
         for _ in range(eval_episodes):
             self.seed += 1

@@ -71,6 +71,15 @@ class _Packed:
         self.versions = None
         self.ws: Dict[int, ops.Rollout] = {}
 
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(module) (snapshots, Agent's target critic) must not share native handles: the copy starts with an empty
+        cache bound to the COPIED owner and packs its own weights on first use."""
+        import copy as _copy
+        return _Packed(_copy.deepcopy(self.owner, memo), self.prefix, self.R, self.C, self.D, self.A)
+
+    def __getstate__(self):
+        return dict(owner=self.owner, prefix=self.prefix, R=self.R, C=self.C, D=self.D, A=self.A, model=None, versions=None, ws={})
+
     def sd(self):
         return {self.prefix + k: v for k, v in self.owner.state_dict(keep_vars=True).items()}
 
@@ -213,7 +222,8 @@ class Actor(nn.Module):
         torch.nn.init.zeros_(self.mu_head.weight)
         torch.nn.init.zeros_(self.mu_head.bias)
         self.action_dim = action_dim
-        self._pk = _Packed(self, "agent.actor.", latent_row_dim, latent_column_dim, hidden_state_dim, action_dim)
+        # (the reference's constructor names are swapped, Agent.py:175: `latent_column_dim` receives latent_dims[0] = the row count)
+        self._pk = _Packed(self, "agent.actor.", latent_column_dim, latent_row_dim, hidden_state_dim, action_dim)
 
     def _run(self, ht, zt, normals):
         B, S, _ = ht.shape
@@ -357,6 +367,10 @@ class _VaeEngine:
         self.versions = None
         self.obs_ws: Dict[tuple, ops.Observe] = {}
         self.roll_ws: Dict[tuple, ops.Rollout] = {}
+
+    def __deepcopy__(self, memo):
+        raise RuntimeError("_VaeEngine holds native handles bound to one WorldModel's parameters: deep-copy the WorldModel's "
+                           "state_dict into a new WorldModel instead")
 
     def refresh(self):
         sd = self.get_sd()

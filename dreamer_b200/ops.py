@@ -182,6 +182,20 @@ def twohot_ce(logits, value, buckets, apply_symlog: bool = False):
     return out
 
 
+def onehot32(idx: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """(..., ) uint8 classes < 32 -> (..., 32) fp32 one-hot (into `out` when given)."""
+    L.require_cuda(idx, "idx")
+    if idx.dtype != torch.uint8:
+        raise RuntimeError("dreamer_b200.onehot32: idx must be uint8")
+    ix = idx.contiguous()
+    if out is None:
+        out = torch.empty(tuple(ix.shape) + (32,), dtype=torch.float32, device=ix.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != ix.numel() * 32:
+        raise RuntimeError("dreamer_b200.onehot32: out must be a contiguous fp32 tensor with 32 values per class index")
+    L.check(L.load().drm_onehot32(L.ptr(ix), L.ptr(out), ix.numel(), L.stream()), "onehot32")
+    return out
+
+
 def bucket_value(logits, buckets):
     """symexp(sum(softmax(logits) * buckets)): (..., NB) -> (..., 1)."""
     L.require_cuda(logits, "logits")
@@ -223,7 +237,20 @@ def _mlp_struct(sd: Dict[str, torch.Tensor], prefix: Optional[str], keep: list, 
     return s
 
 
-class PackedRssm:
+class _NoCopy:
+    """Owners of a native handle: a copy would free the handle twice (double cudaFree / stale TMA descriptors)."""
+
+    def __copy__(self):
+        raise RuntimeError(f"{type(self).__name__} owns a native handle and cannot be copied; build a new one")
+
+    def __deepcopy__(self, memo):
+        raise RuntimeError(f"{type(self).__name__} owns a native handle and cannot be copied; build a new one")
+
+    def __reduce__(self):
+        raise RuntimeError(f"{type(self).__name__} owns a native handle and cannot be pickled")
+
+
+class PackedRssm(_NoCopy):
     """drm_rssm handle: bf16 tile-packed copies of the RSSM / head weights.
 
     ``state_dict`` uses the reference's key names (``world_model.*`` / ``agent.*``).
@@ -309,7 +336,7 @@ class PackedRssm:
             pass
 
 
-class Rollout:
+class Rollout(_NoCopy):
     """drm_rollout handle: state buffers + TMA descriptors for up to B rows and horizon H."""
 
     def __init__(self, model: PackedRssm, B: int, H: int):
@@ -447,7 +474,7 @@ def neg_sse_rows(a: torch.Tensor, b: torch.Tensor, row_dims: int = 3) -> torch.T
     return out
 
 
-class PackedVae:
+class PackedVae(_NoCopy):
     """drm_vae handle: packed Encoder / Decoder weights (reference keys world_model.encoder.*, world_model.decoder.*)."""
 
     def __init__(self, model: PackedRssm, H: int, W: int, e1: int, e2: int, d1: int, d2: int, h_enc: int, h_dec: int):
@@ -502,7 +529,7 @@ class PackedVae:
             pass
 
 
-class Observe:
+class Observe(_NoCopy):
     """drm_observe handle: workspace for B sequences x T steps (posterior scan, batched heads, encoder / decoder calls)."""
 
     def __init__(self, vae: PackedVae, B: int, T: int):

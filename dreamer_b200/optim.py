@@ -79,7 +79,22 @@ class FlatAdamW(torch.optim.Optimizer):
         self._rebind_grads()
         self.grad.zero_()
 
+    def _check_aliasing(self):
+        """The kernel updates `self.flat` through raw pointers: a parameter whose storage was replaced since construction
+        (module.to(...), .half(), load_state_dict(assign=True)) would silently stop training.  Re-point it at its slice (keeping
+        its current values) when only the storage moved; refuse when its dtype / device / size changed."""
+        for p, o in zip(self._params, self._offs):
+            if p.data_ptr() == self.flat.data_ptr() + 4 * o:
+                continue
+            if p.dtype != torch.float32 or p.device != self.flat.device or p.numel() != self.flat[o:o + p.numel()].numel():
+                raise RuntimeError("FlatAdamW: a parameter no longer matches the flat bucket (dtype / device / size changed); "
+                                   "rebuild the optimiser after converting the module")
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+
     def _rebind_grads(self):
+        self._check_aliasing()
         for p, o in zip(self._params, self._offs):
             g = p.grad
             if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * o:

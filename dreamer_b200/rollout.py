@@ -29,6 +29,8 @@ def dream_episodes(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, ge
 def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=None, generator=None):
     """Host-buffer call: the start states are (pinned) CPU tensors; the draws are made on the device exactly as
     ``Dreamer.dream_episodes`` does (pass ``uniforms`` / ``normals`` host tensors to supply them instead).
+    ``z0`` is either the fp32 latent (B, 1, R, 32) -- 4 KB per state over the host link -- or, since a sampled latent is a
+    one-hot, its uint8 class indices (B, R): 32 bytes per state, expanded on the device (drm_onehot32).
     Returns dict(device=7-tuple, host=(rewards, continues)); the host tensors are pinned buffers reused by the next call.
 
     The workspace keeps static device inputs and, after two eager calls, replays the rollout's ~110 launches as ONE CUDA graph
@@ -39,10 +41,15 @@ def dream_episodes_host(rollout: ops.Rollout, z0, h0, uniforms=None, normals=Non
     st = rollout.__dict__.get("_host_state")
     if st is None:
         f = dict(dtype=torch.float32, device=dev)
-        st = dict(z=torch.empty((B,) + tuple(z0.shape[1:]), **f), h=torch.empty((B,) + tuple(h0.shape[1:]), **f),
-                  u=torch.empty((H, B, m.R), **f), n=torch.empty((H, B, m.A), **f), host=None)
+        st = dict(z=torch.empty((B, 1, m.R, m.C), **f), h=torch.empty((B,) + tuple(h0.shape[1:]), **f),
+                  u=torch.empty((H, B, m.R), **f), n=torch.empty((H, B, m.A), **f), host=None,
+                  zi=torch.empty((B, m.R), dtype=torch.uint8, device=dev))
         rollout.__dict__["_host_state"] = st
-    st["z"].copy_(z0, non_blocking=True)
+    if z0.dtype == torch.uint8:
+        st["zi"].copy_(z0.reshape(B, m.R), non_blocking=True)
+        ops.onehot32(st["zi"], st["z"])
+    else:
+        st["z"].copy_(z0.reshape(st["z"].shape), non_blocking=True)
     st["h"].copy_(h0, non_blocking=True)
     if uniforms is not None:
         st["u"].copy_(uniforms, non_blocking=True)

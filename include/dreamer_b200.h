@@ -60,7 +60,8 @@ int64_t drm_launch_count(void);
 #define DRM_STAGE_HEADS_L2 5
 #define DRM_STAGE_HEADS_OUT 6
 #define DRM_STAGE_OTHER 7
-#define DRM_STAGE_COUNT 8
+#define DRM_STAGE_ROLLOUT 8 /* the persistent rollout kernel (one launch per drm_rollout_run) */
+#define DRM_STAGE_COUNT 9
 /* Runtime switches between kernel paths that compute the same thing (tests/test_gpu_errors.py compares them):           */
 /*   "persist"    (default 1)  drm_rollout_run as ONE persistent kernel for the whole horizon (rollout_persist.cuh) whenever its */
 /*                             static schedule fits the machine (e.g. <= 1024 start states at the reference sizes); 0 = always */
@@ -94,6 +95,9 @@ int drm_profile_read(int32_t stage, double* total_ms, int64_t* launches);
 /*   z_bf16 [n_rows, 32] bf16 one-hot (raw uint16 storage).                                     */
 int drm_categorical32_fwd(const float* logits, const float* uniforms, uint8_t* idx, float* z_st, float* probs,
                           uint16_t* z_bf16, int64_t n_rows, void* stream);
+/* One-hot expansion of sampled classes: idx [n_rows] u8 (< 32) -> out [n_rows, 32] fp32, 16-byte aligned.  Lets a caller hand a   */
+/* latent state across the host link as 32 bytes instead of 4 KB (the start states of Dreamer.dream_episodes, Dreamer.py:143).    */
+int drm_onehot32(const uint8_t* idx, float* out, int64_t n_rows, void* stream);
 /* Teacher-forced forward (the class idx [n_rows] u8 is given, not drawn): z_st = (onehot(idx) + p) - p and/or  */
 /* probs p = 0.99 softmax + 0.01/32.  Used by the gradient tail, which replays the classes the scan sampled.    */
 int drm_categorical32_st(const float* logits, const uint8_t* idx, float* z_st, float* probs, int64_t n_rows, void* stream);

@@ -283,6 +283,69 @@ def golden_agent_grads(cfg, tag, B, H, seed):
                 critic_grad_norm=float(torch.sqrt(sum((g.double() ** 2).sum() for g in snaps[0]))))
 
 
+def golden_acting(cfg, tag, steps, episode_len, seed, margin=0.25):
+    """The B = 1 acting loop: the REFERENCE's unmodified Dreamer.rollout_policy (Dreamer.py:177-226) on a fake environment, draws
+    redirected to streams.  The oracle walks the same loop first to place every posterior uniform inside its CDF bin; the
+    reference then has to reproduce the oracle's classes and actions, and ITS actions / classes / ring contents are stored."""
+    from oracle.fake_env import FakeEnv
+    sd = W.make_state_dict(cfg, seed=seed)
+    cfg = dict(cfg, sequence_length=steps, buffer_size=64)
+    ref = build_reference(cfg, sd)
+    rng = np.random.Generator(np.random.PCG64(seed + 5))
+    u_raw = torch.from_numpy(rng.random((steps + 1, 1, 32), dtype=np.float32))
+    normals = torch.from_numpy(rng.standard_normal((steps, 1, 3)).astype(np.float32))
+    D = cfg["hidden_state_dims"]
+
+    def norm(frame_hwc):
+        return torch.from_numpy(frame_hwc.transpose(2, 0, 1).astype(np.float32) / 255.0 - 0.5).unsqueeze(0)
+
+    def encode0(obs, u):
+        lg = O.encoder_logits(sd, torch.zeros(1, D), obs)
+        uu = O.interior_uniforms(O.unimix_probs(lg), u, margin, 1e-5)
+        z, idx, _ = O.categorical_st(lg, uu)
+        return z, idx, uu
+
+    # --- the oracle's walk over the loop (fixes the uniforms) ---
+    env = FakeEnv(episode_len, seed=seed + 6)
+    obs, _ = env.reset(seed=7)
+    h = torch.zeros(1, D)
+    used, idxs, acts, hs = [], [], [], []
+    z, idx, uu = encode0(norm(obs), u_raw[0]); used.append(uu); idxs.append(idx)
+    k = 1
+    with torch.no_grad():
+        for i in range(steps):
+            a, _, _ = O.actor_act(sd, h, z, normals[i])
+            acts.append(a)
+            obs_, reward, term, trunc, _ = env.step(a.numpy().reshape(-1))
+            if term or trunc:
+                obs, _ = env.reset(seed=0)
+                h = torch.zeros(1, D)
+                z, idx, uu = encode0(norm(obs), u_raw[k])
+            else:
+                z, h, _, idx, uu = O.observe_step(sd, z, h, a, norm(obs_), u_raw[k], margin_frac=margin, delta=1e-5)
+            used.append(uu); idxs.append(idx); hs.append(h.clone()); k += 1
+    # --- the reference, unmodified, on an identical environment ---
+    env_r = FakeEnv(episode_len, seed=seed + 6)
+    st = Streams(); st.u = list(used); st.n = [normals[i].reshape(1, 1, 3) for i in range(steps)]
+    ref.seed = 7
+    with patched_reference(st):
+        ref.rollout_policy(env_r, random_policy=False)
+    assert not st.u and not st.n
+    a_ref = np.stack(env_r.actions)
+    err = check(f"{tag}.actions", torch.from_numpy(a_ref), torch.cat(acts).reshape(steps, 3), tol=1e-5)
+    check(f"{tag}.hidden_last", ref.agent_hidden.reshape(1, D), hs[-1], tol=1e-5)
+    check(f"{tag}.idx_last", ref.agent_latent.argmax(-1).reshape(1, 32), idxs[-1], exact=True)
+    n = ref.buffer.size
+    np.savez_compressed(os.path.join(GOLD, f"{tag}.npz"), cfg=json.dumps(cfg), seed=seed, steps=steps, episode_len=episode_len,
+                        env_seed=seed + 6, uniforms_used=torch.stack(used).numpy(), normals=normals.numpy(), actions=a_ref,
+                        idx=torch.stack(idxs).numpy().astype(np.uint8).reshape(steps + 1, 32),
+                        hidden_last=ref.agent_hidden.numpy().reshape(D),
+                        ring_obs_sum=ref.buffer.observation_buffer[:n].reshape(n, -1).sum(-1).numpy().astype(np.float64) if hasattr(ref.buffer.observation_buffer, "numpy") else np.asarray(ref.buffer.observation_buffer[:n]).reshape(n, -1).sum(-1).astype(np.float64),
+                        ring_act=np.asarray(ref.buffer.action_buffer[:n]), ring_rew=np.asarray(ref.buffer.reward_buffer[:n]),
+                        ring_cont=np.asarray(ref.buffer.continue_buffer[:n]))
+    return dict(actions=err, transitions=int(n))
+
+
 def golden_replay(tag):
     sys.path.insert(0, REF)
     from Buffer import Buffer  # Buffer.py:5
@@ -337,6 +400,7 @@ def main():
     report["replay_small"] = golden_replay("replay_small")
     report["wm_grads_small"] = golden_wm_grads(small, "wm_grads_small", B=3, T=6, seed=61)
     report["agent_grads_small"] = golden_agent_grads(small, "agent_grads_small", B=6, H=5, seed=71)
+    report["acting_small"] = golden_acting(small, "acting_small", steps=12, episode_len=5, seed=81)
     # full reference sizes: compared here, only a digest is committed
     full = dict(W.REF_CONFIG, horizon=15)
     errs, r, out = golden_rollout(full, "rollout_ref", B=32, H=15, seed=41, save_full=False)

@@ -159,3 +159,87 @@ def test_patched_rollout_policy_and_evaluate_agent_follow_the_reference_loop():
     z0, h0 = d.warm_start_generator(obs, act, L)
     out = d.dream_episodes(z0, h0)
     assert z0.shape == (3, 1, 32, 32) and out[0].shape == (3, cfg["horizon"] + 1, 32, 32) and out[2].shape == (3, cfg["horizon"], 3)
+
+
+def test_acting_path_matches_the_reference_rollout_policy_fixture(golden_dir):
+    """The acting loop against the REFERENCE's unmodified Dreamer.rollout_policy (Dreamer.py:177-226) on the same fake environment
+    and the same draws (tests/golden/acting_small.npz, oracle/make_golden.py: golden_acting): every posterior class of every
+    step bit-exact, actions within the bf16 bound, the ring contents (frames, actions, symlog rewards, continue flags) as the
+    reference's ring holds them, across an episode boundary."""
+    import json
+    import os
+    from oracle.fake_env import FakeEnv
+    from dreamer_b200.acting import ActingPath
+    from dreamer_b200.modules import Buffer
+    g = np.load(os.path.join(golden_dir, "acting_small.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    steps, ep_len, seed = int(g["steps"]), int(g["episode_len"]), int(g["seed"])
+    wm, ag = W.build_learners(cfg, W.make_state_dict(cfg, seed=seed), DEV)
+    ring = Buffer(64, cfg["sequence_length"], cfg["action_dims"], tuple(cfg["observation_dims"]), device=DEV)
+    ap = ActingPath(wm, ag, ring, deterministic=False, warmup=2)
+    env = FakeEnv(ep_len, seed=int(g["env_seed"]))
+    u = torch.from_numpy(g["uniforms_used"]).to(DEV)          # (steps + 1, 1, 32)
+    nrm = torch.from_numpy(g["normals"]).to(DEV)              # (steps, 1, 3)
+    chw = lambda f: np.ascontiguousarray(f.transpose(2, 0, 1))
+    obs, _ = env.reset(seed=7)
+    ap.reset(chw(obs), u[0])
+    idx = [ap.latent.argmax(-1).view(-1).cpu().numpy()]
+    k = 1
+    for i in range(steps):
+        a = ap.act(nrm[i])
+        obs_, reward, term, trunc, _ = env.step(a)
+        done = bool(term or trunc)
+        ap.record(reward, 1 - done)
+        if done:
+            obs, _ = env.reset(seed=0)
+            ap.reset(chw(obs), u[k])
+        else:
+            ap.observe(chw(obs_), u[k])
+        idx.append(ap.latent.argmax(-1).view(-1).cpu().numpy())
+        k += 1
+    assert np.array_equal(np.stack(idx).astype(np.uint8), g["idx"])                        # every class of every step
+    acts = np.stack(env.actions)
+    assert np.abs(acts - g["actions"]).max() <= 1e-2 * np.abs(g["actions"]).max()
+    hl = ap.hidden.view(-1).cpu().numpy()
+    assert np.abs(hl - g["hidden_last"]).max() <= 1e-2 * np.abs(g["hidden_last"]).max()
+    n = steps
+    assert ring.size == n
+    assert np.array_equal(ring.observation_buffer[:n].reshape(n, -1).sum(-1, dtype=torch.float64).cpu().numpy(), g["ring_obs_sum"])
+    assert np.abs(ring.action_buffer[:n].cpu().numpy() - g["ring_act"]).max() <= 1e-2
+    assert np.allclose(ring.reward_buffer[:n].cpu().numpy(), g["ring_rew"], atol=1e-6)
+    assert np.array_equal(ring.continue_buffer[:n].cpu().numpy(), g["ring_cont"])
+
+
+def test_patched_rollout_policy_acts_on_updated_weights_mid_episode():
+    """An episode continues across training phases (Dreamer.py:340-343): the second rollout_policy call must act with the weights
+    as they are NOW, although no reset happened in between (the captured graphs read packed weight caches)."""
+    from dreamer_b200 import dropin
+    cfg = W.small_config(sequence_length=5, horizon=4)
+    Shell = dropin.patch_dreamer(type("Shell", (_DreamerShell,), {}))
+    d = Shell(cfg)
+    env = _FakeEnv(episode_len=1000)                     # no episode boundary in this test
+    for _ in range(3):                                   # warm-up calls: the acting graphs get captured
+        d.rollout_policy(env, random_policy=False)
+    n0 = len(env.actions)
+    with torch.no_grad():                                # "training": push the policy mean far positive
+        d.agent.actor.mu_head.bias.add_(6.0)
+    torch.autograd.graph.increment_version(list(d.agent.actor.parameters()))
+    d.rollout_policy(env, random_policy=False)
+    new = np.stack(env.actions[n0:])
+    assert new.shape[0] == cfg["sequence_length"] and (new > 0.9).all(), new
+
+
+def test_standalone_actor_with_non_square_latents():
+    """Actor mirrors the reference's swapped constructor names (Agent.py:175); the packed engine must still get (rows, classes)."""
+    from dreamer_b200 import modules as M
+    torch.manual_seed(0)
+    R, C, Dh = 16, 32, 64
+    actor = M.Actor(3, R, C, Dh, 40, 40, device=DEV)
+    with torch.no_grad():
+        actor.mu_head.weight.normal_(0, 0.1)
+    h = torch.tanh(torch.randn(5, 1, Dh, device=DEV))
+    z = torch.nn.functional.one_hot(torch.randint(0, C, (5, 1, R), device=DEV), C).float()
+    mu, sigma = actor(h, z)
+    base = actor.base_net(torch.cat([h, z.flatten(2)], -1))
+    mu_ref = actor.mu_head(base)
+    assert (mu - mu_ref).abs().max() <= 1e-2 * max(mu_ref.abs().max().item(), 1e-3) + 1e-3

@@ -123,3 +123,18 @@ def test_flat_adamw_is_graph_capturable():
     assert float(og.opt_state[0]) == 5
     for a, b in zip(eager.parameters(), graphed.parameters()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_flat_adamw_follows_parameters_whose_storage_was_replaced():
+    """FlatAdamW updates its flat bucket through raw pointers: when a parameter's storage is replaced after construction (e.g.
+    load_state_dict(assign=True)) the next step must re-point it at its slice instead of silently training an orphan."""
+    import torch
+    from dreamer_b200.optim import FlatAdamW
+    lin = torch.nn.Linear(8, 4, device="cuda")
+    opt = FlatAdamW(lin.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0)
+    lin.weight.data = lin.weight.data.clone()            # storage replaced: no longer a view of the flat bucket
+    w0 = lin.weight.detach().clone()
+    lin(torch.randn(3, 8, device="cuda")).sum().backward()
+    opt.step()
+    assert not torch.equal(lin.weight.detach(), w0)      # the live parameter moved
+    assert lin.weight.data_ptr() == opt.flat.data_ptr() + 4 * opt._offs[0]

@@ -207,3 +207,10 @@ def test_host_buffer_rollout_call_matches_device_call_across_graph_capture(ops):
                 assert torch.equal(a, b), call
         assert torch.equal(got["host"][0], ref[3].cpu()) and torch.equal(got["host"][1], ref[4].cpu())
     assert ro.__dict__["_graphs"][False].captured(*[ro.__dict__["_host_state"][k] for k in ("z", "h", "u", "n")])
+    # the start latent handed over as its uint8 class indices (32 B per state instead of 4 KB): same rollout
+    z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=200)
+    ref = [t.clone() for t in ro.run(z0.to(DEV), h0.to(DEV), u.to(DEV), n.to(DEV), want_idx=False)]
+    zi = z0.reshape(B, 32, 32).argmax(-1).to(torch.uint8).pin_memory()
+    got = dream_episodes_host(ro, zi, h0.pin_memory(), uniforms=u.pin_memory(), normals=n.pin_memory())
+    for a, b in zip(ref, got["device"]):
+        assert torch.equal(a, b)
