@@ -135,7 +135,11 @@ class ActingPath:
         if self.buffer is None:
             return
         self._stage("meta", self._meta_host, self.meta, torch.tensor([float(reward), float(continue_)], dtype=torch.float32))
-        self.buffer.add_batch(self.frame[None], self.action.view(1, -1), self.meta[0:1], self.meta[1:2])
+        # Dreamer.rollout_policy keeps the current frame normalised and stores ((obs / 255 - 0.5) + 0.5) * 255 truncated to uint8
+        # (Dreamer.py:186, 209): in fp32 that round trip lands just below the integer for 63 of the 256 pixel values, so the reference's
+        # ring holds x - 1 there.  Reproduced bit for bit (12 KB of elementwise work per step) so that the ring contents are identical.
+        stored = ((((self.frame.to(torch.float32) / 255.0) - 0.5) + 0.5) * 255.0).to(torch.uint8)
+        self.buffer.add_batch(stored[None], self.action.view(1, -1), self.meta[0:1], self.meta[1:2])
 
     def step(self, next_frame_u8_chw, reward: float, continue_: float, uniforms: Optional[torch.Tensor] = None,
              normals: Optional[torch.Tensor] = None) -> np.ndarray:

@@ -45,7 +45,8 @@ def test_acting_path_matches_module_calls_and_fills_the_ring():
     assert torch.allclose(acting.hidden, h) and torch.equal(acting.latent.argmax(-1), z.argmax(-1))
     # transitions landed in the HBM ring exactly as buffer.add_to_buffer(obs_t, a_t, r_t, c_t) would have put them
     assert buf.size == n and buf.next_idx == n
-    assert np.array_equal(buf.observation_buffer[:n].cpu().numpy(), frames[:n])
+    # (with the reference's fp32 round trip of the stored frame, Dreamer.py:186,209)
+    assert np.array_equal(buf.observation_buffer[:n].cpu().numpy(), (((frames[:n].astype(np.float32) / 255.0) - 0.5 + 0.5) * 255.0).astype(np.uint8))
     assert np.allclose(buf.action_buffer[:n].cpu().numpy(), np.stack(ref_actions[:n]), atol=1e-6)
     assert np.allclose(buf.continue_buffer[:n].cpu().numpy().reshape(-1), conts)
     sym = np.sign(rewards) * np.log1p(np.abs(rewards))
@@ -145,7 +146,8 @@ def test_patched_rollout_policy_and_evaluate_agent_follow_the_reference_loop():
             cur = env.frames[idx]; idx += 1
         else:
             cur = nxt
-    assert np.array_equal(stored, np.stack(seen))
+    roundtrip = lambda x: (((x.astype(np.float32) / 255.0) - 0.5 + 0.5) * 255.0).astype(np.uint8)      # what Dreamer.py:186,209 store
+    assert np.array_equal(stored, roundtrip(np.stack(seen)))
     assert np.allclose(d.buffer.action_buffer[:n].cpu().numpy(), np.stack(env.actions), atol=1e-6)
     cont = d.buffer.continue_buffer[:n].cpu().numpy().reshape(-1)
     assert np.array_equal(cont, np.array([0.0 if (i + 1) % 4 == 0 else 1.0 for i in range(n)], dtype=np.float32))
