@@ -46,6 +46,8 @@ class ActingPath:
         self._action_in_host = torch.zeros(A, dtype=torch.float32).pin_memory()      # host -> device staging of set_action (not the read-back buffer)
         # one event per pinned staging buffer: recorded after its asynchronous copy is enqueued, waited for before the buffer is rewritten
         self._staged = {"frame": None, "meta": None, "action": None}
+        lut = (((np.arange(256, dtype=np.uint8).astype(np.float32) / 255.0) - 0.5 + 0.5) * 255.0).astype(np.uint8)
+        self._roundtrip_lut = torch.from_numpy(lut).to(dev)
         world_model.attach_actor(agent.actor)
         if use_graphs:
             self._reset = StepGraph(self._reset_body, warmup)
@@ -137,8 +139,9 @@ class ActingPath:
         self._stage("meta", self._meta_host, self.meta, torch.tensor([float(reward), float(continue_)], dtype=torch.float32))
         # Dreamer.rollout_policy keeps the current frame normalised and stores ((obs / 255 - 0.5) + 0.5) * 255 truncated to uint8
         # (Dreamer.py:186, 209): in fp32 that round trip lands just below the integer for 63 of the 256 pixel values, so the reference's
-        # ring holds x - 1 there.  Reproduced bit for bit (12 KB of elementwise work per step) so that the ring contents are identical.
-        stored = ((((self.frame.to(torch.float32) / 255.0) - 0.5) + 0.5) * 255.0).to(torch.uint8)
+        # ring holds x - 1 there.  Reproduced bit for bit (a 12 KB table look-up per step) so that the ring contents are identical.
+        # The 256-entry table is evaluated once on the host in numpy fp32, exactly as the reference evaluates it; the device only gathers.
+        stored = self._roundtrip_lut[self.frame.long()]
         self.buffer.add_batch(stored[None], self.action.view(1, -1), self.meta[0:1], self.meta[1:2])
 
     def step(self, next_frame_u8_chw, reward: float, continue_: float, uniforms: Optional[torch.Tensor] = None,

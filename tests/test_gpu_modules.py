@@ -16,7 +16,7 @@ DEV = "cuda"
 
 def _close(got, ref, rel=1e-2, what="", **_):
     """North-star bound for bf16-operand quantities: max |got - ref| <= 1e-2 of the reference tensor's scale (profiles/parity_r2.md)."""
-    got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
+    got, ref = torch.as_tensor(got).detach().cpu().float(), torch.as_tensor(ref).detach().cpu().float()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
