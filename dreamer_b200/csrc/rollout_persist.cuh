@@ -250,6 +250,119 @@ struct EpiGruP {
 };
 
 // ------------------------------------------------------------------------------------------
+// cluster exchanges without barrier.cluster: st.async writes a few bytes into a peer's shared memory through the async proxy and
+// counts them on an mbarrier IN THAT PEER (complete_tx), so the receiver just waits on its own mbarrier until every contribution
+// has landed -- no all-thread cluster barrier (measured ~0.9 - 1.2 us with its release of the pending remote stores) in the middle
+// of an epilogue.  Receivers arm the barrier with arrive.expect_tx; a barrier / buffer pair is reused every second exchange (a CTA
+// can run at most ONE exchange ahead of a peer: exchange k + 1 needs that peer's contribution k + 1, sent after it finished k).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_async_v2(float* local_ptr, uint64_t* local_bar, uint32_t cta, float a, float b) {
+  uint32_t ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(cta));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n" ::"r"(ra), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(rb)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(float* local_ptr, uint64_t* local_bar, uint32_t cta, float a, float b, float c, float d) {
+  uint32_t ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(cta));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(ra),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rb)
+               : "memory");
+}
+
+struct PsXchg {
+  float* xst;        // [2][4 ranks][128 rows][2] LayerNorm statistics (mean, M2) of every rank's 64 columns
+  uint64_t* xbar;    // [2] mbarriers counting the 4 KB of an exchange
+  float* xact;       // rank 0: [4 ranks][128 rows][8] actor-output partial sums
+  uint64_t* abar;    // rank 0: mbarrier counting their 16 KB
+  uint32_t xuse;     // LayerNorm exchanges so far, identical in every thread of the cluster
+  uint32_t ause;     // actor exchanges so far
+  unsigned* dbg;
+};
+
+// EpiLnSiluN4T<false>::compute with the statistics exchanged by st.async + mbarrier (SiLU through tanh.approx)
+__device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const TileG& g, float* sm, PsXchg& x, uint32_t taddr, int m, int row,
+                                              int part, int slot, int tid, unsigned code, float (&v)[16]) {
+  const int nv = p.n_valid;
+  const int cr = (int)cluster_ctarank();
+  const int c0 = part * 16;
+  const int gc0 = 64 * cr + c0;
+  auto cnt_of = [](int nvv, int first, int width) { return max(0, min(width, nvv - first)); };
+  const int cnt = cnt_of(nv, gc0, 16);
+  const uint32_t buf = x.xuse & 1u, par = (x.xuse >> 1) & 1u;
+  float* xst = x.xst + buf * (4 * 128 * 2);
+  if (tid == 0) mbar_expect_tx(&x.xbar[buf], 4u * 128u * 8u);      // this CTA will receive 8 bytes per row from each of the 4 ranks
+  tmem_ld16(taddr + c0, v);
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(sm + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = b4[j];
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+  const float shift = v[0];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float d = v[j] - shift;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  }
+  const float npad = (float)(16 - cnt);
+  s1 = fmaf(npad, shift, s1);
+  s2 = fmaf(-npad * shift, shift, s2);
+  const float inv_cnt = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+  float* xs = sm + XCHG;
+  xs[part * 128 + row] = shift + s1 * inv_cnt;
+  xs[512 + part * 128 + row] = fmaxf(s2 - s1 * s1 * inv_cnt, 0.f);
+  epi_bar_sync();
+  if (part == 0) {   // merge the CTA's four parts, send (mean, M2) of these 64 columns to every CTA of the cluster
+    const int cnt_c = cnt_of(nv, 64 * cr, 64);
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPI_PARTS; ++q) tot += xs[q * 128 + row] * (float)cnt_of(nv, 64 * cr + 16 * q, 16);
+    const float mean_c = cnt_c > 0 ? tot / (float)cnt_c : 0.f;
+    float M2c = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPI_PARTS; ++q) {
+      const float d = xs[q * 128 + row] - mean_c;
+      M2c += xs[512 + q * 128 + row] + d * d * (float)cnt_of(nv, 64 * cr + 16 * q, 16);
+    }
+#pragma unroll
+    for (uint32_t dst = 0; dst < 4; ++dst) st_async_v2(xst + (cr * 128 + row) * 2, &x.xbar[buf], dst, mean_c, M2c);
+  }
+  if ((tid & 31) == 0) ps_mbar_wait(&x.xbar[buf], par, x.dbg, code | (11u << 20));
+  __syncwarp();
+  float tot = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tot += xst[(q * 128 + row) * 2] * (float)cnt_of(nv, 64 * q, 64);
+  const float mean = tot / (float)nv;
+  float M2 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float d = xst[(q * 128 + row) * 2] - mean;
+    M2 += xst[(q * 128 + row) * 2 + 1] + d * d * (float)cnt_of(nv, 64 * q, 64);
+  }
+  const float rstd = rsqrtf(M2 / (float)nv + p.eps);
+  const float nmr = -mean * rstd;
+  const float4* ga = reinterpret_cast<const float4*>(sm + 256 + c0);
+  const float4* be = reinterpret_cast<const float4*>(sm + 512 + c0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 G = ga[j], Bt = be[j];
+    v[4 * j] = silu_fast_(fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x));
+    v[4 * j + 1] = silu_fast_(fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y));
+    v[4 * j + 2] = silu_fast_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
+    v[4 * j + 3] = silu_fast_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
+  }
+  x.xuse += 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // prior logits -> sample (EpiCat's arithmetic, DynamicsPredictors.py:31-40) for the persistent kernel.  The straight-through
 // latent (onehot + p) - p is exactly 0 off the sampled class, so the fp32 `latent` output is zero-filled once per rollout
 // (cudaMemsetAsync) and the epilogue stores ONE float per 32-class row -- no 128 x 256 fp32 tile through shared memory.
@@ -354,9 +467,12 @@ struct PsActorOut {
       sm[WOFF + i] = __bfloat162float(w3[(long)wrow * 256 + 64 * cr + c]);
     }
   }
-  // v: this thread's 16 activations (columns 64 * rank + 16 * part ..).  red / xact: two 16 KB areas of the (idle) pipeline ring.
-  __device__ __forceinline__ void run(const float (&v)[16], float* sm, float* red, float* xact, int m, int row, int part, int tid) const {
+  // v: this thread's 16 activations (columns 64 * rank + 16 * part ..).  red: 16 KB of the (idle) pipeline ring; the row sums go to
+  // rank 0 by st.async (x.xact / x.abar), ranks 1 .. 3 are done as soon as they have sent theirs.
+  __device__ __forceinline__ void run(const float (&v)[16], float* sm, float* red, PsXchg& x, int m, int row, int part, int tid, unsigned code) const {
     const int cr = (int)cluster_ctarank();
+    const uint32_t par = x.ause & 1u;
+    if (cr == 0 && tid == 0) mbar_expect_tx(x.abar, 4u * 128u * 32u);
     float pa[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) pa[k] = 0.f;
@@ -380,30 +496,32 @@ struct PsActorOut {
     ps_lap(sm, tid, 0);
     epi_bar_sync();
     ps_lap(sm, tid, 1);
+    float bm[4] = {0.f, 0.f, 0.f, 0.f}, bl[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f};
     if (part == 0) {   // the row's sum over this CTA's 64 columns -> rank 0
       float sacc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) sacc[k] = 0.f;
 #pragma unroll
       for (int q = 0; q < EPI_PARTS; ++q) {
-        const float4 x = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8), y = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8 + 4);
-        sacc[0] += x.x; sacc[1] += x.y; sacc[2] += x.z; sacc[3] += x.w; sacc[4] += y.x; sacc[5] += y.y; sacc[6] += y.z; sacc[7] += y.w;
+        const float4 xx = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8), yy = *reinterpret_cast<const float4*>(red + (q * 128 + row) * 8 + 4);
+        sacc[0] += xx.x; sacc[1] += xx.y; sacc[2] += xx.z; sacc[3] += xx.w; sacc[4] += yy.x; sacc[5] += yy.y; sacc[6] += yy.z; sacc[7] += yy.w;
       }
-      st_cluster_v4f32(xact + (cr * 128 + row) * 8, 0u, sacc[0], sacc[1], sacc[2], sacc[3]);
-      st_cluster_v4f32(xact + (cr * 128 + row) * 8 + 4, 0u, sacc[4], sacc[5], sacc[6], sacc[7]);
+      st_async_v4(x.xact + (cr * 128 + row) * 8, x.abar, 0u, sacc[0], sacc[1], sacc[2], sacc[3]);
+      st_async_v4(x.xact + (cr * 128 + row) * 8 + 4, x.abar, 0u, sacc[4], sacc[5], sacc[6], sacc[7]);
+      if (cr == 0 && m < M) {   // (fetched while the partial sums travel)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < A) { bm[k] = __ldg(b3 + k); bl[k] = __ldg(b3 + 16 + k); ep[k] = __ldg(normals + (long)m * A + k); }
+      }
     }
     ps_lap(sm, tid, 2);
-    float bm[4] = {0.f, 0.f, 0.f, 0.f}, bl[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f};
-    if (cr == 0 && part == 0 && m < M) {   // (fetched under the barrier)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < A) { bm[k] = __ldg(b3 + k); bl[k] = __ldg(b3 + 16 + k); ep[k] = __ldg(normals + (long)m * A + k); }
-    }
+    x.ause += 1;
+    if (cr != 0 || part != 0) return;
+    if ((tid & 31) == 0) ps_mbar_wait(x.abar, par, x.dbg, code | (12u << 20));
     __syncwarp();
-    cluster_arrive_release();
-    cluster_wait_acquire();
     ps_lap(sm, tid, 3);
-    if (cr == 0 && part == 0 && m < M) {
+    if (m < M) {
+      const float* xact = x.xact;
       float av[3] = {0.f, 0.f, 0.f};
       float t[8];
 #pragma unroll
@@ -640,12 +758,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     tma_prefetch_desc(&P.tmS); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
     for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    for (int i = 12; i < 15; ++i) mbar_init(&full[i], 1);   // xbar[0], xbar[1], abar (bytes 96 .. 120 of the barrier block; the lap pointer sits at byte 128)
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < PS_SCHED_STRIDE; i += GEMM_THREADS) sched[i] = __ldg(P.sched + (long)blockIdx.x * PS_SCHED_STRIDE + i);
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // every CTA's mbarriers exist before a peer's st.async can target them
   tc_fence_after();
 
   PsCtx c;
@@ -687,6 +807,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     const int rank = (int)cluster_ctarank();
     const int m0 = m_tile * BM, m = m0 + row;
     const int ya = (1 + HS_ACTOR) * Mp;   // the actor's slot of the hidden-activation buffers (slot 0 = prior)
+    PsXchg xg;
+    xg.xst = reinterpret_cast<float*>(smem + PS_RING_BYTES);                 // (the 16 KB behind the ring, unused by chain CTAs otherwise)
+    xg.xbar = full + 12; xg.abar = full + 14;
+    xg.xact = reinterpret_cast<float*>(smem + PS_RING_BYTES - 16384);        // rank 0: last 16 KB of the ring (idle while the epilogue runs)
+    xg.xuse = 0; xg.ause = 0; xg.dbg = P.dbg;
     for (int j = 0; j <= H; ++j) {
       trace_window(j);
       const int s_row = j * B + m0;       // this m-tile's rows of state j in the time-major state buffer
@@ -694,7 +819,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
       if (j >= 1) {
         {   // prior L1: h_j -> Y1[slot 0], this CTA's 64 columns   (DynamicsPredictors.py:15-18)
           tile_init(t, 0, j, m_tile);
-          t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2;
           t.tcol = 256;
           if (j < H) {
             // the actor's first layer reads the same h k-blocks: its 64 weight rows ride along under the prior's (one N = 128 MMA per
@@ -707,16 +832,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, taddr + 256, m, row, part, 0, tid); });
+                         [&](int tid) {
+                           float v[16];
+                           ps_ln_compute(p, g, epi_sm, xg, taddr + 256, m, row, part, 0, tid, t.code, v);
+                           EpiLnSiluN4::store(p, g, tile, m, row, part, 0, tid, v);
+                         });
           ps_cluster_handover();
         }
         {   // prior L2: Y1 -> Y2[slot 0]   (:19-22)
           tile_init(t, 1, j, m_tile);
-          t.tmA = &P.tmY1; t.tmB = &P.tmWp2q; t.a_row = m0; t.b_row = 64 * rank; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.tmA = &P.tmY1; t.tmB = &P.tmWp2q; t.a_row = m0; t.b_row = 64 * rank; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = 64; t.kps = 2;
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p2_b, P.p2_g, P.p2_be, nullptr, 0, P.Y2, 256, 0, 0, P.hp2, 1e-5f, P.bnp2};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, taddr, m, row, part, 0, tid); });
+                         [&](int tid) {
+                           float v[16];
+                           ps_ln_compute(p, g, epi_sm, xg, taddr, m, row, part, 0, tid, t.code, v);
+                           EpiLnSiluN4::store(p, g, tile, m, row, part, 0, tid, v);
+                         });
           ps_cluster_handover();
         }
         // prior logits + sample: 256 logit columns (8 latent rows) per tile, tiles rank, rank + 4, ...   (:23, 31-40)
@@ -739,7 +872,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           tile_init(t, 0, j, m_tile);
           t.code |= 1u << 19;
           t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
-          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2; t.cbar = 1;
+          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2;
           if (j >= 1) {   // the h part is already accumulated (prior L1 above): z k-blocks only
             t.nka1 = 0; t.tcol = 320; t.acc0 = 1;
           }
@@ -748,26 +881,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
           const uint32_t ta = taddr + (uint32_t)t.tcol;
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); },
-                         [&](int tid) { EpiLnSiluN4::run_fast(p, g, epi_sm, tile, ta, m, row, part, HS_ACTOR, tid); });
+                         [&](int tid) {
+                           float v[16];
+                           ps_ln_compute(p, g, epi_sm, xg, ta, m, row, part, HS_ACTOR, tid, t.code, v);
+                           EpiLnSiluN4::store(p, g, tile, m, row, part, HS_ACTOR, tid, v);
+                         });
           ps_cluster_handover();
         }
         {   // actor L2 + output layer -> a_j = tanh(mu + sigma * eps)   (Agent.py:182-187, 199-209)
           tile_init(t, 1, j, m_tile);
           t.code |= 1u << 19;
           t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
-          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2; t.cbar = 2;
+          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2;
           t.chain = 0;   // (no hand-over follows, and its epilogue used the ring as scratch: keep the proxy fence before the next tile's TMA loads)
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
           const PsActorOut ao{P.Wh3 + (long)HS_ACTOR * 256 * 256, P.h3_b + HS_ACTOR * 256, P.normals + (long)j * B * A,
                               P.mu + (long)j * A, P.sigma + (long)j * A, P.actions + (long)j * A, P.apack + (long)j * Mp, ldA, A, B};
           float* red = reinterpret_cast<float*>(smem);
-          float* xact = reinterpret_cast<float*>(smem + 16384);
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, HS_ACTOR, epi_sm, tid, m0); ao.stage(epi_sm, tid); },
                          [&](int tid) {
                            float v[16];
-                           EpiLnSiluN4::compute<true>(p, g, epi_sm, taddr, m, row, part, v);
-                           ao.run(v, epi_sm, red, xact, m, row, part, tid);
+                           ps_ln_compute(p, g, epi_sm, xg, taddr, m, row, part, HS_ACTOR, tid, t.code, v);
+                           ao.run(v, epi_sm, red, xg, m, row, part, tid, t.code);
                          });
         }
       }
