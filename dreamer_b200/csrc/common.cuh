@@ -225,16 +225,9 @@ __device__ __forceinline__ float tanhf_(float x) {  // 1 - 2 / (1 + e^{2x}); sat
   return fmaf(-2.0f, rcpf_(1.0f + ex2f_(2.8853900817779268f * x)), 1.0f);
 }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
-// One-MUFU forms (tanh.approx.f32, relative error 2^-11): sigmoid = 0.5 tanh(x / 2) + 0.5.  The epilogues of the persistent rollout
-// kernel are bound by the 16 special-function results per clock of an SM (SiLU and the three GRU gates cost two MUFU operations
-// each in the ex2 + rcp form); the absolute error added, <= 2.5e-4, is an order below the bf16 rounding of the same values.
-__device__ __forceinline__ float tanh_fast_(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_fast_(float x) { return fmaf(0.5f, tanh_fast_(0.5f * x), 0.5f); }
-__device__ __forceinline__ float silu_fast_(float x) { return x * sigmoid_fast_(x); }
+// (tanh.approx.f32 was measured as a replacement for the ex2 + rcp forms in the persistent kernel's epilogues: one MUFU operation
+// instead of two, but MUFU.TANH issues at a quarter of the EX2 rate on B200 -- the GRU epilogue went from 2.1 to 3.0 us -- so the
+// ex2 / rcp forms stay.)
 __device__ __forceinline__ float symexpf_(float x) {  // DreamerUtils.py:35-37
   const float c = fminf(fmaxf(x, -20.0f), 20.0f);   // fminf / fmaxf drop a NaN; torch.clamp keeps it -> x * 0 below restores it
   float e = expf(fabsf(c)) - 1.0f;

@@ -239,9 +239,7 @@ struct EpiLnSiluN4T {
     }
   }
   static __device__ __forceinline__ int cnt_of(int nv, int first, int width) { return max(0, min(width, nv - first)); }
-  // accumulator -> LayerNorm + SiLU of this thread's 16 columns (v); contains the cluster's ONE statistics barrier.
-  // FAST: SiLU through tanh.approx (one MUFU operation per element instead of two; persistent rollout kernel)
-  template <bool FAST = false>
+  // accumulator -> LayerNorm + SiLU of this thread's 16 columns (v); contains the cluster's ONE statistics barrier
   static __device__ __forceinline__ void compute(const Params& p, const TileG& g, float* sm, uint32_t taddr, int m, int row, int part,
                                                  float (&v)[16]) {
     const int nv = p.n_valid;
@@ -322,10 +320,10 @@ struct EpiLnSiluN4T {
         const float4 G = ga[j], Bt = be[j];
         const float x0 = fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x), x1 = fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y);
         const float x2 = fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z), x3 = fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w);
-        v[4 * j] = FAST ? silu_fast_(x0) : siluf_(x0);
-        v[4 * j + 1] = FAST ? silu_fast_(x1) : siluf_(x1);
-        v[4 * j + 2] = FAST ? silu_fast_(x2) : siluf_(x2);
-        v[4 * j + 3] = FAST ? silu_fast_(x3) : siluf_(x3);
+        v[4 * j] = siluf_(x0);
+        v[4 * j + 1] = siluf_(x1);
+        v[4 * j + 2] = siluf_(x2);
+        v[4 * j + 3] = siluf_(x3);
       }
     }
   }
@@ -357,12 +355,6 @@ struct EpiLnSiluN4T {
                                              int row, int part, int slot, int tid) {
     float v[16];
     compute(p, g, sm, taddr, m, row, part, v);
-    store(p, g, tile, m, row, part, slot, tid, v);
-  }
-  static __device__ __forceinline__ void run_fast(const Params& p, const TileG& g, float* sm, float* tile, uint32_t taddr, int m,
-                                                  int row, int part, int slot, int tid) {
-    float v[16];
-    compute<true>(p, g, sm, taddr, m, row, part, v);
     store(p, g, tile, m, row, part, slot, tid, v);
   }
 };

@@ -199,6 +199,9 @@ struct EpiGruP {
     const int u0 = n_tile * U;
     const int m0 = m - row;
     const int nvalid = min(U, p.D - u0);
+    // (uniform over the CTA) whole 8-unit groups, 16-byte aligned rows: the direct-store path
+    const bool direct = (p.D & 7) == 0 && (p.ld_h & 3) == 0 && (p.ld_s & 7) == 0 && (reinterpret_cast<uintptr_t>(p.h_out) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.s_h) & 15u) == 0;
     float4 a = make_float4(0.f, 0.f, 0.f, 1.f);
     if (m < M) {   // the action arrives as one 8-byte record per row whose top half-word is the ready tag: no separate flag, no second round trip
       unsigned long long rec;
@@ -234,17 +237,31 @@ struct EpiGruP {
         const float ar = fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, wr.w)));   // action term + bias
         const float az = fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, wz.w)));
         const float an = fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, wn.w)));
-        const float rr = sigmoid_fast_(r_[j] + ar);   // (one MUFU operation per gate: common.cuh)
-        const float zz = sigmoid_fast_(z_[j] + az);
-        const float nn = tanh_fast_(nx[j] + an + rr * (nh[j] + sm[c + j]));
+        const float rr = sigmoidf_(r_[j] + ar);
+        const float zz = sigmoidf_(z_[j] + az);
+        const float nn = tanhf_(nx[j] + an + rr * (nh[j] + sm[c + j]));
         hn[j] = (1.0f - zz) * nn + zz * hp[row * PITCH + c + j];
       }
-      tile_put<UP>(tile, PITCH, row, c, hn);
+      if (direct) {
+        // this thread's 8 units are one 32-byte sector of the fp32 hidden row and 16 bytes of the bf16 state row: straight from
+        // registers (no shared-memory transpose, barrier and copy-out pass between the gate math and the publication of h)
+        if (m < M && c < nvalid) {
+          float* o = p.h_out + (long)m * p.ld_h + u0 + c;
+          *reinterpret_cast<float4*>(o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          *reinterpret_cast<uint4*>(p.s_h + (long)m * p.ld_s + u0 + c) =
+              make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+        }
+      } else {
+        tile_put<UP>(tile, PITCH, row, c, hn);
+      }
     }
     ps_lap(sm, tid, 1);
-    epi_bar_sync();
-    ps_lap(sm, tid, 2);
-    tile_copy_out(tile, PITCH, U, nvalid, m0, M, p.h_out + u0, p.ld_h, p.s_h + u0, p.ld_s, tid);
+    if (!direct) {
+      epi_bar_sync();
+      ps_lap(sm, tid, 2);
+      tile_copy_out(tile, PITCH, U, nvalid, m0, M, p.h_out + u0, p.ld_h, p.s_h + u0, p.ld_s, tid);
+    }
     ps_lap(sm, tid, 3);
   }
 };
@@ -283,7 +300,7 @@ struct PsXchg {
   unsigned* dbg;
 };
 
-// EpiLnSiluN4T<false>::compute with the statistics exchanged by st.async + mbarrier (SiLU through tanh.approx)
+// EpiLnSiluN4T<false>::compute with the statistics exchanged by st.async + mbarrier
 __device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const TileG& g, float* sm, PsXchg& x, uint32_t taddr, int m, int row,
                                               int part, int slot, int tid, unsigned code, float (&v)[16]) {
   const int nv = p.n_valid;
@@ -354,10 +371,10 @@ __device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float4 G = ga[j], Bt = be[j];
-    v[4 * j] = silu_fast_(fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x));
-    v[4 * j + 1] = silu_fast_(fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y));
-    v[4 * j + 2] = silu_fast_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
-    v[4 * j + 3] = silu_fast_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
+    v[4 * j] = siluf_(fmaf(fmaf(v[4 * j], rstd, nmr), G.x, Bt.x));
+    v[4 * j + 1] = siluf_(fmaf(fmaf(v[4 * j + 1], rstd, nmr), G.y, Bt.y));
+    v[4 * j + 2] = siluf_(fmaf(fmaf(v[4 * j + 2], rstd, nmr), G.z, Bt.z));
+    v[4 * j + 3] = siluf_(fmaf(fmaf(v[4 * j + 3], rstd, nmr), G.w, Bt.w));
   }
   x.xuse += 1;
 }
@@ -532,10 +549,14 @@ struct PsActorOut {
           const float muv = t[k] + bm[k];
           float ls = t[A + k] + bl[k];
           ls = fminf(fmaxf(ls, -5.0f), 2.0f);
-          const float sg = softplusf_(ls) + 1e-3f;
+          // softplus on [-5, 2] and tanh through ex2 / lg2 / rcp (relative error ~1e-6): these 128 threads are the only ones between
+          // the last partial sum and the GRU CTAs' wake-up, and libm's expf / log1pf / tanhf are ~150 dependent instructions per action
+          float l2;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.0f + fexpf_(ls)));
+          const float sg = fmaf(l2, 0.6931471805599453f, 1e-3f);
           mu[(long)m * ld_act + k] = muv;
           sigma[(long)m * ld_act + k] = sg;
-          const float ak = tanhf(muv + sg * ep[k]);
+          const float ak = tanhf_(muv + sg * ep[k]);
           action[(long)m * ld_act + k] = ak;
           if (k < 3) av[k] = ak;
         }
