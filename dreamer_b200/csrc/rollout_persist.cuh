@@ -286,7 +286,7 @@ struct PsXchg {
 };
 
 // EpiLnSiluN4T<false>::compute with the statistics exchanged by st.async + mbarrier
-__device__ __noinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const TileG& g, float* sm, PsXchg& x, uint32_t taddr, int m, int row,
+__device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const TileG& g, float* sm, PsXchg& x, uint32_t taddr, int m, int row,
                                               int part, int slot, int tid, unsigned code, float (&v)[16]) {
   const int nv = p.n_valid;
   const int cr = (int)cluster_ctarank();
@@ -592,131 +592,118 @@ struct PsTile {
 
 __device__ __forceinline__ int ps_ka(const PsTile& t, int kb) { return kb < t.nka0 ? t.ka0 + kb : t.ka1 + (kb - t.nka0); }
 
-// The operand producer and the MMA issuer are ONE copy of code each, shared by every tile of every role (not inlined): a chain CTA
-// walks five different tiles per state, and with everything inlined the kernel was 270 KB of SASS -- each tile's code had left
-// the 32 KB instruction cache by the time the next state came round.
-__device__ __noinline__ void ps_produce(PsCtx& c, const PsTile& t) {
-  const int nk = t.nka0 + t.nka1;
-  const int kps = t.kps;
-  const int n_st = (nk + kps - 1) / kps;
-  const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;   // one k-block: [A 16 KB | B]
-  if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
-  // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
-  // pre-filled while waiting; otherwise A and B of a stage are issued together
-  const int tx_sub = sub_bytes;
-  auto load_b = [&](uint32_t s, int u, int kb) {
-    uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES;
-    tma_load_2d(sb, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
-    if (t.tmB2) tma_load_2d(sb + t.n1 * BK * 2, t.tmB2, (kb + t.b2_koff) * BK, t.b2_row, &c.full[s]);
-  };
-  auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
-    int st = st0;
-    if (w != nullptr || gte != nullptr) {
-      const int npre = min(st1 - st0, PS_STAGES);
-      for (; st < st0 + npre; ++st) {
-        const uint32_t i = c.it + st, s = i % PS_STAGES;
-        ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
-        const int n_sub = min(kps, nk - st * kps);
-        mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
-        for (int u = 0; u < n_sub; ++u) load_b(s, u, st * kps + u);
-      }
-      ps_flag_wait(gte, tg, c.dbg, t.code | (6u << 20));
-      ps_flag_wait(w, tw, c.dbg, t.code | (2u << 20));
-      fence_proxy_async_all();   // the A operand was written through the generic proxy by another SM: order it before the TMA reads
-      if (mark && c.tr) c.tr[2] = ps_now();
-      for (int s2 = st0; s2 < st0 + npre; ++s2) {
-        const uint32_t s = (c.it + s2) % PS_STAGES;
-        const int n_sub = min(kps, nk - s2 * kps);
-        for (int u = 0; u < n_sub; ++u)
-          tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
-      }
-    } else if (mark) {
-      fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
-      if (c.tr) c.tr[2] = ps_now();
-    }
-    for (; st < st1; ++st) {
-      const uint32_t i = c.it + st, s = i % PS_STAGES;
-      ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
-      const int n_sub = min(kps, nk - st * kps);
-      mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
-      for (int u = 0; u < n_sub; ++u) {
-        const int kb = st * kps + u, ka = ps_ka(t, kb);
-        tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
-        load_b(s, u, kb);
-      }
-    }
-  };
-  if (t.w1 != nullptr || t.g1 != nullptr) {   // two separately released k ranges (kps == 1)
-    issue(0, t.nka0, t.w0, t.t0, t.g0, t.gt0, true);
-    issue(t.nka0, nk, t.w1, t.t1, t.g1, t.gt1, false);
-  } else {
-    issue(0, n_st, t.w0, t.t0, t.g0, t.gt0, true);
-  }
-}
-
-__device__ __noinline__ void ps_issue_mma(PsCtx& c, const PsTile& t, int gru_u) {
-  const int nk = t.nka0 + t.nka1;
-  const int kps = t.kps;
-  const int n_st = (nk + kps - 1) / kps;
-  const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;
-  for (int st = 0; st < n_st; ++st) {
-    const uint32_t i = c.it + st, s = i % PS_STAGES;
-    ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
-    tc_fence_after();
-    if (c.tr && st == 0) c.tr[3] = ps_now();
-    const int n_sub = min(kps, nk - st * kps);
-    for (int u = 0; u < n_sub; ++u) {
-      const int kb = st * kps + u;
-      const uint32_t a_addr = smem_u32(c.smem + s * t.stage_bytes + u * sub_bytes);
-      const uint64_t adesc = umma_desc_sw128(a_addr);
-      const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-      if (gru_u == 0) {
-        const uint32_t idesc = umma_idesc_bf16(t.bn);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem + t.tcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k | t.acc0) != 0);
-      } else {
-        // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U).
-        // The h part comes first (h_j is there long before z_j): the very first z MMA must START n_x while ADDING to r, z, so it is
-        // issued as an N = 2U and an N = U instruction.
-        const int U = gru_u;
-        const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U), idesc_3 = umma_idesc_bf16(3 * U);
-        const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
-        if (kb < t.nka0) {   // h part
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, (kb | k) != 0);
-            umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb | k) != 0);
-          }
-        } else {             // z part
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (kb == t.nka0 && k == 0) {
-              umma_bf16(c.tmem, adesc, bdesc, idesc_rz, 1u);
-              umma_bf16(c.tmem + 2 * U, adesc, bdesc_n, idesc_n, 0u);
-            } else {
-              umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_3, 1u);
-            }
-          }
-        }
-      }
-    }
-    umma_commit(&c.empty[s]);
-    if (st == n_st - 1 && t.lsig) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;\n" ::"l"(t.lsig), "r"(1u) : "memory");   // every operand of the tile is in shared memory
-  }
-  umma_commit(c.tmem_full);
-}
-
-// gru_u = 0: plain N = bn accumulator.  pre(tid) runs on the EPI_THREADS epilogue threads while the main loop is in flight,
+// GRU_U = 0: plain N = bn accumulator.  pre(tid) runs on the EPI_THREADS epilogue threads while the main loop is in flight,
 // epilogue(tid) between the accumulator-complete wait and the publication of the tile.
 template <int GRU_U, class Pre, class Epi>
 __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = t.nka0 + t.nka1;
-  const int n_st = (nk + t.kps - 1) / t.kps;
+  const int kps = t.kps;
+  const int n_st = (nk + kps - 1) / kps;
+  const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;   // one k-block: [A 16 KB | B]
   if (warp == 0) {
-    if (lane == 0) ps_produce(c, t);
+    if (lane == 0) {
+      if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
+      // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
+      // pre-filled while waiting; otherwise A and B of a stage are issued together
+      const int tx_sub = sub_bytes;
+      auto load_b = [&](uint32_t s, int u, int kb) {
+        uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES;
+        tma_load_2d(sb, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
+        if (t.tmB2) tma_load_2d(sb + t.n1 * BK * 2, t.tmB2, (kb + t.b2_koff) * BK, t.b2_row, &c.full[s]);
+      };
+      auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
+        int st = st0;
+        if (w != nullptr || gte != nullptr) {
+          const int npre = min(st1 - st0, PS_STAGES);
+          for (; st < st0 + npre; ++st) {
+            const uint32_t i = c.it + st, s = i % PS_STAGES;
+            ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+            const int n_sub = min(kps, nk - st * kps);
+            mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
+            for (int u = 0; u < n_sub; ++u) load_b(s, u, st * kps + u);
+          }
+          ps_flag_wait(gte, tg, c.dbg, t.code | (6u << 20));
+          ps_flag_wait(w, tw, c.dbg, t.code | (2u << 20));
+          fence_proxy_async_all();   // the A operand was written through the generic proxy by another SM: order it before the TMA reads
+          if (mark && c.tr) c.tr[2] = ps_now();
+          for (int s2 = st0; s2 < st0 + npre; ++s2) {
+            const uint32_t s = (c.it + s2) % PS_STAGES;
+            const int n_sub = min(kps, nk - s2 * kps);
+            for (int u = 0; u < n_sub; ++u)
+              tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
+          }
+        } else if (mark) {
+          fence_proxy_async_all();   // (dependency already resolved by a cluster barrier / program order)
+          if (c.tr) c.tr[2] = ps_now();
+        }
+        for (; st < st1; ++st) {
+          const uint32_t i = c.it + st, s = i % PS_STAGES;
+          ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
+          const int n_sub = min(kps, nk - st * kps);
+          mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
+          for (int u = 0; u < n_sub; ++u) {
+            const int kb = st * kps + u, ka = ps_ka(t, kb);
+            tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ka * BK, t.a_row, &c.full[s]);
+            load_b(s, u, kb);
+          }
+        }
+      };
+      if (t.w1 != nullptr || t.g1 != nullptr) {   // two separately released k ranges (kps == 1)
+        issue(0, t.nka0, t.w0, t.t0, t.g0, t.gt0, true);
+        issue(t.nka0, nk, t.w1, t.t1, t.g1, t.gt1, false);
+      } else {
+        issue(0, n_st, t.w0, t.t0, t.g0, t.gt0, true);
+      }
+    }
   } else if (warp == 1) {
-    if (lane == 0) ps_issue_mma(c, t, GRU_U);
+    if (lane == 0) {
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t i = c.it + st, s = i % PS_STAGES;
+        ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
+        tc_fence_after();
+        if (c.tr && st == 0) c.tr[3] = ps_now();
+        const int n_sub = min(kps, nk - st * kps);
+        for (int u = 0; u < n_sub; ++u) {
+          const int kb = st * kps + u;
+          const uint32_t a_addr = smem_u32(c.smem + s * t.stage_bytes + u * sub_bytes);
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          if constexpr (GRU_U == 0) {
+            const uint32_t idesc = umma_idesc_bf16(t.bn);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(c.tmem + t.tcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k | t.acc0) != 0);
+          } else {
+            // TMEM columns [r | z | n_x | n_h]: z k-blocks feed r, z, n_x in one N = 3U MMA; h k-blocks feed r, z (N = 2U) and n_h (N = U).
+            // The h part comes first (h_j is there long before z_j): the very first z MMA must START n_x while ADDING to r, z, so it is
+            // issued as an N = 2U and an N = U instruction.
+            constexpr int U = GRU_U;
+            const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U), idesc_3 = umma_idesc_bf16(3 * U);
+            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            if (kb < t.nka0) {   // h part
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, (kb | k) != 0);
+                umma_bf16(c.tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb | k) != 0);
+              }
+            } else {             // z part
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                if (kb == t.nka0 && k == 0) {
+                  umma_bf16(c.tmem, adesc, bdesc, idesc_rz, 1u);
+                  umma_bf16(c.tmem + 2 * U, adesc, bdesc_n, idesc_n, 0u);
+                } else {
+                  umma_bf16(c.tmem, adesc + 2 * k, bdesc + 2 * k, idesc_3, 1u);
+                }
+              }
+            }
+          }
+        }
+        umma_commit(&c.empty[s]);
+        if (st == n_st - 1 && t.lsig) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;\n" ::"l"(t.lsig), "r"(1u) : "memory");   // every operand of the tile is in shared memory
+      }
+      umma_commit(c.tmem_full);
+    }
   } else {
     const int tid = (int)threadIdx.x - 64;
     if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 128) = c.tr ? c.tr + c.lap_off : nullptr;
