@@ -528,6 +528,7 @@ struct PsActorOut {
       float t[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) t[k] = (xact[(0 * 128 + row) * 8 + k] + xact[(1 * 128 + row) * 8 + k]) + (xact[(2 * 128 + row) * 8 + k] + xact[(3 * 128 + row) * 8 + k]);
+      ps_lap(sm, tid, 4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < A) {
@@ -546,8 +547,10 @@ struct PsActorOut {
           if (k < 3) av[k] = ak;
         }
       }
+      ps_lap(sm, tid, 5);
       const unsigned long long rec = (unsigned long long)pack_bf16x2(av[0], av[1]) | ((unsigned long long)(pack_bf16x2(av[2], 0.f) & 0xFFFFu) << 32) | (1ull << 48);
       asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(apack + m), "l"(rec) : "memory");
+      ps_lap(sm, tid, 6);
     }
   }
 };

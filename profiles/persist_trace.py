@@ -61,11 +61,11 @@ for t_start, kind, layer, j, m, cta, ts, lp in sorted(rows):
     if kind == 3:
         gru_done.setdefault(j, []).append(rel)
         if cta % 8 == 0 and any(lp):
-            print(f"  gru cta {cta} j={j} laps(vs acc) " + " ".join(f"{(x - ts[4]) / 1e3:.2f}" for x in lp if x))
+            print(f"  gru cta {cta} j={j} acc {rel[4]:.2f} | action seen, gates done, barrier, copied out (absolute us): " + " ".join(f"{(x - t0) / 1e3:.2f}" for x in lp if x) + f" | published {rel[6]:.2f}")
         continue
     print(f"{name:<18}{cta:>4} " + "".join(f"{x:>8.2f}" if i != 2 else f"{x:>9.2f}" for i, x in enumerate(rel)) +
           f"   {rel[4] - rel[2]:5.2f} {rel[5] - rel[4]:4.2f} {rel[6] - rel[5]:4.2f}" +
-          ("   laps(vs acc) " + " ".join(f"{(x - ts[4]) / 1e3:.2f}" for x in lp if x) if any(lp) else ""))
+          ("   laps(abs) " + " ".join(f"{(x - t0) / 1e3:.2f}" for x in lp if x) if any(lp) else ""))
 for j, lst in sorted(gru_done.items()):
     a = np.array(lst)
     print(f"gru j={j}: {len(lst)} tiles; start {a[:,0].min():.2f}..{a[:,0].max():.2f}  dep {a[:,1].min():.2f}..{a[:,1].max():.2f}  operands {a[:,2].min():.2f}..{a[:,2].max():.2f}  "
