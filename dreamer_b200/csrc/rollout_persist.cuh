@@ -194,13 +194,35 @@ struct EpiGruP {
       *reinterpret_cast<float4*>(hp + r * PITCH + cc) = x;
     }
   }
+  // The accumulator is complete ~2 us before the action of the same state exists (the actor chain is the longer path), so every
+  // TMEM load happens BEFORE the action poll; behind the poll there is only the gate arithmetic, which is MUFU-bound
+  // (16 lanes per clock and SM): r and z share ONE reciprocal (1 / ((1 + e_r)(1 + e_z))), 5 instead of 6 MUFU operations per unit.
+  // The bf16 h columns of the next state (what the chain's TMA loads read) leave first; the fp32 `hidden` output follows after
+  // the tile has been published (post()).
   static __device__ __forceinline__ void run(const Params& p, int n_tile, int M, const float* sm, const float4* wa, const float* hp,
                                              float* tile, uint32_t taddr, int m, int row, int part, int tid) {
     const int u0 = n_tile * U;
     const int m0 = m - row;
     const int nvalid = min(U, p.D - u0);
+    float acc[PASSES][4][UP];
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int c = (ps * EPI_PARTS + part) * UP;
+      tmem_ld8_nowait(taddr + c, acc[ps][0]);
+      tmem_ld8_nowait(taddr + U + c, acc[ps][1]);
+      tmem_ld8_nowait(taddr + 2 * U + c, acc[ps][2]);
+      tmem_ld8_nowait(taddr + 3 * U + c, acc[ps][3]);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int c = (ps * EPI_PARTS + part) * UP;
+#pragma unroll
+      for (int j = 0; j < UP; ++j) acc[ps][3][j] += sm[c + j];   // n_h + b_hn
+    }
     float4 a = make_float4(0.f, 0.f, 0.f, 1.f);
     if (m < M) {   // the action arrives as one 8-byte record per row whose top half-word is the ready tag: no separate flag, no second round trip
+      // (polling with one thread per row + a shared-memory broadcast, or with a __nanosleep back-off, was measured: no faster)
       unsigned long long rec;
       unsigned n = 0;
       unsigned long long t0 = 0;
@@ -218,26 +240,23 @@ struct EpiGruP {
       a.z = __uint_as_float(((unsigned)(rec >> 32) & 0xFFFFu) << 16);
     }
     ps_lap(sm, tid, 0);
-#pragma unroll 1
+#pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
       const int c = (ps * EPI_PARTS + part) * UP;
-      float r_[UP], z_[UP], nx[UP], nh[UP];
-      tmem_ld8_nowait(taddr + c, r_);
-      tmem_ld8_nowait(taddr + U + c, z_);
-      tmem_ld8_nowait(taddr + 2 * U + c, nx);
-      tmem_ld8_nowait(taddr + 3 * U + c, nh);
-      tmem_ld_wait();
       float hn[UP];
 #pragma unroll
       for (int j = 0; j < UP; ++j) {
         const float4 wr = wa[c + j], wz = wa[U + c + j], wn = wa[2 * U + c + j];
-        const float ar = fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, wr.w)));   // action term + bias
-        const float az = fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, wz.w)));
-        const float an = fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, wn.w)));
-        const float rr = sigmoidf_(r_[j] + ar);
-        const float zz = sigmoidf_(z_[j] + az);
-        const float nn = tanhf_(nx[j] + an + rr * (nh[j] + sm[c + j]));
-        hn[j] = (1.0f - zz) * nn + zz * hp[row * PITCH + c + j];
+        const float xr = acc[ps][0][j] + fmaf(a.x, wr.x, fmaf(a.y, wr.y, fmaf(a.z, wr.z, wr.w)));   // + action term + bias
+        const float xz = acc[ps][1][j] + fmaf(a.x, wz.x, fmaf(a.y, wz.y, fmaf(a.z, wz.z, wz.w)));
+        const float xn = acc[ps][2][j] + fmaf(a.x, wn.x, fmaf(a.y, wn.y, fmaf(a.z, wn.z, wn.w)));
+        // (the exponent is capped so that the product of the two denominators stays finite; sigmoid(-41) is 0 in fp32 arithmetic anyway)
+        const float dr = 1.0f + ex2f_(fminf(-1.4426950408889634f * xr, 60.0f));
+        const float dz = 1.0f + ex2f_(fminf(-1.4426950408889634f * xz, 60.0f));
+        const float inv = rcpf_(dr * dz);
+        const float rr = inv * dz, zz = inv * dr;
+        const float nn = tanhf_(fmaf(rr, acc[ps][3][j], xn));
+        hn[j] = fmaf(zz, hp[row * PITCH + c + j] - nn, nn);
       }
       tile_put<UP>(tile, PITCH, row, c, hn);
     }
@@ -246,8 +265,12 @@ struct EpiGruP {
     // 2.1 + 1.3 us through the transposed tile, so the coalesced copy-out stays)
     epi_bar_sync();
     ps_lap(sm, tid, 2);
-    tile_copy_out(tile, PITCH, U, nvalid, m0, M, p.h_out + u0, p.ld_h, p.s_h + u0, p.ld_s, tid);
+    tile_copy_out(tile, PITCH, U, nvalid, m0, M, nullptr, 0, p.s_h + u0, p.ld_s, tid);
     ps_lap(sm, tid, 3);
+  }
+  static __device__ __forceinline__ void post(const Params& p, int n_tile, int M, const float* tile, int m0, int tid) {
+    const int u0 = n_tile * U;
+    tile_copy_out(tile, PITCH, U, min(U, p.D - u0), m0, M, p.h_out + u0, p.ld_h, nullptr, 0, tid);
   }
 };
 
@@ -524,32 +547,39 @@ struct PsActorOut {
     ps_lap(sm, tid, 3);
     if (m < M) {
       const float* xact = x.xact;
-      float av[3] = {0.f, 0.f, 0.f};
       float t[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) t[k] = (xact[(0 * 128 + row) * 8 + k] + xact[(1 * 128 + row) * 8 + k]) + (xact[(2 * 128 + row) * 8 + k] + xact[(3 * 128 + row) * 8 + k]);
       ps_lap(sm, tid, 4);
+      float muv[4], sgv[4], akv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        muv[k] = 0.f; sgv[k] = 0.f; akv[k] = 0.f;
         if (k < A) {
-          const float muv = t[k] + bm[k];
+          muv[k] = t[k] + bm[k];
           float ls = t[A + k] + bl[k];
           ls = fminf(fmaxf(ls, -5.0f), 2.0f);
           // softplus on [-5, 2] and tanh through ex2 / lg2 / rcp (relative error ~1e-6): these 128 threads are the only ones between
           // the last partial sum and the GRU CTAs' wake-up, and libm's expf / log1pf / tanhf are ~150 dependent instructions per action
           float l2;
           asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.0f + fexpf_(ls)));
-          const float sg = fmaf(l2, 0.6931471805599453f, 1e-3f);
-          mu[(long)m * ld_act + k] = muv;
-          sigma[(long)m * ld_act + k] = sg;
-          const float ak = tanhf_(muv + sg * ep[k]);
-          action[(long)m * ld_act + k] = ak;
-          if (k < 3) av[k] = ak;
+          sgv[k] = fmaf(l2, 0.6931471805599453f, 1e-3f);
+          akv[k] = tanhf_(muv[k] + sgv[k] * ep[k]);
         }
       }
       ps_lap(sm, tid, 5);
-      const unsigned long long rec = (unsigned long long)pack_bf16x2(av[0], av[1]) | ((unsigned long long)(pack_bf16x2(av[2], 0.f) & 0xFFFFu) << 32) | (1ull << 48);
+      // the record the GRU CTAs poll goes out FIRST: the 9 row-strided output stores below are 32 sectors per warp instruction and
+      // would sit in front of it in the store pipe
+      const unsigned long long rec = (unsigned long long)pack_bf16x2(akv[0], akv[1]) | ((unsigned long long)(pack_bf16x2(akv[2], 0.f) & 0xFFFFu) << 32) | (1ull << 48);
       asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(apack + m), "l"(rec) : "memory");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < A) {
+          mu[(long)m * ld_act + k] = muv[k];
+          sigma[(long)m * ld_act + k] = sgv[k];
+          action[(long)m * ld_act + k] = akv[k];
+        }
+      }
       ps_lap(sm, tid, 6);
     }
   }
@@ -597,8 +627,11 @@ __device__ __forceinline__ int ps_ka(const PsTile& t, int kb) { return kb < t.nk
 
 // GRU_U = 0: plain N = bn accumulator.  pre(tid) runs on the EPI_THREADS epilogue threads while the main loop is in flight,
 // epilogue(tid) between the accumulator-complete wait and the publication of the tile.
+struct PsNoPost { __device__ __forceinline__ void operator()(int) const {} };
 template <int GRU_U, class Pre, class Epi>
-__device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue) {
+__device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue);
+template <int GRU_U, class Pre, class Epi, class Post>
+__device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue, Post&& post) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = t.nka0 + t.nka1;
   const int kps = t.kps;
@@ -728,6 +761,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
         red_release_add(t.sig, 1u);
       }
     }
+    post(tid);   // outputs nobody inside the kernel waits for
     if (!t.chain) fence_proxy_async_all();   // this thread's generic-proxy accesses to the ring / its global stores vs the next tile's TMA traffic
                                              // (chain tiles: the cluster hand-over's release / acquire + the consumer's proxy fence order them)
     if (c.tr && tid == 0) c.tr[7] = ps_now();
@@ -743,6 +777,10 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+}
+template <int GRU_U, class Pre, class Epi>
+__device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre, Epi&& epilogue) {
+  ps_run_tile<GRU_U>(c, t, pre, epilogue, PsNoPost{});
 }
 
 // hand-over between two layers of a chain cluster: every thread of the four CTAs; release / acquire at cluster scope orders the
@@ -946,12 +984,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const EpiGruP<32>::Params p{P.b_ih, P.b_hh, P.hidden + (long)j * D, P.hidden + (long)(j + 1) * D, s_h, ldH, P.KS, D,
                                       P.Wgru + ZP, P.KS, A, P.apack + (long)j * Mp, P.dbg, t.code};
           ps_run_tile<32>(c, t, [&](int tid) { EpiGruP<32>::stage(p, n_tile, m0, B, epi_sm, wa, hp_tile, tid); },
-                          [&](int tid) { EpiGruP<32>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); });
+                          [&](int tid) { EpiGruP<32>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); },
+                          [&](int tid) { EpiGruP<32>::post(p, n_tile, B, tile, m0, tid); });
         } else {
           const EpiGruP<64>::Params p{P.b_ih, P.b_hh, P.hidden + (long)j * D, P.hidden + (long)(j + 1) * D, s_h, ldH, P.KS, D,
                                       P.Wgru + ZP, P.KS, A, P.apack + (long)j * Mp, P.dbg, t.code};
           ps_run_tile<64>(c, t, [&](int tid) { EpiGruP<64>::stage(p, n_tile, m0, B, epi_sm, wa, hp_tile, tid); },
-                          [&](int tid) { EpiGruP<64>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); });
+                          [&](int tid) { EpiGruP<64>::run(p, n_tile, B, epi_sm, wa, hp_tile, tile, taddr, m, row, part, tid); },
+                          [&](int tid) { EpiGruP<64>::post(p, n_tile, B, tile, m0, tid); });
         }
       }
     }
