@@ -72,6 +72,65 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return DRM_OK;
 }
 
+// 2D bf16 tensor map with a narrower inner box: box {inner, box_rows}, swizzle span = inner * 2 bytes (inner = 16 / 32 / 64 elements).
+// Weights of the implicit-GEMM convolutions whose k-block is one tap of <= 64 channels.
+int make_tmap_bf16_2d_inner(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                            uint32_t inner) {
+  auto fn = encode_fn();
+  if (!fn) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (((uintptr_t)base & 15u) || ((ld_elems * 2) & 15u)) return fail(DRM_ERR_ALIGN, "tensor map base / pitch must be 16-byte aligned");
+  if (box_rows == 0 || box_rows > 256) return fail(DRM_ERR_SHAPE, "tensor map box rows must be in [1, 256]");
+  if (inner != 16 && inner != 32 && inner != 64) return fail(DRM_ERR_SHAPE, "tensor map inner box must be 16, 32 or 64 elements");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return DRM_OK;
+}
+
+static PFN_cuTensorMapEncodeIm2col_v12000 encode_im2col_fn() {
+  static PFN_cuTensorMapEncodeIm2col_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(p);
+  });
+  return fn;
+}
+
+// im2col-mode tensor map over an NHWC bf16 activation [N, H, W, C]: one load delivers `pixels` consecutive filter positions (W, then
+// H, then N; traversal stride `stride`) x `chunk` channels of ONE filter tap -- the A operand of an implicit-GEMM k-block, straight
+// from the activation (no patch matrix).  The base pixel of a filter position ranges over [lower, extent - 1 + upper] per axis;
+// positions outside the image read zeros.
+int make_tmap_im2col_bf16(CUtensorMap* tm, const void* base, uint32_t C, uint32_t W, uint32_t H, uint32_t N, int lower_w, int lower_h,
+                          int upper_w, int upper_h, uint32_t chunk, uint32_t pixels, uint32_t stride) {
+  auto fn = encode_im2col_fn();
+  if (!fn) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+  if (((uintptr_t)base & 15u) || ((C * 2) & 15u)) return fail(DRM_ERR_ALIGN, "im2col tensor map base / channel pitch must be 16-byte aligned");
+  if (chunk != 16 && chunk != 32 && chunk != 64) return fail(DRM_ERR_SHAPE, "im2col tensor map: channels per load must be 16, 32 or 64");
+  if (pixels == 0 || pixels > 1024 || stride == 0 || stride > 8) return fail(DRM_ERR_SHAPE, "im2col tensor map: bad pixel count / stride");
+  cuuint64_t gdim[4] = {C, W, H, N};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
+  const CUtensorMapSwizzle sw = chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, lower, upper, chunk, pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
+  // Drivers up to CUDA 13.1 set a descriptor bit for tensors below 128 KB that im2col loads must not see (the same correction
+  // CUTLASS applies in make_im2col_tma_copy_desc).
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (uint64_t)N * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return DRM_OK;
+}
+
 // ---- per-stage event timing ---------------------------------------------------------------
 static bool g_profile = false;
 static std::mutex g_prof_mu;

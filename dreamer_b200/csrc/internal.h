@@ -49,6 +49,12 @@ int check_arch();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
 
+int make_tmap_bf16_2d_inner(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                            uint32_t inner);
+// im2col-mode map over NHWC bf16 [N, H, W, C] (see core.cu)
+int make_tmap_im2col_bf16(CUtensorMap* tm, const void* base, uint32_t C, uint32_t W, uint32_t H, uint32_t N, int lower_w, int lower_h,
+                          int upper_w, int upper_h, uint32_t chunk, uint32_t pixels, uint32_t stride);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -69,6 +69,7 @@ struct Options {
   int ln_cluster = 1;  // LN stages of small grids split over clusters of 4 CTAs
   int gru_ksplit = 1;  // single-m-tile grids split the GRU tile's K range over a 2-CTA cluster
   int conv_persist = 1;  // narrow conv layers on the persistent GEMM
+  int conv_implicit = 1; // conv layers as implicit GEMMs fed by im2col-mode TMA loads (no patch matrix)
   int gru_pair = -1;   // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
   int small_a = 1;     // stages with <= 32 rows load 32-row A boxes
   int gru_u = 0;       // 0: automatic GRU tile width, else 32 / 64
@@ -922,6 +923,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   if (n == "ln_cluster") o.ln_cluster = value != 0;
   else if (n == "small_a") o.small_a = value != 0;
   else if (n == "conv_persist") o.conv_persist = value != 0;
+  else if (n == "conv_implicit") o.conv_implicit = value != 0;
   else if (n == "gru_ksplit") o.gru_ksplit = value != 0;
   else if (n == "persist") o.persist = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
@@ -986,6 +988,68 @@ static int launch_conv_persist(const GemmCommon& g, const EpiPlain::Params& p, i
 }
 static bool use_conv_persist(const GemmCommon& g, const EpiPlain::Params& p) {
   return opts().conv_persist && (g.bn == 32 || g.bn == 64) && p.out_bf16 && !p.out_f32 && g.nka1 == 0 && g.ka0 == 0 && g.a_row0 == 0;
+}
+}  // namespace drm
+
+#include "conv_implicit.cuh"
+namespace drm {
+// One conv / transposed-conv layer as an implicit GEMM (conv_implicit.cuh).  tmA: `phases` im2col maps; (Wo, Ho): filter positions
+// per frame and phase; transposed = the sub-pixel phase decomposition of ConvTranspose2d(k4, s2, p1), else Conv2d(k4, s2, p1).
+static int launch_conv_implicit(const CUtensorMap* tmA, int phases, const CUtensorMap& tmB, int M, int Wo, int Ho, int stride, int n_base,
+                                int ntap, int cpad, int chunk, int bn, const float* bias, __nv_bfloat16* out, long ld, int n_valid, int act,
+                                RowMap rm, bool transposed, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRM_CUDA(cudaFuncSetAttribute(conv_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CI_SMEM));
+    attr_set = true;
+  }
+  ConvImplicit c;
+  memset(&c, 0, sizeof(c));
+  for (int p = 0; p < phases; ++p) c.tmA[p] = tmA[p];
+  c.tmB = tmB;
+  c.M = M; c.n_mtiles = ceil_div(M, BM); c.phases = phases;
+  c.Wo = Wo; c.Ho = Ho; c.stride = stride; c.n_base = n_base;
+  c.ntap = ntap; c.cpt = cpad / chunk; c.chunk = chunk;
+  for (int p = 0; p < phases; ++p) {
+    if (!transposed) {
+      c.lower_w[p] = -1; c.lower_h[p] = -1;
+      for (int t = 0; t < 16; ++t) { c.off_w[p][t] = (unsigned char)(t & 3); c.off_h[p][t] = (unsigned char)(t >> 2); }
+    } else {
+      // phase (py, px): output (2q + py, 2r + px) sums input rows {q, q - 1} (py = 0) or {q, q + 1} (py = 1), weight tap order
+      // (ty, tx) with t = 0 the centre (ct_d in vae.cuh): as a 2-tap window the base row is q - 1 (py = 0) or q (py = 1)
+      const int py = p >> 1, px = p & 1;
+      c.lower_w[p] = px ? 0 : -1; c.lower_h[p] = py ? 0 : -1;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          c.off_h[p][ty * 2 + tx] = (unsigned char)(py ? ty : 1 - ty);
+          c.off_w[p][ty * 2 + tx] = (unsigned char)(px ? tx : 1 - tx);
+        }
+    }
+  }
+  c.bn = bn;
+  c.stage_bytes = round_up(BM * chunk * 2 + bn * chunk * 2, 1024);
+  c.n_stages = std::min(CI_MAX_STAGES, CI_RING_BYTES / c.stage_bytes);
+  c.tmem_cols = 32;
+  while (c.tmem_cols < 2 * bn) c.tmem_cols *= 2;
+  c.bias = bias; c.out = out; c.ld = ld; c.n_valid = n_valid; c.act = act; c.rm = rm;
+  const int n_tiles = c.n_mtiles * phases;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_tiles < 148 ? n_tiles : 148);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = CI_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (!profile_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, conv_implicit_kernel, c));
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
 }
 }  // namespace drm
 

@@ -258,6 +258,8 @@ struct drm_vae {
   __nv_bfloat16 *We[4], *Wef, *Weh, *We3, *Wd1, *Wd2, *Wdc[4];
   float *be[4], *e1_b, *e1_g, *e1_be, *e3_b, *d1_b, *d1_g, *d1_be, *d2_b, *bdc[4];
   CUtensorMap tmWe[4], tmWef, tmWeh, tmWehq, tmWe3, tmWe3h, tmWd1, tmWd1q, tmWd2, tmWdc[4];
+  CUtensorMap tmWeI[4], tmWdcI[4];   // implicit-GEMM twins of tmWe / tmWdc: box {chunk, bn} (conv_implicit.cuh)
+  int echunk[4], dchunk[4];          // channels per k-block of encoder conv i / decoder convT j (0: layer stays on the patch path)
   std::vector<drm::OffOp> mat_ops;
   std::vector<drm::VecOp> vec_ops;
   std::vector<void*> allocs;
@@ -271,6 +273,9 @@ struct drm_observe {
   __nv_bfloat16 *S, *Y1, *Y2, *feat, *dec0, *patch, *actA, *actB;
   float *zero_h, *featpart;
   CUtensorMap tmS, tmY1, tmY2, tmFeat, tmPatchE[4], tmPatchD[4];
+  CUtensorMap tmI2cE[4];       // im2col maps over the NHWC input of encoder conv i (i = 1 .. 3)
+  CUtensorMap tmI2cD[4][4];    // ... of decoder convT j (j = 0 .. 2), one per sub-pixel phase
+  bool i2cE[4] = {false, false, false, false}, i2cD[4] = {false, false, false, false};   // the layer has its im2col map(s)
   CUtensorMap tmS_s, tmY1_s, tmY2_s;   // short-box twins (SMALL_A_ROWS rows) for steps with few sequences
   long patch_elems, act_elems;
   std::vector<void*> allocs;
@@ -410,6 +415,17 @@ extern "C" int drm_vae_create(drm_rssm* m, const drm_vae_dims* dims, drm_vae** o
     TRY(make_tmap_bf16_2d(&v->tmWe[i], v->We[i], v->ebn[i + 1], v->EK[i], v->EK[i], v->ebn[i + 1]));
     TRY(make_tmap_bf16_2d(&v->tmWdc[i], v->Wdc[i], 4 * v->dbn[i + 1], v->DK[i], v->DK[i], v->dbn[i + 1]));
   }
+  // implicit-GEMM layers: k-block = one tap x `chunk` channels; the output width must suit conv_implicit_kernel's epilogue
+  auto chunk_of = [](int cpad, int bn) {
+    if (bn % 16 || bn > 256 || (bn < 64 && bn != 16 && bn != 32)) return 0;
+    return cpad % 64 == 0 ? 64 : (cpad % 32 == 0 ? 32 : 16);
+  };
+  for (int i = 0; i < 4; ++i) {
+    v->echunk[i] = i == 0 ? 0 : chunk_of(v->ebn[i], v->ebn[i + 1]);   // (layer 0 reads fp32 NCHW frames: im2col_first_kernel)
+    v->dchunk[i] = i == 3 ? 0 : chunk_of(v->dbn[i], v->dbn[i + 1]);   // (image layer: convt_last_direct_kernel)
+    if (v->echunk[i]) TRY(make_tmap_bf16_2d_inner(&v->tmWeI[i], v->We[i], v->ebn[i + 1], v->EK[i], v->EK[i], v->ebn[i + 1], v->echunk[i]));
+    if (v->dchunk[i]) TRY(make_tmap_bf16_2d_inner(&v->tmWdcI[i], v->Wdc[i], 4 * v->dbn[i + 1], v->DK[i], v->DK[i], v->dbn[i + 1], v->dchunk[i]));
+  }
   TRY(make_tmap_bf16_2d(&v->tmWef, v->Wef, v->bn_he, v->Kf, v->Kf, v->bn_he));
   TRY(make_tmap_bf16_2d(&v->tmWeh, v->Weh, 256, DP, DP, v->bn_he));
   TRY(make_tmap_bf16_2d(&v->tmWehq, v->Weh, 256, DP, DP, 64));
@@ -485,7 +501,7 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
     }
   }
   o->patch_elems = pe + 128l * 4096;   // slack: TMA boxes of the last tile may read past the valid rows
-  o->act_elems = ae + 128l * 256;
+  o->act_elems = ae + 130l * 64 * 256;   // slack: an im2col tile may walk up to 128 filter positions past the chunk's last frame
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
   TRY(dev_alloc(o->allocs, &o->S, (size_t)o->rows_p * m->KS));
@@ -509,6 +525,31 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
     TRY(make_tmap_bf16_2d(&o->tmPatchE[i], o->patch, (uint64_t)(o->patch_elems / v->EK[i]), v->EK[i], v->EK[i], BM));
     TRY(make_tmap_bf16_2d(&o->tmPatchD[i], o->patch, (uint64_t)(o->patch_elems / v->DK[i]), v->DK[i], v->DK[i], BM));
   }
+  {
+    // im2col maps: frames mapped = chunk + the frames a last partial tile can reach (never stored, only read)
+    int hs = H / 2, ws = W / 2;      // input grid of encoder conv 1
+    for (int i = 1; i < 4; ++i) {
+      const int extra = ceil_div(BM, (hs / 2) * (ws / 2)) + 1;
+      if (v->echunk[i] && (long)(o->FC + extra) * hs * ws * v->ebn[i] <= o->act_elems) {
+        TRY(make_tmap_im2col_bf16(&o->tmI2cE[i], (i & 1) ? o->actA : o->actB, v->ebn[i], ws, hs, o->FC + extra, -1, -1, -2, -2, v->echunk[i], BM, 2));
+        o->i2cE[i] = rc == DRM_OK;
+      }
+      hs >>= 1; ws >>= 1;
+    }
+    hs = H / 16; ws = W / 16;        // input grid of decoder convT 0
+    for (int j = 0; j < 3; ++j) {
+      const int extra = ceil_div(BM, hs * ws) + 1;
+      const __nv_bfloat16* base = j == 0 ? o->dec0 : (j == 1 ? o->actA : o->actB);
+      const int nfr = j == 0 ? NF + extra : o->FC + extra;
+      const bool fits = j == 0 ? extra <= BM : (long)nfr * hs * ws * v->dbn[j] <= o->act_elems;
+      for (int ph = 0; ph < 4 && v->dchunk[j] && fits; ++ph) {
+        const int lw = (ph & 1) ? 0 : -1, lh = (ph >> 1) ? 0 : -1;
+        TRY(make_tmap_im2col_bf16(&o->tmI2cD[j][ph], base, v->dbn[j], ws, hs, nfr, lw, lh, lw, lh, v->dchunk[j], BM, 1));
+        o->i2cD[j] = rc == DRM_OK;
+      }
+      hs <<= 1; ws <<= 1;
+    }
+  }
 #undef TRY
   if (rc != DRM_OK) { drm_observe_destroy(o); return rc; }
   *out = o;
@@ -524,6 +565,19 @@ extern "C" int drm_observe_destroy(drm_observe* o) {
 
 namespace drm {
 
+// patch rows of encoder conv i + 1 from the NHWC output `cur` (grid hs x ws) of conv i -- only for layers that stay on the patch path
+static int encoder_patch_gather(drm_observe* o, const __nv_bfloat16* cur, int nf, int hs, int ws, int i, cudaStream_t st) {
+  drm_vae* v = o->v;
+  Taps4 tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.t[0].n = 16;
+  for (int t = 0; t < 16; ++t) { tp.t[0].dy[t] = (t >> 2) - 1; tp.t[0].dx[t] = (t & 3) - 1; }
+  const long rows = (long)nf * (hs / 2) * (ws / 2);
+  patch_gather_kernel<<<dim3(grid_for(rows * 16 * (v->ebn[i + 1] / 8)), 1), 256, 0, st>>>(cur, o->patch, rows, hs, ws, v->ebn[i + 1], hs / 2, ws / 2, 2, tp, 0, v->EK[i + 1]);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
 // Encoder convs over frames [f0, f0 + nf) -> o->feat rows [f0, f0 + nf).  tm = 1: frame n of the (time-major)
 // feature matrix is obs[b = n % B, t = n / B]; tm = 0: frames in the given order.
 static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, int tm, cudaStream_t st) {
@@ -536,6 +590,18 @@ static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, 
   __nv_bfloat16* nxt = o->actB;
   for (int i = 0; i < 4; ++i) {
     const int M = nf * hs * ws;
+    const bool implicit_next = i < 3 && o->i2cE[i + 1] && opts().conv_implicit;
+    if (i > 0 && o->i2cE[i] && opts().conv_implicit) {
+      // implicit GEMM: the A operand comes straight from the previous layer's NHWC output (cur was swapped: the input is `nxt`)
+      __nv_bfloat16* dst = i == 3 ? o->feat + (long)f0 * v->Kf : cur;
+      RC(launch_conv_implicit(&o->tmI2cE[i], 1, v->tmWeI[i], M, ws, hs, 2, 0, 16, v->ebn[i], v->echunk[i], v->ebn[i + 1], v->be[i], dst,
+                              (long)v->ebn[i + 1], v->ebn[i + 1], 1, RowMap{0, 0, 0, 0}, false, st));
+      if (i == 3) break;
+      if (!implicit_next) RC(encoder_patch_gather(o, cur, nf, hs, ws, i, st));
+      hs >>= 1; ws >>= 1;
+      std::swap(cur, nxt);
+      continue;
+    }
     GemmCommon g = common(o->tmPatchE[i], v->tmWe[i], M, v->ebn[i + 1]);
     g.ka0 = 0; g.nka0 = v->EK[i] / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
@@ -545,13 +611,7 @@ static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, 
     else if (v->ebn[i + 1] <= 64 && !env_off("DRM_NO_PLAIN_S", 0)) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div(M, BM), 1), st));
     if (i == 3) break;
-    Taps4 tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.t[0].n = 16;
-    for (int t = 0; t < 16; ++t) { tp.t[0].dy[t] = (t >> 2) - 1; tp.t[0].dx[t] = (t & 3) - 1; }
-    const long rows = (long)nf * (hs / 2) * (ws / 2);
-    patch_gather_kernel<<<dim3(grid_for(rows * 16 * (v->ebn[i + 1] / 8)), 1), 256, 0, st>>>(cur, o->patch, rows, hs, ws, v->ebn[i + 1], hs / 2, ws / 2, 2, tp, 0, v->EK[i + 1]);
-    DRM_LAUNCH_CHECK();
+    if (!implicit_next) RC(encoder_patch_gather(o, cur, nf, hs, ws, i, st));
     hs >>= 1; ws >>= 1;
     std::swap(cur, nxt);
   }
@@ -583,9 +643,18 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
       DRM_LAUNCH_CHECK();
       break;
     }
+    __nv_bfloat16* dst = bufs[j & 1];
+    if (j < 3 && o->i2cD[j] && opts().conv_implicit) {
+      // implicit GEMM: four sub-pixel phases read the NHWC input through their im2col maps, no patch matrix
+      const int n_base = j == 0 ? (int)((act0 - o->dec0) / ((long)v->hw4 * v->dbn[0])) : 0;
+      RC(launch_conv_implicit(o->tmI2cD[j], 4, v->tmWdcI[j], (int)rows, ws, hs, 1, n_base, 4, v->dbn[j], v->dchunk[j], v->dbn[j + 1], v->bdc[j],
+                              dst, (long)v->dbn[j + 1], v->dbn[j + 1], 1, RowMap{2, hs, ws, 0}, true, st));
+      hs <<= 1; ws <<= 1;
+      src = dst;
+      continue;
+    }
     patch_gather_kernel<<<dim3(grid_for(rows * 4 * (v->dbn[j] / 8)), 4), 256, 0, st>>>(src, o->patch, rows, hs, ws, v->dbn[j], hs, ws, 1, tp, rows, v->DK[j]);
     DRM_LAUNCH_CHECK();
-    __nv_bfloat16* dst = bufs[j & 1];
     GemmCommon g = common(o->tmPatchD[j], v->tmWdc[j], (int)rows, v->dbn[j + 1]);
     g.a_y_stride = (int)rows;
     g.ka0 = 0; g.nka0 = v->DK[j] / 64;

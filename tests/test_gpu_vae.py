@@ -156,12 +156,41 @@ def test_persistent_conv_gemm_is_bit_identical_to_one_tile_per_cta(ops):
         z = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device=DEV, generator=g), 32).float().reshape(N, 1024)
         outs = []
         try:
+            L.check(lib.drm_set_option(b"conv_implicit", 0), "set_option")   # (the patch-matrix path is the one with the two GEMM variants)
             for flag in (1, 0):
                 L.check(lib.drm_set_option(b"conv_persist", flag), "set_option")
                 outs.append((ws.encode(h, obs)["logits"].clone(), ws.decode(h, z).clone()))
         finally:
             lib.drm_set_option(b"conv_persist", 1)
+            lib.drm_set_option(b"conv_implicit", 1)
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), name
+
+
+@pytest.mark.parametrize("name,N", [("small", 5), ("small", 37), ("ref", 9), ("ref", 300), ("ref", 700)])
+def test_implicit_gemm_convs_are_bit_identical_to_the_patch_matrix_path(ops, name, N):
+    """Option "conv_implicit" (default on): conv / transposed-conv layers whose A operand is fetched by im2col-mode TMA loads
+    straight from the NHWC activation (VariationalAutoEncoder.py:33-42, 128-137) versus patch gather + GEMM.  Same bf16 operands,
+    same (tap, channel) K order, fp32 accumulation in the same order: logits and images must agree bit for bit -- including the
+    zero padding ring, tiles that span image rows / frames, a partial last tile and (700 frames) two conv chunks."""
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    cfg = CFGS[name]
+    _, _, vae = _build(ops, cfg, 17)
+    ws = ops.Observe(vae, N, 1)
+    g = torch.Generator(device="cuda").manual_seed(N)
+    h = torch.tanh(torch.randn(N, cfg["hidden_state_dims"], device=DEV, generator=g))
+    obs = torch.rand(N, 3, 64, 64, device=DEV, generator=g) - 0.5
+    z = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device=DEV, generator=g), 32).float().reshape(N, 1024)
+    outs = []
+    try:
+        for flag in (1, 0):
+            L.check(lib.drm_set_option(b"conv_implicit", flag), "set_option")
+            outs.append((ws.encode(h, obs)["logits"].clone(), ws.decode(h, z).clone()))
+    finally:
+        lib.drm_set_option(b"conv_implicit", 1)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    assert torch.equal(outs[0][0], outs[1][0]), f"encoder logits differ: max {(outs[0][0] - outs[1][0]).abs().max().item()}"
+    assert torch.equal(outs[0][1], outs[1][1]), f"decoder images differ: max {(outs[0][1] - outs[1][1]).abs().max().item()}"
 
 
 def test_ksplit_gru_scan_agrees_with_single_cta_scan(ops):
