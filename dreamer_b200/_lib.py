@@ -84,6 +84,7 @@ SIGNATURES = {
     "drm_rollout_run": (C.c_int, [C.c_void_p] * 13 + [c_stream]),
     "drm_rollout_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "drm_rollout_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "drm_observe_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "drm_gru_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, c_stream]),
     "drm_prior": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, c_stream]),
     "drm_heads": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.POINTER(DrmHeadsOut), C.c_int32, c_stream]),

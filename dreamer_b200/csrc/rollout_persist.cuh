@@ -33,7 +33,8 @@
 
 namespace drm {
 
-constexpr int PS_STAGES = 4;
+constexpr int PS_STAGES = 4;                                       // ring depth at the full 48 KB stage
+constexpr int PS_MAX_STAGES = 8;                                   // ring depth with smaller stages (barrier slots)
 constexpr int PS_STAGE_BYTES = A_STAGE_BYTES + 256 * BK * 2;       // 48 KB: A tile + up to 256 weight rows per k-block
 constexpr int PS_RING_BYTES = PS_STAGES * PS_STAGE_BYTES;          // 192 KB
 constexpr int PS_GRU_STAGE_BYTES = A_STAGE_BYTES + 192 * BK * 2;   // 40 KB: GRU CTAs (<= 192 weight rows per k-block)
@@ -133,10 +134,10 @@ __device__ __forceinline__ void ps_mbar_wait(uint64_t* bar, uint32_t parity, uns
 }
 
 // debug laps inside an epilogue (thread tid == 0 only): the current tile's lap record (8 x u64) is published in shared memory
-// 128 bytes below the epilogue scratch; NULL when tracing is off
+// 64 bytes below the epilogue scratch; NULL when tracing is off
 __device__ __forceinline__ void ps_lap(const float* epi_sm, int tid, int k) {
   if (tid != 0) return;
-  unsigned long long* lap = *reinterpret_cast<unsigned long long* const*>(reinterpret_cast<const uint8_t*>(epi_sm) - 128);
+  unsigned long long* lap = *reinterpret_cast<unsigned long long* const*>(reinterpret_cast<const uint8_t*>(epi_sm) - 64);
   if (lap) lap[k] = ps_now();
 }
 
@@ -161,8 +162,9 @@ struct EpiGruP {
     int ld_s, D;
     const __nv_bfloat16* w_a; // packed GRU weights, first action column (row pitch ldw)
     int ldw, A;
-    const unsigned long long* apack;   // [M] action records of this state {bf16 a0, a1, a2, tag}: polled until the tag is set
+    const unsigned long long* apack;   // [M] action records of this state {bf16 a0, a1, a2, tag}: polled until the tag is set; NULL: the action is in the MMA
     unsigned* dbg; unsigned code;
+    long ld_prev;             // row pitch of h_prev when it differs from ld_h (0: the same)
   };
   // b_hn -> sm[U];  action weights + biases -> wa[3U] float4 {w_a0, w_a1, w_a2, bias};  h_prev tile -> hp (pitch U + 4)
   static __device__ __forceinline__ void stage(const Params& p, int n_tile, int m0, int M, float* sm, float4* wa, float* hp, int tid) {
@@ -187,7 +189,7 @@ struct EpiGruP {
       const int r = i / (U / 4), cc = (i % (U / 4)) * 4;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m0 + r < M && cc < nvalid) {
-        const float* src = p.h_prev + (long)(m0 + r) * p.ld_h + u0 + cc;
+        const float* src = p.h_prev + (long)(m0 + r) * (p.ld_prev ? p.ld_prev : p.ld_h) + u0 + cc;
         if (cc + 4 <= nvalid && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) x = __ldcg(reinterpret_cast<const float4*>(src));
         else { x.x = __ldcg(src); if (cc + 1 < nvalid) x.y = __ldcg(src + 1); if (cc + 2 < nvalid) x.z = __ldcg(src + 2); if (cc + 3 < nvalid) x.w = __ldcg(src + 3); }
       }
@@ -221,7 +223,7 @@ struct EpiGruP {
       for (int j = 0; j < UP; ++j) acc[ps][3][j] += sm[c + j];   // n_h + b_hn
     }
     float4 a = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (m < M) {   // the action arrives as one 8-byte record per row whose top half-word is the ready tag: no separate flag, no second round trip
+    if (m < M && p.apack != nullptr) {   // the action arrives as one 8-byte record per row whose top half-word is the ready tag: no separate flag, no second round trip
       // (polling with one thread per row + a shared-memory broadcast, or with a __nanosleep back-off, was measured: no faster)
       unsigned long long rec;
       unsigned n = 0;
@@ -309,8 +311,9 @@ struct PsXchg {
 };
 
 // EpiLnSiluN4T<false>::compute with the statistics exchanged by st.async + mbarrier
+// addv: 16 values added to the pre-activation before the statistics (the posterior's hoisted feature part), or nullptr
 __device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const TileG& g, float* sm, PsXchg& x, uint32_t taddr, int m, int row,
-                                              int part, int slot, int tid, unsigned code, float (&v)[16]) {
+                                              int part, int slot, int tid, unsigned code, float (&v)[16], const float* addv = nullptr) {
   const int nv = p.n_valid;
   const int cr = (int)cluster_ctarank();
   const int c0 = part * 16;
@@ -328,6 +331,10 @@ __device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const 
       const float4 t = b4[j];
       v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
     }
+  }
+  if (addv) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += addv[j];
   }
   const float shift = v[0];
   float s1 = 0.f, s2 = 0.f;
@@ -415,6 +422,11 @@ struct EpiCatP {
       float v[32];
       tmem_ld32(taddr + gi * 32, v);
       add_const32(v, sm + gi * 32);
+      if (p.logits && m < g.M && gi * 32 < ncols) {   // posterior logits of the observe scan: 128 contiguous bytes per thread, whole sectors
+        float4* lg = reinterpret_cast<float4*>(p.logits + (long)m * p.ld_logits + col0 + gi * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lg[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
@@ -592,6 +604,7 @@ struct PsCtx {
   uint8_t* smem;
   uint64_t *full, *empty, *tmem_full;
   uint32_t tmem;
+  uint32_t ns;        // ring depth of this CTA (constant for its whole life: the ring's phase bookkeeping runs across tiles)
   uint32_t it;        // pipeline stages issued so far (ring position / phase), identical in every thread
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
   unsigned* dbg;
@@ -611,6 +624,8 @@ struct PsTile {
   int acc0;                   // 1: the accumulator already holds a partial sum (the first MMA accumulates)
   int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
   int stage_bytes;            // ring stride of this CTA's role
+  int a_bytes;                // shared-memory bytes of the A part of a k-block (A_STAGE_BYTES, or less with a short-box tensor map)
+  int a_tx;                   // bytes one A load delivers (A_STAGE_BYTES; less with a short-box tensor map: the tile's tail rows stay stale and are never stored)
   int cbar;                   // cluster barriers the epilogue executes (the producer / MMA warps mirror them)
   int chain;                  // 1: a cluster hand-over follows this tile
   const unsigned* w0; unsigned t0;     // data dependency of the first A k-block range (NULL: resolved by a barrier / program order)
@@ -636,25 +651,26 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   const int nk = t.nka0 + t.nka1;
   const int kps = t.kps;
   const int n_st = (nk + kps - 1) / kps;
-  const int sub_bytes = A_STAGE_BYTES + t.bn * BK * 2;   // one k-block: [A 16 KB | B]
+  const int sub_bytes = t.a_bytes + t.bn * BK * 2;   // one k-block: [A | B]
+  const uint32_t NS = c.ns;
   if (warp == 0) {
     if (lane == 0) {
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
       // issue pipeline stages [st0, st1): with an open dependency / gate the weights go first (they depend on nothing), so the ring is
       // pre-filled while waiting; otherwise A and B of a stage are issued together
-      const int tx_sub = sub_bytes;
+      const int tx_sub = sub_bytes - t.a_bytes + t.a_tx;
       auto load_b = [&](uint32_t s, int u, int kb) {
-        uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + A_STAGE_BYTES;
+        uint8_t* sb = c.smem + s * t.stage_bytes + u * sub_bytes + t.a_bytes;
         tma_load_2d(sb, t.tmB, (t.b_follows_a ? ps_ka(t, kb) : kb) * BK, t.b_row, &c.full[s]);
         if (t.tmB2) tma_load_2d(sb + t.n1 * BK * 2, t.tmB2, (kb + t.b2_koff) * BK, t.b2_row, &c.full[s]);
       };
       auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
         int st = st0;
         if (w != nullptr || gte != nullptr) {
-          const int npre = min(st1 - st0, PS_STAGES);
+          const int npre = min(st1 - st0, (int)NS);
           for (; st < st0 + npre; ++st) {
-            const uint32_t i = c.it + st, s = i % PS_STAGES;
-            ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+            const uint32_t i = c.it + st, s = i % NS;
+            ps_mbar_wait(&c.empty[s], ((i / NS) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
             const int n_sub = min(kps, nk - st * kps);
             mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
             for (int u = 0; u < n_sub; ++u) load_b(s, u, st * kps + u);
@@ -664,7 +680,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           fence_proxy_async_all();   // the A operand was written through the generic proxy by another SM: order it before the TMA reads
           if (mark && c.tr) c.tr[2] = ps_now();
           for (int s2 = st0; s2 < st0 + npre; ++s2) {
-            const uint32_t s = (c.it + s2) % PS_STAGES;
+            const uint32_t s = (c.it + s2) % NS;
             const int n_sub = min(kps, nk - s2 * kps);
             for (int u = 0; u < n_sub; ++u)
               tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
@@ -674,8 +690,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           if (c.tr) c.tr[2] = ps_now();
         }
         for (; st < st1; ++st) {
-          const uint32_t i = c.it + st, s = i % PS_STAGES;
-          ps_mbar_wait(&c.empty[s], ((i / PS_STAGES) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
+          const uint32_t i = c.it + st, s = i % NS;
+          ps_mbar_wait(&c.empty[s], ((i / NS) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
           const int n_sub = min(kps, nk - st * kps);
           mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
           for (int u = 0; u < n_sub; ++u) {
@@ -685,9 +701,9 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           }
         }
       };
-      if (t.w1 != nullptr || t.g1 != nullptr) {   // two separately released k ranges (kps == 1)
-        issue(0, t.nka0, t.w0, t.t0, t.g0, t.gt0, true);
-        issue(t.nka0, nk, t.w1, t.t1, t.g1, t.gt1, false);
+      if (t.w1 != nullptr || t.g1 != nullptr) {   // two separately released k ranges (the first a whole number of pipeline stages)
+        issue(0, t.nka0 / kps, t.w0, t.t0, t.g0, t.gt0, true);
+        issue(t.nka0 / kps, n_st, t.w1, t.t1, t.g1, t.gt1, false);
       } else {
         issue(0, n_st, t.w0, t.t0, t.g0, t.gt0, true);
       }
@@ -695,8 +711,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   } else if (warp == 1) {
     if (lane == 0) {
       for (int st = 0; st < n_st; ++st) {
-        const uint32_t i = c.it + st, s = i % PS_STAGES;
-        ps_mbar_wait(&c.full[s], (i / PS_STAGES) & 1, c.dbg, t.code | (4u << 20));
+        const uint32_t i = c.it + st, s = i % NS;
+        ps_mbar_wait(&c.full[s], (i / NS) & 1, c.dbg, t.code | (4u << 20));
         tc_fence_after();
         if (c.tr && st == 0) c.tr[3] = ps_now();
         const int n_sub = min(kps, nk - st * kps);
@@ -704,7 +720,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           const int kb = st * kps + u;
           const uint32_t a_addr = smem_u32(c.smem + s * t.stage_bytes + u * sub_bytes);
           const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + t.a_bytes);
           if constexpr (GRU_U == 0) {
             const uint32_t idesc = umma_idesc_bf16(t.bn);
 #pragma unroll
@@ -715,7 +731,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
             // issued as an N = 2U and an N = U instruction.
             constexpr int U = GRU_U;
             const uint32_t idesc_rz = umma_idesc_bf16(2 * U), idesc_n = umma_idesc_bf16(U), idesc_3 = umma_idesc_bf16(3 * U);
-            const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
+            const uint64_t bdesc_n = umma_desc_sw128(a_addr + t.a_bytes + 2 * U * BK * 2);
             if (kb < t.nka0) {   // h part
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -742,7 +758,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     }
   } else {
     const int tid = (int)threadIdx.x - 64;
-    if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 128) = c.tr ? c.tr + c.lap_off : nullptr;
+    if (tid == 0) *reinterpret_cast<unsigned long long**>(c.smem + PS_EPI_OFF - 64) = c.tr ? c.tr + c.lap_off : nullptr;
     pre(tid);
     if (lane == 0) ps_flag_wait(t.e0, t.et0, c.dbg, t.code | (5u << 20));
     __syncwarp();
@@ -794,8 +810,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + PS_BAR_OFF);
-  uint64_t* empty = full + PS_STAGES;
-  uint64_t* tmem_full = empty + PS_STAGES;
+  // barrier block (256 bytes = 32 slots): full[0, 8) | empty[8, 16) | tmem_full 16 | TMEM address 17 | xbar 18, 19 | abar 20 | lap pointer 24
+  uint64_t* empty = full + PS_MAX_STAGES;
+  uint64_t* tmem_full = empty + PS_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* epi_sm = reinterpret_cast<float*>(smem + PS_EPI_OFF);
   int* sched = reinterpret_cast<int*>(smem + PS_SCHED_OFF);
@@ -803,9 +820,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&P.tmS); tma_prefetch_desc(&P.tmY1); tma_prefetch_desc(&P.tmY2);
-    for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < PS_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
-    for (int i = 12; i < 15; ++i) mbar_init(&full[i], 1);   // xbar[0], xbar[1], abar (bytes 96 .. 120 of the barrier block; the lap pointer sits at byte 128)
+    for (int i = 18; i < 21; ++i) mbar_init(&full[i], 1);   // xbar[0], xbar[1], abar
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < PS_SCHED_STRIDE; i += GEMM_THREADS) sched[i] = __ldg(P.sched + (long)blockIdx.x * PS_SCHED_STRIDE + i);
@@ -816,7 +833,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.ns = PS_STAGES; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
@@ -828,7 +845,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   float* tile = reinterpret_cast<float*>(smem);
   auto flag = [&](int kind, int m) { return P.flags + (long)(kind * mt + m) * 32; };
   auto tile_init = [&](PsTile& t, int layer, int j, int m_tile) {
-    t.stage_bytes = PS_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0; t.chain = role == PS_CHAIN ? 1 : 0;
+    t.stage_bytes = PS_STAGE_BYTES; t.a_bytes = A_STAGE_BYTES; t.a_tx = A_STAGE_BYTES; t.b_follows_a = 0; t.ka0 = 0; t.nka0 = 0; t.ka1 = 0; t.nka1 = 0; t.kps = 1; t.cbar = 0; t.chain = role == PS_CHAIN ? 1 : 0;
     t.w0 = nullptr; t.t0 = 0; t.g0 = nullptr; t.gt0 = 0; t.w1 = nullptr; t.t1 = 0; t.g1 = nullptr; t.gt1 = 0; t.lsig = nullptr;
     t.h_first = 0; t.tmB2 = nullptr; t.n1 = 0; t.b2_row = 0; t.b2_koff = 0; t.tcol = 0; t.acc0 = 0; t.e0 = nullptr; t.et0 = 0; t.sig = nullptr;
     t.code = ((unsigned)role << 24) | ((unsigned)layer << 16) | ((unsigned)j << 8) | (unsigned)m_tile;
@@ -856,7 +873,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     const int ya = (1 + HS_ACTOR) * Mp;   // the actor's slot of the hidden-activation buffers (slot 0 = prior)
     PsXchg xg;
     xg.xst = reinterpret_cast<float*>(smem + PS_RING_BYTES);                 // (the 16 KB behind the ring, unused by chain CTAs otherwise)
-    xg.xbar = full + 12; xg.abar = full + 14;
+    xg.xbar = full + 18; xg.abar = full + 20;
     xg.xact = reinterpret_cast<float*>(smem + PS_RING_BYTES - 16384);        // rank 0: last 16 KB of the ring (idle while the epilogue runs)
     xg.xuse = 0; xg.ause = 0; xg.dbg = P.dbg;
     for (int j = 0; j <= H; ++j) {

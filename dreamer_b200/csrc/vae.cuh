@@ -266,7 +266,11 @@ struct drm_vae {
   bool packed;
 };
 
+struct drm_obs_persist;   // schedule + counters of the persistent scan kernel (observe_persist.cuh)
+namespace drm { static void obs_persist_free(drm_obs_persist* ps); }
+
 struct drm_observe {
+  drm_obs_persist* ps = nullptr;
   drm_rssm* m;
   drm_vae* v;
   int B, T, rows, rows_p, FC;
@@ -558,6 +562,7 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
 
 extern "C" int drm_observe_destroy(drm_observe* o) {
   if (!o) return DRM_OK;
+  drm::obs_persist_free(o->ps);
   for (void* p : o->allocs) cudaFree(p);
   delete o;
   return DRM_OK;
@@ -736,6 +741,8 @@ static int decoder_dense(drm_observe* o, const WsView& vw, __nv_bfloat16* act0, 
 
 }  // namespace drm
 
+#include "observe_persist.cuh"
+
 extern "C" int drm_observe_scan(drm_observe* o, const float* obs, const float* act, const float* uniforms, int32_t mode,
                                 float* latent, float* hidden, float* post_logits, uint8_t* idx, void* stream) {
   RC(check_arch());
@@ -751,10 +758,18 @@ extern "C" int drm_observe_scan(drm_observe* o, const float* obs, const float* a
   //     (time-major), their product with the feature columns of latent_mapper.0, and the actions
   for (int f0 = 0; f0 < NF; f0 += o->FC) RC(encoder_conv_chunk(o, obs, f0, std::min(o->FC, NF - f0), 1, st));
   RC(encoder_feat_part(o, NF, st));
-  DRM_CUDA(cudaMemsetAsync(o->S, 0, (size_t)2 * B * KS * sizeof(__nv_bfloat16), st));   // slab 0 (zero state) and slab 1's h
+  // (2) the recurrence: one persistent kernel for all T steps when its clusters fit the device (observe_persist.cuh), else
+  //     three launches per step
+  const bool persist = opts().persist && obs_persist_eligible(o);
+  // slab 0 (zero state) and slab 1's h; the persistent kernel flips single one-hot entries, so it starts from all-zero z columns
+  DRM_CUDA(cudaMemsetAsync(o->S, 0, (size_t)(persist ? (T + 1) : 2) * B * KS * sizeof(__nv_bfloat16), st));
   pack_actions_kernel<<<grid_for((long)B * T * A), 256, 0, st>>>(o->S, KS, ZP, act, B, T, A);
   DRM_LAUNCH_CHECK();
-  // (2) the recurrence
+  if (persist) {
+    RC(observe_persist(o, uniforms, mode, latent, hidden, post_logits, idx, st));
+    o->scanned = true;
+    return DRM_OK;
+  }
   const long ldL = (long)T * ZP, ldH = (long)T * D;
   for (int t = 0; t < T; ++t) {
     const WsView prev = view_of(o, t * B), cur = view_of(o, (t + 1) * B);

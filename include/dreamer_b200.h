@@ -280,6 +280,9 @@ int drm_vae_destroy(drm_vae* v);
 int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T, drm_observe** out);
 int drm_observe_destroy(drm_observe* o);
 
+/* debug: per-tile %globaltimer records of the persistent posterior-scan kernel (protocol of drm_rollout_trace) */
+int drm_observe_trace(drm_observe* o, int32_t j0, int32_t nj, unsigned long long* out, int64_t n_words);
+
 /* The posterior scan.  mode 0 = WorldModel.unroll_model's loop  WorldModel.py:92-107 (step 0 runs a GRU  */
 /* step on the all-zero state); mode 1 = Dreamer.warm_start_generator  Dreamer.py:252-261 (frame 0 is       */
 /* encoded with h = 0 and no GRU step).  The conv stack runs once over all B*T frames (it does not depend  */

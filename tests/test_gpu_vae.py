@@ -206,14 +206,61 @@ def test_ksplit_gru_scan_agrees_with_single_cta_scan(ops):
     obs = obs / 255.0 - 0.5
     outs = []
     try:
+        L.check(lib.drm_set_option(b"persist", 0), "set_option")   # (the launch-per-stage scan is the one with the two GRU kernels)
         for flag in (1, 0):
             L.check(lib.drm_set_option(b"gru_ksplit", flag), "set_option")
             sc = ws.scan(obs, act, u)
             outs.append({k: v.clone() for k, v in sc.items()})
     finally:
         lib.drm_set_option(b"gru_ksplit", 1)
+        lib.drm_set_option(b"persist", 1)
     assert (outs[0]["idx"] != outs[1]["idx"]).float().mean().item() < 0.01
     same = (outs[0]["idx"] == outs[1]["idx"]).all(dim=-1).all(dim=-1)
     assert same.any()
     assert torch.allclose(outs[0]["hidden"][same], outs[1]["hidden"][same], atol=2e-3, rtol=2e-3)
     assert not torch.equal(outs[0]["hidden"], outs[1]["hidden"])          # the two paths really are different kernels
+
+
+@pytest.mark.parametrize("name,B,T,warm", [("small", 3, 6, False), ("small", 40, 5, True), ("ref", 16, 12, False), ("ref", 50, 7, True),
+                                           ("ref", 130, 4, False)])
+def test_persistent_scan_agrees_with_the_launch_per_stage_scan(ops, name, B, T, warm):
+    """Option "persist" (default on): the posterior scan (WorldModel.py:92-107, Dreamer.py:252-261) as ONE persistent kernel for all T
+    steps versus three launches per step.  The oracle's own trajectory fixes the draws (uniforms placed inside the oracle's CDF
+    bins), so both paths must sample the oracle's classes exactly; hidden states and posterior logits agree to the 1e-2 bound against
+    the oracle and to fp32 rounding between the two paths.  Covers short-box (<= 32 sequences) and full A tiles, a partial m-tile
+    pair (130 sequences) and the warm start (h_0 = 0)."""
+    from dreamer_b200 import _lib as L
+    lib = L.load()
+    cfg = CFGS[name]
+    sd, _, vae = _build(ops, cfg, 23)
+    ws = ops.Observe(vae, B, T)
+    obs, act, _, _, u = W.sequence_inputs(cfg, B, T, seed=24)
+    obs = obs / 255.0 - 0.5
+    used = u
+    ref = None
+    if not warm:
+        with torch.no_grad():
+            zr, hr, lr, ir, used = O.observe_scan(sd, obs, act, u, margin_frac=0.25, delta=1e-5)
+        ref = dict(latent=zr, hidden=hr, logits=lr, idx=ir)
+    outs = []
+    try:
+        for flag in (1, 0):
+            L.check(lib.drm_set_option(b"persist", flag), "set_option")
+            sc = ws.scan(obs.to(DEV), act.to(DEV), used.to(DEV), warm_start=warm)
+            outs.append({k: v.clone() for k, v in sc.items()})
+    finally:
+        lib.drm_set_option(b"persist", 1)
+    if ref is not None:
+        for o in outs:
+            assert torch.equal(o["idx"].cpu().long(), ref["idx"].long()), "sampled classes differ from the oracle"
+            _close(o["hidden"], ref["hidden"], what="hidden")
+            _close(o["logits"], ref["logits"], what="posterior logits")
+            assert torch.equal(o["latent"].cpu() != 0, ref["latent"] != 0)
+        same = torch.ones(B, dtype=torch.bool, device=DEV)
+    else:   # warm start (no GRU step before the first posterior): the two paths against each other, raw uniforms
+        assert (outs[0]["idx"] != outs[1]["idx"]).float().mean().item() < 0.01
+        same = (outs[0]["idx"] == outs[1]["idx"]).all(dim=-1).all(dim=-1)
+        assert same.any()
+        assert outs[0]["hidden"][:, 0].abs().max().item() == 0.0 and outs[1]["hidden"][:, 0].abs().max().item() == 0.0
+    assert torch.allclose(outs[0]["hidden"][same], outs[1]["hidden"][same], atol=2e-3, rtol=2e-3)
+    assert torch.allclose(outs[0]["logits"][same], outs[1]["logits"][same], atol=2e-2, rtol=2e-2)
