@@ -312,6 +312,28 @@ class Harness:
             self.dist.destroy_process_group()
 
 
+def time_gradient_all_reduce(hs, n_params, dev, world):
+    """The one collective of the design's training path, timed alone: all-reduce (SUM) of a flat fp32
+    gradient bucket of `n_params` elements over NCCL; device time, max over ranks; bus GB/s = 2 (n - 1) / n x bytes / time."""
+    import torch
+    buf = torch.zeros(n_params, device=dev)
+    for _ in range(5):
+        hs.dist.all_reduce(buf)
+    hs.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    a.record()
+    for _ in range(reps):
+        hs.dist.all_reduce(buf)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+    hs.dist.all_reduce(t, op=hs.dist.ReduceOp.MAX)
+    ms = float(t.item())
+    by = n_params * 4
+    return dict(bucket_bytes=by, all_reduce_ms=ms, bus_gbs=2 * (world - 1) / world * by / (ms * 1e-3) / 1e9)
+
+
 def bench_rollout(hs, args, cfg, sd, B, H, desc):
     import ctypes as C
     from dreamer_b200 import _lib as L, ops, synthetic as W
@@ -407,6 +429,13 @@ def bench_rollout(hs, args, cfg, sd, B, H, desc):
                 e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
                 gpu_launches=int(launches_per_rollout * args.steps), clocks=clocks, roofline=roofline,
                 whole_rollout=dict(achieved_tflops=whole_tf, frac_of_bf16_sustained=whole_tf / peaks["bf16_sustained"], flops_per_state=fl["total"]))
+    if world > 1:
+        # the rollout itself shards with no exchange; what the same ranks exchange when they TRAIN on these rollouts is one flat gradient
+        # bucket per optimiser group -- timed here (outside the timed region) so that every multi-GPU line carries the collective's cost
+        coll = time_gradient_all_reduce(hs, 7757035, dev, world)
+        coll["note"] = ("not part of this workload: the world model's 31 MB gradient bucket all-reduced alone over NCCL (what --workload c5 "
+                        "runs inside every training iteration)")
+        line["collective"] = coll
     return line, [ro]
 
 
@@ -501,24 +530,9 @@ def bench_iteration(hs, args, cfg, desc):
     coll = None
     if world > 1:
         n_wm = sum(p.numel() for p in hp.world_model.parameters())
-        buf = torch.zeros(n_wm, device=dev)
-        for _ in range(5):
-            hs.dist.all_reduce(buf)
-        hs.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        a.record()
-        for _ in range(reps):
-            hs.dist.all_reduce(buf)
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
-        hs.dist.all_reduce(t, op=hs.dist.ReduceOp.MAX)
-        ms = float(t.item())
-        by = n_wm * 4
-        coll = dict(bucket_bytes=by, all_reduce_ms=ms, bus_gbs=2 * (world - 1) / world * by / (ms * 1e-3) / 1e9,
-                    per_iteration=f"{cfg['WM_epochs']} x this bucket + {cfg['AC_epochs']} x (1.47 MB actor + 1.67 MB critic) + packed scalars",
-                    share_of_iteration=cfg["WM_epochs"] * ms / (total_ms / args.steps))
+        coll = time_gradient_all_reduce(hs, n_wm, dev, world)
+        coll.update(per_iteration=f"{cfg['WM_epochs']} x this bucket + {cfg['AC_epochs']} x (1.47 MB actor + 1.67 MB critic) + packed scalars",
+                    share_of_iteration=cfg["WM_epochs"] * coll["all_reduce_ms"] / (total_ms / args.steps))
     line = dict(metric="training iterations/sec", value=value, unit="iterations/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=desc, l2="flushed (256 MiB write) between timed iterations",

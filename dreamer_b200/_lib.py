@@ -77,6 +77,7 @@ SIGNATURES = {
     "drm_twohot_ce": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, c_stream]),
     "drm_bucket_value": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, c_stream]),
     "drm_rssm_create": (C.c_int, [C.POINTER(DrmDims), C.POINTER(C.c_void_p)]),
+    "drm_rssm_create_ex": (C.c_int, [C.POINTER(DrmDims), C.c_int32, C.POINTER(C.c_void_p)]),
     "drm_rssm_pack": (C.c_int, [C.c_void_p, C.POINTER(DrmRssmWeights), c_stream]),
     "drm_rssm_destroy": (C.c_int, [C.c_void_p]),
     "drm_rollout_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

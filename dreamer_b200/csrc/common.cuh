@@ -150,6 +150,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (the tensor core reads the top 19 bits), K = 8 per instruction, FP32 accumulate.
+// The "wide operand" (TF32) mode of the launch-per-stage path: same 128-byte swizzled rows, 32 elements per k-block instead of 64.
+__host__ __device__ constexpr uint32_t umma_idesc(int n, int wide) {
+  return (1u << 4) | ((wide ? 2u : 1u) << 7) | ((wide ? 2u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_op(int wide, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (wide) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+// round-to-nearest TF32 (what cuBLAS's TF32 GEMMs feed the tensor cores; a plain fp32 operand would be truncated)
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return __uint_as_float(y);
+}
+
 // All previously issued UMMAs of this thread arrive on `bar` when complete (implies
 // tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

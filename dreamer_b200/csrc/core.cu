@@ -72,6 +72,24 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return DRM_OK;
 }
 
+// Operand tensor map of either precision mode: bf16 (box {64, rows}) or, wide = 1, fp32 for kind::tf32 MMAs (box {32, rows});
+// both are 128-byte swizzled rows.  ld_elems / cols count ELEMENTS.
+int make_tmap_op_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows, int wide) {
+  if (!wide) return make_tmap_bf16_2d(tm, base, rows, cols, ld_elems, box_rows);
+  auto fn = encode_fn();
+  if (!fn) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (((uintptr_t)base & 15u) || ((ld_elems * 4) & 15u)) return fail(DRM_ERR_ALIGN, "tensor map base / pitch must be 16-byte aligned");
+  if (box_rows == 0 || box_rows > 256) return fail(DRM_ERR_SHAPE, "tensor map box rows must be in [1, 256]");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string((int)r));
+  return DRM_OK;
+}
+
 // 2D bf16 tensor map with a narrower inner box: box {inner, box_rows}, swizzle span = inner * 2 bytes (inner = 16 / 32 / 64 elements).
 // Weights of the implicit-GEMM convolutions whose k-block is one tap of <= 64 channels.
 int make_tmap_bf16_2d_inner(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,

@@ -209,7 +209,7 @@ struct EpiLnSiluT {
     normalise(p, g, sm, taddr, m, row, part, ncols, [&](int c, float (&v)[32]) { tile_put<32>(tile, pitch, row, c, v); });
     epi_bar_sync();
     tile_copy_out(tile, pitch, ncols, ncols, (m - row), g.M, nullptr, 0,
-                  p.out + (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out, p.ld_out, tid);
+                  opnd_at(p.out, (long)(p.out_row0 + slot * p.out_y_stride) * p.ld_out, g.wide), p.ld_out, tid, RowMap{0, 0, 0, 0}, g.wide);
   }
 };
 using EpiLnSilu = EpiLnSiluT<false>;
@@ -444,7 +444,7 @@ struct EpiGru {
       tile_put<UP>(tile, pitch, row, c, hn);
     }
     epi_bar_sync();
-    tile_copy_out(tile, pitch, U, nvalid, m0, g.M, p.h_out + u0, p.ld_hout, p.s_h + u0, p.ld_s, tid);
+    tile_copy_out(tile, pitch, U, nvalid, m0, g.M, p.h_out + u0, p.ld_hout, opnd_at(p.s_h, u0, g.wide), p.ld_s, tid, RowMap{0, 0, 0, 0}, g.wide);
   }
 };
 
@@ -540,7 +540,17 @@ struct EpiCat {
         if (m0 + r < g.M && gi < ngrp) p.idx[map_row(p.rm, m0 + r) * p.ld_idx + slot * G + gi] = idx_sm[i];
       }
     }
-    if (p.s_z) {
+    if (p.s_z && g.wide) {   // TF32 mode: the state buffer holds fp32 -- eight floats (two 16-byte stores) per item
+      float* sz = reinterpret_cast<float*>(p.s_z);
+      for (int i = tid; i < BM * 32; i += EPI_THREADS) {
+        const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
+        if (m0 + r >= g.M || gi >= ngrp) continue;
+        const int idx = idx_sm[r * 8 + gi];
+        float4* o = reinterpret_cast<float4*>(sz + (long)(m0 + r) * p.ld_s + col0 + w * 8);
+        o[0] = make_float4(idx == j0 ? 1.f : 0.f, idx == j0 + 1 ? 1.f : 0.f, idx == j0 + 2 ? 1.f : 0.f, idx == j0 + 3 ? 1.f : 0.f);
+        o[1] = make_float4(idx == j0 + 4 ? 1.f : 0.f, idx == j0 + 5 ? 1.f : 0.f, idx == j0 + 6 ? 1.f : 0.f, idx == j0 + 7 ? 1.f : 0.f);
+      }
+    } else if (p.s_z) {
       for (int i = tid; i < BM * 32; i += EPI_THREADS) {    // one uint4 (8 bf16) per item
         const int r = i >> 5, w = i & 31, gi = w >> 2, j0 = (w & 3) * 8;
         if (m0 + r >= g.M || gi >= ngrp) continue;
@@ -675,7 +685,15 @@ struct EpiHeads {
             }
           }
         }
-        if (p.s_a && p.normals) store_bf16_row<16>(p.s_a + (long)m * p.ld_s, act, 16);
+        if (p.s_a && p.normals) {
+          if (g.wide) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.s_a) + (long)m * p.ld_s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(tf32_rn(act[4 * j]), tf32_rn(act[4 * j + 1]), tf32_rn(act[4 * j + 2]), tf32_rn(act[4 * j + 3]));
+          } else {
+            store_bf16_row<16>(p.s_a + (long)m * p.ld_s, act, 16);
+          }
+        }
       }
     }
   }

@@ -30,7 +30,11 @@ struct TileG {
   int M;             // valid rows (epilogues guard their global stores with m < M)
   int bn;            // B rows per tile == UMMA N of the (first) accumulator group
   int hp_pre;        // 32-unit GRU tiles: 1 = the tile's h_prev was fetched into the epilogue scratch under the main loop
+  int wide;          // 1: TF32 mode -- operand buffers (state, hidden activations, weights) hold fp32, 32 elements per k-block
 };
+
+// Operand buffers are declared as bf16 pointers; in TF32 mode the same fields address fp32 data: element offset -> pointer
+__device__ __host__ __forceinline__ __nv_bfloat16* opnd_at(__nv_bfloat16* base, long elems, int wide) { return base + (elems << wide); }
 
 struct GemmCommon : TileG {
   CUtensorMap tmA;   // activations, box {64, 128}
@@ -124,6 +128,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nk = g.nka0 + g.nka1;
+  const int bke = g.wide ? BK / 2 : BK;   // elements per 128-byte k-block
   const int slot = g.n_slots > 0 ? g.y_slot[blockIdx.y] : (int)blockIdx.y;
   const int m0 = (int)blockIdx.x * BM;
   const int a_row = g.a_row0 + slot * g.a_y_stride + m0;
@@ -174,8 +179,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
             const int kb = st * KPS + j;
             uint8_t* sa = smem + s * SL::STAGE_BYTES + j * SL::SUB_BYTES;
             const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
-            tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
-            tma_load_2d(sa + A_STAGE_BYTES, &g.tmB, kb * BK, b_row, &full[s]);
+            tma_load_2d(sa, &g.tmA, ka * bke, a_row, &full[s]);
+            tma_load_2d(sa + A_STAGE_BYTES, &g.tmB, kb * bke, b_row, &full[s]);
           }
           if (st == 0) probe(g, 2);
         }
@@ -188,8 +193,8 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
           uint8_t* sb = sa + A_STAGE_BYTES;
           const int ka = kb < g.nka0 ? g.ka0 + kb : g.ka1 + (kb - g.nka0);
           mbar_expect_tx(&full[s], tx_b + tx_a);
-          tma_load_2d(sa, &g.tmA, ka * BK, a_row, &full[s]);
-          tma_load_2d(sb, &g.tmB, kb * BK, b_row, &full[s]);
+          tma_load_2d(sa, &g.tmA, ka * bke, a_row, &full[s]);
+          tma_load_2d(sb, &g.tmB, kb * bke, b_row, &full[s]);
           if (kb == 0) probe(g, 2);
         }
       }
@@ -197,7 +202,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       if constexpr (KPS > 1) {
-        const uint32_t idesc = umma_idesc_bf16(g.bn);
+        const uint32_t idesc = umma_idesc(g.bn, g.wide);
         const int n_st = (nk + KPS - 1) / KPS;
         for (int st = 0; st < n_st; ++st) {
           const int s = st % STAGES;
@@ -209,7 +214,7 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
             const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES + j * SL::SUB_BYTES);
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (st | j | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma_op(g.wide, tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (st | j | k) != 0);
           }
           umma_commit(&empty[s]);
         }
@@ -224,28 +229,28 @@ fused_gemm_kernel(const __grid_constant__ GemmCommon g, const __grid_constant__ 
           const uint64_t adesc = umma_desc_sw128(a_addr);
           const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
           if constexpr (Epi::GRU_U == 0) {
-            const uint32_t idesc = umma_idesc_bf16(g.bn);
+            const uint32_t idesc = umma_idesc(g.bn, g.wide);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_op(g.wide, tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           } else {
             // GRU tile: B rows = [r(U) | z(U) | n(U)], TMEM cols = [r | z | n_x | n_h].
             // x-part k-blocks feed r, z, n_x in one N = 3U MMA; h-part k-blocks feed r, z (N = 2U)
             // and n_h (N = U, B rows 2U.., TMEM cols 3U..) because r multiplies only W_hn h.
             constexpr int U = Epi::GRU_U;
             if (kb < g.nka0) {
-              const uint32_t idesc = umma_idesc_bf16(3 * U);
+              const uint32_t idesc = umma_idesc(3 * U, g.wide);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                umma_op(g.wide, tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             } else {
-              const uint32_t idesc_rz = umma_idesc_bf16(2 * U);
-              const uint32_t idesc_n = umma_idesc_bf16(U);
+              const uint32_t idesc_rz = umma_idesc(2 * U, g.wide);
+              const uint32_t idesc_n = umma_idesc(U, g.wide);
               const uint64_t bdesc_n = umma_desc_sw128(a_addr + A_STAGE_BYTES + 2 * U * BK * 2);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
-                umma_bf16(tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > g.nka0 || k > 0) ? 1u : 0u);
+                umma_op(g.wide, tmem, adesc + 2 * k, bdesc + 2 * k, idesc_rz, 1u);
+                umma_op(g.wide, tmem + 3 * U, adesc + 2 * k, bdesc_n + 2 * k, idesc_n, (kb > g.nka0 || k > 0) ? 1u : 0u);
               }
             }
           }
@@ -320,7 +325,8 @@ __device__ __forceinline__ long map_row(const RowMap& rm, int m) {
 // for m0 + r < M and c < nvalid (ncols % 4 == 0; full float4 groups take the vector path).
 // Warp w streams rows in passes of 32 / lpr rows; its lanes walk a row 16 bytes apiece.
 __device__ __forceinline__ void tile_copy_out(const float* tile, int pitch, int ncols, int nvalid, int m0, int M, float* out_f32,
-                                              long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid, RowMap rm = RowMap{0, 0, 0, 0}) {
+                                              long ld_f, __nv_bfloat16* out_bf, long ld_b, int tid, RowMap rm = RowMap{0, 0, 0, 0},
+                                              int wide = 0) {   // wide: out_bf addresses an fp32 (TF32-rounded) operand buffer
   const bool al_f = out_f32 && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0) && ((ld_f & 3) == 0);
   const bool al_b = out_bf && ((reinterpret_cast<uintptr_t>(out_bf) & 7u) == 0) && ((ld_b & 3) == 0);
   const int rows = min(BM, M - m0);
@@ -349,7 +355,17 @@ __device__ __forceinline__ void tile_copy_out(const float* tile, int pitch, int 
         if (full && al_f) *reinterpret_cast<float4*>(o) = x;
         else { o[0] = x.x; if (c + 1 < nvalid) o[1] = x.y; if (c + 2 < nvalid) o[2] = x.z; if (c + 3 < nvalid) o[3] = x.w; }
       }
-      if (out_bf) {
+      if (out_bf && wide) {
+        float* o = reinterpret_cast<float*>(out_bf) + orow * ld_b + c;
+        if (full && ((reinterpret_cast<uintptr_t>(out_bf) & 15u) == 0) && ((ld_b & 3) == 0)) {
+          *reinterpret_cast<float4*>(o) = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+        } else {
+          o[0] = tf32_rn(x.x);
+          if (c + 1 < nvalid) o[1] = tf32_rn(x.y);
+          if (c + 2 < nvalid) o[2] = tf32_rn(x.z);
+          if (c + 3 < nvalid) o[3] = tf32_rn(x.w);
+        }
+      } else if (out_bf) {
         __nv_bfloat16* o = out_bf + orow * ld_b + c;
         if (full && al_b) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
         else {

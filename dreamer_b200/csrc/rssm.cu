@@ -26,13 +26,15 @@ namespace drm {
 // ------------------------------------------------------------------------------------------
 __global__ void pack_matrix_kernel(__nv_bfloat16* __restrict__ dst, int ld_dst, int dst_row0, int nrows, int dst_col0,
                                    int ncols, const float* __restrict__ src, int ld_src, const int* __restrict__ row_map,
-                                   const int* __restrict__ col_map) {
+                                   const int* __restrict__ col_map, int wide = 0) {
   const long total = (long)nrows * ncols;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ncols), c = (int)(i % ncols);
     const int sr = row_map[r], sc = col_map[c];
     const float v = (sr >= 0 && sc >= 0) ? src[(long)sr * ld_src + sc] : 0.f;
-    dst[(long)(dst_row0 + r) * ld_dst + dst_col0 + c] = __float2bfloat16_rn(v);
+    const long o = (long)(dst_row0 + r) * ld_dst + dst_col0 + c;
+    if (wide) reinterpret_cast<float*>(dst)[o] = tf32_rn(v);   // TF32 mode: the operand buffer holds fp32
+    else dst[o] = __float2bfloat16_rn(v);
   }
 }
 __global__ void pack_vector_kernel(float* __restrict__ dst, int n, const float* __restrict__ src, const int* __restrict__ map,
@@ -43,12 +45,13 @@ __global__ void pack_vector_kernel(float* __restrict__ dst, int n, const float* 
 
 // fp32 rows -> bf16 columns of a state buffer (and optional fp32 copies into strided outputs).
 __global__ void pack_state_kernel(__nv_bfloat16* __restrict__ S, int ld_s, int col0, const float* __restrict__ src,
-                                  long ld_src, int ncols, int N, float* __restrict__ copy, long ld_copy) {
+                                  long ld_src, int ncols, int N, float* __restrict__ copy, long ld_copy, int wide = 0) {
   const long total = (long)N * ncols;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ncols), c = (int)(i % ncols);
     const float v = src[(long)r * ld_src + c];
-    S[(long)r * ld_s + col0 + c] = __float2bfloat16_rn(v);
+    if (wide) reinterpret_cast<float*>(S)[(long)r * ld_s + col0 + c] = tf32_rn(v);
+    else S[(long)r * ld_s + col0 + c] = __float2bfloat16_rn(v);
     if (copy) copy[(long)r * ld_copy + c] = v;
   }
 }
@@ -69,6 +72,7 @@ struct Options {
   int ln_cluster = 1;  // LN stages of small grids split over clusters of 4 CTAs
   int gru_ksplit = 1;  // single-m-tile grids split the GRU tile's K range over a 2-CTA cluster
   int conv_persist = 1;  // narrow conv layers on the persistent GEMM
+  int conv_chunk = 512;  // frames per conv chunk of an observe workspace (read when the workspace is created)
   int conv_implicit = 1; // conv layers as implicit GEMMs fed by im2col-mode TMA loads (no patch matrix)
   int gru_pair = -1;   // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
   int small_a = 1;     // stages with <= 32 rows load 32-row A boxes
@@ -217,6 +221,7 @@ using namespace drm;
 
 struct drm_rssm {
   drm_dims d;
+  int wide = 0;                  // 1: TF32 mode -- every operand buffer below (declared bf16) holds fp32, tensor maps have 32-element boxes
   int ZP, DP, KS, KG, KH;        // state layout: z cols, padded h cols, state pitch, GRU K, head-L1 K
   int gru_tiles2[2];             // GRU n-tiles for U = 32 / 64 (both layouts are packed; the launch picks by grid size)
   int bnp1, bnp2, bnh1, bnh2;    // padded hidden widths (multiples of 16)
@@ -298,9 +303,12 @@ static int add_vec(drm_rssm* m, float* dst, int src, const std::vector<int>& map
     if (int rc__ = (x)) return rc__; \
   } while (0)
 
-extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
+extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) { return drm_rssm_create_ex(dims, DRM_PRECISION_BF16, out); }
+
+extern "C" int drm_rssm_create_ex(const drm_dims* dims, int32_t precision, drm_rssm** out) {
   RC(check_arch());
   DRM_REQUIRE(dims && out, DRM_ERR_ARG, "drm_rssm_create: NULL argument");
+  DRM_REQUIRE(precision == DRM_PRECISION_BF16 || precision == DRM_PRECISION_TF32, DRM_ERR_ARG, "drm_rssm_create_ex: unknown precision");
   const drm_dims d = *dims;
   DRM_REQUIRE(d.C == 32, DRM_ERR_SHAPE, "drm_rssm_create: latent classes C must be 32");
   DRM_REQUIRE(d.R > 0 && (d.R * d.C) % 256 == 0, DRM_ERR_SHAPE, "drm_rssm_create: R * C must be a multiple of 256");
@@ -312,6 +320,8 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
                 "drm_rssm_create: MLP hidden sizes must be in [1, 256]");
   drm_rssm* m = new drm_rssm();
   m->d = d;
+  m->wide = precision == DRM_PRECISION_TF32 ? 1 : 0;
+  const int wd = m->wide;
   m->packed = false;
   m->has_critic = false;
   m->have = 0;
@@ -330,13 +340,13 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   auto& bag = m->allocs;
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
-  for (int v = 0; v < 2; ++v) TRY(dev_alloc(bag, &m->Wgru2[v], (size_t)m->gru_tiles2[v] * 3 * (32 << v) * m->KG));
-  TRY(dev_alloc(bag, &m->Wp1, (size_t)256 * DP));                 // LN-stage weights: 256-row slots (zero padded)
-  TRY(dev_alloc(bag, &m->Wp2, (size_t)256 * 256));
-  TRY(dev_alloc(bag, &m->Wp3, (size_t)ZP * 256));
-  TRY(dev_alloc(bag, &m->Wh1, (size_t)MAX_HEADS * 256 * m->KH));
-  TRY(dev_alloc(bag, &m->Wh2, (size_t)MAX_HEADS * 256 * 256));
-  TRY(dev_alloc(bag, &m->Wh3, (size_t)MAX_HEADS * 256 * 256));
+  for (int v = 0; v < 2; ++v) TRY(dev_alloc(bag, &m->Wgru2[v], ((size_t)m->gru_tiles2[v] * 3 * (32 << v) * m->KG) << wd));
+  TRY(dev_alloc(bag, &m->Wp1, ((size_t)256 * DP) << wd));                 // LN-stage weights: 256-row slots (zero padded)
+  TRY(dev_alloc(bag, &m->Wp2, ((size_t)256 * 256) << wd));
+  TRY(dev_alloc(bag, &m->Wp3, ((size_t)ZP * 256) << wd));
+  TRY(dev_alloc(bag, &m->Wh1, ((size_t)MAX_HEADS * 256 * m->KH) << wd));
+  TRY(dev_alloc(bag, &m->Wh2, ((size_t)MAX_HEADS * 256 * 256) << wd));
+  TRY(dev_alloc(bag, &m->Wh3, ((size_t)MAX_HEADS * 256 * 256) << wd));
   TRY(dev_alloc(bag, &m->b_ih, (size_t)3 * D));
   TRY(dev_alloc(bag, &m->b_hh, (size_t)3 * D));
   TRY(dev_alloc(bag, &m->p1_b, (size_t)m->bnp1)); TRY(dev_alloc(bag, &m->p1_g, (size_t)m->bnp1)); TRY(dev_alloc(bag, &m->p1_be, (size_t)m->bnp1));
@@ -414,21 +424,21 @@ extern "C" int drm_rssm_create(const drm_dims* dims, drm_rssm** out) {
   // ---- TMA descriptors of the packed weights (box = {64, rows per tile})
   for (int v = 0; v < 2; ++v) {
     const int U = 32 << v;
-    TRY(make_tmap_bf16_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U));
-    TRY(make_tmap_bf16_2d(&m->tmWgruQ[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, U / 2));
+    TRY(make_tmap_op_2d(&m->tmWgru2[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, 3 * U, wd));
+    TRY(make_tmap_op_2d(&m->tmWgruQ[v], m->Wgru2[v], (uint64_t)m->gru_tiles2[v] * 3 * U, m->KG, m->KG, U / 2, wd));
   }
-  TRY(make_tmap_bf16_2d(&m->tmWp1, m->Wp1, 256, DP, DP, m->bnp1));
-  TRY(make_tmap_bf16_2d(&m->tmWp2, m->Wp2, 256, 256, 256, m->bnp2));
-  TRY(make_tmap_bf16_2d(&m->tmWp1q, m->Wp1, 256, DP, DP, 64));
-  TRY(make_tmap_bf16_2d(&m->tmWp2q, m->Wp2, 256, 256, 256, 64));
-  TRY(make_tmap_bf16_2d(&m->tmWh1q, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, 64));
-  TRY(make_tmap_bf16_2d(&m->tmWh2q, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, 64));
-  TRY(make_tmap_bf16_2d(&m->tmWp3, m->Wp3, ZP, 256, 256, 256));
-  TRY(make_tmap_bf16_2d(&m->tmWp3h, m->Wp3, ZP, 256, 256, 128));
-  TRY(make_tmap_bf16_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1));
-  TRY(make_tmap_bf16_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2));
-  TRY(make_tmap_bf16_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256));
-  TRY(make_tmap_bf16_2d(&m->tmWh3a, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 32));
+  TRY(make_tmap_op_2d(&m->tmWp1, m->Wp1, 256, DP, DP, m->bnp1, wd));
+  TRY(make_tmap_op_2d(&m->tmWp2, m->Wp2, 256, 256, 256, m->bnp2, wd));
+  TRY(make_tmap_op_2d(&m->tmWp1q, m->Wp1, 256, DP, DP, 64, wd));
+  TRY(make_tmap_op_2d(&m->tmWp2q, m->Wp2, 256, 256, 256, 64, wd));
+  TRY(make_tmap_op_2d(&m->tmWh1q, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, 64, wd));
+  TRY(make_tmap_op_2d(&m->tmWh2q, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, 64, wd));
+  TRY(make_tmap_op_2d(&m->tmWp3, m->Wp3, ZP, 256, 256, 256, wd));
+  TRY(make_tmap_op_2d(&m->tmWp3h, m->Wp3, ZP, 256, 256, 128, wd));
+  TRY(make_tmap_op_2d(&m->tmWh1, m->Wh1, (uint64_t)MAX_HEADS * 256, m->KH, m->KH, m->bnh1, wd));
+  TRY(make_tmap_op_2d(&m->tmWh2, m->Wh2, (uint64_t)MAX_HEADS * 256, 256, 256, m->bnh2, wd));
+  TRY(make_tmap_op_2d(&m->tmWh3, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 256, wd));
+  TRY(make_tmap_op_2d(&m->tmWh3a, m->Wh3, (uint64_t)MAX_HEADS * 256, 256, 256, 32, wd));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rssm_destroy(m);
@@ -464,7 +474,7 @@ extern "C" int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* strea
   for (const MatOp& op : m->mat_ops) {
     if (!src[op.src]) continue;  // optional head (critic) absent
     pack_matrix_kernel<<<grid_for((long)op.nrows * op.ncols), 256, 0, st>>>(op.dst, op.ld_dst, op.row0, op.nrows, op.col0, op.ncols,
-                                                                         src[op.src], op.ld_src, op.row_map, op.col_map);
+                                                                         src[op.src], op.ld_src, op.row_map, op.col_map, m->wide);
     DRM_LAUNCH_CHECK();
   }
   for (const VecOp& op : m->vec_ops) {
@@ -495,15 +505,15 @@ extern "C" int drm_rollout_create(drm_rssm* m, int32_t B, int32_t H, drm_rollout
   r->m = m; r->B = B; r->H = H; r->Mp = round_up(B, BM);
   int rc = DRM_OK;
 #define TRY(x) if (rc == DRM_OK) rc = (x)
-  for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->S[i], (size_t)r->Mp * m->KS));
-  TRY(dev_alloc(r->allocs, &r->Y1, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
-  TRY(dev_alloc(r->allocs, &r->Y2, (size_t)(MAX_HEADS + 1) * r->Mp * 256));
-  for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM));
-  TRY(make_tmap_bf16_2d(&r->tmY1, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
-  TRY(make_tmap_bf16_2d(&r->tmY2, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM));
-  for (int i = 0; i < 2; ++i) TRY(make_tmap_bf16_2d(&r->tmS_s[i], r->S[i], r->Mp, m->KS, m->KS, SMALL_A_ROWS));
-  TRY(make_tmap_bf16_2d(&r->tmY1_s, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS));
-  TRY(make_tmap_bf16_2d(&r->tmY2_s, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS));
+  for (int i = 0; i < 2; ++i) TRY(dev_alloc(r->allocs, &r->S[i], ((size_t)r->Mp * m->KS) << m->wide));
+  TRY(dev_alloc(r->allocs, &r->Y1, ((size_t)(MAX_HEADS + 1) * r->Mp * 256) << m->wide));
+  TRY(dev_alloc(r->allocs, &r->Y2, ((size_t)(MAX_HEADS + 1) * r->Mp * 256) << m->wide));
+  for (int i = 0; i < 2; ++i) TRY(make_tmap_op_2d(&r->tmS[i], r->S[i], r->Mp, m->KS, m->KS, BM, m->wide));
+  TRY(make_tmap_op_2d(&r->tmY1, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM, m->wide));
+  TRY(make_tmap_op_2d(&r->tmY2, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, BM, m->wide));
+  for (int i = 0; i < 2; ++i) TRY(make_tmap_op_2d(&r->tmS_s[i], r->S[i], r->Mp, m->KS, m->KS, SMALL_A_ROWS, m->wide));
+  TRY(make_tmap_op_2d(&r->tmY1_s, r->Y1, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS, m->wide));
+  TRY(make_tmap_op_2d(&r->tmY2_s, r->Y2, (uint64_t)(MAX_HEADS + 1) * r->Mp, 256, 256, SMALL_A_ROWS, m->wide));
 #undef TRY
   if (rc != DRM_OK) {
     drm_rollout_destroy(r);
@@ -555,6 +565,12 @@ static void small_a(GemmCommon& g, const CUtensorMap* small) {
     g.a_bytes = SMALL_A_ROWS * BK * 2;
   }
 }
+// TF32 mode: k-block counts were written in 64-element units; a 128-byte k-block holds 32 fp32 elements, and every block boundary
+// of the state / weight layouts is a multiple of 64 elements, so offsets and counts simply double.
+static void set_precision(GemmCommon& g, const drm_rssm* m) {
+  g.wide = m->wide;
+  if (m->wide) { g.ka0 *= 2; g.nka0 *= 2; g.ka1 *= 2; g.nka1 *= 2; }
+}
 // GRU: src = [z | a | h_t]  ->  h_{t+1} (fp32 h_out, bf16 into dst's h columns)
 static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const float* h_prev, long ld_hprev, float* h_out,
                      long ld_hout, int M, cudaStream_t st, bool allow_ksplit = false) {
@@ -568,13 +584,14 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
   g.ka0 = 0; g.nka0 = m->ZP / 64 + 1;                 // x part: z blocks + the action block
   g.ka1 = m->ZP / 64 + 1; g.nka1 = m->DP / 64;        // h part
   small_a(g, src.tmS_s);
+  set_precision(g, m);
   const dim3 grid(mt, m->gru_tiles2[v]);
-  __nv_bfloat16* s_h = dst.S + (long)dst.row0 * m->KS + m->ZP + 64;
+  __nv_bfloat16* s_h = opnd_at(dst.S, (long)dst.row0 * m->KS + m->ZP + 64, m->wide);
   // CTA pairs (cta_group::2): two m-tiles issue one M = 256 MMA, each SM stages half of the weight tile (gru_pair.cuh).
   // Measured: 16 384 rows, D = 4096: 897 -> 1057 TFLOP/s; D = 600: 647 -> 720; 1024 rows (76 pairs of U = 32 tiles): 21.6 -> 24.4 us,
   // so the automatic choice pairs only the wide-tile (large-grid) configuration.
   const bool pair = opts().gru_pair < 0 ? v == 1 : opts().gru_pair != 0;
-  if (pair && mt >= 2) {
+  if (pair && mt >= 2 && !m->wide) {   // (TF32 mode runs on the one-CTA-per-tile kernel only)
     g.tmB = m->tmWgruQ[v];
     g.a_bytes = 0;
     g.band = opts().gru_band & ~1;
@@ -587,7 +604,7 @@ static int stage_gru(drm_rssm* m, const WsView& src, const WsView& dst, const fl
   }
   // (allow_ksplit: the posterior scan and the step-level entry point; drm_rollout_run keeps kernels whose per-row arithmetic does
   // not depend on the batch size, so that shards of a rollout concatenate bit-exactly to the full batch)
-  if (allow_ksplit && opts().gru_ksplit && mt <= 1 && mt * m->gru_tiles2[0] <= 148) {
+  if (allow_ksplit && opts().gru_ksplit && mt <= 1 && mt * m->gru_tiles2[0] <= 148 && !m->wide) {
     // tiny grid (the 16-sequence posterior scan, the B = 1 acting path, warm starts): x part and h part of every tile on two
     // CTAs of a cluster, rows swapped for the epilogue (gru_ksplit.cuh).  Measured per imagined step at D = 600: 128 rows
     // 62.1 -> 59.4 us, 256 rows 62.9 -> 65.1 us, 512 rows 66.2 -> 67.7 us, 896 rows 66.0 -> 66.8 us; a 48-unit-tile variant that
@@ -610,7 +627,7 @@ template <bool HAS_ADD>
 static int launch_ln(GemmCommon g, const CUtensorMap& tmB_full, const CUtensorMap& tmB_q, int bn_full,
                      typename EpiLnSiluT<HAS_ADD>::Params p, int mt, int n_slots, cudaStream_t st, int stage_id) {
   g.b_slot_rows = 256;
-  if (opts().ln_cluster && mt * n_slots <= 37) {
+  if (opts().ln_cluster && mt * n_slots <= 37 && !g.wide) {
     g.tmB = tmB_q;
     g.bn = 64;
     return launch_gemm<EpiLnSiluN4T<HAS_ADD>>(g, p, dim3(mt, n_slots, 4), st, stage_id);
@@ -630,6 +647,7 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.a_row0 = v.row0;
     g.ka0 = m->ZP / 64 + 1; g.nka0 = m->DP / 64;
     g.n_slots = 1; g.y_slot[0] = 0;
+    set_precision(g, m);
     EpiLnSilu::Params p{m->p1_b, m->p1_g, m->p1_be, nullptr, 0, v.Y1, 256, v.row0, v.slot_rows, m->d.h_prior[0], 1e-5f, m->bnp1};
     RC(launch_ln<false>(g, m->tmWp1, m->tmWp1q, m->bnp1, p, mt, 1, st, DRM_STAGE_PRIOR_L1));
   }
@@ -639,6 +657,7 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[0], 64);
     g.n_slots = 1; g.y_slot[0] = 0;
+    set_precision(g, m);
     EpiLnSilu::Params p{m->p2_b, m->p2_g, m->p2_be, nullptr, 0, v.Y2, 256, v.row0, v.slot_rows, m->d.h_prior[1], 1e-5f, m->bnp2};
     RC(launch_ln<false>(g, m->tmWp2, m->tmWp2q, m->bnp2, p, mt, 1, st, DRM_STAGE_PRIOR_L2));
   }
@@ -648,7 +667,8 @@ static int stage_prior(drm_rssm* m, const WsView& v, const float* uniforms, floa
     small_a(g, v.tmY2_s);
     g.a_row0 = v.row0;
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_prior[1], 64);
-    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? v.S + (long)v.row0 * m->KS : nullptr, nullptr,
+    set_precision(g, m);
+    EpiCat::Params p{m->p3_b, uniforms, latent, logits, idx, write_sz ? opnd_at(v.S, (long)v.row0 * m->KS, m->wide) : nullptr, nullptr,
                      ld_latent, ld_logits, ld_idx, 0, m->KS, m->d.R, rm};
     RC(launch_gemm<EpiCat>(g, p, dim3(mt, m->ZP / bn), st, DRM_STAGE_PRIOR_CAT));
   }
@@ -675,6 +695,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
     small_a(g, v.tmS_s);
+    set_precision(g, m);
     EpiLnSilu::Params p{m->h1_b, m->h1_g, m->h1_be, nullptr, 0, v.Y1, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[0], 1e-5f, m->bnh1};
     RC(launch_ln<false>(g, m->tmWh1, m->tmWh1q, m->bnh1, p, mt, n_slots, st, DRM_STAGE_HEADS_L1));
   }
@@ -685,6 +706,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[0], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    set_precision(g, m);
     EpiLnSilu::Params p{m->h2_b, m->h2_g, m->h2_be, nullptr, 0, v.Y2, 256, v.slot_rows + v.row0, v.slot_rows, m->d.h_head[1], 1e-5f, m->bnh2};
     RC(launch_ln<false>(g, m->tmWh2, m->tmWh2q, m->bnh2, p, mt, n_slots, st, DRM_STAGE_HEADS_L2));
   }
@@ -695,6 +717,7 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
     g.ka0 = 0; g.nka0 = ceil_div(m->d.h_head[1], 64);
     g.n_slots = n_slots;
     for (int i = 0; i < n_slots; ++i) g.y_slot[i] = slots[i];
+    set_precision(g, m);
     fill_heads(m, hp);
     RC(launch_gemm<EpiHeads>(g, hp, dim3(mt, n_slots), st, DRM_STAGE_HEADS_OUT));
   }
@@ -702,14 +725,14 @@ static int stage_heads(drm_rssm* m, const WsView& v, const int* slots, int n_slo
 }
 
 static int pack_cols(__nv_bfloat16* S, int ld_s, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
-                     long ld_copy, cudaStream_t st) {
-  pack_state_kernel<<<grid_for((long)N * ncols), 256, 0, st>>>(S, ld_s, col0, src, ld_src, ncols, N, copy, ld_copy);
+                     long ld_copy, cudaStream_t st, int wide = 0) {
+  pack_state_kernel<<<grid_for((long)N * ncols), 256, 0, st>>>(S, ld_s, col0, src, ld_src, ncols, N, copy, ld_copy, wide);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
 static int pack_state(drm_rollout* r, int sb, int col0, const float* src, long ld_src, int ncols, int N, float* copy,
                       long ld_copy, cudaStream_t st) {
-  return pack_cols(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy, st);
+  return pack_cols(r->S[sb], r->m->KS, col0, src, ld_src, ncols, N, copy, ld_copy, st, r->m->wide);
 }
 
 // One lane of an imagination rollout: start states [b0, b0 + M) of the workspace, every pointer is the FULL tensor's base.
@@ -724,17 +747,17 @@ static int rollout_lane(drm_rollout* r, int b0, int M, const float* z0, const fl
   rewards += (long)b0 * H; continues += (long)b0 * H;
   if (idx) idx += (long)b0 * H * R;
   auto view = [&](int sb) { WsView v = view_of(r, sb); v.row0 = b0; return v; };
-  auto S_rows = [&](int sb) { return r->S[sb] + (long)b0 * m->KS; };
+  auto S_rows = [&](int sb) { return opnd_at(r->S[sb], (long)b0 * m->KS, m->wide); };
   // t = 0 state into S[0]; latent[:, 0] = z0, hidden[:, 0] = h0
-  RC(pack_cols(S_rows(0), m->KS, 0, z0, ZP, ZP, M, latent, ldL, st));
-  RC(pack_cols(S_rows(0), m->KS, ZP + 64, h0, D, D, M, hidden, ldH, st));
+  RC(pack_cols(S_rows(0), m->KS, 0, z0, ZP, ZP, M, latent, ldL, st, m->wide));
+  RC(pack_cols(S_rows(0), m->KS, ZP + 64, h0, D, D, M, hidden, ldH, st, m->wide));
   const int actor_only[1] = {HS_ACTOR};
   const int all3[3] = {HS_REWARD, HS_CONT, HS_ACTOR};
   {
     EpiHeads::Params hp;
     memset(&hp, 0, sizeof(hp));
     hp.normals = normals; hp.ld_normals = A; hp.mu = mu; hp.sigma = sigma; hp.action = actions; hp.ld_act = ldA;
-    hp.s_a = S_rows(0) + ZP; hp.ld_s = m->KS;
+    hp.s_a = opnd_at(S_rows(0), ZP, m->wide); hp.ld_s = m->KS;
     RC(stage_heads(m, view(0), actor_only, 1, hp, M, st));
   }
   for (int t = 0; t < H; ++t) {
@@ -752,7 +775,7 @@ static int rollout_lane(drm_rollout* r, int b0, int M, const float* z0, const fl
       hp.ld_normals = A;
       hp.mu = mu + (long)(t + 1) * A; hp.sigma = sigma + (long)(t + 1) * A; hp.action = actions + (long)(t + 1) * A;
       hp.ld_act = ldA;
-      hp.s_a = S_rows(nxt) + ZP; hp.ld_s = m->KS;
+      hp.s_a = opnd_at(S_rows(nxt), ZP, m->wide); hp.ld_s = m->KS;
     }
     RC(stage_heads(m, view(nxt), all3, more ? 3 : 2, hp, M, st));
   }
@@ -777,7 +800,7 @@ extern "C" int drm_rollout_run(drm_rollout* r, const float* z0, const float* h0,
   // One persistent kernel for the whole horizon when its static schedule fits the machine (rollout_persist.cuh); the
   // launch-per-stage chain otherwise (large batches, where every stage fills the machine and is throughput bound), while the
   // launch-per-stage timeline probe is on, or with option "persist" = 0.
-  if (opts().persist && !g_timeline && persist_eligible(r))
+  if (opts().persist && !g_timeline && !r->m->wide && persist_eligible(r))
     return rollout_persist(r, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
   return rollout_lane(r, 0, r->B, z0, h0, uniforms, normals, latent, hidden, actions, rewards, continues, mu, sigma, idx, st);
 }
@@ -789,6 +812,7 @@ extern "C" int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n) {
   DRM_REQUIRE(r && out && n >= 5, DRM_ERR_ARG, "drm_rollout_info: bad argument");
   for (int i = 0; i < n; ++i) out[i] = 0;
   if (!(r->ps && r->ps->tried)) RC(check_arch());   // (no CUDA call once the plan exists: this must still answer after a trapped launch)
+  if (r->m->wide) return DRM_OK;   // TF32 handles run launch by launch
   const bool ok = opts().persist && persist_eligible(r);
   out[0] = ok ? 1u : 0u;
   if (!r->ps || !r->ps->ok) return DRM_OK;
@@ -810,7 +834,7 @@ extern "C" int drm_rollout_info(drm_rollout* r, uint32_t* out, int32_t n) {
 extern "C" int drm_rollout_trace(drm_rollout* r, int32_t j0, int32_t nj, unsigned long long* out, int64_t n_words) {
   DRM_REQUIRE(r, DRM_ERR_ARG, "drm_rollout_trace: NULL workspace");
   RC(check_arch());
-  DRM_REQUIRE(persist_eligible(r), DRM_ERR_ARG, "drm_rollout_trace: this workspace does not use the persistent kernel");
+  DRM_REQUIRE(!r->m->wide && persist_eligible(r), DRM_ERR_ARG, "drm_rollout_trace: this workspace does not use the persistent kernel");
   drm_persist* ps = r->ps;
   const size_t words = (size_t)ps->n_cta * PS_TRACE_SLOTS * 8 * 2;   // tile records, then the epilogue-lap records
   if (!out) {
@@ -924,6 +948,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "small_a") o.small_a = value != 0;
   else if (n == "conv_persist") o.conv_persist = value != 0;
   else if (n == "conv_implicit") o.conv_implicit = value != 0;
+  else if (n == "conv_chunk") o.conv_chunk = value >= 16 ? value : 512;
   else if (n == "gru_ksplit") o.gru_ksplit = value != 0;
   else if (n == "persist") o.persist = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }

@@ -16,13 +16,6 @@
 
 namespace drm {
 
-// debug switches read once per process (A/B runs of the conv-path variants)
-static bool env_off(const char* name, int slot) {
-  static int cache[2] = {-1, -1};
-  if (cache[slot] < 0) cache[slot] = getenv(name) != nullptr;
-  return cache[slot] != 0;
-}
-
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -320,6 +313,7 @@ static inline int ct_d(int p, int t) { return t == 0 ? 0 : (p == 0 ? -1 : 1); }
 extern "C" int drm_vae_create(drm_rssm* m, const drm_vae_dims* dims, drm_vae** out) {
   RC(check_arch());
   DRM_REQUIRE(m && dims && out, DRM_ERR_ARG, "drm_vae_create: NULL argument");
+  DRM_REQUIRE(!m->wide, DRM_ERR_ARG, "drm_vae_create: the observe / VAE path runs on DRM_PRECISION_BF16 handles only");
   const drm_vae_dims d = *dims;
   DRM_REQUIRE(d.H >= 16 && d.W >= 16 && d.H % 16 == 0 && d.W % 16 == 0, DRM_ERR_SHAPE, "drm_vae_create: H, W must be multiples of 16");
   DRM_REQUIRE(d.e1 >= 1 && d.e2 >= 1 && d.d1 >= 1 && d.d2 >= 1 && 4 * d.e2 <= 256 && 4 * d.d2 <= 256 && d.e1 <= 256 && d.d1 <= 256,
@@ -483,8 +477,7 @@ extern "C" int drm_observe_create(drm_rssm* m, drm_vae* v, int32_t B, int32_t T,
   o->rows_p = round_up(o->rows, BM) + BM;
   const int NF = T * B;
   {
-    const char* e = getenv("DRM_FC");
-    const int fc = e ? atoi(e) : 512;   // frames per conv chunk: 512 measured best (4.37 -> 3.94 ms per 1024-frame forward vs 128); scratch ~0.5 GB
+    const int fc = opts().conv_chunk;   // frames per conv chunk: 512 measured best (4.37 -> 3.94 ms per 1024-frame forward vs 128); scratch ~0.5 GB
     o->FC = NF < fc ? NF : fc;
   }
   const int H = v->d.H, W = v->d.W;
@@ -613,7 +606,7 @@ static int encoder_conv_chunk(drm_observe* o, const float* obs, int f0, int nf, 
     __nv_bfloat16* dst = i == 3 ? o->feat + (long)f0 * v->Kf : cur;
     EpiPlain::Params p{v->be[i], nullptr, dst, 0, (long)v->ebn[i + 1], v->ebn[i + 1], 1, 0, RowMap{0, 0, 0, 0}};
     if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 1, st));
-    else if (v->ebn[i + 1] <= 64 && !env_off("DRM_NO_PLAIN_S", 0)) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
+    else if (v->ebn[i + 1] <= 64) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div(M, BM), 1), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div(M, BM), 1), st));
     if (i == 3) break;
     if (!implicit_next) RC(encoder_patch_gather(o, cur, nf, hs, ws, i, st));
@@ -639,7 +632,7 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
       for (int ty = 0; ty < 2; ++ty)
         for (int tx = 0; tx < 2; ++tx) { tp.t[ph].dy[ty * 2 + tx] = ct_d(ph >> 1, ty); tp.t[ph].dx[ty * 2 + tx] = ct_d(ph & 1, tx); }
     }
-    if (j == 3 && (v->dbn[3] == 32 || v->dbn[3] == 16 || v->dbn[3] == 8 || v->dbn[3] == 64) && !env_off("DRM_NO_DIRECT_CONVT", 1)) {
+    if (j == 3 && (v->dbn[3] == 32 || v->dbn[3] == 16 || v->dbn[3] == 8 || v->dbn[3] == 64)) {
       // image layer: direct kernel, no patch matrix (see convt_last_direct_kernel)
       const int grid = grid_for(rows);
 #define DRM_CT_LAST(CPV) convt_last_direct_kernel<CPV><<<grid, 256, 0, st>>>(src, v->Wdc[3], v->bdc[3], mu_out, rows, hs, ws, v->dbn[4], 3, v->DK[3])
@@ -666,7 +659,7 @@ static int decoder_conv_chunk(drm_observe* o, const __nv_bfloat16* act0, int nf,
     EpiPlain::Params p{v->bdc[j], nullptr, dst, 0, (long)v->dbn[j + 1], v->dbn[j + 1], 1, 1, RowMap{2, hs, ws, 0}};
     if (j == 3) { p.out_f32 = mu_out; p.out_bf16 = nullptr; p.ld_f32 = 0; p.N = 3; p.act = 2; p.rm = RowMap{3, hs, ws, 0}; }
     if (use_conv_persist(g, p)) RC(launch_conv_persist(g, p, 4, st));
-    else if (v->dbn[j + 1] <= 64 && !env_off("DRM_NO_PLAIN_S", 0)) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
+    else if (v->dbn[j + 1] <= 64) RC(launch_gemm<EpiPlainS>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     else RC(launch_gemm<EpiPlain>(g, p, dim3(ceil_div((int)rows, BM), 4), st));
     hs <<= 1; ws <<= 1;
     src = dst;

@@ -257,14 +257,20 @@ class PackedRssm(_NoCopy):
     Call :meth:`pack` again after every optimiser step -- the packed weights are a cache.
     """
 
-    def __init__(self, D: int, R: int, C_: int, A: int, NB: int, h_prior, h_head):
+    PRECISIONS = {"bf16": 0, "tf32": 1}   # DRM_PRECISION_*
+
+    def __init__(self, D: int, R: int, C_: int, A: int, NB: int, h_prior, h_head, precision: str = "bf16"):
+        """precision "tf32": fp32 operands rounded to TF32 (tcgen05.mma kind::tf32) -- the class the reference's own GPU runs use
+        (train_car_racer.py:13); rollout / step-level calls only, on the launch-per-stage kernels."""
         self.dims = L.DrmDims(D, R, C_, A, NB, (C.c_int32 * 2)(*h_prior), (C.c_int32 * 2)(*h_head))
         self.D, self.R, self.C, self.A, self.NB = D, R, C_, A, NB
+        self.precision = precision
         self.handle = C.c_void_p()
-        L.check(L.load().drm_rssm_create(C.byref(self.dims), C.byref(self.handle)), "rssm_create")
+        L.check(L.load().drm_rssm_create_ex(C.byref(self.dims), self.PRECISIONS[precision], C.byref(self.handle)), "rssm_create")
 
     @classmethod
-    def from_state_dict(cls, sd: Dict[str, torch.Tensor], R: int = 32, C_: int = 32, D: Optional[int] = None, A: int = 3):
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], R: int = 32, C_: int = 32, D: Optional[int] = None, A: int = 3,
+                        precision: str = "bf16"):
         """Build from any subset of the reference state_dict (a full Dreamer, or one module's slice)."""
         g = "world_model.sequence_model.GRU."
         heads = [p for p in ("world_model.reward_predictor.logit_net", "world_model.continue_predictor.logit_generator",
@@ -291,7 +297,7 @@ class PackedRssm(_NoCopy):
         if len(sizes) != 1:
             raise RuntimeError("dreamer_b200: reward / continue / actor / critic MLPs must share hidden sizes "
                                f"(got {sorted(sizes)}); the fused head stage batches them in one launch")
-        obj = cls(D, R, C_, A, NB, hp, sizes.pop())
+        obj = cls(D, R, C_, A, NB, hp, sizes.pop(), precision=precision)
         obj.pack(sd)
         return obj
 

@@ -196,6 +196,14 @@ typedef struct drm_rssm drm_rssm;       /* packed bf16 weights (a cache: re-pack
 typedef struct drm_rollout drm_rollout; /* workspace + TMA descriptors for a fixed (B, H) */
 
 int drm_rssm_create(const drm_dims* dims, drm_rssm** out);
+/* The same with an explicit operand precision.  DRM_PRECISION_BF16 (drm_rssm_create): bf16 operands, fp32 accumulation -- the
+ * north star's "bf16 <= 1e-2" mode and the only one the persistent kernels, the observe / VAE path and the CTA-pair / cluster
+ * stage variants implement.  DRM_PRECISION_TF32: fp32 state, activations and packed weights rounded to TF32, tcgen05.mma
+ * kind::tf32 -- the precision class the reference itself runs its imagination path in on a GPU
+ * (torch.backends.cuda.matmul.allow_tf32, train_car_racer.py:13); launch-per-stage kernels, rollout / step-level entry points only
+ * (drm_vae_create rejects such a handle). */
+enum { DRM_PRECISION_BF16 = 0, DRM_PRECISION_TF32 = 1 };
+int drm_rssm_create_ex(const drm_dims* dims, int32_t precision, drm_rssm** out);
 int drm_rssm_pack(drm_rssm* m, const drm_rssm_weights* w, void* stream);
 int drm_rssm_destroy(drm_rssm* m);
 

@@ -4,6 +4,7 @@ the free-running draws.  The table is written to gpurun_out/parity_table.json / 
 every row is asserted against the north star's bound:
 
     bf16-operand quantities:  max |got - ref|  <=  1e-2 * max |ref|      (relative to the tensor's scale)
+    TF32 mode (DRM_PRECISION_TF32): the same quantities, bound 1.25e-3 (three more mantissa bits: an eighth of the bf16 bound)
     fp32 kernels:             max |got - ref|  <=  1e-4 * max(1, max |ref|)
 
 Rows whose bound is looser say why in `note`.
@@ -29,7 +30,7 @@ def _row(config, quantity, got, ref, bound=1e-2, kind="bf16", note=""):
     assert got.shape == ref.shape, (config, quantity, got.shape, ref.shape)
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
-    denom = scale if kind == "bf16" else max(1.0, scale)
+    denom = scale if kind in ("bf16", "tf32") else max(1.0, scale)
     rel = err / max(denom, 1e-30)
     ROWS.append(dict(config=config, quantity=quantity, kind=kind, max_abs_err=err, ref_scale=scale, rel_to_scale=rel, bound=bound, note=note))
     assert rel <= bound, f"{config} / {quantity}: max |err| {err:.4g} = {rel:.3g} of the tensor's scale {scale:.3g} (bound {bound})"
@@ -66,20 +67,26 @@ def _write_table():
         pass
 
 
-def _model(ops, cfg, seed):
+TF32_BOUND = 1.25e-3   # TF32 keeps 10 mantissa bits against bf16's 7: an eighth of the bf16 bound
+
+
+def _model(ops, cfg, seed, precision="bf16"):
     sd = W.make_state_dict(cfg, seed=seed)
     dsd = {k: v.to(DEV) for k, v in sd.items()}
-    return sd, dsd, ops.PackedRssm.from_state_dict(dsd)
+    return sd, dsd, ops.PackedRssm.from_state_dict(dsd, precision=precision)
 
 
 @pytest.mark.parametrize("fixture,name", [("rollout_small.npz", "small 6x5 (reference fixture)"), ("rollout_ref_digest.npz", "ref sizes 32x15 (reference fixture)")])
-@pytest.mark.parametrize("persist", [1, 0])
+@pytest.mark.parametrize("persist", [1, 0, "tf32"])
 def test_rollout_vs_reference_fixture(ops, golden_dir, fixture, name, persist):
     from dreamer_b200 import _lib as L
     g = np.load(os.path.join(golden_dir, fixture))
     cfg = json.loads(str(g["cfg"]))
     B, H, seed = int(g["B"]), int(g["H"]), int(g["seed"])
-    sd, _, model = _model(ops, cfg, seed)
+    tf32 = persist == "tf32"
+    persist = 0 if tf32 else persist
+    bound, kind = (TF32_BOUND, "tf32") if tf32 else (1e-2, "bf16")
+    sd, _, model = _model(ops, cfg, seed, "tf32" if tf32 else "bf16")
     z0, h0, _, n = W.rollout_inputs(cfg, B, H, seed=seed + 1)
     ro = ops.Rollout(model, B, H)
     lib = L.load()
@@ -88,24 +95,27 @@ def test_rollout_vs_reference_fixture(ops, golden_dir, fixture, name, persist):
         out = ro.run(z0.to(DEV), h0.to(DEV), torch.from_numpy(g["uniforms_used"]).to(DEV), n.to(DEV))
     finally:
         lib.drm_set_option(b"persist", 1)
-    cfgname = f"{name}, {'persistent kernel' if persist else 'launch-per-stage'}"
+    cfgname = f"{name}, {'TF32 mode (launch-per-stage)' if tf32 else 'persistent kernel' if persist else 'launch-per-stage'}"
     _rate(cfgname, "sampled classes, whole trajectory", int((out[7].cpu().numpy() != g["idx"]).sum()), g["idx"].size, 0.0,
           "uniforms in the middle half of the reference's CDF bin")
     for key, i in (("actions", 2), ("rewards", 3), ("continues", 4), ("mu", 5), ("sigma", 6)):
-        _row(cfgname, key, out[i], torch.from_numpy(g[key]))
+        _row(cfgname, key, out[i], torch.from_numpy(g[key]), bound, kind)
     if "hidden" in g.files:
-        _row(cfgname, "hidden", out[1], torch.from_numpy(g["hidden"]))
+        _row(cfgname, "hidden", out[1], torch.from_numpy(g["hidden"]), bound, kind)
     else:
-        _row(cfgname, "hidden (last step)", out[1][:, -1], torch.from_numpy(g["hidden_last"]))
+        _row(cfgname, "hidden (last step)", out[1][:, -1], torch.from_numpy(g["hidden_last"]), bound, kind)
 
 
-@pytest.mark.parametrize("persist", [1, 0])
+@pytest.mark.parametrize("persist", [1, 0, "tf32"])
 def test_rollout_c2_teacher_forced(ops, persist):
     """BASELINE config 2 (1024 x 15): every third step re-derived by the oracle from the kernel's own previous state."""
     from dreamer_b200 import _lib as L
     cfg = dict(W.REF_CONFIG, horizon=15)
     B, H = 1024, 15
-    sd, _, model = _model(ops, cfg, 0)
+    tf32 = persist == "tf32"
+    persist = 0 if tf32 else persist
+    bound, kind = (TF32_BOUND, "tf32") if tf32 else (1e-2, "bf16")
+    sd, _, model = _model(ops, cfg, 0, "tf32" if tf32 else "bf16")
     z0, h0, u, n = W.rollout_inputs(cfg, B, H, seed=1234)
     ro = ops.Rollout(model, B, H)
     lib = L.load()
@@ -115,7 +125,7 @@ def test_rollout_c2_teacher_forced(ops, persist):
     finally:
         lib.drm_set_option(b"persist", 1)
     lat, hid, act, rew, con, mu, sg, idx = out
-    name = f"C2 1024x15 teacher-forced, {'persistent kernel' if persist else 'launch-per-stage'}"
+    name = f"C2 1024x15 teacher-forced, {'TF32 mode (launch-per-stage)' if tf32 else 'persistent kernel' if persist else 'launch-per-stage'}"
     steps = list(range(0, H, 3))
     refs = {k: [] for k in ("action", "mu", "sigma", "hidden", "reward", "continue")}
     gots = {k: [] for k in refs}
@@ -129,9 +139,9 @@ def test_rollout_c2_teacher_forced(ops, persist):
                           ("reward", rew[:, t], r_k), ("continue", con[:, t], c_k)):
             gots[k].append(g_); refs[k].append(r_)
     for k in refs:
-        _row(name, k, torch.stack(gots[k]), torch.stack(refs[k]))
-    _rate(name, "free-running prior draws vs the oracle's draw on the same state", mismatch, len(steps) * B * 32, 5e-3,
-          "raw uniforms: a draw flips when bf16 logits move a CDF edge across the uniform")
+        _row(name, k, torch.stack(gots[k]), torch.stack(refs[k]), bound, kind)
+    _rate(name, "free-running prior draws vs the oracle's draw on the same state", mismatch, len(steps) * B * 32, 1e-3 if tf32 else 5e-3,
+          "raw uniforms: a draw flips when bf16 / TF32 logits move a CDF edge across the uniform")
     oh = lat[:, 1:].sum(-1)
     assert torch.allclose(oh, torch.ones_like(oh), atol=1e-6)
 
