@@ -429,6 +429,18 @@ def bench_rollout(hs, args, cfg, sd, B, H, desc):
                 e2e=dict(value=e2e_val, unit="states/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=res.get("d2h", 0), ms_per_step=e2e_ms / args.steps),
                 gpu_launches=int(launches_per_rollout * args.steps), clocks=clocks, roofline=roofline,
                 whole_rollout=dict(achieved_tflops=whole_tf, frac_of_bf16_sustained=whole_tf / peaks["bf16_sustained"], flops_per_state=fl["total"]))
+    if args.workload == "c2":
+        # the same rollout in the TF32 mode (fp32 operands rounded to TF32, tcgen05.mma kind::tf32: the precision class the reference's own
+        # GPU runs use, train_car_racer.py:13) -- launch-per-stage kernels, replayed as one CUDA graph, device-resident inputs
+        model32 = ops.PackedRssm.from_state_dict({k: v.to(dev) for k, v in sd.items()}, precision="tf32")
+        ro32 = ops.Rollout(model32, B, H)
+        step32 = lambda: ro32.run_graphed(z0d, h0d, ud, nd, want_idx=False)
+        for _ in range(4):
+            step32()
+        ms32 = hs.timed(step32, args.steps, 1)
+        line["tf32_mode"] = dict(value=states * args.steps / (ms32 * 1e-3), unit="states/s", ms_per_step=ms32 / args.steps,
+                                 note="DRM_PRECISION_TF32 handle; parity bound 1.25e-3 of the tensor's scale (profiles/parity_r2.md: worst 7.8e-4), "
+                                      "7 launches per imagined step (the persistent kernel is bf16-only)")
     if world > 1:
         # the rollout itself shards with no exchange; what the same ranks exchange when they TRAIN on these rollouts is one flat gradient
         # bucket per optimiser group -- timed here (outside the timed region) so that every multi-GPU line carries the collective's cost
@@ -436,7 +448,7 @@ def bench_rollout(hs, args, cfg, sd, B, H, desc):
         coll["note"] = ("not part of this workload: the world model's 31 MB gradient bucket all-reduced alone over NCCL (what --workload c5 "
                         "runs inside every training iteration)")
         line["collective"] = coll
-    return line, [ro]
+    return line, [ro] + ([ro32] if args.workload == "c2" else [])
 
 
 def bench_wm(hs, args, cfg, sd, B, T, desc):
