@@ -70,6 +70,7 @@ SIGNATURES = {
     "drm_ln_silu_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, c_stream]),
     "drm_actor_head_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, c_stream]),
     "drm_gru_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int64, C.c_int32, c_stream]),
+    "drm_gru_bwd_add": (C.c_int, [C.c_void_p] * 8 + [C.c_int32, C.c_int64, C.c_int32, c_stream]),
     "drm_categorical32_kl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_stream]),
     "drm_replay_gather": (C.c_int, [C.c_void_p] * 9 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_stream]),
     "drm_replay_insert": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_stream]),

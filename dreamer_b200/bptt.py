@@ -37,6 +37,16 @@ class _matmul_precision:
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def _acc(p: torch.nn.Parameter, g: torch.Tensor):
     if p.grad is None:
         p.grad = torch.zeros_like(p)
@@ -177,14 +187,31 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         Whh = gru.weight_hh                                                     # (3D, D)
         A1_tm = A1.view(T, B, -1)
         dz_carry = None
+        # The recurrent term dgh_t W_hh is only needed by the GRU cell backward of step t - 1, three kernels further down the chain
+        # (straight-through, posterior MLP): it runs on a side stream into its own buffer and joins there (drm_gru_bwd_add).  In a
+        # captured training step the fork / join become graph edges.
+        dHrec = torch.empty(T, B, Dh, device=dev)
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        joined = None
         for t in range(T - 1, -1, -1):
             ops.categorical32_bwd(LG[t], gZ[t], dz_carry, gLG[t], out=dLG[t])   # through the ST sample, + the KL term
             dA1 = ops.ln_silu_bwd(dLG[t] @ W2, A1_tm[t], ln1.weight, ln1.bias, ln1.eps)
-            gH[t].addmm_(dA1, W1h)                                              # d/dh_t is complete
-            ops.gru_bwd(gH[t], GI[t], GH[t], Hprev[t], dGI[t], dGH[t], gH[t - 1] if t > 0 else None, accumulate=True)
+            gH[t].addmm_(dA1, W1h)                                              # d/dh_t is complete up to the recurrent term
+            if joined is not None:
+                main.wait_event(joined)
+            ops.gru_bwd(gH[t], GI[t], GH[t], Hprev[t], dGI[t], dGH[t], gH[t - 1] if t > 0 else None, accumulate=True,
+                        dh_add=dHrec[t] if joined is not None else None)
             if t > 0:
-                gH[t - 1].addmm_(dGH[t], Whh)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    torch.mm(dGH[t], Whh, out=dHrec[t - 1])
+                    joined = torch.cuda.Event()
+                    joined.record(side)
                 dz_carry = dGI[t] @ Wih_z
+        if joined is not None:
+            main.wait_event(joined)     # (every side-stream node is an ancestor of the capture's end)
         mark("recurrence backward (T steps)")
         # ---- (3) weight gradients: batched GEMMs over all B*T rows ----------------------------------------------------
         dGI2, dGH2, dLG2 = dGI.view(T * B, -1), dGH.view(T * B, -1), dLG.view(T * B, -1)

@@ -124,6 +124,36 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
   }
 }
 
+// The same for FEW rows (the sequential BPTT step: B * R = 512 rows per call): one warp per ROW, one class per lane, so all four
+// operand rows are fetched by four independent coalesced 128-byte loads and the three row reductions are shuffle trees -- the row-per-
+// lane kernel below needs 16 warps and ~10 us of dependent load / expf latency for such a call, this one ~3 us on 64 SMs.
+__global__ void __launch_bounds__(256) categorical32_bwd_rowwarp_kernel(const float* __restrict__ logits, const float* __restrict__ dz,
+                                                                        const float* __restrict__ dz2, const float* __restrict__ dl_add,
+                                                                        float* __restrict__ dlogits, int64_t n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int64_t o = row * 32 + lane;
+  const float l = __ldg(logits + o);
+  float g = __ldg(dz + o);
+  const float g2 = dz2 ? __ldg(dz2 + o) : 0.f;
+  const float add = dl_add ? __ldg(dl_add + o) : 0.f;
+  g += g2;
+  float mx = l;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  // (summation order differs from the row-per-lane kernel's left-to-right sums: gradients agree to fp32 rounding, not bitwise)
+  const float e = expf(l - mx);
+  float sum = e;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float sft = e * (1.0f / sum);
+  float dot = sft * g;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+  dlogits[o] = 0.99f * sft * (g - dot) + add;
+}
+
 // Backward of the straight-through sample z = onehot + p - stopgrad(p), p = 0.99 softmax(l) + 0.01 / 32
 // (DynamicsPredictors.py:33-39, VariationalAutoEncoder.py:88-98):  dl = 0.99 * s * (g - sum_j s_j g_j), s = softmax(l), g = dz.
 // Same tiling as the forward: a warp owns 32 rows, coalesced float4 tile loads, one row per lane.
@@ -196,6 +226,7 @@ __global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __r
 // recomputed from the pre-activation a, two-pass like torch):  dln = dy * silu'(ln);  dxh = dln * gamma;
 //   da = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)).   dln (optional) feeds the batched dgamma / dbeta sums.
 // ------------------------------------------------------------------------------------------
+template <int J>   // J = ceil(n / 32) values per lane: 8 for the <= 256-wide hidden layers of the reference (short unrolled loops), else 32
 __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ da, float* __restrict__ dln_out, int64_t rows, int n, float eps) {
@@ -206,18 +237,19 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
   for (int64_t row = warp; row < rows; row += nwarps) {
     const float* ar = a + row * n;
     const float* dr = dy + row * n;
-    float x[32], d[32];
+    float x[J], d[J];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int c = lane + 32 * j;
       x[j] = c < n ? __ldg(ar + c) : 0.f;
+      d[j] = c < n ? __ldg(dr + c) : 0.f;   // (fetched with the pre-activation: nothing below waits on a second round trip)
       s += x[j];
     }
     const float mean = warp_sum(s) * inv_n;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int c = lane + 32 * j;
       const float t = c < n ? x[j] - mean : 0.f;
       q = fmaf(t, t, q);
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
     const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int c = lane + 32 * j;
       float dxh = 0.f, xh = 0.f;
       if (c < n) {
@@ -233,7 +265,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
         const float g = __ldg(gamma + c);
         const float ln = fmaf(xh, g, __ldg(beta + c));
         const float sg = 1.0f / (1.0f + expf(-ln));
-        const float dl = __ldg(dr + c) * (sg * (1.0f + ln * (1.0f - sg)));   // silu'(x) = sig (1 + x (1 - sig))
+        const float dl = d[j] * (sg * (1.0f + ln * (1.0f - sg)));   // silu'(x) = sig (1 + x (1 - sig))
         if (dln_out) dln_out[row * n + c] = dl;
         dxh = dl * g;
       }
@@ -243,7 +275,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
     }
     const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < J; ++j) {
       const int c = lane + 32 * j;
       if (c < n) da[row * n + c] = rstd * (d[j] - m1 - x[j] * m2);
     }
@@ -259,7 +291,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gru_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ gi,
                                                       const float* __restrict__ gh, const float* __restrict__ h_prev,
                                                       float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev,
-                                                      int accumulate, int64_t rows, int D) {
+                                                      int accumulate, int64_t rows, int D, const float* __restrict__ dh_add = nullptr) {
   const int64_t total = rows * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / D;
@@ -270,7 +302,7 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(const float* __restrict__ 
     const float u = 1.0f / (1.0f + expf(-(gi[g0 + D] + gh[g0 + D])));
     const float n = tanhf(gi[g0 + 2 * D] + r * ghn);
     const float hp = h_prev ? h_prev[i] : 0.f;
-    const float g = dh[i];
+    const float g = dh[i] + (dh_add ? dh_add[i] : 0.f);
     const float dn_pre = g * (1.0f - u) * (1.0f - n * n);
     const float du_pre = g * (hp - n) * u * (1.0f - u);
     const float dr_pre = dn_pre * ghn * r * (1.0f - r);
@@ -548,6 +580,11 @@ extern "C" int drm_categorical32_bwd(const float* logits, const float* dz, const
   DRM_REQUIRE(((uintptr_t)logits % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)dlogits % 16 == 0) &&
                   (!dz2 || (uintptr_t)dz2 % 16 == 0) && (!dl_add || (uintptr_t)dl_add % 16 == 0),
               DRM_ERR_ALIGN, "drm_categorical32_bwd: 16-byte alignment required");
+  if (n_rows <= 8192) {   // few rows: warp per row (latency-bound calls of the BPTT recurrence)
+    categorical32_bwd_rowwarp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dz2, dl_add, dlogits, n_rows);
+    DRM_LAUNCH_CHECK();
+    return DRM_OK;
+  }
   categorical32_bwd_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dz2, dl_add, dlogits, n_rows);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
@@ -559,7 +596,8 @@ extern "C" int drm_ln_silu_bwd(const float* dy, const float* a, const float* gam
   DRM_REQUIRE(rows >= 0 && n >= 1 && n <= 1024, DRM_ERR_SHAPE, "drm_ln_silu_bwd: n must be in [1, 1024]");
   if (rows == 0) return DRM_OK;
   DRM_REQUIRE(dy && a && gamma && beta && da, DRM_ERR_ARG, "drm_ln_silu_bwd: NULL pointer");
-  ln_silu_bwd_kernel<<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
+  if (n <= 256) ln_silu_bwd_kernel<8><<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
+  else ln_silu_bwd_kernel<32><<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -573,6 +611,21 @@ extern "C" int drm_gru_bwd(const float* dh, const float* gi, const float* gh, co
   const int64_t total = rows * D;
   const int64_t want = (total + 255) / 256;
   gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+// drm_gru_bwd with dh = dh + dh_add: the recurrent term dgh_{t+1} W_hh of the BPTT walk is produced by a GEMM on a side stream and
+// joins here instead of through an extra accumulation pass over dh.
+extern "C" int drm_gru_bwd_add(const float* dh, const float* dh_add, const float* gi, const float* gh, const float* h_prev, float* dgi,
+                               float* dgh, float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 0 && D >= 1, DRM_ERR_SHAPE, "drm_gru_bwd_add: bad shape");
+  if (rows == 0) return DRM_OK;
+  DRM_REQUIRE(dh && gi && gh && dgi && dgh, DRM_ERR_ARG, "drm_gru_bwd_add: NULL pointer");
+  const int64_t total = rows * D;
+  const int64_t want = (total + 255) / 256;
+  gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D, dh_add);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -92,14 +92,19 @@ def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, o
     return (da, dln) if want_dln else da
 
 
-def gru_bwd(dh, gi, gh, h_prev, dgi, dgh, dh_prev=None, accumulate: bool = False):
-    """Elementwise backward of one GRUCell step (drm_gru_bwd); writes dgi, dgh (rows, 3D) and dh_prev (=|+=) dh * u."""
+def gru_bwd(dh, gi, gh, h_prev, dgi, dgh, dh_prev=None, accumulate: bool = False, dh_add=None):
+    """Elementwise backward of one GRUCell step (drm_gru_bwd); writes dgi, dgh (rows, 3D) and dh_prev (=|+=) dh * u.
+    ``dh_add`` (optional, same shape as dh) is added to dh (drm_gru_bwd_add)."""
     rows, Dh = dh.shape
-    for t in (dh, gi, gh, h_prev, dgi, dgh, dh_prev):
+    for t in (dh, gi, gh, h_prev, dgi, dgh, dh_prev, dh_add):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
             raise RuntimeError("dreamer_b200.gru_bwd: fp32 contiguous CUDA tensors are required")
     if gi.shape != (rows, 3 * Dh) or gh.shape != gi.shape or dgi.shape != gi.shape or dgh.shape != gi.shape:
         raise RuntimeError("dreamer_b200.gru_bwd: shape mismatch")
+    if dh_add is not None:
+        L.check(L.load().drm_gru_bwd_add(L.ptr(dh), L.ptr(dh_add), L.ptr(gi), L.ptr(gh), L.ptr(h_prev), L.ptr(dgi), L.ptr(dgh), L.ptr(dh_prev),
+                                         1 if accumulate else 0, rows, Dh, L.stream()), "gru_bwd_add")
+        return
     L.check(L.load().drm_gru_bwd(L.ptr(dh), L.ptr(gi), L.ptr(gh), L.ptr(h_prev), L.ptr(dgi), L.ptr(dgh), L.ptr(dh_prev),
                                  1 if accumulate else 0, rows, Dh, L.stream()), "gru_bwd")
 

@@ -122,6 +122,9 @@ int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const float* da,
                        const float* log_sigma, float* d_head, int64_t rows, int32_t A, void* stream);
 int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
                 float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
+/* ... with dh = dh + dh_add (dh_add may be NULL): lets the recurrent term dgh W_hh arrive from a GEMM on a side stream */
+int drm_gru_bwd_add(const float* dh, const float* dh_add, const float* gi, const float* gh, const float* h_prev, float* dgi,
+                    float* dgh, float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
 /* KL balance terms of WorldModel.training_step  WorldModel.py:175-181:                         */
 /*   kl[g] = sum over the `rows_per_group` categorical rows of group g of KL(Cat(post)||Cat(prior)) */
 /* post/prior logits [n_groups * rows_per_group, 32] fp32 -> kl [n_groups] fp32.                 */
