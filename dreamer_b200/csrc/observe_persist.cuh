@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
         const EpiCat::Params p{P.e3_b, P.uniforms + (long)t_ * B * R, P.latent + (long)t_ * ZP, P.logits ? P.logits + (long)t_ * ZP : nullptr,
                                P.idx ? P.idx + (long)t_ * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, ldL, (long)T * R, 0, P.KS, R,
                                RowMap{0, 0, 0, 0}};
-        ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
+        ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); EpiCatP::stage_prev(p, P.idx_prev + (long)j * B * R, g, epi_sm, x, tid, m0); },
                        [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, g, epi_sm, taddr, m, row, part, x, tid); });
       }
       ps_cluster_handover();   // Y1 is rewritten by the next step's first layer: every rank's loads of it are done

@@ -401,6 +401,17 @@ __device__ __forceinline__ void ps_ln_compute(const EpiLnSilu::Params& p, const 
 // ------------------------------------------------------------------------------------------
 struct EpiCatP {
   using Params = EpiCat::Params;
+  // the classes whose one-hot is currently set in this tile's z columns -> shared memory, while the main loop runs (the epilogue then
+  // contains no global load at all)
+  static __device__ __forceinline__ void stage_prev(const Params& p, const uint8_t* idx_prev, const TileG& g, float* sm, int slot, int tid, int m0) {
+    uint8_t* old_sm = reinterpret_cast<uint8_t*>(sm + 2304);
+    const int G = g.bn >> 5;
+    const int ngrp = max(0, min(g.bn, p.R * 32 - slot * g.bn)) >> 5;
+    for (int i = tid; i < BM * 8; i += EPI_THREADS) {
+      const int r = i >> 3, gi = i & 7;
+      old_sm[i] = (p.s_z && m0 + r < g.M && gi < ngrp) ? __ldcg(idx_prev + (long)(m0 + r) * p.R + slot * G + gi) : (uint8_t)255;
+    }
+  }
   static __device__ __forceinline__ void run(const Params& p, uint8_t* idx_prev, const TileG& g, float* sm, uint32_t taddr,
                                              int m, int row, int part, int slot, int tid) {
     const int m0 = m - row;
@@ -409,14 +420,7 @@ struct EpiCatP {
     const int ncols = max(0, min(g.bn, p.R * 32 - col0));
     uint8_t* idx_sm = reinterpret_cast<uint8_t*>(sm + 2048);       // [128 rows][8] (sm[256, 1280) holds the uniforms)
     const int ngrp = ncols >> 5;
-    int old2[2] = {255, 255};                                      // what is set in S for the (row, latent row) pairs this thread updates below
-    if (p.s_z) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int i = tid + e * EPI_THREADS, r = i >> 3, gi = i & 7;
-        if (m0 + r < g.M && gi < ngrp) old2[e] = __ldcg(idx_prev + (long)(m0 + r) * p.R + slot * G + gi);
-      }
-    }
+    const uint8_t* old_sm = reinterpret_cast<const uint8_t*>(sm + 2304);   // [128 rows][8]: what is set in S (stage_prev, under the main loop)
 #pragma unroll 1
     for (int gi = part; gi < G; gi += EPI_PARTS) {
       float v[32];
@@ -468,7 +472,7 @@ struct EpiCatP {
         const int i = tid + e * EPI_THREADS, r = i >> 3, gi = i & 7;
         if (m0 + r >= g.M || gi >= ngrp) continue;
         uint8_t* pv = idx_prev + (long)(m0 + r) * p.R + slot * G + gi;
-        const int old = old2[e], idx = idx_sm[i];
+        const int old = old_sm[i], idx = idx_sm[i];
         unsigned short* zrow = reinterpret_cast<unsigned short*>(p.s_z + (long)(m0 + r) * p.ld_s + col0 + gi * 32);
         if (old != idx) {
           if (old != 255) zrow[old] = 0;
@@ -926,7 +930,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           const EpiCat::Params p{P.p3_b, P.uniforms + (long)(j - 1) * B * R, P.latent + (long)j * ZP, nullptr,
                                  P.idx ? P.idx + (long)(j - 1) * R : nullptr, P.S + (long)j * B * P.KS, nullptr, ldL, 0, (long)H * R, 0, P.KS, R,
                                  RowMap{0, 0, 0, 0}};
-          ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); },
+          ps_run_tile<0>(c, t, [&](int tid) { EpiCat::stage(p, g, x, epi_sm, tid, m0); EpiCatP::stage_prev(p, P.idx_prev + (long)j * B * R, g, epi_sm, x, tid, m0); },
                          [&](int tid) { EpiCatP::run(p, P.idx_prev + (long)j * B * R, g, epi_sm, taddr, m, row, part, x, tid); });
         }
         ps_cluster_handover();
