@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.ns = PS_STAGES; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.nsh = 2; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, T = P.T, D = P.D, ZP = P.ZP, R = P.R, mt = P.mt;
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
     const int gru_sub = P.a_tx + 3 * P.U * BK * 2;
     const int gru_kps = (nkh % 2 == 0) ? 2 : 1;     // one full / empty handshake per two k-blocks (the h range must be whole stages)
     const int gru_stage = gru_kps * gru_sub;
-    c.ns = (uint32_t)min(PS_MAX_STAGES, PS_HP_OFF / gru_stage);
+    c.nsh = 0;
+    while (c.nsh < 3 && (2 << c.nsh) * gru_stage <= PS_HP_OFF) ++c.nsh;
     for (int s = P.h_skip; s < T; ++s) {
       trace_window(s);
 #pragma unroll 1

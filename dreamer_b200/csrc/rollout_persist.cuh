@@ -38,6 +38,7 @@ constexpr int PS_MAX_STAGES = 8;                                   // ring depth
 constexpr int PS_STAGE_BYTES = A_STAGE_BYTES + 256 * BK * 2;       // 48 KB: A tile + up to 256 weight rows per k-block
 constexpr int PS_RING_BYTES = PS_STAGES * PS_STAGE_BYTES;          // 192 KB
 constexpr int PS_GRU_STAGE_BYTES = A_STAGE_BYTES + 192 * BK * 2;   // 40 KB: GRU CTAs (<= 192 weight rows per k-block)
+constexpr int PS_CHAIN_STAGE_BYTES = PS_RING_BYTES / 2;              // chain CTAs: two slots of 96 KB
 constexpr int PS_HP_OFF = PS_STAGES * PS_GRU_STAGE_BYTES;          // GRU CTAs: h_prev tile, 128 x 68 fp32, behind their ring
 constexpr int PS_WA_OFF = PS_HP_OFF + BM * 68 * 4;                 // GRU CTAs: action-term weights [3U] float4
 constexpr int PS_BAR_OFF = PS_RING_BYTES + 16384;
@@ -608,7 +609,7 @@ struct PsCtx {
   uint8_t* smem;
   uint64_t *full, *empty, *tmem_full;
   uint32_t tmem;
-  uint32_t ns;        // ring depth of this CTA (constant for its whole life: the ring's phase bookkeeping runs across tiles)
+  uint32_t nsh;       // log2 of the ring depth of this CTA (constant for its whole life: the ring's phase bookkeeping runs across tiles)
   uint32_t it;        // pipeline stages issued so far (ring position / phase), identical in every thread
   uint32_t tile_no;   // tiles finished so far (tmem_full phase)
   unsigned* dbg;
@@ -626,7 +627,9 @@ struct PsTile {
   int n1, b2_row, b2_koff;    // rows of the first block; row / k-block offset of the second
   int tcol;                   // TMEM column of the accumulator
   int acc0;                   // 1: the accumulator already holds a partial sum (the first MMA accumulates)
-  int kps;                    // k-blocks per pipeline stage (2 for the 64-column LN tiles: one full / empty handshake per 2 k-blocks)
+  int kps;                    // k-blocks per pipeline stage.  Every full / empty handshake (tcgen05.commit -> mbarrier -> producer -> TMA -> mbarrier)
+                              // costs ~0.3 us whatever the ring depth (profiles/scan_knobs.py: 5 k-blocks per stage in ONE slot beat 1 per stage in 8),
+                              // so the chain CTAs run TWO slots of 96 KB and put 2 - 4 k-blocks into a stage
   int stage_bytes;            // ring stride of this CTA's role
   int a_bytes;                // shared-memory bytes of the A part of a k-block (A_STAGE_BYTES, or less with a short-box tensor map)
   int a_tx;                   // bytes one A load delivers (A_STAGE_BYTES; less with a short-box tensor map: the tile's tail rows stay stale and are never stored)
@@ -656,7 +659,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   const int kps = t.kps;
   const int n_st = (nk + kps - 1) / kps;
   const int sub_bytes = t.a_bytes + t.bn * BK * 2;   // one k-block: [A | B]
-  const uint32_t NS = c.ns;
+  const uint32_t NSH = c.nsh, NSM = (1u << NSH) - 1u;   // slot = stage & mask, phase = stage >> shift
   if (warp == 0) {
     if (lane == 0) {
       if (c.tr) { c.tr[0] = t.code; c.tr[1] = ps_now(); }
@@ -671,10 +674,10 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
       auto issue = [&](int st0, int st1, const unsigned* w, unsigned tw, const unsigned* gte, unsigned tg, bool mark) {
         int st = st0;
         if (w != nullptr || gte != nullptr) {
-          const int npre = min(st1 - st0, (int)NS);
+          const int npre = min(st1 - st0, (int)NSM + 1);
           for (; st < st0 + npre; ++st) {
-            const uint32_t i = c.it + st, s = i % NS;
-            ps_mbar_wait(&c.empty[s], ((i / NS) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
+            const uint32_t i = c.it + st, s = i & NSM;
+            ps_mbar_wait(&c.empty[s], ((i >> NSH) & 1) ^ 1u, c.dbg, t.code | (1u << 20));
             const int n_sub = min(kps, nk - st * kps);
             mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
             for (int u = 0; u < n_sub; ++u) load_b(s, u, st * kps + u);
@@ -684,7 +687,7 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           fence_proxy_async_all();   // the A operand was written through the generic proxy by another SM: order it before the TMA reads
           if (mark && c.tr) c.tr[2] = ps_now();
           for (int s2 = st0; s2 < st0 + npre; ++s2) {
-            const uint32_t s = (c.it + s2) % NS;
+            const uint32_t s = (c.it + s2) & NSM;
             const int n_sub = min(kps, nk - s2 * kps);
             for (int u = 0; u < n_sub; ++u)
               tma_load_2d(c.smem + s * t.stage_bytes + u * sub_bytes, t.tmA, ps_ka(t, s2 * kps + u) * BK, t.a_row, &c.full[s]);
@@ -694,8 +697,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
           if (c.tr) c.tr[2] = ps_now();
         }
         for (; st < st1; ++st) {
-          const uint32_t i = c.it + st, s = i % NS;
-          ps_mbar_wait(&c.empty[s], ((i / NS) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
+          const uint32_t i = c.it + st, s = i & NSM;
+          ps_mbar_wait(&c.empty[s], ((i >> NSH) & 1) ^ 1u, c.dbg, t.code | (3u << 20));
           const int n_sub = min(kps, nk - st * kps);
           mbar_expect_tx(&c.full[s], (uint32_t)(n_sub * tx_sub));
           for (int u = 0; u < n_sub; ++u) {
@@ -715,8 +718,8 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
   } else if (warp == 1) {
     if (lane == 0) {
       for (int st = 0; st < n_st; ++st) {
-        const uint32_t i = c.it + st, s = i % NS;
-        ps_mbar_wait(&c.full[s], (i / NS) & 1, c.dbg, t.code | (4u << 20));
+        const uint32_t i = c.it + st, s = i & NSM;
+        ps_mbar_wait(&c.full[s], (i >> NSH) & 1, c.dbg, t.code | (4u << 20));
         tc_fence_after();
         if (c.tr && st == 0) c.tr[3] = ps_now();
         const int n_sub = min(kps, nk - st * kps);
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
   tc_fence_after();
 
   PsCtx c;
-  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.ns = PS_STAGES; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
+  c.smem = smem; c.full = full; c.empty = empty; c.tmem_full = tmem_full; c.tmem = *tmem_slot; c.nsh = 2; c.it = 0; c.tile_no = 0; c.dbg = P.dbg; c.tr = nullptr; c.lap_off = (long)gridDim.x * PS_TRACE_SLOTS * 8;
   const int n_items = sched[0];
   const int role = n_items > 0 ? sched[1] : -1;
   const int B = P.B, H = P.H, D = P.D, ZP = P.ZP, A = P.A, R = P.R, Mp = P.Mp, mt = P.mt;
@@ -880,6 +883,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
     xg.xbar = full + 18; xg.abar = full + 20;
     xg.xact = reinterpret_cast<float*>(smem + PS_RING_BYTES - 16384);        // rank 0: last 16 KB of the ring (idle while the epilogue runs)
     xg.xuse = 0; xg.ause = 0; xg.dbg = P.dbg;
+    c.nsh = 1;                                    // two ring slots of up to 96 KB (PS_CHAIN_STAGE_BYTES)
     for (int j = 0; j <= H; ++j) {
       trace_window(j);
       const int s_row = j * B + m0;       // this m-tile's rows of state j in the time-major state buffer
@@ -887,13 +891,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
       if (j >= 1) {
         {   // prior L1: h_j -> Y1[slot 0], this CTA's 64 columns   (DynamicsPredictors.py:15-18)
           tile_init(t, 0, j, m_tile);
-          t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2;
+          t.tmA = &P.tmS; t.tmB = &P.tmWp1q; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 4;   // (4 x 24 KB)
+          t.stage_bytes = PS_CHAIN_STAGE_BYTES;
           t.tcol = 256;
           if (j < H) {
             // the actor's first layer reads the same h k-blocks: its 64 weight rows ride along under the prior's (one N = 128 MMA per
             // k-step), so the h part of actor L1 is already in TMEM columns [320, 384) when z_j arrives -- 10 of its 26 k-blocks
             // leave the critical path for 8 KB more per k-block here
-            t.tmB2 = &P.tmWh1q; t.n1 = 64; t.b2_row = HS_ACTOR * 256 + 64 * rank; t.b2_koff = nkz; t.bn = 128; t.kps = 1;
+            t.tmB2 = &P.tmWh1q; t.n1 = 64; t.b2_row = HS_ACTOR * 256 + 64 * rank; t.b2_koff = nkz; t.bn = 128; t.kps = 3;   // (3 x 32 KB)
           }
           t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
           t.lsig = flag(PF_LP, m_tile);
@@ -909,7 +914,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         }
         {   // prior L2: Y1 -> Y2[slot 0]   (:19-22)
           tile_init(t, 1, j, m_tile);
-          t.tmA = &P.tmY1; t.tmB = &P.tmWp2q; t.a_row = m0; t.b_row = 64 * rank; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = 64; t.kps = 2;
+          t.tmA = &P.tmY1; t.tmB = &P.tmWp2q; t.a_row = m0; t.b_row = 64 * rank; t.ka0 = 0; t.nka0 = (P.hp1 + 63) / 64; t.bn = 64; t.kps = 4; t.stage_bytes = PS_CHAIN_STAGE_BYTES;   // all 4 k-blocks in one stage
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p2_b, P.p2_g, P.p2_be, nullptr, 0, P.Y2, 256, 0, 0, P.hp2, 1e-5f, P.bnp2};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSiluN4::stage(p, g, 0, epi_sm, tid, m0); },
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         // -> z_j into the state buffer, latent[:, j], idx[:, j - 1]
         for (int x = rank; x < P.nq; x += 4) {
           tile_init(t, 2, j, m_tile);
-          t.tmA = &P.tmY2; t.tmB = &P.tmWp3; t.a_row = m0; t.b_row = x * 256; t.ka0 = 0; t.nka0 = (P.hp2 + 63) / 64; t.bn = 256;
+          t.tmA = &P.tmY2; t.tmB = &P.tmWp3; t.a_row = m0; t.b_row = x * 256; t.ka0 = 0; t.nka0 = (P.hp2 + 63) / 64; t.bn = 256; t.kps = 2; t.stage_bytes = PS_CHAIN_STAGE_BYTES;   // 2 x 48 KB
           t.sig = flag(PF_Z, m_tile);
           const TileG g{B, 256, 0};
           const EpiCat::Params p{P.p3_b, P.uniforms + (long)(j - 1) * B * R, P.latent + (long)j * ZP, nullptr,
@@ -940,7 +945,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           tile_init(t, 0, j, m_tile);
           t.code |= 1u << 19;
           t.tmA = &P.tmS; t.tmB = &P.tmWh1q; t.a_row = s_row; t.b_row = HS_ACTOR * 256 + 64 * rank;
-          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 2;
+          t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = 64; t.kps = 4; t.stage_bytes = PS_CHAIN_STAGE_BYTES;
           if (j >= 1) {   // the h part is already accumulated (prior L1 above): z k-blocks only
             t.nka1 = 0; t.tcol = 320; t.acc0 = 1;
           }
@@ -960,7 +965,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           tile_init(t, 1, j, m_tile);
           t.code |= 1u << 19;
           t.tmA = &P.tmY1; t.tmB = &P.tmWh2q; t.a_row = ya + m0; t.b_row = HS_ACTOR * 256 + 64 * rank;
-          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 2;
+          t.ka0 = 0; t.nka0 = (P.hh1 + 63) / 64; t.bn = 64; t.kps = 4; t.stage_bytes = PS_CHAIN_STAGE_BYTES;
           t.chain = 0;   // (no hand-over follows, and its epilogue used the ring as scratch: keep the proxy fence before the next tile's TMA loads)
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.h2_b, P.h2_g, P.h2_be, nullptr, 0, P.Y2, 256, Mp, Mp, P.hh2, 1e-5f, P.bnh2};
