@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
     xg.xbar = full + 18; xg.abar = full + 20;
     xg.xact = nullptr;
     xg.xuse = 0; xg.ause = 0; xg.dbg = P.dbg;
+    c.nsh = 1;   // two ring slots of 96 KB, 2 - 4 k-blocks per stage (rollout_persist.cuh: a handshake costs ~0.3 us whatever the depth)
     for (int j = 1; j <= T; ++j) {
       trace_window(j);
       const int t_ = j - 1;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
       PsTile t;
       {   // latent_mapper.0 on [features, h_t] (VariationalAutoEncoder.py:45-48, 84-86): the feature part was hoisted (featpart), the h part here
         tile_init(t, 0, j, m_tile);
-        t.tmA = &P.tmS; t.tmB = &P.tmWehq; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 2;
+        t.tmA = &P.tmS; t.tmB = &P.tmWehq; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 4; t.stage_bytes = PS_CHAIN_STAGE_BYTES;
         t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * (j - P.h_skip));
         const TileG g{B, 64, 0};
         const EpiLnSilu::Params p{P.e1_b, P.e1_g, P.e1_be, nullptr, 0, P.Y1, 256, 0, 0, P.h_enc, 1e-5f, P.bn_he};
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
       // latent_mapper.3 -> posterior logits -> sample (VariationalAutoEncoder.py:49, 88-99): 256 logit columns per tile, tiles rank, rank + 4, ...
       for (int x = rank; x < P.nq; x += 4) {
         tile_init(t, 2, j, m_tile);
-        t.tmA = &P.tmY1; t.tmB = &P.tmWe3; t.a_row = m0; t.b_row = x * 256; t.ka0 = 0; t.nka0 = (P.h_enc + 63) / 64; t.bn = 256;
+        t.tmA = &P.tmY1; t.tmB = &P.tmWe3; t.a_row = m0; t.b_row = x * 256; t.ka0 = 0; t.nka0 = (P.h_enc + 63) / 64; t.bn = 256; t.kps = 2; t.stage_bytes = PS_CHAIN_STAGE_BYTES;
         t.sig = flag(PF_Z, m_tile);
         const TileG g{B, 256, 0};
         const EpiCat::Params p{P.e3_b, P.uniforms + (long)t_ * B * R, P.latent + (long)t_ * ZP, P.logits ? P.logits + (long)t_ * ZP : nullptr,
@@ -151,7 +152,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
     // a step's 27 k-blocks are latency-bound at 16 - 50 sequences: compact stages ([A 4 or 16 KB | 3U weight rows]) and a ring as deep
     // as fits in front of the h_prev tile
     const int gru_sub = P.a_tx + 3 * P.U * BK * 2;
-    const int gru_kps = (nkh % 2 == 0) ? 2 : 1;     // one full / empty handshake per two k-blocks (the h range must be whole stages)
+    // k-blocks per handshake: as many as divide the h range (it must be whole stages) with two stages still fitting in front of the
+    // h_prev tile -- measured at 16 x 64: 1 per stage / 8 slots 2.23 ms per scan() call, 2 / 8 2.08, 5 / 2 2.01, 5 / 1 2.08
+    int gru_kps = 1;
+    for (int k = 5; k >= 2; --k)
+      if (nkh % k == 0 && 2 * k * gru_sub <= PS_HP_OFF) { gru_kps = k; break; }
     const int gru_stage = gru_kps * gru_sub;
     c.nsh = 0;
     while (c.nsh < 3 && (2 << c.nsh) * gru_stage <= PS_HP_OFF) ++c.nsh;
