@@ -37,6 +37,7 @@ struct ConvImplicit {
   unsigned char off_w[4][16], off_h[4][16];   // im2col offsets of tap t in phase p
   int bn;                      // MMA N (padded output channels, multiple of 16, <= 256)
   int stage_bytes, n_stages, tmem_cols;
+  int kps, sub_bytes;          // k-blocks per pipeline stage (a full / empty handshake costs ~0.3 us whatever it carries: DESIGN.md 4a) and bytes of one
   const float* bias;
   __nv_bfloat16* out;          // [rows, ld] bf16
   long ld;
@@ -106,16 +107,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_implicit_kernel(const __
         const int n = m0 / ppf, rem = m0 - n * ppf, oy = rem / c.Wo, ox = rem - oy * c.Wo;
         const int cw = ox * c.stride + c.lower_w[ph], chh = oy * c.stride + c.lower_h[ph], cn = n + c.n_base;
         const int b_row = ph * c.bn;
-        int kb = 0;
-        for (int tap = 0; tap < c.ntap; ++tap) {
-          const uint16_t ow = c.off_w[ph][tap], oh = c.off_h[ph][tap];
-          for (int cc = 0; cc < c.cpt; ++cc, ++kb, ++it) {
-            const int s = it % NS;
-            mbar_wait(&empty[s], ((it / NS) & 1) ^ 1u);
-            uint8_t* sa = smem + s * c.stage_bytes;
-            mbar_expect_tx(&full[s], tx);
-            tma_load_im2col_4d(sa, &c.tmA[ph], cc * c.chunk, cw, chh, cn, ow, oh, &full[s]);
+        int tap = 0, cc = 0;
+        for (int kb = 0; kb < nk; ++it) {
+          const int s = it % NS;
+          mbar_wait(&empty[s], ((it / NS) & 1) ^ 1u);
+          const int n_sub = min(c.kps, nk - kb);
+          mbar_expect_tx(&full[s], (uint32_t)n_sub * tx);
+          for (int u = 0; u < n_sub; ++u, ++kb) {
+            uint8_t* sa = smem + s * c.stage_bytes + u * c.sub_bytes;
+            tma_load_im2col_4d(sa, &c.tmA[ph], cc * c.chunk, cw, chh, cn, c.off_w[ph][tap], c.off_h[ph][tap], &full[s]);
             tma_load_2d(sa + a_bytes, &c.tmB, kb * c.chunk, b_row, &full[s]);
+            if (++cc == c.cpt) { cc = 0; ++tap; }
           }
         }
       }
@@ -129,13 +131,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_implicit_kernel(const __
         const int buf = i & 1;
         mbar_wait(&tempty[buf], ((i >> 1) & 1) ^ 1u);      // the epilogue has drained this accumulator's previous tile
         tc_fence_after();
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        for (int kb = 0; kb < nk; ++it) {
           const int s = it % NS;
           mbar_wait(&full[s], (it / NS) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * c.stage_bytes);
-          const uint64_t adesc = umma_desc_kmajor(a_addr, row_bytes), bdesc = umma_desc_kmajor(a_addr + a_bytes, row_bytes);
-          for (int k = 0; k < ksteps; ++k) umma_bf16(tmem + (uint32_t)(buf * c.bn), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          const int n_sub = min(c.kps, nk - kb);
+          for (int u = 0; u < n_sub; ++u, ++kb) {
+            const uint32_t a_addr = smem_u32(smem + s * c.stage_bytes + u * c.sub_bytes);
+            const uint64_t adesc = umma_desc_kmajor(a_addr, row_bytes), bdesc = umma_desc_kmajor(a_addr + a_bytes, row_bytes);
+            for (int k = 0; k < ksteps; ++k) umma_bf16(tmem + (uint32_t)(buf * c.bn), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[buf]);

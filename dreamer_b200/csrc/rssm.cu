@@ -72,6 +72,7 @@ struct Options {
   int ln_cluster = 1;  // LN stages of small grids split over clusters of 4 CTAs
   int gru_ksplit = 1;  // single-m-tile grids split the GRU tile's K range over a 2-CTA cluster
   int conv_persist = 1;  // narrow conv layers on the persistent GEMM
+  int conv_kps = 0;      // implicit-GEMM convs: k-blocks per pipeline stage (0 = as many as fit in 48 KB)
   int conv_chunk = 512;  // frames per conv chunk of an observe workspace (read when the workspace is created)
   int conv_implicit = 1; // conv layers as implicit GEMMs fed by im2col-mode TMA loads (no patch matrix)
   int gru_pair = -1;   // GRU stage on CTA pairs (cta_group::2 M = 256 MMAs, half the weight tile per SM): -1 auto (large grids), 0, 1
@@ -949,6 +950,7 @@ extern "C" int drm_set_option(const char* name, int32_t value) {
   else if (n == "conv_persist") o.conv_persist = value != 0;
   else if (n == "conv_implicit") o.conv_implicit = value != 0;
   else if (n == "conv_chunk") o.conv_chunk = value >= 16 ? value : 512;
+  else if (n == "conv_kps") o.conv_kps = value;
   else if (n == "gru_ksplit") o.gru_ksplit = value != 0;
   else if (n == "persist") o.persist = value != 0;
   else if (n == "gru_pair") { DRM_REQUIRE(value >= -1 && value <= 1, DRM_ERR_ARG, "drm_set_option: gru_pair must be -1, 0 or 1"); o.gru_pair = value; }
@@ -1052,7 +1054,11 @@ static int launch_conv_implicit(const CUtensorMap* tmA, int phases, const CUtens
     }
   }
   c.bn = bn;
-  c.stage_bytes = round_up(BM * chunk * 2 + bn * chunk * 2, 1024);
+  // pipeline shape: stages of up to ~48 KB (one full / empty handshake per stage costs ~0.3 us whatever it carries), at least two slots
+  c.sub_bytes = round_up(BM * chunk * 2 + bn * chunk * 2, 1024);
+  const int nk = ntap * (cpad / chunk);
+  c.kps = std::max(1, std::min(std::min(opts().conv_kps > 0 ? opts().conv_kps : 48 * 1024 / c.sub_bytes, nk), CI_RING_BYTES / (2 * c.sub_bytes)));
+  c.stage_bytes = c.kps * c.sub_bytes;
   c.n_stages = std::min(CI_MAX_STAGES, CI_RING_BYTES / c.stage_bytes);
   c.tmem_cols = 32;
   while (c.tmem_cols < 2 * bn) c.tmem_cols *= 2;

@@ -28,9 +28,9 @@ def timeit(fn, n=20):
 cfg3 = dict(W.REF_CONFIG, horizon=64, sequence_length=64, batch_size=16)
 wm, _ = W.build_learners(cfg3, W.make_state_dict(cfg3, seed=0), torch.device(dev))
 o3, a3, r3, c3, u3 = (x.to(dev) for x in W.sequence_inputs(cfg3, 16, 64, seed=4321))
-for flag in (1, 0, 1, 0):
-    L.check(lib.drm_set_option(b"conv_implicit", flag), "opt")
+for flag, kps in ((1, 0), (1, 1), (1, 2), (1, 4), (0, 0)):
+    L.check(lib.drm_set_option(b"conv_implicit", flag), "opt"); L.check(lib.drm_set_option(b"conv_kps", kps), "opt")
     te = timeit(lambda: ws.encode(h, obs))
     td = timeit(lambda: ws.decode(h, z))
     tl = timeit(lambda: wm.loss_forward(o3, a3, r3, c3, uniforms=u3))
-    print(f"conv_implicit={flag}: encode {N} frames {te:.3f} ms, decode {td:.3f} ms, world-model loss forward (16 x 64) {tl:.3f} ms")
+    print(f"conv_implicit={flag} conv_kps={kps}: encode {N} frames {te:.3f} ms, decode {td:.3f} ms, world-model loss forward (16 x 64) {tl:.3f} ms")
