@@ -214,3 +214,34 @@ def test_host_buffer_rollout_call_matches_device_call_across_graph_capture(ops):
     got = dream_episodes_host(ro, zi, h0.pin_memory(), uniforms=u.pin_memory(), normals=n.pin_memory())
     for a, b in zip(ref, got["device"]):
         assert torch.equal(a, b)
+
+
+def test_host_rollout_queue_matches_synchronous_calls(ops):
+    """rollout.HostRolloutQueue (two-deep submit / result, copies on a side stream) returns, call by call, what dream_episodes_host
+    returns for the same start states and draws -- including when slots are reused and results are collected late."""
+    from dreamer_b200.rollout import HostRolloutQueue, dream_episodes_host
+    cfg = W.small_config()
+    sd, model = _model(ops, cfg, 11)
+    B, H = 40, 5
+    ro = ops.Rollout(model, B, H)
+    starts = []
+    for s in range(5):
+        z0, h0, _, _ = W.rollout_inputs(cfg, B, H, seed=100 + s)
+        starts.append((z0.reshape(B, -1, 32).argmax(-1).to(torch.uint8).contiguous().pin_memory(), h0.contiguous().pin_memory()))
+    want = []
+    g = torch.Generator(device=DEV).manual_seed(7)
+    for zi, h0 in starts:
+        out = dream_episodes_host(ro, zi, h0, generator=g)
+        want.append([t.clone() for t in out["host"]])
+    g = torch.Generator(device=DEV).manual_seed(7)
+    q = HostRolloutQueue(ro, generator=g)
+    tickets, got = [], []
+    for i, (zi, h0) in enumerate(starts):
+        tickets.append(q.submit(zi, h0))
+        if i >= 1:
+            got.append([t.clone() for t in q.result(tickets[i - 1])])
+    got.append([t.clone() for t in q.result(tickets[-1])])
+    for a, b in zip(got, want):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    with pytest.raises(RuntimeError):
+        q.result(tickets[0])          # that slot has been reused
