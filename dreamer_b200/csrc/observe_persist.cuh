@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
       {   // latent_mapper.0 on [features, h_t] (VariationalAutoEncoder.py:45-48, 84-86): the feature part was hoisted (featpart), the h part here
         tile_init(t, 0, j, m_tile);
         t.tmA = &P.tmS; t.tmB = &P.tmWehq; t.a_row = s_row; t.b_row = 64 * rank; t.ka0 = kh0; t.nka0 = nkh; t.bn = 64; t.kps = 4; t.stage_bytes = PS_CHAIN_STAGE_BYTES;
-        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * (j - P.h_skip));
+        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(PS_PUB * P.nt * (j - P.h_skip));
         const TileG g{B, 64, 0};
         const EpiLnSilu::Params p{P.e1_b, P.e1_g, P.e1_be, nullptr, 0, P.Y1, 256, 0, 0, P.h_enc, 1e-5f, P.bn_he};
         float addv[16];
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) observe_persist_kernel(const 
         t.stage_bytes = gru_stage; t.a_bytes = P.a_tx; t.kps = gru_kps;
         t.tmA = &P.tmS; t.tmB = &P.tmWgru; t.a_row = s * B + m0; t.b_row = n_tile * 3 * P.U;
         t.ka0 = kh0; t.nka0 = nkh; t.ka1 = 0; t.nka1 = nkz + 1; t.b_follows_a = 1; t.bn = 3 * P.U; t.h_first = 1;
-        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * (s - P.h_skip));   // h_{s-1} (slab s) complete
-        t.w1 = flag(PF_Z, m_tile); t.t1 = (unsigned)(P.nq * s);                // z_{s-1} (slab s) sampled
+        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(PS_PUB * P.nt * (s - P.h_skip));   // h_{s-1} (slab s) complete
+        t.w1 = flag(PF_Z, m_tile); t.t1 = (unsigned)(PS_PUB * P.nq * s);                // z_{s-1} (slab s) sampled
         t.sig = flag(PF_H, m_tile);
         __nv_bfloat16* s_h = P.S + (long)(s + 1) * B * P.KS + ZP + 64;
         const float* h_prev = s == 0 ? P.zero_h : P.hidden + (long)(s - 1) * D;

@@ -58,6 +58,7 @@ enum { PS_CHAIN = 0, PS_RC = 2, PS_GRU = 3 };   // CTA roles (the record's first
 enum { PF_H = 0, PF_Z = 1, PF_LP = 2, PF_LA = 3, PF_COUNT = 4 };   // + loads landed: prior L1 / actor L1 of a state (bandwidth gates of the GRU CTAs)
 constexpr int PS_DBG_WORDS = 8 * 160 + 8;
 constexpr int PS_TRACE_SLOTS = 32;
+constexpr unsigned PS_PUB = EPI_THREADS / 32;   // increments of a hand-over counter per published tile (one per epilogue warp)
 
 struct PersistParams {
   CUtensorMap tmS, tmY1, tmY2, tmWgru, tmWp1q, tmWp2q, tmWp3, tmWh1q, tmWh2q, tmWh3a, tmWh1, tmWh2, tmWh3;
@@ -777,9 +778,12 @@ __device__ __forceinline__ void ps_run_tile(PsCtx& c, const PsTile& t, Pre&& pre
     if (c.tr && tid == 0) c.tr[5] = ps_now();
     epilogue(tid);
     if (c.tr && tid == 0) c.tr[6] = ps_now();
-    if (t.sig) {   // publish to other CTAs' waiters: CTA barrier, then one device-scope fence + release (cumulative over the CTA's stores)
-      epi_bar_sync();
-      if (tid == 0) {
+    if (t.sig) {
+      // publish to other CTAs' waiters, WARP BY WARP: every epilogue warp releases its own stores (warp barrier, one device-scope fence
+      // + release by lane 0) as soon as it has issued them -- no CTA barrier and no single thread fencing the whole tile's stores; a
+      // tile counts PS_PUB (= 16 warps) on the hand-over counter
+      __syncwarp();
+      if (lane == 0) {
         __threadfence();
         red_release_add(t.sig, 1u);
       }
@@ -900,7 +904,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
             // leave the critical path for 8 KB more per k-block here
             t.tmB2 = &P.tmWh1q; t.n1 = 64; t.b2_row = HS_ACTOR * 256 + 64 * rank; t.b2_koff = nkz; t.bn = 128; t.kps = 3;   // (3 x 32 KB)
           }
-          t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
+          t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(PS_PUB * P.nt * j);
           t.lsig = flag(PF_LP, m_tile);
           const TileG g{B, 64, 0};
           const EpiLnSilu::Params p{P.p1_b, P.p1_g, P.p1_be, nullptr, 0, P.Y1, 256, 0, 0, P.hp1, 1e-5f, P.bnp1};
@@ -1000,9 +1004,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
         // The GRU CTAs move 83 MB per step -- alone they would saturate the L2 -> SM fabric for 6 us and starve the chain's small
         // loads exactly when those are on the critical path.  So each half waits until the chain layer that reads the same data has
         // its operands: the h part (needs h_j) behind prior L1 of state j, the z part (needs z_j) behind actor L1 of state j.
-        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(P.nt * j);
+        t.w0 = flag(PF_H, m_tile); t.t0 = (unsigned)(PS_PUB * P.nt * j);
         t.g0 = flag(PF_LP, m_tile); t.gt0 = (unsigned)(4 * j);
-        t.w1 = flag(PF_Z, m_tile); t.t1 = (unsigned)(P.nq * j);
+        t.w1 = flag(PF_Z, m_tile); t.t1 = (unsigned)(PS_PUB * P.nq * j);
         t.g1 = flag(PF_LA, m_tile); t.gt1 = (unsigned)(4 * (j + 1));
         t.sig = flag(PF_H, m_tile);     // (a_j is awaited inside the epilogue, row by row: EpiGruP::run)
         __nv_bfloat16* s_h = P.S + (long)(j + 1) * B * P.KS + ZP + 64;
@@ -1035,7 +1039,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rollout_persist_kernel(const 
           tile_init(t, 0, j, m_tile);
           t.tmA = &P.tmS; t.tmB = &P.tmWh1; t.a_row = j * B + m0; t.b_row = head * 256;
           t.ka0 = 0; t.nka0 = nkz; t.ka1 = kh0; t.nka1 = nkh; t.bn = P.bnh1;
-          t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(P.nq * j);
+          t.w0 = flag(PF_Z, m_tile); t.t0 = (unsigned)(PS_PUB * P.nq * j);
           const TileG g{B, P.bnh1, 0};
           const EpiLnSilu::Params p{P.h1_b, P.h1_g, P.h1_be, nullptr, 0, P.Y1, 256, Mp, Mp, P.hh1, 1e-5f, P.bnh1};
           ps_run_tile<0>(c, t, [&](int tid) { EpiLnSilu::stage(p, g, head, epi_sm, tid, m0); },
