@@ -103,6 +103,10 @@ SIGNATURES = {
     "drm_adamw_scratch_bytes": (C.c_int64, []),
     "drm_adamw_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 6 + [C.c_void_p, C.c_float, C.c_int32, c_stream]),
     "drm_grad_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_stream]),
+    "drm_gemm_tf32_workspace_bytes": (C.c_int64, [C.c_int32] * 3),
+    "drm_gemm_tf32": (C.c_int, [C.c_int32] * 3 + [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                C.c_int32, C.c_void_p, C.c_int64, c_stream]),
+    "drm_pack_tf32": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, c_stream]),
     "drm_test_gemm": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32, c_stream]),
 }
 

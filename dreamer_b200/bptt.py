@@ -47,6 +47,30 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+# Which GEMM runs the contractions of the two backward passes: "drm" = this library's TMA / tcgen05 kind::tf32 kernel
+# (drm_gemm_tf32, csrc/gemm_tf32.cu), "torch" = the library GEMM behind torch.mm (TF32 when MATMUL_TF32).  GEMM_BATCHED covers the
+# GEMMs over all B*T rows (re-evaluated pre-activations, every weight gradient, batched input gradients), GEMM_STEP the per-time-step
+# GEMMs inside the two recurrence walks (16 - 1024 rows).
+GEMM_BATCHED = "drm"
+GEMM_STEP = "drm"
+
+
+def _mm(a, b, out=None, accumulate=False, step=False):
+    """out (+)= a [M, K] @ b [K, N]"""
+    if (GEMM_STEP if step else GEMM_BATCHED) == "drm":
+        return ops.mm(a, b, out=out, accumulate=accumulate)
+    if out is None:
+        return torch.mm(a, b)
+    return out.addmm_(a, b) if accumulate else torch.mm(a, b, out=out)
+
+
+def _linear(x, weight, bias):
+    """x [rows, in] @ weight [out, in]^T + bias"""
+    if GEMM_BATCHED == "drm":
+        return ops.mm_nt(x, weight, bias)
+    return torch.addmm(bias, x, weight.t())
+
+
 def _acc(p: torch.nn.Parameter, g: torch.Tensor):
     if p.grad is None:
         p.grad = torch.zeros_like(p)
@@ -57,7 +81,10 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
     """p.grad += a_t^T @ b   (a_t [rows, out], b [rows, in])"""
     if p.grad is None:
         p.grad = torch.zeros_like(p)
-    p.grad.addmm_(a_t.t(), b)
+    if GEMM_BATCHED == "drm" and p.grad.dim() == 2 and p.grad.is_contiguous():
+        ops.mm_nt(a_t.t(), b.t(), out=p.grad, accumulate=True)
+    else:
+        p.grad.addmm_(a_t.t(), b)
 
 
 def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None, on_loss=None):
@@ -105,8 +132,8 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         X = torch.zeros(T, B, Z + act.shape[-1], device=dev)
         X[1:, :, :Z] = z_oh.transpose(0, 1)[:-1]
         X[1:, :, Z:] = act.transpose(0, 1)[:-1]                                 # x_t = [z_{t-1}, a_{t-1}], zeros at t = 0
-        GI = torch.addmm(gru.bias_ih, X.view(T * B, -1), gru.weight_ih.t()).view(T, B, 3 * Dh)
-        GH = torch.addmm(gru.bias_hh, Hprev.view(T * B, -1), gru.weight_hh.t()).view(T, B, 3 * Dh)
+        GI = _linear(X.view(T * B, -1), gru.weight_ih, gru.bias_ih).view(T, B, 3 * Dh)
+        GH = _linear(Hprev.view(T * B, -1), gru.weight_hh, gru.bias_hh).view(T, B, 3 * Dh)
     # encoder convs: the one autograd graph that is closed later with d(loss)/d(features)
     conv_dtype = wm.__dict__.get("conv_grad_dtype", torch.bfloat16)     # the reference trains these convs under fp16 autocast
     with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
@@ -114,9 +141,9 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
     feats = feats.float().flatten(1)                                                               # (B*T, n_feat)
     with torch.no_grad():
         X1 = torch.cat([feats.detach().view(B, T, n_feat).transpose(0, 1), H_tm], -1).contiguous()   # (T,B,n_feat+D)
-        A1 = torch.addmm(lin1.bias, X1.view(T * B, -1), lin1.weight.t())
+        A1 = _linear(X1.view(T * B, -1), lin1.weight, lin1.bias)
         Y1 = F.silu(F.layer_norm(A1, (A1.shape[-1],), ln1.weight, ln1.bias, ln1.eps))
-        LG = torch.addmm(lin2.bias, Y1, lin2.weight.t()).view(T, B, Z)          # posterior logits, time-major
+        LG = _linear(Y1, lin2.weight, lin2.bias).view(T, B, Z)                   # posterior logits, time-major
 
     mark("recurrent pre-activations + posterior MLP forward (batched)")
     # ---- (1b) everything that reads (h_t, z_t) at one step: batched autograd on leaves --------------------------------------
@@ -195,8 +222,8 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         joined = None
         for t in range(T - 1, -1, -1):
             ops.categorical32_bwd(LG[t], gZ[t], dz_carry, gLG[t], out=dLG[t])   # through the ST sample, + the KL term
-            dA1 = ops.ln_silu_bwd(dLG[t] @ W2, A1_tm[t], ln1.weight, ln1.bias, ln1.eps)
-            gH[t].addmm_(dA1, W1h)                                              # d/dh_t is complete up to the recurrent term
+            dA1 = ops.ln_silu_bwd(_mm(dLG[t], W2, step=True), A1_tm[t], ln1.weight, ln1.bias, ln1.eps)
+            _mm(dA1, W1h, out=gH[t], accumulate=True, step=True)                                             # d/dh_t is complete up to the recurrent term
             if joined is not None:
                 main.wait_event(joined)
             ops.gru_bwd(gH[t], GI[t], GH[t], Hprev[t], dGI[t], dGH[t], gH[t - 1] if t > 0 else None, accumulate=True,
@@ -206,10 +233,10 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
                 fork.record(main)
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
-                    torch.mm(dGH[t], Whh, out=dHrec[t - 1])
+                    _mm(dGH[t], Whh, out=dHrec[t - 1], step=True)
                     joined = torch.cuda.Event()
                     joined.record(side)
-                dz_carry = dGI[t] @ Wih_z
+                dz_carry = _mm(dGI[t], Wih_z, step=True)
         if joined is not None:
             main.wait_event(joined)     # (every side-stream node is an ancestor of the capture's end)
         mark("recurrence backward (T steps)")
@@ -221,13 +248,13 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         _acc(gru.bias_hh, dGH2.sum(0))
         _acc_mm(lin2.weight, dLG2, Y1)
         _acc(lin2.bias, dLG2.sum(0))
-        dA1_all, dln = ops.ln_silu_bwd(dLG2 @ W2, A1, ln1.weight, ln1.bias, ln1.eps, want_dln=True)
+        dA1_all, dln = ops.ln_silu_bwd(_mm(dLG2, W2), A1, ln1.weight, ln1.bias, ln1.eps, want_dln=True)
         xhat = F.layer_norm(A1, (A1.shape[-1],), None, None, ln1.eps)
         _acc(ln1.weight, (dln * xhat).sum(0))
         _acc(ln1.bias, dln.sum(0))
         _acc_mm(lin1.weight, dA1_all, X1.view(T * B, -1))
         _acc(lin1.bias, dA1_all.sum(0))
-        dfeat = (dA1_all @ lin1.weight[:, :n_feat]).view(T, B, n_feat).transpose(0, 1).reshape(B * T, n_feat)
+        dfeat = _mm(dA1_all, lin1.weight[:, :n_feat]).view(T, B, n_feat).transpose(0, 1).reshape(B * T, n_feat)
     mark("batched weight-gradient GEMMs")
     feats.backward(dfeat)    # encoder convs
     mark("encoder conv backward")
@@ -244,9 +271,9 @@ def _tanh_normal_log_prob(a, mu, sigma):
 
 def _mlp_fwd(x, lin_a, ln_a, lin_b, ln_b):
     """Linear-LN-SiLU x2 keeping the pre-LayerNorm activations (the backward kernels recompute the statistics from them)."""
-    a1 = torch.addmm(lin_a.bias, x, lin_a.weight.t())
+    a1 = _linear(x, lin_a.weight, lin_a.bias)
     y1 = F.silu(F.layer_norm(a1, (a1.shape[-1],), ln_a.weight, ln_a.bias, ln_a.eps))
-    a2 = torch.addmm(lin_b.bias, y1, lin_b.weight.t())
+    a2 = _linear(y1, lin_b.weight, lin_b.bias)
     y2 = F.silu(F.layer_norm(a2, (a2.shape[-1],), ln_b.weight, ln_b.bias, ln_b.eps))
     return a1, y1, a2, y2
 
@@ -283,7 +310,7 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         Z = Ztm.shape[-1]
         Xa = torch.cat([Htm[:H], Ztm[:H]], -1).view(H * B, Dh + Z)                      # actor input [h, z] (Agent.py:196-198)
         A1, Y1, A2, Y2 = _mlp_fwd(Xa, l1, n1, l2, n2)
-        LS = torch.addmm(actor.log_sig_head.bias, Y2, actor.log_sig_head.weight.t())
+        LS = _linear(Y2, actor.log_sig_head.weight, actor.log_sig_head.bias)
         mu_k = mu.detach().transpose(0, 1).reshape(H * B, A)
         sg_k = sigma.detach().transpose(0, 1).reshape(H * B, A)
         a_flat = Atm.view(H * B, A)
@@ -295,10 +322,10 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         gMU, gSG = mu_l.grad.view(H, B, A), sg_l.grad.view(H, B, A)
         # world-model pre-activations of the transitions s -> s+1, s = 0..H-1 (needed for s <= H-2)
         X = torch.cat([Ztm[:H], Atm], -1).view(H * B, Z + A)
-        GI = torch.addmm(gru.bias_ih, X, gru.weight_ih.t()).view(H, B, 3 * Dh)
-        GH = torch.addmm(gru.bias_hh, Htm[:H].reshape(H * B, Dh), gru.weight_hh.t()).view(H, B, 3 * Dh)
+        GI = _linear(X, gru.weight_ih, gru.bias_ih).view(H, B, 3 * Dh)
+        GH = _linear(Htm[:H].reshape(H * B, Dh), gru.weight_hh, gru.bias_hh).view(H, B, 3 * Dh)
         P1, _, P2, PY2 = _mlp_fwd(Htm[1:].reshape(H * B, Dh), p1, q1, p2, q2)
-        LG = torch.addmm(p3.bias, PY2, p3.weight.t()).view(H, B, Z)                     # prior logits of states 1..H
+        LG = _linear(PY2, p3.weight, p3.bias).view(H, B, Z)                               # prior logits of states 1..H
         P1, P2 = P1.view(H, B, -1), P2.view(H, B, -1)
         A1s, A2s, LSs = A1.view(H, B, -1), A2.view(H, B, -1), LS.view(H, B, A)
         Wih_z, Wih_a = gru.weight_ih[:, :Z].contiguous(), gru.weight_ih[:, Z:].contiguous()
@@ -313,23 +340,23 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
             ch = cz = None                                                              # carried into state s from the transition s -> s + 1
             if Gh is not None:
                 dlg = ops.categorical32_bwd(LG[s], Gz)                                  # z_{s+1} = ST(prior(h_{s+1}))
-                dP2 = ops.ln_silu_bwd(dlg @ p3.weight, P2[s], q2.weight, q2.bias, q2.eps)
-                dP1 = ops.ln_silu_bwd(dP2 @ p2.weight, P1[s], q1.weight, q1.bias, q1.eps)
-                Gh.addmm_(dP1, p1.weight)                                               # total d/dh_{s+1}
+                dP2 = ops.ln_silu_bwd(_mm(dlg, p3.weight, step=True), P2[s], q2.weight, q2.bias, q2.eps)
+                dP1 = ops.ln_silu_bwd(_mm(dP2, p2.weight, step=True), P1[s], q1.weight, q1.bias, q1.eps)
+                _mm(dP1, p1.weight, out=Gh, accumulate=True, step=True)                                              # total d/dh_{s+1}
                 ch = torch.empty_like(Gh)
                 ops.gru_bwd(Gh, GI[s], GH[s], Htm[s], dgi, dgh, ch, accumulate=False)   # h_{s+1} = GRU([z_s, a_s], h_s)
-                ch.addmm_(dgh, gru.weight_hh)
-                cz = dgi @ Wih_z
-                da = dgi @ Wih_a
+                _mm(dgh, gru.weight_hh, out=ch, accumulate=True, step=True)
+                cz = _mm(dgi, Wih_z, step=True)
+                da = _mm(dgi, Wih_a, step=True)
             # actor at state s: a_s = tanh(mu_s + sigma_s eps_s), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209)
             ops.actor_head_bwd(gMU[s], gSG[s], da, Atm[s], EPS[s], LSs[s], dHEAD[s])
-            torch.mm(dHEAD[s], Whead, out=dY2s[s])
+            _mm(dHEAD[s], Whead, out=dY2s[s], step=True)
             dA2 = ops.ln_silu_bwd(dY2s[s], A2s[s], n2.weight, n2.bias, n2.eps)
-            torch.mm(dA2, l2.weight, out=dY1s[s])
+            _mm(dA2, l2.weight, out=dY1s[s], step=True)
             if s > 0:                                                                   # state 0 is an input: nothing upstream
                 dA1 = ops.ln_silu_bwd(dY1s[s], A1s[s], n1.weight, n1.bias, n1.eps)
-                Gh = torch.mm(dA1, W1_h) if ch is None else ch.addmm_(dA1, W1_h)
-                Gz = torch.mm(dA1, W1_z) if cz is None else cz.addmm_(dA1, W1_z)
+                Gh = _mm(dA1, W1_h, step=True) if ch is None else _mm(dA1, W1_h, out=ch, accumulate=True, step=True)
+                Gz = _mm(dA1, W1_z, step=True) if cz is None else _mm(dA1, W1_z, out=cz, accumulate=True, step=True)
         # ---- actor weight gradients: batched GEMMs over all B*H rows ----------------------------------------------------
         dH2 = dHEAD.view(H * B, 2 * A)
         _acc_mm(actor.mu_head.weight, dH2[:, :A], Y2)

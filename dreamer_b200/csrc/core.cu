@@ -90,6 +90,22 @@ int make_tmap_op_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t c
   return DRM_OK;
 }
 
+// fp32 operand lying K-last ([K][rows], pitch ld): box {32 rows, 32 k} written as 32 rows of 128 B with 32-byte chunks swizzled by the
+// row number mod 4 (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- the one shared-memory layout tcgen05 accepts for MN-major 32-bit operands.
+int make_tmap_f32_mn(CUtensorMap* tm, const void* base, uint64_t k_rows, uint64_t mn_cols, uint64_t ld_elems) {
+  auto fn = encode_fn();
+  if (!fn) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (((uintptr_t)base & 15u) || ((ld_elems * 4) & 15u)) return fail(DRM_ERR_ALIGN, "tensor map base / pitch must be 16-byte aligned");
+  cuuint64_t gdim[2] = {mn_cols, k_rows};
+  cuuint64_t gstride[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32, MN-major) failed with CUresult " + std::to_string((int)r));
+  return DRM_OK;
+}
+
 // 2D bf16 tensor map with a narrower inner box: box {inner, box_rows}, swizzle span = inner * 2 bytes (inner = 16 / 32 / 64 elements).
 // Weights of the implicit-GEMM convolutions whose k-block is one tap of <= 64 channels.
 int make_tmap_bf16_2d_inner(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,

@@ -50,6 +50,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
                       uint32_t box_rows);
 
 int make_tmap_op_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows, int wide);
+int make_tmap_f32_mn(CUtensorMap* tm, const void* base, uint64_t k_rows, uint64_t mn_cols, uint64_t ld_elems);
 int make_tmap_bf16_2d_inner(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
                             uint32_t inner);
 // im2col-mode map over NHWC bf16 [N, H, W, C] (see core.cu)

@@ -224,6 +224,94 @@ def test_gemm(A, W, bias=None):
 
 
 # --------------------------------------------------------------------------------------------
+# contractions of the backward passes (drm_gemm_tf32)
+# --------------------------------------------------------------------------------------------
+GEMM_TRANS_A, GEMM_TRANS_B, GEMM_ACCUMULATE, GEMM_A_DIRECT, GEMM_B_DIRECT = 1, 2, 4, 8, 16
+
+# one persistent workspace per (device, stream): its first 1 KB are the split-K tile tickets, which must start zero and which every
+# call leaves zero; calls on one stream are ordered, so they can share it (a call on another stream gets its own)
+_GEMM_WS: Dict[tuple, torch.Tensor] = {}
+
+
+def _gemm_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _GEMM_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 16 << 20), dtype=torch.uint8, device=dev)
+        ws[:1024].zero_()        # the tickets (under graph capture this is one 1 KB memset node)
+        _GEMM_WS[key] = ws       # (the old buffer stays alive while queued work or a captured graph still refers to it)
+    return ws
+
+
+def _gemm_operand(t: torch.Tensor):
+    """2-D fp32 view -> (tensor, leading dimension, K-first?) without copying when it is row-major or a transposed row-major view."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    r, c = t.shape
+    if (t.stride(1) == 1 or c == 1) and t.stride(0) >= c:
+        return t, t.stride(0), False
+    if (t.stride(0) == 1 or r == 1) and t.stride(1) >= r:
+        return t, t.stride(1), True
+    t = t.contiguous()
+    return t, t.stride(0), False
+
+
+def mm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+          accumulate: bool = False, a_direct: bool = False, b_direct: bool = False) -> torch.Tensor:
+    """out [M, N] (+)= a [M, K] @ b [N, K]^T (+ bias [N]) on the library's TF32 tcgen05 GEMM (fp32 in / out).
+
+    `a` / `b` may be transposed views (x.t()): they are read in place either way.  The three shapes of a linear layer:
+    forward mm_nt(x, W, bias), input gradient mm_nt(dy, W.t()), weight gradient mm_nt(dy.t(), x.t(), out=W.grad, accumulate=True).
+    Operands are rounded to nearest TF32 on the way in (a pack launch, or inside the kernel for the few-row operand of a skinny
+    problem); `a_direct` / `b_direct`: that operand is already rounded (round_tf32 / pack_tf32) and, if aligned, is read in place."""
+    L.require_cuda(a, "a")
+    at, lda, ta = _gemm_operand(a)
+    bt, ldb, tb = _gemm_operand(b)
+    M, K = at.shape
+    N = bt.shape[0]
+    if bt.shape[1] != K:
+        raise RuntimeError(f"dreamer_b200.mm_nt: inner dimensions differ ({tuple(at.shape)} x {tuple(bt.shape)}^T)")
+    if out is None:
+        if accumulate:
+            raise RuntimeError("dreamer_b200.mm_nt: accumulate needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=at.device)
+    elif out.dtype != torch.float32 or out.shape != (M, N) or (out.stride(1) != 1 and N != 1) or out.stride(0) < N:
+        raise RuntimeError("dreamer_b200.mm_nt: `out` must be a row-major fp32 [M, N] tensor")
+    flags = (GEMM_TRANS_A if ta else 0) | (GEMM_TRANS_B if tb else 0) | (GEMM_ACCUMULATE if accumulate else 0) \
+        | (GEMM_A_DIRECT if a_direct else 0) | (GEMM_B_DIRECT if b_direct else 0)
+    lib = L.load()
+    nbytes = lib.drm_gemm_tf32_workspace_bytes(M, N, K)
+    ws = _gemm_workspace(at.device, nbytes)
+    bs = L.f32c(bias) if bias is not None else None
+    L.check(lib.drm_gemm_tf32(M, N, K, L.ptr(at), lda, L.ptr(bt), ldb, L.ptr(out), out.stride(0), L.ptr(bs), flags, L.ptr(ws),
+                              ws.numel(), L.stream()), "gemm_tf32")
+    return out
+
+
+def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+       a_direct: bool = False, b_direct: bool = False) -> torch.Tensor:
+    """out (+)= a [M, K] @ b [K, N]"""
+    return mm_nt(a, b.t(), out=out, accumulate=accumulate, a_direct=a_direct, b_direct=b_direct)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [rows, in] @ weight [out, in]^T + bias (torch.nn.functional.linear on 2-D inputs)"""
+    return mm_nt(x, weight, bias)
+
+
+def pack_tf32(w: torch.Tensor) -> torch.Tensor:
+    """K-major, TF32-rounded copy of the 2-D operand w [rows, K] (a transposed view is read in place) with a pitch that is a multiple
+    of 4 (mm_nt(..., b_direct=True) then reads it in place; for weights that stay fixed over the steps of a recurrence)."""
+    L.require_cuda(w, "w")
+    wt, ld, tr = _gemm_operand(w)
+    rows, K = wt.shape
+    Kp = (K + 3) // 4 * 4
+    out = torch.empty((rows, Kp), dtype=torch.float32, device=wt.device)
+    L.check(L.load().drm_pack_tf32(rows, K, L.ptr(wt), ld, 1 if tr else 0, L.ptr(out), Kp, L.stream()), "pack_tf32")
+    return out[:, :K]
+
+
+# --------------------------------------------------------------------------------------------
 # packed RSSM + rollout workspace
 # --------------------------------------------------------------------------------------------
 def _mlp_struct(sd: Dict[str, torch.Tensor], prefix: Optional[str], keep: list, final: bool = True) -> L.DrmMlpW:

@@ -332,6 +332,34 @@ int drm_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
 /* ||grad||_2 over the flat buffer -> norm_out[0] (device float).  Deterministic two-stage reduction (fp64 partials).        */
 int drm_grad_norm(const float* grad, int64_t n, void* scratch, float* norm_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Contractions of the backward passes: what autograd's mm / addmm nodes do behind                     */
+/* WorldModel.training_step's loss.backward() (WorldModel.py:193) and Agent.train_step's (Agent.py:141-151), on this          */
+/* library's TMA / tcgen05 kind::tf32 kernel (csrc/gemm_tf32.cu) instead of a library GEMM:                                   */
+/*   C[M, N] (+)= op(A)[M, K] * op(B)[N, K]^T (+ bias[n]),  fp32 row-major in / out, operands rounded to TF32, fp32 accumulate */
+/*   A: [M, K] (lda), or [K, M] with DRM_GEMM_TRANS_A;   B: [N, K] (ldb), or [K, N] with DRM_GEMM_TRANS_B;   bias may be NULL  */
+/*   forward  Y = X W^T + b: flags 0;   input gradient dX = dY W: TRANS_B;   weight gradient dW += dY^T X: TRANS_A|TRANS_B|ACCUMULATE */
+/* Both operands are first rewritten K-major and ROUNDED to nearest TF32 by a pack kernel (a tensor core truncates a plain fp32     */
+/* operand; the bias compounds over the steps of a recurrence) -- except: an operand flagged DRM_GEMM_A_DIRECT / _B_DIRECT (the      */
+/* caller has rounded it already, e.g. weights through drm_pack_tf32 once per backward) is read in place by TMA in either            */
+/* orientation when its base is 16-byte aligned and its leading dimension a multiple of 4; and the few-row operand A of a skinny      */
+/* problem (M <= 64, not transposed) is rounded inside the GEMM kernel.                                                         */
+/* workspace: device memory, 256-byte aligned, >= drm_gemm_tf32_workspace_bytes(M, N, K).  Its first 1024 bytes (split-K tile      */
+/* tickets) must be ZERO before the first call and are left zero by every call; calls that share a workspace must be             */
+/* stream-ordered.  1 - 2 launches, no host synchronisation, deterministic (a K split is summed in split order by the last       */
+/* CTA of each tile): safe inside CUDA-graph capture.                                                                         */
+#define DRM_GEMM_TRANS_A 1
+#define DRM_GEMM_TRANS_B 2
+#define DRM_GEMM_ACCUMULATE 4
+#define DRM_GEMM_A_DIRECT 8
+#define DRM_GEMM_B_DIRECT 16
+int64_t drm_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                  int64_t ldc, const float* bias, int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+/* out[r][k] = tf32_round(trans ? in[k][r] : in[r][k]) for r < rows, k < K, zeros up to ld_out (a multiple of 4): a K-major,     */
+/* pre-rounded operand for drm_gemm_tf32 (weights that stay fixed over the steps of a recurrence).                            */
+int drm_pack_tf32(int32_t rows, int32_t K, const float* in, int64_t ld, int32_t trans, float* out, int64_t ld_out, void* stream);
+
 /* Test hook: plain bf16 GEMM  out[M, N] = A[M, K] * W[N, K]^T + bias  through the same TMA /      */
 /* tcgen05 main loop the fused stages use (fp32 inputs are rounded to bf16 on the device).        */
 int drm_test_gemm(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
