@@ -23,8 +23,8 @@ from . import dist as D
 from . import ops
 
 
-# The backward's library GEMMs run on the tensor cores in TF32 (10-bit mantissa, what the reference's fp16 autocast keeps,
-# WorldModel.py:162); set to False for bit-for-bit fp32 GEMMs (the gradient tests compare both ways against fp32 autograd).
+# The backward's GEMMs run on the tensor cores in TF32 (10-bit mantissa, what the reference's fp16 autocast keeps,
+# WorldModel.py:162); False = fp32 library GEMMs whatever the backend below (the exact mode the gradient tests start from).
 MATMUL_TF32 = True
 
 
@@ -53,21 +53,33 @@ def _side_stream(dev):
 # GEMMs inside the two recurrence walks (16 - 1024 rows).
 GEMM_BATCHED = "drm"
 GEMM_STEP = "drm"
+# Step GEMMs with more gradient rows than this stay library GEMMs: up to 64 rows the problem runs swapped with the rows as the MMA's
+# N dimension, rounded inside the kernel, K split over a cluster (5.6 - 8.2 us against 4.6 - 7.8 us for the library GEMM, in a graph);
+# a 1024-row step GEMM needs a pack launch for the rounding and is ingress-bound at 128 x 128 tiles (26 us against 9.4 us) --
+# measured with profiles/gemm_tf32_time.py, numbers in profiles/README.md.
+GEMM_STEP_MAX_ROWS = 64
 
 
 def _mm(a, b, out=None, accumulate=False, step=False):
-    """out (+)= a [M, K] @ b [K, N]"""
-    if (GEMM_STEP if step else GEMM_BATCHED) == "drm":
-        return ops.mm(a, b, out=out, accumulate=accumulate)
+    """out (+)= a [M, K] @ b [K, N].  Operand policy of the "drm" backend: a step GEMM multiplies gradient rows (rounded to nearest
+    TF32 on the way in -- the walks compound any bias over their steps) by a weight pre-rounded with _rounded() and read in place;
+    a batched GEMM reads both operands in place when they are aligned (tensor-core truncation, as a library TF32 GEMM)."""
+    if (GEMM_STEP if step else GEMM_BATCHED) == "drm" and MATMUL_TF32 and not (step and a.shape[0] > GEMM_STEP_MAX_ROWS):
+        return ops.mm(a, b, out=out, accumulate=accumulate, a_direct=not step, b_direct=True)
     if out is None:
         return torch.mm(a, b)
     return out.addmm_(a, b) if accumulate else torch.mm(a, b, out=out)
 
 
+def _rounded(w):
+    """weight operand of the step GEMMs: a TF32-rounded, aligned copy made once per backward (drm backend), else w itself"""
+    return ops.pack_tf32(w) if GEMM_STEP == "drm" and MATMUL_TF32 else (w if w.is_contiguous() else w.contiguous())
+
+
 def _linear(x, weight, bias):
     """x [rows, in] @ weight [out, in]^T + bias"""
-    if GEMM_BATCHED == "drm":
-        return ops.mm_nt(x, weight, bias)
+    if GEMM_BATCHED == "drm" and MATMUL_TF32:
+        return ops.mm_nt(x, weight, bias, a_direct=True, b_direct=True)
     return torch.addmm(bias, x, weight.t())
 
 
@@ -81,8 +93,8 @@ def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
     """p.grad += a_t^T @ b   (a_t [rows, out], b [rows, in])"""
     if p.grad is None:
         p.grad = torch.zeros_like(p)
-    if GEMM_BATCHED == "drm" and p.grad.dim() == 2 and p.grad.is_contiguous():
-        ops.mm_nt(a_t.t(), b.t(), out=p.grad, accumulate=True)
+    if GEMM_BATCHED == "drm" and MATMUL_TF32 and p.grad.dim() == 2 and p.grad.is_contiguous():
+        ops.mm_nt(a_t.t(), b.t(), out=p.grad, accumulate=True, a_direct=True, b_direct=True)
     else:
         p.grad.addmm_(a_t.t(), b)
 
@@ -208,10 +220,10 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         dLG = torch.empty(T, B, Z, device=dev)
         dGI = torch.empty(T, B, 3 * Dh, device=dev)
         dGH = torch.empty(T, B, 3 * Dh, device=dev)
-        W2 = lin2.weight                                                        # (Z, Hn)
-        W1h = lin1.weight[:, n_feat:].contiguous()                              # (Hn, D)
-        Wih_z = gru.weight_ih[:, :Z].contiguous()                               # (3D, Z)
-        Whh = gru.weight_hh                                                     # (3D, D)
+        W2 = _rounded(lin2.weight)                                              # (Z, Hn)
+        W1h = _rounded(lin1.weight[:, n_feat:])                                 # (Hn, D)
+        Wih_z = _rounded(gru.weight_ih[:, :Z])                                  # (3D, Z)
+        Whh = _rounded(gru.weight_hh)                                           # (3D, D)
         A1_tm = A1.view(T, B, -1)
         dz_carry = None
         # The recurrent term dgh_t W_hh is only needed by the GRU cell backward of step t - 1, three kernels further down the chain
@@ -328,9 +340,10 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         LG = _linear(PY2, p3.weight, p3.bias).view(H, B, Z)                               # prior logits of states 1..H
         P1, P2 = P1.view(H, B, -1), P2.view(H, B, -1)
         A1s, A2s, LSs = A1.view(H, B, -1), A2.view(H, B, -1), LS.view(H, B, A)
-        Wih_z, Wih_a = gru.weight_ih[:, :Z].contiguous(), gru.weight_ih[:, Z:].contiguous()
-        W1_h, W1_z = l1.weight[:, :Dh].contiguous(), l1.weight[:, Dh:].contiguous()
-        Whead = torch.cat([actor.mu_head.weight, actor.log_sig_head.weight], 0)         # (2A, h2)
+        Wih_z, Wih_a, Whh = _rounded(gru.weight_ih[:, :Z]), _rounded(gru.weight_ih[:, Z:]), _rounded(gru.weight_hh)
+        W1_h, W1_z, W2a = _rounded(l1.weight[:, :Dh]), _rounded(l1.weight[:, Dh:]), _rounded(l2.weight)
+        Wp1, Wp2, Wp3 = _rounded(p1.weight), _rounded(p2.weight), _rounded(p3.weight)
+        Whead = _rounded(torch.cat([actor.mu_head.weight, actor.log_sig_head.weight], 0))   # (2A, h2)
         dHEAD = torch.empty(H, B, 2 * A, device=h.device)                               # d/d[mu | log-sigma pre-activation]
         dY2s, dY1s = torch.empty_like(A2s), torch.empty_like(A1s)
         dgi, dgh = torch.empty(B, 3 * Dh, device=h.device), torch.empty(B, 3 * Dh, device=h.device)
@@ -340,19 +353,19 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
             ch = cz = None                                                              # carried into state s from the transition s -> s + 1
             if Gh is not None:
                 dlg = ops.categorical32_bwd(LG[s], Gz)                                  # z_{s+1} = ST(prior(h_{s+1}))
-                dP2 = ops.ln_silu_bwd(_mm(dlg, p3.weight, step=True), P2[s], q2.weight, q2.bias, q2.eps)
-                dP1 = ops.ln_silu_bwd(_mm(dP2, p2.weight, step=True), P1[s], q1.weight, q1.bias, q1.eps)
-                _mm(dP1, p1.weight, out=Gh, accumulate=True, step=True)                                              # total d/dh_{s+1}
+                dP2 = ops.ln_silu_bwd(_mm(dlg, Wp3, step=True), P2[s], q2.weight, q2.bias, q2.eps)
+                dP1 = ops.ln_silu_bwd(_mm(dP2, Wp2, step=True), P1[s], q1.weight, q1.bias, q1.eps)
+                _mm(dP1, Wp1, out=Gh, accumulate=True, step=True)                                              # total d/dh_{s+1}
                 ch = torch.empty_like(Gh)
                 ops.gru_bwd(Gh, GI[s], GH[s], Htm[s], dgi, dgh, ch, accumulate=False)   # h_{s+1} = GRU([z_s, a_s], h_s)
-                _mm(dgh, gru.weight_hh, out=ch, accumulate=True, step=True)
+                _mm(dgh, Whh, out=ch, accumulate=True, step=True)
                 cz = _mm(dgi, Wih_z, step=True)
                 da = _mm(dgi, Wih_a, step=True)
             # actor at state s: a_s = tanh(mu_s + sigma_s eps_s), sigma = softplus(clamp(ls, -5, 2)) + 1e-3 (Agent.py:199-209)
             ops.actor_head_bwd(gMU[s], gSG[s], da, Atm[s], EPS[s], LSs[s], dHEAD[s])
             _mm(dHEAD[s], Whead, out=dY2s[s], step=True)
             dA2 = ops.ln_silu_bwd(dY2s[s], A2s[s], n2.weight, n2.bias, n2.eps)
-            _mm(dA2, l2.weight, out=dY1s[s], step=True)
+            _mm(dA2, W2a, out=dY1s[s], step=True)
             if s > 0:                                                                   # state 0 is an input: nothing upstream
                 dA1 = ops.ln_silu_bwd(dY1s[s], A1s[s], n1.weight, n1.bias, n1.eps)
                 Gh = _mm(dA1, W1_h, step=True) if ch is None else _mm(dA1, W1_h, out=ch, accumulate=True, step=True)

@@ -17,13 +17,15 @@
 //     drm_pack_tf32) is passed with DRM_GEMM_A_DIRECT / _B_DIRECT and read IN PLACE by TMA whichever way it lies -- K-first rows
 //     (128-byte-swizzled boxes of 32 k x rows) or K-last (MN-major: boxes of 32 rows x 32 k, SWIZZLE_128B_ATOM_32B, UMMA descriptors
 //     with the transpose bit) -- if its base is 16-byte aligned and its pitch a multiple of 4 floats (else it is packed after all).
-//   * gemm_tf32_kernel: 128 x bn output tiles (bn <= 128), a 3-stage ring of 2 k-blocks (32 fp32 = one swizzle row) per stage,
+//   * gemm_tf32_kernel: 128 x bn output tiles (bn <= 128), a 2-stage ring of 2 k-blocks (32 fp32 = one swizzle row) per stage,
 //     tcgen05.mma kind::tf32 accumulating in TMEM, 16 epilogue warps.  Skinny problems (M <= 64 rows: the per-time-step GEMMs of the
 //     recurrences) run swapped -- the WEIGHT rows fill the 128 MMA rows, the few gradient rows are the N dimension -- and their
 //     few-row operand needs no pack launch: the epilogue warps, idle under the main loop, round this CTA's K slice of it and write
-//     it into shared memory in the swizzled operand layout themselves.  Problems with fewer than ~100 tiles are split along K over
-//     gridDim.z; every CTA stores its partial tile, takes a ticket, and the LAST CTA of a tile sums the partials in split order
-//     (deterministic whatever the arrival order), applies bias / accumulate and stores C.
+//     it into shared memory in the swizzled operand layout themselves; the 2 / 4 / 8 CTAs that split a skinny tile's K form a
+//     thread-block cluster and reduce through distributed shared memory (each CTA owns a slice of the tile's rows, the peers push
+//     their partial sums into it, one cluster barrier, a z-ordered sum).  Other problems with fewer than ~100 tiles are split
+//     along K over gridDim.z through global memory: every CTA stores its partial tile, takes a ticket, and the LAST CTA of a tile sums
+//     the partials in split order (deterministic whatever the arrival order), applies bias / accumulate and stores C.
 #include <algorithm>
 #include <cmath>
 #include <string>
@@ -38,19 +40,22 @@ constexpr int TM = 128;                 // MMA rows per tile (UMMA M == TMEM lan
 constexpr int TN = 128;                 // widest N tile
 constexpr int TK = 32;                  // fp32 per k-block: one 128-byte swizzle row
 constexpr int KPS = 2;                  // k-blocks per pipeline stage
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int P_BYTES = TM * TK * 4;    // 16 KB
 constexpr int Q_BYTES = TN * TK * 4;    // 16 KB
 constexpr int SUB_BYTES = P_BYTES + Q_BYTES;
 constexpr int STAGE_BYTES = KPS * SUB_BYTES;
-constexpr int BAR_OFF = STAGES * STAGE_BYTES;          // 192 KB
+constexpr int BAR_OFF = STAGES * STAGE_BYTES;          // 128 KB
 constexpr int QREG_OFF = BAR_OFF + 1024;               // swapped skinny problems: this CTA's whole slice of the few-row operand,
-constexpr int QREG_BYTES = 32 * 1024;                  //   rounded and swizzled by the epilogue warps (no pack launch)
-constexpr int SMEM_TOTAL = QREG_OFF + QREG_BYTES + 1024;   // + alignment slack
+constexpr int QREG_BYTES = 64 * 1024;                  //   rounded and swizzled by the epilogue warps (no pack launch)
+constexpr int XCHG_OFF = QREG_OFF + QREG_BYTES;        // cluster split-K: the partial sums the peer CTAs push into this CTA's slice
+constexpr int XCHG_BYTES = 32 * 1024;                  //   [split][bn][128 / split] fp32 <= bn * 512 B
+constexpr int SMEM_TOTAL = XCHG_OFF + XCHG_BYTES + 1024;   // + alignment slack
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int TILE_PITCH = TN + 4;                     // fp32 words per row of the transposition tile (67.6 KB, reuses the ring)
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 static_assert(TM * TILE_PITCH * 4 <= BAR_OFF, "output tile must fit in the pipeline's shared memory");
 
 struct GemmArgs {
@@ -69,6 +74,7 @@ struct GemmArgs {
   const float* q_src;      // q_convert: the N-side operand [QR][K] as the caller gave it (any alignment), pitch q_src_ld
   long q_src_ld;
   int q_convert, K;
+  int cluster;             // 1: the `split` CTAs of a tile form a thread-block cluster and reduce through distributed shared memory
 };
 
 // MN-major fp32 operand descriptor.  32-bit MN-major operands have one legal shared-memory layout (cute::UMMA
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (g.cluster) cluster_arrive_release();   // phase 1 ("this CTA runs"): waited for just before the first remote store
 
   if (warp == 0) {
     if (lane == 0) {
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
     const int row = q * 32 + lane;
     const bool active = part * 32 < g.bn;
     // first destination: C itself, or this split's plane of the partial buffer (C layout, padded: no guards / bias / accumulate)
-    const bool direct = split == 1;
+    const bool direct = split == 1 || g.cluster;
     const int C_rows = g.swap ? g.QR : g.PR, C_cols = g.swap ? g.PR : g.QR;
     float* dst = direct ? g.C : g.part + (long)z * g.part_plane;
     const long ld = direct ? g.ldc : g.part_ld;
@@ -204,15 +211,51 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
 
     if (g.q_convert) {
       // this CTA's slice of the few-row operand: global (any alignment) -> round to nearest TF32 -> K-major 128-byte-swizzled
-      // k-blocks of bn rows (rows >= QR and k >= K are zeros); consecutive threads take consecutive k (coalesced loads)
+      // k-blocks of bn rows (rows >= QR and k >= K are zeros)
       uint8_t* qreg = smem + QREG_OFF;
-      const int kcount = nkl * TK, kbase = kb0 * TK;
-      for (int idx = tid; idx < g.bn * kcount; idx += EPI_THREADS) {
-        const int r = idx / kcount, kk = idx - r * kcount;
-        const int kg = kbase + kk;
-        const float x = (r < g.QR && kg < g.K) ? tf32_rn(g.q_src[(long)r * g.q_src_ld + kg]) : 0.f;
-        const int kb = kk >> 5, kin = kk & 31;
-        *reinterpret_cast<float*>(qreg + (long)kb * (g.bn * 128) + r * 128 + ((((kin >> 2) ^ (r & 7))) << 4) + ((kin & 3) << 2)) = x;
+      const bool vec = ((reinterpret_cast<uintptr_t>(g.q_src) & 15u) == 0) && ((g.q_src_ld & 3) == 0);
+      if (vec) {
+        // 16-byte chunks: chunk j of row r = floats [4j, 4j + 4) of this CTA's K slice; consecutive threads take consecutive chunks of
+        // a row (coalesced), every load is issued before the first store (at most QREG_BYTES / 16 / 512 = 8 chunks per thread)
+        const int cpr = nkl * 8;                                               // chunks per row, <= 256
+        const int n_chunk = g.bn * cpr;
+        const uint32_t inv = (uint32_t)((0x100000000ull + (uint32_t)cpr - 1u) / (uint32_t)cpr);   // idx / cpr == umulhi(idx, inv) (idx < 4096, 8 <= cpr <= 256)
+        constexpr int PER = QREG_BYTES / 16 / EPI_THREADS;
+        float4 x[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int idx = tid + i * EPI_THREADS;
+          x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < n_chunk) {
+            const int r = (int)__umulhi((uint32_t)idx, inv), j = idx - r * cpr;
+            const int kg = kb0 * TK + j * 4;
+            if (r < g.QR && kg < g.K) {
+              const float* src = g.q_src + (long)r * g.q_src_ld + kg;
+              if (kg + 3 < g.K) x[i] = *reinterpret_cast<const float4*>(src);
+              else { x[i].x = src[0]; if (kg + 1 < g.K) x[i].y = src[1]; if (kg + 2 < g.K) x[i].z = src[2]; }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int idx = tid + i * EPI_THREADS;
+          if (idx < n_chunk) {
+            const int r = (int)__umulhi((uint32_t)idx, inv), j = idx - r * cpr;
+            const int kb = j >> 3, c = j & 7;
+            *reinterpret_cast<float4*>(qreg + (long)kb * (g.bn * 128) + r * 128 + ((c ^ (r & 7)) << 4)) =
+                make_float4(tf32_rn(x[i].x), tf32_rn(x[i].y), tf32_rn(x[i].z), tf32_rn(x[i].w));
+          }
+        }
+      } else {
+        // unaligned source: one float at a time, consecutive threads on consecutive k
+        const int kcount = nkl * TK, kbase = kb0 * TK;
+        for (int idx = tid; idx < g.bn * kcount; idx += EPI_THREADS) {
+          const int r = idx / kcount, kk = idx - r * kcount;
+          const int kg = kbase + kk;
+          const float xv = (r < g.QR && kg < g.K) ? tf32_rn(g.q_src[(long)r * g.q_src_ld + kg]) : 0.f;
+          const int kb = kk >> 5, kin = kk & 31;
+          *reinterpret_cast<float*>(qreg + (long)kb * (g.bn * 128) + r * 128 + ((((kin >> 2) ^ (r & 7))) << 4) + ((kin & 3) << 2)) = xv;
+        }
       }
       fence_proxy_async();
       epi_bar();
@@ -222,7 +265,38 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
     tc_fence_after();
     float v[32];
     if (active) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 32), v);
-    if (g.swap) {
+    if (g.cluster) {
+      // Cluster split-K (swapped tiles): CTA z owns rows [z * slice, (z + 1) * slice) of the tile.  Every CTA pushes its partial sums
+      // of a row into the owner's exchange buffer [source z][q][row in slice] (st.shared::cluster; lanes = consecutive rows), one
+      // cluster barrier, then the owner adds the `split` partials in z order: no global round trip, no atomics, no fences.
+      const int slice = TM / split;
+      float* xchg = reinterpret_cast<float*>(smem + XCHG_OFF);
+      cluster_wait_acquire();              // every peer CTA has started: its shared memory may be written
+      if (active) {
+        const int owner = row / slice, rl = row - owner * slice;
+        uint32_t rbase;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbase) : "r"(smem_u32(xchg)), "r"((uint32_t)owner));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qq = part * 32 + j;
+          if (qq < g.bn)
+            asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(rbase + (uint32_t)(((z * g.bn + qq) * slice + rl) << 2)), "f"(v[j]) : "memory");
+        }
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      for (int idx = tid; idx < g.bn * slice; idx += EPI_THREADS) {
+        const int qq = idx / slice, rl = idx - qq * slice;
+        const int p = p0 + z * slice + rl, cq = q0 + qq;
+        if (p >= c_cols || cq >= c_rows) continue;
+        float sum = xchg[qq * slice + rl];
+        for (int zz = 1; zz < split; ++zz) sum += xchg[(zz * g.bn + qq) * slice + rl];
+        if (bias) sum += bias[p];
+        float* o = dst + (long)cq * ld + p;
+        if (acc) sum += *o;
+        *o = sum;
+      }
+    } else if (g.swap) {
       // C[q][p]: the 32 lanes of a warp hold 32 consecutive p for every q -> coalesced stores straight from registers
       const int p = p0 + row;
       if (active && p < c_cols) {
@@ -254,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
         store4(dst, ld, p0 + r, q0 + c, *reinterpret_cast<const float4*>(tile + r * TILE_PITCH + c), c_cols, bias, acc, al);
       }
     }
-    if (!direct) {
+    if (!direct) {          // (split > 1 without a cluster)
       // ticket: the last CTA of this tile to finish sums the `split` partial planes in z order and stores C
       uint32_t* last_flag = tmem_slot + 1;
       const int tile_id = (int)blockIdx.x + (int)gridDim.x * (int)blockIdx.y;
@@ -272,6 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
           if (R0 + r >= C_rows || C0 + c >= C_cols) continue;
           const float* src = g.part + (long)(R0 + r) * g.part_ld + C0 + c;
           float4 s = __ldcg(reinterpret_cast<const float4*>(src));
+#pragma unroll 8
           for (int zz = 1; zz < split; ++zz) {
             const float4 y = __ldcg(reinterpret_cast<const float4*>(src + (long)zz * g.part_plane));
             s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
@@ -281,6 +356,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
         if (tid == 0) g.tickets[tile_id] = 0u;       // ready for the next call on this workspace
       }
     }
+  }
+  if (g.cluster && warp < 2) {       // the producer / MMA warps take part in the epilogue's cluster barrier
+    __syncwarp();
+    cluster_wait_acquire();
+    cluster_arrive_release();
+    cluster_wait_acquire();
   }
   tc_fence_before();
   __syncthreads();
@@ -327,7 +408,7 @@ constexpr long PART_MAX_BYTES = 148L * TM * TN * 4;   // split * tiles <= 148 CT
 
 struct Plan {
   int swap, PR, QR, bn, nk, split, mt, nt;
-  bool pack_a, pack_b, q_convert;
+  bool pack_a, pack_b, q_convert, cluster;
   long kp;                         // packed pitch (elements)
   long off_a, off_b, off_part;     // workspace offsets (bytes)
   long part_ld, part_plane;        // elements
@@ -340,7 +421,7 @@ inline bool aligned_operand(const float* p, long ld) { return (((uintptr_t)p & 1
 // a_direct / b_direct: the operand is read in place by TMA (caller's flag and aligned); a_kfirst: A lies [M][K]
 Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst) {
   Plan p{};
-  p.swap = (M <= 64 && N > M) ? 1 : 0;
+  p.swap = M <= 64 ? 1 : 0;
   p.PR = p.swap ? N : M;
   p.QR = p.swap ? M : N;
   p.bn = p.QR >= TN ? TN : round_up(p.QR, 16);
@@ -362,13 +443,24 @@ Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst)
     const int s_min = ceil_div(p.nk, kb_fit);
     if (s_min <= std::min(148 / tiles, p.nk)) { p.q_convert = true; p.split = std::max(p.split, s_min); }
   }
+  // swapped tiles of up to 64 rows of C: 2 / 4 / 8 CTAs per tile as a cluster, reduction through distributed shared memory
+  p.cluster = false;
+  if (p.swap && p.nt == 1 && p.bn * 512 <= XCHG_BYTES && p.nk >= 4) {
+    const int sc = p.nk >= 16 ? 8 : (p.nk >= 8 ? 4 : 2);
+    const bool convert_ok = !(p.swap && !a_direct && a_kfirst) || ceil_div(p.nk, sc) * p.bn * 128 <= QREG_BYTES;
+    if (sc * tiles <= 148 && convert_ok) {
+      p.cluster = true;
+      p.split = sc;
+      p.q_convert = !a_direct && a_kfirst;
+    }
+  }
   p.pack_a = !a_direct && !p.q_convert; p.pack_b = !b_direct;
   p.kp = round_up(K, 4);
   long off = TICKET_BYTES;
   p.off_a = off; if (p.pack_a) off = align256(off + (long)M * p.kp * 4);
   p.off_b = off; if (p.pack_b) off = align256(off + (long)N * p.kp * 4);
   p.off_part = off;
-  if (p.split > 1) {
+  if (p.split > 1 && !p.cluster) {
     const long c_rows_pad = p.swap ? (long)p.nt * p.bn : (long)p.mt * TM;
     const long c_cols_pad = p.swap ? (long)p.mt * TM : (long)p.nt * p.bn;
     p.part_ld = c_cols_pad;
@@ -455,17 +547,30 @@ extern "C" int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, in
   g.p_mn = p_mn; g.q_mn = q_mn;
   g.accumulate = (flags & DRM_GEMM_ACCUMULATE) ? 1 : 0;
   g.bias = bias; g.C = C; g.ldc = ldc;
-  g.part = p.split > 1 ? reinterpret_cast<float*>(ws + p.off_part) : nullptr;
+  g.part = (p.split > 1 && !p.cluster) ? reinterpret_cast<float*>(ws + p.off_part) : nullptr;
+  g.cluster = p.cluster ? 1 : 0;
   g.part_ld = p.part_ld; g.part_plane = p.part_plane;
   g.tickets = reinterpret_cast<unsigned int*>(ws);
-  DRM_REQUIRE(p.split == 1 || p.mt * p.nt <= (int)(TICKET_BYTES / 4), DRM_ERR_SHAPE, "drm_gemm_tf32: internal: too many split tiles");
+  DRM_REQUIRE(p.split == 1 || p.cluster || p.mt * p.nt <= (int)(TICKET_BYTES / 4), DRM_ERR_SHAPE, "drm_gemm_tf32: internal: too many split tiles");
 
   static bool attr_set = false;
   if (!attr_set) {
     DRM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
-  gemm_tf32_kernel<<<dim3(p.mt, p.nt, p.split), THREADS, SMEM_TOTAL, st>>>(g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.mt, p.nt, p.split);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (p.cluster) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p.split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  DRM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, g));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

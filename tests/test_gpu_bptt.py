@@ -92,6 +92,18 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
         scale = float(g_ref[k].abs().max()) + 1e-8
         err = float((g_ref[k] - g_new[k]).abs().max()) / scale
         assert err < 2e-3, (k, err, scale)
+    # every contraction on this library's TF32 GEMM (drm_gemm_tf32; convs still fp32): 5e-3 of each tensor's largest gradient
+    # (measured worst 2.6e-3 -- TF32 keeps 10 mantissa bits, operands rounded to nearest)
+    bptt.MATMUL_TF32 = True
+    assert bptt.GEMM_BATCHED == "drm" and bptt.GEMM_STEP == "drm"
+    wm.optimiser.zero_grad()
+    bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_fp32, parts)
+    g_t = _grads(wm)
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max()) + 1e-8
+        err = float((g_ref[k] - g_t[k]).abs().max()) / scale
+        assert err < 5e-3, (k, err, scale)
+    bptt.MATMUL_TF32 = False
     # on the kernels' trajectory: same gradient up to the bf16 state rounding
     wm.optimiser.zero_grad()
     bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_k, parts)
@@ -99,7 +111,7 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
     num = sum(float(((g_ref[k] - g_k[k]) ** 2).sum()) for k in g_ref)
     den = sum(float((g_ref[k] ** 2).sum()) for k in g_ref)
     assert (num / den) ** 0.5 < 5e-2
-    # default: TF32 library GEMMs and the batched encoder / decoder conv graphs under bf16 autocast (the reference runs
+    # default: TF32 GEMMs (this library's) and the batched encoder / decoder conv graphs under bf16 autocast (the reference runs
     # the whole step under fp16 autocast)
     bptt.MATMUL_TF32 = True
     wm.conv_grad_dtype = torch.bfloat16

@@ -27,6 +27,8 @@ SHAPES = [
     (16, 600, 1800),      # one BPTT step: dgh W_hh (swapped, split-K)
     (50, 1024, 256),      # one actor-backward step
     (1800, 1027, 1024),   # weight-gradient shape
+    (50, 3, 1800),        # d(action) of one actor-backward step: few rows AND few columns
+    (50, 600, 1800), (64, 1024, 2048), (24, 6, 256),
     (1, 1, 1), (3, 5, 7), (129, 17, 33), (64, 65, 40), (65, 64, 40), (300, 3, 256), (2, 1030, 96), (257, 255, 8),
 ]
 
