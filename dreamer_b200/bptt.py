@@ -386,3 +386,40 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         _acc(n1.bias, dln1.sum(0))
         _acc_mm(l1.weight, dA1_all, Xa)
         _acc(l1.bias, dA1_all.sum(0))
+
+
+def _mlp3_backward(net, x, d_out_fn):
+    """Parameter gradients (accumulated into ``.grad``) of a Linear-LN-SiLU-Linear-LN-SiLU-Linear stack (modules._mlp) on the batched
+    rows x [rows, in]: fp32 re-evaluation of the pre-activations on this library's GEMM, d_out_fn(logits) -> d(loss)/d(logits), then
+    the chain rule layer by layer (drm_ln_silu_bwd, drm_gemm_tf32).  Returns d(loss)/dx when the caller wants it (else None is fine)."""
+    l1, n1, _, l2, n2, _, l3 = net
+    a1, y1, a2, y2 = _mlp_fwd(x, l1, n1, l2, n2)
+    logits = _linear(y2, l3.weight, l3.bias)
+    d3 = d_out_fn(logits)
+    _acc_mm(l3.weight, d3, y2)
+    _acc(l3.bias, d3.sum(0))
+    da2, dln2 = ops.ln_silu_bwd(_mm(d3, l3.weight), a2, n2.weight, n2.bias, n2.eps, want_dln=True)
+    _acc(n2.weight, (dln2 * F.layer_norm(a2, (a2.shape[-1],), None, None, n2.eps)).sum(0))
+    _acc(n2.bias, dln2.sum(0))
+    _acc_mm(l2.weight, da2, y1)
+    _acc(l2.bias, da2.sum(0))
+    da1, dln1 = ops.ln_silu_bwd(_mm(da2, l2.weight), a1, n1.weight, n1.bias, n1.eps, want_dln=True)
+    _acc(n1.weight, (dln1 * F.layer_norm(a1, (a1.shape[-1],), None, None, n1.eps)).sum(0))
+    _acc(n1.bias, dln1.sum(0))
+    _acc_mm(l1.weight, da1, x)
+    _acc(l1.bias, da1.sum(0))
+    return da1
+
+
+def critic_backward(agent, z, h, returns, n_global):
+    """Accumulate into the CRITIC parameters' ``.grad`` the gradient of  -sum_{b,t} twohot(symlog(R_bt)) . log_softmax(critic(h_bt, z_bt)) / N
+    (Agent.py:128-134 as autograd differentiates it): the states and the lambda-returns are constants, so the whole pass is one batched
+    MLP backward -- two-hot cross-entropy backward (drm_twohot_ce_bwd), LayerNorm-SiLU backward (drm_ln_silu_bwd) and this library's
+    GEMMs; no autograd graph.  z (B,H+1,R,C), h (B,H+1,D), returns (B,H,1), n_global a 0-d device tensor (global element count)."""
+    with _matmul_precision(), torch.no_grad():
+        B, H1 = h.shape[:2]
+        x = torch.cat([h.detach()[:, :-1], z.detach().reshape(B, H1, -1)[:, :-1]], -1).reshape(B * (H1 - 1), -1)
+        inv_n = 1.0 / n_global
+        _mlp3_backward(agent.critic.value_net, x,
+                       lambda lg: ops.twohot_ce_bwd(lg, returns.reshape(-1, 1), agent.critic.buckets_crit, scale_dev=inv_n, scale=-1.0,
+                                                    apply_symlog=True))

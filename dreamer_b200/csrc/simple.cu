@@ -501,6 +501,52 @@ __global__ void __launch_bounds__(256) twohot_ce_kernel(const float* __restrict_
   }
 }
 
+// Backward of twohot_ce_kernel: d ll[row] / d logits[row][c] = twohot(v)[c] - softmax(logits[row])[c]; one warp per row.
+//   dlogits[row][c] = scale * (scale_dev ? *scale_dev : 1) * (coef ? coef[row] : 1) * (twohot[c] - softmax[c])
+// (coef: a per-row mask / weight; scale_dev: a device scalar such as 1 / (global element count), so no host read is needed)
+__global__ void __launch_bounds__(256) twohot_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ value,
+                                                            const float* __restrict__ buckets, const float* __restrict__ coef,
+                                                            const float* __restrict__ scale_dev, float scale, float* __restrict__ dlogits,
+                                                            int64_t N, int NB, int apply_symlog) {
+  __shared__ float sb[256];
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) sb[i] = buckets[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  for (int64_t row = warp; row < N; row += nwarps) {
+    const float* x = logits + row * NB;
+    float xv[8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      xv[j] = c < NB ? __ldg(x + c) : -INFINITY;
+      m = fmaxf(m, xv[j]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { xv[j] = (lane + 32 * j < NB) ? expf(xv[j] - m) : 0.f; s += xv[j]; }
+    const float inv = 1.0f / warp_sum(s);
+    float v = __ldg(value + row);
+    if (apply_symlog) v = symlogf_(v);
+    int idx; float w;
+    twohot_index_weight(sb, NB, v, idx, w);
+    const float g = sc * (coef ? __ldg(coef + row) : 1.0f);
+    float* o = dlogits + row * NB;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      if (c < NB) {
+        const float t = c == idx ? 1.0f - w : (c == idx + 1 ? w : 0.f);
+        o[c] = (v != v) ? v : g * (t - xv[j] * inv);
+      }
+    }
+  }
+}
+
 // symexp(sum(softmax(logits) * buckets)), one warp per row.  DynamicsPredictors.py:70-74.
 __global__ void __launch_bounds__(256) bucket_value_kernel(const float* __restrict__ logits, const float* __restrict__ buckets,
                                                            float* __restrict__ value, int64_t N, int NB) {
@@ -696,6 +742,18 @@ extern "C" int drm_lambda_return(const float* rew, const float* cont, const floa
   if (B == 0) return DRM_OK;
   DRM_REQUIRE(rew && cont && value && out, DRM_ERR_ARG, "drm_lambda_return: NULL pointer");
   lambda_return_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(rew, cont, value, out, B, H, gamma, lambda_);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_twohot_ce_bwd(const float* logits, const float* value, const float* buckets, const float* coef, const float* scale_dev,
+                                 float scale, float* dlogits, int64_t N, int32_t NB, int32_t apply_symlog, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(N >= 0 && NB >= 2 && NB <= 256, DRM_ERR_SHAPE, "drm_twohot_ce_bwd: NB must be in [2, 256]");
+  if (N == 0) return DRM_OK;
+  DRM_REQUIRE(logits && value && buckets && dlogits, DRM_ERR_ARG, "drm_twohot_ce_bwd: NULL pointer");
+  twohot_ce_bwd_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, value, buckets, coef, scale_dev, scale, dlogits, N, NB,
+                                                                       apply_symlog);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -400,12 +400,16 @@ class Agent(nn.Module):
         B, H1 = h_batch_seq.shape[:2]
         hz = torch.cat([h_batch_seq.detach(), z_batch_seq.detach().reshape(B, H1, -1)], -1)
         self.critic_optimiser.zero_grad()
-        lsm = F.log_softmax(self.critic.value_net(hz[:, :-1]), -1)
-        b = self.critic.buckets_crit
-        tv = torch.maximum(torch.minimum(symlog(f["returns"]), b[-1]), b[0])   # clamp to the (sorted) bucket range, no host read
-        lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
-        w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
-        ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / f["n_global"]).backward()
+        if self.__dict__.get("grad_mode", "bptt") == "bptt" and h_batch_seq.is_cuda:
+            # hand-scheduled batched MLP backward on the library's kernels (two-hot CE backward, LayerNorm-SiLU backward, drm_gemm_tf32)
+            bptt.critic_backward(self, z_batch_seq, h_batch_seq, f["returns"], f["n_global"])
+        else:       # grad_mode = "autograd": torch autograd on the batched MLP (the implementation critic_backward is tested against)
+            lsm = F.log_softmax(self.critic.value_net(hz[:, :-1]), -1)
+            b = self.critic.buckets_crit
+            tv = torch.maximum(torch.minimum(symlog(f["returns"]), b[-1]), b[0])   # clamp to the (sorted) bucket range, no host read
+            lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
+            w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+            ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / f["n_global"]).backward()
         self.actor_optimiser.zero_grad()
         wm = self.__dict__.get("_world_model")
         if wm is not None and self.__dict__.get("grad_mode", "bptt") == "bptt" and z_batch_seq.shape[-1] == 32:

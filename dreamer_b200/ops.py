@@ -187,6 +187,23 @@ def twohot_ce(logits, value, buckets, apply_symlog: bool = False):
     return out
 
 
+def twohot_ce_bwd(logits, value, buckets, coef=None, scale_dev=None, scale: float = 1.0, apply_symlog: bool = False):
+    """d/dlogits of sum(coef * twohot_ce(logits, value)) * scale * scale_dev: logits (..., NB), value (..., 1), coef (..., 1) or None,
+    scale_dev a 0-d device tensor or None -> (..., NB)."""
+    L.require_cuda(logits, "logits")
+    lg, v, b = L.f32c(logits), L.f32c(value), L.f32c(buckets)
+    NB = lg.shape[-1]
+    N = lg.numel() // NB
+    cf = L.f32c(coef) if coef is not None else None
+    sd = L.f32c(scale_dev) if scale_dev is not None else None
+    if v.numel() != N or (cf is not None and cf.numel() != N):
+        raise RuntimeError("dreamer_b200.twohot_ce_bwd: one value (and coefficient) per row is required")
+    out = torch.empty_like(lg)
+    L.check(L.load().drm_twohot_ce_bwd(L.ptr(lg), L.ptr(v), L.ptr(b), L.ptr(cf), L.ptr(sd), float(scale), L.ptr(out), N, NB,
+                                       1 if apply_symlog else 0, L.stream()), "twohot_ce_bwd")
+    return out
+
+
 def onehot32(idx: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """(..., ) uint8 classes < 32 -> (..., 32) fp32 one-hot (into `out` when given)."""
     L.require_cuda(idx, "idx")

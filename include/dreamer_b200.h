@@ -160,6 +160,11 @@ int drm_lambda_return(const float* rew, const float* cont, const float* value, f
 /* applied first when apply_symlog != 0), buckets [NB] -> ll [N] (log-likelihood, not negated).  */
 int drm_twohot_ce(const float* logits, const float* value, const float* buckets, float* ll, int64_t N, int32_t NB,
                   int32_t apply_symlog, void* stream);
+/* Backward of drm_twohot_ce (what autograd does behind WorldModel.py:193 / Agent.py:141-146 for the two-hot losses):              */
+/*   dlogits[row][c] = scale * (scale_dev ? *scale_dev : 1) * (coef ? coef[row] : 1) * (twohot(value[row])[c] - softmax(logits[row])[c]) */
+/* coef [N] (a mask / per-row weight) and scale_dev (a DEVICE scalar, e.g. 1 / global element count) may be NULL.                   */
+int drm_twohot_ce_bwd(const float* logits, const float* value, const float* buckets, const float* coef, const float* scale_dev,
+                      float scale, float* dlogits, int64_t N, int32_t NB, int32_t apply_symlog, void* stream);
 /* symexp(sum(softmax(logits) * buckets))  DynamicsPredictors.py:70-74, Agent.py:237-241.        */
 int drm_bucket_value(const float* logits, const float* buckets, float* value, int64_t N, int32_t NB, void* stream);
 

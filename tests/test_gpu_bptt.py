@@ -180,3 +180,66 @@ def test_actor_gradient_through_the_imagined_states_matches_autograd():
     den = sum(float((g_ref[k] ** 2).sum()) for k in g_ref)
     err_detached = (num / den) ** 0.5
     assert err_detached > 3e-3 and err_detached > 4 * err_tf32      # the omitted term is real, and well above the TF32 rounding
+
+
+def test_twohot_ce_bwd_matches_autograd():
+    from dreamer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, NB = 777, 255
+    logits = torch.randn(N, NB, device=DEV, generator=g) * 2
+    value = torch.randn(N, 1, device=DEV, generator=g) * 30
+    value[:5, 0] = torch.tensor([-1e9, 1e9, 0.0, 20.0, -20.0], device=DEV)          # outside / on the ends of the bucket range
+    coef = torch.rand(N, 1, device=DEV, generator=g)
+    buckets = torch.linspace(-20, 20, NB, device=DEV)
+    sd = torch.tensor(0.37, device=DEV)
+    for sym in (False, True):
+        lg = logits.clone().requires_grad_(True)
+        (ops.twohot_ce(lg.detach(), value, buckets, apply_symlog=sym) * 0).sum()      # forward kernel runs on the same inputs
+        v = torch.sign(value) * torch.log1p(value.abs()) if sym else value
+        v = torch.clamp(v, buckets[0], buckets[-1])
+        lo = torch.clamp(torch.searchsorted(buckets, v.contiguous(), right=True) - 1, max=NB - 2)
+        w = (v - buckets[lo]) / (buckets[lo + 1] - buckets[lo] + 1e-8)
+        lsm = F.log_softmax(lg, -1)
+        ll = (1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)
+        (-(coef * ll).sum() * sd * 2.0).backward()
+        got = ops.twohot_ce_bwd(logits, value, buckets, coef=coef, scale_dev=sd, scale=-2.0, apply_symlog=sym)
+        assert torch.allclose(got, lg.grad, rtol=1e-4, atol=1e-6)
+    got = ops.twohot_ce_bwd(logits, value, buckets)
+    assert torch.allclose(got.sum(-1), torch.zeros(N, device=DEV), atol=1e-5)          # twohot and softmax both sum to one
+
+
+def test_critic_backward_matches_autograd():
+    """bptt.critic_backward (two-hot CE backward + LayerNorm-SiLU backward + drm_gemm_tf32, no autograd graph) against torch autograd
+    on the batched critic MLP (Agent.py:128-134): fp32 library GEMMs first (2e-3 per tensor), then the default TF32 kernel."""
+    from dreamer_b200 import bptt
+    cfg = W.small_config(horizon=5)
+    wm, ag = W.build_learners(cfg, W.make_state_dict(cfg, seed=21, actor_mu_zero=False), DEV)
+    B, H1, D = 40, cfg["horizon"] + 1, cfg["hidden_state_dims"]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    z = F.one_hot(torch.randint(0, 32, (B, H1, 32), device=DEV, generator=g), 32).float()
+    h = torch.tanh(torch.randn(B, H1, D, device=DEV, generator=g))
+    R = torch.randn(B, H1 - 1, 1, device=DEV, generator=g) * 5
+    n_glob = torch.tensor(float(B * (H1 - 1)), device=DEV)
+    for p in ag.critic.parameters():
+        p.grad = None
+    x = torch.cat([h[:, :-1], z.reshape(B, H1, -1)[:, :-1]], -1)
+    b = ag.critic.buckets_crit
+    tv = torch.clamp(torch.sign(R) * torch.log1p(R.abs()), b[0], b[-1])
+    lo = torch.clamp(torch.searchsorted(b, tv.contiguous(), right=True) - 1, max=len(b) - 2)
+    w = (tv - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+    lsm = F.log_softmax(ag.critic.value_net(x), -1)
+    ((-((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1))).sum() / n_glob).backward()
+    g_ref = {k: p.grad.detach().clone() for k, p in ag.critic.named_parameters()}
+    den = sum(float((v ** 2).sum()) for v in g_ref.values())
+    for tf32, bound in ((False, 2e-3), (True, 5e-3)):
+        bptt.MATMUL_TF32 = tf32
+        for p in ag.critic.parameters():
+            p.grad = None
+        bptt.critic_backward(ag, z, h, R, n_glob)
+        num = 0.0
+        for k, p in ag.critic.named_parameters():
+            scale = float(g_ref[k].abs().max()) + 1e-12
+            assert float((g_ref[k] - p.grad).abs().max()) / scale < bound, (k, tf32)
+            num += float(((g_ref[k] - p.grad) ** 2).sum())
+        assert (num / den) ** 0.5 < bound
+    bptt.MATMUL_TF32 = True
