@@ -58,6 +58,10 @@ GEMM_STEP = "drm"
 # a 1024-row step GEMM needs a pack launch for the rounding and is ingress-bound at 128 x 128 tiles (26 us against 9.4 us) --
 # measured with profiles/gemm_tf32_time.py, numbers in profiles/README.md.
 GEMM_STEP_MAX_ROWS = 64
+# The batched part of the world-model backward that reads (h_t, z_t) at one step -- prior MLP, reward / continue heads, decoder MLP,
+# KL terms: "drm" = differentiated by hand on this library's kernels (only the conv stacks stay torch autograd / cuDNN),
+# "autograd" = one torch autograd graph (the implementation the hand-written one is tested against).
+HEADS_BACKWARD = "drm"
 
 
 def _mm(a, b, out=None, accumulate=False, step=False):
@@ -103,6 +107,169 @@ def world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks
     # the batched conv graph has fixed shapes: let cuDNN pick its fastest (TF32 tensor-core) algorithms during the eager warm-up
     with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True), _matmul_precision():
         return _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts, marks, on_loss)
+
+
+def _heads_autograd(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, mark):
+    """(1b) everything that reads (h_t, z_t) at one step as ONE batched torch autograd graph on leaves (HEADS_BACKWARD = "autograd":
+    the implementation _heads_manual is tested against).  Returns (ok, total, loss, gH, gZ, gLG), time-major gradients."""
+    B, T = obs.shape[:2]
+    R, C = wm.latent_num_rows, wm.latent_num_columns
+    Z = R * C
+    dev = obs.device
+    # ---- (1b) everything that reads (h_t, z_t) at one step: batched autograd on leaves --------------------------------------
+    Hl = Hk.clone().requires_grad_(True)                                        # (B,T,D)
+    Zl = z_oh.clone().requires_grad_(True)                                      # (B,T,Z)
+    LGl = LG.transpose(0, 1).reshape(B, T, R, C).clone().requires_grad_(True)   # posterior logits as a leaf (KL terms)
+    prior = wm.dynamics_predictor.logit_net(Hl).view(B, T, R, C)
+    hz = torch.cat([Hl, Zl], -1)
+    x = wm.decoder.upscaler(hz.reshape(B * T, -1)).view(B * T, wm.decoder.num_filters_start, wm.decoder.start_height, wm.decoder.start_width)
+    with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
+        dec = wm.decoder.image_builder(x.contiguous(memory_format=torch.channels_last))
+    dec = dec.float().view(obs.shape)
+    rl = wm.reward_predictor.logit_net(hz[:, 1:])
+    cl = wm.continue_predictor.logit_generator(hz[:, 1:])
+    mask = cont[:, :T - 1]
+    m1 = mask.squeeze(-1)
+    obs_ll = -((dec.float() - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
+    b = wm.reward_predictor.buckets_rew
+    v = torch.maximum(torch.minimum(rew[:, :T - 1], b[-1]), b[0])
+    lo = torch.clamp(torch.searchsorted(b, v.contiguous(), right=True) - 1, max=len(b) - 2)
+    w = (v - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
+    lsm = F.log_softmax(rl, -1)
+    rew_ll = ((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)) * mask
+    cont_ll = F.binary_cross_entropy_with_logits(cl, mask, reduction='none') * mask
+
+    def cat_kl(lp_logits, lq_logits):
+        lp = F.log_softmax(lp_logits, -1)
+        lq = F.log_softmax(lq_logits, -1)
+        return (lp.exp() * (lp - lq)).sum(-1).sum(-1)
+
+    dyn_sum = (cat_kl(LGl[:, 1:].detach(), prior[:, 1:]) * m1).sum()
+    rep_sum = (cat_kl(LGl[:, 1:], prior[:, 1:].detach()) * m1).sum()
+    total = None
+    if isinstance(parts, str):
+        if parts != "reduce":
+            raise ValueError("world_model_backward: parts must be a dict, None or 'reduce'")
+        # forward values of this rank's sums -> one packed all-reduce -> global denominators and the global loss on every rank
+        local = torch.stack([obs_ll.sum(), rew_ll.sum(), cont_ll.sum(), mask.sum(), dyn_sum, torch.full((), float(m1.numel()), device=dev)]).detach()
+        total, parts = D.world_model_loss_from_sums(local, (wm.beta_pred, wm.beta_dyn, wm.beta_rep))
+    if parts is None:
+        denom, n_el = mask.sum() + 1e-5, float(m1.numel())
+        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
+        one = torch.ones((), device=dev)
+        loss = wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn_sum / n_el) + wm.beta_rep * torch.maximum(one, rep_sum / n_el)
+    else:
+        denom, n_el, kl_mean = parts["denom"], parts["n_elements"], parts["kl_mean"]
+        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
+        live = (kl_mean > 1.0).to(loss_pred.dtype)
+        const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
+        loss = wm.beta_pred * loss_pred + live * (wm.beta_dyn * (dyn_sum / n_el) + wm.beta_rep * (rep_sum / n_el)) + const
+    if total is not None and on_loss is not None and not on_loss(total):
+        return False, total
+    mark("batched heads / decoder forward")
+    loss.backward()          # parameter gradients of prior / decoder / heads; d/dh, d/dz, d/dlogits at every step
+    with torch.no_grad():
+        gH = Hl.grad.transpose(0, 1).contiguous()                               # (T,B,D)  accumulates the total d/dh_t
+        gZ = Zl.grad.transpose(0, 1).contiguous()                               # (T,B,Z)  direct d/dz_t (decoder, reward, continue)
+        gLG = LGl.grad.view(B, T, Z).transpose(0, 1).contiguous()               # (T,B,Z)  KL terms on the posterior logits
+    return True, total, loss, gH, gZ, gLG
+
+
+
+def _heads_manual(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, mark):
+    """(1b) on this library's kernels: prior MLP, reward / continue heads and the decoder's MLP are re-evaluated batched over all
+    B*T rows and differentiated by hand (drm_twohot_ce_bwd, closed-form KL / BCE gradients, drm_ln_silu_bwd, drm_gemm_tf32); only the
+    decoder's transposed-conv stack stays a torch autograd graph (cuDNN), closed from its input.  Same contract as _heads_autograd."""
+    B, T = obs.shape[:2]
+    R, C, Dh = wm.latent_num_rows, wm.latent_num_columns, wm.hidden_dims
+    Z = R * C
+    dev = obs.device
+    dec_mod = wm.decoder
+    u1, un, _, u2, _ = dec_mod.upscaler
+    mask = cont[:, :T - 1]
+    m1 = mask.squeeze(-1)
+    with torch.no_grad():
+        hz = torch.cat([Hk, z_oh], -1)                                                  # (B,T,D+Z)
+        rows_all = hz.view(B * T, Dh + Z)
+        rows_1 = hz[:, 1:].reshape(B * (T - 1), Dh + Z)
+        pr = _mlp3_forward(wm.dynamics_predictor.logit_net, Hk.reshape(B * T, Dh))
+        rw = _mlp3_forward(wm.reward_predictor.logit_net, rows_1)
+        cn = _mlp3_forward(wm.continue_predictor.logit_generator, rows_1)
+        ua1 = _linear(rows_all, u1.weight, u1.bias)
+        uy1 = F.silu(F.layer_norm(ua1, (ua1.shape[-1],), un.weight, un.bias, un.eps))
+        ua2 = _linear(uy1, u2.weight, u2.bias)
+    # the transposed-conv stack: autograd (cuDNN) from its pre-SiLU input
+    a2l = ua2.requires_grad_(True)
+    x = F.silu(a2l).view(B * T, dec_mod.num_filters_start, dec_mod.start_height, dec_mod.start_width)
+    with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
+        dec = dec_mod.image_builder(x.contiguous(memory_format=torch.channels_last))
+    dec = dec.float().view(obs.shape)
+    obs_ll = -((dec - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
+    with torch.no_grad():
+        b = wm.reward_predictor.buckets_rew
+        rew_rows = rew[:, :T - 1].reshape(-1, 1)
+        mask_rows = mask.reshape(-1, 1)
+        rew_ll = ops.twohot_ce(rw["logits"], rew_rows, b) * mask_rows
+        cl = cn["logits"]
+        cont_ll = F.binary_cross_entropy_with_logits(cl, mask_rows, reduction='none') * mask_rows
+        lp = F.log_softmax(LG.transpose(0, 1).reshape(B, T, R, C), -1)                  # posterior (the scan's logits), batch-major
+        lq = F.log_softmax(pr["logits"].view(B, T, R, C), -1)
+        p_post = lp.exp()
+        diff = lp - lq
+        kl_row = (p_post * diff).sum(-1, keepdim=True)                                  # (B,T,R,1)
+        kl = kl_row.sum(dim=[-2, -1])                                                   # (B,T)
+        kl_sum = (kl[:, 1:] * m1).sum()
+        total = None
+        if isinstance(parts, str):
+            if parts != "reduce":
+                raise ValueError("world_model_backward: parts must be a dict, None or 'reduce'")
+            local = torch.stack([obs_ll.detach().sum(), rew_ll.sum(), cont_ll.sum(), mask.sum(), kl_sum, torch.full((), float(m1.numel()), device=dev)])
+            total, parts = D.world_model_loss_from_sums(local, (wm.beta_pred, wm.beta_dyn, wm.beta_rep))
+        one = torch.ones((), device=dev)
+        if parts is None:
+            denom, n_el = mask.sum() + 1e-5, float(m1.numel())
+            kl_mean = kl_sum / n_el
+            loss_pred = (-obs_ll.detach().sum() - rew_ll.sum() + cont_ll.sum()) / denom
+            loss = wm.beta_pred * loss_pred + (wm.beta_dyn + wm.beta_rep) * torch.maximum(one, kl_mean)
+            live = (kl_mean > 1.0).to(torch.float32)
+        else:
+            denom, n_el, kl_mean = parts["denom"], parts["n_elements"], parts["kl_mean"]
+            loss_pred = (-obs_ll.detach().sum() - rew_ll.sum() + cont_ll.sum()) / denom
+            live = (kl_mean > 1.0).to(torch.float32)
+            const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
+            loss = wm.beta_pred * loss_pred + live * ((wm.beta_dyn + wm.beta_rep) * (kl_sum / n_el)) + const
+        c_pred = (wm.beta_pred / denom).to(torch.float32).reshape(())
+        c_dyn = (live * (wm.beta_dyn / n_el)).to(torch.float32)
+        c_rep = (live * (wm.beta_rep / n_el)).to(torch.float32)
+    if total is not None and on_loss is not None and not on_loss(total):
+        return False, total
+    mark("batched heads / decoder forward")
+    (c_pred * (-obs_ll.sum())).backward()                                               # conv stack parameters + d/d(its input)
+    with torch.no_grad():
+        # decoder MLP: Linear-LN-SiLU-Linear(-SiLU, differentiated above)
+        da2 = a2l.grad
+        _acc_mm(u2.weight, da2, uy1)
+        _acc(u2.bias, da2.sum(0))
+        da1, dln = ops.ln_silu_bwd(_mm(da2, u2.weight), ua1, un.weight, un.bias, un.eps, want_dln=True)
+        _acc(un.weight, (dln * F.layer_norm(ua1, (ua1.shape[-1],), None, None, un.eps)).sum(0))
+        _acc(un.bias, dln.sum(0))
+        _acc_mm(u1.weight, da1, rows_all)
+        _acc(u1.bias, da1.sum(0))
+        gHZ = _mm(da1, u1.weight).view(B, T, Dh + Z)
+        # reward head: - c_pred * sum(mask * twohot_ll);   continue head: + c_pred * sum(mask * BCE(cl, mask))
+        d_rw = ops.twohot_ce_bwd(rw["logits"], rew_rows, b, coef=mask_rows, scale_dev=c_pred, scale=-1.0)
+        d_cn = (c_pred * mask_rows) * (torch.sigmoid(cl) - mask_rows)
+        gHZ[:, 1:] += (_mlp3_backward(rw, d_rw, want_dx=True) + _mlp3_backward(cn, d_cn, want_dx=True)).view(B, T - 1, Dh + Z)
+        # KL terms (WorldModel.py:175-181): dyn = KL(sg(post) || prior) -> prior logits; rep = KL(post || sg(prior)) -> posterior logits
+        mk = torch.zeros(B, T, 1, 1, device=dev)
+        mk[:, 1:, 0, 0] = m1
+        d_prior = (c_dyn * mk) * (lq.exp() - p_post)
+        d_post = (c_rep * mk) * (p_post * (diff - kl_row))
+        gH = gHZ[..., :Dh] + _mlp3_backward(pr, d_prior.reshape(B * T, Z), want_dx=True).view(B, T, Dh)
+        gH = gH.transpose(0, 1).contiguous()
+        gZ = gHZ[..., Dh:].transpose(0, 1).contiguous()
+        gLG = d_post.reshape(B, T, Z).transpose(0, 1).contiguous()
+    return True, total, loss, gH, gZ, gLG
 
 
 def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, marks=None, on_loss=None):
@@ -158,64 +325,19 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         LG = _linear(Y1, lin2.weight, lin2.bias).view(T, B, Z)                   # posterior logits, time-major
 
     mark("recurrent pre-activations + posterior MLP forward (batched)")
-    # ---- (1b) everything that reads (h_t, z_t) at one step: batched autograd on leaves --------------------------------------
-    Hl = Hk.clone().requires_grad_(True)                                        # (B,T,D)
-    Zl = z_oh.clone().requires_grad_(True)                                      # (B,T,Z)
-    LGl = LG.transpose(0, 1).reshape(B, T, R, C).clone().requires_grad_(True)   # posterior logits as a leaf (KL terms)
-    prior = wm.dynamics_predictor.logit_net(Hl).view(B, T, R, C)
-    hz = torch.cat([Hl, Zl], -1)
-    x = wm.decoder.upscaler(hz.reshape(B * T, -1)).view(B * T, wm.decoder.num_filters_start, wm.decoder.start_height, wm.decoder.start_width)
-    with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
-        dec = wm.decoder.image_builder(x.contiguous(memory_format=torch.channels_last))
-    dec = dec.float().view(obs.shape)
-    rl = wm.reward_predictor.logit_net(hz[:, 1:])
-    cl = wm.continue_predictor.logit_generator(hz[:, 1:])
-    mask = cont[:, :T - 1]
-    m1 = mask.squeeze(-1)
-    obs_ll = -((dec.float() - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
-    b = wm.reward_predictor.buckets_rew
-    v = torch.maximum(torch.minimum(rew[:, :T - 1], b[-1]), b[0])
-    lo = torch.clamp(torch.searchsorted(b, v.contiguous(), right=True) - 1, max=len(b) - 2)
-    w = (v - b[lo]) / (b[lo + 1] - b[lo] + 1e-8)
-    lsm = F.log_softmax(rl, -1)
-    rew_ll = ((1 - w) * lsm.gather(-1, lo) + w * lsm.gather(-1, lo + 1)) * mask
-    cont_ll = F.binary_cross_entropy_with_logits(cl, mask, reduction='none') * mask
-
-    def cat_kl(lp_logits, lq_logits):
-        lp = F.log_softmax(lp_logits, -1)
-        lq = F.log_softmax(lq_logits, -1)
-        return (lp.exp() * (lp - lq)).sum(-1).sum(-1)
-
-    dyn_sum = (cat_kl(LGl[:, 1:].detach(), prior[:, 1:]) * m1).sum()
-    rep_sum = (cat_kl(LGl[:, 1:], prior[:, 1:].detach()) * m1).sum()
-    total = None
-    if isinstance(parts, str):
-        if parts != "reduce":
-            raise ValueError("world_model_backward: parts must be a dict, None or 'reduce'")
-        # forward values of this rank's sums -> one packed all-reduce -> global denominators and the global loss on every rank
-        local = torch.stack([obs_ll.sum(), rew_ll.sum(), cont_ll.sum(), mask.sum(), dyn_sum, torch.full((), float(m1.numel()), device=dev)]).detach()
-        total, parts = D.world_model_loss_from_sums(local, (wm.beta_pred, wm.beta_dyn, wm.beta_rep))
-    if parts is None:
-        denom, n_el = mask.sum() + 1e-5, float(m1.numel())
-        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
-        one = torch.ones((), device=dev)
-        loss = wm.beta_pred * loss_pred + wm.beta_dyn * torch.maximum(one, dyn_sum / n_el) + wm.beta_rep * torch.maximum(one, rep_sum / n_el)
+    if HEADS_BACKWARD == "drm":
+        res = _heads_manual(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, mark)
+        if res[0] is False:
+            return res[1], False
+        total, loss, gH, gZ, gLG = res[1:]
     else:
-        denom, n_el, kl_mean = parts["denom"], parts["n_elements"], parts["kl_mean"]
-        loss_pred = (-obs_ll.sum() - rew_ll.sum() + cont_ll.sum()) / denom
-        live = (kl_mean > 1.0).to(loss_pred.dtype)
-        const = (1.0 - live) * ((wm.beta_dyn + wm.beta_rep) / D.world())
-        loss = wm.beta_pred * loss_pred + live * (wm.beta_dyn * (dyn_sum / n_el) + wm.beta_rep * (rep_sum / n_el)) + const
-    if total is not None and on_loss is not None and not on_loss(total):
-        return total, False
-    mark("batched heads / decoder forward")
-    loss.backward()          # parameter gradients of prior / decoder / heads; d/dh, d/dz, d/dlogits at every step
+        res = _heads_autograd(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, mark)
+        if res[0] is False:
+            return res[1], False
+        total, loss, gH, gZ, gLG = res[1:]
 
     mark("batched heads / decoder backward")
     with torch.no_grad():
-        gH = Hl.grad.transpose(0, 1).contiguous()                               # (T,B,D)  accumulates the total d/dh_t
-        gZ = Zl.grad.transpose(0, 1).contiguous()                               # (T,B,Z)  direct d/dz_t (decoder, reward, continue)
-        gLG = LGl.grad.view(B, T, Z).transpose(0, 1).contiguous()               # (T,B,Z)  KL terms on the posterior logits
         # ---- (2) the recurrence, backwards: 7 launches per step ---------------------------------------------------------
         dLG = torch.empty(T, B, Z, device=dev)
         dGI = torch.empty(T, B, 3 * Dh, device=dev)
@@ -388,27 +510,31 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         _acc(l1.bias, dA1_all.sum(0))
 
 
-def _mlp3_backward(net, x, d_out_fn):
-    """Parameter gradients (accumulated into ``.grad``) of a Linear-LN-SiLU-Linear-LN-SiLU-Linear stack (modules._mlp) on the batched
-    rows x [rows, in]: fp32 re-evaluation of the pre-activations on this library's GEMM, d_out_fn(logits) -> d(loss)/d(logits), then
-    the chain rule layer by layer (drm_ln_silu_bwd, drm_gemm_tf32).  Returns d(loss)/dx when the caller wants it (else None is fine)."""
+def _mlp3_forward(net, x):
+    """Linear-LN-SiLU-Linear-LN-SiLU-Linear (modules._mlp) on the batched rows x [rows, in], fp32 re-evaluation on this library's
+    GEMM; keeps what the backward needs (pre-LayerNorm activations, layer inputs)."""
     l1, n1, _, l2, n2, _, l3 = net
     a1, y1, a2, y2 = _mlp_fwd(x, l1, n1, l2, n2)
-    logits = _linear(y2, l3.weight, l3.bias)
-    d3 = d_out_fn(logits)
-    _acc_mm(l3.weight, d3, y2)
+    return dict(net=net, x=x, a1=a1, y1=y1, a2=a2, y2=y2, logits=_linear(y2, l3.weight, l3.bias))
+
+
+def _mlp3_backward(c, d3, want_dx=False):
+    """Parameter gradients (accumulated into ``.grad``) of the stack from d3 = d(loss)/d(logits) by the chain rule, layer by layer
+    (drm_ln_silu_bwd, drm_gemm_tf32); returns d(loss)/dx when asked."""
+    l1, n1, _, l2, n2, _, l3 = c["net"]
+    _acc_mm(l3.weight, d3, c["y2"])
     _acc(l3.bias, d3.sum(0))
-    da2, dln2 = ops.ln_silu_bwd(_mm(d3, l3.weight), a2, n2.weight, n2.bias, n2.eps, want_dln=True)
-    _acc(n2.weight, (dln2 * F.layer_norm(a2, (a2.shape[-1],), None, None, n2.eps)).sum(0))
+    da2, dln2 = ops.ln_silu_bwd(_mm(d3, l3.weight), c["a2"], n2.weight, n2.bias, n2.eps, want_dln=True)
+    _acc(n2.weight, (dln2 * F.layer_norm(c["a2"], (da2.shape[-1],), None, None, n2.eps)).sum(0))
     _acc(n2.bias, dln2.sum(0))
-    _acc_mm(l2.weight, da2, y1)
+    _acc_mm(l2.weight, da2, c["y1"])
     _acc(l2.bias, da2.sum(0))
-    da1, dln1 = ops.ln_silu_bwd(_mm(da2, l2.weight), a1, n1.weight, n1.bias, n1.eps, want_dln=True)
-    _acc(n1.weight, (dln1 * F.layer_norm(a1, (a1.shape[-1],), None, None, n1.eps)).sum(0))
+    da1, dln1 = ops.ln_silu_bwd(_mm(da2, l2.weight), c["a1"], n1.weight, n1.bias, n1.eps, want_dln=True)
+    _acc(n1.weight, (dln1 * F.layer_norm(c["a1"], (da1.shape[-1],), None, None, n1.eps)).sum(0))
     _acc(n1.bias, dln1.sum(0))
-    _acc_mm(l1.weight, da1, x)
+    _acc_mm(l1.weight, da1, c["x"])
     _acc(l1.bias, da1.sum(0))
-    return da1
+    return _mm(da1, l1.weight) if want_dx else None
 
 
 def critic_backward(agent, z, h, returns, n_global):
@@ -420,6 +546,6 @@ def critic_backward(agent, z, h, returns, n_global):
         B, H1 = h.shape[:2]
         x = torch.cat([h.detach()[:, :-1], z.detach().reshape(B, H1, -1)[:, :-1]], -1).reshape(B * (H1 - 1), -1)
         inv_n = 1.0 / n_global
-        _mlp3_backward(agent.critic.value_net, x,
-                       lambda lg: ops.twohot_ce_bwd(lg, returns.reshape(-1, 1), agent.critic.buckets_crit, scale_dev=inv_n, scale=-1.0,
-                                                    apply_symlog=True))
+        c = _mlp3_forward(agent.critic.value_net, x)
+        _mlp3_backward(c, ops.twohot_ce_bwd(c["logits"], returns.reshape(-1, 1), agent.critic.buckets_crit, scale_dev=inv_n, scale=-1.0,
+                                            apply_symlog=True))

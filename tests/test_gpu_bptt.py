@@ -92,6 +92,19 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
         scale = float(g_ref[k].abs().max()) + 1e-8
         err = float((g_ref[k] - g_new[k]).abs().max()) / scale
         assert err < 2e-3, (k, err, scale)
+    # the same with the batched heads / decoder-MLP / KL part as one torch autograd graph (the switch HEADS_BACKWARD = "autograd")
+    assert bptt.HEADS_BACKWARD == "drm"
+    bptt.HEADS_BACKWARD = "autograd"
+    try:
+        wm.optimiser.zero_grad()
+        val_a = bptt.world_model_backward(wm, parts["obs_norm"], act, rew, cont, idx, hidden_fp32, parts)
+    finally:
+        bptt.HEADS_BACKWARD = "drm"
+    g_a = _grads(wm)
+    assert torch.allclose(val_a, val, rtol=1e-5, atol=1e-5)
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max()) + 1e-8
+        assert float((g_ref[k] - g_a[k]).abs().max()) / scale < 2e-3, k
     # every contraction on this library's TF32 GEMM (drm_gemm_tf32; convs still fp32): 5e-3 of each tensor's largest gradient
     # (measured worst 2.6e-3 -- TF32 keeps 10 mantissa bits, operands rounded to nearest)
     bptt.MATMUL_TF32 = True
