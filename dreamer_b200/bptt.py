@@ -449,11 +449,10 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         sg_k = sigma.detach().transpose(0, 1).reshape(H * B, A)
         a_flat = Atm.view(H * B, A)
         EPS = ((torch.atanh(torch.clamp(a_flat, -1.0 + 1e-6, 1.0 - 1e-6)) - mu_k) / sg_k).view(H, B, A)   # the draw behind a_t
-    # direct d/d(mu, sigma) of the objective (closed-form expression differentiated by autograd on two leaves, batched)
-    mu_l, sg_l = mu_k.clone().requires_grad_(True), sg_k.clone().requires_grad_(True)
-    (coef.detach().transpose(0, 1).reshape(-1) * _tanh_normal_log_prob(a_flat, mu_l, sg_l)).sum().backward()
     with torch.no_grad():
-        gMU, gSG = mu_l.grad.view(H, B, A), sg_l.grad.view(H, B, A)
+        # direct d/d(mu, sigma) of the objective: closed form, one kernel (drm_tanh_normal_logp)
+        gMU, gSG = ops.tanh_normal_logp(a_flat, mu_k, sg_k, coef=coef.detach().transpose(0, 1).reshape(-1), want_logp=False, want_grad=True)
+        gMU, gSG = gMU.view(H, B, A), gSG.view(H, B, A)
         # world-model pre-activations of the transitions s -> s+1, s = 0..H-1 (needed for s <= H-2)
         X = torch.cat([Ztm[:H], Atm], -1).view(H * B, Z + A)
         GI = _linear(X, gru.weight_ih, gru.bias_ih).view(H, B, 3 * Dh)

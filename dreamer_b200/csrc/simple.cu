@@ -341,6 +341,35 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const float* __rest
   }
 }
 
+// log pi(a | mu, sigma) of a tanh-squashed Normal, summed over the action dimension (Agent.py:110-115), and its gradient.
+//   y = atanh(clamp(a, -1 + 1e-6, 1 - 1e-6));  logp = sum_j [ -(y - mu)^2 / (2 sigma^2) - log sigma - log sqrt(2 pi) - 2 (log 2 - y - softplus(-2 y)) ]
+//   g_mu = coef[row] * (y - mu) / sigma^2;   g_sigma = coef[row] * ((y - mu)^2 / sigma^3 - 1 / sigma)        (a is a constant)
+// One thread per row (A <= 32 actions); logp / g_mu / g_sigma may each be NULL.
+__global__ void __launch_bounds__(256) tanh_normal_logp_kernel(const float* __restrict__ a, const float* __restrict__ mu,
+                                                               const float* __restrict__ sigma, const float* __restrict__ coef,
+                                                               float* __restrict__ logp, float* __restrict__ g_mu, float* __restrict__ g_sg,
+                                                               int64_t rows, int A) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float cf = coef ? coef[r] : 1.0f;
+    float acc = 0.f;
+    for (int j = 0; j < A; ++j) {
+      const int64_t i = r * A + j;
+      const float av = fminf(fmaxf(a[i], -1.0f + 1e-6f), 1.0f - 1e-6f);
+      const float y = atanhf(av);
+      const float m = mu[i], sg = sigma[i];
+      const float d = y - m, inv = 1.0f / sg;
+      if (logp) {
+        const float t = -2.0f * y;
+        const float sp = t > 20.0f ? t : log1pf(expf(t));
+        acc += -0.5f * d * d * inv * inv - logf(sg) - 0.9189385332046727f - 2.0f * (0.6931471805599453f - y - sp);
+      }
+      if (g_mu) g_mu[i] = cf * d * inv * inv;
+      if (g_sg) g_sg[i] = cf * (d * d * inv * inv * inv - inv);
+    }
+    if (logp) logp[r] = acc;
+  }
+}
+
 // KL(Cat(post) || Cat(prior)) summed over the rows of a group (one warp per group).
 // WorldModel.py:175-181.
 __global__ void __launch_bounds__(256) categorical32_kl_kernel(const float* __restrict__ post,
@@ -684,6 +713,18 @@ extern "C" int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const
   DRM_REQUIRE(g_mu && g_sigma && log_sigma && d_head && (!da || (a && eps)), DRM_ERR_ARG, "drm_actor_head_bwd: NULL pointer");
   const int64_t want = (rows * A + 255) / 256;
   actor_head_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(g_mu, g_sigma, da, a, eps, log_sigma, d_head, rows, A);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_tanh_normal_logp(const float* a, const float* mu, const float* sigma, const float* coef, float* logp, float* g_mu,
+                                    float* g_sigma, int64_t rows, int32_t A, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 0 && A >= 1 && A <= 32, DRM_ERR_SHAPE, "drm_tanh_normal_logp: A must be in [1, 32]");
+  if (rows == 0) return DRM_OK;
+  DRM_REQUIRE(a && mu && sigma && (logp || g_mu || g_sigma), DRM_ERR_ARG, "drm_tanh_normal_logp: NULL pointer");
+  const int64_t want = (rows + 255) / 256;
+  tanh_normal_logp_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(a, mu, sigma, coef, logp, g_mu, g_sigma, rows, A);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

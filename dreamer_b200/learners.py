@@ -341,7 +341,7 @@ class Agent(nn.Module):
         v = hd["value"].view(B, H1, 1)
         R = ops.lambda_return(rew, cont, v_t, self.gamma, self.lambda_)
         adv = (R - v[:, :-1]).squeeze(-1)
-        logp = _tanh_normal_log_prob(act, mu, sigma)
+        logp = ops.tanh_normal_logp(act, mu, sigma) if act.is_cuda else _tanh_normal_log_prob(act, mu, sigma)
         self.update_S(R)
         norm = torch.maximum(self.S, torch.ones((), device=R.device))
         ce = -ops.twohot_ce(hd["value_logits"].view(B, H1, -1)[:, :-1], R, self.critic.buckets_crit, apply_symlog=True)

@@ -187,6 +187,25 @@ def twohot_ce(logits, value, buckets, apply_symlog: bool = False):
     return out
 
 
+def tanh_normal_logp(a, mu, sigma, coef=None, want_logp: bool = True, want_grad: bool = False):
+    """Agent.py:110-115: a, mu, sigma (..., A) -> logp (...) and / or (g_mu, g_sigma) (..., A) = coef (...) * d logp / d(mu, sigma)."""
+    L.require_cuda(a, "a")
+    av, m, sg = L.f32c(a), L.f32c(mu), L.f32c(sigma)
+    A = av.shape[-1]
+    rows = av.numel() // A
+    cf = L.f32c(coef) if coef is not None else None
+    if m.shape != av.shape or sg.shape != av.shape or (cf is not None and cf.numel() != rows):
+        raise RuntimeError("dreamer_b200.tanh_normal_logp: shape mismatch")
+    logp = torch.empty(av.shape[:-1], dtype=torch.float32, device=av.device) if want_logp else None
+    gm = torch.empty_like(av) if want_grad else None
+    gs = torch.empty_like(av) if want_grad else None
+    L.check(L.load().drm_tanh_normal_logp(L.ptr(av), L.ptr(m), L.ptr(sg), L.ptr(cf), L.ptr(logp), L.ptr(gm), L.ptr(gs), rows, A, L.stream()),
+            "tanh_normal_logp")
+    if want_logp and want_grad:
+        return logp, gm, gs
+    return logp if want_logp else (gm, gs)
+
+
 def twohot_ce_bwd(logits, value, buckets, coef=None, scale_dev=None, scale: float = 1.0, apply_symlog: bool = False):
     """d/dlogits of sum(coef * twohot_ce(logits, value)) * scale * scale_dev: logits (..., NB), value (..., 1), coef (..., 1) or None,
     scale_dev a 0-d device tensor or None -> (..., NB)."""

@@ -120,6 +120,11 @@ int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const f
 /* step: d_head [rows, 2A] = [g_mu + du | (g_sigma + du eps) sigmoid(ls) 1(-5 < ls < 2)], du = da (1 - a^2); da may be NULL (= 0).   */
 int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const float* da, const float* a, const float* eps,
                        const float* log_sigma, float* d_head, int64_t rows, int32_t A, void* stream);
+/* log-probability of the taken action under tanh(Normal(mu, sigma)) summed over the action dimension (Agent.py:110-115) and its   */
+/* gradient with respect to mu, sigma (the action is a constant there):  a, mu, sigma [rows, A] -> logp [rows] and / or                */
+/* g_mu, g_sigma [rows, A] = coef[row] * d logp / d(mu, sigma)  (coef may be NULL = 1; each output may be NULL).                      */
+int drm_tanh_normal_logp(const float* a, const float* mu, const float* sigma, const float* coef, float* logp, float* g_mu,
+                         float* g_sigma, int64_t rows, int32_t A, void* stream);
 int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
                 float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
 /* ... with dh = dh + dh_add (dh_add may be NULL): lets the recurrent term dgh W_hh arrive from a GEMM on a side stream */

@@ -22,19 +22,21 @@ def t(fn, reps=10, warm=4):
 
 cfg = dict(W.REF_CONFIG, horizon=64, sequence_length=64, batch_size=16)
 obs, act, rew, cont, uu = (x.to(dev) for x in W.sequence_inputs(cfg, 16, 64, seed=4321))
-for batched, step in (("torch", "torch"), ("drm", "torch"), ("drm", "drm"), ("torch", "torch"), ("drm", "drm")):
-    bptt.GEMM_BATCHED, bptt.GEMM_STEP = batched, step
+for batched, step, heads in (("torch", "torch", "autograd"), ("drm", "torch", "autograd"), ("drm", "drm", "autograd"), ("drm", "drm", "drm"),
+                             ("torch", "torch", "autograd"), ("drm", "drm", "drm")):
+    bptt.GEMM_BATCHED, bptt.GEMM_STEP, bptt.HEADS_BACKWARD = batched, step, heads
     wm, _ = W.build_learners(cfg, W.make_state_dict(cfg, seed=0), dev)
     wm.enable_cuda_graphs(1)
     g = t(lambda: wm.training_step(obs, act, rew, cont, uniforms=uu))
-    print(f"world-model step 16 x 64: batched GEMMs {batched:5s} step GEMMs {step:5s}: {g:7.3f} ms ({1e3 / g:6.1f} steps/s)", flush=True)
+    print(f"world-model step 16 x 64: batched GEMMs {batched:5s} step GEMMs {step:5s} heads backward {heads:8s}: {g:7.3f} ms ({1e3 / g:6.1f} steps/s)", flush=True)
     del wm
 
 # one training iteration at car_racer_config.yaml (batch 50 x seq 50, horizon 30): world-model step and agent step as graphs
 import numpy as np
 from dreamer_b200.hotpath import HotPath
-for batched, step in (("torch", "torch"), ("drm", "torch"), ("drm", "drm")):
-    bptt.GEMM_BATCHED, bptt.GEMM_STEP = batched, step
+for batched, step, heads in (("torch", "torch", "autograd"), ("drm", "drm", "autograd"), ("drm", "drm", "drm")):
+    bptt.GEMM_BATCHED, bptt.GEMM_STEP, bptt.HEADS_BACKWARD = batched, step, heads
+    hp_mode = "bptt"
     cfg = dict(W.REF_CONFIG, buffer_size=8192)
     hp = HotPath(cfg, dev)
     rng = np.random.default_rng(1)
@@ -50,5 +52,5 @@ for batched, step in (("torch", "torch"), ("drm", "torch"), ("drm", "drm")):
     z, h, a, r, c, mu, sg = hp.dream_episodes(z0, h0)
     t_wm = t(lambda: hp.world_model.training_step(obs, act, rew, cont))
     t_ag = t(lambda: hp.agent.train_step(z, h, r, c, a, mu, sg))
-    print(f"car_racer_config (50 x 50, horizon 30): batched {batched:5s} step {step:5s}: world-model step {t_wm:7.3f} ms, agent step {t_ag:7.3f} ms", flush=True)
+    print(f"car_racer_config (50 x 50, horizon 30): batched {batched:5s} step {step:5s} heads {heads:8s}: world-model step {t_wm:7.3f} ms, agent step {t_ag:7.3f} ms", flush=True)
     del hp

@@ -256,3 +256,20 @@ def test_critic_backward_matches_autograd():
             num += float(((g_ref[k] - p.grad) ** 2).sum())
         assert (num / den) ** 0.5 < bound
     bptt.MATMUL_TF32 = True
+
+
+def test_tanh_normal_logp_matches_torch():
+    from dreamer_b200 import ops, learners
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.tanh(torch.randn(64, 15, 3, device=DEV, generator=g) * 2)
+    a[0, 0] = torch.tensor([1.0, -1.0, 0.0], device=DEV)                      # clamped ends
+    mu = torch.randn(64, 15, 3, device=DEV, generator=g)
+    sg = torch.rand(64, 15, 3, device=DEV, generator=g) * 2 + 1e-2
+    coef = torch.randn(64, 15, device=DEV, generator=g)
+    mu_l, sg_l = mu.clone().requires_grad_(True), sg.clone().requires_grad_(True)
+    ref = learners._tanh_normal_log_prob(a, mu_l, sg_l)
+    (coef * ref).sum().backward()
+    logp, gm, gs = ops.tanh_normal_logp(a, mu, sg, coef=coef, want_grad=True)
+    assert torch.allclose(logp, ref.detach(), rtol=1e-4, atol=1e-3)          # atanh near +-1: ~7.25 with fp32 ulps of the clamp
+    assert torch.allclose(gm, mu_l.grad, rtol=1e-4, atol=1e-4 * float(mu_l.grad.abs().max()))
+    assert torch.allclose(gs, sg_l.grad, rtol=1e-4, atol=1e-4 * float(sg_l.grad.abs().max()))
