@@ -370,6 +370,71 @@ __global__ void __launch_bounds__(256) tanh_normal_logp_kernel(const float* __re
   }
 }
 
+// Percentiles of Agent.update_S (Agent.py:78-88: torch.quantile's definition, sorted[lo] + (sorted[hi] - sorted[lo]) * frac) without a
+// sort: the four order statistics (ranks r[0..3]) are found by an MSB-first radix select on the order-preserving integer image of the
+// floats, 8 bits per pass, all four selections sharing each pass over the data.  One CTA (the set is 1.5 K - 123 K values and
+// L2-resident; a pass is n / 1024 loads per thread); histogram updates are aggregated per warp (__match_any_sync) because the
+// leading digits of a return set fall into a handful of bins.  out[0] = v[r0] + (v[r1] - v[r0]) * f_lo, out[1] = v[r2] + (v[r3] -
+// v[r2]) * f_hi, out[2] = 1 if every value is finite else 0 (the reference then leaves S unchanged, Agent.py:80-81).
+__device__ __forceinline__ unsigned f32_sortable(float x) {
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unsortable(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(1024) quantile4_kernel(const float* __restrict__ x, int64_t n, long long r0, long long r1, long long r2,
+                                                         long long r3, float f_lo, float f_hi, float* __restrict__ out) {
+  __shared__ unsigned hist[4][256];
+  __shared__ unsigned prefix[4];
+  __shared__ long long rank[4];
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  if (tid < 4) { prefix[tid] = 0u; rank[tid] = tid == 0 ? r0 : (tid == 1 ? r1 : (tid == 2 ? r2 : r3)); }
+  if (tid == 0) bad = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 4 * 256; i += blockDim.x) (&hist[0][0])[i] = 0u;
+    __syncthreads();
+    const unsigned p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
+    for (int64_t base = 0; base < n; base += blockDim.x) {       // whole warps iterate together (match_any needs the full mask)
+      const int64_t i = base + tid;
+      const bool valid = i < n;
+      const float xv = valid ? x[i] : 0.f;
+      if (pass == 0 && valid && !isfinite(xv)) bad = 1;
+      const unsigned key = f32_sortable(xv);
+      const unsigned digit = (key >> shift) & 255u;
+      const unsigned hi = pass == 0 ? 0u : (key >> (shift + 8));
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned pt = t == 0 ? p0 : (t == 1 ? p1 : (t == 2 ? p2 : p3));
+        const bool in = valid && hi == pt;
+        const unsigned group = __match_any_sync(0xffffffffu, in ? digit : 0xffffffffu);     // lanes with the same digit (or all idle lanes)
+        if (in && (int)(__ffs(group) - 1) == (tid & 31)) atomicAdd(&hist[t][digit], (unsigned)__popc(group));
+      }
+    }
+    __syncthreads();
+    if (tid < 4) {
+      long long cum = 0, rk = rank[tid];
+      unsigned pick = 255u;
+      for (int b = 0; b < 256; ++b) {
+        const unsigned c = hist[tid][b];
+        if (rk < cum + (long long)c) { pick = (unsigned)b; break; }
+        cum += c;
+      }
+      prefix[tid] = (prefix[tid] << 8) | pick;
+      rank[tid] = rk - cum;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float v0 = f32_unsortable(prefix[0]), v1 = f32_unsortable(prefix[1]), v2 = f32_unsortable(prefix[2]), v3 = f32_unsortable(prefix[3]);
+    out[0] = __fadd_rn(v0, __fmul_rn(v1 - v0, f_lo));      // (no fused multiply-add: the same roundings as the reference's torch expression)
+    out[1] = __fadd_rn(v2, __fmul_rn(v3 - v2, f_hi));
+    out[2] = bad ? 0.f : 1.f;
+  }
+}
+
 // KL(Cat(post) || Cat(prior)) summed over the rows of a group (one warp per group).
 // WorldModel.py:175-181.
 __global__ void __launch_bounds__(256) categorical32_kl_kernel(const float* __restrict__ post,
@@ -725,6 +790,26 @@ extern "C" int drm_tanh_normal_logp(const float* a, const float* mu, const float
   DRM_REQUIRE(a && mu && sigma && (logp || g_mu || g_sigma), DRM_ERR_ARG, "drm_tanh_normal_logp: NULL pointer");
   const int64_t want = (rows + 255) / 256;
   tanh_normal_logp_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(a, mu, sigma, coef, logp, g_mu, g_sigma, rows, A);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
+
+extern "C" int drm_percentile_pair(const float* x, int64_t n, double p_lo, double p_hi, float* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(n >= 1 && p_lo >= 0.0 && p_lo <= 1.0 && p_hi >= 0.0 && p_hi <= 1.0, DRM_ERR_SHAPE, "drm_percentile_pair: n >= 1 and percentiles in [0, 1] required");
+  DRM_REQUIRE(x && out, DRM_ERR_ARG, "drm_percentile_pair: NULL pointer");
+  // torch.quantile's "linear" rule, as Agent.update_S spells it: pos = p (n - 1), lo = floor(pos), hi = min(lo + 1, n - 1)
+  auto split = [n](double p, long long& lo, long long& hi, float& f) {
+    const double pos = p * (double)(n - 1);
+    lo = (long long)pos;
+    hi = lo + 1 < n ? lo + 1 : n - 1;
+    f = (float)(pos - (double)lo);
+  };
+  long long r0, r1, r2, r3;
+  float f_lo, f_hi;
+  split(p_lo, r0, r1, f_lo);
+  split(p_hi, r2, r3, f_hi);
+  quantile4_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, r0, r1, r2, r3, f_lo, f_hi, out);
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -305,17 +305,22 @@ class Agent(nn.Module):
         """Agent.py:78-88 (percentiles by sort + linear interpolation, the definition torch.quantile uses).  S lives on the
         device and is updated in place; a non-finite return set leaves it unchanged (Agent.py:80-81) -- decided on the device."""
         flat = D.all_gather_cat(lambda_returns.detach().flatten())     # percentiles over the GLOBAL return set
-        ok = torch.isfinite(flat).all()
-        s, _ = torch.sort(flat)
-        n = s.numel()
+        if flat.is_cuda:
+            q = ops.percentile_pair(flat, 0.05, 0.95)                  # radix select, one launch (drm_percentile_pair)
+            ok = q[2] > 0.5
+            rng = torch.maximum(q[1] - q[0], torch.ones((), device=flat.device))
+        else:
+            ok = torch.isfinite(flat).all()
+            s, _ = torch.sort(flat)
+            n = s.numel()
 
-        def q(p):
-            pos = p * (n - 1)
-            lo = int(pos)
-            hi = min(lo + 1, n - 1)
-            return s[lo] + (s[hi] - s[lo]) * (pos - lo)
+            def q(p):
+                pos = p * (n - 1)
+                lo = int(pos)
+                hi = min(lo + 1, n - 1)
+                return s[lo] + (s[hi] - s[lo]) * (pos - lo)
 
-        rng = torch.maximum(q(0.95) - q(0.05), torch.ones((), device=flat.device))
+            rng = torch.maximum(q(0.95) - q(0.05), torch.ones((), device=flat.device))
         alpha = 1.0 - self.smoothing_factor
         if not isinstance(self.S, torch.Tensor):
             self.S = torch.full((), float(self.S), dtype=torch.float32, device=flat.device)

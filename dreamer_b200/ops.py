@@ -206,6 +206,15 @@ def tanh_normal_logp(a, mu, sigma, coef=None, want_logp: bool = True, want_grad:
     return logp if want_logp else (gm, gs)
 
 
+def percentile_pair(x: torch.Tensor, p_lo: float, p_hi: float) -> torch.Tensor:
+    """(q(p_lo), q(p_hi), all-finite flag) of the flattened x as a 3-element device tensor (torch.quantile's linear rule, Agent.py:78-88)."""
+    L.require_cuda(x, "x")
+    xv = L.f32c(x).reshape(-1)
+    out = torch.empty(3, dtype=torch.float32, device=xv.device)
+    L.check(L.load().drm_percentile_pair(L.ptr(xv), xv.numel(), float(p_lo), float(p_hi), L.ptr(out), L.stream()), "percentile_pair")
+    return out
+
+
 def twohot_ce_bwd(logits, value, buckets, coef=None, scale_dev=None, scale: float = 1.0, apply_symlog: bool = False):
     """d/dlogits of sum(coef * twohot_ce(logits, value)) * scale * scale_dev: logits (..., NB), value (..., 1), coef (..., 1) or None,
     scale_dev a 0-d device tensor or None -> (..., NB)."""

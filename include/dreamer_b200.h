@@ -125,6 +125,9 @@ int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const float* da,
 /* g_mu, g_sigma [rows, A] = coef[row] * d logp / d(mu, sigma)  (coef may be NULL = 1; each output may be NULL).                      */
 int drm_tanh_normal_logp(const float* a, const float* mu, const float* sigma, const float* coef, float* logp, float* g_mu,
                          float* g_sigma, int64_t rows, int32_t A, void* stream);
+/* The two percentiles of Agent.update_S (Agent.py:78-88; torch.quantile's linear rule) of x [n] without a sort (radix select, one     */
+/* launch): out[0] = percentile p_lo, out[1] = percentile p_hi, out[2] = 1.0 if every value is finite else 0.0 (device floats).       */
+int drm_percentile_pair(const float* x, int64_t n, double p_lo, double p_hi, float* out, void* stream);
 int drm_gru_bwd(const float* dh, const float* gi, const float* gh, const float* h_prev, float* dgi, float* dgh,
                 float* dh_prev, int32_t accumulate, int64_t rows, int32_t D, void* stream);
 /* ... with dh = dh + dh_add (dh_add may be NULL): lets the recurrent term dgh W_hh arrive from a GEMM on a side stream */

@@ -178,3 +178,33 @@ def test_straight_through_forward_and_backward_match_autograd():
         (z_ref * w).sum().backward()
         assert torch.equal(z.detach() != 0, z_ref.detach() != 0) and torch.allclose(z.detach(), z_ref.detach(), atol=1e-7)
         assert torch.allclose(g_kernel, lg.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 20, 1500, 15360, 122880])
+def test_percentile_pair_matches_sort(n):
+    """drm_percentile_pair (radix select) against the sort-and-interpolate definition Agent.update_S spells out (Agent.py:78-88):
+    bit-exact order statistics, identical interpolation arithmetic."""
+    import torch
+    from dreamer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n)
+    for kind in range(4):
+        x = torch.randn(n, device="cuda", generator=g) * (50.0 if kind == 1 else 1.0)
+        if kind == 2:
+            x = torch.round(x * 2) / 2                     # many ties, +-0
+        if kind == 3:
+            x = x.abs() * 1e-3 + 7.0                        # narrow range: the leading digits all collide
+        s, _ = torch.sort(x)
+
+        def q(p):
+            pos = p * (n - 1)
+            lo = int(pos)
+            hi = min(lo + 1, n - 1)
+            return s[lo] + (s[hi] - s[lo]) * torch.tensor(pos - lo, dtype=torch.float32, device="cuda")
+
+        out = ops.percentile_pair(x, 0.05, 0.95)
+        assert float(out[2]) == 1.0
+        assert float(out[0]) == float(q(0.05)) and float(out[1]) == float(q(0.95)), (n, kind, out.tolist(), float(q(0.05)), float(q(0.95)))
+    x[n // 2] = float("inf")
+    assert float(ops.percentile_pair(x, 0.05, 0.95)[2]) == 0.0
+    x[n // 2] = float("nan")
+    assert float(ops.percentile_pair(x, 0.05, 0.95)[2]) == 0.0
