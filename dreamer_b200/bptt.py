@@ -53,11 +53,13 @@ def _side_stream(dev):
 # GEMMs inside the two recurrence walks (16 - 1024 rows).
 GEMM_BATCHED = "drm"
 GEMM_STEP = "drm"
-# Step GEMMs with more gradient rows than this stay library GEMMs: up to 64 rows the problem runs swapped with the rows as the MMA's
-# N dimension, rounded inside the kernel, K split over a cluster (5.6 - 8.2 us against 4.6 - 7.8 us for the library GEMM, in a graph);
-# a 1024-row step GEMM needs a pack launch for the rounding and is ingress-bound at 128 x 128 tiles (26 us against 9.4 us) --
-# measured with profiles/gemm_tf32_time.py, numbers in profiles/README.md.
+# Step GEMMs with more than 64 gradient rows (the 1024-row agent step of c5) cannot round their gradient rows inside the kernel (that is
+# the swapped skinny path).  GEMM_STEP_LARGE = "torch" (default) keeps the library GEMM for them: read in place on 128 x 128 tiles this
+# library's kernel is bound by the ~110 GB/s an SM ingests from L2 (15.3 us against 10.1 us at 1024 x 600 x 1800; agent step 1024 x 15
+# 4.29 -> 5.47 ms, profiles/gemm_backend_ab.py agent).  "drm" runs them on drm_gemm_tf32 all the same (gradient operand truncated by
+# the tensor core, weights pre-rounded: < 0.1 % over a 15-step walk; the gradient tests pass either way).
 GEMM_STEP_MAX_ROWS = 64
+GEMM_STEP_LARGE = "torch"
 # The batched part of the world-model backward that reads (h_t, z_t) at one step -- prior MLP, reward / continue heads, decoder MLP,
 # KL terms: "drm" = differentiated by hand on this library's kernels (only the conv stacks stay torch autograd / cuDNN),
 # "autograd" = one torch autograd graph (the implementation the hand-written one is tested against).
@@ -68,8 +70,10 @@ def _mm(a, b, out=None, accumulate=False, step=False):
     """out (+)= a [M, K] @ b [K, N].  Operand policy of the "drm" backend: a step GEMM multiplies gradient rows (rounded to nearest
     TF32 on the way in -- the walks compound any bias over their steps) by a weight pre-rounded with _rounded() and read in place;
     a batched GEMM reads both operands in place when they are aligned (tensor-core truncation, as a library TF32 GEMM)."""
-    if (GEMM_STEP if step else GEMM_BATCHED) == "drm" and MATMUL_TF32 and not (step and a.shape[0] > GEMM_STEP_MAX_ROWS):
-        return ops.mm(a, b, out=out, accumulate=accumulate, a_direct=not step, b_direct=True)
+    if (GEMM_STEP if step else GEMM_BATCHED) == "drm" and MATMUL_TF32:
+        large = step and a.shape[0] > GEMM_STEP_MAX_ROWS
+        if not (large and GEMM_STEP_LARGE != "drm"):
+            return ops.mm(a, b, out=out, accumulate=accumulate, a_direct=large or not step, b_direct=True)
     if out is None:
         return torch.mm(a, b)
     return out.addmm_(a, b) if accumulate else torch.mm(a, b, out=out)

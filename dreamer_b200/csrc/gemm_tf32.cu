@@ -17,7 +17,7 @@
 //     drm_pack_tf32) is passed with DRM_GEMM_A_DIRECT / _B_DIRECT and read IN PLACE by TMA whichever way it lies -- K-first rows
 //     (128-byte-swizzled boxes of 32 k x rows) or K-last (MN-major: boxes of 32 rows x 32 k, SWIZZLE_128B_ATOM_32B, UMMA descriptors
 //     with the transpose bit) -- if its base is 16-byte aligned and its pitch a multiple of 4 floats (else it is packed after all).
-//   * gemm_tf32_kernel: 128 x bn output tiles (bn <= 128), a 2-stage ring of 2 k-blocks (32 fp32 = one swizzle row) per stage,
+//   * gemm_tf32_kernel: 128 x bn output tiles (bn <= 128), a ring of 3 stages (2 when swapped) of 2 k-blocks (32 fp32 = one swizzle row) each,
 //     tcgen05.mma kind::tf32 accumulating in TMEM, 16 epilogue warps.  Skinny problems (M <= 64 rows: the per-time-step GEMMs of the
 //     recurrences) run swapped -- the WEIGHT rows fill the 128 MMA rows, the few gradient rows are the N dimension -- and their
 //     few-row operand needs no pack launch: the epilogue warps, idle under the main loop, round this CTA's K slice of it and write
@@ -40,15 +40,15 @@ constexpr int TM = 128;                 // MMA rows per tile (UMMA M == TMEM lan
 constexpr int TN = 128;                 // widest N tile
 constexpr int TK = 32;                  // fp32 per k-block: one 128-byte swizzle row
 constexpr int KPS = 2;                  // k-blocks per pipeline stage
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;                // ring slots; swapped problems use two and put the converted operand into the third
 constexpr int P_BYTES = TM * TK * 4;    // 16 KB
 constexpr int Q_BYTES = TN * TK * 4;    // 16 KB
 constexpr int SUB_BYTES = P_BYTES + Q_BYTES;
 constexpr int STAGE_BYTES = KPS * SUB_BYTES;
-constexpr int BAR_OFF = STAGES * STAGE_BYTES;          // 128 KB
-constexpr int QREG_OFF = BAR_OFF + 1024;               // swapped skinny problems: this CTA's whole slice of the few-row operand,
+constexpr int BAR_OFF = STAGES * STAGE_BYTES;          // 192 KB
+constexpr int QREG_OFF = 2 * STAGE_BYTES;              // swapped skinny problems: this CTA's whole slice of the few-row operand,
 constexpr int QREG_BYTES = 64 * 1024;                  //   rounded and swizzled by the epilogue warps (no pack launch)
-constexpr int XCHG_OFF = QREG_OFF + QREG_BYTES;        // cluster split-K: the partial sums the peer CTAs push into this CTA's slice
+constexpr int XCHG_OFF = BAR_OFF + 1024;               // cluster split-K: the partial sums the peer CTAs push into this CTA's slice
 constexpr int XCHG_BYTES = 32 * 1024;                  //   [split][bn][128 / split] fp32 <= bn * 512 B
 constexpr int SMEM_TOTAL = XCHG_OFF + XCHG_BYTES + 1024;   // + alignment slack
 constexpr int EPI_WARPS = 16;
@@ -56,6 +56,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int TILE_PITCH = TN + 4;                     // fp32 words per row of the transposition tile (67.6 KB, reuses the ring)
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(QREG_BYTES <= STAGE_BYTES, "the conversion buffer takes the third ring slot");
 static_assert(TM * TILE_PITCH * 4 <= BAR_OFF, "output tile must fit in the pipeline's shared memory");
 
 struct GemmArgs {
@@ -74,7 +75,7 @@ struct GemmArgs {
   const float* q_src;      // q_convert: the N-side operand [QR][K] as the caller gave it (any alignment), pitch q_src_ld
   long q_src_ld;
   int q_convert, K;
-  int cluster;             // 1: the `split` CTAs of a tile form a thread-block cluster and reduce through distributed shared memory
+  int cluster;             // the `split` CTAs of a tile form a thread-block cluster: 1 = reduce through distributed shared memory, 2 = through global planes
 };
 
 // MN-major fp32 operand descriptor.  32-bit MN-major operands have one legal shared-memory layout (cute::UMMA
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
   const int kb0 = (int)(((long)g.nk * z) / split), kb1 = (int)(((long)g.nk * (z + 1)) / split);   // split <= nk: never empty
   const int nkl = kb1 - kb0;
   const int n_st = (nkl + KPS - 1) / KPS;
+  const int stages = g.swap ? STAGES - 1 : STAGES;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&g.tmP);
@@ -149,8 +151,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
       const int q_chunks = (g.bn + 31) >> 5;
       const uint32_t tx = (uint32_t)P_BYTES + (g.q_convert ? 0u : (g.q_mn ? (uint32_t)q_chunks * 4096u : (uint32_t)g.bn * TK * 4));
       for (int st = 0; st < n_st; ++st) {
-        const int s = st % STAGES;
-        mbar_wait(&empty[s], ((st / STAGES) & 1) ^ 1u);
+        const int s = st % stages;
+        mbar_wait(&empty[s], ((st / stages) & 1) ^ 1u);
         const int n_sub = min(KPS, nkl - st * KPS);
         mbar_expect_tx(&full[s], (uint32_t)n_sub * tx);
         for (int j = 0; j < n_sub; ++j) {
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
       const uint32_t p_step = g.p_mn ? (1024 >> 4) : 2, q_step = g.q_mn ? (1024 >> 4) : 2;
       if (g.q_convert) mbar_wait(q_ready, 0);
       for (int st = 0; st < n_st; ++st) {
-        const int s = st % STAGES;
-        mbar_wait(&full[s], (st / STAGES) & 1);
+        const int s = st % stages;
+        mbar_wait(&full[s], (st / stages) & 1);
         tc_fence_after();
         const int n_sub = min(KPS, nkl - st * KPS);
         for (int j = 0; j < n_sub; ++j) {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
     const int row = q * 32 + lane;
     const bool active = part * 32 < g.bn;
     // first destination: C itself, or this split's plane of the partial buffer (C layout, padded: no guards / bias / accumulate)
-    const bool direct = split == 1 || g.cluster;
+    const bool direct = split == 1 || g.cluster == 1;
     const int C_rows = g.swap ? g.QR : g.PR, C_cols = g.swap ? g.PR : g.QR;
     float* dst = direct ? g.C : g.part + (long)z * g.part_plane;
     const long ld = direct ? g.ldc : g.part_ld;
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
     tc_fence_after();
     float v[32];
     if (active) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 32), v);
-    if (g.cluster) {
+    if (g.cluster == 1) {
       // Cluster split-K (swapped tiles): CTA z owns rows [z * slice, (z + 1) * slice) of the tile.  Every CTA pushes its partial sums
       // of a row into the owner's exchange buffer [source z][q][row in slice] (st.shared::cluster; lanes = consecutive rows), one
       // cluster barrier, then the owner adds the `split` partials in z order: no global round trip, no atomics, no fences.
@@ -328,7 +330,31 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
         store4(dst, ld, p0 + r, q0 + c, *reinterpret_cast<const float4*>(tile + r * TILE_PITCH + c), c_cols, bias, acc, al);
       }
     }
-    if (!direct) {          // (split > 1 without a cluster)
+    if (g.cluster == 2) {
+      // Cluster split-K (128-row tiles): every CTA has stored its partial tile into its plane of the global buffer (L2); one cluster
+      // barrier (release / acquire orders those stores for the peers), then CTA z sums rows [z * slice, (z + 1) * slice) of all planes
+      // in z order -- each CTA reads one tile's worth of partials whatever the split, all loads of a row group in flight together.
+      cluster_wait_acquire();              // phase 1 (start-up) is over
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      const int slice = (TM + split - 1) / split, CN4 = g.bn >> 2;        // (any split of 2 ... 8: the last slice may be short)
+      const bool al = ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0) && ((g.ldc & 3) == 0);
+      for (int idx = tid; idx < slice * CN4; idx += EPI_THREADS) {
+        const int r = idx / CN4, c = (idx - r * CN4) << 2;
+        const int row = p0 + z * slice + r, col = q0 + c;
+        if (z * slice + r >= TM || row >= C_rows || col >= C_cols) continue;
+        const float* src = g.part + (long)row * g.part_ld + col;
+        float4 y[8];
+#pragma unroll
+        for (int zz = 0; zz < 8; ++zz)
+          if (zz < split) y[zz] = __ldcg(reinterpret_cast<const float4*>(src + (long)zz * g.part_plane));
+        float4 sum = y[0];
+#pragma unroll
+        for (int zz = 1; zz < 8; ++zz)
+          if (zz < split) { sum.x += y[zz].x; sum.y += y[zz].y; sum.z += y[zz].z; sum.w += y[zz].w; }
+        store4(g.C, g.ldc, row, col, sum, C_cols, g.bias, g.accumulate != 0, al);
+      }
+    } else if (!direct) {          // (split > 1 without a cluster: swapped tiles whose K slice does not fit the conversion buffer)
       // ticket: the last CTA of this tile to finish sums the `split` partial planes in z order and stores C
       uint32_t* last_flag = tmem_slot + 1;
       const int tile_id = (int)blockIdx.x + (int)gridDim.x * (int)blockIdx.y;
@@ -357,7 +383,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
       }
     }
   }
-  if (g.cluster && warp < 2) {       // the producer / MMA warps take part in the epilogue's cluster barrier
+  if (g.cluster && warp < 2) {       // the producer / MMA warps take part in the epilogue's cluster barriers
     __syncwarp();
     cluster_wait_acquire();
     cluster_arrive_release();
@@ -408,7 +434,8 @@ constexpr long PART_MAX_BYTES = 148L * TM * TN * 4;   // split * tiles <= 148 CT
 
 struct Plan {
   int swap, PR, QR, bn, nk, split, mt, nt;
-  bool pack_a, pack_b, q_convert, cluster;
+  bool pack_a, pack_b, q_convert;
+  int cluster;                     // 0: none, 1: swapped tiles reduced through DSMEM, 2: 128-row tiles reduced through global planes
   long kp;                         // packed pitch (elements)
   long off_a, off_b, off_part;     // workspace offsets (bytes)
   long part_ld, part_plane;        // elements
@@ -419,7 +446,7 @@ inline long align256(long x) { return (x + 255) & ~255L; }
 inline bool aligned_operand(const float* p, long ld) { return (((uintptr_t)p & 15u) == 0) && ((ld & 3) == 0); }
 
 // a_direct / b_direct: the operand is read in place by TMA (caller's flag and aligned); a_kfirst: A lies [M][K]
-Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst) {
+Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst, int force_split = 0) {
   Plan p{};
   p.swap = M <= 64 ? 1 : 0;
   p.PR = p.swap ? N : M;
@@ -430,11 +457,27 @@ Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst)
   p.nt = ceil_div(p.QR, p.bn);
   const int tiles = p.mt * p.nt;
   p.split = 1;
-  if (tiles < 100 && p.nk >= 4) {
-    // main loop ~0.2 us per k-block; the last CTA of a tile re-reads `split` partial tiles from L2 at ~150 GB/s
-    const double per_plane_us = (double)TM * p.bn * 4 / 150e3;
-    const int s = (int)(std::sqrt(p.nk * 0.2 / per_plane_us) + 0.5);
-    p.split = std::max(1, std::min({s, 148 / tiles, p.nk / 2, 32}));
+  p.cluster = 0;
+  if (p.swap) {
+    if (tiles < 100 && p.nk >= 4) {
+      // (fallback for swapped tiles that cannot use the cluster path below: ticket reduction by the last CTA of a tile)
+      const double per_plane_us = (double)TM * p.bn * 4 / 150e3;
+      const int s = (int)(std::sqrt(p.nk * 0.2 / per_plane_us) + 0.5);
+      p.split = std::max(1, std::min({s, 148 / tiles, p.nk / 2, 32}));
+    }
+  } else {
+    // 128-row tiles: 1 ... 8 CTAs per tile as a cluster.  Measured (profiles/README.md): ~0.22 us per k-block of main loop, ~2 us
+    // for the store / cluster barrier / slice reduction once K is split
+    // (a cluster must fit one GPC, ~16 - 18 SMs at one CTA per SM: clusters of 5 - 8 CTAs only when there are few of them)
+    auto fits = [tiles](int sc) { return sc * tiles <= 148 && (sc <= 4 ? true : tiles <= 8); };
+    double best = p.nk * 0.22;
+    for (int sc = 2; sc <= 8; ++sc) {
+      if (!fits(sc) || p.nk / sc < 2) continue;
+      const double cost = ceil_div(p.nk, sc) * 0.22 + 2.0;
+      if (cost < best) { best = cost; p.split = sc; }
+    }
+    if (force_split > 0) p.split = force_split <= 8 && force_split * tiles <= 148 && force_split <= p.nk ? force_split : p.split;   // profiling only
+    if (p.split > 1) p.cluster = 2;
   }
   // swapped problems: the few-row operand (A) is rounded and swizzled inside the kernel when a CTA's K slice of it fits QREG_BYTES
   p.q_convert = false;
@@ -444,12 +487,11 @@ Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst)
     if (s_min <= std::min(148 / tiles, p.nk)) { p.q_convert = true; p.split = std::max(p.split, s_min); }
   }
   // swapped tiles of up to 64 rows of C: 2 / 4 / 8 CTAs per tile as a cluster, reduction through distributed shared memory
-  p.cluster = false;
   if (p.swap && p.nt == 1 && p.bn * 512 <= XCHG_BYTES && p.nk >= 4) {
     const int sc = p.nk >= 16 ? 8 : (p.nk >= 8 ? 4 : 2);
     const bool convert_ok = !(p.swap && !a_direct && a_kfirst) || ceil_div(p.nk, sc) * p.bn * 128 <= QREG_BYTES;
     if (sc * tiles <= 148 && convert_ok) {
-      p.cluster = true;
+      p.cluster = 1;
       p.split = sc;
       p.q_convert = !a_direct && a_kfirst;
     }
@@ -460,7 +502,7 @@ Plan make_plan(int M, int N, int K, bool a_direct, bool b_direct, bool a_kfirst)
   p.off_a = off; if (p.pack_a) off = align256(off + (long)M * p.kp * 4);
   p.off_b = off; if (p.pack_b) off = align256(off + (long)N * p.kp * 4);
   p.off_part = off;
-  if (p.split > 1 && !p.cluster) {
+  if (p.split > 1 && p.cluster != 1) {
     const long c_rows_pad = p.swap ? (long)p.nt * p.bn : (long)p.mt * TM;
     const long c_cols_pad = p.swap ? (long)p.mt * TM : (long)p.nt * p.bn;
     p.part_ld = c_cols_pad;
@@ -507,7 +549,7 @@ extern "C" int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, in
   const bool ta = flags & DRM_GEMM_TRANS_A, tb = flags & DRM_GEMM_TRANS_B;
   DRM_REQUIRE(lda >= (ta ? M : K) && ldb >= (tb ? N : K) && ldc >= N, DRM_ERR_SHAPE, "drm_gemm_tf32: leading dimension too small");
   const Plan p = make_plan(M, N, K, (flags & DRM_GEMM_A_DIRECT) && aligned_operand(A, lda),
-                           (flags & DRM_GEMM_B_DIRECT) && aligned_operand(B, ldb), !ta);
+                           (flags & DRM_GEMM_B_DIRECT) && aligned_operand(B, ldb), !ta, (flags >> 8) & 0xff);
   DRM_REQUIRE(p.total <= drm_gemm_tf32_workspace_bytes(M, N, K), DRM_ERR_SHAPE, "drm_gemm_tf32: internal: workspace bound");
   DRM_REQUIRE(workspace && workspace_bytes >= p.total && ((uintptr_t)workspace & 255u) == 0, DRM_ERR_ARG,
               "drm_gemm_tf32: workspace missing, misaligned (256 bytes) or smaller than drm_gemm_tf32_workspace_bytes");
@@ -547,8 +589,8 @@ extern "C" int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, in
   g.p_mn = p_mn; g.q_mn = q_mn;
   g.accumulate = (flags & DRM_GEMM_ACCUMULATE) ? 1 : 0;
   g.bias = bias; g.C = C; g.ldc = ldc;
-  g.part = (p.split > 1 && !p.cluster) ? reinterpret_cast<float*>(ws + p.off_part) : nullptr;
-  g.cluster = p.cluster ? 1 : 0;
+  g.part = (p.split > 1 && p.cluster != 1) ? reinterpret_cast<float*>(ws + p.off_part) : nullptr;
+  g.cluster = p.cluster;
   g.part_ld = p.part_ld; g.part_plane = p.part_plane;
   g.tickets = reinterpret_cast<unsigned int*>(ws);
   DRM_REQUIRE(p.split == 1 || p.cluster || p.mt * p.nt <= (int)(TICKET_BYTES / 4), DRM_ERR_SHAPE, "drm_gemm_tf32: internal: too many split tiles");

@@ -276,15 +276,20 @@ GEMM_TRANS_A, GEMM_TRANS_B, GEMM_ACCUMULATE, GEMM_A_DIRECT, GEMM_B_DIRECT = 1, 2
 # one persistent workspace per (device, stream): its first 1 KB are the split-K tile tickets, which must start zero and which every
 # call leaves zero; calls on one stream are ordered, so they can share it (a call on another stream gets its own)
 _GEMM_WS: Dict[tuple, torch.Tensor] = {}
+_GEMM_WS_RETIRED: list = []
 
 
 def _gemm_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _GEMM_WS.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 16 << 20), dtype=torch.uint8, device=dev)
+        if ws is not None:
+            # a captured graph may replay kernels that point into the old buffer, and releasing a block of a destroyed graph's private
+            # pool while another capture is running makes the allocator cudaFree inside the capture: outgrown buffers are kept
+            _GEMM_WS_RETIRED.append(ws)
+        ws = torch.empty(max(nbytes, 2 * ws.numel() if ws is not None else 0, 32 << 20), dtype=torch.uint8, device=dev)
         ws[:1024].zero_()        # the tickets (under graph capture this is one 1 KB memset node)
-        _GEMM_WS[key] = ws       # (the old buffer stays alive while queued work or a captured graph still refers to it)
+        _GEMM_WS[key] = ws
     return ws
 
 
