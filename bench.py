@@ -524,7 +524,7 @@ def bench_wm(hs, args, cfg, sd, B, T, desc):
     roofline = dict(bound="tensor", kernel="whole training step (kernel forward + BPTT + optimiser) as one CUDA graph", achieved=tf,
                     peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=tf / peaks["bf16_sustained"], traffic=None,
                     peak_source=peaks["source"] + " bf16 sustained", flops_per_launch=flops,
-                    note="119.7 MFLOP forward per (b, t) x 3 (SURVEY.md section 8d); the backward's GEMMs / convolutions are library calls (DESIGN.md section 6)")
+                    note="119.7 MFLOP forward per (b, t) x 3 (SURVEY.md section 8d); the hand-scheduled backward's contractions run on drm_gemm_tf32, the conv stacks' backward is cuDNN through torch autograd (DESIGN.md sections 4e, 6)")
     line = dict(metric="world-model train steps/sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=desc, batch_per_gpu=B, seq=T, global_batch=B * world, l2="flushed (256 MiB write) between timed iterations",
@@ -532,7 +532,7 @@ def bench_wm(hs, args, cfg, sd, B, T, desc):
                             parallelism=f"data parallel over {world} rank(s): flat 31 MB gradient bucket + packed loss scalars all-reduced over NCCL"),
                 samples_per_s=value * B * world,
                 e2e=dict(value=args.steps / (e2e_ms * 1e-3), unit="steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
-                gpu_launches=int(launches_per_step * args.steps), gpu_launches_note="kernels of this library per step (the torch autograd tail adds library kernels)",
+                gpu_launches=int(launches_per_step * args.steps), gpu_launches_note="kernels of this library per step (the conv stacks' autograd graph adds library kernels)",
                 clocks=clocks, roofline=roofline)
     return line, [wm]
 
