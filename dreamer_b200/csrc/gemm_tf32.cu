@@ -145,6 +145,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (g.cluster) cluster_arrive_release();   // phase 1 ("this CTA runs"): waited for just before the first remote store
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel in
+  // the stream; nothing below touches global memory before that kernel has completed.  The trigger for the NEXT kernel follows at
+  // once (its own prologue then overlaps this kernel; it waits here in turn).
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -402,6 +407,8 @@ struct PackJob {
 };
 __global__ void __launch_bounds__(256) pack_tf32_kernel(const PackJob ja, const PackJob jb, int tiles_a) {
   __shared__ float t[32][33];
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");                 // (programmatic dependent launch, as in gemm_tf32_kernel)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const bool second = (int)blockIdx.x >= tiles_a;
   const PackJob& j = second ? jb : ja;
   const int id = (int)blockIdx.x - (second ? tiles_a : 0);
@@ -567,7 +574,16 @@ extern "C" int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, in
     int tiles_a = ja.tiles_r * ja.tiles_k, tiles_b = jb.tiles_r * jb.tiles_k;
     if (!p.pack_a) { ja = jb; tiles_a = 0; }
     if (!p.pack_b) tiles_b = 0;
-    pack_tf32_kernel<<<tiles_a + tiles_b, 256, 0, st>>>(ja, jb, tiles_a);
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = dim3(tiles_a + tiles_b);
+    pc.blockDim = dim3(256);
+    pc.stream = st;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pa[0].val.programmaticStreamSerializationAllowed = 1;
+    pc.attrs = pa;
+    pc.numAttrs = (flags & DRM_GEMM_NO_PDL) ? 0 : 1;
+    DRM_CUDA(cudaLaunchKernelEx(&pc, pack_tf32_kernel, ja, jb, tiles_a));
     DRM_LAUNCH_CHECK();
     if (p.pack_a) { a_k = a_out; a_ld = p.kp; a_mn = false; }
     if (p.pack_b) { b_k = b_out; b_ld = p.kp; b_mn = false; }
@@ -605,13 +621,20 @@ extern "C" int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, in
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (p.cluster) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p.split;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)p.split;
+    ++na;
   }
+  if (!(flags & DRM_GEMM_NO_PDL)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   DRM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, g));
   DRM_LAUNCH_CHECK();
   return DRM_OK;

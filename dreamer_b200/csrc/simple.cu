@@ -9,6 +9,31 @@
 
 namespace drm {
 
+// Programmatic dependent launch for the kernels of the backward walks (7 launches per time step, each a few microseconds): the next
+// kernel's blocks are scheduled while this one drains.  A kernel launched through launch_pdl() starts with PDL_ENTRY(): it waits for
+// the previous kernel in the stream to complete (nothing before that point touches global memory) and at once lets its own successor
+// be scheduled.  Inside a captured graph these become programmatic dependency edges.
+#define PDL_ENTRY()                                              \
+  do {                                                           \
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");          \
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -130,6 +155,7 @@ __global__ void __launch_bounds__(256) categorical32_kernel(const float* __restr
 __global__ void __launch_bounds__(256) categorical32_bwd_rowwarp_kernel(const float* __restrict__ logits, const float* __restrict__ dz,
                                                                         const float* __restrict__ dz2, const float* __restrict__ dl_add,
                                                                         float* __restrict__ dlogits, int64_t n_rows) {
+  PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -161,6 +187,7 @@ __global__ void __launch_bounds__(256) categorical32_bwd_rowwarp_kernel(const fl
 __global__ void __launch_bounds__(256) categorical32_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dz,
                                                                 const float* __restrict__ dz2, const float* __restrict__ dl_add,
                                                                 float* __restrict__ dlogits, int64_t n_rows) {
+  PDL_ENTRY();
   __shared__ float tiles[8][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float(*t)[33] = tiles[w];
@@ -230,6 +257,7 @@ template <int J>   // J = ceil(n / 32) values per lane: 8 for the <= 256-wide hi
 __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ da, float* __restrict__ dln_out, int64_t rows, int n, float eps) {
+  PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -292,6 +320,7 @@ __global__ void __launch_bounds__(256) gru_bwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ gh, const float* __restrict__ h_prev,
                                                       float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dh_prev,
                                                       int accumulate, int64_t rows, int D, const float* __restrict__ dh_add = nullptr) {
+  PDL_ENTRY();
   const int64_t total = rows * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / D;
@@ -322,6 +351,7 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const float* __rest
                                                              const float* __restrict__ da, const float* __restrict__ a,
                                                              const float* __restrict__ eps, const float* __restrict__ ls,
                                                              float* __restrict__ d_head, int64_t rows, int A) {
+  PDL_ENTRY();
   const int64_t total = rows * A;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / A;
@@ -349,6 +379,7 @@ __global__ void __launch_bounds__(256) tanh_normal_logp_kernel(const float* __re
                                                                const float* __restrict__ sigma, const float* __restrict__ coef,
                                                                float* __restrict__ logp, float* __restrict__ g_mu, float* __restrict__ g_sg,
                                                                int64_t rows, int A) {
+  PDL_ENTRY();
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const float cf = coef ? coef[r] : 1.0f;
     float acc = 0.f;
@@ -602,6 +633,7 @@ __global__ void __launch_bounds__(256) twohot_ce_bwd_kernel(const float* __restr
                                                             const float* __restrict__ buckets, const float* __restrict__ coef,
                                                             const float* __restrict__ scale_dev, float scale, float* __restrict__ dlogits,
                                                             int64_t N, int NB, int apply_symlog) {
+  PDL_ENTRY();
   __shared__ float sb[256];
   for (int i = threadIdx.x; i < NB; i += blockDim.x) sb[i] = buckets[i];
   __syncthreads();
@@ -721,11 +753,11 @@ extern "C" int drm_categorical32_bwd(const float* logits, const float* dz, const
                   (!dz2 || (uintptr_t)dz2 % 16 == 0) && (!dl_add || (uintptr_t)dl_add % 16 == 0),
               DRM_ERR_ALIGN, "drm_categorical32_bwd: 16-byte alignment required");
   if (n_rows <= 8192) {   // few rows: warp per row (latency-bound calls of the BPTT recurrence)
-    categorical32_bwd_rowwarp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dz2, dl_add, dlogits, n_rows);
+    DRM_CUDA(launch_pdl(categorical32_bwd_rowwarp_kernel, (unsigned)((n_rows + 7) / 8), 256, (cudaStream_t)stream, logits, dz, dz2, dl_add, dlogits, n_rows));
     DRM_LAUNCH_CHECK();
     return DRM_OK;
   }
-  categorical32_bwd_kernel<<<rows_grid((n_rows + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(logits, dz, dz2, dl_add, dlogits, n_rows);
+  DRM_CUDA(launch_pdl(categorical32_bwd_kernel, (unsigned)rows_grid((n_rows + 31) / 32, 8), 256, (cudaStream_t)stream, logits, dz, dz2, dl_add, dlogits, n_rows));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -736,8 +768,8 @@ extern "C" int drm_ln_silu_bwd(const float* dy, const float* a, const float* gam
   DRM_REQUIRE(rows >= 0 && n >= 1 && n <= 1024, DRM_ERR_SHAPE, "drm_ln_silu_bwd: n must be in [1, 1024]");
   if (rows == 0) return DRM_OK;
   DRM_REQUIRE(dy && a && gamma && beta && da, DRM_ERR_ARG, "drm_ln_silu_bwd: NULL pointer");
-  if (n <= 256) ln_silu_bwd_kernel<8><<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
-  else ln_silu_bwd_kernel<32><<<rows_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(dy, a, gamma, beta, da, dln, rows, n, eps);
+  if (n <= 256) DRM_CUDA(launch_pdl(ln_silu_bwd_kernel<8>, (unsigned)rows_grid(rows, 8), 256, (cudaStream_t)stream, dy, a, gamma, beta, da, dln, rows, n, eps));
+  else DRM_CUDA(launch_pdl(ln_silu_bwd_kernel<32>, (unsigned)rows_grid(rows, 8), 256, (cudaStream_t)stream, dy, a, gamma, beta, da, dln, rows, n, eps));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -750,7 +782,7 @@ extern "C" int drm_gru_bwd(const float* dh, const float* gi, const float* gh, co
   DRM_REQUIRE(dh && gi && gh && dgi && dgh, DRM_ERR_ARG, "drm_gru_bwd: NULL pointer");
   const int64_t total = rows * D;
   const int64_t want = (total + 255) / 256;
-  gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D);
+  DRM_CUDA(launch_pdl(gru_bwd_kernel, (unsigned)(want > 148 * 8 ? 148 * 8 : want), 256, (cudaStream_t)stream, dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D, (const float*)nullptr));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -765,7 +797,7 @@ extern "C" int drm_gru_bwd_add(const float* dh, const float* dh_add, const float
   DRM_REQUIRE(dh && gi && gh && dgi && dgh, DRM_ERR_ARG, "drm_gru_bwd_add: NULL pointer");
   const int64_t total = rows * D;
   const int64_t want = (total + 255) / 256;
-  gru_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D, dh_add);
+  DRM_CUDA(launch_pdl(gru_bwd_kernel, (unsigned)(want > 148 * 8 ? 148 * 8 : want), 256, (cudaStream_t)stream, dh, gi, gh, h_prev, dgi, dgh, dh_prev, accumulate, rows, D, dh_add));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -777,7 +809,7 @@ extern "C" int drm_actor_head_bwd(const float* g_mu, const float* g_sigma, const
   if (rows == 0) return DRM_OK;
   DRM_REQUIRE(g_mu && g_sigma && log_sigma && d_head && (!da || (a && eps)), DRM_ERR_ARG, "drm_actor_head_bwd: NULL pointer");
   const int64_t want = (rows * A + 255) / 256;
-  actor_head_bwd_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(g_mu, g_sigma, da, a, eps, log_sigma, d_head, rows, A);
+  DRM_CUDA(launch_pdl(actor_head_bwd_kernel, (unsigned)(want > 148 * 8 ? 148 * 8 : want), 256, (cudaStream_t)stream, g_mu, g_sigma, da, a, eps, log_sigma, d_head, rows, A));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -789,7 +821,8 @@ extern "C" int drm_tanh_normal_logp(const float* a, const float* mu, const float
   if (rows == 0) return DRM_OK;
   DRM_REQUIRE(a && mu && sigma && (logp || g_mu || g_sigma), DRM_ERR_ARG, "drm_tanh_normal_logp: NULL pointer");
   const int64_t want = (rows + 255) / 256;
-  tanh_normal_logp_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want), 256, 0, (cudaStream_t)stream>>>(a, mu, sigma, coef, logp, g_mu, g_sigma, rows, A);
+  DRM_CUDA(launch_pdl(tanh_normal_logp_kernel, (unsigned)(want > 148 * 8 ? 148 * 8 : want), 256, (cudaStream_t)stream, a, mu, sigma, coef, logp, g_mu, g_sigma,
+                       rows, (int)A));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }
@@ -878,8 +911,8 @@ extern "C" int drm_twohot_ce_bwd(const float* logits, const float* value, const 
   DRM_REQUIRE(N >= 0 && NB >= 2 && NB <= 256, DRM_ERR_SHAPE, "drm_twohot_ce_bwd: NB must be in [2, 256]");
   if (N == 0) return DRM_OK;
   DRM_REQUIRE(logits && value && buckets && dlogits, DRM_ERR_ARG, "drm_twohot_ce_bwd: NULL pointer");
-  twohot_ce_bwd_kernel<<<rows_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(logits, value, buckets, coef, scale_dev, scale, dlogits, N, NB,
-                                                                       apply_symlog);
+  DRM_CUDA(launch_pdl(twohot_ce_bwd_kernel, (unsigned)rows_grid(N, 8), 256, (cudaStream_t)stream, logits, value, buckets, coef, scale_dev, scale,
+                       dlogits, N, (int)NB, (int)apply_symlog));
   DRM_LAUNCH_CHECK();
   return DRM_OK;
 }

@@ -366,6 +366,7 @@ int drm_grad_norm(const float* grad, int64_t n, void* scratch, float* norm_out, 
 #define DRM_GEMM_ACCUMULATE 4
 #define DRM_GEMM_A_DIRECT 8
 #define DRM_GEMM_B_DIRECT 16
+#define DRM_GEMM_NO_PDL 32      /* launch without programmatic stream serialisation (profiling) */
 int64_t drm_gemm_tf32_workspace_bytes(int32_t M, int32_t N, int32_t K);
 int drm_gemm_tf32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                   int64_t ldc, const float* bias, int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
