@@ -54,12 +54,13 @@ def _side_stream(dev):
 GEMM_BATCHED = "drm"
 GEMM_STEP = "drm"
 # Step GEMMs with more than 64 gradient rows (the 1024-row agent step of c5) cannot round their gradient rows inside the kernel (that is
-# the swapped skinny path).  GEMM_STEP_LARGE = "torch" (default) keeps the library GEMM for them: read in place on 128 x 128 tiles this
-# library's kernel is bound by the ~110 GB/s an SM ingests from L2 (15.3 us against 10.1 us at 1024 x 600 x 1800; agent step 1024 x 15
-# 4.29 -> 5.47 ms, profiles/gemm_backend_ab.py agent).  "drm" runs them on drm_gemm_tf32 all the same (gradient operand truncated by
-# the tensor core, weights pre-rounded: < 0.1 % over a 15-step walk; the gradient tests pass either way).
+# the swapped skinny path): they run on drm_gemm_tf32's 128-row tiles with the gradient operand read in place (truncated by the tensor
+# core; the weights are pre-rounded: < 0.1 % over a 15-step walk, tests/test_gpu_bptt.py at 160 rows).  One 128 x 128 tile per SM is
+# bound by the ~110 GB/s an SM ingests from L2, so these cost more than the library GEMM (13.6 us against 9.9 us at 1024 x 600 x 1800;
+# agent step 1024 x 15: 4.56 ms against 4.18 ms, profiles/gemm_backend_ab.py agent); GEMM_STEP_LARGE = "torch" selects the library GEMM
+# for them.
 GEMM_STEP_MAX_ROWS = 64
-GEMM_STEP_LARGE = "torch"
+GEMM_STEP_LARGE = "drm"
 # The batched part of the world-model backward that reads (h_t, z_t) at one step -- prior MLP, reward / continue heads, decoder MLP,
 # KL terms: "drm" = differentiated by hand on this library's kernels (only the conv stacks stay torch autograd / cuDNN),
 # "autograd" = one torch autograd graph (the implementation the hand-written one is tested against).

@@ -135,7 +135,8 @@ def test_world_model_bptt_gradient_matches_autograd_tail(B, T):
     assert (num / den) ** 0.5 < 3e-2
 
 
-def test_actor_gradient_through_the_imagined_states_matches_autograd():
+@pytest.mark.parametrize("B", [24, 160])          # 24 rows: swapped skinny step GEMMs; 160 rows: 128-row tiles (bptt.GEMM_STEP_LARGE)
+def test_actor_gradient_through_the_imagined_states_matches_autograd(B):
     """bptt.actor_backward against torch autograd over a pure-torch imagination (Dreamer.py:158-164 + Agent.py:110-126) on the
     same classes and draws: the reference's actor gradient, INCLUDING the path through the imagined states.  Also shows that the
     detached-state gradient (no world model attached) differs from it, i.e. that the through-the-world-model term is real."""
@@ -144,7 +145,8 @@ def test_actor_gradient_through_the_imagined_states_matches_autograd():
     cfg = W.small_config(horizon=6)
     sd = W.make_state_dict(cfg, seed=31, actor_mu_zero=False)
     wm, ag = W.build_learners(cfg, sd, DEV)
-    B, H, D, A = 24, cfg["horizon"], cfg["hidden_state_dims"], cfg["action_dims"]
+    H, D, A = cfg["horizon"], cfg["hidden_state_dims"], cfg["action_dims"]
+    assert bptt.GEMM_STEP == "drm" and bptt.GEMM_STEP_LARGE == "drm"
     g = torch.Generator(device="cuda").manual_seed(7)
     z = F.one_hot(torch.randint(0, 32, (B, 32), device=DEV, generator=g), 32).float().reshape(B, 1024)
     h = torch.tanh(torch.randn(B, D, device=DEV, generator=g))
