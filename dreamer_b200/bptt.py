@@ -98,6 +98,25 @@ def _acc(p: torch.nn.Parameter, g: torch.Tensor):
     p.grad.add_(g.view_as(p))
 
 
+def _acc_colsum(p: torch.nn.Parameter, x: torch.Tensor):
+    """p.grad += x.sum(0)   (bias / LayerNorm-affine gradients: drm_colsum accumulates in place, one launch)"""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    if GEMM_BATCHED == "drm" and x.is_cuda and p.grad.is_contiguous():
+        ops.colsum(x, out=p.grad.view(-1), accumulate=True)
+    else:
+        p.grad.add_(x.sum(0).view_as(p))
+
+
+def _ln_bwd(dy, a, ln):
+    """Backward of SiLU(LayerNorm(a)) for a batched block: returns d(loss)/da and accumulates the affine gradients
+    (d gamma = colsum(dln * xhat), d beta = colsum(dln))."""
+    da, dln, dlnx = ops.ln_silu_bwd(dy, a, ln.weight, ln.bias, ln.eps, want_dln=True, want_dlnx=True)
+    _acc_colsum(ln.weight, dlnx)
+    _acc_colsum(ln.bias, dln)
+    return da
+
+
 def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
     """p.grad += a_t^T @ b   (a_t [rows, out], b [rows, in])"""
     if p.grad is None:
@@ -254,12 +273,10 @@ def _heads_manual(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, 
         # decoder MLP: Linear-LN-SiLU-Linear(-SiLU, differentiated above)
         da2 = a2l.grad
         _acc_mm(u2.weight, da2, uy1)
-        _acc(u2.bias, da2.sum(0))
-        da1, dln = ops.ln_silu_bwd(_mm(da2, u2.weight), ua1, un.weight, un.bias, un.eps, want_dln=True)
-        _acc(un.weight, (dln * F.layer_norm(ua1, (ua1.shape[-1],), None, None, un.eps)).sum(0))
-        _acc(un.bias, dln.sum(0))
+        _acc_colsum(u2.bias, da2)
+        da1 = _ln_bwd(_mm(da2, u2.weight), ua1, un)
         _acc_mm(u1.weight, da1, rows_all)
-        _acc(u1.bias, da1.sum(0))
+        _acc_colsum(u1.bias, da1)
         gHZ = _mm(da1, u1.weight).view(B, T, Dh + Z)
         # reward head: - c_pred * sum(mask * twohot_ll);   continue head: + c_pred * sum(mask * BCE(cl, mask))
         d_rw = ops.twohot_ce_bwd(rw["logits"], rew_rows, b, coef=mask_rows, scale_dev=c_pred, scale=-1.0)
@@ -382,17 +399,14 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
         # ---- (3) weight gradients: batched GEMMs over all B*T rows ----------------------------------------------------
         dGI2, dGH2, dLG2 = dGI.view(T * B, -1), dGH.view(T * B, -1), dLG.view(T * B, -1)
         _acc_mm(gru.weight_ih, dGI2, X.view(T * B, -1))
-        _acc(gru.bias_ih, dGI2.sum(0))
+        _acc_colsum(gru.bias_ih, dGI2)
         _acc_mm(gru.weight_hh, dGH2, Hprev.view(T * B, -1))
-        _acc(gru.bias_hh, dGH2.sum(0))
+        _acc_colsum(gru.bias_hh, dGH2)
         _acc_mm(lin2.weight, dLG2, Y1)
-        _acc(lin2.bias, dLG2.sum(0))
-        dA1_all, dln = ops.ln_silu_bwd(_mm(dLG2, W2), A1, ln1.weight, ln1.bias, ln1.eps, want_dln=True)
-        xhat = F.layer_norm(A1, (A1.shape[-1],), None, None, ln1.eps)
-        _acc(ln1.weight, (dln * xhat).sum(0))
-        _acc(ln1.bias, dln.sum(0))
+        _acc_colsum(lin2.bias, dLG2)
+        dA1_all = _ln_bwd(_mm(dLG2, W2), A1, ln1)
         _acc_mm(lin1.weight, dA1_all, X1.view(T * B, -1))
-        _acc(lin1.bias, dA1_all.sum(0))
+        _acc_colsum(lin1.bias, dA1_all)
         dfeat = _mm(dA1_all, lin1.weight[:, :n_feat]).view(T, B, n_feat).transpose(0, 1).reshape(B * T, n_feat)
     mark("batched weight-gradient GEMMs")
     feats.backward(dfeat)    # encoder convs
@@ -499,19 +513,15 @@ def _actor_backward(agent, wm, z, h, act, mu, sigma, coef):
         # ---- actor weight gradients: batched GEMMs over all B*H rows ----------------------------------------------------
         dH2 = dHEAD.view(H * B, 2 * A)
         _acc_mm(actor.mu_head.weight, dH2[:, :A], Y2)
-        _acc(actor.mu_head.bias, dH2[:, :A].sum(0))
+        _acc_colsum(actor.mu_head.bias, dH2[:, :A])
         _acc_mm(actor.log_sig_head.weight, dH2[:, A:], Y2)
-        _acc(actor.log_sig_head.bias, dH2[:, A:].sum(0))
-        dA2_all, dln2 = ops.ln_silu_bwd(dY2s.view(H * B, -1), A2, n2.weight, n2.bias, n2.eps, want_dln=True)
-        _acc(n2.weight, (dln2 * F.layer_norm(A2, (A2.shape[-1],), None, None, n2.eps)).sum(0))
-        _acc(n2.bias, dln2.sum(0))
+        _acc_colsum(actor.log_sig_head.bias, dH2[:, A:])
+        dA2_all = _ln_bwd(dY2s.view(H * B, -1), A2, n2)
         _acc_mm(l2.weight, dA2_all, Y1)
-        _acc(l2.bias, dA2_all.sum(0))
-        dA1_all, dln1 = ops.ln_silu_bwd(dY1s.view(H * B, -1), A1, n1.weight, n1.bias, n1.eps, want_dln=True)
-        _acc(n1.weight, (dln1 * F.layer_norm(A1, (A1.shape[-1],), None, None, n1.eps)).sum(0))
-        _acc(n1.bias, dln1.sum(0))
+        _acc_colsum(l2.bias, dA2_all)
+        dA1_all = _ln_bwd(dY1s.view(H * B, -1), A1, n1)
         _acc_mm(l1.weight, dA1_all, Xa)
-        _acc(l1.bias, dA1_all.sum(0))
+        _acc_colsum(l1.bias, dA1_all)
 
 
 def _mlp3_forward(net, x):
@@ -527,17 +537,13 @@ def _mlp3_backward(c, d3, want_dx=False):
     (drm_ln_silu_bwd, drm_gemm_tf32); returns d(loss)/dx when asked."""
     l1, n1, _, l2, n2, _, l3 = c["net"]
     _acc_mm(l3.weight, d3, c["y2"])
-    _acc(l3.bias, d3.sum(0))
-    da2, dln2 = ops.ln_silu_bwd(_mm(d3, l3.weight), c["a2"], n2.weight, n2.bias, n2.eps, want_dln=True)
-    _acc(n2.weight, (dln2 * F.layer_norm(c["a2"], (da2.shape[-1],), None, None, n2.eps)).sum(0))
-    _acc(n2.bias, dln2.sum(0))
+    _acc_colsum(l3.bias, d3)
+    da2 = _ln_bwd(_mm(d3, l3.weight), c["a2"], n2)
     _acc_mm(l2.weight, da2, c["y1"])
-    _acc(l2.bias, da2.sum(0))
-    da1, dln1 = ops.ln_silu_bwd(_mm(da2, l2.weight), c["a1"], n1.weight, n1.bias, n1.eps, want_dln=True)
-    _acc(n1.weight, (dln1 * F.layer_norm(c["a1"], (da1.shape[-1],), None, None, n1.eps)).sum(0))
-    _acc(n1.bias, dln1.sum(0))
+    _acc_colsum(l2.bias, da2)
+    da1 = _ln_bwd(_mm(da2, l2.weight), c["a1"], n1)
     _acc_mm(l1.weight, da1, c["x"])
-    _acc(l1.bias, da1.sum(0))
+    _acc_colsum(l1.bias, da1)
     return _mm(da1, l1.weight) if want_dx else None
 
 

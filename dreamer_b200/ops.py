@@ -77,8 +77,8 @@ def categorical32_bwd(logits, dz, dz2=None, dl_add=None, out=None):
     return out
 
 
-def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, out=None):
-    """Backward of SiLU(LayerNorm(a) * gamma + beta): dy, a (..., n) -> da (..., n) [, dln]."""
+def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, out=None, want_dlnx: bool = False):
+    """Backward of SiLU(LayerNorm(a) * gamma + beta): dy, a (..., n) -> da (..., n) [, dln] [, dlnx = dln * xhat with want_dlnx]."""
     n = a.shape[-1]
     for t in (dy, a, gamma, beta):
         if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
@@ -87,9 +87,34 @@ def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, o
         raise RuntimeError("dreamer_b200.ln_silu_bwd: shape mismatch")
     da = torch.empty_like(a) if out is None else out
     dln = torch.empty_like(a) if want_dln else None
+    if want_dlnx:
+        dlnx = torch.empty_like(a)
+        L.check(L.load().drm_ln_silu_bwd_affine(L.ptr(dy), L.ptr(a), L.ptr(gamma), L.ptr(beta), L.ptr(da), L.ptr(dln), L.ptr(dlnx),
+                                                a.numel() // n, n, eps, L.stream()), "ln_silu_bwd_affine")
+        return da, dln, dlnx
     L.check(L.load().drm_ln_silu_bwd(L.ptr(dy), L.ptr(a), L.ptr(gamma), L.ptr(beta), L.ptr(da), L.ptr(dln), a.numel() // n, n, eps, L.stream()),
             "ln_silu_bwd")
     return (da, dln) if want_dln else da
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """out [n] (+)= x [rows, n].sum(0) (x may be a column slice of a wider matrix); deterministic."""
+    L.require_cuda(x, "x")
+    if x.dtype != torch.float32 or x.dim() != 2 or (x.stride(1) != 1 and x.shape[1] != 1):
+        x = L.f32c(x.reshape(-1, x.shape[-1]))
+    rows, n = x.shape
+    if out is None:
+        if accumulate:
+            raise RuntimeError("dreamer_b200.colsum: accumulate needs `out`")
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    elif out.dtype != torch.float32 or out.numel() != n or not out.is_contiguous():
+        raise RuntimeError("dreamer_b200.colsum: `out` must be a contiguous fp32 tensor of n elements")
+    lib = L.load()
+    nscr = lib.drm_colsum_scratch_bytes(rows, n)
+    scratch = torch.empty(nscr, dtype=torch.uint8, device=x.device) if nscr else None
+    L.check(lib.drm_colsum(L.ptr(x), rows, n, x.stride(0) if rows > 1 else n, L.ptr(out), 1 if accumulate else 0, L.ptr(scratch), L.stream()),
+            "colsum")
+    return out
 
 
 def gru_bwd(dh, gi, gh, h_prev, dgi, dgh, dh_prev=None, accumulate: bool = False, dh_add=None):

@@ -112,6 +112,16 @@ int drm_categorical32_bwd(const float* logits, const float* dz, const float* dz2
 /* batched dgamma = sum(dln * xhat), dbeta = sum(dln).  Statistics are recomputed from a (eps as in the forward, 1e-5).       */
 int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const float* beta, float* da, float* dln,
                     int64_t rows, int32_t n, float eps, void* stream);
+/* ... with a third optional output dlnx = dln * xhat (xhat = the normalised activation): its column sums are d(loss)/d(gamma),   */
+/* dln's are d(loss)/d(beta) (drm_colsum).                                                                                   */
+int drm_ln_silu_bwd_affine(const float* dy, const float* a, const float* gamma, const float* beta, float* da, float* dln, float* dlnx,
+                           int64_t rows, int32_t n, float eps, void* stream);
+/* out[c] (=, or += when accumulate) sum over the rows of x [rows, n] (row pitch ld): the bias / LayerNorm-affine gradients of the  */
+/* batched backward (autograd's sum-to-size nodes).  Deterministic (fixed reduction order).                                     */
+/* scratch: device memory of drm_colsum_scratch_bytes(rows, n) bytes (0 up to 64 rows: may be NULL; taller matrices are summed in    */
+/* two stages).                                                                                                              */
+int64_t drm_colsum_scratch_bytes(int64_t rows, int32_t n);
+int drm_colsum(const float* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
 /* Backward of one nn.GRUCell step (SequenceModel.py:13,19-24) from its pre-activations gi = x W_ih^T + b_ih,                */
 /* gh = h W_hh^T + b_hh [rows, 3D] (gate order r, u, n), h_prev [rows, D] (NULL = zeros) and dh [rows, D]:                    */
 /*   dgi = [dr, du, dn], dgh = [dr, du, dn * r] (pre-activation gradients), dh_prev (=, or += when accumulate) dh * u.        */

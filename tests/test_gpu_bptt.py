@@ -275,3 +275,27 @@ def test_tanh_normal_logp_matches_torch():
     assert torch.allclose(logp, ref.detach(), rtol=1e-4, atol=1e-3)          # atanh near +-1: ~7.25 with fp32 ulps of the clamp
     assert torch.allclose(gm, mu_l.grad, rtol=1e-4, atol=1e-4 * float(mu_l.grad.abs().max()))
     assert torch.allclose(gs, sg_l.grad, rtol=1e-4, atol=1e-4 * float(sg_l.grad.abs().max()))
+
+
+def test_colsum_and_ln_affine_outputs():
+    from dreamer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for rows, n in ((1, 5), (7, 33), (1024, 1800), (2049, 200), (15360, 200), (15360, 3), (100000, 40), (1000, 3)):
+        big = torch.randn(rows, n + 5, device=DEV, generator=g)
+        x = big[:, 2:2 + n]                                                   # a column slice: row pitch n + 5
+        ref = x.double().sum(0)
+        got = ops.colsum(x)
+        assert torch.allclose(got.double(), ref, rtol=1e-5, atol=1e-6 * rows + 1e-4)
+        acc = torch.full((n,), 3.0, device=DEV)
+        ops.colsum(x, out=acc, accumulate=True)
+        assert torch.allclose(acc.double(), ref + 3.0, rtol=1e-5, atol=1e-6 * rows + 1e-4)
+        assert torch.equal(ops.colsum(x), got)                                # deterministic
+    rows, n = 300, 200
+    a = torch.randn(rows, n, device=DEV, generator=g) * 2
+    dy = torch.randn(rows, n, device=DEV, generator=g)
+    gamma, beta = torch.randn(n, device=DEV, generator=g), torch.randn(n, device=DEV, generator=g)
+    da, dln, dlnx = ops.ln_silu_bwd(dy, a, gamma, beta, 1e-5, want_dln=True, want_dlnx=True)
+    da0, dln0 = ops.ln_silu_bwd(dy, a, gamma, beta, 1e-5, want_dln=True)
+    assert torch.equal(da, da0) and torch.equal(dln, dln0)
+    xhat = F.layer_norm(a, (n,), None, None, 1e-5)
+    assert torch.allclose(dlnx, dln * xhat, rtol=1e-4, atol=1e-5)
