@@ -16,6 +16,8 @@ Gradients are accumulated into the parameters' ``.grad`` (the flat bucket of opt
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 import torch.nn.functional as F
 
@@ -115,6 +117,43 @@ def _ln_bwd(dy, a, ln):
     _acc_colsum(ln.weight, dlnx)
     _acc_colsum(ln.bias, dln)
     return da
+
+
+def _conv_bias_hook(bias, g):
+    """grad_output of a conv layer -> bias.grad += sum over N, H, W (the rows of the channels-last matrix [N * H * W, C])"""
+    with torch.no_grad():
+        C = g.shape[1]
+        if g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last):
+            _acc_colsum(bias, g.permute(0, 2, 3, 1).reshape(-1, C))
+        else:
+            if bias.grad is None:
+                bias.grad = torch.zeros_like(bias)
+            bias.grad.add_(g.float().sum(dim=(0, 2, 3)))
+    return None
+
+
+def _conv_stack(seq, x):
+    """Run a conv stack (nn.Sequential of Conv2d / ConvTranspose2d / SiLU) under autograd with the BIAS gradients taken out of the
+    graph: each conv node is recorded while its bias does not require grad (the fused bias add of the forward stays), and a hook on
+    the conv's output accumulates the column sums of grad_output into bias.grad (drm_colsum / drm_colsum_bf16) -- autograd's own
+    conv-bias reduction is a ~75 us bf16 reduce kernel per layer at these sizes, 0.45 ms per world-model step."""
+    if GEMM_BATCHED != "drm":
+        return seq(x)
+    toggled = []
+    try:
+        for m in seq:
+            hook = (isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) and m.bias is not None and m.bias.requires_grad
+                    and m.out_channels % 2 == 0 and m.out_channels >= 16)
+            if hook:
+                m.bias.requires_grad_(False)
+                toggled.append(m.bias)
+            x = m(x)
+            if hook and x.requires_grad:
+                x.register_hook(functools.partial(_conv_bias_hook, m.bias))
+    finally:
+        for b in toggled:
+            b.requires_grad_(True)
+    return x
 
 
 def _acc_mm(p: torch.nn.Parameter, a_t: torch.Tensor, b: torch.Tensor):
@@ -226,7 +265,7 @@ def _heads_manual(wm, obs, rew, cont, Hk, z_oh, LG, parts, conv_dtype, on_loss, 
     a2l = ua2.requires_grad_(True)
     x = F.silu(a2l).view(B * T, dec_mod.num_filters_start, dec_mod.start_height, dec_mod.start_width)
     with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
-        dec = dec_mod.image_builder(x.contiguous(memory_format=torch.channels_last))
+        dec = _conv_stack(dec_mod.image_builder, x.contiguous(memory_format=torch.channels_last))
     dec = dec.float().view(obs.shape)
     obs_ll = -((dec - obs) ** 2).sum(dim=[-3, -2, -1])[:, 1:] * m1
     with torch.no_grad():
@@ -338,7 +377,7 @@ def _world_model_backward(wm, obs, act, rew, cont, idx, hidden, parts=None, mark
     # encoder convs: the one autograd graph that is closed later with d(loss)/d(features)
     conv_dtype = wm.__dict__.get("conv_grad_dtype", torch.bfloat16)     # the reference trains these convs under fp16 autocast
     with torch.autocast("cuda", dtype=conv_dtype, enabled=conv_dtype != torch.float32):
-        feats = wm.encoder.feature_extractor(obs.reshape(B * T, *obs.shape[2:]).contiguous(memory_format=torch.channels_last))
+        feats = _conv_stack(wm.encoder.feature_extractor, obs.reshape(B * T, *obs.shape[2:]).contiguous(memory_format=torch.channels_last))
     feats = feats.float().flatten(1)                                                               # (B*T, n_feat)
     with torch.no_grad():
         X1 = torch.cat([feats.detach().view(B, T, n_feat).transpose(0, 1), H_tm], -1).contiguous()   # (T,B,n_feat+D)

@@ -20,6 +20,21 @@ namespace drm {
   } while (0)
 
 template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl2(void (*kernel)(KArgs...), dim3 grid, unsigned block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -343,6 +358,41 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 #pragma unroll
     for (int k = 1; k < 8; ++k) t += part[k][lane];
     out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+// First stage of the column sums of a bf16 matrix (the conv layers' bias gradients: grad_output as [N * H * W, C] channels-last rows):
+// one block per 64 columns x 64 rows, lane = two columns (one 4-byte load), 8 rows per warp all in flight, fp32 partial sums to
+// out [gridDim.y][n].
+__global__ void __launch_bounds__(256) colsum_bf16_stage_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int n, int64_t ld,
+                                                                float* __restrict__ out) {
+  PDL_ENTRY();
+  __shared__ float part[8][65];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = (int)blockIdx.x * 64 + 2 * lane;
+  const int64_t r0 = (int64_t)blockIdx.y * 64 + w * 8;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < n) {
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = make_float2(0.f, 0.f);
+      if (r0 + i < rows) v[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (r0 + i) * ld + c));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0 += v[i].x; a1 += v[i].y; }
+  }
+  part[w][2 * lane] = a0;
+  part[w][2 * lane + 1] = a1;
+  __syncthreads();
+  if (w < 2) {
+    const int cc = (int)blockIdx.x * 64 + w * 32 + lane;
+    if (cc < n) {
+      float t = part[0][w * 32 + lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += part[k][w * 32 + lane];
+      out[(int64_t)blockIdx.y * n + cc] = t;
+    }
   }
 }
 
@@ -813,6 +863,31 @@ extern "C" int drm_ln_silu_bwd_affine(const float* dy, const float* a, const flo
 extern "C" int drm_ln_silu_bwd(const float* dy, const float* a, const float* gamma, const float* beta, float* da, float* dln,
                                int64_t rows, int32_t n, float eps, void* stream) {
   return drm_ln_silu_bwd_affine(dy, a, gamma, beta, da, dln, nullptr, rows, n, eps, stream);
+}
+
+extern "C" int drm_colsum(const float* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
+
+extern "C" int64_t drm_colsum_bf16_scratch_bytes(int64_t rows, int32_t n) {
+  return rows >= 1 && n >= 1 ? ((rows + 63) / 64 + 64) * (int64_t)n * (int64_t)sizeof(float) : 0;
+}
+
+// bf16 input (n even, x 4-byte aligned, ld even): 64-row chunks to fp32 partials, then drm_colsum over the partials
+extern "C" int drm_colsum_bf16(const void* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(rows >= 1 && n >= 2 && (n & 1) == 0 && ld >= n && (ld & 1) == 0 && ((uintptr_t)x & 3u) == 0, DRM_ERR_SHAPE,
+              "drm_colsum_bf16: n and ld must be even, x 4-byte aligned");
+  DRM_REQUIRE(x && out && scratch, DRM_ERR_ARG, "drm_colsum_bf16: NULL pointer");
+  const int64_t chunks = (rows + 63) / 64;
+  DRM_REQUIRE(chunks <= 0x7fffffff / 1 && chunks <= 65535LL * 1024, DRM_ERR_SHAPE, "drm_colsum_bf16: too many rows");
+  float* part = static_cast<float*>(scratch);
+  // (grid y is limited to 65535: fold longer chunk lists into several launches)
+  for (int64_t y0 = 0; y0 < chunks; y0 += 65535) {
+    const int64_t ny = chunks - y0 < 65535 ? chunks - y0 : 65535;
+    DRM_CUDA(launch_pdl2(colsum_bf16_stage_kernel, dim3((unsigned)((n + 63) / 64), (unsigned)ny), 256, (cudaStream_t)stream,
+                         static_cast<const __nv_bfloat16*>(x) + y0 * 64 * ld, rows - y0 * 64, (int)n, ld, part + y0 * n));
+    DRM_LAUNCH_CHECK();
+  }
+  return drm_colsum(part, chunks, n, n, out, accumulate, part + chunks * n, stream);
 }
 
 extern "C" int64_t drm_colsum_scratch_bytes(int64_t rows, int32_t n) {

@@ -98,9 +98,11 @@ def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, o
 
 
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """out [n] (+)= x [rows, n].sum(0) (x may be a column slice of a wider matrix); deterministic."""
+    """out [n] (+)= x [rows, n].sum(0) (x may be a column slice of a wider matrix; fp32, or bf16 with even n / pitch); deterministic."""
     L.require_cuda(x, "x")
-    if x.dtype != torch.float32 or x.dim() != 2 or (x.stride(1) != 1 and x.shape[1] != 1):
+    bf16 = x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 2 == 0 and x.stride(0) % 2 == 0 \
+        and x.data_ptr() % 4 == 0 and x.shape[0] >= 1
+    if not bf16 and (x.dtype != torch.float32 or x.dim() != 2 or (x.stride(1) != 1 and x.shape[1] != 1)):
         x = L.f32c(x.reshape(-1, x.shape[-1]))
     rows, n = x.shape
     if out is None:
@@ -110,6 +112,12 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     elif out.dtype != torch.float32 or out.numel() != n or not out.is_contiguous():
         raise RuntimeError("dreamer_b200.colsum: `out` must be a contiguous fp32 tensor of n elements")
     lib = L.load()
+    if bf16:
+        nscr = lib.drm_colsum_bf16_scratch_bytes(rows, n)
+        scratch = torch.empty(nscr, dtype=torch.uint8, device=x.device)
+        L.check(lib.drm_colsum_bf16(L.ptr(x), rows, n, x.stride(0) if rows > 1 else n, L.ptr(out), 1 if accumulate else 0, L.ptr(scratch),
+                                    L.stream()), "colsum_bf16")
+        return out
     nscr = lib.drm_colsum_scratch_bytes(rows, n)
     scratch = torch.empty(nscr, dtype=torch.uint8, device=x.device) if nscr else None
     L.check(lib.drm_colsum(L.ptr(x), rows, n, x.stride(0) if rows > 1 else n, L.ptr(out), 1 if accumulate else 0, L.ptr(scratch), L.stream()),

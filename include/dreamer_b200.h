@@ -122,6 +122,10 @@ int drm_ln_silu_bwd_affine(const float* dy, const float* a, const float* gamma, 
 /* two stages).                                                                                                              */
 int64_t drm_colsum_scratch_bytes(int64_t rows, int32_t n);
 int drm_colsum(const float* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
+/* The same for a bf16 matrix (n, ld even; x 4-byte aligned): the conv layers' bias gradients from grad_output viewed as              */
+/* [N * H * W, C] channels-last rows (autograd's conv-bias reduction).  scratch: drm_colsum_bf16_scratch_bytes(rows, n) bytes.          */
+int64_t drm_colsum_bf16_scratch_bytes(int64_t rows, int32_t n);
+int drm_colsum_bf16(const void* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
 /* Backward of one nn.GRUCell step (SequenceModel.py:13,19-24) from its pre-activations gi = x W_ih^T + b_ih,                */
 /* gh = h W_hh^T + b_hh [rows, 3D] (gate order r, u, n), h_prev [rows, D] (NULL = zeros) and dh [rows, D]:                    */
 /*   dgi = [dr, du, dn], dgh = [dr, du, dn * r] (pre-activation gradients), dh_prev (=, or += when accumulate) dh * u.        */

@@ -290,6 +290,17 @@ def test_colsum_and_ln_affine_outputs():
         ops.colsum(x, out=acc, accumulate=True)
         assert torch.allclose(acc.double(), ref + 3.0, rtol=1e-5, atol=1e-6 * rows + 1e-4)
         assert torch.equal(ops.colsum(x), got)                                # deterministic
+    # bf16 rows (conv bias gradients: grad_output viewed as [N * H * W, C]), incl. a channels-last view and a long matrix
+    for rows, n in ((1, 16), (65, 32), (5000, 64), (300000, 24)):
+        xb = torch.randn(rows, n, device=DEV, generator=g).to(torch.bfloat16)
+        ref = xb.double().sum(0)
+        got = ops.colsum(xb)
+        assert torch.allclose(got.double(), ref, rtol=1e-5, atol=2e-6 * rows + 1e-4), (rows, n)
+        assert torch.equal(ops.colsum(xb), got)
+    g4 = torch.randn(6, 32, 5, 7, device=DEV, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    rows_view = g4.permute(0, 2, 3, 1).reshape(-1, 32)
+    assert rows_view.data_ptr() == g4.data_ptr()
+    assert torch.allclose(ops.colsum(rows_view).double(), g4.double().sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-3)
     rows, n = 300, 200
     a = torch.randn(rows, n, device=DEV, generator=g) * 2
     dy = torch.randn(rows, n, device=DEV, generator=g)
