@@ -6,10 +6,16 @@ is a function of (h_t, z_t, obs_t) at one time step.  A torch autograd graph ove
 step (3 850 per step at batch 16 x sequence 64) on 16-row tensors.  Here instead:
 
   1. everything non-recurrent is evaluated ONCE, batched over all B*T rows, on the teacher-forced trajectory the scan kernels
-     produced (hidden states and sampled classes); autograd handles that batched graph (decoder / encoder convs, heads);
+     produced (hidden states and sampled classes): prior MLP, reward / continue heads, decoder MLP and the KL terms are re-evaluated
+     and differentiated by hand on this library's kernels (_heads_manual: drm_gemm_tf32, drm_twohot_ce_bwd, drm_ln_silu_bwd,
+     drm_colsum); only the two conv stacks remain a torch autograd graph (cuDNN), closed from / into the hand-written part;
   2. the recurrence is walked backwards with 7 launches per step: the straight-through backward (drm_categorical32_bwd), the
-     posterior MLP's input gradient (2 library GEMMs + drm_ln_silu_bwd), the GRU cell backward (drm_gru_bwd) and 2 library GEMMs;
-  3. every weight gradient is a batched GEMM over all B*T rows after the walk.
+     posterior MLP's input gradient (2 x drm_gemm_tf32 + drm_ln_silu_bwd), the GRU cell backward (drm_gru_bwd) and 2 x drm_gemm_tf32
+     (skinny: gradient rows rounded in-kernel, K split over a cluster), chained by programmatic dependent launches;
+  3. every weight gradient is a batched drm_gemm_tf32 over all B*T rows after the walk, every bias / LayerNorm-affine gradient a
+     drm_colsum.
+
+The same pieces give Agent.train_step its gradients: actor_backward (through the imagined states) and critic_backward.
 
 Gradients are accumulated into the parameters' ``.grad`` (the flat bucket of optim.FlatAdamW).  The autograd tail
 (learners._tail_world_model) stays as the reference this is tested against (tests/test_gpu_bptt.py).

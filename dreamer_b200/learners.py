@@ -2,8 +2,9 @@
 
 Forward quantities (states, logits, log-likelihoods, returns, losses) come from the sm_100a kernels.
 The world model's gradient comes from bptt.world_model_backward: a hand-scheduled back-propagation through time on the
-trajectory the scan kernels produced (batched non-recurrent graph, 7 launches per time step for the recurrence, batched
-weight-gradient GEMMs).  ``_tail_world_model`` below -- a torch autograd graph over the Python scan, teacher-forced on the
+trajectory the scan kernels produced (batched heads / decoder MLP / KL part differentiated by hand, 7 launches per time step for the
+recurrence, batched weight-gradient GEMMs -- all on the library's drm_gemm_tf32 and elementwise backward kernels; the conv stacks'
+backward is torch autograd); the Agent's from bptt.actor_backward / bptt.critic_backward.  ``_tail_world_model`` below -- a torch autograd graph over the Python scan, teacher-forced on the
 sampled classes -- is the reference implementation of that gradient (``grad_mode = "autograd"``) and the Agent's tail.  Clipping, AdamW, the target-critic EMA and gradient zeroing run as the fused
 flat-bucket kernels of optim.FlatAdamW (section 8f rank 2).
 """
