@@ -100,6 +100,16 @@ class HostRolloutQueue:
         self.out_done = [None] * self.depth
         self.count = 0
 
+    def _graph_inputs(self):
+        """(z, uniforms, normals) to fill for the next call: the captured graph's static inputs when it exists, else own buffers"""
+        g = self.ro.__dict__.get("_graphs", {}).get(False)
+        if g is not None:
+            for ent in g.cache.values():
+                st = ent.get("static")
+                if st is not None and st[0].shape == self.z.shape and st[2].shape == self.u.shape and st[3].shape == self.n.shape:
+                    return st[0], st[2], st[3]
+        return self.z, self.u, self.n
+
     def submit(self, z0_idx: torch.Tensor, h0: torch.Tensor) -> int:
         """z0_idx (B, R) uint8 classes of the one-hot start latent, h0 (B, 1, D) / (B, D) fp32 -- pinned host tensors."""
         k = self.count % self.depth
@@ -111,10 +121,13 @@ class HostRolloutQueue:
             self.h[k].copy_(h0.reshape(self.h[k].shape), non_blocking=True)
             self.in_done[k].record(self.copy_stream)
         main.wait_event(self.in_done[k])
-        ops.onehot32(self.zi[k], self.z)
-        self.u.uniform_(generator=self.generator)
-        self.n.normal_(generator=self.generator)
-        out = self.ro.run_graphed(self.z, self.h[k], self.u, self.n, want_idx=False)
+        # once the rollout graph exists, the one-hot start latent and the draws are written straight into ITS static input buffers
+        # (run_graphed then has nothing to copy but h0): three device-to-device copies (6 MB) less per call
+        z_t, u_t, n_t = self._graph_inputs()
+        ops.onehot32(self.zi[k], z_t)
+        u_t.uniform_(generator=self.generator)
+        n_t.normal_(generator=self.generator)
+        out = self.ro.run_graphed(z_t, self.h[k], u_t, n_t, want_idx=False)
         self.read_done[k] = torch.cuda.Event()
         self.read_done[k].record(main)
         if self.host[k] is None:
