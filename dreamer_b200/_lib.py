@@ -78,6 +78,7 @@ SIGNATURES = {
     "drm_tanh_normal_logp": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, c_stream]),
     "drm_percentile_pair": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, c_stream]),
     "drm_ln_silu_bwd_affine": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, C.c_float, c_stream]),
+    "drm_convt_image_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 5 + [c_stream]),
     "drm_colsum_bf16_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "drm_colsum_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, c_stream]),
     "drm_colsum_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),

@@ -138,6 +138,34 @@ def _conv_bias_hook(bias, g):
     return None
 
 
+class _ImageLayer(torch.autograd.Function):
+    """y = tanh(ConvTranspose2d(k 4, s 2, p 1)(x) + b) to <= 3 image channels, forward on this library's direct kernel
+    (drm_convt_image_fwd: ~30 us at 1024 frames, the library conv ~340 us -- with 3 output channels a GEMM formulation is all
+    overhead); backward: tanh' from the saved output, then the library's convolution_backward for d/dx, d/dweight (cuDNN, as before)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = ops.convt_image_fwd(x, weight, bias)
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        da = (dy * (1.0 - y * y)).to(x.dtype).contiguous(memory_format=torch.channels_last)
+        dx, dw, _ = torch.ops.aten.convolution_backward(da, x, weight.to(x.dtype), None, [2, 2], [1, 1], [1, 1], True, [0, 0], 1,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        db = da.float().sum(dim=(0, 2, 3)) if ctx.needs_input_grad[2] else None
+        return dx, (dw.float() if dw is not None else None), db
+
+
+def _image_layer_ok(conv, nxt, x):
+    return (isinstance(conv, torch.nn.ConvTranspose2d) and isinstance(nxt, torch.nn.Tanh) and conv.out_channels <= 3
+            and conv.in_channels in (8, 16, 32, 64) and tuple(conv.kernel_size) == (4, 4) and tuple(conv.stride) == (2, 2)
+            and tuple(conv.padding) == (1, 1) and tuple(conv.output_padding) == (0, 0) and conv.groups == 1 and conv.bias is not None
+            and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last))
+
+
 def _conv_stack(seq, x):
     """Run a conv stack (nn.Sequential of Conv2d / ConvTranspose2d / SiLU) under autograd with the BIAS gradients taken out of the
     graph: each conv node is recorded while its bias does not require grad (the fused bias add of the forward stays), and a hook on
@@ -146,8 +174,16 @@ def _conv_stack(seq, x):
     if GEMM_BATCHED != "drm":
         return seq(x)
     toggled = []
+    mods = list(seq)
     try:
-        for m in seq:
+        for k, m in enumerate(mods):
+            if k > 0 and isinstance(m, torch.nn.Tanh) and getattr(mods[k - 1], "_drm_fused_tanh", False):
+                mods[k - 1]._drm_fused_tanh = False
+                continue                                                   # (applied inside _ImageLayer)
+            if k + 1 < len(mods) and _image_layer_ok(m, mods[k + 1], x):
+                x = _ImageLayer.apply(x, m.weight, m.bias)                  # the decoder's image layer + tanh: own forward kernel
+                m._drm_fused_tanh = True
+                continue
             hook = (isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) and m.bias is not None and m.bias.requires_grad
                     and m.out_channels % 2 == 0 and m.out_channels >= 16)
             if hook:

@@ -2,6 +2,7 @@
 // terms, the replay-ring gather/insert, the lambda-return scan, two-hot cross-entropy and the
 // bucket-value readout.  One warp per row everywhere (lane = class / bucket stripe), 16-byte
 // vector accesses where the layout allows, grids sized in multiples of the SM count.
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -392,6 +393,89 @@ __global__ void __launch_bounds__(256) colsum_bf16_stage_kernel(const __nv_bfloa
 #pragma unroll
       for (int k = 1; k < 8; ++k) t += part[k][w * 32 + lane];
       out[(int64_t)blockIdx.y * n + cc] = t;
+    }
+  }
+}
+
+// The decoder's image layer for the TRAINING graph: y = tanh(ConvTranspose2d(k 4, s 2, p 1)(x) + b) to <= 3 image channels
+// (VariationalAutoEncoder.py:134-137), straight from the module's fp32 weight [C_in][co][4][4] (rounded to bf16 on the way into shared
+// memory, as the bf16-autocast library conv rounds it).  With 3 output channels a GEMM formulation is all overhead and the library's
+// kernel for it takes ~340 us at 1024 frames; here one thread per INPUT pixel produces the 2 x 2 output pixels it is the centre of from
+// its 3 x 3 neighbourhood (16-byte NHWC vectors), weights as warp-wide float4 broadcasts from shared memory -- the scheme of vae.cuh's
+// convt_last_direct_kernel.   x: bf16 NHWC [N, Hin, Win, CP];  out: fp32 NCHW [N, co_n, 2 Hin, 2 Win].
+template <int CP>
+__global__ void __launch_bounds__(256) convt_image_fwd_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ W,
+                                                              const float* __restrict__ bias, float* __restrict__ out, long npix, int Hin,
+                                                              int Win, int co_n) {
+  __shared__ float4 w_s[16 * CP];
+  for (int i = threadIdx.x; i < 16 * CP; i += blockDim.x) {
+    const int ph = i / (4 * CP), r = i - ph * 4 * CP;
+    const int tap = r / CP, c = r - tap * CP;
+    const int py = ph >> 1, px = ph & 1, ty = tap >> 1, tx = tap & 1;
+    // output row 2 i + py takes input row i through ky = 1 (py = 0) / 2 (py = 1) [ty = 0] and input row i - 1 / i + 1 through ky = 3 / 0 [ty = 1]
+    const int ky = py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 2 : 0);
+    const int kx = px == 0 ? (tx == 0 ? 1 : 3) : (tx == 0 ? 2 : 0);
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < co_n && co < 3; ++co) w[co] = __bfloat162float(__float2bfloat16_rn(W[((long)(c * co_n + co) * 4 + ky) * 4 + kx]));
+    w_s[i] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const float b0 = co_n > 0 ? bias[0] : 0.f, b1 = co_n > 1 ? bias[1] : 0.f, b2 = co_n > 2 ? bias[2] : 0.f;
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(pix % Win);
+    const int i = (int)((pix / Win) % Hin);
+    const long f = pix / ((long)Win * Hin);
+    float acc[4][3];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) { acc[ph][0] = b0; acc[ph][1] = b1; acc[ph][2] = b2; }
+#pragma unroll
+    for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll
+      for (int dxi = 0; dxi < 3; ++dxi) {
+        const int dy = dyi - 1, dx = dxi - 1;
+        const int iy = i + dy, ix = j + dx;
+        const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+        const uint4* src = reinterpret_cast<const uint4*>(in + ((f * Hin + iy) * Win + ix) * CP);
+#pragma unroll
+        for (int c8 = 0; c8 < CP / 8; ++c8) {
+          uint4 raw = make_uint4(0, 0, 0, 0);
+          if (ok) raw = __ldg(src + c8);
+          float xv[8];
+          const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { xv[2 * e] = __uint_as_float(rw[e] << 16); xv[2 * e + 1] = __uint_as_float(rw[e] & 0xFFFF0000u); }
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            if (!(dy == 0 || (dy == -1 && py == 0) || (dy == 1 && py == 1))) continue;
+            const int ty = dy == 0 ? 0 : 1;
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+              if (!(dx == 0 || (dx == -1 && px == 0) || (dx == 1 && px == 1))) continue;
+              const int tx = dx == 0 ? 0 : 1;
+              const int ph = py * 2 + px;
+              const float4* wp = w_s + (ph * 4 + ty * 2 + tx) * CP + c8 * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 w = wp[e];
+                acc[ph][0] = fmaf(xv[e], w.x, acc[ph][0]);
+                acc[ph][1] = fmaf(xv[e], w.y, acc[ph][1]);
+                acc[ph][2] = fmaf(xv[e], w.z, acc[ph][2]);
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int co = 0; co < co_n; ++co) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        float* o = out + ((f * co_n + co) * Ho + 2 * i + py) * Wo + 2 * j;
+        float v0 = acc[py * 2][0], v1 = acc[py * 2 + 1][0];
+        if (co == 1) { v0 = acc[py * 2][1]; v1 = acc[py * 2 + 1][1]; }
+        if (co == 2) { v0 = acc[py * 2][2]; v1 = acc[py * 2 + 1][2]; }
+        *reinterpret_cast<float2*>(o) = make_float2(tanhf(v0), tanhf(v1));
+      }
     }
   }
 }
@@ -866,6 +950,25 @@ extern "C" int drm_ln_silu_bwd(const float* dy, const float* a, const float* gam
 }
 
 extern "C" int drm_colsum(const float* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
+
+extern "C" int drm_convt_image_fwd(const void* x_nhwc_bf16, const float* weight, const float* bias, float* out_nchw, int32_t N, int32_t Hin,
+                                   int32_t Win, int32_t C_in, int32_t C_out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  DRM_REQUIRE(N >= 1 && Hin >= 1 && Win >= 1 && C_out >= 1 && C_out <= 3, DRM_ERR_SHAPE, "drm_convt_image_fwd: 1 - 3 image channels");
+  DRM_REQUIRE(C_in == 8 || C_in == 16 || C_in == 32 || C_in == 64, DRM_ERR_SHAPE, "drm_convt_image_fwd: C_in must be 8, 16, 32 or 64");
+  DRM_REQUIRE(x_nhwc_bf16 && weight && bias && out_nchw, DRM_ERR_ARG, "drm_convt_image_fwd: NULL pointer");
+  DRM_REQUIRE(((uintptr_t)x_nhwc_bf16 & 15u) == 0 && ((uintptr_t)out_nchw & 7u) == 0, DRM_ERR_ALIGN, "drm_convt_image_fwd: alignment");
+  const long npix = (long)N * Hin * Win;
+  const int grid = (int)std::min<long>((npix + 255) / 256, 148L * 16);
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_nhwc_bf16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C_in == 8) convt_image_fwd_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, out_nchw, npix, Hin, Win, C_out);
+  else if (C_in == 16) convt_image_fwd_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, out_nchw, npix, Hin, Win, C_out);
+  else if (C_in == 32) convt_image_fwd_kernel<32><<<grid, 256, 0, st>>>(x, weight, bias, out_nchw, npix, Hin, Win, C_out);
+  else convt_image_fwd_kernel<64><<<grid, 256, 0, st>>>(x, weight, bias, out_nchw, npix, Hin, Win, C_out);
+  DRM_LAUNCH_CHECK();
+  return DRM_OK;
+}
 
 extern "C" int64_t drm_colsum_bf16_scratch_bytes(int64_t rows, int32_t n) {
   return rows >= 1 && n >= 1 ? ((rows + 63) / 64 + 64) * (int64_t)n * (int64_t)sizeof(float) : 0;

@@ -97,6 +97,22 @@ def ln_silu_bwd(dy, a, gamma, beta, eps: float = 1e-5, want_dln: bool = False, o
     return (da, dln) if want_dln else da
 
 
+def convt_image_fwd(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """tanh(conv_transpose2d(x, weight, bias, stride=2, padding=1)) for the decoder's image layer: x (N, C_in, H, W) bf16 in
+    channels-last memory, weight (C_in, C_out <= 3, 4, 4) fp32, bias (C_out) -> (N, C_out, 2H, 2W) fp32."""
+    L.require_cuda(x, "x")
+    if x.dtype != torch.bfloat16 or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("dreamer_b200.convt_image_fwd: x must be a bf16 channels-last (N, C, H, W) tensor")
+    N, Ci, H, W = x.shape
+    Co = weight.shape[1]
+    if tuple(weight.shape) != (Ci, Co, 4, 4) or bias.numel() != Co:
+        raise RuntimeError("dreamer_b200.convt_image_fwd: weight must be (C_in, C_out, 4, 4), bias (C_out)")
+    w, b = L.f32c(weight), L.f32c(bias)
+    out = torch.empty((N, Co, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    L.check(L.load().drm_convt_image_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(out), N, H, W, Ci, Co, L.stream()), "convt_image_fwd")
+    return out
+
+
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """out [n] (+)= x [rows, n].sum(0) (x may be a column slice of a wider matrix; fp32, or bf16 with even n / pitch); deterministic."""
     L.require_cuda(x, "x")

@@ -124,6 +124,12 @@ int64_t drm_colsum_scratch_bytes(int64_t rows, int32_t n);
 int drm_colsum(const float* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
 /* The same for a bf16 matrix (n, ld even; x 4-byte aligned): the conv layers' bias gradients from grad_output viewed as              */
 /* [N * H * W, C] channels-last rows (autograd's conv-bias reduction).  scratch: drm_colsum_bf16_scratch_bytes(rows, n) bytes.          */
+/* The decoder's image layer inside the TRAINING graph: out = tanh(conv_transpose2d(x, weight, bias, stride 2, padding 1)) for a 4 x 4     */
+/* kernel and 1 - 3 output channels (VariationalAutoEncoder.py:134-137; what the world-model step's autograd graph evaluates).          */
+/* x: bf16 NHWC [N, Hin, Win, C_in] (C_in = 8 / 16 / 32 / 64), weight fp32 [C_in][C_out][4][4] (the module's parameter, rounded to bf16   */
+/* in the kernel), bias fp32 [C_out] -> out fp32 NCHW [N, C_out, 2 Hin, 2 Win].                                                  */
+int drm_convt_image_fwd(const void* x_nhwc_bf16, const float* weight, const float* bias, float* out_nchw, int32_t N, int32_t Hin,
+                        int32_t Win, int32_t C_in, int32_t C_out, void* stream);
 int64_t drm_colsum_bf16_scratch_bytes(int64_t rows, int32_t n);
 int drm_colsum_bf16(const void* x, int64_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* scratch, void* stream);
 /* Backward of one nn.GRUCell step (SequenceModel.py:13,19-24) from its pre-activations gi = x W_ih^T + b_ih,                */

@@ -310,3 +310,28 @@ def test_colsum_and_ln_affine_outputs():
     assert torch.equal(da, da0) and torch.equal(dln, dln0)
     xhat = F.layer_norm(a, (n,), None, None, 1e-5)
     assert torch.allclose(dlnx, dln * xhat, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("Ci,Co,N,H", [(32, 3, 5, 32), (8, 3, 3, 8), (16, 1, 2, 5)])
+def test_image_layer_forward_and_backward_match_torch(Ci, Co, N, H):
+    """drm_convt_image_fwd (bptt._ImageLayer) against torch's conv_transpose2d + tanh on the same bf16-rounded operands"""
+    from dreamer_b200 import bptt, ops
+    g = torch.Generator(device="cuda").manual_seed(Ci + N)
+    x = (torch.randn(N, Ci, H, H + 1, device=DEV, generator=g)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(Ci, Co, 4, 4, device=DEV, generator=g) * 0.1
+    b = torch.randn(Co, device=DEV, generator=g) * 0.1
+    ref = torch.tanh(F.conv_transpose2d(x.float(), w.to(torch.bfloat16).float(), b, stride=2, padding=1))
+    got = ops.convt_image_fwd(x, w, b)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=1e-4, atol=2e-5), float((got - ref).abs().max())
+    # through the autograd function: gradients against torch autograd of the same expression
+    xr = x.float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    coef = torch.randn(ref.shape, device=DEV, generator=g)
+    (torch.tanh(F.conv_transpose2d(xr, wr, br, stride=2, padding=1)) * coef).sum().backward()
+    xl = x.clone().requires_grad_(True)
+    wl, bl = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    (bptt._ImageLayer.apply(xl, wl, bl) * coef).sum().backward()
+    for a_, r_ in ((xl.grad.float(), xr.grad), (wl.grad, wr.grad), (bl.grad, br.grad)):
+        scale = float(r_.abs().max()) + 1e-8
+        assert float((a_ - r_).abs().max()) / scale < 2e-2            # bf16 operands / bf16 gradient maps in the backward
