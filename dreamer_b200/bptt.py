@@ -176,13 +176,14 @@ def _conv_stack(seq, x):
     toggled = []
     mods = list(seq)
     try:
+        skip = False
         for k, m in enumerate(mods):
-            if k > 0 and isinstance(m, torch.nn.Tanh) and getattr(mods[k - 1], "_drm_fused_tanh", False):
-                mods[k - 1]._drm_fused_tanh = False
-                continue                                                   # (applied inside _ImageLayer)
+            if skip:                                                        # the Tanh that _ImageLayer applied
+                skip = False
+                continue
             if k + 1 < len(mods) and _image_layer_ok(m, mods[k + 1], x):
                 x = _ImageLayer.apply(x, m.weight, m.bias)                  # the decoder's image layer + tanh: own forward kernel
-                m._drm_fused_tanh = True
+                skip = True
                 continue
             hook = (isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) and m.bias is not None and m.bias.requires_grad
                     and m.out_channels % 2 == 0 and m.out_channels >= 16)
