@@ -106,7 +106,7 @@ int drm_categorical32_st(const float* logits, const uint8_t* idx, float* z_st, f
 int drm_categorical32_bwd(const float* logits, const float* dz, const float* dz2, const float* dl_add, float* dlogits,
                           int64_t n_rows, void* stream);
 
-/* ---- elementwise pieces of the hand-scheduled BPTT (the GEMMs between them are library GEMMs) ------- */
+/* ---- elementwise pieces of the hand-scheduled BPTT (the GEMMs between them: drm_gemm_tf32 below) ---- */
 /* Backward of y = SiLU(LayerNorm(a) * gamma + beta) (the Linear-LN-SiLU blocks of every MLP, e.g.                           */
 /* VariationalAutoEncoder.py:48-52): dy, a [rows, n] (n <= 1024) -> da [rows, n]; dln (optional) = dy * silu'(ln) for the     */
 /* batched dgamma = sum(dln * xhat), dbeta = sum(dln).  Statistics are recomputed from a (eps as in the forward, 1e-5).       */
